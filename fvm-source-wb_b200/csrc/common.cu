@@ -1,0 +1,196 @@
+// Error plumbing, device selection and the dlopen'ed NCCL shim shared by all solvers.
+#include "common.cuh"
+#include <dlfcn.h>
+#include <nccl.h>   // types/enums only; the symbols are resolved at run time with dlsym
+#include <mutex>
+
+namespace wb {
+
+static thread_local char t_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+int select_device(int device_ordinal, int* chosen) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    (void)cudaGetLastError();
+    return WB_ERR_CUDA;
+  }
+  int dev = device_ordinal;
+  if (dev < 0) WB_CUDA(cudaGetDevice(&dev));
+  WB_REQUIRE(dev < n, "device ordinal %d out of range (%d devices)", dev, n);
+  cudaDeviceProp prop;
+  WB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev, prop.name,
+              prop.major, prop.minor);
+    return WB_ERR_CUDA;
+  }
+  WB_CUDA(cudaSetDevice(dev));
+  if (chosen) *chosen = dev;
+  return WB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL
+struct NcclApi {
+  void* dl = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+static bool g_nccl_ok = false;
+
+static void nccl_load() {
+  // If the host program (e.g. torch) already mapped a libnccl.so.2 this returns that instance.
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.dl = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+    if (g_nccl.dl) break;
+  }
+  if (!g_nccl.dl) return;
+#define WB_SYM(field, name)                                              \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.dl, name);                     \
+  if (!g_nccl.field) return;
+  WB_SYM(GetUniqueId, "ncclGetUniqueId")
+  WB_SYM(CommInitRank, "ncclCommInitRank")
+  WB_SYM(CommDestroy, "ncclCommDestroy")
+  WB_SYM(GroupStart, "ncclGroupStart")
+  WB_SYM(GroupEnd, "ncclGroupEnd")
+  WB_SYM(Send, "ncclSend")
+  WB_SYM(Recv, "ncclRecv")
+  WB_SYM(AllReduce, "ncclAllReduce")
+  WB_SYM(Broadcast, "ncclBroadcast")
+  WB_SYM(GetErrorString, "ncclGetErrorString")
+#undef WB_SYM
+  g_nccl_ok = true;
+}
+
+static int nccl_ready() {
+  std::call_once(g_nccl_once, nccl_load);
+  if (!g_nccl_ok) {
+    set_error("libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbol");
+    return WB_ERR_NCCL;
+  }
+  return WB_OK;
+}
+
+#define WB_NCCL(expr)                                                                       \
+  do {                                                                                      \
+    ncclResult_t _r = (expr);                                                               \
+    if (_r != ncclSuccess) {                                                                \
+      set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r));  \
+      return WB_ERR_NCCL;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+struct Nccl {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+int nccl_get_unique_id(void* id128) {
+  WB_CHECK(nccl_ready());
+  static_assert(sizeof(ncclUniqueId) == WB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  WB_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return WB_OK;
+}
+
+int nccl_comm_create(Nccl** c, const void* id128, int rank, int nranks) {
+  WB_CHECK(nccl_ready());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  Nccl* n = new Nccl;
+  n->rank = rank;
+  n->nranks = nranks;
+  ncclResult_t r = g_nccl.CommInitRank(&n->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    delete n;
+    return WB_ERR_NCCL;
+  }
+  *c = n;
+  return WB_OK;
+}
+
+void nccl_comm_destroy(Nccl* c) {
+  if (!c) return;
+  if (c->comm && g_nccl_ok) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* lo, int nlo,
+                             const HaloSeg* hi, int nhi, cudaStream_t s) {
+  WB_NCCL(g_nccl.GroupStart());
+  if (lo_peer >= 0)
+    for (int k = 0; k < nlo; ++k) {
+      WB_NCCL(g_nccl.Send(lo[k].send, lo[k].count, ncclDouble, lo_peer, c->comm, s));
+      WB_NCCL(g_nccl.Recv(lo[k].recv, lo[k].count, ncclDouble, lo_peer, c->comm, s));
+    }
+  if (hi_peer >= 0)
+    for (int k = 0; k < nhi; ++k) {
+      WB_NCCL(g_nccl.Send(hi[k].send, hi[k].count, ncclDouble, hi_peer, c->comm, s));
+      WB_NCCL(g_nccl.Recv(hi[k].recv, hi[k].count, ncclDouble, hi_peer, c->comm, s));
+    }
+  WB_NCCL(g_nccl.GroupEnd());
+  return WB_OK;
+}
+
+int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, double* recv_lo,
+                       const double* send_hi, double* recv_hi, size_t count, cudaStream_t s) {
+  HaloSeg lo{send_lo, recv_lo, count}, hi{send_hi, recv_hi, count};
+  int lo_peer = (rank > 0 && send_lo) ? rank - 1 : -1;
+  int hi_peer = (rank < nranks - 1 && send_hi) ? rank + 1 : -1;
+  return nccl_halo_exchange_multi(c, lo_peer, hi_peer, &lo, 1, &hi, 1, s);
+}
+
+int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s) {
+  WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint64, ncclMax, c->comm, s));
+  return WB_OK;
+}
+int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s) {
+  WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclMin, c->comm, s));
+  return WB_OK;
+}
+int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s) {
+  WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclMax, c->comm, s));
+  return WB_OK;
+}
+int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s) {
+  WB_NCCL(g_nccl.Broadcast(buf, buf, count, ncclDouble, root, c->comm, s));
+  return WB_OK;
+}
+
+}  // namespace wb
+
+extern "C" {
+const char* wb_last_error(void) { return wb::t_err; }
+const char* wb_version(void) { return "wbeuler-b200 0.1 (sm_100a, FP64)"; }
+long long wb_kernel_launch_count(void) { return wb::g_launches.load(); }
+int wb_nccl_get_unique_id(void* id128) {
+  if (!id128) { wb::set_error("null id buffer"); return WB_ERR_ARG; }
+  return wb::nccl_get_unique_id(id128);
+}
+}

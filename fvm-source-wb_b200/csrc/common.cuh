@@ -1,0 +1,80 @@
+// Shared host/device helpers for the wbeuler C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include "../../include/wbeuler.h"
+
+namespace wb {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define WB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      wb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                    cudaGetErrorString(_e));                                               \
+      return WB_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define WB_CHECK(expr)                  \
+  do {                                  \
+    int _s = (expr);                    \
+    if (_s != WB_OK) return _s;         \
+  } while (0)
+
+#define WB_REQUIRE(cond, ...)           \
+  do {                                  \
+    if (!(cond)) {                      \
+      wb::set_error(__VA_ARGS__);       \
+      return WB_ERR_ARG;                \
+    }                                   \
+  } while (0)
+
+#define WB_LAUNCH_CHECK()               \
+  do {                                  \
+    wb::g_launches.fetch_add(1);        \
+    WB_CUDA(cudaGetLastError());        \
+  } while (0)
+
+// Selects the device and verifies it is a Blackwell sm_100 part.  No CPU fallback exists.
+int select_device(int device_ordinal, int* chosen);
+
+// ---------------------------------------------------------------- NCCL (dlopen'ed, no link dependency)
+struct Nccl;                       // opaque communicator wrapper
+int nccl_get_unique_id(void* id128);
+int nccl_comm_create(Nccl** c, const void* id128, int rank, int nranks);
+void nccl_comm_destroy(Nccl* c);
+// grouped exchange of ghost rows with the slab neighbours: send `count` doubles from send_lo to
+// rank-1 / send_hi to rank+1 and receive into recv_lo / recv_hi (null pointers skip a side)
+int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, double* recv_lo,
+                       const double* send_hi, double* recv_hi, size_t count, cudaStream_t s);
+// generalised: lists of (ptr,count) segments per side, all inside one ncclGroup
+struct HaloSeg { const double* send; double* recv; size_t count; };
+int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* lo, int nlo,
+                             const HaloSeg* hi, int nhi, cudaStream_t s);
+int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s);
+int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
+int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
+int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s);
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+// max-reduction of non-negative doubles through their (order-preserving) bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+}  // namespace wb

@@ -1,0 +1,915 @@
+// 2D well-balanced finite-volume RK-stage kernels + C-ABI (replaces benchmark_2d.f90:221-279,370-618).
+//
+// Device layout: structure-of-arrays planes  plane_v[(r)*pitch + i],  v = rho, mx, my, E,
+// i contiguous (x), r = local row + 1 (row 0 and row nyl+1 are the slab ghost rows).
+//
+// Kernels
+//   k_stage_ref<MODE,WB>   reference operation order (arith = 1, parity entry points)
+//   k_stage_fast<MODE>     fused RK-stage kernel: delta tile + halo staged in shared memory, each face
+//                          flux computed once, well-balanced source, RK axpy, and (stage 2) the
+//                          warp-shuffle max reduction for the next CFL time step.
+//   MODE 0: out = dudt      MODE 1: out = in + dt*dudt      MODE 2: out = .5*base + .5*in + .5*dt*dudt
+#include "common.cuh"
+#include "fv2d_math.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace wb { namespace fv2d {
+
+struct Ctrl {
+  unsigned long long cmax_bits[2];  // max wave speed (bit pattern of a non-negative double), per step parity
+  double t[2];
+  int iter[2];
+  double dt_last, cmax_last;
+  int nonzero_vel;                  // set when the supplied w_eq has a non-zero velocity somewhere
+};
+
+struct Grid {
+  int nx, ny;        // global
+  int j0, nyl;       // first global row of this slab, local row count
+  int pitch;         // doubles per row
+  size_t plane;      // doubles per plane ((nyl+2)*pitch)
+};
+
+struct StageArgs {
+  const double* in;     // state whose RHS is evaluated (4 planes)
+  const double* base;   // MODE 2: u^n (4 planes)
+  double* out;          // 4 planes
+  const double* weq;    // ref kernels: supplied primitive equilibrium at centres (4 planes)
+  const double* eqz;    // fast kernels: (rho_e, E_e) planes
+  const double* exf; const double* exc; const double* eyf; const double* eyc;  // separable exp tables
+  Ctrl* ctrl;
+  int parity;
+  double tend;
+  int max_iter;
+  int row_begin, row_end;   // local rows [row_begin,row_end) covered by this launch
+};
+
+// ------------------------------------------------------------------------------------ layout kernels
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, Grid g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  if (i >= g.nx) return;
+  const double2* src = reinterpret_cast<const double2*>(aos + ((size_t)j * g.nx + i) * 4);
+  double2 a = src[0], b = src[1];
+  size_t o = (size_t)(j + 1) * g.pitch + i;
+  soa[o] = a.x;
+  soa[g.plane + o] = a.y;
+  soa[2 * g.plane + o] = b.x;
+  soa[3 * g.plane + o] = b.y;
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, Grid g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  if (i >= g.nx) return;
+  size_t o = (size_t)(j + 1) * g.pitch + i;
+  double2 a = make_double2(soa[o], soa[g.plane + o]);
+  double2 b = make_double2(soa[2 * g.plane + o], soa[3 * g.plane + o]);
+  double2* dst = reinterpret_cast<double2*>(aos + ((size_t)j * g.nx + i) * 4);
+  dst[0] = a;
+  dst[1] = b;
+}
+
+// (rho_e, E_e) planes from the supplied primitive equilibrium, all rows incl. ghosts
+// (compute_conservative, benchmark_2d.f90:159-171, :496); flags non-zero equilibrium velocity.
+__global__ void k_prepare_eq(const double* __restrict__ weq, double* __restrict__ eqz, Grid g, Phys P,
+                             Ctrl* ctrl) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (i >= g.nx) return;
+  size_t o = (size_t)r * g.pitch + i;
+  double w[4] = {weq[o], weq[g.plane + o], weq[2 * g.plane + o], weq[3 * g.plane + o]};
+  double u[4];
+  ref::cons(P, w, u);
+  eqz[o] = u[0];
+  eqz[g.plane + o] = u[3];
+  int jg = g.j0 + r - 1;
+  if ((w[1] != 0.0 || w[2] != 0.0) && jg >= 0 && jg < g.ny) atomicOr(&ctrl->nonzero_vel, 1);
+}
+
+// ------------------------------------------------------------------------------------ IC on device
+// get_initial_conditions (benchmark_2d.f90:45-113) and the centre equilibrium (:174-218) for rows
+// r = 0..nyl+1 that exist globally.
+__global__ void k_init(double* __restrict__ u, double* __restrict__ weq, Grid g, Phys P, int ninit,
+                       double eta, int fill_u, int fill_weq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (i >= g.nx) return;
+  int jg = g.j0 + r - 1;
+  size_t o = (size_t)r * g.pitch + i;
+  if (jg < 0 || jg >= g.ny) {
+    if (fill_u) { u[o] = 1.0; u[g.plane + o] = 0.0; u[2 * g.plane + o] = 0.0; u[3 * g.plane + o] = 1.0; }
+    if (fill_weq) { weq[o] = 1.0; weq[g.plane + o] = 0.0; weq[2 * g.plane + o] = 0.0; weq[3 * g.plane + o] = 1.0; }
+    return;
+  }
+  double x = x_cent(i, P.dx), y = x_cent(jg, P.dy);
+  if (fill_weq) {
+    double rho, p;
+    ref::eq_prim(P, x, y, rho, p);
+    weq[o] = rho; weq[g.plane + o] = 0.0; weq[2 * g.plane + o] = 0.0; weq[3 * g.plane + o] = p;
+  }
+  if (fill_u) {
+    double w[4];
+    const double rho_0 = (double)1.21f;
+    if (ninit == 1) {
+      double e = exp(-(x + y));
+      w[0] = e; w[1] = 0; w[2] = 0; w[3] = e;
+    } else if (ninit == 2 || ninit == 3) {
+      double e = exp(-(rho_0 * 1.0 / 1.0) * (x + y));
+      w[0] = rho_0 * e; w[1] = 0; w[2] = 0; w[3] = 1.0 * e;
+      if (ninit == 3) {
+        double ddx = x - (double)0.3f, ddy = y - (double)0.3f;
+        w[3] = w[3] + eta * exp(-(100.0 * (rho_0 * 1.0 / 1.0) * (ddx * ddx + ddy * ddy)));
+      }
+    } else {
+      if (x >= 0.5 && y >= 0.5)      { w[0] = 1.5; w[1] = 0.; w[2] = 0.; w[3] = 1.5; }
+      else if (x < 0.5 && y >= 0.5)  { w[0] = (double)0.5323f; w[1] = (double)1.206f; w[2] = 0.; w[3] = (double)0.3f; }
+      else if (x < 0.5 && y < 0.5)   { w[0] = (double)0.138f; w[1] = (double)1.206f; w[2] = (double)1.206f; w[3] = (double)0.029f; }
+      else                           { w[0] = (double)0.5323f; w[1] = 0.; w[2] = (double)1.206f; w[3] = (double)0.3f; }
+    }
+    double c[4];
+    ref::cons(P, w, c);
+    u[o] = c[0]; u[g.plane + o] = c[1]; u[2 * g.plane + o] = c[2]; u[3 * g.plane + o] = c[3];
+  }
+}
+
+// ------------------------------------------------------------------------------------ max speed
+// compute_max_speed (benchmark_2d.f90:264-279): max over all cells (boundary included) of
+// sqrt(vx^2+vy^2) + sqrt(gamma*max(p,1d-10)/max(rho,1d-10)); warp-shuffle + one atomicMax per block.
+template <bool FAST>
+__global__ void k_max_speed(const double* __restrict__ u, Grid g, Phys P, unsigned long long* out) {
+  double m = 0.0;
+  for (int r = blockIdx.y + 1; r <= g.nyl; r += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nx; i += gridDim.x * blockDim.x) {
+      size_t o = (size_t)r * g.pitch + i;
+      double s;
+      if (FAST) {
+        s = fast::speed(P, u[o], u[g.plane + o], u[2 * g.plane + o], u[3 * g.plane + o]);
+      } else {
+        double uu[4] = {u[o], u[g.plane + o], u[2 * g.plane + o], u[3 * g.plane + o]};
+        s = ref::speed(P, uu);
+      }
+      m = fmax(m, s);
+    }
+  m = warp_max(m);
+  __shared__ double sm[32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm[w] = m;
+  __syncthreads();
+  if (w == 0) {
+    m = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+    m = warp_max(m);
+    if (lane == 0) atomic_max_nonneg(out, m);
+  }
+}
+
+__global__ void k_ctrl_reset(Ctrl* c) {
+  c->cmax_bits[0] = 0ull; c->cmax_bits[1] = 0ull;
+  c->t[0] = 0.0; c->t[1] = 0.0;
+  c->iter[0] = 0; c->iter[1] = 0;
+  c->dt_last = 0.0; c->cmax_last = 0.0;
+}
+
+__device__ __forceinline__ bool step_done(const Ctrl* c, int parity, double tend, int max_iter) {
+  double t = c->t[parity];
+  int it = c->iter[parity];
+  return !(t < tend) || (max_iter >= 0 && it >= max_iter);
+}
+// dt = 0.5*dx/cmax*cfl   (benchmark_2d.f90:242)
+__device__ __forceinline__ double step_dt(const Ctrl* c, int parity, const Phys& P) {
+  double cmax = __longlong_as_double((long long)c->cmax_bits[parity]);
+  return 0.5 * P.dx / cmax * P.cfl;
+}
+// a finished run (t >= tend) turns the remaining enqueued steps into no-ops; the stage-2 launch
+// carries the bookkeeping slot forward so that the next parity sees the same (t, iter, cmax)
+__device__ __forceinline__ void carry_forward(Ctrl* c, int parity) {
+  c->t[parity ^ 1] = c->t[parity];
+  c->iter[parity ^ 1] = c->iter[parity];
+  c->cmax_bits[parity ^ 1] = c->cmax_bits[parity];
+}
+template <int MODE>
+__device__ __forceinline__ void bookkeeping(Ctrl* c, int parity, double dt) {
+  if (MODE == 1) c->cmax_bits[parity ^ 1] = 0ull;
+  if (MODE == 2) {
+    c->t[parity ^ 1] = c->t[parity] + dt;
+    c->iter[parity ^ 1] = c->iter[parity] + 1;
+    c->dt_last = dt;
+    c->cmax_last = __longlong_as_double((long long)c->cmax_bits[parity]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ reference-order stage
+// One thread per cell, every quantity recomputed from global memory exactly as
+// compute_update_exact does (benchmark_2d.f90:465-618); WB=false is the plain compute_update (:370-463).
+template <int MODE, bool WB>
+__global__ void __launch_bounds__(128) k_stage_ref(StageArgs A, Grid g, Phys P) {
+  double dt = 0.0;
+  if (MODE != 0) {
+    if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
+      if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+        carry_forward(A.ctrl, A.parity);
+      return;
+    }
+    dt = step_dt(A.ctrl, A.parity, P);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+      bookkeeping<MODE>(A.ctrl, A.parity, dt);
+  }
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int jl = A.row_begin + blockIdx.y;
+  double spd = 0.0;
+  if (i < g.nx && jl < A.row_end) {
+    int jg = g.j0 + jl;
+    size_t o = (size_t)(jl + 1) * g.pitch + i;
+    double uc[4] = {A.in[o], A.in[g.plane + o], A.in[2 * g.plane + o], A.in[3 * g.plane + o]};
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+    bool interior = (i > 0 && i < g.nx - 1 && jg > 0 && jg < g.ny - 1);
+    if (interior) {
+      // neighbours: left, right, bottom, top
+      const size_t on[4] = {o - 1, o + 1, o - g.pitch, o + g.pitch};
+      double dc[4], dn[4][4];
+      if (WB) {
+        double wq[4] = {A.weq[o], A.weq[g.plane + o], A.weq[2 * g.plane + o], A.weq[3 * g.plane + o]};
+        double ue[4];
+        ref::cons(P, wq, ue);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dc[v] = uc[v] - ue[v];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double wn[4] = {A.weq[on[k]], A.weq[g.plane + on[k]], A.weq[2 * g.plane + on[k]], A.weq[3 * g.plane + on[k]]};
+          double un[4];
+          ref::cons(P, wn, un);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dn[k][v] = A.in[v * g.plane + on[k]] - un[v];
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dc[v] = uc[v];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dn[k][v] = A.in[v * g.plane + on[k]];
+      }
+      // conservative equilibrium at the four faces of the cell
+      double UX[2][4], UY[2][4];
+      if (WB) {
+        double xc = x_cent(i, P.dx), yc = x_cent(jg, P.dy);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          double w[4] = {0, 0, 0, 0};
+          ref::eq_prim(P, x_face(i + k, P.dx), yc, w[0], w[3]);
+          ref::cons(P, w, UX[k]);
+          ref::eq_prim(P, xc, x_face(jg + k, P.dx) /* (j-1)*dx sic, :513 */, w[0], w[3]);
+          ref::cons(P, w, UY[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { UX[k][v] = 0.0; UY[k][v] = 0.0; }
+      }
+      double ul[4], ur[4], F0[4], F1[4], G0[4], G1[4];
+      // x-face i: left state u_right(i-1), right state u_left(i)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { ul[v] = WB ? UX[0][v] + dn[0][v] : dn[0][v]; ur[v] = WB ? UX[0][v] + dc[v] : dc[v]; }
+      ref::llf<0>(P, ul, ur, F0);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { ul[v] = WB ? UX[1][v] + dc[v] : dc[v]; ur[v] = WB ? UX[1][v] + dn[1][v] : dn[1][v]; }
+      ref::llf<0>(P, ul, ur, F1);
+      // y-face j: lower state u_top(j-1), upper state u_bottom(j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { ul[v] = WB ? UY[0][v] + dn[2][v] : dn[2][v]; ur[v] = WB ? UY[0][v] + dc[v] : dc[v]; }
+      ref::llf<1>(P, ul, ur, G0);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { ul[v] = WB ? UY[1][v] + dc[v] : dc[v]; ur[v] = WB ? UY[1][v] + dn[3][v] : dn[3][v]; }
+      ref::llf<1>(P, ul, ur, G1);
+      double w[4], s[4];
+      ref::prim(P, uc, w);
+      ref::source(w, s);
+      if (WB) {
+        double wq[4] = {A.weq[o], A.weq[g.plane + o], A.weq[2 * g.plane + o], A.weq[3 * g.plane + o]};
+        double se[4], Fe0[4], Fe1[4], Ge0[4], Ge1[4];
+        ref::source(wq, se);
+        ref::flux<0>(P, UX[0], Fe0);
+        ref::flux<0>(P, UX[1], Fe1);
+        ref::flux<1>(P, UY[0], Ge0);
+        ref::flux<1>(P, UY[1], Ge1);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          double r = -(F1[v] - F0[v]) * P.odx - (G1[v] - G0[v]) * P.ody;
+          r = r + s[v];
+          r = r - se[v];
+          r = r + (Fe1[v] - Fe0[v]) * P.odx;
+          r = r + (Ge1[v] - Ge0[v]) * P.ody;
+          d[v] = r;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) d[v] = -(F1[v] - F0[v]) * P.odx - (G1[v] - G0[v]) * P.ody + s[v];
+      }
+    }
+    double un[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (MODE == 0) un[v] = d[v];
+      if (MODE == 1) un[v] = uc[v] + dt * d[v];                                   // w1=u+dt*dudt  :247
+      if (MODE == 2) un[v] = 0.5 * A.base[v * g.plane + o] + 0.5 * uc[v] + 0.5 * dt * d[v];  // :250
+      A.out[v * g.plane + o] = un[v];
+    }
+    if (MODE == 2) spd = ref::speed(P, un);
+  }
+  if (MODE == 2) {
+    spd = warp_max(spd);
+    __shared__ double sm[4];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sm[w] = spd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = fmax(fmax(sm[0], sm[1]), fmax(sm[2], sm[3]));
+      atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ fused fast stage
+// Tile TX x TY cells per CTA, one thread per cell.
+//   phase 1  delta = u - u_eq of the tile and its 4 halo strips -> shared memory
+//   phase 2  every thread evaluates its LEFT and BOTTOM face (2 states each, LLF) -> shared memory;
+//            TX+TY threads then do the tile's right-column / top-row faces in one mixed x/y pass
+//   phase 3  flux differences + well-balanced source + RK axpy (+ stage-2 max wave speed)
+// Face data in shared memory: 4 flux components + the equilibrium face pressure gm1*E_f (the only
+// non-zero entry of the equilibrium flux, velocities being zero in every reference equilibrium).
+template <int TX, int TY>
+struct FastSmem {
+  double d[4][TY + 2][TX + 2];
+  double F[5][TY][TX + 1];
+  double G[5][TY + 1][TX];
+  double red[(TX * TY) / 32];
+  double dt;
+};
+
+// One LLF face in (normal,tangential) form.  lo/hi = delta on the low/high side of the face,
+// (rf,Ef) = conservative equilibrium at the face.  Returns flux (mass, normal mom, tangential mom, energy)
+// and pf = gm1*Ef.
+struct FaceFlux { double f0, fn, ft, f3, pf; };
+__device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef, double lr, double ln,
+                                             double lt, double lE, double hr, double hn, double ht,
+                                             double hE) {
+  // states: equilibrium at the face + the cell's own delta (benchmark_2d.f90:533-537)
+  double ar = rf + lr, aE = Ef + lE;   // low side  ("u_right(i-1)" / "u_top(j-1)")
+  double br = rf + hr, bE = Ef + hE;   // high side ("u_left(i)"   / "u_bottom(j)")
+  fast::Eval a = fast::eval_state(P, ar, ln, lt, aE);
+  fast::Eval b = fast::eval_state(P, br, hn, ht, bE);
+  double hc = 0.5 * fmax(a.spd, b.spd);
+  FaceFlux o;
+  // 0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)   (benchmark_2d.f90:366)
+  o.f0 = fma(hc, ar - br, 0.5 * (b.f0 + a.f0));
+  o.fn = fma(hc, ln - hn, 0.5 * (b.fn + a.fn));
+  o.ft = fma(hc, lt - ht, 0.5 * (b.ft + a.ft));
+  o.f3 = fma(hc, aE - bE, 0.5 * (b.f3 + a.f3));
+  o.pf = P.gm1 * Ef;
+  return o;
+}
+
+template <int TX, int TY, int MODE>
+__global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) k_stage_fast(StageArgs A, Grid g, Phys P) {
+  if (MODE != 0) {
+    if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
+      if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0 && A.row_begin == 0)
+        carry_forward(A.ctrl, A.parity);
+      return;
+    }
+  }
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem<TX, TY>& S = *reinterpret_cast<FastSmem<TX, TY>*>(smem_raw);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * TX + tx;
+  const int i0 = blockIdx.x * TX, jl0 = A.row_begin + blockIdx.y * TY;
+  const int i = i0 + tx, jl = jl0 + ty;
+
+  if (MODE != 0 && tid == 0) {
+    double dt = step_dt(A.ctrl, A.parity, P);
+    S.dt = dt;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && A.row_begin == 0) bookkeeping<MODE>(A.ctrl, A.parity, dt);
+  }
+
+  // ---- phase 1: own cell
+  const int ic = min(i, g.nx - 1);
+  const int jc = min(jl, g.nyl - 1);            // clamp tile overhang (results discarded)
+  const size_t o = (size_t)(jc + 1) * g.pitch + ic;
+  const double u0 = A.in[o], u1 = A.in[g.plane + o], u2 = A.in[2 * g.plane + o], u3 = A.in[3 * g.plane + o];
+  const double re = A.eqz[o], Ee = A.eqz[g.plane + o];
+  S.d[0][ty + 1][tx + 1] = u0 - re;
+  S.d[1][ty + 1][tx + 1] = u1;
+  S.d[2][ty + 1][tx + 1] = u2;
+  S.d[3][ty + 1][tx + 1] = u3 - Ee;
+  // ---- phase 1b: halo strips (bottom, top, left, right)
+  if (tid < 2 * TX + 2 * TY) {
+    int hi, hj, sx, sy;   // cell (local) and smem slot
+    if (tid < TX)               { hi = i0 + tid;            hj = jl0 - 1;               sx = tid + 1;          sy = 0; }
+    else if (tid < 2 * TX)      { hi = i0 + tid - TX;       hj = jl0 + TY;              sx = tid - TX + 1;     sy = TY + 1; }
+    else if (tid < 2 * TX + TY) { hi = i0 - 1;              hj = jl0 + tid - 2 * TX;    sx = 0;                sy = tid - 2 * TX + 1; }
+    else                        { hi = i0 + TX;             hj = jl0 + tid - 2 * TX - TY; sx = TX + 1;         sy = tid - 2 * TX - TY + 1; }
+    hi = max(0, min(hi, g.nx - 1));
+    // valid local rows are -1..nyl (ghost rows) intersected with the global grid
+    int jmin = (g.j0 > 0) ? -1 : 0, jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
+    hj = max(jmin, min(hj, jmax));
+    size_t oh = (size_t)(hj + 1) * g.pitch + hi;
+    S.d[0][sy][sx] = A.in[oh] - A.eqz[oh];
+    S.d[1][sy][sx] = A.in[g.plane + oh];
+    S.d[2][sy][sx] = A.in[2 * g.plane + oh];
+    S.d[3][sy][sx] = A.in[3 * g.plane + oh] - A.eqz[g.plane + oh];
+  }
+  __syncthreads();
+
+  // ---- phase 2: left (x) and bottom (y) faces of the own cell
+  {
+    const double eyc = A.eyc[jc], exc = A.exc[ic];
+    const double ex = A.exf[ic] * eyc;         // exp(-a*xf(i)) * exp(-a*yc(j))
+    FaceFlux fx = face_llf(P, P.rho0 * ex, P.pe1 * ex,
+                           S.d[0][ty + 1][tx], S.d[1][ty + 1][tx], S.d[2][ty + 1][tx], S.d[3][ty + 1][tx],
+                           S.d[0][ty + 1][tx + 1], S.d[1][ty + 1][tx + 1], S.d[2][ty + 1][tx + 1], S.d[3][ty + 1][tx + 1]);
+    S.F[0][ty][tx] = fx.f0; S.F[1][ty][tx] = fx.fn; S.F[2][ty][tx] = fx.ft; S.F[3][ty][tx] = fx.f3; S.F[4][ty][tx] = fx.pf;
+    const double ey = exc * A.eyf[jc];
+    FaceFlux fy = face_llf(P, P.rho0 * ey, P.pe1 * ey,
+                           S.d[0][ty][tx + 1], S.d[2][ty][tx + 1], S.d[1][ty][tx + 1], S.d[3][ty][tx + 1],
+                           S.d[0][ty + 1][tx + 1], S.d[2][ty + 1][tx + 1], S.d[1][ty + 1][tx + 1], S.d[3][ty + 1][tx + 1]);
+    S.G[0][ty][tx] = fy.f0; S.G[1][ty][tx] = fy.ft; S.G[2][ty][tx] = fy.fn; S.G[3][ty][tx] = fy.f3; S.G[4][ty][tx] = fy.pf;
+  }
+  // ---- phase 2b: the tile's outer faces (right column: x faces; top row: y faces), one mixed pass
+  if (tid < TX + TY) {
+    const bool isx = tid < TY;
+    int cx, cy;          // smem coordinates (in the d tile) of the low-side cell
+    double e;
+    if (isx) {           // x-face at i0+TX, row tid
+      cx = TX; cy = tid + 1;
+      int jj = min(jl0 + tid, g.nyl - 1);
+      e = A.exf[min(i0 + TX, g.nx)] * A.eyc[jj];
+    } else {             // y-face at jl0+TY, column tid-TY
+      cx = tid - TY + 1; cy = TY;
+      int ii = min(i0 + tid - TY, g.nx - 1);
+      e = A.exc[ii] * A.eyf[min(jl0 + TY, g.nyl)];
+    }
+    const int hx = isx ? cx + 1 : cx, hy = isx ? cy : cy + 1;
+    const int vn = isx ? 1 : 2, vt = isx ? 2 : 1;
+    FaceFlux f = face_llf(P, P.rho0 * e, P.pe1 * e,
+                          S.d[0][cy][cx], S.d[vn][cy][cx], S.d[vt][cy][cx], S.d[3][cy][cx],
+                          S.d[0][hy][hx], S.d[vn][hy][hx], S.d[vt][hy][hx], S.d[3][hy][hx]);
+    if (isx) {
+      S.F[0][tid][TX] = f.f0; S.F[1][tid][TX] = f.fn; S.F[2][tid][TX] = f.ft; S.F[3][tid][TX] = f.f3; S.F[4][tid][TX] = f.pf;
+    } else {
+      const int c = tid - TY;
+      S.G[0][TY][c] = f.f0; S.G[1][TY][c] = f.ft; S.G[2][TY][c] = f.fn; S.G[3][TY][c] = f.f3; S.G[4][TY][c] = f.pf;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: assemble dudt in the reference's order (benchmark_2d.f90:601-607) and update
+  const int jg = g.j0 + jl;
+  const bool inside = (i < g.nx) && (jl < A.row_end) && (jl < g.nyl);
+  const bool interior = inside && (i > 0) && (i < g.nx - 1) && (jg > 0) && (jg < g.ny - 1);
+  double d0, d1, d2, d3;
+  {
+    const double ax = S.F[4][ty][tx + 1] - S.F[4][ty][tx];   // F_eq(i+1)-F_eq(i)   (x-momentum entry)
+    const double ay = S.G[4][ty + 1][tx] - S.G[4][ty][tx];   // G_eq(j+1)-G_eq(j)   (y-momentum entry)
+    d0 = -((S.F[0][ty][tx + 1] - S.F[0][ty][tx]) * P.odx) - (S.G[0][ty + 1][tx] - S.G[0][ty][tx]) * P.ody;
+    d1 = -((S.F[1][ty][tx + 1] - S.F[1][ty][tx]) * P.odx) - (S.G[1][ty + 1][tx] - S.G[1][ty][tx]) * P.ody;
+    d2 = -((S.F[2][ty][tx + 1] - S.F[2][ty][tx]) * P.odx) - (S.G[2][ty + 1][tx] - S.G[2][ty][tx]) * P.ody;
+    d3 = -((S.F[3][ty][tx + 1] - S.F[3][ty][tx]) * P.odx) - (S.G[3][ty + 1][tx] - S.G[3][ty][tx]) * P.ody;
+    // + s - s_eq : s = (0,-rho,-rho,-rho*(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
+    d1 = (d1 - u0) + re;
+    d2 = (d2 - u0) + re;
+    d3 = d3 - (u1 + u2);
+    // + (F_eq(i+1)-F_eq(i))/dx + (G_eq(j+1)-G_eq(j))/dy
+    d1 = d1 + ax * P.odx;
+    d2 = d2 + ay * P.ody;
+    if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // dudt = 0 on the boundary lines :611-614
+  }
+  double n0, n1, n2, n3;
+  if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
+  if (MODE == 1) {
+    const double dt = S.dt;
+    n0 = fma(dt, d0, u0); n1 = fma(dt, d1, u1); n2 = fma(dt, d2, u2); n3 = fma(dt, d3, u3);
+  }
+  if (MODE == 2) {
+    const double hdt = 0.5 * S.dt;
+    n0 = fma(hdt, d0, 0.5 * (A.base[o] + u0));
+    n1 = fma(hdt, d1, 0.5 * (A.base[g.plane + o] + u1));
+    n2 = fma(hdt, d2, 0.5 * (A.base[2 * g.plane + o] + u2));
+    n3 = fma(hdt, d3, 0.5 * (A.base[3 * g.plane + o] + u3));
+  }
+  if (inside) {
+    A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
+  }
+  if (MODE == 2) {
+    double spd = inside ? fast::speed(P, n0, n1, n2, n3) : 0.0;
+    spd = warp_max(spd);
+    if ((tid & 31) == 0) S.red[tid >> 5] = spd;
+    __syncthreads();
+    if (tid < 32) {
+      double m = (tid < (TX * TY) / 32) ? S.red[tid] : 0.0;
+      m = warp_max(m);
+      if (tid == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], m);
+    }
+  }
+}
+
+}}  // namespace wb::fv2d
+
+// ============================================================================================ host side
+using namespace wb;
+using namespace wb::fv2d;
+
+struct wb_fv2d {
+  wb_fv2d_params prm;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Grid g;
+  Phys phys;
+  double *u = nullptr, *w1 = nullptr, *weq = nullptr, *eqz = nullptr, *stage = nullptr, *tab = nullptr;
+  const double *exf = nullptr, *exc = nullptr, *eyf = nullptr, *eyc = nullptr;
+  Ctrl* ctrl = nullptr;
+  Ctrl* h_ctrl = nullptr;       // pinned
+  bool resident = false;
+  bool fast_ok = true;          // supplied equilibrium has zero velocity -> fused kernels usable
+  int parity = 0;
+  wb::Nccl* comm = nullptr;
+};
+
+namespace {
+
+constexpr int FTX = 32, FTY = 8;
+
+int fill_phys(const wb_fv2d_params& p, Phys& P) {
+  P.gamma = p.gamma;
+  P.gm1 = p.gamma - (double)1.0f;
+  P.dx = p.boxlen_x / (double)p.nx;
+  P.dy = p.boxlen_y / (double)p.ny;
+  P.odx = 1 / P.dx;
+  P.ody = 1 / P.dy;
+  P.cfl = p.cfl;
+  P.neq = p.nequilibrium;
+  if (p.nequilibrium == 1) { P.rho0 = 1.0; P.p0 = 1.0; P.a = 1.0; }
+  else if (p.nequilibrium == 2 || p.nequilibrium == 3) {
+    P.rho0 = (double)1.21f; P.p0 = 1.0; P.a = P.rho0 * 1.0 / 1.0;
+  } else { P.rho0 = 0.0; P.p0 = 0.0; P.a = 0.0; }
+  P.pe1 = P.p0 / P.gm1;
+  return WB_OK;
+}
+
+size_t stage_bytes(const wb_fv2d* h) { return sizeof(double) * 4 * (size_t)h->g.nx * h->g.nyl; }
+
+int ensure_stage(wb_fv2d* h) {
+  if (!h->stage) WB_CUDA(cudaMalloc(&h->stage, stage_bytes(h)));
+  return WB_OK;
+}
+
+// host AoS (Fortran u(nvar,nx,ny_local)) -> device SoA planes
+int h2d_state(wb_fv2d* h, const double* host, double* soa) {
+  WB_CHECK(ensure_stage(h));
+  WB_CUDA(cudaMemcpyAsync(h->stage, host, stage_bytes(h), cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
+  k_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+int d2h_state(wb_fv2d* h, const double* soa, double* host) {
+  WB_CHECK(ensure_stage(h));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
+  k_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(host, h->stage, stage_bytes(h), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+
+// ghost-row exchange of a 4-plane field with the slab neighbours (per-stage halo, NCCL send/recv)
+int exchange_ghost_rows(wb_fv2d* h, double* field, int nplanes) {
+  if (h->prm.nranks <= 1) return WB_OK;
+  if (!h->comm) { set_error("nranks > 1 but wb_fv2d_comm_init was not called"); return WB_ERR_STATE; }
+  HaloSeg lo[4], hi[4];
+  const Grid& g = h->g;
+  for (int v = 0; v < nplanes; ++v) {
+    double* p = field + v * g.plane;
+    lo[v] = {p + (size_t)1 * g.pitch, p, (size_t)g.nx};
+    hi[v] = {p + (size_t)g.nyl * g.pitch, p + (size_t)(g.nyl + 1) * g.pitch, (size_t)g.nx};
+  }
+  int lo_peer = h->prm.rank > 0 ? h->prm.rank - 1 : -1;
+  int hi_peer = h->prm.rank < h->prm.nranks - 1 ? h->prm.rank + 1 : -1;
+  return nccl_halo_exchange_multi(h->comm, lo_peer, hi_peer, lo, nplanes, hi, nplanes, h->stream);
+}
+
+int prepare_eq(wb_fv2d* h) {
+  WB_CHECK(exchange_ghost_rows(h, h->weq, 4));
+  WB_CUDA(cudaMemsetAsync(&h->ctrl->nonzero_vel, 0, sizeof(int), h->stream));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
+  k_prepare_eq<<<gr, b, 0, h->stream>>>(h->weq, h->eqz, h->g, h->phys, h->ctrl);
+  WB_LAUNCH_CHECK();
+  int nz = 0;
+  WB_CUDA(cudaMemcpyAsync(&nz, &h->ctrl->nonzero_vel, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  h->fast_ok = (nz == 0);
+  return WB_OK;
+}
+
+bool use_fast(const wb_fv2d* h) { return h->prm.arith == 0 && h->fast_ok; }
+
+template <int MODE>
+int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, double tend, int max_iter,
+                 bool wb_scheme = true) {
+  StageArgs A;
+  A.in = in; A.base = base; A.out = out; A.weq = h->weq; A.eqz = h->eqz;
+  A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
+  A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
+  A.row_begin = 0; A.row_end = h->g.nyl;
+  if (use_fast(h) && wb_scheme) {
+    dim3 b(FTX, FTY), gr((h->g.nx + FTX - 1) / FTX, (h->g.nyl + FTY - 1) / FTY);
+    size_t smem = sizeof(FastSmem<FTX, FTY>);
+    k_stage_fast<FTX, FTY, MODE><<<gr, b, smem, h->stream>>>(A, h->g, h->phys);
+  } else {
+    dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
+    if (wb_scheme) k_stage_ref<MODE, true><<<gr, b, 0, h->stream>>>(A, h->g, h->phys);
+    else k_stage_ref<MODE, false><<<gr, b, 0, h->stream>>>(A, h->g, h->phys);
+  }
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+// max wave speed of `field` into ctrl->cmax_bits[slot] (all-reduced over ranks)
+int launch_max_speed(wb_fv2d* h, const double* field, int slot) {
+  WB_CUDA(cudaMemsetAsync(&h->ctrl->cmax_bits[slot], 0, sizeof(unsigned long long), h->stream));
+  dim3 b(256), gr(std::min((h->g.nx + 255) / 256, 64), std::min(h->g.nyl, 592));
+  if (h->prm.arith == 0) k_max_speed<true><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot]);
+  else k_max_speed<false><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot]);
+  WB_LAUNCH_CHECK();
+  if (h->prm.nranks > 1) {
+    if (!h->comm) { set_error("nranks > 1 but wb_fv2d_comm_init was not called"); return WB_ERR_STATE; }
+    WB_CHECK(nccl_allreduce_max_u64(h->comm, &h->ctrl->cmax_bits[slot], 1, h->stream));
+  }
+  return WB_OK;
+}
+
+int reset_clock(wb_fv2d* h) {
+  k_ctrl_reset<<<1, 1, 0, h->stream>>>(h->ctrl);
+  WB_LAUNCH_CHECK();
+  h->parity = 0;
+  return launch_max_speed(h, h->u, 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
+  if (!out || !p) { set_error("null argument"); return WB_ERR_ARG; }
+  *out = nullptr;
+  WB_REQUIRE(p->nvar == 4, "nvar must be 4 (got %d)", p->nvar);
+  WB_REQUIRE(p->nx >= 3 && p->ny >= 3, "nx, ny must be >= 3 (got %d x %d)", p->nx, p->ny);
+  WB_REQUIRE(p->nx < (1 << 23) && p->ny < (1 << 23), "nx, ny must be < 2^23 (single-precision (i-0.5) of the reference)");
+  WB_REQUIRE(p->nequilibrium >= 1 && p->nequilibrium <= 4, "nequilibrium must be 1..4 (got %d)", p->nequilibrium);
+  WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fast) or 1 (reference order)");
+  WB_REQUIRE(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks, "bad rank/nranks %d/%d", p->rank, p->nranks);
+  WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
+  WB_REQUIRE(p->ny / p->nranks >= 2, "each slab needs at least 2 rows");
+  int dev = 0;
+  WB_CHECK(select_device(p->device, &dev));
+  wb_fv2d* h = new wb_fv2d;
+  h->prm = *p;
+  h->dev = dev;
+  fill_phys(*p, h->phys);
+  Grid& g = h->g;
+  g.nx = p->nx; g.ny = p->ny;
+  g.j0 = (int)((long long)p->ny * p->rank / p->nranks);
+  int j1 = (int)((long long)p->ny * (p->rank + 1) / p->nranks);
+  g.nyl = j1 - g.j0;
+  g.pitch = (p->nx + 15) / 16 * 16;     // 128-byte aligned rows
+  g.plane = (size_t)(g.nyl + 2) * g.pitch;
+  int st = WB_OK;
+  auto fail = [&](int s) { wb_fv2d_destroy(h); return s; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(WB_ERR_CUDA); }
+  h->own_stream = true;
+  size_t fb = sizeof(double) * 4 * g.plane;
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->u, fb)) != cudaSuccess || (e = cudaMalloc(&h->w1, fb)) != cudaSuccess ||
+      (e = cudaMalloc(&h->weq, fb)) != cudaSuccess || (e = cudaMalloc(&h->eqz, fb / 2)) != cudaSuccess ||
+      (e = cudaMalloc(&h->ctrl, sizeof(Ctrl))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl))) != cudaSuccess) {
+    set_error("device allocation failed: %s", cudaGetErrorString(e));
+    return fail(WB_ERR_CUDA);
+  }
+  cudaMemsetAsync(h->u, 0, fb, h->stream);
+  cudaMemsetAsync(h->w1, 0, fb, h->stream);
+  cudaMemsetAsync(h->weq, 0, fb, h->stream);
+  cudaMemsetAsync(h->eqz, 0, fb / 2, h->stream);
+  cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream);
+  // separable equilibrium tables: exp(-a*xf(i)), exp(-a*xc(i)), exp(-a*yf(j)), exp(-a*yc(j)) (local rows)
+  {
+    const Phys& P = h->phys;
+    size_t nxf = g.nx + 1, nxc = g.nx, nyf = g.nyl + 1, nyc = g.nyl;
+    std::vector<double> t(nxf + nxc + nyf + nyc);
+    double z = (P.neq == 4) ? 0.0 : 1.0;
+    for (size_t i = 0; i < nxf; ++i) t[i] = z * std::exp(-P.a * ((double)i * P.dx));
+    for (size_t i = 0; i < nxc; ++i) t[nxf + i] = z * std::exp(-P.a * ((double)((float)(i + 1) - 0.5f) * P.dx));
+    for (size_t j = 0; j < nyf; ++j) t[nxf + nxc + j] = z * std::exp(-P.a * ((double)(g.j0 + j) * P.dx /* sic :513 */));
+    for (size_t j = 0; j < nyc; ++j) t[nxf + nxc + nyf + j] = z * std::exp(-P.a * ((double)((float)(g.j0 + j + 1) - 0.5f) * P.dy));
+    if ((e = cudaMalloc(&h->tab, sizeof(double) * t.size())) != cudaSuccess) { set_error("table allocation failed"); return fail(WB_ERR_CUDA); }
+    if ((e = cudaMemcpy(h->tab, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      set_error("table upload failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA);
+    }
+    h->exf = h->tab; h->exc = h->tab + nxf; h->eyf = h->tab + nxf + nxc; h->eyc = h->tab + nxf + nxc + nyf;
+  }
+  {
+    auto k1 = k_stage_fast<FTX, FTY, 0>; auto k2 = k_stage_fast<FTX, FTY, 1>; auto k3 = k_stage_fast<FTX, FTY, 2>;
+    int sm = (int)sizeof(FastSmem<FTX, FTY>);
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  }
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
+  (void)st;
+  *out = h;
+  return WB_OK;
+}
+
+int wb_fv2d_destroy(wb_fv2d* h) {
+  if (!h) return WB_OK;
+  cudaSetDevice(h->dev);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  nccl_comm_destroy(h->comm);
+  cudaFree(h->u); cudaFree(h->w1); cudaFree(h->weq); cudaFree(h->eqz); cudaFree(h->stage); cudaFree(h->tab);
+  cudaFree(h->ctrl);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WB_OK;
+}
+
+int wb_fv2d_local_rows(const wb_fv2d* h, int* j0, int* nrows) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  if (j0) *j0 = h->g.j0;
+  if (nrows) *nrows = h->g.nyl;
+  return WB_OK;
+}
+
+int wb_fv2d_set_stream(wb_fv2d* h, void* cuda_stream) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int wb_fv2d_comm_init(wb_fv2d* h, const void* id128) {
+  if (!h || !id128) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(h->prm.nranks > 1, "comm_init needs nranks > 1");
+  WB_CUDA(cudaSetDevice(h->dev));
+  if (h->comm) { nccl_comm_destroy(h->comm); h->comm = nullptr; }
+  return nccl_comm_create(&h->comm, id128, h->prm.rank, h->prm.nranks);
+}
+
+int wb_fv2d_upload(wb_fv2d* h, const double* u, const double* w_eq) {
+  if (!h || !u || !w_eq) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CHECK(h2d_state(h, w_eq, h->weq));
+  WB_CHECK(prepare_eq(h));
+  WB_CHECK(h2d_state(h, u, h->u));
+  WB_CHECK(exchange_ghost_rows(h, h->u, 4));
+  WB_CHECK(reset_clock(h));
+  h->resident = true;
+  return WB_OK;
+}
+
+int wb_fv2d_init_device(wb_fv2d* h, int ninit, double eta) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_REQUIRE(ninit >= 1 && ninit <= 4, "ninit must be 1..4 (got %d)", ninit);
+  WB_CUDA(cudaSetDevice(h->dev));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
+  k_init<<<gr, b, 0, h->stream>>>(h->u, h->weq, h->g, h->phys, ninit, eta, 1, 1);
+  WB_LAUNCH_CHECK();
+  WB_CHECK(prepare_eq(h));
+  WB_CHECK(reset_clock(h));
+  h->resident = true;
+  return WB_OK;
+}
+
+int wb_fv2d_get_initial_conditions(wb_fv2d* h, int ninit, double eta, double* u_out, double* w_eq_out) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_REQUIRE(ninit >= 1 && ninit <= 4, "ninit must be 1..4 (got %d)", ninit);
+  WB_CUDA(cudaSetDevice(h->dev));
+  // uses w1 / stage as scratch so that a resident state is not disturbed
+  double* scratch_u = h->w1;
+  double* scratch_w = nullptr;
+  WB_CUDA(cudaMalloc(&scratch_w, sizeof(double) * 4 * h->g.plane));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
+  k_init<<<gr, b, 0, h->stream>>>(scratch_u, scratch_w, h->g, h->phys, ninit, eta, 1, 1);
+  wb::g_launches.fetch_add(1);
+  int st = WB_OK;
+  if (cudaGetLastError() != cudaSuccess) { set_error("k_init launch failed"); st = WB_ERR_CUDA; }
+  if (st == WB_OK && u_out) st = d2h_state(h, scratch_u, u_out);
+  if (st == WB_OK && w_eq_out) st = d2h_state(h, scratch_w, w_eq_out);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(scratch_w);
+  return st;
+}
+
+int wb_fv2d_reset_clock(wb_fv2d* h) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state (call upload or init_device first)"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  return reset_clock(h);
+}
+
+int wb_fv2d_step_async(wb_fv2d* h, int nsteps, double tend) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state (call upload or init_device first)"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  for (int s = 0; s < nsteps; ++s) {
+    // stage 1: w1 = u + dt*L(u)                                   benchmark_2d.f90:246-247
+    WB_CHECK(launch_stage<1>(h, h->u, nullptr, h->w1, tend, -1));
+    WB_CHECK(exchange_ghost_rows(h, h->w1, 4));
+    // stage 2: u = .5u + .5w1 + .5dt*L(w1), fused max speed        benchmark_2d.f90:249-250, :241
+    WB_CHECK(launch_stage<2>(h, h->w1, h->u, h->u, tend, -1));
+    WB_CHECK(exchange_ghost_rows(h, h->u, 4));
+    if (h->prm.nranks > 1) WB_CHECK(nccl_allreduce_max_u64(h->comm, &h->ctrl->cmax_bits[h->parity ^ 1], 1, h->stream));
+    h->parity ^= 1;
+  }
+  return WB_OK;
+}
+
+int wb_fv2d_sync(wb_fv2d* h, int* iters_out, double* t_out, double* last_dt_out, double* last_cmax_out) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  int s = (h->h_ctrl->iter[1] > h->h_ctrl->iter[0]) ? 1 : 0;
+  if (iters_out) *iters_out = h->h_ctrl->iter[s];
+  if (t_out) *t_out = h->h_ctrl->t[s];
+  if (last_dt_out) *last_dt_out = h->h_ctrl->dt_last;
+  if (last_cmax_out) *last_cmax_out = h->h_ctrl->cmax_last;
+  return WB_OK;
+}
+
+int wb_fv2d_download(wb_fv2d* h, double* u_out) {
+  if (!h || !u_out) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  return d2h_state(h, h->u, u_out);
+}
+
+int wb_fv2d_evolve(wb_fv2d* h, double* u_inout, const double* w_eq, double tend, int max_iter, int* iters_out,
+                   double* t_out, double* last_dt_out) {
+  if (!h || !u_inout || !w_eq) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CHECK(wb_fv2d_upload(h, u_inout, w_eq));
+  int iters = 0;
+  double t = 0.0, dt = 0.0;
+  const int batch = 16;
+  for (;;) {
+    if (!(t < tend) || (max_iter >= 0 && iters >= max_iter)) break;
+    int n = batch;
+    if (max_iter >= 0 && max_iter - iters < n) n = max_iter - iters;
+    WB_CHECK(wb_fv2d_step_async(h, n, tend));
+    WB_CHECK(wb_fv2d_sync(h, &iters, &t, &dt, nullptr));
+  }
+  WB_CHECK(wb_fv2d_download(h, u_inout));
+  if (iters_out) *iters_out = iters;
+  if (t_out) *t_out = t;
+  if (last_dt_out) *last_dt_out = dt;
+  return WB_OK;
+}
+
+static int update_common(wb_fv2d* h, const double* u, const double* w_eq, double* dudt, bool wb_scheme) {
+  if (!h || !u || !w_eq || !dudt) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  // stateless: uses the resident buffers as scratch -> invalidates a resident state
+  h->resident = false;
+  WB_CHECK(h2d_state(h, w_eq, h->weq));
+  WB_CHECK(prepare_eq(h));
+  WB_CHECK(h2d_state(h, u, h->u));
+  WB_CHECK(exchange_ghost_rows(h, h->u, 4));
+  WB_CHECK(launch_stage<0>(h, h->u, nullptr, h->w1, 0.0, -1, wb_scheme));
+  return d2h_state(h, h->w1, dudt);
+}
+
+int wb_fv2d_compute_update_exact(wb_fv2d* h, const double* u, const double* w_eq, double* dudt) {
+  return update_common(h, u, w_eq, dudt, true);
+}
+int wb_fv2d_compute_update(wb_fv2d* h, const double* u, const double* w_eq, double* dudt) {
+  return update_common(h, u, w_eq, dudt, false);
+}
+
+int wb_fv2d_compute_max_speed(wb_fv2d* h, const double* u, double* cmax) {
+  if (!h || !u || !cmax) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  WB_CHECK(h2d_state(h, u, h->w1));
+  WB_CHECK(launch_max_speed(h, h->w1, 0));
+  unsigned long long bits = 0;
+  WB_CUDA(cudaMemcpyAsync(&bits, &h->ctrl->cmax_bits[0], sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(cmax, &bits, sizeof(double));
+  return WB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// Pointwise physics of the 2D well-balanced FV path (benchmark_2d.f90), two arithmetic flavours:
+//   ref::  reference operation order, IEEE div/sqrt, no FMA  (file is compiled with -fmad=false, so
+//          plain C expressions are evaluated exactly as written)
+//   fast:: fused arithmetic with Newton reciprocal / rsqrt; same formulas, <= few ulp per operation.
+// Both keep the property that makes the scheme well balanced bit for bit: the numerical-flux side
+// and the equilibrium-flux side run the SAME instruction sequence on the same inputs.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace wb { namespace fv2d {
+
+struct Phys {
+  double gamma, gm1;       // gamma, gamma-1 (gamma - 1.0 with the reference's promoted literal)
+  double dx, dy, odx, ody;
+  double cfl;
+  double rho0, p0, a;      // equilibrium constants: rho = rho0*exp(-a(x+y)), p = p0*exp(-a(x+y))
+  double pe1;              // p0/(gamma-1)
+  int neq;
+};
+
+// ------------------------------------------------------------------ coordinates (benchmark_2d.f90:505-522)
+// i, j are 0-based GLOBAL indices; the reference is 1-based: (i-1)*dx -> i*dx, (i-0.5) in real(4).
+__device__ __forceinline__ double x_face(int i, double dx) { return (double)i * dx; }
+__device__ __forceinline__ double x_cent(int i, double dx) { return (double)((float)(i + 1) - 0.5f) * dx; }
+
+namespace ref {
+
+// benchmark_2d.f90:174-218 (primitives rho, p; velocities are zero in every case)
+__device__ __forceinline__ void eq_prim(const Phys& P, double x, double y, double& rho, double& p) {
+  if (P.neq == 4) { rho = 0.0; p = 0.0; return; }
+  double e = exp(-(P.a) * (x + y));      // case 1: a = 1, -(x+y) == (-1)*(x+y) bit for bit
+  rho = P.rho0 * e;
+  p = P.p0 * e;
+}
+// benchmark_2d.f90:159-171
+__device__ __forceinline__ void cons(const Phys& P, const double w[4], double u[4]) {
+  u[0] = w[0];
+  u[1] = w[0] * w[1];
+  u[2] = w[0] * w[2];
+  u[3] = w[3] / P.gm1 + 0.5 * (w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+// benchmark_2d.f90:145-157
+__device__ __forceinline__ void prim(const Phys& P, const double u[4], double w[4]) {
+  w[0] = u[0];
+  w[1] = u[1] / w[0];
+  w[2] = u[2] / w[0];
+  w[3] = P.gm1 * (u[3] - 0.5 * w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+// benchmark_2d.f90:283-295
+__device__ __forceinline__ double speed(const Phys& P, const double u[4]) {
+  double w[4];
+  prim(P, u, w);
+  double cs = sqrt(P.gamma * fmax(w[3], 1e-10) / fmax(w[0], 1e-10));
+  return sqrt(w[1] * w[1] + w[2] * w[2]) + cs;
+}
+// benchmark_2d.f90:299-325, one direction
+template <int DIR>
+__device__ __forceinline__ void flux(const Phys& P, const double u[4], double f[4]) {
+  double w[4];
+  prim(P, u, w);
+  if (DIR == 0) {
+    f[0] = w[1] * u[0];
+    f[1] = w[1] * u[1] + w[3];
+    f[2] = w[0] * w[1] * w[2];
+    f[3] = w[1] * u[3] + w[1] * w[3];
+  } else {
+    f[0] = u[0] * w[2];
+    f[1] = u[1] * w[2];
+    f[2] = u[2] * w[2] + w[3];
+    f[3] = w[2] * u[3] + w[2] * w[3];
+  }
+}
+// benchmark_2d.f90:353-367
+template <int DIR>
+__device__ __forceinline__ void llf(const Phys& P, const double ul[4], const double ur[4], double fg[4]) {
+  double fl[4], fr[4];
+  flux<DIR>(P, ul, fl);
+  flux<DIR>(P, ur, fr);
+  double cl = speed(P, ul), cr = speed(P, ur);
+  double cmax = fmax(cl, cr);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) fg[v] = 0.5 * (fr[v] + fl[v]) + 0.5 * cmax * (ul[v] - ur[v]);
+}
+// benchmark_2d.f90:327-350 with phi_x = phi_y = 1.
+__device__ __forceinline__ void source(const double w[4], double s[4]) {
+  s[0] = 0.0;
+  s[1] = -w[0] * 1.0;
+  s[2] = -w[0] * 1.0;
+  s[3] = -w[0] * (w[1] * 1.0 + w[2] * 1.0);
+}
+
+}  // namespace ref
+
+namespace fast {
+
+// 1/x: MUFU.RCP64H seed (~2^-20) + one cubic Newton step; relative error ~2^-53.
+__device__ __forceinline__ double rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+// sqrt(a) for a > 0 (callers clamp): MUFU.RSQ64H seed + cubic step on 1/sqrt, then a*y.
+__device__ __forceinline__ double sqrt_pos(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y;
+  double h = fma(-t, y, 1.0);
+  double p = fma(0.375, h, 0.5);
+  p = p * h;
+  double s = fma(t, p, t);        // a*y*(1 + h/2 + 3h^2/8)
+  return s;
+}
+
+// Directional state evaluation in (normal, tangential) momentum form.
+//   f = (mn, vn*mn + p, vn*mt, vn*(E+p)),  spd = |v| + sqrt(gamma*max(p,1e-10)/max(rho,1e-10))
+struct Eval { double f0, fn, ft, f3, spd; };
+__device__ __forceinline__ Eval eval_state(const Phys& P, double rho, double mn, double mt, double E) {
+  Eval o;
+  double r = rcp(rho);
+  double vn = mn * r, vt = mt * r;
+  double q = fma(vt, vt, vn * vn);
+  double p = P.gm1 * fma(-0.5 * rho, q, E);
+  double pm = fmax(p, 1e-10);
+  double rm = (rho >= 1e-10) ? r : 1e10;
+  double c2 = (P.gamma * pm) * rm;
+  double cs = sqrt_pos(c2);
+  double vm = sqrt_pos(fmax(q, 1e-300));   // q == 0 gives 1e-150, absorbed by "+ cs"
+  o.spd = vm + cs;
+  o.f0 = mn;
+  o.fn = fma(vn, mn, p);
+  o.ft = vn * mt;
+  o.f3 = vn * (E + p);
+  return o;
+}
+// max wave speed of a state (stage-2 CFL reduction)
+__device__ __forceinline__ double speed(const Phys& P, double rho, double mx, double my, double E) {
+  double r = rcp(rho);
+  double vx = mx * r, vy = my * r;
+  double q = fma(vy, vy, vx * vx);
+  double p = P.gm1 * fma(-0.5 * rho, q, E);
+  double pm = fmax(p, 1e-10);
+  double rm = (rho >= 1e-10) ? r : 1e10;
+  double cs = sqrt_pos((P.gamma * pm) * rm);
+  double vm = sqrt_pos(fmax(q, 1e-300));
+  return vm + cs;
+}
+
+}  // namespace fast
+
+}}  // namespace wb::fv2d

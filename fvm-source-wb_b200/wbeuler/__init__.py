@@ -1,0 +1,178 @@
+"""wbeuler -- host-side mirror of the reference's update routines over the C-ABI in include/wbeuler.h.
+
+The reference (hanveiga/fvm-source-wb) is serial Fortran whose "interface" is a set of external
+subroutines (`compute_update_exact`, `compute_max_speed`, `evolve`, ...).  This package exposes the
+same names with the same argument meaning on top of ``libwbeuler.so`` (hand-written FP64 CUDA for
+sm_100a).  There is no CPU fallback: if the shared library is missing, or no B200 is visible, every
+call raises.
+
+Array convention: the reference's ``u(nvar,nx,ny)`` is a C-contiguous float64 numpy array of shape
+``(ny, nx, nvar)`` (identical bytes).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwbeuler.so")
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+class WBError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libwbeuler.so (raises if it has not been built: `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WBError(f"{LIB_PATH} is missing: the CUDA library has not been built "
+                          "(run __graft_entry__.build()); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.wb_last_error.restype = C.c_char_p
+        _lib.wb_version.restype = C.c_char_p
+        _lib.wb_kernel_launch_count.restype = C.c_longlong
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise WBError(f"wbeuler error {status}: {lib().wb_last_error().decode()}")
+
+
+def version():
+    return lib().wb_version().decode()
+
+
+def kernel_launch_count():
+    return int(lib().wb_kernel_launch_count())
+
+
+def nccl_get_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().wb_nccl_get_unique_id(buf))
+    return buf.raw
+
+
+def _ptr(a):
+    if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        raise WBError("arrays must be C-contiguous float64")
+    return a.ctypes.data_as(_dp)
+
+
+def F32(v):
+    """A real(4) literal of the reference promoted to real(8) (its Makefiles set no -fdefault-real-8)."""
+    return float(np.float32(v))
+
+
+class FV2DParams(C.Structure):
+    """wb_fv2d_params (include/wbeuler.h); defaults are parameters_2d.f90:3-21."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nvar", C.c_int), ("nequilibrium", C.c_int),
+                ("gamma", C.c_double), ("boxlen_x", C.c_double), ("boxlen_y", C.c_double),
+                ("cfl", C.c_double), ("arith", C.c_int), ("device", C.c_int), ("rank", C.c_int),
+                ("nranks", C.c_int)]
+
+
+class FV2D:
+    """2D well-balanced finite volumes (benchmark_2d.f90).  Methods carry the reference's names."""
+
+    def __init__(self, nx, ny, nequilibrium=2, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=0.5,
+                 arith=0, device=-1, rank=0, nranks=1):
+        self.params = FV2DParams(nx, ny, 4, nequilibrium, gamma, boxlen_x, boxlen_y, cfl, arith, device,
+                                 rank, nranks)
+        self._h = C.c_void_p()
+        _check(lib().wb_fv2d_create(C.byref(self._h), C.byref(self.params)))
+        j0 = C.c_int(); nr = C.c_int()
+        _check(lib().wb_fv2d_local_rows(self._h, C.byref(j0), C.byref(nr)))
+        self.j0, self.nyl = j0.value, nr.value
+        self.nx, self.ny = nx, ny
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().wb_fv2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def local_shape(self):
+        return (self.nyl, self.nx, 4)
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().wb_fv2d_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def comm_init(self, unique_id_bytes):
+        _check(lib().wb_fv2d_comm_init(self._h, C.c_char_p(unique_id_bytes)))
+
+    # -- the reference's routines -----------------------------------------------------------------
+    def compute_update_exact(self, u, w_eq):
+        """compute_update_exact(u,w_eq,dudt)  benchmark_2d.f90:465-618"""
+        dudt = np.empty(self.local_shape)
+        _check(lib().wb_fv2d_compute_update_exact(self._h, _ptr(u), _ptr(w_eq), _ptr(dudt)))
+        return dudt
+
+    def compute_update(self, u, w_eq):
+        """compute_update(u,w_eq,dudt)  benchmark_2d.f90:370-463 (plain scheme)"""
+        dudt = np.empty(self.local_shape)
+        _check(lib().wb_fv2d_compute_update(self._h, _ptr(u), _ptr(w_eq), _ptr(dudt)))
+        return dudt
+
+    def compute_max_speed(self, u):
+        """compute_max_speed(u,cmax)  benchmark_2d.f90:264-279"""
+        c = C.c_double()
+        _check(lib().wb_fv2d_compute_max_speed(self._h, _ptr(u), C.byref(c)))
+        return c.value
+
+    def evolve(self, u, w_eq, tend, max_iter=-1):
+        """evolve(u,u_eq)  benchmark_2d.f90:221-260.  Returns (u_new, iters, t, last_dt)."""
+        u = np.array(u, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_fv2d_evolve(self._h, _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter),
+                                    C.byref(it), C.byref(t), C.byref(dt)))
+        return u, it.value, t.value, dt.value
+
+    def get_initial_conditions(self, ninit, eta=F32(0.00001)):
+        """get_initial_conditions + get_equilibrium_solution at centres (benchmark_2d.f90:45-113,:174-218).
+        Returns (u, w_eq) for the local rows."""
+        u = np.empty(self.local_shape); w = np.empty(self.local_shape)
+        _check(lib().wb_fv2d_get_initial_conditions(self._h, C.c_int(ninit), C.c_double(eta), _ptr(u), _ptr(w)))
+        return u, w
+
+    # -- resident path ------------------------------------------------------------------------------
+    def upload(self, u, w_eq):
+        _check(lib().wb_fv2d_upload(self._h, _ptr(u), _ptr(w_eq)))
+
+    def init_device(self, ninit, eta=F32(0.00001)):
+        _check(lib().wb_fv2d_init_device(self._h, C.c_int(ninit), C.c_double(eta)))
+
+    def step_async(self, nsteps, tend=1e300):
+        _check(lib().wb_fv2d_step_async(self._h, C.c_int(nsteps), C.c_double(tend)))
+
+    def sync(self):
+        """Returns (iters, t, last_dt, last_cmax)."""
+        it = C.c_int(); t = C.c_double(); dt = C.c_double(); cm = C.c_double()
+        _check(lib().wb_fv2d_sync(self._h, C.byref(it), C.byref(t), C.byref(dt), C.byref(cm)))
+        return it.value, t.value, dt.value, cm.value
+
+    def download(self):
+        u = np.empty(self.local_shape)
+        _check(lib().wb_fv2d_download(self._h, _ptr(u)))
+        return u
+
+    def reset_clock(self):
+        _check(lib().wb_fv2d_reset_clock(self._h))

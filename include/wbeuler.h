@@ -1,0 +1,112 @@
+/* wbeuler.h -- C-ABI of the B200-native explicit time-step hot path of hanveiga/fvm-source-wb.
+ *
+ * The reference has no FFI: its de-facto ABI is gfortran's external-procedure convention
+ * (every argument by reference, column-major real(8) arrays).  Each entry point below names the
+ * reference subroutine it replaces (file:line relative to the reference checkout); the
+ * ISO_C_BINDING interface blocks that bind them are in fvm-source-wb_b200/fortran/ and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; wb_last_error() gives the message
+ *     (thread-local).  The library never prints and never aborts.
+ *   - all arithmetic is FP64.  Host arrays keep the reference's Fortran layout byte for byte:
+ *       FV 2D  u(nvar,nx,ny)            == C double[ny][nx][4]
+ *       DG 2D  u(nvar,nx,ny,mx,my)      == C double[my][mx][ny][nx][4]
+ *       1D     u(nvar,nx) / u(nvar,n,nx)== C double[nx][nvar] / double[nx][n][nvar]
+ *     the library transposes to structure-of-arrays planes on the device.
+ *   - the library never retains host pointers; handles own all device memory; a handle is used
+ *     from one host thread at a time.
+ *   - there is no CPU fallback: every entry point fails with WB_ERR_CUDA when no sm_100 device
+ *     (or no CUDA driver) is present.
+ */
+#ifndef WBEULER_H
+#define WBEULER_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_OK            0
+#define WB_ERR_ARG      -1   /* bad argument / unsupported parameter value            */
+#define WB_ERR_CUDA     -2   /* CUDA runtime error, or no usable GPU                  */
+#define WB_ERR_NCCL     -3   /* NCCL error, or libnccl could not be loaded            */
+#define WB_ERR_STATE    -4   /* call sequence error (e.g. step before upload)         */
+
+const char* wb_last_error(void);
+/* library version string, e.g. "wbeuler-b200 0.1 (sm_100a)" */
+const char* wb_version(void);
+/* number of kernel launches issued by this process' library calls so far (for bench.py gpu_launches) */
+long long wb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU plumbing: one process per GPU.  Rank 0 calls wb_nccl_get_unique_id(), ships the
+ * 128 bytes to the other ranks by whatever the host program has (torch.distributed / MPI),
+ * then every rank passes them to the *_comm_init of its handle.
+ * ------------------------------------------------------------------------------------------ */
+#define WB_NCCL_UNIQUE_ID_BYTES 128
+int wb_nccl_get_unique_id(void* id128);
+
+/* ==========================================================================================
+ * 2D well-balanced finite volumes -- benchmark_2d.f90 (module parameters_2d.f90)
+ * ========================================================================================== */
+typedef struct wb_fv2d wb_fv2d;
+
+typedef struct {
+  int nx, ny;            /* GLOBAL grid (parameters_2d.f90:3-4)                                  */
+  int nvar;              /* must be 4 (parameters_2d.f90:6)                                      */
+  int nequilibrium;      /* 1..4 (parameters_2d.f90:14; benchmark_2d.f90:189-216)                */
+  double gamma;          /* parameters_2d.f90:19 (the reference value is 1.4 as real(4))         */
+  double boxlen_x;       /* parameters_2d.f90:17                                                 */
+  double boxlen_y;       /* parameters_2d.f90:18                                                 */
+  double cfl;            /* parameters_2d.f90:20                                                 */
+  int arith;             /* 0 = fused/fast arithmetic (<=1e-12 of the reference, default)
+                            1 = reference operation order (no FMA, IEEE div/sqrt, libm-style exp) */
+  int device;            /* CUDA device ordinal; -1 = current device                             */
+  int rank, nranks;      /* y-slab decomposition: this handle owns global rows
+                            [ny*rank/nranks, ny*(rank+1)/nranks); 0,1 for a single GPU           */
+} wb_fv2d_params;
+
+int wb_fv2d_create(wb_fv2d** h, const wb_fv2d_params* p);
+int wb_fv2d_destroy(wb_fv2d* h);
+/* rows of the global grid owned by this handle: j0 (0-based) and count */
+int wb_fv2d_local_rows(const wb_fv2d* h, int* j0, int* nrows);
+/* enqueue all work of this handle on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int wb_fv2d_set_stream(wb_fv2d* h, void* cuda_stream);
+/* nranks > 1 only: create the NCCL communicator used for the per-stage ghost-row send/recv and
+ * the per-step max all-reduce */
+int wb_fv2d_comm_init(wb_fv2d* h, const void* nccl_unique_id128);
+
+/* --- stateless entries: same contract as the Fortran routines (host arrays in, host arrays out;
+ *     H2D + kernel + D2H inside the call).  In slab mode the arrays are the LOCAL rows. -------- */
+/* replaces compute_update_exact(u,w_eq,dudt)   benchmark_2d.f90:465-618 */
+int wb_fv2d_compute_update_exact(wb_fv2d* h, const double* u, const double* w_eq, double* dudt);
+/* replaces compute_update(u,w_eq,dudt) (plain, non well-balanced)   benchmark_2d.f90:370-463 */
+int wb_fv2d_compute_update(wb_fv2d* h, const double* u, const double* w_eq, double* dudt);
+/* replaces compute_max_speed(u,cmax)           benchmark_2d.f90:264-279 (global max over ranks) */
+int wb_fv2d_compute_max_speed(wb_fv2d* h, const double* u, double* cmax);
+/* replaces evolve(u,u_eq)                      benchmark_2d.f90:221-260
+ * loops `do while (t < tend)` (no clamp of the last dt, as the reference); max_iter < 0 = no cap */
+int wb_fv2d_evolve(wb_fv2d* h, double* u_inout, const double* w_eq, double tend, int max_iter,
+                   int* iters_out, double* t_out, double* last_dt_out);
+/* replaces get_equilibrium_solution at cell centres + get_initial_conditions
+ * (benchmark_2d.f90:174-218, :45-113) for the local rows; host arrays out (either may be NULL) */
+int wb_fv2d_get_initial_conditions(wb_fv2d* h, int ninit, double eta, double* u_out, double* w_eq_out);
+
+/* --- resident path (state stays in HBM between calls) ---------------------------------------- */
+int wb_fv2d_upload(wb_fv2d* h, const double* u, const double* w_eq);
+/* fill u (ninit 1..4, benchmark_2d.f90:56-109) and the centre equilibrium on the device */
+int wb_fv2d_init_device(wb_fv2d* h, int ninit, double eta);
+/* enqueue nsteps RK2 steps (2 fused stage kernels each) WITHOUT synchronising; t/iter bookkeeping
+ * and the CFL reduction stay on the device.  tend caps as in the reference (steps after t>=tend
+ * are no-ops). */
+int wb_fv2d_step_async(wb_fv2d* h, int nsteps, double tend);
+/* wait for the stream and read the bookkeeping */
+int wb_fv2d_sync(wb_fv2d* h, int* iters_out, double* t_out, double* last_dt_out, double* last_cmax_out);
+int wb_fv2d_download(wb_fv2d* h, double* u_out);
+/* reset t = 0, iter = 0 and recompute the max wave speed of the resident state */
+int wb_fv2d_reset_clock(wb_fv2d* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBEULER_H */

@@ -1,0 +1,126 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY (ctypes binding of oracle/libwb_oracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  The product (fvm-source-wb_b200/) never does.
+
+Array convention: the reference's Fortran u(nvar,nx,ny) is passed as a C-contiguous numpy array of
+shape (ny, nx, nvar) -- same bytes.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libwb_oracle.so")
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, -ffp-contract=off)."""
+    if force or not os.path.exists(_LIB) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
+        for f in os.listdir(_HERE) if f.endswith((".c", ".h", "Makefile"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+def _ptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+class FV2DParams(C.Structure):
+    """parameters_2d.f90:3-21."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nequilibrium", C.c_int), ("gamma", C.c_double),
+                ("boxlen_x", C.c_double), ("boxlen_y", C.c_double), ("cfl", C.c_double)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_get_max_threads.restype = C.c_int
+    return _lib
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(C.c_int(n))
+
+
+def max_threads():
+    return lib().orc_get_max_threads()
+
+
+F32 = lambda v: float(np.float32(v))  # noqa: E731  real(4) literal promoted to real(8)
+
+
+def fv2d_params(nx, ny, nequilibrium=2, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=0.5):
+    return FV2DParams(nx, ny, nequilibrium, gamma, boxlen_x, boxlen_y, cfl)
+
+
+# ---------------------------------------------------------------- 2D FV (benchmark_2d.f90)
+def fv2d_get_coords(p):
+    x = np.empty((p.ny, p.nx)); y = np.empty((p.ny, p.nx))
+    lib().orc_fv2d_get_coords(C.c_int(p.nx), C.c_int(p.ny), C.c_double(p.boxlen_x),
+                              C.c_double(p.boxlen_y), _ptr(x), _ptr(y))
+    return x, y
+
+
+def fv2d_get_equilibrium_solution(p, x, y):
+    w = np.empty(x.shape + (4,))
+    lib().orc_fv2d_get_equilibrium_solution(C.c_int(p.nequilibrium), _ptr(x), _ptr(y), _ptr(w),
+                                            C.c_long(x.size))
+    return w
+
+
+def fv2d_get_initial_conditions(p, ninit, x, y, eta=F32(0.00001)):
+    u = np.empty(x.shape + (4,))
+    lib().orc_fv2d_get_initial_conditions(C.c_int(ninit), C.c_double(eta), C.c_double(p.gamma),
+                                          _ptr(x), _ptr(y), _ptr(u), C.c_long(x.size))
+    return u
+
+
+def fv2d_compute_primitive(p, u):
+    w = np.empty_like(u)
+    lib().orc_fv2d_compute_primitive(_ptr(u), _ptr(w), C.c_double(p.gamma), C.c_long(u.size // 4))
+    return w
+
+
+def fv2d_compute_conservative(p, w):
+    u = np.empty_like(w)
+    lib().orc_fv2d_compute_conservative(_ptr(w), _ptr(u), C.c_double(p.gamma), C.c_long(w.size // 4))
+    return u
+
+
+def fv2d_compute_max_speed(p, u):
+    c = C.c_double(0)
+    lib().orc_fv2d_compute_max_speed(C.byref(p), _ptr(u), C.byref(c))
+    return c.value
+
+
+def fv2d_compute_update_exact(p, u, w_eq):
+    dudt = np.empty_like(u)
+    lib().orc_fv2d_compute_update_exact(C.byref(p), _ptr(u), _ptr(w_eq), _ptr(dudt))
+    return dudt
+
+
+def fv2d_compute_update(p, u, w_eq):
+    dudt = np.empty_like(u)
+    lib().orc_fv2d_compute_update(C.byref(p), _ptr(u), _ptr(w_eq), _ptr(dudt))
+    return dudt
+
+
+def fv2d_evolve(p, u, w_eq, tend, max_iter=-1):
+    """Returns (u_new, iters, t, last_dt, last_cmax); u is not modified."""
+    u = np.array(u, copy=True)
+    it = C.c_int(0); t = C.c_double(0); dt = C.c_double(0); cm = C.c_double(0)
+    lib().orc_fv2d_evolve(C.byref(p), _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter),
+                          C.byref(it), C.byref(t), C.byref(dt), C.byref(cm))
+    return u, it.value, t.value, dt.value, cm.value

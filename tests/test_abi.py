@@ -1,0 +1,66 @@
+"""CPU tests of the drop-in boundary: libwbeuler.so loads, exports every symbol include/wbeuler.h
+declares, and fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "wbeuler.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(wb_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import wbeuler
+    return wbeuler.lib()
+
+
+def test_header_declares_the_reference_routines():
+    syms = declared_symbols()
+    for s in ("wb_fv2d_compute_update_exact", "wb_fv2d_compute_max_speed", "wb_fv2d_evolve", "wb_fv2d_create"):
+        assert s in syms
+
+
+def test_every_declared_symbol_is_exported(lib):
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"declared in include/wbeuler.h but not exported: {missing}"
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    import wbeuler
+    p = wbeuler.FV2DParams(64, 64, 3, 2, 1.4, 1.0, 1.0, 0.5, 0, -1, 0, 1)   # nvar = 3
+    h = C.c_void_p()
+    assert lib.wb_fv2d_create(C.byref(h), C.byref(p)) == -1
+    assert b"nvar" in lib.wb_last_error()
+    assert lib.wb_fv2d_create(None, None) == -1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the -m gpu tests")
+    import wbeuler
+    with pytest.raises(wbeuler.WBError) as e:
+        wbeuler.FV2D(32, 32)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under fvm-source-wb_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "fvm-source-wb_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90")):
+                if re.search(r"\boracle\b", open(os.path.join(d, f), errors="ignore").read()):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad

@@ -1,0 +1,189 @@
+"""GPU parity tests of the 2D well-balanced FV path (C-ABI -> CUDA) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): conserved fields within 1e-12 relative L-inf of the reference
+arithmetic; hydrostatic state preserved exactly (bitwise-zero RHS) wherever the reference does.
+For a bare RHS the 1e-12 bound is applied to the field it produces: |dt*(dudt - dudt_ref)| / max|u| with the
+CFL dt of the state, because dudt itself is a difference of O(1) fluxes divided by dx."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "fv2d.npz")
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def wb():
+    import __graft_entry__ as ge
+    ge.build()
+    import wbeuler
+    return wbeuler
+
+
+def setup(o, nx, ny, ninit, neq=2, **kw):
+    p = o.fv2d_params(nx, ny, neq, **kw)
+    x, y = o.fv2d_get_coords(p)
+    return p, o.fv2d_get_initial_conditions(p, ninit, x, y), o.fv2d_get_equilibrium_solution(p, x, y)
+
+
+def rel_linf_fields(a, b):
+    """max over the 4 conserved fields of Linf(a-b)/Linf(b) (fields that are identically 0 must match exactly)."""
+    worst = 0.0
+    for v in range(4):
+        den = np.abs(b[..., v]).max()
+        num = np.abs(a[..., v] - b[..., v]).max()
+        if den == 0.0:
+            assert num == 0.0
+        else:
+            worst = max(worst, num / den)
+    return worst
+
+
+def rhs_err(o, p, u, d, dref):
+    dt = 0.5 * (p.boxlen_x / p.nx) / o.fv2d_compute_max_speed(p, u) * p.cfl
+    return np.abs(dt * (d - dref)).max() / np.abs(u).max()
+
+
+SIZES = [(3, 3), (8, 5), (24, 24), (33, 20), (64, 64), (100, 37), (257, 130)]
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_compute_update_exact_matches_oracle(wb, oracle, nx, ny, arith):
+    p, u, weq = setup(oracle, nx, ny, 3)
+    dref = oracle.fv2d_compute_update_exact(p, u, weq)
+    with wb.FV2D(nx, ny, arith=arith) as s:
+        d = s.compute_update_exact(u, weq)
+    assert np.all(np.isfinite(d))
+    assert rhs_err(oracle, p, u, d, dref) <= TOL
+    # boundary lines frozen exactly
+    assert np.all(d[0] == 0) and np.all(d[-1] == 0) and np.all(d[:, 0] == 0) and np.all(d[:, -1] == 0)
+
+
+@pytest.mark.parametrize("nx,ny", [(24, 24), (100, 37)])
+def test_reference_order_kernel_is_nearly_bitwise(wb, oracle, nx, ny):
+    """arith=1 runs the reference's operation order; the only difference left is libm vs CUDA exp (<=1 ulp)
+    in the face equilibria, which the well-balanced form is insensitive to."""
+    p, u, weq = setup(oracle, nx, ny, 3)
+    dref = oracle.fv2d_compute_update_exact(p, u, weq)
+    with wb.FV2D(nx, ny, arith=1) as s:
+        d = s.compute_update_exact(u, weq)
+    assert rhs_err(oracle, p, u, d, dref) <= 1e-15
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("nx,ny,neq,ninit", [(32, 32, 2, 2), (64, 48, 2, 2), (130, 130, 1, 1), (50, 77, 2, 2)])
+def test_hydrostatic_state_rhs_is_bitwise_zero(wb, oracle, nx, ny, neq, ninit, arith):
+    p, u, weq = setup(oracle, nx, ny, ninit, neq)
+    with wb.FV2D(nx, ny, nequilibrium=neq, arith=arith) as s:
+        d = s.compute_update_exact(u, weq)
+        assert np.all(d == 0.0)
+        un, it, t, dt = s.evolve(u, weq, 1.0, 10)
+        assert it == 10 and np.array_equal(un, u)
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("nx,ny,ninit,steps", [(64, 64, 3, 10), (96, 130, 3, 6), (40, 40, 4, 8), (256, 256, 3, 4)])
+def test_evolve_matches_oracle(wb, oracle, nx, ny, ninit, steps, arith):
+    p, u, weq = setup(oracle, nx, ny, ninit)
+    ref, it, t, dt, cm = oracle.fv2d_evolve(p, u, weq, 1.0, steps)
+    with wb.FV2D(nx, ny, arith=arith) as s:
+        got, it2, t2, dt2 = s.evolve(u, weq, 1.0, steps)
+    assert it2 == it == steps
+    assert abs(t2 - t) <= 1e-13 * t and abs(dt2 - dt) <= 1e-13 * dt
+    assert rel_linf_fields(got, ref) <= TOL
+
+
+def test_evolve_until_tend_overshoots_like_the_reference(wb, oracle):
+    p, u, weq = setup(oracle, 32, 32, 3)
+    ref, it, t, dt, cm = oracle.fv2d_evolve(p, u, weq, 0.05, -1)
+    with wb.FV2D(32, 32) as s:
+        got, it2, t2, dt2 = s.evolve(u, weq, 0.05, -1)
+    assert it2 == it and t2 >= 0.05 and abs(t2 - t) <= 1e-13 * t
+    assert rel_linf_fields(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_compute_max_speed(wb, oracle, arith):
+    p, u, weq = setup(oracle, 70, 45, 4)
+    with wb.FV2D(70, 45, arith=arith) as s:
+        c = s.compute_max_speed(u)
+    cref = oracle.fv2d_compute_max_speed(p, u)
+    assert abs(c - cref) <= (4e-16 if arith == 0 else 0.0) * cref
+
+
+def test_plain_compute_update(wb, oracle):
+    p, u, weq = setup(oracle, 48, 40, 4)
+    dref = oracle.fv2d_compute_update(p, u, weq)
+    with wb.FV2D(48, 40, arith=1) as s:
+        d = s.compute_update(u, weq)
+    assert rhs_err(oracle, p, u, d, dref) <= 1e-15
+
+
+def test_golden_vectors(wb):
+    g = np.load(GOLD)
+    for tag in ("sq_pert", "ragged_pert", "riemann", "eq1"):
+        nx, ny, ninit, neq = (int(v) for v in g[f"{tag}_meta"])
+        u, weq = g[f"{tag}_u"], g[f"{tag}_weq"]
+        with wb.FV2D(nx, ny, nequilibrium=neq) as s:
+            got, it, t, dt = s.evolve(u, weq, 1.0, 3)
+        assert rel_linf_fields(got, g[f"{tag}_u3"]) <= TOL
+        assert it == int(g[f"{tag}_clock"][0]) and abs(t - g[f"{tag}_clock"][1]) <= 1e-13 * t
+
+
+def test_device_initial_conditions_match_reference_formulae(wb, oracle):
+    for ninit in (1, 2, 3, 4):
+        p, u, weq = setup(oracle, 64, 40, ninit)
+        with wb.FV2D(64, 40) as s:
+            ud, wd = s.get_initial_conditions(ninit)
+        assert np.abs(ud - u).max() <= 4e-16 * np.abs(u).max()     # libm vs CUDA exp
+        assert np.abs(wd - weq).max() <= 4e-16 * np.abs(weq).max()
+
+
+def test_resident_path_equals_evolve(wb, oracle):
+    p, u, weq = setup(oracle, 128, 96, 3)
+    with wb.FV2D(128, 96) as s:
+        a, it, t, dt = s.evolve(u, weq, 1.0, 7)
+        s.upload(u, weq)
+        s.step_async(3); s.step_async(4)
+        it2, t2, dt2, cm2 = s.sync()
+        b = s.download()
+    assert it2 == 7 and t2 == t and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n", [1024])
+def test_large_grid_rhs_against_oracle(wb, oracle, n):
+    p, u, weq = setup(oracle, n, n, 3)
+    dref = oracle.fv2d_compute_update_exact(p, u, weq)
+    with wb.FV2D(n, n) as s:
+        d = s.compute_update_exact(u, weq)
+    assert rhs_err(oracle, p, u, d, dref) <= TOL
+
+
+def test_full_size_4096_properties(wb):
+    """BASELINE config 3 size: properties that need no CPU run.
+    (1) device-initialised hydrostatic state stays bitwise unchanged; (2) fused and reference-order kernels
+    agree to 1e-12 on the perturbed state; (3) the x<->y mirror symmetry of the problem is kept."""
+    n = 4096
+    with wb.FV2D(n, n) as s:
+        s.init_device(2)
+        u0 = s.download()
+        s.step_async(3)
+        it, t, dt, cm = s.sync()
+        assert it == 3 and np.array_equal(s.download(), u0)
+        del u0
+        s.init_device(3)
+        s.step_async(3)
+        s.sync()
+        fast = s.download()
+    with wb.FV2D(n, n, arith=1) as s:
+        s.init_device(3)
+        s.step_async(3)
+        s.sync()
+        ref = s.download()
+    assert rel_linf_fields(fast, ref) <= TOL
+    sym = fast.transpose(1, 0, 2)[..., [0, 2, 1, 3]]
+    assert rel_linf_fields(sym, fast) <= TOL
