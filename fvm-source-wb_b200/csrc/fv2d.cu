@@ -13,6 +13,7 @@
 #include "fv2d_math.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace wb { namespace fv2d {
@@ -363,10 +364,11 @@ __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef
   double hc = 0.5 * fmax(a.spd, b.spd);
   FaceFlux o;
   // 0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)   (benchmark_2d.f90:366)
-  o.f0 = fma(hc, ar - br, 0.5 * (b.f0 + a.f0));
-  o.fn = fma(hc, ln - hn, 0.5 * (b.fn + a.fn));
-  o.ft = fma(hc, lt - ht, 0.5 * (b.ft + a.ft));
-  o.f3 = fma(hc, aE - bE, 0.5 * (b.f3 + a.f3));
+  // (kept unfused: a fused multiply-add here flips the last bit of an O(1) flux once in ~1e5 faces)
+  o.f0 = 0.5 * (b.f0 + a.f0) + hc * (ar - br);
+  o.fn = 0.5 * (b.fn + a.fn) + hc * (ln - hn);
+  o.ft = 0.5 * (b.ft + a.ft) + hc * (lt - ht);
+  o.f3 = 0.5 * (b.f3 + a.f3) + hc * (aE - bE);
   o.pf = P.gm1 * Ef;
   return o;
 }
@@ -514,6 +516,141 @@ __global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) k_stage_fast
   }
 }
 
+
+// ------------------------------------------------------------------------------------ fused marching stage
+// The production RK-stage kernel.  No shared memory, no block barriers:
+//   * a warp owns 32 consecutive columns and marches up a strip of rows; lane l evaluates the LEFT x-face
+//     and the TOP y-face of its cell in every row, so each face flux is computed exactly once;
+//   * the right x-face comes from lane l+1 by warp shuffle (lane 31 only feeds lane 30: 31 outputs / warp),
+//     the left neighbour's delta from lane l-1 (lane 0 loads its halo column itself);
+//   * the bottom y-face flux is carried in registers from the previous row;
+//   * rows j+2 are prefetched while row j is computed (software pipelining instead of occupancy).
+// HBM traffic per cell: read u (4 doubles) + (rho_e,E_e) (2) [+ u^n (4) in stage 2], write 4.
+constexpr int MARCH_WARPS = 4;      // warps per CTA (independent of each other)
+constexpr int MARCH_OUT = 31;       // output columns per warp
+
+struct Cell { double d0, d1, d2, d3, u0, u3, re; };   // delta, and what the source/update need of u, u_eq
+
+__device__ __forceinline__ Cell load_cell(const StageArgs& A, const Grid& g, size_t o) {
+  Cell c;
+  c.u0 = A.in[o];
+  c.d1 = A.in[g.plane + o];
+  c.d2 = A.in[2 * g.plane + o];
+  c.u3 = A.in[3 * g.plane + o];
+  c.re = A.eqz[o];
+  const double Ee = A.eqz[g.plane + o];
+  c.d0 = c.u0 - c.re;          // delta_u = u - u_eq   (benchmark_2d.f90:499); momenta of u_eq are zero
+  c.d3 = c.u3 - Ee;
+  return c;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, 4) k_stage_march(StageArgs A, Grid g, Phys P, int R) {
+  double dt = 0.0;
+  if (MODE != 0) {
+    if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
+      if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+        carry_forward(A.ctrl, A.parity);
+      return;
+    }
+    dt = step_dt(A.ctrl, A.parity, P);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+      bookkeeping<MODE>(A.ctrl, A.parity, dt);
+  }
+  const int lane = threadIdx.x & 31;
+  const int wc = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+  const int c0 = wc * MARCH_OUT;
+  if (c0 >= g.nx) return;                                  // whole warp: no barriers in this kernel
+  const int jb = A.row_begin + blockIdx.y * R;
+  const int je = min(jb + R, A.row_end);
+  if (jb >= je) return;
+  const int i = c0 + lane;
+  const int ic = min(i, g.nx - 1);
+  const int ih = max(c0 - 1, 0);                           // lane 0's halo column
+  // loadable local rows: ghost rows exist only where a neighbouring slab does
+  const int jmin = (g.j0 > 0) ? -1 : 0, jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
+  auto row_off = [&](int j) { return (size_t)(max(jmin, min(j, jmax)) + 1) * g.pitch; };
+  const double exf_i = A.exf[ic], exc_i = A.exc[ic];
+  const bool writer = (lane < MARCH_OUT) && (i < g.nx);
+  const bool col_interior = (i > 0) && (i < g.nx - 1);
+
+  Cell cur = load_cell(A, g, row_off(jb) + ic);
+  Cell nxt = load_cell(A, g, row_off(jb + 1) + ic);
+  FaceFlux Gb;
+  {
+    Cell bel = load_cell(A, g, row_off(jb - 1) + ic);
+    const double e = exc_i * A.eyf[jb];
+    Gb = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, cur.d0, cur.d2, cur.d1, cur.d3);
+  }
+  double spd = 0.0;
+  for (int j = jb; j < je; ++j) {
+    // ---- issue the loads of this iteration first: row j+2 (prefetch), lane-0 halo, u^n (stage 2)
+    const size_t o2 = row_off(j + 2) + ic;
+    const double p_u0 = A.in[o2], p_u1 = A.in[g.plane + o2], p_u2 = A.in[2 * g.plane + o2], p_u3 = A.in[3 * g.plane + o2];
+    const double p_re = A.eqz[o2], p_Ee = A.eqz[g.plane + o2];
+    const size_t o = row_off(j) + ic;
+    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    if (lane == 0) {
+      const size_t oh = row_off(j) + ih;
+      h0 = A.in[oh] - A.eqz[oh];
+      h1 = A.in[g.plane + oh];
+      h2 = A.in[2 * g.plane + oh];
+      h3 = A.in[3 * g.plane + oh] - A.eqz[g.plane + oh];
+    }
+    double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    if (MODE == 2) { b0 = A.base[o]; b1 = A.base[g.plane + o]; b2 = A.base[2 * g.plane + o]; b3 = A.base[3 * g.plane + o]; }
+
+    // ---- top y-face (j+1): low side = this cell, high side = the cell above; normal = y
+    const double ey = exc_i * A.eyf[min(j + 1, g.nyl)];
+    const FaceFlux Gt = face_llf(P, P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3);
+    // ---- left x-face (i): low side = left neighbour (lane-1 / halo), high side = this cell; normal = x
+    double l0 = __shfl_up_sync(0xffffffffu, cur.d0, 1), l1 = __shfl_up_sync(0xffffffffu, cur.d1, 1);
+    double l2 = __shfl_up_sync(0xffffffffu, cur.d2, 1), l3 = __shfl_up_sync(0xffffffffu, cur.d3, 1);
+    if (lane == 0) { l0 = h0; l1 = h1; l2 = h2; l3 = h3; }
+    const double ex = exf_i * A.eyc[min(j, g.nyl - 1)];
+    const FaceFlux Fl = face_llf(P, P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3);
+    // ---- right x-face (i+1) from lane+1
+    const double r0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1), rn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
+    const double rt = __shfl_down_sync(0xffffffffu, Fl.ft, 1), r3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
+    const double rp = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
+
+    // ---- dudt in the reference's order (benchmark_2d.f90:601-607); x-mom: F=fn, G=ft; y-mom: F=ft, G=fn
+    const int jg = g.j0 + j;
+    const bool interior = col_interior && (jg > 0) && (jg < g.ny - 1);
+    double d0 = -((r0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
+    double d1 = -((rn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
+    double d2 = -((rt - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
+    double d3 = -((r3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
+    d1 = (d1 - cur.u0) + cur.re;           // + s - s_eq,  s = (0,-rho,-rho,-rho(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
+    d2 = (d2 - cur.u0) + cur.re;
+    d3 = d3 - (cur.d1 + cur.d2);
+    d1 = d1 + (rp - Fl.pf) * P.odx;        // + (F_eq(i+1)-F_eq(i))/dx
+    d2 = d2 + (Gt.pf - Gb.pf) * P.ody;     // + (G_eq(j+1)-G_eq(j))/dy
+    if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // frozen boundary lines :611-614
+    double n0, n1, n2, n3;
+    if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
+    if (MODE == 1) { n0 = fma(dt, d0, cur.u0); n1 = fma(dt, d1, cur.d1); n2 = fma(dt, d2, cur.d2); n3 = fma(dt, d3, cur.u3); }
+    if (MODE == 2) {
+      const double hdt = 0.5 * dt;
+      n0 = fma(hdt, d0, 0.5 * (b0 + cur.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + cur.d1));
+      n2 = fma(hdt, d2, 0.5 * (b2 + cur.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + cur.u3));
+    }
+    if (writer) {
+      A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
+      if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
+    }
+    // ---- rotate the pipeline
+    Gb = Gt;
+    cur = nxt;
+    nxt.u0 = p_u0; nxt.d1 = p_u1; nxt.d2 = p_u2; nxt.u3 = p_u3; nxt.re = p_re;
+    nxt.d0 = p_u0 - p_re; nxt.d3 = p_u3 - p_Ee;
+  }
+  if (MODE == 2) {
+    spd = warp_max(spd);
+    if (lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);
+  }
+}
+
 }}  // namespace wb::fv2d
 
 // ============================================================================================ host side
@@ -535,6 +672,8 @@ struct wb_fv2d {
   bool fast_ok = true;          // supplied equilibrium has zero velocity -> fused kernels usable
   int parity = 0;
   wb::Nccl* comm = nullptr;
+  int kernel_variant = 0;       // 0 = marching kernel (production), 1 = shared-memory tiled kernel (kept for A/B)
+  int march_rows = 32;          // rows per strip of the marching kernel
 };
 
 namespace {
@@ -623,7 +762,12 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
   A.row_begin = 0; A.row_end = h->g.nyl;
-  if (use_fast(h) && wb_scheme) {
+  if (use_fast(h) && wb_scheme && h->kernel_variant == 0) {
+    const int R = h->march_rows;
+    const int ncols = (h->g.nx + MARCH_OUT - 1) / MARCH_OUT;
+    dim3 b(MARCH_WARPS * 32), gr((ncols + MARCH_WARPS - 1) / MARCH_WARPS, (A.row_end - A.row_begin + R - 1) / R);
+    k_stage_march<MODE><<<gr, b, 0, h->stream>>>(A, h->g, h->phys, R);
+  } else if (use_fast(h) && wb_scheme) {
     dim3 b(FTX, FTY), gr((h->g.nx + FTX - 1) / FTX, (h->g.nyl + FTY - 1) / FTY);
     size_t smem = sizeof(FastSmem<FTX, FTY>);
     k_stage_fast<FTX, FTY, MODE><<<gr, b, smem, h->stream>>>(A, h->g, h->phys);
@@ -677,6 +821,8 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   wb_fv2d* h = new wb_fv2d;
   h->prm = *p;
   h->dev = dev;
+  if (const char* e = getenv("WB_FV2D_KERNEL")) h->kernel_variant = atoi(e);
+  if (const char* e = getenv("WB_FV2D_MARCH_ROWS")) h->march_rows = std::max(1, atoi(e));
   fill_phys(*p, h->phys);
   Grid& g = h->g;
   g.nx = p->nx; g.ny = p->ny;

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def fv2d():
     out = {}
     for tag, nx, ny, ninit, neq in (("sq_pert", 24, 24, 3, 2), ("ragged_pert", 33, 20, 3, 2),
-                                    ("riemann", 16, 40, 4, 2), ("eq1", 20, 24, 1, 1)):
+                                    ("riemann", 40, 40, 4, 2), ("riemann_ragged", 32, 24, 4, 2), ("eq1", 20, 24, 1, 1)):
         p = o.fv2d_params(nx, ny, neq)
         x, y = o.fv2d_get_coords(p)
         weq = o.fv2d_get_equilibrium_solution(p, x, y)

@@ -120,7 +120,7 @@ def test_threads_do_not_change_results(oracle):
 
 def test_golden_vectors(oracle):
     g = np.load(GOLD)
-    for tag in ("sq_pert", "ragged_pert", "riemann", "eq1"):
+    for tag in ("sq_pert", "ragged_pert", "riemann", "riemann_ragged", "eq1"):
         nx, ny, ninit, neq = (int(v) for v in g[f"{tag}_meta"])
         p = oracle.fv2d_params(nx, ny, neq)
         u, weq = g[f"{tag}_u"], g[f"{tag}_weq"]
