@@ -528,126 +528,148 @@ __global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) k_stage_fast
 // HBM traffic per cell: read u (4 doubles) + (rho_e,E_e) (2) [+ u^n (4) in stage 2], write 4.
 constexpr int MARCH_WARPS = 4;      // warps per CTA (independent of each other)
 constexpr int MARCH_OUT = 31;       // output columns per warp
+#ifndef MARCH_MIN_BLOCKS
+#define MARCH_MIN_BLOCKS 4
+#endif
 
+struct Raw { double u0, u1, u2, u3, re, Ee; };       // one cell as loaded: u (4 planes) and (rho_e, E_e)
 struct Cell { double d0, d1, d2, d3, u0, u3, re; };   // delta, and what the source/update need of u, u_eq
 
-__device__ __forceinline__ Cell load_cell(const StageArgs& A, const Grid& g, size_t o) {
+__device__ __forceinline__ Raw load_raw(const StageArgs& A, const Grid& g, size_t o) {
+  Raw r;
+  r.u0 = A.in[o]; r.u1 = A.in[g.plane + o]; r.u2 = A.in[2 * g.plane + o]; r.u3 = A.in[3 * g.plane + o];
+  r.re = A.eqz[o]; r.Ee = A.eqz[g.plane + o];
+  return r;
+}
+// delta_u = u - u_eq (benchmark_2d.f90:499); the momenta of u_eq are zero
+__device__ __forceinline__ Cell make_cell(const Raw& r) {
   Cell c;
-  c.u0 = A.in[o];
-  c.d1 = A.in[g.plane + o];
-  c.d2 = A.in[2 * g.plane + o];
-  c.u3 = A.in[3 * g.plane + o];
-  c.re = A.eqz[o];
-  const double Ee = A.eqz[g.plane + o];
-  c.d0 = c.u0 - c.re;          // delta_u = u - u_eq   (benchmark_2d.f90:499); momenta of u_eq are zero
-  c.d3 = c.u3 - Ee;
+  c.u0 = r.u0; c.d1 = r.u1; c.d2 = r.u2; c.u3 = r.u3; c.re = r.re;
+  c.d0 = r.u0 - r.re;
+  c.d3 = r.u3 - r.Ee;
   return c;
 }
 
+// Per-thread constants of the marching loop.
+struct MarchCtx {
+  int lane, ic, ih, jmin, jmax;
+  bool writer, col_interior;
+  double exf_i, exc_i, dt;
+};
+
+// One row of the march.  `cur` is the cell of row j, `nraw` holds row j+1 as loaded one call ago and is
+// refilled with row j+2; `hraw` likewise for lane 0's halo column; `Gb` is the bottom face flux (in) and
+// `Gt` the top face flux (out).  The caller alternates (cur,Gb) <-> (nxt,Gt) so that no register is moved.
 template <int MODE>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, 4) k_stage_march(StageArgs A, Grid g, Phys P, int R) {
-  double dt = 0.0;
+__device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, const Phys& P, const MarchCtx& c, int j,
+                                          const Cell& cur, Cell& nxt, Raw& nraw, Raw& hraw, const FaceFlux& Gb,
+                                          FaceFlux& Gt, double& spd) {
+  auto row_off = [&](int jj) { return (size_t)(max(c.jmin, min(jj, c.jmax)) + 1) * g.pitch; };
+  // ---- rows loaded during the previous call become usable now ...
+  nxt = make_cell(nraw);
+  const Cell hal = make_cell(hraw);
+  // ---- ... and this row's loads are issued before any arithmetic: row j+2, lane 0's halo of row j+1, u^n of
+  //      row j (stage 2).  They are consumed one row (~250 FP64 instructions) later.
+  nraw = load_raw(A, g, row_off(j + 2) + c.ic);
+  if (c.lane == 0) hraw = load_raw(A, g, row_off(j + 1) + c.ih);
+  const size_t o = row_off(j) + c.ic;
+  double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  if (MODE == 2) { b0 = A.base[o]; b1 = A.base[g.plane + o]; b2 = A.base[2 * g.plane + o]; b3 = A.base[3 * g.plane + o]; }
+
+  // ---- top y-face (j+1): low side = this cell, high side = the cell above; normal = y
+  const double ey = c.exc_i * A.eyf[min(j + 1, g.nyl)];
+  Gt = face_llf(P, P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3);
+  // ---- left x-face (i): low side = left neighbour (lane-1 / halo), high side = this cell; normal = x
+  double l0 = __shfl_up_sync(0xffffffffu, cur.d0, 1), l1 = __shfl_up_sync(0xffffffffu, cur.d1, 1);
+  double l2 = __shfl_up_sync(0xffffffffu, cur.d2, 1), l3 = __shfl_up_sync(0xffffffffu, cur.d3, 1);
+  if (c.lane == 0) { l0 = hal.d0; l1 = hal.d1; l2 = hal.d2; l3 = hal.d3; }
+  const double ex = c.exf_i * A.eyc[min(j, g.nyl - 1)];
+  const FaceFlux Fl = face_llf(P, P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3);
+  // ---- right x-face (i+1) from lane+1
+  const double r0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1), rn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
+  const double rt = __shfl_down_sync(0xffffffffu, Fl.ft, 1), r3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
+  const double rp = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
+
+  // ---- dudt in the reference's order (benchmark_2d.f90:601-607); x-mom: F=fn, G=ft; y-mom: F=ft, G=fn
+  const int jg = g.j0 + j;
+  const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
+  double d0 = -((r0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
+  double d1 = -((rn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
+  double d2 = -((rt - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
+  double d3 = -((r3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
+  d1 = (d1 - cur.u0) + cur.re;           // + s - s_eq,  s = (0,-rho,-rho,-rho(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
+  d2 = (d2 - cur.u0) + cur.re;
+  d3 = d3 - (cur.d1 + cur.d2);
+  d1 = d1 + (rp - Fl.pf) * P.odx;        // + (F_eq(i+1)-F_eq(i))/dx
+  d2 = d2 + (Gt.pf - Gb.pf) * P.ody;     // + (G_eq(j+1)-G_eq(j))/dy
+  if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // frozen boundary lines :611-614
+  double n0, n1, n2, n3;
+  if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
+  if (MODE == 1) { n0 = fma(c.dt, d0, cur.u0); n1 = fma(c.dt, d1, cur.d1); n2 = fma(c.dt, d2, cur.d2); n3 = fma(c.dt, d3, cur.u3); }
+  if (MODE == 2) {
+    const double hdt = 0.5 * c.dt;
+    n0 = fma(hdt, d0, 0.5 * (b0 + cur.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + cur.d1));
+    n2 = fma(hdt, d2, 0.5 * (b2 + cur.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + cur.u3));
+  }
+  if (c.writer) {
+    A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
+    if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, MARCH_MIN_BLOCKS) k_stage_march(StageArgs A, Grid g, Phys P, int R) {
+  MarchCtx c;
+  c.dt = 0.0;
   if (MODE != 0) {
     if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
       if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
         carry_forward(A.ctrl, A.parity);
       return;
     }
-    dt = step_dt(A.ctrl, A.parity, P);
+    c.dt = step_dt(A.ctrl, A.parity, P);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
-      bookkeeping<MODE>(A.ctrl, A.parity, dt);
+      bookkeeping<MODE>(A.ctrl, A.parity, c.dt);
   }
-  const int lane = threadIdx.x & 31;
+  c.lane = threadIdx.x & 31;
   const int wc = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
   const int c0 = wc * MARCH_OUT;
   if (c0 >= g.nx) return;                                  // whole warp: no barriers in this kernel
   const int jb = A.row_begin + blockIdx.y * R;
   const int je = min(jb + R, A.row_end);
   if (jb >= je) return;
-  const int i = c0 + lane;
-  const int ic = min(i, g.nx - 1);
-  const int ih = max(c0 - 1, 0);                           // lane 0's halo column
+  const int i = c0 + c.lane;
+  c.ic = min(i, g.nx - 1);
+  c.ih = max(c0 - 1, 0);                                   // lane 0's halo column
   // loadable local rows: ghost rows exist only where a neighbouring slab does
-  const int jmin = (g.j0 > 0) ? -1 : 0, jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
-  auto row_off = [&](int j) { return (size_t)(max(jmin, min(j, jmax)) + 1) * g.pitch; };
-  const double exf_i = A.exf[ic], exc_i = A.exc[ic];
-  const bool writer = (lane < MARCH_OUT) && (i < g.nx);
-  const bool col_interior = (i > 0) && (i < g.nx - 1);
+  c.jmin = (g.j0 > 0) ? -1 : 0;
+  c.jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
+  auto row_off = [&](int j) { return (size_t)(max(c.jmin, min(j, c.jmax)) + 1) * g.pitch; };
+  c.exf_i = A.exf[c.ic];
+  c.exc_i = A.exc[c.ic];
+  c.writer = (c.lane < MARCH_OUT) && (i < g.nx);
+  c.col_interior = (i > 0) && (i < g.nx - 1);
 
-  Cell cur = load_cell(A, g, row_off(jb) + ic);
-  Cell nxt = load_cell(A, g, row_off(jb + 1) + ic);
-  FaceFlux Gb;
+  // ---- prologue: rows jb-1, jb, jb+1 and lane 0's halo of row jb; bottom face of the strip
+  Cell ca = make_cell(load_raw(A, g, row_off(jb) + c.ic)), cb;
+  Raw nraw = load_raw(A, g, row_off(jb + 1) + c.ic);
+  Raw hraw = load_raw(A, g, row_off(jb) + (c.lane == 0 ? c.ih : c.ic));
+  FaceFlux Ga, Gb2;
   {
-    Cell bel = load_cell(A, g, row_off(jb - 1) + ic);
-    const double e = exc_i * A.eyf[jb];
-    Gb = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, cur.d0, cur.d2, cur.d1, cur.d3);
+    const Cell bel = make_cell(load_raw(A, g, row_off(jb - 1) + c.ic));
+    const double e = c.exc_i * A.eyf[jb];
+    Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
   }
   double spd = 0.0;
-  for (int j = jb; j < je; ++j) {
-    // ---- issue the loads of this iteration first: row j+2 (prefetch), lane-0 halo, u^n (stage 2)
-    const size_t o2 = row_off(j + 2) + ic;
-    const double p_u0 = A.in[o2], p_u1 = A.in[g.plane + o2], p_u2 = A.in[2 * g.plane + o2], p_u3 = A.in[3 * g.plane + o2];
-    const double p_re = A.eqz[o2], p_Ee = A.eqz[g.plane + o2];
-    const size_t o = row_off(j) + ic;
-    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    if (lane == 0) {
-      const size_t oh = row_off(j) + ih;
-      h0 = A.in[oh] - A.eqz[oh];
-      h1 = A.in[g.plane + oh];
-      h2 = A.in[2 * g.plane + oh];
-      h3 = A.in[3 * g.plane + oh] - A.eqz[g.plane + oh];
-    }
-    double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    if (MODE == 2) { b0 = A.base[o]; b1 = A.base[g.plane + o]; b2 = A.base[2 * g.plane + o]; b3 = A.base[3 * g.plane + o]; }
-
-    // ---- top y-face (j+1): low side = this cell, high side = the cell above; normal = y
-    const double ey = exc_i * A.eyf[min(j + 1, g.nyl)];
-    const FaceFlux Gt = face_llf(P, P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3);
-    // ---- left x-face (i): low side = left neighbour (lane-1 / halo), high side = this cell; normal = x
-    double l0 = __shfl_up_sync(0xffffffffu, cur.d0, 1), l1 = __shfl_up_sync(0xffffffffu, cur.d1, 1);
-    double l2 = __shfl_up_sync(0xffffffffu, cur.d2, 1), l3 = __shfl_up_sync(0xffffffffu, cur.d3, 1);
-    if (lane == 0) { l0 = h0; l1 = h1; l2 = h2; l3 = h3; }
-    const double ex = exf_i * A.eyc[min(j, g.nyl - 1)];
-    const FaceFlux Fl = face_llf(P, P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3);
-    // ---- right x-face (i+1) from lane+1
-    const double r0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1), rn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
-    const double rt = __shfl_down_sync(0xffffffffu, Fl.ft, 1), r3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
-    const double rp = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
-
-    // ---- dudt in the reference's order (benchmark_2d.f90:601-607); x-mom: F=fn, G=ft; y-mom: F=ft, G=fn
-    const int jg = g.j0 + j;
-    const bool interior = col_interior && (jg > 0) && (jg < g.ny - 1);
-    double d0 = -((r0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
-    double d1 = -((rn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
-    double d2 = -((rt - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
-    double d3 = -((r3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
-    d1 = (d1 - cur.u0) + cur.re;           // + s - s_eq,  s = (0,-rho,-rho,-rho(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
-    d2 = (d2 - cur.u0) + cur.re;
-    d3 = d3 - (cur.d1 + cur.d2);
-    d1 = d1 + (rp - Fl.pf) * P.odx;        // + (F_eq(i+1)-F_eq(i))/dx
-    d2 = d2 + (Gt.pf - Gb.pf) * P.ody;     // + (G_eq(j+1)-G_eq(j))/dy
-    if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // frozen boundary lines :611-614
-    double n0, n1, n2, n3;
-    if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
-    if (MODE == 1) { n0 = fma(dt, d0, cur.u0); n1 = fma(dt, d1, cur.d1); n2 = fma(dt, d2, cur.d2); n3 = fma(dt, d3, cur.u3); }
-    if (MODE == 2) {
-      const double hdt = 0.5 * dt;
-      n0 = fma(hdt, d0, 0.5 * (b0 + cur.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + cur.d1));
-      n2 = fma(hdt, d2, 0.5 * (b2 + cur.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + cur.u3));
-    }
-    if (writer) {
-      A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
-      if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
-    }
-    // ---- rotate the pipeline
-    Gb = Gt;
-    cur = nxt;
-    nxt.u0 = p_u0; nxt.d1 = p_u1; nxt.d2 = p_u2; nxt.u3 = p_u3; nxt.re = p_re;
-    nxt.d0 = p_u0 - p_re; nxt.d3 = p_u3 - p_Ee;
+  int j = jb;
+  for (; j + 1 < je; j += 2) {           // two rows per trip: (ca,Ga)->(cb,Gb2)->(ca,Ga), no register rotation
+    march_row<MODE>(A, g, P, c, j, ca, cb, nraw, hraw, Ga, Gb2, spd);
+    march_row<MODE>(A, g, P, c, j + 1, cb, ca, nraw, hraw, Gb2, Ga, spd);
   }
+  if (j < je) march_row<MODE>(A, g, P, c, j, ca, cb, nraw, hraw, Ga, Gb2, spd);
   if (MODE == 2) {
     spd = warp_max(spd);
-    if (lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);
+    if (c.lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);
   }
 }
 
@@ -672,6 +694,9 @@ struct wb_fv2d {
   bool fast_ok = true;          // supplied equilibrium has zero velocity -> fused kernels usable
   int parity = 0;
   wb::Nccl* comm = nullptr;
+  cudaStream_t comm_stream = nullptr;   // slab mode: boundary rows + NCCL ghost exchange run here, overlapped with the interior
+  cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+  int overlap = 1;
   int kernel_variant = 0;       // 0 = marching kernel (production), 1 = shared-memory tiled kernel (kept for A/B)
   int march_rows = 32;          // rows per strip of the marching kernel
 };
@@ -724,7 +749,8 @@ int d2h_state(wb_fv2d* h, const double* soa, double* host) {
 }
 
 // ghost-row exchange of a 4-plane field with the slab neighbours (per-stage halo, NCCL send/recv)
-int exchange_ghost_rows(wb_fv2d* h, double* field, int nplanes) {
+int exchange_ghost_rows(wb_fv2d* h, double* field, int nplanes, cudaStream_t stream = nullptr) {
+  if (!stream) stream = h->stream;
   if (h->prm.nranks <= 1) return WB_OK;
   if (!h->comm) { set_error("nranks > 1 but wb_fv2d_comm_init was not called"); return WB_ERR_STATE; }
   HaloSeg lo[4], hi[4];
@@ -736,7 +762,7 @@ int exchange_ghost_rows(wb_fv2d* h, double* field, int nplanes) {
   }
   int lo_peer = h->prm.rank > 0 ? h->prm.rank - 1 : -1;
   int hi_peer = h->prm.rank < h->prm.nranks - 1 ? h->prm.rank + 1 : -1;
-  return nccl_halo_exchange_multi(h->comm, lo_peer, hi_peer, lo, nplanes, hi, nplanes, h->stream);
+  return nccl_halo_exchange_multi(h->comm, lo_peer, hi_peer, lo, nplanes, hi, nplanes, stream);
 }
 
 int prepare_eq(wb_fv2d* h) {
@@ -756,25 +782,28 @@ bool use_fast(const wb_fv2d* h) { return h->prm.arith == 0 && h->fast_ok; }
 
 template <int MODE>
 int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, double tend, int max_iter,
-                 bool wb_scheme = true) {
+                 bool wb_scheme = true, int row_begin = 0, int row_end = -1, cudaStream_t stream = nullptr) {
+  if (row_end < 0) row_end = h->g.nyl;
+  if (!stream) stream = h->stream;
+  if (row_begin >= row_end) return WB_OK;
   StageArgs A;
   A.in = in; A.base = base; A.out = out; A.weq = h->weq; A.eqz = h->eqz;
   A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
-  A.row_begin = 0; A.row_end = h->g.nyl;
+  A.row_begin = row_begin; A.row_end = row_end;
   if (use_fast(h) && wb_scheme && h->kernel_variant == 0) {
     const int R = h->march_rows;
     const int ncols = (h->g.nx + MARCH_OUT - 1) / MARCH_OUT;
     dim3 b(MARCH_WARPS * 32), gr((ncols + MARCH_WARPS - 1) / MARCH_WARPS, (A.row_end - A.row_begin + R - 1) / R);
-    k_stage_march<MODE><<<gr, b, 0, h->stream>>>(A, h->g, h->phys, R);
+    k_stage_march<MODE><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
   } else if (use_fast(h) && wb_scheme) {
-    dim3 b(FTX, FTY), gr((h->g.nx + FTX - 1) / FTX, (h->g.nyl + FTY - 1) / FTY);
+    dim3 b(FTX, FTY), gr((h->g.nx + FTX - 1) / FTX, (row_end - row_begin + FTY - 1) / FTY);
     size_t smem = sizeof(FastSmem<FTX, FTY>);
-    k_stage_fast<FTX, FTY, MODE><<<gr, b, smem, h->stream>>>(A, h->g, h->phys);
+    k_stage_fast<FTX, FTY, MODE><<<gr, b, smem, stream>>>(A, h->g, h->phys);
   } else {
-    dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
-    if (wb_scheme) k_stage_ref<MODE, true><<<gr, b, 0, h->stream>>>(A, h->g, h->phys);
-    else k_stage_ref<MODE, false><<<gr, b, 0, h->stream>>>(A, h->g, h->phys);
+    dim3 b(128), gr((h->g.nx + 127) / 128, row_end - row_begin);
+    if (wb_scheme) k_stage_ref<MODE, true><<<gr, b, 0, stream>>>(A, h->g, h->phys);
+    else k_stage_ref<MODE, false><<<gr, b, 0, stream>>>(A, h->g, h->phys);
   }
   WB_LAUNCH_CHECK();
   return WB_OK;
@@ -801,6 +830,27 @@ int reset_clock(wb_fv2d* h) {
   return launch_max_speed(h, h->u, 0);
 }
 
+// One RK stage in slab mode: the two boundary rows first (on the comm stream, followed by the NCCL send/recv of
+// those rows into the neighbours' ghost rows), the interior rows concurrently on the main stream.
+template <int MODE>
+int stage_with_exchange(wb_fv2d* h, const double* in, const double* base, double* out, double tend) {
+  const int nyl = h->g.nyl;
+  if (h->prm.nranks <= 1) return launch_stage<MODE>(h, in, base, out, tend, -1);
+  if (!h->overlap || nyl < 3) {
+    WB_CHECK(launch_stage<MODE>(h, in, base, out, tend, -1));
+    return exchange_ghost_rows(h, out, 4);
+  }
+  WB_CUDA(cudaEventRecord(h->ev_main, h->stream));               // inputs (and their ghosts) are ready
+  WB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 0, 1, h->comm_stream)));
+  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, nyl - 1, nyl, h->comm_stream)));
+  WB_CHECK(exchange_ghost_rows(h, out, 4, h->comm_stream));
+  WB_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
+  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 1, nyl - 1, h->stream)));
+  WB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));        // next stage needs the ghosts
+  return WB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -821,6 +871,7 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   wb_fv2d* h = new wb_fv2d;
   h->prm = *p;
   h->dev = dev;
+  if (const char* e = getenv("WB_FV2D_OVERLAP")) h->overlap = atoi(e);
   if (const char* e = getenv("WB_FV2D_KERNEL")) h->kernel_variant = atoi(e);
   if (const char* e = getenv("WB_FV2D_MARCH_ROWS")) h->march_rows = std::max(1, atoi(e));
   fill_phys(*p, h->phys);
@@ -835,6 +886,14 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   auto fail = [&](int s) { wb_fv2d_destroy(h); return s; };
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(WB_ERR_CUDA); }
   h->own_stream = true;
+  if (p->nranks > 1) {
+    if (cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("comm stream/event creation failed");
+      return fail(WB_ERR_CUDA);
+    }
+  }
   size_t fb = sizeof(double) * 4 * g.plane;
   cudaError_t e;
   if ((e = cudaMalloc(&h->u, fb)) != cudaSuccess || (e = cudaMalloc(&h->w1, fb)) != cudaSuccess ||
@@ -887,6 +946,9 @@ int wb_fv2d_destroy(wb_fv2d* h) {
   cudaFree(h->ctrl);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   delete h;
   return WB_OK;
 }
@@ -973,11 +1035,9 @@ int wb_fv2d_step_async(wb_fv2d* h, int nsteps, double tend) {
   WB_CUDA(cudaSetDevice(h->dev));
   for (int s = 0; s < nsteps; ++s) {
     // stage 1: w1 = u + dt*L(u)                                   benchmark_2d.f90:246-247
-    WB_CHECK(launch_stage<1>(h, h->u, nullptr, h->w1, tend, -1));
-    WB_CHECK(exchange_ghost_rows(h, h->w1, 4));
+    WB_CHECK(stage_with_exchange<1>(h, h->u, nullptr, h->w1, tend));
     // stage 2: u = .5u + .5w1 + .5dt*L(w1), fused max speed        benchmark_2d.f90:249-250, :241
-    WB_CHECK(launch_stage<2>(h, h->w1, h->u, h->u, tend, -1));
-    WB_CHECK(exchange_ghost_rows(h, h->u, 4));
+    WB_CHECK(stage_with_exchange<2>(h, h->w1, h->u, h->u, tend));
     if (h->prm.nranks > 1) WB_CHECK(nccl_allreduce_max_u64(h->comm, &h->ctrl->cmax_bits[h->parity ^ 1], 1, h->stream));
     h->parity ^= 1;
   }

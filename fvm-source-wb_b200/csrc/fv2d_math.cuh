@@ -126,7 +126,7 @@ __device__ __forceinline__ Eval eval_state(const Phys& P, double rho, double mn,
   double rm = (rho >= 1e-10) ? r : 1e10;
   double c2 = (P.gamma * pm) * rm;
   double cs = sqrt_pos(c2);
-  double vm = sqrt_pos(fmax(q, 1e-300));   // q == 0 gives 1e-150, absorbed by "+ cs"
+  double vm = sqrt_pos(q + 1e-300);        // q == 0 gives 1e-150, absorbed by "+ cs"; q > 1e-284 is unchanged
   o.spd = vm + cs;
   o.f0 = mn;
   o.fn = fma(vn, mn, p);
@@ -143,7 +143,7 @@ __device__ __forceinline__ double speed(const Phys& P, double rho, double mx, do
   double pm = fmax(p, 1e-10);
   double rm = (rho >= 1e-10) ? r : 1e10;
   double cs = sqrt_pos((P.gamma * pm) * rm);
-  double vm = sqrt_pos(fmax(q, 1e-300));
+  double vm = sqrt_pos(q + 1e-300);
   return vm + cs;
 }
 

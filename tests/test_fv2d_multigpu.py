@@ -1,0 +1,30 @@
+"""Slab decomposition over >=2 GPUs (NCCL ghost-row exchange inside libwbeuler).  Needs 2 GPUs: on a 1-GPU box the
+test is skipped; the world_size-2 host logic is covered on CPU by tests/test_dist_gloo.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("nx,ny,steps", [(96, 70, 6), (130, 257, 4)])
+def test_slab_evolve_equals_single_gpu_and_oracle(nx, ny, steps):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import __graft_entry__ as ge
+    ge.build()
+    world = 2 if n < 4 else 4
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "slab_parity.py"), str(nx), str(ny), str(steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
