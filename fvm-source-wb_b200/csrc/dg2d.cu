@@ -1,0 +1,1150 @@
+// 2D modal DG (tensor Legendre basis, Gauss-Legendre quadrature) RK-stage kernels + C-ABI.
+// Replaces 2d/benchmark_2d_dg.f90: evolve :624-775, compute_max_speed :826-870, compute_update :1137-1479,
+// apply_limiter :1516-1555, the transforms :497-592, and the limiters of 2d/limiters.f90 it dispatches to
+// ('ONP' :478-654, 'HIO' :1441-1583, '1OR' :203-309, 'LOW' :769-860).
+//
+// Device layout: structure-of-arrays planes  plane(v, m)[jc*nx + ic],  m = jm*M + im, i.e.
+// [var][mode][row][column] with the element column contiguous -> one thread per element reads/writes
+// every plane coalesced.
+//
+// Arithmetic: this first version keeps the REFERENCE'S OPERATION ORDER everywhere (file compiled with
+// -fmad=false, IEEE div/sqrt): accumulation order of every quadrature sum, left-to-right products, the
+// real(4)-rounded RK coefficients.  With the basis tables computed by the same recurrences on the host the
+// results agree with the CPU restatement bit for bit.
+#include "common.cuh"
+#include "dg_basis.h"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace wb { namespace dg {
+
+struct DgGrid {
+  int nx, ny, m, nm;      // elements, order per direction, modes per element (m*m)
+  size_t ne;              // nx*ny
+};
+struct DgPhys {
+  double gamma, gm1a, gm1b;   // gamma, gamma-1.0 (real(4) literal) and gamma-1. -- the same value, kept apart for clarity
+  double oneoverdx, dx;
+  double eps, M;
+  double dt_num;              // cfl*min(1/9, gll_w_1/2)
+  int bc, source, flux_id, ninit;
+};
+struct DgCtrl {
+  double t, dt, tend;
+  int iter, max_iter, skip;
+  double cs_max, vx, vy, speed_max;
+  long long kstar;
+};
+
+#define PL(base, g, v, mode) ((base) + ((size_t)(v) * (g).nm + (mode)) * (g).ne)
+
+// ------------------------------------------------------------------------------------ pointwise physics
+// compute_primitive :891-902 (density floored at the real(4) literal 10e-10)
+__device__ __forceinline__ void prim(const DgPhys& P, const double u[4], double w[4]) {
+  w[0] = fmax(u[0], (double)10e-10f);
+  w[1] = u[1] / w[0];
+  w[2] = u[2] / w[0];
+  w[3] = P.gm1a * (u[3] - 0.5 * w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+// compute_conservative :905-917
+__device__ __forceinline__ void cons(const DgPhys& P, const double w[4], double u[4]) {
+  u[0] = w[0];
+  u[1] = w[0] * w[1];
+  u[2] = w[0] * w[2];
+  u[3] = w[3] / P.gm1b + 0.5 * (w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+// compute_flux :919-944 (volume nodes; flux(1) uses the floored density)
+__device__ __forceinline__ void flux_nodes(const DgPhys& P, const double u[4], double f1[4], double f2[4]) {
+  double w[4];
+  prim(P, u, w);
+  f2[0] = w[0] * w[2];
+  f2[1] = w[0] * w[1] * w[2];
+  f2[2] = w[2] * u[2] + w[3];
+  f2[3] = w[2] * u[3] + w[2] * w[3];
+  f1[0] = w[0] * w[1];
+  f1[1] = w[1] * u[1] + w[3];
+  f1[2] = w[0] * w[1] * w[2];
+  f1[3] = w[1] * u[3] + w[1] * w[3];
+}
+// compute_flux_int :946-965, one direction
+template <int DIR>
+__device__ __forceinline__ void flux_int(const DgPhys& P, const double u[4], double f[4]) {
+  double w[4];
+  prim(P, u, w);
+  if (DIR == 1) {
+    f[0] = w[1] * u[0];
+    f[1] = w[1] * u[1] + w[3];
+    f[2] = w[0] * w[1] * w[2];
+    f[3] = w[1] * u[3] + w[1] * w[3];
+  } else {
+    f[0] = w[2] * u[0];
+    f[1] = w[0] * w[1] * w[2];
+    f[2] = w[2] * u[2] + w[3];
+    f[3] = w[2] * u[3] + w[2] * w[3];
+  }
+}
+// compute_speed :872-889
+__device__ __forceinline__ void speed(const DgPhys& P, const double u[4], double& cs, double& vx, double& vy, double& spd) {
+  double w[4];
+  prim(P, u, w);
+  cs = sqrt(P.gamma * fmax(w[3], 1e-10) / fmax(w[0], 1e-10));
+  vx = w[1];
+  vy = w[2];
+  spd = sqrt(w[1] * w[1] + w[2] * w[2]) + cs;
+}
+// compute_num_flux :991-1006 -> compute_llflux :968-988; flux_id 0 leaves the flux at its initial 0
+template <int DIR>
+__device__ __forceinline__ void num_flux(const DgPhys& P, const double ul[4], const double ur[4], double nf[4]) {
+  if (P.flux_id != 1) { nf[0] = nf[1] = nf[2] = nf[3] = 0.0; return; }
+  double fl[4], fr[4], csl, csr, vxl, vyl, vxr, vyr, sl, sr;
+  flux_int<DIR>(P, ul, fl);
+  flux_int<DIR>(P, ur, fr);
+  speed(P, ul, csl, vxl, vyl, sl);
+  speed(P, ur, csr, vxr, vyr, sr);
+  double cmax = (DIR == 1) ? fmax(fabs(vxr + csr), fabs(vxl + csl)) : fmax(fabs(vyr + csr), fabs(vyl + csl));
+#pragma unroll
+  for (int v = 0; v < 4; ++v) nf[v] = 0.5 * (fr[v] + fl[v]) + 0.5 * cmax * (ul[v] - ur[v]);
+}
+
+// get_boundary_conditions :777-824 on a 0-based index that may be -1 or n
+__device__ __forceinline__ int bc_index(int bc, int idx, int n) {
+  if (bc == 1) { if (idx < 0) idx = n - 1; else if (idx >= n) idx = 0; }
+  else if (bc == 2 || bc == 3) { if (idx < 0) idx = 0; else if (idx >= n) idx = n - 1; }
+  return idx;
+}
+
+template <int M>
+__device__ __forceinline__ void load_modes(const double* __restrict__ u, const DgGrid& g, size_t e, double d[4][M][M]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = 0; i < M; ++i) d[v][i][j] = PL(u, g, v, j * M + i)[e];
+}
+
+// edge traces :1253-1314.  SIDE 0 left (xi=-1), 1 right (xi=+1): points along y; 2 bottom, 3 top: points along x.
+template <int M, int SIDE>
+__device__ __forceinline__ void trace(const double d[4][M][M], const Basis& B, double out[M][4]) {
+#pragma unroll
+  for (int q = 0; q < M; ++q)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) out[q][v] = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int q = 0; q < M; ++q)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (SIDE == 0) out[q][v] = out[q][v] + d[v][i][j] * B.Em[i] * B.P[q][j];
+          if (SIDE == 1) out[q][v] = out[q][v] + d[v][i][j] * B.Ep[i] * B.P[q][j];
+          if (SIDE == 2) out[q][v] = out[q][v] + d[v][i][j] * B.Em[j] * B.P[q][i];
+          if (SIDE == 3) out[q][v] = out[q][v] + d[v][i][j] * B.Ep[j] * B.P[q][i];
+        }
+}
+
+// ------------------------------------------------------------------------------------ layout kernels
+// host u(nvar,nx,ny,mx,my) == [mode][jc][ic][4]  <->  device planes
+__global__ void k_dg_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, DgGrid g) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int mode = blockIdx.y;
+  if (e >= g.ne) return;
+  const double2* src = reinterpret_cast<const double2*>(aos + ((size_t)mode * g.ne + e) * 4);
+  double2 a = src[0], b = src[1];
+  PL(soa, g, 0, mode)[e] = a.x; PL(soa, g, 1, mode)[e] = a.y; PL(soa, g, 2, mode)[e] = b.x; PL(soa, g, 3, mode)[e] = b.y;
+}
+__global__ void k_dg_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, DgGrid g) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int mode = blockIdx.y;
+  if (e >= g.ne) return;
+  double2* dst = reinterpret_cast<double2*>(aos + ((size_t)mode * g.ne + e) * 4);
+  dst[0] = make_double2(PL(soa, g, 0, mode)[e], PL(soa, g, 1, mode)[e]);
+  dst[1] = make_double2(PL(soa, g, 2, mode)[e], PL(soa, g, 3, mode)[e]);
+}
+
+// ------------------------------------------------------------------------------------ transforms :497-592
+template <int M>
+__global__ void k_nodes_from_modes(const double* __restrict__ modes, double* __restrict__ nodes, DgGrid g, Basis B) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  double d[4][M][M];
+  load_modes<M>(modes, g, e, d);
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) a = a + d[v][in][jn] * B.P[i][in] * B.P[j][jn];
+        PL(nodes, g, v, j * M + i)[e] = a;
+      }
+}
+template <int M>
+__device__ __forceinline__ void modes_from_nodes_el(const double nd[4][M][M], const Basis& B, double md[4][M][M]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int xq = 0; xq < M; ++xq)
+#pragma unroll
+          for (int yq = 0; yq < M; ++yq) a = a + 0.25 * nd[v][xq][yq] * B.P[xq][i] * B.P[yq][j] * B.wq[xq] * B.wq[yq];
+        md[v][i][j] = a;
+      }
+}
+template <int M>
+__device__ __forceinline__ void nodes_from_modes_el(const double md[4][M][M], const Basis& B, double nd[4][M][M]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) a = a + md[v][in][jn] * B.P[i][in] * B.P[j][jn];
+        nd[v][i][j] = a;
+      }
+}
+template <int M>
+__global__ void k_modes_from_nodes(const double* __restrict__ nodes, double* __restrict__ modes, DgGrid g, Basis B) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  double nd[4][M][M], md[4][M][M];
+  load_modes<M>(nodes, g, e, nd);
+  modes_from_nodes_el<M>(nd, B, md);
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = 0; i < M; ++i) PL(modes, g, v, j * M + i)[e] = md[v][i][j];
+}
+
+// grad_phi :1599-1644 at every node, once per upload (x, y are static)
+__global__ void k_grad_phi(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ gx,
+                           double* __restrict__ gy, size_t n, int grad_phi_case) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  if (grad_phi_case == 1) { gx[k] = x[k]; gy[k] = y[k]; return; }
+  const double epsilon = 0.25, delta_r = (double)0.1f, x_center = 3., y_center = 3.;
+  double x_dash = x[k] - x_center, y_dash = y[k] - y_center;
+  double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+  if (r > 0.5 - 0.5 * delta_r) {
+    gx[k] = -(x_dash) / ((r * r) * r);
+    gy[k] = -(y_dash) / ((r * r) * r);
+  } else {
+    gx[k] = -(x_dash) / (r * (r * r + epsilon * epsilon));
+    gy[k] = -(y_dash) / (r * (r * r + epsilon * epsilon));
+  }
+}
+// special_boundary_conditions :1481-1514 (ninit == 12): freeze flags per (mode index, element)
+__global__ void k_freeze_mask(const double* __restrict__ x, const double* __restrict__ y, unsigned char* __restrict__ fz,
+                              size_t n, double xc, double yc) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double xd = x[k] - xc, yd = y[k] - yc;
+  fz[k] = (sqrt(xd * xd + yd * yd) > 2.0) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------ compute_update :1137-1479
+template <int M>
+__global__ void __launch_bounds__(128) k_dg_update(const double* __restrict__ du, const double* __restrict__ gx,
+                                                   const double* __restrict__ gy, const unsigned char* __restrict__ fz,
+                                                   double* __restrict__ dudt, DgGrid g, DgPhys P, Basis B,
+                                                   const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  double d[4][M][M];
+  load_modes<M>(du, g, e, d);
+  // nodal values and fluxes at the volume quadrature points :1203-1204
+  double f1[4][M][M], f2[4][M][M], s[4][M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double uq[4], a1[4], a2[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        double a = 0.0;
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) a = a + d[v][in][jn] * B.P[i][in] * B.P[j][jn];
+        uq[v] = a;
+      }
+      flux_nodes(P, uq, a1, a2);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { f1[v][i][j] = a1[v]; f2[v][i][j] = a2[v]; }
+      // source at the node :1414-1424
+      if (P.source == 2) {
+        double w[4];
+        prim(P, uq, w);
+        double g1 = gx[(size_t)(j * M + i) * g.ne + e], g2 = gy[(size_t)(j * M + i) * g.ne + e];
+        s[0][i][j] = 0.;
+        s[1][i][j] = w[0] * g1;
+        s[2][i][j] = w[0] * g2;
+        s[3][i][j] = w[0] * (w[1] * g1 + w[2] * g2);
+      } else if (P.source == 3) {
+        s[0][i][j] = -1.0 * uq[0]; s[1][i][j] = 0.0; s[2][i][j] = 0.0; s[3][i][j] = 0.0;
+      } else {
+        s[0][i][j] = 0.0; s[1][i][j] = 0.0; s[2][i][j] = 0.0; s[3][i][j] = 0.0;
+      }
+    }
+  // own traces and the facing traces of the four neighbours :1253-1314; x-face neighbours are wrapped with ny
+  // (get_boundary_conditions(.,2) in the x sweep, :1338-1339; nx == ny is enforced at create)
+  double tl[M][4], tr[M][4], tb[M][4], tt[M][4];      // own left/right/bottom/top
+  trace<M, 0>(d, B, tl); trace<M, 1>(d, B, tr); trace<M, 2>(d, B, tb); trace<M, 3>(d, B, tt);
+  double FL[M][4], FR[M][4], GB[M][4], GT[M][4];
+  {
+    double nb[4][M][M], tn[M][4];
+    const int il = bc_index(P.bc, ic - 1, g.ny), ir = bc_index(P.bc, ic + 1, g.ny);
+    const int jb = bc_index(P.bc, jc - 1, g.ny), jt = bc_index(P.bc, jc + 1, g.ny);
+    load_modes<M>(du, g, (size_t)jc * g.nx + il, nb);
+    trace<M, 1>(nb, B, tn);                            // left neighbour's right trace
+#pragma unroll
+    for (int q = 0; q < M; ++q) num_flux<1>(P, tn[q], tl[q], FL[q]);
+    load_modes<M>(du, g, (size_t)jc * g.nx + ir, nb);
+    trace<M, 0>(nb, B, tn);                            // right neighbour's left trace
+#pragma unroll
+    for (int q = 0; q < M; ++q) num_flux<1>(P, tr[q], tn[q], FR[q]);
+    load_modes<M>(du, g, (size_t)jb * g.nx + ic, nb);
+    trace<M, 3>(nb, B, tn);                            // bottom neighbour's top trace
+#pragma unroll
+    for (int q = 0; q < M; ++q) num_flux<2>(P, tn[q], tb[q], GB[q]);
+    load_modes<M>(du, g, (size_t)jt * g.nx + ic, nb);
+    trace<M, 2>(nb, B, tn);                            // top neighbour's bottom trace
+#pragma unroll
+    for (int q = 0; q < M; ++q) num_flux<2>(P, tt[q], tn[q], GT[q]);
+  }
+  // volume, edge and source integrals per mode, then the update :1207-1244, :1372-1411, :1427-1466
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        double vol1 = 0.0, vol2 = 0.0, sv = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, e4 = 0.0;
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) vol1 = vol1 + f1[v][in][jn] * B.dP[in][i] * B.wq[in] * B.P[jn][j] * B.wq[jn];
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) vol2 = vol2 + f2[v][in][jn] * B.dP[jn][j] * B.wq[jn] * B.P[in][i] * B.wq[in];
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          e1 = e1 + FR[q][v] * B.Ep[i] * B.P[q][j] * B.wq[q];
+          e2 = e2 + FL[q][v] * B.Em[i] * B.P[q][j] * B.wq[q];
+        }
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          e3 = e3 + GT[q][v] * B.Ep[j] * B.P[q][i] * B.wq[q];
+          e4 = e4 + GB[q][v] * B.Em[j] * B.P[q][i] * B.wq[q];
+        }
+#pragma unroll
+        for (int in = 0; in < M; ++in)
+#pragma unroll
+          for (int jn = 0; jn < M; ++jn) sv = sv + s[v][in][jn] * B.P[in][i] * B.wq[in] * B.P[jn][j] * B.wq[jn];
+        double r = (P.oneoverdx * vol1 + P.oneoverdx * vol2 - P.oneoverdx * (e1 - e2) - P.oneoverdx * (e3 - e4)) / 2. + sv / 4.;
+        if (fz && fz[(size_t)(j * M + i) * g.ne + e]) r = 0.0;
+        PL(dudt, g, v, j * M + i)[e] = r;
+      }
+}
+
+// ------------------------------------------------------------------------------------ RK combinations :672-747
+// out = c0*A0 [+ c1*A1 [+ c2*A2 + c3*A3]] + (cd*dt)*D, evaluated left to right as the Fortran array expressions.
+// c0 == 1 with NA == 1 reproduces `delta_u + c*dt*dudt` (1.0*x == x exactly).
+template <int NA>
+__global__ void k_dg_axpy(double* __restrict__ out, const double* __restrict__ A0, double c0, const double* __restrict__ A1,
+                          double c1, const double* __restrict__ A2, double c2, const double* __restrict__ A3, double c3,
+                          const double* __restrict__ D, double cd, size_t n, const DgCtrl* __restrict__ ctrl) {
+  if (ctrl->skip) return;
+  const double cdt = cd * ctrl->dt;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    if (NA == 0) { out[k] = A0[k]; continue; }
+    double r = (NA == 1 && c0 == 1.0) ? A0[k] : c0 * A0[k];
+    if (NA >= 2) r = r + c1 * A1[k];
+    if (NA >= 4) { r = r + c2 * A2[k]; r = r + c3 * A3[k]; }
+    out[k] = r + cdt * D[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------ limiters (2d/limiters.f90)
+__device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }
+__device__ __forceinline__ double minmod(double x, double y, double z) {                       // :18-28
+  double s = sign1(x);
+  if (sign1(y) == s && sign1(z) == s) return s * fmin(fmin(fabs(x), fabs(y)), fabs(z));
+  return 0.0;
+}
+__device__ __forceinline__ double generalized_minmod(const DgPhys& P, double x, double y, double z) {  // :30-54
+  if (fabs(x) < P.M * (P.dx * P.dx)) return x;
+  return minmod(x, y, z);
+}
+__device__ __forceinline__ double minmod2d(double u, double dlx, double dly, double drx, double dry) {  // :57-78
+  double s = sign1(u);
+  if (sign1(dlx) == s && sign1(dly) == s && sign1(drx) == s && sign1(dry) == s)
+    return s * fmin(fmin(fmin(fmin(fabs(u), fabs(dly)), fabs(dlx)), fabs(dry)), fabs(drx));
+  return 0.0;
+}
+// solve_for_t :312-362
+__device__ __forceinline__ double solve_for_t(const DgPhys& P, const double u[4], const double ua[4]) {
+  const double eps = P.eps;
+  double pa = ua[0], mxa = ua[1], mya = ua[2], ea = ua[3];
+  double pj = u[0], mxj = u[1], myj = u[2], ej = u[3];
+  double a = 2.0 * (pj - pa) * (ej - ea) - (mxj - mxa) * (mxj - mxa) - (myj - mya) * (myj - mya);
+  double b = 2.0 * (pj - pa) * (ea - eps / (P.gamma - 1)) + 2.0 * pa * (ej - ea) - 2.0 * (mxa * (mxj - mxa) + mya * (myj - mya));
+  double c = 2.0 * pa * ea - (mxa * mxa + mya * mya) - 2.0 * eps * pa / P.gm1a;
+  b = b / a;
+  c = c / a;
+  double D = sqrt(fabs(b * b - 4 * c));
+  double t1 = 0.5 * (-b - D), t2 = 0.5 * (-b + D), t;
+  if ((t1 > -eps) && (t1 < (double)1.0f + eps)) t = t1;
+  else if ((t2 > -eps) && (t2 < (double)1.0f + eps)) t = t2;
+  else t = 0.0;
+  t = fmin(1.0, t);
+  t = fmax(0.0, t);
+  return t;
+}
+// compute_set :438-475: point (q, r) of the "left" family (GLL in x, GL in y) and of the "right" family
+template <int M>
+__device__ __forceinline__ void set_point(const double el[4][M][M], const Basis& B, int q, int r, double ul[4], double ur[4]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) { ul[v] = 0.0; ur[v] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        ul[v] = ul[v] + el[v][i][j] * B.Pg[r][i] * B.P[q][j];
+        ur[v] = ur[v] + el[v][i][j] * B.P[q][i] * B.Pg[r][j];
+      }
+}
+// compute_positivity ('ONP') :478-654, one element
+template <int M>
+__device__ __forceinline__ void positivity_el(const DgPhys& P, const Basis& B, double el[4][M][M]) {
+  if (M == 1) return;
+  const double uavg[4] = {el[0][0][0], el[1][0][0], el[2][0][0], el[3][0][0]};
+  // 1. density: theta from the minimum over the point set (the set is stored left family first, then right)
+  double p_min = 0.0;
+  bool first = true;
+  for (int fam = 0; fam < 2; ++fam)
+    for (int q = 0; q < M; ++q)
+      for (int r = 0; r < B.gll; ++r) {
+        double ul[4], ur[4];
+        set_point<M>(el, B, q, r, ul, ur);
+        double val = fam == 0 ? ul[0] : ur[0];
+        p_min = first ? val : fmin(p_min, val);
+        first = false;
+      }
+  const double theta = fmin(fabs((uavg[0] - P.eps) / (uavg[0] - p_min)), 1.0);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+      if (i != 0 || j != 0) el[0][i][j] = theta * el[0][i][j];
+  // 2. pressure
+  double t_min = 1.;
+  for (int fam = 0; fam < 2; ++fam)
+    for (int q = 0; q < M; ++q)
+      for (int r = 0; r < B.gll; ++r) {
+        double ul[4], ur[4], w[4], t;
+        set_point<M>(el, B, q, r, ul, ur);
+        const double* pt = fam == 0 ? ul : ur;
+        prim(P, pt, w);
+        if (w[3] > P.eps) t = 1.;
+        else t = solve_for_t(P, pt, uavg);
+        if (t_min >= t) t_min = t;
+      }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+      if (i != 0 || j != 0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) el[v][i][j] = t_min * el[v][i][j];
+      }
+}
+template <int M>
+__device__ __forceinline__ void store_modes(double* __restrict__ u, const DgGrid& g, size_t e, const double d[4][M][M]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = 0; i < M; ++i) PL(u, g, v, j * M + i)[e] = d[v][i][j];
+}
+template <int M>
+__global__ void k_limiter_onp(double* __restrict__ u, DgGrid g, DgPhys P, Basis B, const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  double el[4][M][M];
+  load_modes<M>(u, g, e, el);
+  positivity_el<M>(P, B, el);
+  store_modes<M>(u, g, e, el);
+}
+// limiter_low_order ('LOW') :769-860
+template <int M>
+__global__ void k_limiter_low(double* __restrict__ u, DgGrid g, const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne || M == 1) return;
+  for (int v = 0; v < 4; ++v) {
+    for (int j = 1; j < M; ++j) PL(u, g, v, j * M + 0)[e] = 0.0;
+    for (int i = 1; i < M; ++i) PL(u, g, v, 0 * M + i)[e] = 0.0;
+  }
+}
+// high_order_limiter ('HIO') :1478-1583 without its trailing compute_positivity (launched separately).
+// Reads the un-limited modes of the element and of its 4 neighbours from `u`, writes `un`.
+template <int M>
+__global__ void k_limiter_hio(const double* __restrict__ u, double* __restrict__ un, DgGrid g, DgPhys P,
+                              const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nx), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nx);
+  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
+  // mode (a,b), 1-based as in the reference -> plane index (b-1)*M + (a-1)
+#define MD(el, a, b) (PL(u, g, v, ((b) - 1) * M + ((a) - 1))[el])
+  for (int v = 0; v < 4; ++v) {
+    // u_new = u for this element/variable
+    for (int m = 0; m < M * M; ++m) PL(un, g, v, m)[e] = PL(u, g, v, m)[e];
+    auto limiting = [&](int a, int b) {                                              // :1441-1476
+      double coeff_j = (2.0 * (double)(a - 1) + 1.0) * (2 * (double)(b - 1) - 1);
+      double coeff_i = (2.0 * (double)(b - 1) + 1.0) * (2 * (double)(a - 1) - 1);
+      double coeff_u = (2.0 * (double)(a - 1) + 1.0) * (2.0 * (double)(b - 1) + 1.0);
+      double central_u = MD(e, a, b);
+      double d_r_y = (MD(eT, a, b - 1) - MD(e, a, b - 1)) * coeff_j;
+      double d_l_y = (MD(e, a, b - 1) - MD(eB, a, b - 1)) * coeff_j;
+      double d_r_x = (MD(eR, a - 1, b) - MD(e, a - 1, b)) * coeff_i;
+      double d_l_x = (MD(e, a - 1, b) - MD(eL, a - 1, b)) * coeff_i;
+      return minmod2d(central_u * coeff_u, d_r_y, d_l_y, d_r_x, d_l_x) / coeff_u;
+    };
+    int done = 0;
+    for (int a = M; a >= 2; --a) {
+      double limited = limiting(a, a);
+      if (limited != MD(e, a, a)) PL(un, g, v, (a - 1) * M + (a - 1))[e] = limited;
+      else break;
+      for (int b = a - 1; b >= 2; --b) {
+        double l1 = limiting(a, b), l2 = limiting(b, a);
+        if ((fabs(l1 - MD(e, a, b)) < P.eps) && (fabs(l2 - MD(e, b, a)) < P.eps)) { done = 1; break; }
+        PL(un, g, v, (b - 1) * M + (a - 1))[e] = l1;
+        PL(un, g, v, (a - 1) * M + (b - 1))[e] = l2;
+      }
+      if (done == 1) break;
+      double coeff_y = (2 * (double)(a - 1) + 1), coeff_u = (2 * (double)(a - 1) + 1);
+      double d_r_y = MD(eT, a - 1, 1) - MD(e, a - 1, 1);
+      double d_l_y = MD(e, a - 1, 1) - MD(eB, a - 1, 1);
+      double d_r_x = MD(eR, 1, a - 1) - MD(e, 1, a - 1);
+      double d_l_x = MD(e, 1, a - 1) - MD(eL, 1, a - 1);
+      double l1 = generalized_minmod(P, MD(e, 1, a) * coeff_u, d_r_y * coeff_y, d_l_y * coeff_y) / coeff_u;
+      double l2 = generalized_minmod(P, MD(e, a, 1) * coeff_u, d_r_x * coeff_y, d_l_x * coeff_y) / coeff_u;
+      if ((l1 == MD(e, 1, a)) && (l2 == MD(e, a, 1))) break;
+      PL(un, g, v, (a - 1) * M + 0)[e] = l1;      // u_new(1,a)
+      PL(un, g, v, 0 * M + (a - 1))[e] = l2;      // u_new(a,1)
+    }
+  }
+#undef MD
+}
+// compute_limiter ('1OR') :203-309, step A: modal PRIMITIVE variables w = modes(prim(nodes(u)))
+template <int M>
+__global__ void k_limiter_1or_a(const double* __restrict__ u, double* __restrict__ w, DgGrid g, DgPhys P, Basis B,
+                                const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  double md[4][M][M], nd[4][M][M];
+  load_modes<M>(u, g, e, md);
+  nodes_from_modes_el<M>(md, B, nd);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double uu[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]}, ww[4];
+      prim(P, uu, ww);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) nd[v][i][j] = ww[v];
+    }
+  modes_from_nodes_el<M>(nd, B, md);
+  store_modes<M>(w, g, e, md);
+}
+// step B: minmod on the linear modes against the neighbours' means, drop the higher modes, back to conservative modes
+template <int M>
+__global__ void k_limiter_1or_b(const double* __restrict__ w, double* __restrict__ u, DgGrid g, DgPhys P, Basis B,
+                                const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nx), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nx);
+  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
+  const double norm = 3.;
+  double md[4][M][M], nd[4][M][M];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) md[v][i][j] = 0.0;
+    const double c = PL(w, g, v, 0)[e];
+    md[v][0][0] = c;
+    if (M > 1) {
+      const double u21 = PL(w, g, v, 1)[e], u12 = PL(w, g, v, M)[e];
+      double l1 = generalized_minmod(P, norm * u21, (PL(w, g, v, 0)[eR] - c), (c - PL(w, g, v, 0)[eL])) / norm;
+      double l2 = generalized_minmod(P, norm * u12, (PL(w, g, v, 0)[eT] - c), (c - PL(w, g, v, 0)[eB])) / norm;
+      if ((fabs(l1 - u21) > (double)1E-6f) || fabs(l2 - u12) > (double)1E-6f) { md[v][1][0] = l1; md[v][0][1] = l2; }
+      else { md[v][0][1] = u12; md[v][1][0] = u21; }
+    }
+  }
+  nodes_from_modes_el<M>(md, B, nd);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double ww[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]}, uu[4];
+      cons(P, ww, uu);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) nd[v][i][j] = uu[v];
+    }
+  modes_from_nodes_el<M>(nd, B, md);
+  store_modes<M>(u, g, e, md);
+}
+
+// ------------------------------------------------------------------------------------ compute_max_speed :826-870
+// The reference scan (i outer, j inner; `>=` keeps the LAST maximum; every later cell with a smaller cs lowers
+// cs_max) in its commutative two-phase form:
+//   phase 1: (speed_max, k*) = lexicographic max of (speed, k), k = i*ny + j; v_x, v_y, cs taken at k*
+//   phase 2: cs_max = min(cs(k*), min of cs over k > k*)
+struct SpeedKey { double speed; long long k; double vx, vy, cs; };
+__device__ __forceinline__ bool key_less(const SpeedKey& a, const SpeedKey& b) {   // a < b
+  return (a.speed < b.speed) || (a.speed == b.speed && a.k < b.k);
+}
+__global__ void k_speed_phase1(const double* __restrict__ u, DgGrid g, DgPhys P, SpeedKey* __restrict__ part) {
+  SpeedKey best{-1.0, -1, 0.0, 0.0, 0.0};
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne; e += (size_t)gridDim.x * blockDim.x) {
+    const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+    double uu[4] = {PL(u, g, 0, 0)[e], PL(u, g, 1, 0)[e], PL(u, g, 2, 0)[e], PL(u, g, 3, 0)[e]};
+    SpeedKey c;
+    speed(P, uu, c.cs, c.vx, c.vy, c.speed);
+    c.k = (long long)ic * g.ny + jc;
+    if (key_less(best, c)) best = c;
+  }
+  __shared__ SpeedKey sh[256];
+  sh[threadIdx.x] = best;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s && key_less(sh[threadIdx.x], sh[threadIdx.x + s])) sh[threadIdx.x] = sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void k_speed_phase1b(const SpeedKey* __restrict__ part, int nparts, DgCtrl* ctrl) {
+  __shared__ SpeedKey sh[256];
+  SpeedKey best{-1.0, -1, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+    if (key_less(best, part[i])) best = part[i];
+  sh[threadIdx.x] = best;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s && key_less(sh[threadIdx.x], sh[threadIdx.x + s])) sh[threadIdx.x] = sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // speed_max starts at 0.0 and the test is `speed >= speed_max`: with non-negative speeds the first cell always enters
+    ctrl->speed_max = fmax(0.0, sh[0].speed);
+    ctrl->vx = sh[0].vx; ctrl->vy = sh[0].vy; ctrl->cs_max = sh[0].cs; ctrl->kstar = sh[0].k;
+  }
+}
+__global__ void k_speed_phase2(const double* __restrict__ u, DgGrid g, DgPhys P, const DgCtrl* __restrict__ ctrl,
+                               double* __restrict__ part) {
+  const long long kstar = ctrl->kstar;
+  double m = ctrl->cs_max;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne; e += (size_t)gridDim.x * blockDim.x) {
+    const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+    if ((long long)ic * g.ny + jc <= kstar) continue;
+    double uu[4] = {PL(u, g, 0, 0)[e], PL(u, g, 1, 0)[e], PL(u, g, 2, 0)[e], PL(u, g, 3, 0)[e]};
+    double cs, vx, vy, sp;
+    speed(P, uu, cs, vx, vy, sp);
+    m = fmin(m, cs);
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+// final: cs_max and the time step of evolve (:671) -- dt = min(tend-t, cfl*min(1/9, gll_w_1/2)/((|vx|+cs)/dx + (|vy|+cs)/dx))
+__global__ void k_speed_phase2b(const double* __restrict__ part, int nparts, DgCtrl* ctrl, DgPhys P, int set_dt) {
+  __shared__ double sh[256];
+  double m = ctrl->cs_max;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = fmin(m, part[i]);
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ctrl->cs_max = sh[0];
+    if (set_dt) {
+      const bool done = !(ctrl->t < ctrl->tend) || (ctrl->max_iter >= 0 && ctrl->iter >= ctrl->max_iter);
+      ctrl->skip = done ? 1 : 0;
+      if (!done) {
+        const double cs = sh[0];
+        ctrl->dt = fmin(ctrl->tend - ctrl->t, P.dt_num / ((fabs(ctrl->vx) + (cs)) / P.dx + (fabs(ctrl->vy) + (cs)) / P.dx));
+      }
+    }
+  }
+}
+__global__ void k_dg_advance(DgCtrl* ctrl) {
+  if (ctrl->skip) return;
+  ctrl->t = ctrl->t + ctrl->dt;
+  ctrl->iter = ctrl->iter + 1;
+}
+__global__ void k_dg_ctrl_init(DgCtrl* ctrl, double tend, int max_iter, int reset_clock) {
+  if (reset_clock) { ctrl->t = 0.0; ctrl->iter = 0; ctrl->dt = 0.0; }
+  ctrl->tend = tend; ctrl->max_iter = max_iter; ctrl->skip = 0;
+}
+
+}}  // namespace wb::dg
+
+// ============================================================================================ host side
+using namespace wb;
+using namespace wb::dg;
+
+struct wb_dg2d {
+  wb_dg2d_params prm;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  DgGrid g;
+  DgPhys phys;
+  Basis B;
+  size_t nfield = 0;                 // doubles per field (4*nm*ne)
+  double *du = nullptr, *A = nullptr, *Bf = nullptr, *C = nullptr, *D = nullptr, *E = nullptr;   // state, RK buffers, dudt, scratch
+  double *gx = nullptr, *gy = nullptr, *stage = nullptr, *xy = nullptr;
+  unsigned char* fz = nullptr;
+  DgCtrl* ctrl = nullptr;
+  DgCtrl* h_ctrl = nullptr;
+  SpeedKey* part1 = nullptr;
+  double* part2 = nullptr;
+  int nparts = 0;
+  bool resident = false;
+  bool have_xy = false;
+};
+
+namespace {
+
+#define DISPATCH_M(h, ...)                              \
+  switch ((h)->g.m) {                                   \
+    case 1: { constexpr int MM = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int MM = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int MM = 3; __VA_ARGS__; } break; \
+    default: { constexpr int MM = 4; __VA_ARGS__; } break; \
+  }
+
+inline dim3 elem_grid(const wb_dg2d* h, int block) { return dim3((unsigned)((h->g.ne + block - 1) / block)); }
+
+int dg_h2d_field(wb_dg2d* h, const double* host, double* soa) {
+  WB_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * h->nfield, cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
+  k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+int dg_d2h_field(wb_dg2d* h, const double* soa, double* host) {
+  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
+  k_dg_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * h->nfield, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+// x,y(nx,ny,mx,my) have the device layout already ([mode][jc][ic]); derive grad_phi / freeze mask from them
+int dg_set_xy(wb_dg2d* h, const double* x, const double* y) {
+  const size_t n = (size_t)h->g.nm * h->g.ne;
+  const bool need = (h->phys.source == 2) || (h->phys.ninit == 12);
+  h->have_xy = true;
+  if (!need) return WB_OK;
+  WB_REQUIRE(x && y, "x and y are required when source == 2 or ninit == 12");
+  WB_CUDA(cudaMemcpyAsync(h->xy, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->xy + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  dim3 b(256), gr((unsigned)((n + 255) / 256));
+  if (h->phys.source == 2) {
+    k_grad_phi<<<gr, b, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case);
+    WB_LAUNCH_CHECK();
+  }
+  if (h->phys.ninit == 12) {
+    k_freeze_mask<<<gr, b, 0, h->stream>>>(h->xy, h->xy + n, h->fz, n, h->prm.boxlen_x / 2., h->prm.boxlen_y / 2.);
+    WB_LAUNCH_CHECK();
+  }
+  return WB_OK;
+}
+
+int dg_update(wb_dg2d* h, const double* in, double* out, bool use_ctrl) {
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_dg_update<MM><<<gr, b, 0, h->stream>>>(in, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, out, h->g,
+                                                        h->phys, h->B, use_ctrl ? h->ctrl : nullptr));
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
+  const DgCtrl* c = use_ctrl ? h->ctrl : nullptr;
+  dim3 b(128), gr = elem_grid(h, 128);
+  if (h->g.m == 1) return WB_OK;           // every limiter returns early for mx == my == 1
+  switch (h->prm.limiter_id) {
+    case 1:
+      DISPATCH_M(h, k_limiter_onp<MM><<<gr, b, 0, h->stream>>>(u, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      break;
+    case 2:
+      DISPATCH_M(h, k_limiter_hio<MM><<<gr, b, 0, h->stream>>>(u, h->E, h->g, h->phys, c));
+      WB_LAUNCH_CHECK();
+      // u = u_new, then compute_positivity(u) (:1571-1574); a skipped step must not copy a stale scratch buffer
+      DISPATCH_M(h, k_limiter_onp<MM><<<gr, b, 0, h->stream>>>(h->E, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      {
+        dim3 gb((unsigned)std::min<size_t>((h->nfield + 255) / 256, 148 * 16));
+        k_dg_axpy<0><<<gb, 256, 0, h->stream>>>(u, h->E, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, h->E, 0.0, h->nfield,
+                                                c ? c : h->ctrl);
+        WB_LAUNCH_CHECK();
+      }
+      break;
+    case 3:
+      DISPATCH_M(h, k_limiter_1or_a<MM><<<gr, b, 0, h->stream>>>(u, h->E, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      DISPATCH_M(h, k_limiter_1or_b<MM><<<gr, b, 0, h->stream>>>(h->E, u, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      break;
+    case 4:
+      DISPATCH_M(h, k_limiter_low<MM><<<gr, b, 0, h->stream>>>(u, h->g, c));
+      WB_LAUNCH_CHECK();
+      break;
+    default: break;
+  }
+  return WB_OK;
+}
+
+// max speed of the mean mode of `u` into ctrl (and, if set_dt, the step's dt / skip flag)
+int dg_max_speed(wb_dg2d* h, const double* u, int set_dt) {
+  k_speed_phase1<<<h->nparts, 256, 0, h->stream>>>(u, h->g, h->phys, h->part1);
+  WB_LAUNCH_CHECK();
+  k_speed_phase1b<<<1, 256, 0, h->stream>>>(h->part1, h->nparts, h->ctrl);
+  WB_LAUNCH_CHECK();
+  k_speed_phase2<<<h->nparts, 256, 0, h->stream>>>(u, h->g, h->phys, h->ctrl, h->part2);
+  WB_LAUNCH_CHECK();
+  k_speed_phase2b<<<1, 256, 0, h->stream>>>(h->part2, h->nparts, h->ctrl, h->phys, set_dt);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+// real(4) literal promoted to real(8)
+#define F32(x) ((double)(x##f))
+
+int dg_axpy(wb_dg2d* h, int na, double* out, const double* A0, double c0, const double* A1, double c1, const double* A2,
+            double c2, const double* A3, double c3, const double* D, double cd) {
+  dim3 gb((unsigned)std::min<size_t>((h->nfield + 255) / 256, 148 * 16));
+  if (na == 1) k_dg_axpy<1><<<gb, 256, 0, h->stream>>>(out, A0, c0, A1, c1, A2, c2, A3, c3, D, cd, h->nfield, h->ctrl);
+  else if (na == 2) k_dg_axpy<2><<<gb, 256, 0, h->stream>>>(out, A0, c0, A1, c1, A2, c2, A3, c3, D, cd, h->nfield, h->ctrl);
+  else k_dg_axpy<4><<<gb, 256, 0, h->stream>>>(out, A0, c0, A1, c1, A2, c2, A3, c3, D, cd, h->nfield, h->ctrl);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+// one time step of evolve (:666-757)
+int dg_step(wb_dg2d* h) {
+  double *du = h->du, *A = h->A, *Bf = h->Bf, *C = h->C, *D = h->D;
+  WB_CHECK(dg_max_speed(h, du, 1));
+  const int solver = h->prm.solver_id;
+  if (solver == 3) {            // 'EQL' :672-681
+    WB_CHECK(dg_update(h, du, D, true));
+    WB_CHECK(dg_axpy(h, 1, A, du, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, D, 1.0));
+    WB_CHECK(dg_limiter(h, A, true));
+    WB_CHECK(dg_update(h, A, D, true));
+    WB_CHECK(dg_axpy(h, 2, du, du, 0.5, A, 0.5, nullptr, 0, nullptr, 0, D, 0.5));
+    WB_CHECK(dg_limiter(h, du, true));
+  } else if (solver == 1 || solver == 2) {   // 'RK4' :683-710 / 'SS4' :711-735 (identical real(4) coefficients)
+    WB_CHECK(dg_update(h, du, D, true));
+    WB_CHECK(dg_axpy(h, 1, A, du, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, D, F32(0.391752226571890)));          // w1
+    WB_CHECK(dg_limiter(h, A, true));
+    WB_CHECK(dg_update(h, A, D, true));
+    WB_CHECK(dg_axpy(h, 2, Bf, du, F32(0.444370493651235), A, F32(0.555629506348765), nullptr, 0, nullptr, 0, D,
+                     F32(0.368410593050371)));                                                                    // w2
+    WB_CHECK(dg_limiter(h, Bf, true));
+    WB_CHECK(dg_update(h, Bf, D, true));
+    WB_CHECK(dg_axpy(h, 2, A, du, F32(0.620101851488403), Bf, F32(0.379898148511597), nullptr, 0, nullptr, 0, D,
+                     F32(0.251891774271694)));                                                                    // w3 (over w1)
+    WB_CHECK(dg_limiter(h, A, true));
+    WB_CHECK(dg_update(h, A, D, true));
+    WB_CHECK(dg_axpy(h, 2, C, du, F32(0.178079954393132), A, F32(0.821920045606868), nullptr, 0, nullptr, 0, D,
+                     F32(0.544974750228521)));                                                                    // w4
+    WB_CHECK(dg_limiter(h, C, true));
+    // :700 recomputes compute_update(w3): D still holds exactly that result, so the launch is not repeated
+    WB_CHECK(dg_axpy(h, 4, Bf, du, F32(0.00683325884039), Bf, F32(0.51723167208978), A, F32(0.12759831133288), C,
+                     F32(0.34833675773694), D, F32(0.08460416338212)));                                           // w5 (over w2)
+    WB_CHECK(dg_update(h, C, D, true));
+    WB_CHECK(dg_axpy(h, 1, du, Bf, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, D, F32(0.22600748319395)));
+    WB_CHECK(dg_limiter(h, du, true));
+  } else {                      // 'DEB' :737-747
+    WB_CHECK(dg_update(h, du, D, true));
+    WB_CHECK(dg_axpy(h, 1, du, du, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, D, 1.0));
+    WB_CHECK(dg_limiter(h, du, true));
+  }
+  k_dg_advance<<<1, 1, 0, h->stream>>>(h->ctrl);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
+  if (!out || !p) { set_error("null argument"); return WB_ERR_ARG; }
+  *out = nullptr;
+  WB_REQUIRE(p->nvar == 4, "nvar must be 4 (got %d)", p->nvar);
+  WB_REQUIRE(p->nx >= 1 && p->ny >= 1, "nx, ny must be >= 1");
+  WB_REQUIRE(p->nx == p->ny, "nx == ny required: the reference wraps x-face neighbours with ny (2d/benchmark_2d_dg.f90:1338)");
+  WB_REQUIRE(p->mx == p->my, "mx == my required: the reference integrates the x edges with the x rule in y (:1378)");
+  WB_REQUIRE(p->mx >= 1 && p->mx <= MAXM, "mx must be 1..%d (got %d)", MAXM, p->mx);
+  WB_REQUIRE(p->bc >= 1 && p->bc <= 3, "bc must be 1..3");
+  WB_REQUIRE(p->source >= 1 && p->source <= 3, "source must be 1..3");
+  WB_REQUIRE(p->grad_phi_case == 1 || p->grad_phi_case == 2, "grad_phi_case must be 1 or 2");
+  WB_REQUIRE(p->flux_id == 0 || p->flux_id == 1, "flux_id must be 0 (as shipped) or 1 (llf1); hll2/hllc are not built yet");
+  WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 4, "limiter_id must be 0..4 (none, ONP, HIO, 1OR, LOW)");
+  WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
+  WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
+  int dev = 0;
+  WB_CHECK(select_device(p->device, &dev));
+  wb_dg2d* h = new wb_dg2d;
+  h->prm = *p;
+  h->dev = dev;
+  DgGrid& g = h->g;
+  g.nx = p->nx; g.ny = p->ny; g.m = p->mx; g.nm = p->mx * p->my; g.ne = (size_t)p->nx * p->ny;
+  h->nfield = (size_t)4 * g.nm * g.ne;
+  h->B = make_basis(p->mx);
+  DgPhys& P = h->phys;
+  P.gamma = p->gamma; P.gm1a = p->gamma - (double)1.0f; P.gm1b = p->gamma - (double)1.f;
+  P.dx = p->boxlen_x / (double)p->nx;
+  P.oneoverdx = 1. / P.dx;
+  P.eps = p->eps; P.M = p->M;
+  P.bc = p->bc; P.source = p->source; P.flux_id = p->flux_id; P.ninit = p->ninit;
+  {
+    const int gll = h->B.gll;
+    double gll_w_1 = (p->mx == 1) ? 1. : 1. / (double)((float)(gll * (gll - 1)) + 1e-10f);   // :651-655
+    P.dt_num = p->cfl * std::fmin(1. / (double)(2 * 4 + 1), gll_w_1 / 2.);                    // :671
+  }
+  auto fail = [&](int s) { wb_dg2d_destroy(h); return s; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(WB_ERR_CUDA); }
+  h->own_stream = true;
+  const size_t fb = sizeof(double) * h->nfield, nb = sizeof(double) * g.nm * g.ne;
+  h->nparts = (int)std::min<size_t>((g.ne + 255) / 256, 148 * 8);
+  cudaError_t e = cudaSuccess;
+  double** bufs[] = {&h->du, &h->A, &h->Bf, &h->C, &h->D, &h->E, &h->stage};
+  for (double** b : bufs)
+    if (e == cudaSuccess) e = cudaMalloc(b, fb);
+  if (e == cudaSuccess) e = cudaMalloc(&h->gx, nb);
+  if (e == cudaSuccess) e = cudaMalloc(&h->gy, nb);
+  if (e == cudaSuccess) e = cudaMalloc(&h->xy, 2 * nb);
+  if (e == cudaSuccess) e = cudaMalloc(&h->fz, (size_t)g.nm * g.ne);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ctrl, sizeof(DgCtrl));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(DgCtrl));
+  if (e == cudaSuccess) e = cudaMalloc(&h->part1, sizeof(SpeedKey) * h->nparts);
+  if (e == cudaSuccess) e = cudaMalloc(&h->part2, sizeof(double) * h->nparts);
+  if (e != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
+  cudaMemsetAsync(h->ctrl, 0, sizeof(DgCtrl), h->stream);
+  cudaMemsetAsync(h->gx, 0, nb, h->stream);
+  cudaMemsetAsync(h->gy, 0, nb, h->stream);
+  cudaMemsetAsync(h->fz, 0, (size_t)g.nm * g.ne, h->stream);
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
+  *out = h;
+  return WB_OK;
+}
+
+int wb_dg2d_destroy(wb_dg2d* h) {
+  if (!h) return WB_OK;
+  cudaSetDevice(h->dev);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->du); cudaFree(h->A); cudaFree(h->Bf); cudaFree(h->C); cudaFree(h->D); cudaFree(h->E); cudaFree(h->stage);
+  cudaFree(h->gx); cudaFree(h->gy); cudaFree(h->xy); cudaFree(h->fz); cudaFree(h->ctrl); cudaFree(h->part1); cudaFree(h->part2);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return WB_OK;
+}
+
+int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int wb_dg2d_quadrature(wb_dg2d* h, double* x_quad, double* w_quad) {
+  if (!h || !x_quad || !w_quad) { set_error("null argument"); return WB_ERR_ARG; }
+  for (int i = 0; i < h->g.m; ++i) { x_quad[i] = h->B.xq[i]; w_quad[i] = h->B.wq[i]; }
+  return WB_OK;
+}
+
+int wb_dg2d_get_modes_from_nodes(wb_dg2d* h, const double* nodes, double* modes) {
+  if (!h || !nodes || !modes) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  WB_CHECK(dg_h2d_field(h, nodes, h->A));
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_modes_from_nodes<MM><<<gr, b, 0, h->stream>>>(h->A, h->Bf, h->g, h->B));
+  WB_LAUNCH_CHECK();
+  return dg_d2h_field(h, h->Bf, modes);
+}
+
+int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes) {
+  if (!h || !nodes || !modes) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  WB_CHECK(dg_h2d_field(h, modes, h->A));
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_nodes_from_modes<MM><<<gr, b, 0, h->stream>>>(h->A, h->Bf, h->g, h->B));
+  WB_LAUNCH_CHECK();
+  return dg_d2h_field(h, h->Bf, nodes);
+}
+
+int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, const double* y, double* dudt) {
+  if (!h || !modes || !dudt) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  WB_CHECK(dg_set_xy(h, x, y));
+  WB_CHECK(dg_h2d_field(h, modes, h->A));
+  WB_CHECK(dg_update(h, h->A, h->D, false));
+  return dg_d2h_field(h, h->D, dudt);
+}
+
+int wb_dg2d_apply_limiter(wb_dg2d* h, double* modes_inout) {
+  if (!h || !modes_inout) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 0);
+  WB_LAUNCH_CHECK();
+  WB_CHECK(dg_h2d_field(h, modes_inout, h->A));
+  WB_CHECK(dg_limiter(h, h->A, false));
+  return dg_d2h_field(h, h->A, modes_inout);
+}
+
+int wb_dg2d_compute_max_speed(wb_dg2d* h, const double* mean_mode, double* cs_max, double* v_xmax, double* v_ymax,
+                              double* speed_max) {
+  if (!h || !mean_mode) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  // mean mode (nvar,nx,ny) -> planes (v, mode 0) of buffer A
+  WB_CUDA(cudaMemcpyAsync(h->stage, mean_mode, sizeof(double) * 4 * h->g.ne, cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), 1);
+  k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, h->A, h->g);
+  WB_LAUNCH_CHECK();
+  WB_CHECK(dg_max_speed(h, h->A, 0));
+  WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(DgCtrl), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (cs_max) *cs_max = h->h_ctrl->cs_max;
+  if (v_xmax) *v_xmax = h->h_ctrl->vx;
+  if (v_ymax) *v_ymax = h->h_ctrl->vy;
+  if (speed_max) *speed_max = h->h_ctrl->speed_max;
+  return WB_OK;
+}
+
+int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const double* y) {
+  if (!h || !u_nodes) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CHECK(dg_set_xy(h, x, y));
+  WB_CHECK(dg_h2d_field(h, u_nodes, h->A));
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_modes_from_nodes<MM><<<gr, b, 0, h->stream>>>(h->A, h->du, h->g, h->B));      // :644
+  WB_LAUNCH_CHECK();
+  k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
+  WB_LAUNCH_CHECK();
+  WB_CHECK(dg_limiter(h, h->du, false));                                                         // :659
+  h->resident = true;
+  return WB_OK;
+}
+
+int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state (call wb_dg2d_upload first)"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, tend, -1, 0);
+  WB_LAUNCH_CHECK();
+  for (int s = 0; s < nsteps; ++s) WB_CHECK(dg_step(h));
+  return WB_OK;
+}
+
+int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(DgCtrl), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (iters_out) *iters_out = h->h_ctrl->iter;
+  if (t_out) *t_out = h->h_ctrl->t;
+  if (last_dt_out) *last_dt_out = h->h_ctrl->dt;
+  return WB_OK;
+}
+
+int wb_dg2d_download_modes(wb_dg2d* h, double* modes_out) {
+  if (!h || !modes_out) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  return dg_d2h_field(h, h->du, modes_out);
+}
+
+int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out) {
+  if (!h || !u_nodes_out) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_nodes_from_modes<MM><<<gr, b, 0, h->stream>>>(h->du, h->A, h->g, h->B));      // :771
+  WB_LAUNCH_CHECK();
+  return dg_d2h_field(h, h->A, u_nodes_out);
+}
+
+int wb_dg2d_evolve(wb_dg2d* h, double* u_nodes_inout, const double* x, const double* y, double tend, int max_iter,
+                   int* iters_out, double* t_out, double* last_dt_out) {
+  if (!h || !u_nodes_inout) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CHECK(wb_dg2d_upload(h, u_nodes_inout, x, y));
+  int iters = 0;
+  double t = 0.0, dt = 0.0;
+  const int batch = 8;
+  for (;;) {
+    if (!(t < tend) || (max_iter >= 0 && iters >= max_iter)) break;
+    int n = batch;
+    if (max_iter >= 0 && max_iter - iters < n) n = max_iter - iters;
+    WB_CHECK(wb_dg2d_step_async(h, n, tend));
+    WB_CHECK(wb_dg2d_sync(h, &iters, &t, &dt));
+  }
+  WB_CHECK(wb_dg2d_download(h, u_nodes_inout));
+  if (iters_out) *iters_out = iters;
+  if (t_out) *t_out = t;
+  if (last_dt_out) *last_dt_out = dt;
+  return WB_OK;
+}
+
+}  // extern "C"

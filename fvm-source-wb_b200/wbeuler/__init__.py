@@ -176,3 +176,116 @@ class FV2D:
 
     def reset_clock(self):
         _check(lib().wb_fv2d_reset_clock(self._h))
+
+
+# ================================================================================================== 2D DG
+class DG2DParams(C.Structure):
+    """wb_dg2d_params (include/wbeuler.h); defaults follow 2d/parameters_dg_2d.f90:3-35."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("mx", C.c_int), ("my", C.c_int), ("nvar", C.c_int), ("bc", C.c_int),
+                ("source", C.c_int), ("grad_phi_case", C.c_int), ("flux_id", C.c_int), ("limiter_id", C.c_int),
+                ("solver_id", C.c_int), ("ninit", C.c_int), ("gamma", C.c_double), ("boxlen_x", C.c_double),
+                ("boxlen_y", C.c_double), ("cfl", C.c_double), ("eps", C.c_double), ("M", C.c_double), ("device", C.c_int)]
+
+
+LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4}     # limiter_type (2d/benchmark_2d_dg.f90:1516-1555)
+SOLVERS = {"RK4": 1, "SS4": 2, "EQL": 3, "DEB": 4}                 # solver (:672-747)
+FLUXES = {"llf": 0, "llf1": 1}                                     # flux_type; 'llf' is the shipped value that matches no branch
+
+
+class DG2D:
+    """2D modal DG (2d/benchmark_2d_dg.f90).  Arrays: u(nvar,nx,ny,mx,my) == numpy (my, mx, ny, nx, 4)."""
+
+    def __init__(self, nx=8, ny=8, mx=2, my=2, bc=1, source=1, grad_phi_case=2, flux="llf1", limiter="ONP", solver="RK4",
+                 ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, device=-1):
+        self.params = DG2DParams(nx, ny, mx, my, 4, bc, source, grad_phi_case, FLUXES[flux], LIMITERS[limiter],
+                                 SOLVERS[solver], ninit, gamma, boxlen_x, boxlen_y, cfl, eps, M, device)
+        self._h = C.c_void_p()
+        _check(lib().wb_dg2d_create(C.byref(self._h), C.byref(self.params)))
+        self.shape = (my, mx, ny, nx, 4)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().wb_dg2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().wb_dg2d_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def quadrature(self):
+        """gl_quadrature(x_quad, w_quad, mx)  2d/legendre.f90:77-108"""
+        x = np.zeros(self.params.mx); w = np.zeros(self.params.mx)
+        _check(lib().wb_dg2d_quadrature(self._h, _ptr(x), _ptr(w)))
+        return x, w
+
+    def get_modes_from_nodes(self, nodes):
+        """2d/benchmark_2d_dg.f90:497-542"""
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_get_modes_from_nodes(self._h, _ptr(nodes), _ptr(out)))
+        return out
+
+    def get_nodes_from_modes(self, modes):
+        """2d/benchmark_2d_dg.f90:544-592"""
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_get_nodes_from_modes(self._h, _ptr(modes), _ptr(out)))
+        return out
+
+    def compute_update(self, modes, x=None, y=None):
+        """compute_update(delta_u,x,y,u_eq,dudt)  2d/benchmark_2d_dg.f90:1137-1479"""
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_compute_update(self._h, _ptr(modes), _ptr(x) if x is not None else None,
+                                            _ptr(y) if y is not None else None, _ptr(out)))
+        return out
+
+    def apply_limiter(self, modes):
+        """apply_limiter(u)  2d/benchmark_2d_dg.f90:1516-1555"""
+        u = np.array(modes, dtype=np.float64, order="C", copy=True)
+        _check(lib().wb_dg2d_apply_limiter(self._h, _ptr(u)))
+        return u
+
+    def compute_max_speed(self, mean_mode):
+        """compute_max_speed(u(:,:,:,1,1),...)  2d/benchmark_2d_dg.f90:826-870 -> (cs_max, v_xmax, v_ymax, speed_max)"""
+        a = [C.c_double() for _ in range(4)]
+        mm = np.ascontiguousarray(mean_mode)
+        _check(lib().wb_dg2d_compute_max_speed(self._h, _ptr(mm), *[C.byref(v) for v in a]))
+        return tuple(v.value for v in a)
+
+    def evolve(self, u_nodes, x=None, y=None, tend=1.0, max_iter=-1):
+        """evolve(u,x,y,u_eq)  2d/benchmark_2d_dg.f90:624-775 -> (u_nodes_new, iters, t, last_dt)"""
+        u = np.array(u_nodes, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_dg2d_evolve(self._h, _ptr(u), _ptr(x) if x is not None else None, _ptr(y) if y is not None else None,
+                                    C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt)))
+        return u, it.value, t.value, dt.value
+
+    def upload(self, u_nodes, x=None, y=None):
+        _check(lib().wb_dg2d_upload(self._h, _ptr(u_nodes), _ptr(x) if x is not None else None, _ptr(y) if y is not None else None))
+
+    def step_async(self, nsteps, tend=1e300):
+        _check(lib().wb_dg2d_step_async(self._h, C.c_int(nsteps), C.c_double(tend)))
+
+    def sync(self):
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_dg2d_sync(self._h, C.byref(it), C.byref(t), C.byref(dt)))
+        return it.value, t.value, dt.value
+
+    def download(self):
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_download(self._h, _ptr(out)))
+        return out
+
+    def download_modes(self):
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_download_modes(self._h, _ptr(out)))
+        return out

@@ -106,6 +106,59 @@ int wb_fv2d_download(wb_fv2d* h, double* u_out);
 /* reset t = 0, iter = 0 and recompute the max wave speed of the resident state */
 int wb_fv2d_reset_clock(wb_fv2d* h);
 
+
+/* ==========================================================================================
+ * 2D modal discontinuous Galerkin -- 2d/benchmark_2d_dg.f90, 2d/legendre.f90, 2d/limiters.f90
+ * (module 2d/parameters_dg_2d.f90).  Host layout u(nvar,nx,ny,mx,my) == double[my][mx][ny][nx][4],
+ * x,y(nx,ny,mx,my) == double[my][mx][ny][nx].
+ * ========================================================================================== */
+typedef struct wb_dg2d wb_dg2d;
+
+typedef struct {
+  int nx, ny;            /* 2d/parameters_dg_2d.f90:3-4 (nx == ny required: the reference wraps x-face
+                            neighbours with ny, 2d/benchmark_2d_dg.f90:1338-1339)                      */
+  int mx, my;            /* :5-6, 1..4, mx == my required (the reference mixes the x and y rules)       */
+  int nvar;              /* must be 4                                                                    */
+  int bc;                /* :18   1 periodic, 2|3 index clamp                                            */
+  int source;            /* :20   1 none, 2 gravity (get_source + grad_phi), 3 advection sink            */
+  int grad_phi_case;     /* :21   1: g=(x,y) [sic], 2: softened Keplerian centred at (3,3)               */
+  int flux_id;           /* :15   0 = as shipped ('llf' matches no branch: numerical flux stays 0),
+                                  1 = 'llf1' local Lax-Friedrichs                                       */
+  int limiter_id;        /* :14   0 = use_limiter .false., 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW'            */
+  int solver_id;         /* :13   1 'RK4' SSPRK(5,4), 2 'SS4' (same after real(4) rounding), 3 'EQL' RK2,
+                                  4 'DEB' forward Euler                                                  */
+  int ninit;             /* :17   only used for special_boundary_conditions (ninit == 12)                */
+  double gamma, boxlen_x, boxlen_y, cfl, eps, M;   /* :23-35                                             */
+  int device;
+} wb_dg2d_params;
+
+int wb_dg2d_create(wb_dg2d** h, const wb_dg2d_params* p);
+int wb_dg2d_destroy(wb_dg2d* h);
+int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream);
+/* Gauss-Legendre nodes/weights exactly as gl_quadrature computes them (2d/legendre.f90:77-108) */
+int wb_dg2d_quadrature(wb_dg2d* h, double* x_quad, double* w_quad);
+/* replaces get_modes_from_nodes / get_nodes_from_modes   2d/benchmark_2d_dg.f90:497-542 / :544-592
+ * (also 2d/commons.f90, the routines 2d/test2d.f90 exercises) */
+int wb_dg2d_get_modes_from_nodes(wb_dg2d* h, const double* nodes, double* modes);
+int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes);
+/* replaces compute_update(delta_u,x,y,u_eq,dudt)   2d/benchmark_2d_dg.f90:1137-1479 (u_eq is never read there) */
+int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, const double* y, double* dudt);
+/* replaces apply_limiter(u)   2d/benchmark_2d_dg.f90:1516-1555 -> 2d/limiters.f90 */
+int wb_dg2d_apply_limiter(wb_dg2d* h, double* modes_inout);
+/* replaces compute_max_speed(u(:,:,:,1,1),cs_max,v_xmax,v_ymax,speed_max)   2d/benchmark_2d_dg.f90:826-870;
+ * mean_mode is u(nvar,nx,ny) == double[ny][nx][4] */
+int wb_dg2d_compute_max_speed(wb_dg2d* h, const double* mean_mode, double* cs_max, double* v_xmax, double* v_ymax,
+                              double* speed_max);
+/* replaces evolve(u,x,y,u_eq)   2d/benchmark_2d_dg.f90:624-775: nodal values in, nodal values out */
+int wb_dg2d_evolve(wb_dg2d* h, double* u_nodes_inout, const double* x, const double* y, double tend, int max_iter,
+                   int* iters_out, double* t_out, double* last_dt_out);
+/* resident path: upload nodal values (projected to modes and limited on the device, :644,:659), step, download nodes */
+int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const double* y);
+int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend);
+int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out);
+int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out);
+int wb_dg2d_download_modes(wb_dg2d* h, double* modes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,823 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+ *
+ * CPU restatement (plain C, FP64, -ffp-contract=off) of the 2D modal discontinuous-Galerkin path of the
+ * reference: 2d/benchmark_2d_dg.f90, 2d/legendre.f90, 2d/limiters.f90 (module 2d/parameters_dg_2d.f90).
+ *
+ * PARITY UNPINNED by reference artefacts (no Fortran compiler in the image, no golden vectors in the
+ * reference).  Pinned by: the fixed point of 2d/test2d.f90 (modes<->nodes round trip), exactness of the
+ * projection for polynomials, conservation/periodicity invariants and the textbook GL nodes
+ * (tests/test_oracle_dg2d.py).
+ *
+ * Layout: Fortran u(nvar,nx,ny,mx,my) == C double[my][mx][ny][nx][4]; x,y(nx,ny,mx,my) == double[my][mx][ny][nx].
+ * Literal kinds: un-suffixed reals are real(4) promoted: gamma, cfl, eps, eta, the SSPRK(5,4)
+ * coefficients, the 10e-10 density floor.  The Legendre/quadrature tables are computed with the reference's own
+ * recurrences (Newton, 500 iterations) -- not pasted textbook constants.  Loop nests keep the reference's
+ * accumulation order and left-to-right products; only the calls to legendre() inside the innermost loops are
+ * replaced by look-ups of values produced by the same function (bit-identical).
+ * Debug prints / `pause` / file output are omitted (no arithmetic effect).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NV 4
+#define MAXM 7          /* legendre() supports n = 0..6 */
+#define MAXG 8
+
+typedef struct {
+  int nx, ny, mx, my;       /* 2d/parameters_dg_2d.f90:3-6 */
+  int bc;                   /* :18  1 periodic, 2/3 clamp */
+  int source;               /* :20  1 none, 2 gravity (get_source), 3 advection sink */
+  int grad_phi_case;        /* :21 */
+  int flux_id;              /* :15  0 = as shipped ('llf ' matches nothing -> numerical flux stays 0), 1 = 'llf1' */
+  int limiter_id;           /* :14  0 = use_limiter false, 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW' */
+  int solver_id;            /* :13  1 'RK4', 2 'SS4', 3 'EQL', 4 'DEB' */
+  int ninit;                /* :17 */
+  double gamma, boxlen_x, boxlen_y, cfl, eps, M, eta;  /* :23-35 */
+} orc_dg2d_params;
+
+static inline int gll_of(int mx) { return (2 * (mx - 1) + 3) / 2; }   /* :7 */
+
+/* ------------------------------------------------------------------ 2d/legendre.f90:1-25 */
+double orc_dg2d_legendre(double *px, int n) {
+  double x = *px;
+  x = fmin(fmax(x, (double)-1.0f), (double)1.0f);
+  *px = x;                      /* the Fortran function clamps its argument in place */
+  double l = 0.0;
+  switch (n) {
+    case 0: l = 1.0; break;
+    case 1: l = x; break;
+    case 2: l = 0.5 * (3 * (x * x) - 1); break;
+    case 3: l = 0.5 * (5.0 * ((x * x) * x) - 3.0 * x); break;
+    case 4: { double x2 = x * x; l = 0.125 * (35.0 * (x2 * x2) - 30.0 * x2 + 3.0); } break;
+    case 5: { double x2 = x * x; l = 0.125 * (63.0 * ((x2 * x2) * x) - 70.0 * (x2 * x) + 15.0 * x); } break;
+    case 6: { double x2 = x * x; l = (double)(1.0f / 16.0f) * (231.0 * ((x2 * x2) * x2) - 315.0 * (x2 * x2) + 105.0 * x2 - 5.0); } break;
+  }
+  return sqrt((2.0 * (double)n + 1.0)) * l;
+}
+/* 2d/legendre.f90:27-50 */
+double orc_dg2d_legendre_prime(double *px, int n) {
+  double x = *px;
+  x = fmin(fmax(x, (double)-1.0f), (double)1.0f);
+  *px = x;
+  double l = 0.0;
+  switch (n) {
+    case 0: l = 0.0; break;
+    case 1: l = 1.0; break;
+    case 2: l = 3.0 * x; break;
+    case 3: l = 0.5 * (15.0 * (x * x) - 3.0); break;
+    case 4: l = 0.125 * (140.0 * ((x * x) * x) - 60.0 * x); break;
+    case 5: { double x2 = x * x; l = 0.125 * (315.0 * (x2 * x2) - 210.0 * x2 + 15.0); } break;
+    case 6: { double x2 = x * x; l = (double)(1.0f / 16.0f) * (1386.0 * ((x2 * x2) * x) - 1260.0 * (x2 * x) + 210.0 * x); } break;
+  }
+  return sqrt((2.0 * (double)n + 1.0)) * l;
+}
+static double leg(double x, int n) { return orc_dg2d_legendre(&x, n); }
+static double legp(double x, int n) { return orc_dg2d_legendre_prime(&x, n); }
+
+/* 2d/legendre.f90:77-108 */
+void orc_dg2d_gl_quadrature(double *x_quad, double *w_quad, int n) {
+  const double dpi = acos(-1.0);
+  for (int i = 1; i <= n; ++i) {
+    /* (1.0-0.125/n/n+0.125/n/n/n) is single precision (integer n converted to real(4)) */
+    float fn = (float)n;
+    float pre = (1.0f - 0.125f / fn / fn) + 0.125f / fn / fn / fn;
+    double xx = (double)pre * cos(dpi * (4.0 * (double)i - 1.0) / (4.0 * (double)n + 2.0));
+    for (int iter = 1; iter <= 500; ++iter) {
+      double a = orc_dg2d_legendre(&xx, n);
+      double b = orc_dg2d_legendre_prime(&xx, n);
+      xx = xx - a / b;
+    }
+    x_quad[i - 1] = -xx;
+    double xi = x_quad[i - 1];
+    double lp = orc_dg2d_legendre_prime(&xi, n);
+    x_quad[i - 1] = xi;
+    w_quad[i - 1] = 2 * (2.0 * (double)n + 1.0) / (1.0 - xi * xi) / (lp * lp);
+  }
+  for (int i = n / 2 + 1; i <= n; ++i) {
+    x_quad[i - 1] = -x_quad[n - i];
+    w_quad[i - 1] = w_quad[n - i];
+  }
+}
+/* 2d/legendre.f90:111-170 (weights as shipped, incl. the odd ones for n = 2, 3; real(4) arithmetic) */
+void orc_dg2d_gll_quadrature(double *x, double *w, int n) {
+  switch (n) {
+    case 2: x[0] = -1.; w[0] = 1.; x[1] = 0.; w[1] = 1.; break;
+    case 3: x[0] = -1.; w[0] = 3.f / 4.f; x[2] = 1.; w[2] = 3.f / 4.f; x[1] = 0.; w[1] = 1.f / 4.f; break;
+    case 4:
+      x[0] = -1.; w[0] = 1.f / 6.f; x[1] = -1.f / 5.f * sqrtf(5.f); w[1] = 5.f / 6.f;
+      x[2] = 1.f / 5.f * sqrtf(5.f); w[2] = 5.f / 6.f; x[3] = 1.; w[3] = 1.f / 6.f; break;
+    case 5:
+      x[0] = -1.; w[0] = 1.f / 10.f; x[1] = -1.f / 7.f * sqrtf(21.f); w[1] = 49.f / 90.f; x[2] = 0.0; w[2] = 32.f / 45.f;
+      x[3] = 1.f / 7.f * sqrtf(21.f); w[3] = 49.f / 90.f; x[4] = 1.; w[4] = 1.f / 10.f; break;
+    case 6:
+      x[0] = -1.; w[0] = 1.f / 15.f;
+      x[1] = -sqrtf(1.f / 21.f * (7 + 2 * sqrtf(7.f))); w[1] = 1.f / 30.f * (14.f - sqrtf(7.f));
+      x[2] = -sqrtf(1.f / 21.f * (7 - 2 * sqrtf(7.f))); w[2] = 1.f / 30.f * (14.f + sqrtf(7.f));
+      x[3] = sqrtf(1.f / 21.f * (7 - 2 * sqrtf(7.f))); w[3] = 1.f / 30.f * (14.f + sqrtf(7.f));
+      x[4] = sqrtf(1.f / 21.f * (7 + 2 * sqrtf(7.f))); w[4] = 1.f / 30.f * (14.f - sqrtf(7.f));
+      x[5] = 1.; w[5] = 1.f / 15.f; break;
+    default: break; /* n = 1: print 'error' */
+  }
+}
+
+/* ------------------------------------------------------------------ basis tables (values of the functions above) */
+typedef struct {
+  int mx, my, gll;
+  double xq[MAXM], wx[MAXM], yq[MAXM], wy[MAXM];
+  double xg[MAXG], wg[MAXG];
+  double Px[MAXM][MAXM];    /* Px[q][m] = legendre(x_quad(q), m)   */
+  double Py[MAXM][MAXM];
+  double dPx[MAXM][MAXM];   /* legendre_prime(x_quad(q), m)        */
+  double dPy[MAXM][MAXM];
+  double Em[MAXM], Ep[MAXM];/* legendre(-1, m), legendre(+1, m)    */
+  double Pgx[MAXG][MAXM];   /* legendre(x_gll_quad(r), m)          */
+} basis_t;
+
+static void make_basis(const orc_dg2d_params *p, basis_t *B) {
+  memset(B, 0, sizeof(*B));
+  B->mx = p->mx; B->my = p->my; B->gll = gll_of(p->mx);
+  orc_dg2d_gl_quadrature(B->xq, B->wx, p->mx);
+  orc_dg2d_gl_quadrature(B->yq, B->wy, p->my);
+  if (B->gll >= 2) orc_dg2d_gll_quadrature(B->xg, B->wg, B->gll);
+  for (int q = 0; q < p->mx; ++q)
+    for (int m = 0; m < p->mx; ++m) { B->Px[q][m] = leg(B->xq[q], m); B->dPx[q][m] = legp(B->xq[q], m); }
+  for (int q = 0; q < p->my; ++q)
+    for (int m = 0; m < p->my; ++m) { B->Py[q][m] = leg(B->yq[q], m); B->dPy[q][m] = legp(B->yq[q], m); }
+  int mm = p->mx > p->my ? p->mx : p->my;
+  for (int m = 0; m < mm; ++m) { B->Em[m] = leg(-1.0, m); B->Ep[m] = leg(1.0, m); }
+  for (int r = 0; r < B->gll; ++r)
+    for (int m = 0; m < mm; ++m) B->Pgx[r][m] = leg(B->xg[r], m);
+}
+
+void orc_dg2d_basis_tables(const orc_dg2d_params *p, double *xq, double *wx, double *xg, double *wg) {
+  basis_t B; make_basis(p, &B);
+  for (int i = 0; i < p->mx; ++i) { xq[i] = B.xq[i]; wx[i] = B.wx[i]; }
+  for (int i = 0; i < B.gll; ++i) { xg[i] = B.xg[i]; wg[i] = B.wg[i]; }
+}
+
+#define IDX5(P, ic, jc, im, jm) ((((size_t)(jm) * (P)->mx + (im)) * (P)->ny + (jc)) * (P)->nx + (ic))
+#define U5(a, P, v, ic, jc, im, jm) ((a)[IDX5(P, ic, jc, im, jm) * NV + (v)])
+#define X4(a, P, ic, jc, im, jm) ((a)[IDX5(P, ic, jc, im, jm)])
+
+static size_t nelem5(const orc_dg2d_params *p) { return (size_t)p->nx * p->ny * p->mx * p->my; }
+
+/* ------------------------------------------------------------------ 2d/benchmark_2d_dg.f90:93-120 */
+void orc_dg2d_get_coords(const orc_dg2d_params *p, double *x, double *y) {
+  basis_t B; make_basis(p, &B);
+  double dx = p->boxlen_x / (double)p->nx, dy = p->boxlen_y / (double)p->ny;
+  for (int i = 1; i <= p->nx; ++i)
+    for (int j = 1; j <= p->ny; ++j)
+      for (int ni = 1; ni <= p->mx; ++ni)
+        for (int nj = 1; nj <= p->my; ++nj) {
+          X4(x, p, i - 1, j - 1, ni - 1, nj - 1) = (double)((float)i - 0.5f) * dx + dx / 2.0 * B.xq[ni - 1];
+          X4(y, p, i - 1, j - 1, ni - 1, nj - 1) = (double)((float)j - 0.5f) * dy + dy / 2.0 * B.yq[nj - 1];
+        }
+}
+
+/* :891-902 (density floored at the real(4) literal 10e-10) */
+static inline void prim1(const orc_dg2d_params *p, const double *u, double *w) {
+  w[0] = fmax(u[0], (double)10e-10f);
+  w[1] = u[1] / w[0];
+  w[2] = u[2] / w[0];
+  w[3] = (p->gamma - (double)1.0f) * (u[3] - 0.5 * w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+/* :905-917 */
+static inline void cons1(const orc_dg2d_params *p, const double *w, double *u) {
+  u[0] = w[0];
+  u[1] = w[0] * w[1];
+  u[2] = w[0] * w[2];
+  u[3] = w[3] / (p->gamma - (double)1.f) + 0.5 * (w[0] * (w[1] * w[1] + w[2] * w[2]));
+}
+void orc_dg2d_compute_primitive(const orc_dg2d_params *p, const double *u, double *w, long n) {
+  for (long k = 0; k < n; ++k) prim1(p, u + NV * k, w + NV * k);
+}
+void orc_dg2d_compute_conservative(const orc_dg2d_params *p, const double *w, double *u, long n) {
+  for (long k = 0; k < n; ++k) cons1(p, w + NV * k, u + NV * k);
+}
+
+/* :122-466 get_initial_conditions, cases 1-5 (nodal conservative values) */
+void orc_dg2d_get_initial_conditions(const orc_dg2d_params *p, const double *x, const double *y, double *u) {
+  size_t n = nelem5(p);
+  double *w = (double *)malloc(sizeof(double) * NV * n);
+  for (size_t k = 0; k < n; ++k) {
+    double xx = x[k], yy = y[k];
+    double *ww = w + NV * k;
+    switch (p->ninit) {
+      case 1: {
+        double ax = xx - p->boxlen_x / 2., ay = yy - p->boxlen_y / 2.;
+        ww[0] = exp(-((ax * ax + ay * ay) * 10));
+        ww[1] = 1.0; ww[2] = 1.0; ww[3] = 0.0; /* w(4) = minval(w(1)) below */
+      } break;
+      case 2: {
+        double rho_0 = (double)1.21f, p_0 = 1., g = 1.;
+        double e = exp(-(rho_0 * g / p_0) * (xx + yy));
+        double bx = xx - (double)0.3f, by = yy - (double)0.3f;
+        ww[0] = rho_0 * e; ww[1] = 0; ww[2] = 0;
+        ww[3] = p_0 * e + p->eta * exp(-(100 * (rho_0 * g / p_0) * (bx * bx + by * by)));
+      } break;
+      case 3:
+        if (xx >= 0.5 && yy >= 0.5) { ww[0] = 1.; ww[1] = 0.; ww[2] = 0.; ww[3] = 1.; }
+        else if (xx < 0.5 && yy >= 0.5) { ww[0] = (double)0.5197f; ww[1] = (double)-0.7259f; ww[2] = 0.; ww[3] = (double)0.4f; }
+        else if (xx < 0.5 && yy < 0.5) { ww[0] = (double)0.1072f; ww[1] = (double)-0.7259f; ww[2] = (double)-1.4045f; ww[3] = (double)0.0439f; }
+        else { ww[0] = (double)0.2579f; ww[1] = 0.0; ww[2] = (double)-1.4045f; ww[3] = (double)0.15f; }
+        break;
+      case 4:
+        if (xx >= 0.5 && yy >= 0.5) { ww[0] = 1.5; ww[1] = 0.; ww[2] = 0.; ww[3] = 1.5; }
+        else if (xx < 0.5 && yy >= 0.5) { ww[0] = (double)0.5323f; ww[1] = (double)1.206f; ww[2] = 0.; ww[3] = (double)0.3f; }
+        else if (xx < 0.5 && yy < 0.5) { ww[0] = (double)0.138f; ww[1] = (double)1.206f; ww[2] = (double)1.206f; ww[3] = (double)0.029f; }
+        else { ww[0] = (double)0.5323f; ww[1] = 0.0; ww[2] = (double)1.206f; ww[3] = (double)0.3f; }
+        break;
+      default: /* case 5 */
+        if (xx + yy >= 0.5) { ww[0] = 1.; ww[1] = 0.; ww[2] = 0.; ww[3] = 1.; }
+        else { ww[0] = 0.125; ww[1] = 0.; ww[2] = 0.; ww[3] = (double)0.4f; }
+        break;
+    }
+  }
+  if (p->ninit == 1) {
+    double mn = w[0];
+    for (size_t k = 0; k < n; ++k) mn = fmin(mn, w[NV * k]);
+    for (size_t k = 0; k < n; ++k) w[NV * k + 3] = mn;
+  }
+  orc_dg2d_compute_conservative(p, w, u, (long)n);
+  free(w);
+}
+
+/* ------------------------------------------------------------------ :497-542 / :544-592 transforms */
+void orc_dg2d_get_modes_from_nodes(const orc_dg2d_params *p, const double *nodes, double *u) {
+  basis_t B; make_basis(p, &B);
+  memset(u, 0, sizeof(double) * NV * nelem5(p));
+  for (int ic = 0; ic < p->nx; ++ic)
+    for (int jc = 0; jc < p->ny; ++jc)
+      for (int i = 0; i < p->mx; ++i)
+        for (int j = 0; j < p->my; ++j)
+          for (int xq = 0; xq < p->mx; ++xq)
+            for (int yq = 0; yq < p->my; ++yq)
+              for (int v = 0; v < NV; ++v)
+                U5(u, p, v, ic, jc, i, j) = U5(u, p, v, ic, jc, i, j) +
+                    0.25 * U5(nodes, p, v, ic, jc, xq, yq) * B.Px[xq][i] * B.Py[yq][j] * B.wx[xq] * B.wy[yq];
+}
+void orc_dg2d_get_nodes_from_modes(const orc_dg2d_params *p, const double *modes, double *u) {
+  basis_t B; make_basis(p, &B);
+  memset(u, 0, sizeof(double) * NV * nelem5(p));
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 0; ic < p->nx; ++ic)
+      for (int jc = 0; jc < p->ny; ++jc)
+        for (int i = 0; i < p->mx; ++i)
+          for (int j = 0; j < p->my; ++j)
+            for (int in = 0; in < p->mx; ++in)
+              for (int jn = 0; jn < p->my; ++jn)
+                U5(u, p, v, ic, jc, i, j) = U5(u, p, v, ic, jc, i, j) + U5(modes, p, v, ic, jc, in, jn) * B.Px[i][in] * B.Py[j][jn];
+}
+/* ------------------------------------------------------------------ :777-824 get_boundary_conditions (1-based index) */
+static int bc_index(const orc_dg2d_params *p, int index, int dim) {
+  int n = (dim == 1) ? p->nx : p->ny;
+  if (p->bc == 1) { if (index == 0) index = n; else if (index == n + 1) index = 1; }
+  else if (p->bc == 2 || p->bc == 3) { if (index == 0) index = 1; else if (index == n + 1) index = n; }
+  return index;
+}
+
+/* :872-889 compute_speed */
+static void compute_speed(const orc_dg2d_params *p, const double *u, double *cs, double *vx, double *vy, double *speed) {
+  double w[NV];
+  prim1(p, u, w);
+  *cs = sqrt(p->gamma * fmax(w[3], 1e-10) / fmax(w[0], 1e-10));
+  *vx = w[1]; *vy = w[2];
+  *speed = sqrt(w[1] * w[1] + w[2] * w[2]) + *cs;
+}
+
+/* :826-870 compute_max_speed on the mean mode u(1:nvar,nx,ny): order-dependent scan, i outer, j inner */
+void orc_dg2d_compute_max_speed(const orc_dg2d_params *p, const double *modes, double *cs_max, double *v_xmax,
+                                double *v_ymax, double *speed_max) {
+  *speed_max = 0.0; *cs_max = 0.0; *v_xmax = 0.0; *v_ymax = 0.0;
+  for (int ic = 0; ic < p->nx; ++ic)
+    for (int jc = 0; jc < p->ny; ++jc) {
+      double cs, vx, vy, speed;
+      compute_speed(p, &U5(modes, p, 0, ic, jc, 0, 0), &cs, &vx, &vy, &speed);
+      if (speed >= *speed_max) {
+        *speed_max = fmax(*speed_max, speed);
+        *v_xmax = vx; *v_ymax = vy; *cs_max = cs;
+      }
+      if (*cs_max > cs) *cs_max = cs;
+    }
+}
+
+/* :946-965 compute_flux_int */
+static void flux_int(const orc_dg2d_params *p, const double *u, double *f1, double *f2) {
+  double w[NV];
+  prim1(p, u, w);
+  f1[0] = w[1] * u[0];
+  f1[1] = w[1] * u[1] + w[3];
+  f1[2] = w[0] * w[1] * w[2];
+  f1[3] = w[1] * u[3] + w[1] * w[3];
+  f2[0] = w[2] * u[0];
+  f2[1] = w[0] * w[1] * w[2];
+  f2[2] = w[2] * u[2] + w[3];
+  f2[3] = w[2] * u[3] + w[2] * w[3];
+}
+/* :919-944 compute_flux at the volume nodes (note flux(1) uses the floored density) */
+static void flux_nodes(const orc_dg2d_params *p, const double *u, double *f1, double *f2) {
+  double w[NV];
+  prim1(p, u, w);
+  f2[0] = w[0] * w[2];
+  f2[1] = w[0] * w[1] * w[2];
+  f2[2] = w[2] * u[2] + w[3];
+  f2[3] = w[2] * u[3] + w[2] * w[3];
+  f1[0] = w[0] * w[1];
+  f1[1] = w[1] * u[1] + w[3];
+  f1[2] = w[0] * w[1] * w[2];
+  f1[3] = w[1] * u[3] + w[1] * w[3];
+}
+/* :968-988 compute_llflux */
+static void llflux(const orc_dg2d_params *p, const double *ul, const double *ur, const double *fl, const double *fr,
+                   double *fg, int flag) {
+  double cs_l, cs_r, vxl, vyl, vxr, vyr, sl, sr, cmax = 0.0;
+  compute_speed(p, ul, &cs_l, &vxl, &vyl, &sl);
+  compute_speed(p, ur, &cs_r, &vxr, &vyr, &sr);
+  if (flag == 1) cmax = fmax(fabs(vxr + cs_r), fabs(vxl + cs_l));
+  else if (flag == 2) cmax = fmax(fabs(vyr + cs_r), fabs(vyl + cs_l));
+  for (int v = 0; v < NV; ++v) fg[v] = 0.5 * (fr[v] + fl[v]) + 0.5 * cmax * (ul[v] - ur[v]);
+}
+/* :991-1006 compute_num_flux: flux_type that matches none of 'llf1','hll2','hllc' leaves the output untouched */
+static void num_flux(const orc_dg2d_params *p, const double *ul, const double *ur, const double *fl, const double *fr,
+                     double *nf, int flag) {
+  if (p->flux_id == 1) llflux(p, ul, ur, fl, fr, nf, flag);
+}
+
+/* :1599-1644 grad_phi at one node */
+static void grad_phi1(const orc_dg2d_params *p, double x, double y, double *g1, double *g2) {
+  if (p->grad_phi_case == 1) { *g1 = x; *g2 = y; return; }
+  double epsilon = 0.25, delta_r = (double)0.1f, x_center = 3., y_center = 3.;
+  double x_dash = x - x_center, y_dash = y - y_center;
+  double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+  if (r > 0.5 - 0.5 * delta_r) {
+    *g1 = -(x_dash) / ((r * r) * r);
+    *g2 = -(y_dash) / ((r * r) * r);
+  } else {
+    *g1 = -(x_dash) / (r * (r * r + epsilon * epsilon));
+    *g2 = -(y_dash) / (r * (r * r + epsilon * epsilon));
+  }
+}
+
+/* ------------------------------------------------------------------ :1137-1479 compute_update */
+void orc_dg2d_compute_update(const orc_dg2d_params *p, const double *delta_u, const double *x, const double *y,
+                             double *dudt) {
+  basis_t B; make_basis(p, &B);
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  const size_t n5 = nelem5(p);
+  const double dx = p->boxlen_x / (double)nx;
+  const double oneoverdx = 1. / dx;
+  double *uq = (double *)calloc(NV * n5, sizeof(double));
+  double *fq1 = (double *)malloc(sizeof(double) * NV * n5);
+  double *fq2 = (double *)malloc(sizeof(double) * NV * n5);
+  double *vol1 = (double *)calloc(NV * n5, sizeof(double));
+  double *vol2 = (double *)calloc(NV * n5, sizeof(double));
+  double *svol = (double *)calloc(NV * n5, sizeof(double));
+  double *s = (double *)calloc(NV * n5, sizeof(double));
+  double *edge = (double *)calloc(4 * NV * n5, sizeof(double));
+  /* traces and their fluxes: [jc][ic][node][v] */
+  size_t nt = (size_t)nx * ny * (mx > my ? mx : my) * NV;
+  double *u_left = (double *)calloc(nt, sizeof(double)), *u_right = (double *)calloc(nt, sizeof(double));
+  double *u_top = (double *)calloc(nt, sizeof(double)), *u_bottom = (double *)calloc(nt, sizeof(double));
+  double *fl1 = (double *)calloc(nt, sizeof(double)), *fr1 = (double *)calloc(nt, sizeof(double));
+  double *ft2 = (double *)calloc(nt, sizeof(double)), *fb2 = (double *)calloc(nt, sizeof(double));
+  const int mm = (mx > my ? mx : my);
+#define TR(a, ic, jc, q) ((a) + (((size_t)(jc) * nx + (ic)) * mm + (q)) * NV)
+  double *F = (double *)calloc((size_t)NV * mm * (nx + 1) * ny, sizeof(double));
+  double *G = (double *)calloc((size_t)NV * mm * nx * (ny + 1), sizeof(double));
+#define FX(q, iface, j) (F + (((size_t)(j) * (nx + 1) + (iface)) * mm + (q)) * NV)
+#define GY(q, i, jface) (G + (((size_t)(jface) * nx + (i)) * mm + (q)) * NV)
+
+  /* :1203-1204 */
+  orc_dg2d_get_nodes_from_modes(p, delta_u, uq);
+  for (size_t k = 0; k < n5; ++k) flux_nodes(p, uq + NV * k, fq1 + NV * k, fq2 + NV * k);
+
+  /* :1207-1244 volume integrals */
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc)
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j) {
+          for (int in = 0; in < mx; ++in)
+            for (int jn = 0; jn < my; ++jn)
+              for (int v = 0; v < NV; ++v)
+                U5(vol1, p, v, ic, jc, i, j) = U5(vol1, p, v, ic, jc, i, j) +
+                    U5(fq1, p, v, ic, jc, in, jn) * B.dPx[in][i] * B.wx[in] * B.Py[jn][j] * B.wy[jn];
+          for (int in = 0; in < mx; ++in)
+            for (int jn = 0; jn < my; ++jn)
+              for (int v = 0; v < NV; ++v)
+                U5(vol2, p, v, ic, jc, i, j) = U5(vol2, p, v, ic, jc, i, j) +
+                    U5(fq2, p, v, ic, jc, in, jn) * B.dPy[jn][j] * B.wy[jn] * B.Px[in][i] * B.wx[in];
+        }
+
+  /* :1253-1314 edge traces */
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc) {
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int q = 0; q < my; ++q)
+            for (int v = 0; v < NV; ++v) {
+              double d = U5(delta_u, p, v, ic, jc, i, j);
+              TR(u_left, ic, jc, q)[v] = TR(u_left, ic, jc, q)[v] + d * B.Em[i] * B.Py[q][j];
+              TR(u_right, ic, jc, q)[v] = TR(u_right, ic, jc, q)[v] + d * B.Ep[i] * B.Py[q][j];
+            }
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int q = 0; q < mx; ++q)
+            for (int v = 0; v < NV; ++v) {
+              double d = U5(delta_u, p, v, ic, jc, i, j);
+              TR(u_bottom, ic, jc, q)[v] = TR(u_bottom, ic, jc, q)[v] + d * B.Em[j] * B.Px[q][i];
+              TR(u_top, ic, jc, q)[v] = TR(u_top, ic, jc, q)[v] + d * B.Ep[j] * B.Px[q][i];
+            }
+    }
+  /* :1320-1331 physical fluxes at the traces */
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc)
+      for (int q = 0; q < mx; ++q) {
+        double f1[NV], f2[NV];
+        flux_int(p, TR(u_left, ic, jc, q), f1, f2);   memcpy(TR(fl1, ic, jc, q), f1, sizeof(f1));
+        flux_int(p, TR(u_right, ic, jc, q), f1, f2);  memcpy(TR(fr1, ic, jc, q), f1, sizeof(f1));
+        flux_int(p, TR(u_top, ic, jc, q), f1, f2);    memcpy(TR(ft2, ic, jc, q), f2, sizeof(f2));
+        flux_int(p, TR(u_bottom, ic, jc, q), f1, f2); memcpy(TR(fb2, ic, jc, q), f2, sizeof(f2));
+      }
+  /* :1333-1349 x faces; the neighbour index goes through get_boundary_conditions(.,2) (sic) */
+  for (int j = 1; j <= ny; ++j)
+    for (int iface = 1; iface <= nx + 1; ++iface) {
+      int ileft = bc_index(p, iface - 1, 2), iright = bc_index(p, iface, 2);
+      if (ileft < 1 || ileft > nx || iright < 1 || iright > nx) continue; /* only reachable when nx != ny (reference reads out of bounds) */
+      for (int q = 0; q < my; ++q)
+        num_flux(p, TR(u_right, ileft - 1, j - 1, q), TR(u_left, iright - 1, j - 1, q), TR(fr1, ileft - 1, j - 1, q),
+                 TR(fl1, iright - 1, j - 1, q), FX(q, iface - 1, j - 1), 1);
+    }
+  /* :1351-1366 y faces */
+  for (int i = 1; i <= nx; ++i)
+    for (int jface = 1; jface <= ny + 1; ++jface) {
+      int ileft = bc_index(p, jface - 1, 2), iright = bc_index(p, jface, 2);
+      for (int q = 0; q < mx; ++q)
+        num_flux(p, TR(u_top, i - 1, ileft - 1, q), TR(u_bottom, i - 1, iright - 1, q), TR(ft2, i - 1, ileft - 1, q),
+                 TR(fb2, i - 1, iright - 1, q), GY(q, i - 1, jface - 1), 2);
+    }
+  /* :1372-1411 edge integrals (edges 1,2 use x_quad / w_x_quad for the y variation, as shipped) */
+#define EDGE(e, v, ic, jc, i, j) (edge[(size_t)(e) * NV * n5 + IDX5(p, ic, jc, i, j) * NV + (v)])
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc) {
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int q = 0; q < mx; ++q)
+            for (int v = 0; v < NV; ++v) {
+              EDGE(0, v, ic, jc, i, j) = EDGE(0, v, ic, jc, i, j) + FX(q, ic + 1, jc)[v] * B.Ep[i] * B.Px[q][j] * B.wx[q];
+              EDGE(1, v, ic, jc, i, j) = EDGE(1, v, ic, jc, i, j) + FX(q, ic, jc)[v] * B.Em[i] * B.Px[q][j] * B.wx[q];
+            }
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int q = 0; q < my; ++q)
+            for (int v = 0; v < NV; ++v) {
+              EDGE(2, v, ic, jc, i, j) = EDGE(2, v, ic, jc, i, j) + GY(q, ic, jc + 1)[v] * B.Ep[j] * B.Px[q][i] * B.wx[q];
+              EDGE(3, v, ic, jc, i, j) = EDGE(3, v, ic, jc, i, j) + GY(q, ic, jc)[v] * B.Em[j] * B.Px[q][i] * B.wx[q];
+            }
+    }
+  /* :1414-1443 source */
+  if (p->source == 2) {
+    for (size_t k = 0; k < n5; ++k) {
+      double w[NV], g1, g2;
+      prim1(p, uq + NV * k, w);
+      grad_phi1(p, x[k], y[k], &g1, &g2);
+      s[NV * k + 0] = 0.;
+      s[NV * k + 1] = w[0] * g1;
+      s[NV * k + 2] = w[0] * g2;
+      s[NV * k + 3] = w[0] * (w[1] * g1 + w[2] * g2);
+    }
+  } else if (p->source == 3) {
+    for (size_t k = 0; k < n5; ++k) { s[NV * k] = -1.0 * uq[NV * k]; s[NV * k + 1] = 0.0; s[NV * k + 2] = 0.0; s[NV * k + 3] = 0.0; }
+  }
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc)
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int in = 0; in < mx; ++in)
+            for (int jn = 0; jn < my; ++jn)
+              for (int v = 0; v < NV; ++v)
+                U5(svol, p, v, ic, jc, i, j) = U5(svol, p, v, ic, jc, i, j) +
+                    U5(s, p, v, ic, jc, in, jn) * B.Px[in][i] * B.wx[in] * B.Py[jn][j] * B.wy[jn];
+  /* :1449-1466 */
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc)
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int v = 0; v < NV; ++v)
+            U5(dudt, p, v, ic, jc, i, j) =
+                (oneoverdx * U5(vol1, p, v, ic, jc, i, j) + oneoverdx * U5(vol2, p, v, ic, jc, i, j)
+                 - oneoverdx * (EDGE(0, v, ic, jc, i, j) - EDGE(1, v, ic, jc, i, j))
+                 - oneoverdx * (EDGE(2, v, ic, jc, i, j) - EDGE(3, v, ic, jc, i, j))) / 2.
+                + U5(svol, p, v, ic, jc, i, j) / 4.;
+  /* :1481-1514 special_boundary_conditions: only ninit == 12 */
+  if (p->ninit == 12) {
+    double xc = p->boxlen_x / 2., yc = p->boxlen_y / 2.;
+    for (size_t k = 0; k < n5; ++k) {
+      double xd = x[k] - xc, yd = y[k] - yc;
+      if (sqrt(xd * xd + yd * yd) > 2.0) for (int v = 0; v < NV; ++v) dudt[NV * k + v] = 0.0;
+    }
+  }
+  free(uq); free(fq1); free(fq2); free(vol1); free(vol2); free(svol); free(s); free(edge);
+  free(u_left); free(u_right); free(u_top); free(u_bottom); free(fl1); free(fr1); free(ft2); free(fb2); free(F); free(G);
+}
+
+/* ------------------------------------------------------------------ 2d/limiters.f90 */
+static inline double sign1(double x) { return copysign(1.0, x); }
+/* :18-28 */
+static double minmod(double x, double y, double z) {
+  double s = sign1(x);
+  if (sign1(y) == s && sign1(z) == s) return s * fmin(fmin(fabs(x), fabs(y)), fabs(z));
+  return 0.0;
+}
+/* :30-54 */
+static double generalized_minmod(const orc_dg2d_params *p, double x, double y, double z) {
+  double dx = p->boxlen_x / (double)p->nx;
+  if (fabs(x) < p->M * (dx * dx)) return x;
+  return minmod(x, y, z);
+}
+/* :57-78 */
+static double minmod2d(double u, double dlx, double dly, double drx, double dry) {
+  double s = sign1(u);
+  if (sign1(dlx) == s && sign1(dly) == s && sign1(drx) == s && sign1(dry) == s)
+    return s * fmin(fmin(fmin(fmin(fabs(u), fabs(dly)), fabs(dlx)), fabs(dry)), fabs(drx));
+  return 0.0;
+}
+
+/* :312-362 solve_for_t */
+static double solve_for_t(const orc_dg2d_params *p, const double *u, const double *u_avg) {
+  const double eps = p->eps, gamma = p->gamma;
+  double pa = u_avg[0], mxa = u_avg[1], mya = u_avg[2], ea = u_avg[3];
+  double pj = u[0], mxj = u[1], myj = u[2], ej = u[3];
+  double a = 2.0 * (pj - pa) * (ej - ea) - (mxj - mxa) * (mxj - mxa) - (myj - mya) * (myj - mya);
+  double b = 2.0 * (pj - pa) * (ea - eps / (gamma - 1)) + 2.0 * pa * (ej - ea) - 2.0 * (mxa * (mxj - mxa) + mya * (myj - mya));
+  double c = 2.0 * pa * ea - (mxa * mxa + mya * mya) - 2.0 * eps * pa / (gamma - (double)1.0f);
+  b = b / a;
+  c = c / a;
+  double D = sqrt(fabs(b * b - 4 * c));
+  double t1 = 0.5 * (-b - D), t2 = 0.5 * (-b + D), t;
+  if ((t1 > -eps) && (t1 < (double)1.0f + eps)) t = t1;
+  else if ((t2 > -eps) && (t2 < (double)1.0f + eps)) t = t2;
+  else t = 0.0;
+  t = fmin(1.0, t);
+  t = fmax(0.0, t);
+  return t;
+}
+
+/* :438-475 compute_set: the GLL x GL point set of one element; modes laid out [jm][im][v] */
+static void compute_set(const orc_dg2d_params *p, const basis_t *B, const double *modes, double *pts /*[2*my*gll][4]*/) {
+  const int mx = p->mx, my = p->my, gll = B->gll;
+  for (int q = 0; q < my; ++q)
+    for (int r = 0; r < gll; ++r) {
+      double ul[NV] = {0, 0, 0, 0}, ur[NV] = {0, 0, 0, 0};
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int v = 0; v < NV; ++v) {
+            double m = modes[(j * mx + i) * NV + v];
+            ul[v] = ul[v] + m * B->Pgx[r][i] * B->Py[q][j];
+            ur[v] = ur[v] + m * B->Px[q][i] * B->Pgx[r][j];
+          }
+      memcpy(pts + (size_t)(q * gll + r) * NV, ul, sizeof(ul));
+      memcpy(pts + (size_t)(q * gll + r + my * gll) * NV, ur, sizeof(ur));
+    }
+}
+
+/* :478-654 compute_positivity ('ONP') */
+void orc_dg2d_compute_positivity(const orc_dg2d_params *p, double *u) {
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  if (mx == 1 && my == 1) return;
+  basis_t B; make_basis(p, &B);
+  const int npts = mx * B.gll + my * B.gll;
+  double el[MAXM * MAXM * NV], pts[2 * MAXM * MAXG * NV];
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc) {
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int v = 0; v < NV; ++v) el[(j * mx + i) * NV + v] = U5(u, p, v, ic, jc, i, j);
+      double uavg[NV] = {el[0], el[1], el[2], el[3]};
+      /* 1. density */
+      compute_set(p, &B, el, pts);
+      double p_min = pts[0];
+      for (int k = 1; k < npts; ++k) p_min = fmin(p_min, pts[(size_t)k * NV]);
+      double theta = fmin(fabs((uavg[0] - p->eps) / (uavg[0] - p_min)), 1.0);
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          if (i != 0 || j != 0) el[(j * mx + i) * NV + 0] = theta * el[(j * mx + i) * NV + 0];
+      /* 2. pressure */
+      double t_min = 1.;
+      compute_set(p, &B, el, pts);
+      for (int k = 0; k < npts; ++k) {
+        double w[NV], t;
+        prim1(p, pts + (size_t)k * NV, w);
+        if (w[3] > p->eps) t = 1.;
+        else t = solve_for_t(p, pts + (size_t)k * NV, uavg);
+        if (t_min >= t) t_min = t;
+      }
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j)
+          for (int v = 0; v < NV; ++v) {
+            double m = el[(j * mx + i) * NV + v];
+            U5(u, p, v, ic, jc, i, j) = (i != 0 || j != 0) ? t_min * m : m;
+          }
+    }
+}
+
+/* :1441-1476 limiting(); 1-based mode indices a=intnode, b=jntnode; neighbours 1-based cell indices */
+static double limiting(const orc_dg2d_params *p, const double *u, int v, int ic, int jc, int itop, int ibottom, int ileft,
+                       int iright, int a, int b) {
+  double coeff_j = (2.0 * (double)(a - 1) + 1.0) * (2 * (double)(b - 1) - 1);
+  double coeff_i = (2.0 * (double)(b - 1) + 1.0) * (2 * (double)(a - 1) - 1);
+  double coeff_u = (2.0 * (double)(a - 1) + 1.0) * (2.0 * (double)(b - 1) + 1.0);
+  double central_u = U5(u, p, v, ic - 1, jc - 1, a - 1, b - 1);
+  double d_r_y = (U5(u, p, v, ic - 1, itop - 1, a - 1, b - 2) - U5(u, p, v, ic - 1, jc - 1, a - 1, b - 2)) * coeff_j;
+  double d_l_y = (U5(u, p, v, ic - 1, jc - 1, a - 1, b - 2) - U5(u, p, v, ic - 1, ibottom - 1, a - 1, b - 2)) * coeff_j;
+  double d_r_x = (U5(u, p, v, iright - 1, jc - 1, a - 2, b - 1) - U5(u, p, v, ic - 1, jc - 1, a - 2, b - 1)) * coeff_i;
+  double d_l_x = (U5(u, p, v, ic - 1, jc - 1, a - 2, b - 1) - U5(u, p, v, ileft - 1, jc - 1, a - 2, b - 1)) * coeff_i;
+  return minmod2d(central_u * coeff_u, d_r_y, d_l_y, d_r_x, d_l_x) / coeff_u;
+}
+
+/* :1478-1583 high_order_limiter ('HIO') */
+void orc_dg2d_high_order_limiter(const orc_dg2d_params *p, double *u) {
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  if (mx == 1 && my == 1) return;
+  size_t n5 = nelem5(p);
+  double *un = (double *)malloc(sizeof(double) * NV * n5);
+  memcpy(un, u, sizeof(double) * NV * n5);
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= ny; ++jc) {
+        int done = 0;
+        int ileft = bc_index(p, ic - 1, 1), iright = bc_index(p, ic + 1, 1);
+        int itop = bc_index(p, jc + 1, 2), ibottom = bc_index(p, jc - 1, 2);
+        for (int a = mx; a >= 2; --a) {
+          double limited = limiting(p, u, v, ic, jc, itop, ibottom, ileft, iright, a, a);
+          if (limited != U5(u, p, v, ic - 1, jc - 1, a - 1, a - 1)) U5(un, p, v, ic - 1, jc - 1, a - 1, a - 1) = limited;
+          else break;
+          for (int b = a - 1; b >= 2; --b) {
+            double l1 = limiting(p, u, v, ic, jc, itop, ibottom, ileft, iright, a, b);
+            double l2 = limiting(p, u, v, ic, jc, itop, ibottom, ileft, iright, b, a);
+            if ((fabs(l1 - U5(u, p, v, ic - 1, jc - 1, a - 1, b - 1)) < p->eps) &&
+                (fabs(l2 - U5(u, p, v, ic - 1, jc - 1, b - 1, a - 1)) < p->eps)) { done = 1; break; }
+            U5(un, p, v, ic - 1, jc - 1, a - 1, b - 1) = l1;
+            U5(un, p, v, ic - 1, jc - 1, b - 1, a - 1) = l2;
+          }
+          if (done == 1) break;
+          double coeff_y = (2 * (double)(a - 1) + 1), coeff_u = (2 * (double)(a - 1) + 1);
+          double d_r_y = U5(u, p, v, ic - 1, itop - 1, a - 2, 0) - U5(u, p, v, ic - 1, jc - 1, a - 2, 0);
+          double d_l_y = U5(u, p, v, ic - 1, jc - 1, a - 2, 0) - U5(u, p, v, ic - 1, ibottom - 1, a - 2, 0);
+          double d_r_x = U5(u, p, v, iright - 1, jc - 1, 0, a - 2) - U5(u, p, v, ic - 1, jc - 1, 0, a - 2);
+          double d_l_x = U5(u, p, v, ic - 1, jc - 1, 0, a - 2) - U5(u, p, v, ileft - 1, jc - 1, 0, a - 2);
+          double l1 = generalized_minmod(p, U5(u, p, v, ic - 1, jc - 1, 0, a - 1) * coeff_u, d_r_y * coeff_y, d_l_y * coeff_y) / coeff_u;
+          double l2 = generalized_minmod(p, U5(u, p, v, ic - 1, jc - 1, a - 1, 0) * coeff_u, d_r_x * coeff_y, d_l_x * coeff_y) / coeff_u;
+          if ((l1 == U5(u, p, v, ic - 1, jc - 1, 0, a - 1)) && (l2 == U5(u, p, v, ic - 1, jc - 1, a - 1, 0))) break;
+          U5(un, p, v, ic - 1, jc - 1, 0, a - 1) = l1;
+          U5(un, p, v, ic - 1, jc - 1, a - 1, 0) = l2;
+        }
+      }
+  memcpy(u, un, sizeof(double) * NV * n5);
+  free(un);
+  orc_dg2d_compute_positivity(p, u);
+}
+
+/* :203-309 compute_limiter ('1OR'): minmod on the linear modes of the PRIMITIVE variables, higher modes dropped */
+void orc_dg2d_compute_limiter(const orc_dg2d_params *p, double *u) {
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  if (mx == 1 && my == 1) return;
+  size_t n5 = nelem5(p);
+  const double norm = 3.;
+  double *nodes = (double *)malloc(sizeof(double) * NV * n5), *w_nodes = (double *)malloc(sizeof(double) * NV * n5);
+  double *w = (double *)malloc(sizeof(double) * NV * n5), *modes = (double *)calloc(NV * n5, sizeof(double));
+  orc_dg2d_get_nodes_from_modes(p, u, nodes);
+  orc_dg2d_compute_primitive(p, nodes, w_nodes, (long)n5);
+  orc_dg2d_get_modes_from_nodes(p, w_nodes, w);
+  for (int ic = 0; ic < nx; ++ic)
+    for (int jc = 0; jc < ny; ++jc)
+      for (int v = 0; v < NV; ++v) U5(modes, p, v, ic, jc, 0, 0) = U5(w, p, v, ic, jc, 0, 0);
+  memcpy(u, w, sizeof(double) * NV * n5);
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= ny; ++jc) {
+        int ileft = bc_index(p, ic - 1, 1), iright = bc_index(p, ic + 1, 1);
+        int itop = bc_index(p, jc + 1, 2), ibottom = bc_index(p, jc - 1, 2);
+        double c = U5(u, p, v, ic - 1, jc - 1, 0, 0);
+        double u21 = (mx > 1) ? U5(u, p, v, ic - 1, jc - 1, 1, 0) : 0.0, u12 = (my > 1) ? U5(u, p, v, ic - 1, jc - 1, 0, 1) : 0.0;
+        double l1 = generalized_minmod(p, norm * u21, (U5(u, p, v, iright - 1, jc - 1, 0, 0) - c), (c - U5(u, p, v, ileft - 1, jc - 1, 0, 0))) / norm;
+        double l2 = generalized_minmod(p, norm * u12, (U5(u, p, v, ic - 1, itop - 1, 0, 0) - c), (c - U5(u, p, v, ic - 1, ibottom - 1, 0, 0))) / norm;
+        if ((fabs(l1 - u21) > (double)1E-6f) || fabs(l2 - u12) > (double)1E-6f) {
+          U5(modes, p, v, ic - 1, jc - 1, 1, 0) = l1;
+          U5(modes, p, v, ic - 1, jc - 1, 0, 1) = l2;
+        } else {
+          U5(modes, p, v, ic - 1, jc - 1, 0, 1) = u12;
+          U5(modes, p, v, ic - 1, jc - 1, 1, 0) = u21;
+        }
+      }
+  orc_dg2d_get_nodes_from_modes(p, modes, w_nodes);
+  orc_dg2d_compute_conservative(p, w_nodes, nodes, (long)n5);
+  orc_dg2d_get_modes_from_nodes(p, nodes, u);
+  free(nodes); free(w_nodes); free(w); free(modes);
+}
+
+/* :769-860 limiter_low_order ('LOW'): zeroes the first row / first column of the non-mean modes */
+void orc_dg2d_limiter_low_order(const orc_dg2d_params *p, double *u) {
+  if (p->mx == 1 && p->my == 1) return;
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 0; ic < p->nx; ++ic)
+      for (int jc = 0; jc < p->ny; ++jc) {
+        for (int j = 1; j < p->my; ++j) U5(u, p, v, ic, jc, 0, j) = 0.0;
+        for (int i = 1; i < p->mx; ++i) U5(u, p, v, ic, jc, i, 0) = 0.0;
+      }
+}
+
+/* 2d/benchmark_2d_dg.f90:1516-1555 apply_limiter */
+void orc_dg2d_apply_limiter(const orc_dg2d_params *p, double *u) {
+  switch (p->limiter_id) {
+    case 1: orc_dg2d_compute_positivity(p, u); break;
+    case 2: orc_dg2d_high_order_limiter(p, u); break;
+    case 3: orc_dg2d_compute_limiter(p, u); break;
+    case 4: orc_dg2d_limiter_low_order(p, u); break;
+    default: break;
+  }
+}
+
+/* ------------------------------------------------------------------ :624-775 evolve on the MODES
+ * (the reference's evolve wraps this between get_modes_from_nodes/apply_limiter and get_nodes_from_modes,
+ * see orc_dg2d_evolve below).  SSPRK(5,4) coefficients are real(4) literals. */
+#define F32(x) ((double)(x##f))
+static void axpy2(size_t n, double *out, double a, const double *A, double dt_c, const double *d) {
+  for (size_t k = 0; k < n; ++k) out[k] = a * A[k] + dt_c * d[k];
+}
+void orc_dg2d_evolve_modes(const orc_dg2d_params *p, double *du, const double *x, const double *y, double tend,
+                           int max_iter, int *iters_out, double *t_out, double *dt_out) {
+  const size_t n = NV * nelem5(p);
+  const double dx = p->boxlen_x / (double)p->nx;
+  const int gll = gll_of(p->mx);
+  double gll_w_1;
+  if (p->mx == 1) gll_w_1 = 1.;
+  else gll_w_1 = 1. / (double)((float)(gll * (gll - 1)) + 1e-10f);
+  double *dudt = (double *)malloc(sizeof(double) * n), *w1 = (double *)malloc(sizeof(double) * n);
+  double *w2 = (double *)malloc(sizeof(double) * n), *w3 = (double *)malloc(sizeof(double) * n);
+  double *w4 = (double *)malloc(sizeof(double) * n), *w5 = (double *)malloc(sizeof(double) * n);
+  double t = 0, dt = 0;
+  int iter = 0;
+  while (t < tend && (max_iter < 0 || iter < max_iter)) {
+    double cs_max, vx, vy, cmax;
+    orc_dg2d_compute_max_speed(p, du, &cs_max, &vx, &vy, &cmax);
+    dt = fmin(tend - t, p->cfl * fmin(1. / (double)(2 * 4 + 1), gll_w_1 / 2.) / ((fabs(vx) + (cs_max)) / dx + (fabs(vy) + (cs_max)) / dx));
+    if (p->solver_id == 3) { /* 'EQL' RK2 */
+      orc_dg2d_compute_update(p, du, x, y, dudt);
+      for (size_t k = 0; k < n; ++k) w1[k] = du[k] + dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w1);
+      orc_dg2d_compute_update(p, w1, x, y, dudt);
+      for (size_t k = 0; k < n; ++k) du[k] = 0.5 * du[k] + 0.5 * w1[k] + 0.5 * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, du);
+    }
+    if (p->solver_id == 1 || p->solver_id == 2) { /* 'RK4' and 'SS4' round to the same real(4) coefficients */
+      orc_dg2d_compute_update(p, du, x, y, dudt);
+      for (size_t k = 0; k < n; ++k) w1[k] = du[k] + F32(0.391752226571890) * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w1);
+      orc_dg2d_compute_update(p, w1, x, y, dudt);
+      for (size_t k = 0; k < n; ++k)
+        w2[k] = F32(0.444370493651235) * du[k] + F32(0.555629506348765) * w1[k] + F32(0.368410593050371) * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w2);
+      orc_dg2d_compute_update(p, w2, x, y, dudt);
+      for (size_t k = 0; k < n; ++k)
+        w3[k] = F32(0.620101851488403) * du[k] + F32(0.379898148511597) * w2[k] + F32(0.251891774271694) * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w3);
+      orc_dg2d_compute_update(p, w3, x, y, dudt);
+      for (size_t k = 0; k < n; ++k)
+        w4[k] = F32(0.178079954393132) * du[k] + F32(0.821920045606868) * w3[k] + F32(0.544974750228521) * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w4);
+      orc_dg2d_compute_update(p, w3, x, y, dudt);     /* :700 recomputed, same result as two calls above */
+      for (size_t k = 0; k < n; ++k)
+        w5[k] = F32(0.00683325884039) * du[k] + F32(0.51723167208978) * w2[k] + F32(0.12759831133288) * w3[k] +
+                F32(0.34833675773694) * w4[k] + F32(0.08460416338212) * dt * dudt[k];
+      orc_dg2d_compute_update(p, w4, x, y, dudt);
+      for (size_t k = 0; k < n; ++k) du[k] = w5[k] + F32(0.22600748319395) * dt * dudt[k];
+      orc_dg2d_apply_limiter(p, du);
+    }
+    if (p->solver_id == 4) { /* 'DEB' forward Euler */
+      orc_dg2d_compute_update(p, du, x, y, dudt);
+      for (size_t k = 0; k < n; ++k) w1[k] = du[k] + dt * dudt[k];
+      orc_dg2d_apply_limiter(p, w1);
+      memcpy(du, w1, sizeof(double) * n);
+    }
+    t = t + dt;
+    iter = iter + 1;
+  }
+  if (iters_out) *iters_out = iter;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  free(dudt); free(w1); free(w2); free(w3); free(w4); free(w5);
+  (void)axpy2;
+}
+
+/* evolve(u,x,y,u_eq) as the reference: nodal values in, nodal values out (:644, :659, :771-774) */
+void orc_dg2d_evolve(const orc_dg2d_params *p, double *u_nodes, const double *x, const double *y, double tend,
+                     int max_iter, int *iters_out, double *t_out, double *dt_out) {
+  size_t n = NV * nelem5(p);
+  double *du = (double *)malloc(sizeof(double) * n);
+  orc_dg2d_get_modes_from_nodes(p, u_nodes, du);
+  orc_dg2d_apply_limiter(p, du);
+  orc_dg2d_evolve_modes(p, du, x, y, tend, max_iter, iters_out, t_out, dt_out);
+  orc_dg2d_get_nodes_from_modes(p, du, u_nodes);
+  free(du);
+}

@@ -124,3 +124,105 @@ def fv2d_evolve(p, u, w_eq, tend, max_iter=-1):
     lib().orc_fv2d_evolve(C.byref(p), _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter),
                           C.byref(it), C.byref(t), C.byref(dt), C.byref(cm))
     return u, it.value, t.value, dt.value, cm.value
+
+
+# ---------------------------------------------------------------- 2D DG (2d/benchmark_2d_dg.f90, 2d/legendre.f90, 2d/limiters.f90)
+class DG2DParams(C.Structure):
+    """2d/parameters_dg_2d.f90:3-35."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("mx", C.c_int), ("my", C.c_int), ("bc", C.c_int),
+                ("source", C.c_int), ("grad_phi_case", C.c_int), ("flux_id", C.c_int), ("limiter_id", C.c_int),
+                ("solver_id", C.c_int), ("ninit", C.c_int), ("gamma", C.c_double), ("boxlen_x", C.c_double),
+                ("boxlen_y", C.c_double), ("cfl", C.c_double), ("eps", C.c_double), ("M", C.c_double),
+                ("eta", C.c_double)]
+
+
+LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4}
+SOLVERS = {"RK4": 1, "SS4": 2, "EQL": 3, "DEB": 4}
+FLUXES = {"llf": 0, "llf1": 1}   # 'llf' is the shipped default that matches no branch (numerical flux stays 0)
+
+
+def dg2d_params(nx=8, ny=8, mx=2, my=2, bc=1, source=1, grad_phi_case=2, flux="llf1", limiter="ONP", solver="RK4",
+                ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, eta=F32(0.1)):
+    return DG2DParams(nx, ny, mx, my, bc, source, grad_phi_case, FLUXES[flux], LIMITERS[limiter], SOLVERS[solver], ninit,
+                      gamma, boxlen_x, boxlen_y, cfl, eps, M, eta)
+
+
+def _dg_shape(p):
+    return (p.my, p.mx, p.ny, p.nx)
+
+
+def dg2d_basis(p):
+    gll = (2 * (p.mx - 1) + 3) // 2
+    xq = np.zeros(p.mx); wx = np.zeros(p.mx); xg = np.zeros(max(gll, 1)); wg = np.zeros(max(gll, 1))
+    lib().orc_dg2d_basis_tables(C.byref(p), _ptr(xq), _ptr(wx), _ptr(xg), _ptr(wg))
+    return xq, wx, xg, wg
+
+
+def dg2d_legendre(x, n):
+    f = lib().orc_dg2d_legendre; f.restype = C.c_double
+    v = C.c_double(x)
+    return f(C.byref(v), C.c_int(n))
+
+
+def dg2d_legendre_prime(x, n):
+    f = lib().orc_dg2d_legendre_prime; f.restype = C.c_double
+    v = C.c_double(x)
+    return f(C.byref(v), C.c_int(n))
+
+
+def dg2d_get_coords(p):
+    x = np.empty(_dg_shape(p)); y = np.empty(_dg_shape(p))
+    lib().orc_dg2d_get_coords(C.byref(p), _ptr(x), _ptr(y))
+    return x, y
+
+
+def dg2d_get_initial_conditions(p, x, y):
+    u = np.empty(_dg_shape(p) + (4,))
+    lib().orc_dg2d_get_initial_conditions(C.byref(p), _ptr(x), _ptr(y), _ptr(u))
+    return u
+
+
+def dg2d_get_modes_from_nodes(p, nodes):
+    u = np.empty_like(nodes)
+    lib().orc_dg2d_get_modes_from_nodes(C.byref(p), _ptr(nodes), _ptr(u))
+    return u
+
+
+def dg2d_get_nodes_from_modes(p, modes):
+    u = np.empty_like(modes)
+    lib().orc_dg2d_get_nodes_from_modes(C.byref(p), _ptr(modes), _ptr(u))
+    return u
+
+
+def dg2d_compute_update(p, modes, x, y):
+    d = np.empty_like(modes)
+    lib().orc_dg2d_compute_update(C.byref(p), _ptr(modes), _ptr(x), _ptr(y), _ptr(d))
+    return d
+
+
+def dg2d_compute_max_speed(p, modes):
+    a = [C.c_double() for _ in range(4)]
+    lib().orc_dg2d_compute_max_speed(C.byref(p), _ptr(modes), *[C.byref(v) for v in a])
+    return tuple(v.value for v in a)   # cs_max, v_xmax, v_ymax, speed_max
+
+
+def dg2d_apply_limiter(p, modes):
+    u = np.array(modes, copy=True)
+    lib().orc_dg2d_apply_limiter(C.byref(p), _ptr(u))
+    return u
+
+
+def dg2d_evolve_modes(p, modes, x, y, tend, max_iter=-1):
+    u = np.array(modes, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_dg2d_evolve_modes(C.byref(p), _ptr(u), _ptr(x), _ptr(y), C.c_double(tend), C.c_int(max_iter),
+                                C.byref(it), C.byref(t), C.byref(dt))
+    return u, it.value, t.value, dt.value
+
+
+def dg2d_evolve(p, nodes, x, y, tend, max_iter=-1):
+    u = np.array(nodes, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_dg2d_evolve(C.byref(p), _ptr(u), _ptr(x), _ptr(y), C.c_double(tend), C.c_int(max_iter),
+                          C.byref(it), C.byref(t), C.byref(dt))
+    return u, it.value, t.value, dt.value

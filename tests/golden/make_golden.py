@@ -35,8 +35,42 @@ def fv2d():
     np.savez_compressed(os.path.join(HERE, "fv2d.npz"), **out)
 
 
+def dg2d():
+    """2D DG: shipped pulse (ninit=1), hydrostatic+bump with gravity source (ninit=2, source=2, grad_phi_case=1 and 2),
+    Riemann problem with each limiter; orders 1-3; RK4 / EQL / DEB."""
+    out = {}
+    cases = [  # tag, nx, mx, bc, source, gcase, flux, limiter, solver, ninit, steps
+        ("pulse_o2_onp", 8, 2, 1, 1, 2, "llf1", "ONP", "RK4", 1, 3),
+        ("pulse_o3_onp", 6, 3, 1, 1, 2, "llf1", "ONP", "RK4", 1, 2),
+        ("pulse_o1", 8, 1, 1, 1, 2, "llf1", "ONP", "RK4", 1, 3),
+        ("shipped_flux", 6, 2, 1, 1, 2, "llf", "ONP", "RK4", 1, 2),
+        ("hydro_o3_g1", 6, 3, 2, 2, 1, "llf1", "ONP", "RK4", 2, 2),
+        ("hydro_o2_kepler", 6, 2, 2, 2, 2, "llf1", "ONP", "EQL", 2, 2),
+        ("riemann_o3_hio", 8, 3, 2, 1, 2, "llf1", "HIO", "RK4", 3, 3),
+        ("riemann_o2_1or", 8, 2, 2, 1, 2, "llf1", "1OR", "EQL", 4, 3),
+        ("riemann_o3_low", 6, 3, 2, 1, 2, "llf1", "LOW", "DEB", 4, 3),
+        ("advsink_o2", 6, 2, 1, 3, 2, "llf1", "none", "SS4", 1, 2),
+        ("riemann_o4_onp", 4, 4, 3, 1, 2, "llf1", "ONP", "RK4", 5, 2),
+    ]
+    for tag, nx, mx, bc, source, gcase, flux, lim, solver, ninit, steps in cases:
+        p = o.dg2d_params(nx=nx, ny=nx, mx=mx, my=mx, bc=bc, source=source, grad_phi_case=gcase, flux=flux, limiter=lim,
+                          solver=solver, ninit=ninit)
+        x, y = o.dg2d_get_coords(p)
+        u0 = o.dg2d_get_initial_conditions(p, x, y)
+        m0 = o.dg2d_get_modes_from_nodes(p, u0)
+        out[f"{tag}_meta"] = np.array([nx, mx, bc, source, gcase, p.flux_id, p.limiter_id, p.solver_id, ninit, steps])
+        out[f"{tag}_u0"] = u0
+        out[f"{tag}_dudt"] = o.dg2d_compute_update(p, m0, x, y)
+        out[f"{tag}_lim"] = o.dg2d_apply_limiter(p, m0)
+        un, it, t, dt = o.dg2d_evolve(p, u0, x, y, 1.0, steps)
+        out[f"{tag}_un"] = un
+        out[f"{tag}_clock"] = np.array([it, t, dt])
+        assert np.all(np.isfinite(un)), tag
+    np.savez_compressed(os.path.join(HERE, "dg2d.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fv2d"]
+    which = sys.argv[1:] or ["fv2d", "dg2d"]
     for w in which:
         globals()[w]()
         print("wrote", w)
