@@ -289,3 +289,109 @@ class DG2D:
         out = np.empty(self.shape)
         _check(lib().wb_dg2d_download_modes(self._h, _ptr(out)))
         return out
+
+
+# ================================================================================================== 1D FV
+class FVM1DParams(C.Structure):
+    """wb_fvm1d_params; defaults follow fvm_commons.f90."""
+    _fields_ = [("nx", C.c_int), ("nvar", C.c_int), ("bc", C.c_int), ("source", C.c_int), ("n", C.c_int),
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("device", C.c_int)]
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            getattr(lib(), self._destroy)(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class FVM1D(_Handle):
+    """fvm.f90: plain 1D finite volumes.  u(nvar,nx) == numpy (nx, 3)."""
+    _destroy = "wb_fvm1d_destroy"
+
+    def __init__(self, nx=200, bc=2, source=2, n=3, gamma=F32(1.4), boxlen=1.0, device=-1):
+        self.params = FVM1DParams(nx, 3, bc, source, n, gamma, boxlen, device)
+        self._h = C.c_void_p()
+        _check(lib().wb_fvm1d_create(C.byref(self._h), C.byref(self.params)))
+        self.shape = (nx, 3)
+
+    def compute_update(self, u):
+        """compute_update(u,dudt)  fvm.f90:188-251"""
+        d = np.empty(self.shape)
+        _check(lib().wb_fvm1d_compute_update(self._h, _ptr(u), _ptr(d)))
+        return d
+
+    def compute_max_speed(self, u):
+        c = C.c_double()
+        _check(lib().wb_fvm1d_compute_max_speed(self._h, _ptr(u), C.byref(c)))
+        return c.value
+
+    def evolve(self, u, tend, max_iter=-1):
+        u = np.array(u, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_fvm1d_evolve(self._h, _ptr(u), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt)))
+        return u, it.value, t.value, dt.value
+
+
+class FV1DParams(C.Structure):
+    """wb_fv1d_params; defaults follow parameters.f90."""
+    _fields_ = [("nx", C.c_int), ("nvar", C.c_int), ("bc", C.c_int), ("nequilibrium", C.c_int), ("solver", C.c_int),
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("device", C.c_int)]
+
+
+SOLVERS_1D = {"FVM": 1, "EQL": 2, "WB1": 3}
+
+
+class FV1D(_Handle):
+    """benchmark_1d.f90: 'FVM' | 'EQL' | 'WB1'.  u(nvar,nx) == numpy (nx, 3)."""
+    _destroy = "wb_fv1d_destroy"
+
+    def __init__(self, nx=128, bc=2, nequilibrium=2, solver="WB1", gamma=F32(1.4), boxlen=1.0, device=-1):
+        self.params = FV1DParams(nx, 3, bc, nequilibrium, SOLVERS_1D[solver], gamma, boxlen, device)
+        self._h = C.c_void_p()
+        _check(lib().wb_fv1d_create(C.byref(self._h), C.byref(self.params)))
+        self.shape = (nx, 3)
+
+    def _upd(self, fn, u, w_eq):
+        d = np.empty(self.shape)
+        _check(getattr(lib(), fn)(self._h, _ptr(u), _ptr(w_eq) if w_eq is not None else None, _ptr(d)))
+        return d
+
+    def compute_update(self, u, w_eq):
+        """compute_update ('EQL')  benchmark_1d.f90:263-377"""
+        return self._upd("wb_fv1d_compute_update", u, w_eq)
+
+    def compute_update_fvm(self, u, w_eq):
+        """compute_update_fvm ('FVM')  benchmark_1d.f90:454-549"""
+        return self._upd("wb_fv1d_compute_update_fvm", u, w_eq)
+
+    def compute_update_sr(self, u, w_eq=None):
+        """compute_update_sr ('WB1')  benchmark_1d.f90:553-747"""
+        return self._upd("wb_fv1d_compute_update_sr", u, w_eq)
+
+    def compute_max_speed(self, u):
+        c = C.c_double()
+        _check(lib().wb_fv1d_compute_max_speed(self._h, _ptr(u), C.byref(c)))
+        return c.value
+
+    def evolve(self, u, w_eq, tend, max_iter=-1):
+        """evolve(u,u_eq,x)  benchmark_1d.f90:200-261"""
+        u = np.array(u, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_fv1d_evolve(self._h, _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter), C.byref(it),
+                                    C.byref(t), C.byref(dt)))
+        return u, it.value, t.value, dt.value

@@ -159,6 +159,57 @@ int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out)
 int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out);
 int wb_dg2d_download_modes(wb_dg2d* h, double* modes_out);
 
+/* ==========================================================================================
+ * 1D finite volumes.  Host layout u(nvar,nx) == C double[nx][3].
+ * ========================================================================================== */
+/* ---- fvm.f90 (module fvm_commons.f90): plain first-order FV, LLF, centred gravity source, SSP-RK2 ---- */
+typedef struct wb_fvm1d wb_fvm1d;
+typedef struct {
+  int nx;          /* fvm_commons.f90:6                                   */
+  int nvar;        /* must be 3 (:7)                                      */
+  int bc;          /* :13   1 periodic, 2 zero gradient                   */
+  int source;      /* :14   1 none, 2 gravity (compute_source :253-264)   */
+  int n;           /* :4    only enters dt = 0.8*dx/cmax/(2n+1) (fvm.f90:59) */
+  double gamma;    /* :17                                                 */
+  double boxlen;   /* :16                                                 */
+  int device;
+} wb_fvm1d_params;
+int wb_fvm1d_create(wb_fvm1d** h, const wb_fvm1d_params* p);
+int wb_fvm1d_destroy(wb_fvm1d* h);
+/* replaces compute_update(u,dudt)      fvm.f90:188-251 */
+int wb_fvm1d_compute_update(wb_fvm1d* h, const double* u, double* dudt);
+/* replaces compute_max_speed(u,cmax)   fvm.f90:314-330 */
+int wb_fvm1d_compute_max_speed(wb_fvm1d* h, const double* u, double* cmax);
+/* replaces the main time loop          fvm.f90:56-76 */
+int wb_fvm1d_evolve(wb_fvm1d* h, double* u_inout, double tend, int max_iter, int* iters_out, double* t_out,
+                    double* last_dt_out);
+
+/* ---- benchmark_1d.f90 (module parameters.f90): 'FVM' | 'EQL' | 'WB1' -------------------------------- */
+typedef struct wb_fv1d wb_fv1d;
+typedef struct {
+  int nx;            /* parameters.f90:3                                                      */
+  int nvar;          /* must be 3 (:4)                                                        */
+  int bc;            /* :12   1 periodic, 2 zero gradient, 3 reflexive                        */
+  int nequilibrium;  /* :13   1|2 isothermal exp(-x), 3 isentropic                            */
+  int solver;        /* :8    1 'FVM', 2 'EQL', 3 'WB1' (default)                             */
+  double gamma;      /* :17                                                                   */
+  double boxlen;     /* :16                                                                   */
+  int device;
+} wb_fv1d_params;
+int wb_fv1d_create(wb_fv1d** h, const wb_fv1d_params* p);
+int wb_fv1d_destroy(wb_fv1d* h);
+/* replaces compute_update(u,w_eq,dudt) ('EQL')        benchmark_1d.f90:263-377 */
+int wb_fv1d_compute_update(wb_fv1d* h, const double* u, const double* w_eq, double* dudt);
+/* replaces compute_update_fvm(u,w_eq,dudt) ('FVM')    benchmark_1d.f90:454-549 */
+int wb_fv1d_compute_update_fvm(wb_fv1d* h, const double* u, const double* w_eq, double* dudt);
+/* replaces compute_update_sr(u,w_eq,dudt) ('WB1')     benchmark_1d.f90:553-747 (w_eq is not read, may be NULL) */
+int wb_fv1d_compute_update_sr(wb_fv1d* h, const double* u, const double* w_eq, double* dudt);
+/* replaces compute_max_speed(u,cmax)                  benchmark_1d.f90:154-165 */
+int wb_fv1d_compute_max_speed(wb_fv1d* h, const double* u, double* cmax);
+/* replaces evolve(u,u_eq,x)                           benchmark_1d.f90:200-261 (scheme = params.solver) */
+int wb_fv1d_evolve(wb_fv1d* h, double* u_inout, const double* w_eq, double tend, int max_iter, int* iters_out,
+                   double* t_out, double* last_dt_out);
+
 #ifdef __cplusplus
 }
 #endif

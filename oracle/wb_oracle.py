@@ -226,3 +226,100 @@ def dg2d_evolve(p, nodes, x, y, tend, max_iter=-1):
     lib().orc_dg2d_evolve(C.byref(p), _ptr(u), _ptr(x), _ptr(y), C.c_double(tend), C.c_int(max_iter),
                           C.byref(it), C.byref(t), C.byref(dt))
     return u, it.value, t.value, dt.value
+
+
+# ---------------------------------------------------------------- 1D FV (fvm.f90, benchmark_1d.f90)
+class FVM1DParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("bc", C.c_int), ("source", C.c_int), ("n", C.c_int), ("gamma", C.c_double),
+                ("boxlen", C.c_double)]
+
+
+def fvm1d_params(nx=200, bc=2, source=2, n=3, gamma=F32(1.4), boxlen=1.0):
+    return FVM1DParams(nx, bc, source, n, gamma, boxlen)
+
+
+def fvm1d_initial_conditions(p, ninit=4):
+    u = np.empty((p.nx, 3))
+    lib().orc_fvm1d_initial_conditions(C.byref(p), C.c_int(ninit), _ptr(u))
+    return u
+
+
+def fvm1d_compute_update(p, u):
+    d = np.empty_like(u)
+    lib().orc_fvm1d_compute_update(C.byref(p), _ptr(u), _ptr(d))
+    return d
+
+
+def fvm1d_compute_max_speed(p, u):
+    c = C.c_double()
+    lib().orc_fvm1d_compute_max_speed(C.byref(p), _ptr(u), C.byref(c))
+    return c.value
+
+
+def fvm1d_evolve(p, u, tend, max_iter=-1):
+    u = np.array(u, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_fvm1d_evolve(C.byref(p), _ptr(u), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt))
+    return u, it.value, t.value, dt.value
+
+
+class FV1DParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("bc", C.c_int), ("nequilibrium", C.c_int), ("solver", C.c_int), ("gamma", C.c_double),
+                ("boxlen", C.c_double)]
+
+
+SOLVERS_1D = {"FVM": 1, "EQL": 2, "WB1": 3}
+
+
+def fv1d_params(nx=128, bc=2, nequilibrium=2, solver="WB1", gamma=F32(1.4), boxlen=1.0):
+    return FV1DParams(nx, bc, nequilibrium, SOLVERS_1D[solver], gamma, boxlen)
+
+
+def fv1d_get_x(p):
+    x = np.empty(p.nx)
+    lib().orc_fv1d_get_x(C.byref(p), _ptr(x))
+    return x
+
+
+def fv1d_get_equilibrium_solution(p, x):
+    w = np.empty((x.size, 3))
+    lib().orc_fv1d_get_equilibrium_solution(C.byref(p), _ptr(x), _ptr(w), C.c_int(x.size))
+    return w
+
+
+def fv1d_get_initial_conditions(p, ninit, x, eta=F32(1e-8)):
+    u = np.empty((p.nx, 3))
+    lib().orc_fv1d_get_initial_conditions(C.byref(p), C.c_int(ninit), C.c_double(eta), _ptr(x), _ptr(u))
+    return u
+
+
+def _fv1d_upd(fn, p, u, w_eq):
+    d = np.empty_like(u)
+    getattr(lib(), fn)(C.byref(p), _ptr(u), _ptr(w_eq), _ptr(d))
+    return d
+
+
+def fv1d_compute_update(p, u, w_eq):
+    return _fv1d_upd("orc_fv1d_compute_update", p, u, w_eq)
+
+
+def fv1d_compute_update_fvm(p, u, w_eq):
+    return _fv1d_upd("orc_fv1d_compute_update_fvm", p, u, w_eq)
+
+
+def fv1d_compute_update_sr(p, u, w_eq):
+    return _fv1d_upd("orc_fv1d_compute_update_sr", p, u, w_eq)
+
+
+def fv1d_compute_max_speed(p, u):
+    c = C.c_double()
+    lib().orc_fv1d_compute_max_speed(C.byref(p), _ptr(u), C.byref(c))
+    return c.value
+
+
+def fv1d_evolve(p, u, w_eq, tend, max_iter=-1):
+    u = np.array(u, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_fv1d_evolve(C.byref(p), _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t),
+                          C.byref(dt))
+    return u, it.value, t.value, dt.value

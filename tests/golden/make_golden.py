@@ -69,8 +69,35 @@ def dg2d():
     np.savez_compressed(os.path.join(HERE, "dg2d.npz"), **out)
 
 
+def fv1d():
+    out = {}
+    for tag, nx, bc, source, ninit, steps in (("fvm_sod", 200, 2, 2, 4, 5), ("fvm_sine_periodic", 64, 1, 1, 1, 5),
+                                              ("fvm_hydro", 50, 2, 2, 7, 4)):
+        p = o.fvm1d_params(nx=nx, bc=bc, source=source)
+        u0 = o.fvm1d_initial_conditions(p, ninit)
+        out[f"{tag}_meta"] = np.array([0, nx, bc, source, steps])
+        out[f"{tag}_u0"] = u0
+        out[f"{tag}_dudt"] = o.fvm1d_compute_update(p, u0)
+        un, it, t, dt = o.fvm1d_evolve(p, u0, 1.0, steps)
+        out[f"{tag}_un"] = un; out[f"{tag}_clock"] = np.array([it, t, dt])
+    for tag, nx, bc, neq, solver, ninit, eta, steps in (("b1_wb1_default", 128, 2, 2, "WB1", 2, o.F32(1e-8), 5),
+                                                        ("b1_wb1_isentropic", 64, 2, 3, "WB1", 3, 0.0, 4),
+                                                        ("b1_eql_bump", 96, 2, 2, "EQL", 2, 1e-3, 5),
+                                                        ("b1_eql_bc3", 40, 3, 2, "EQL", 2, 1e-3, 3),
+                                                        ("b1_fvm_bump", 77, 1, 2, "FVM", 2, 1e-3, 4)):
+        p = o.fv1d_params(nx=nx, bc=bc, nequilibrium=neq, solver=solver)
+        x = o.fv1d_get_x(p); weq = o.fv1d_get_equilibrium_solution(p, x); u0 = o.fv1d_get_initial_conditions(p, ninit, x, eta)
+        fn = {"FVM": o.fv1d_compute_update_fvm, "EQL": o.fv1d_compute_update, "WB1": o.fv1d_compute_update_sr}[solver]
+        out[f"{tag}_meta"] = np.array([1, nx, bc, neq, p.solver, steps])
+        out[f"{tag}_u0"] = u0; out[f"{tag}_weq"] = weq
+        out[f"{tag}_dudt"] = fn(p, u0, weq)
+        un, it, t, dt = o.fv1d_evolve(p, u0, weq, 1.0, steps)
+        out[f"{tag}_un"] = un; out[f"{tag}_clock"] = np.array([it, t, dt])
+    np.savez_compressed(os.path.join(HERE, "fv1d.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fv2d", "dg2d"]
+    which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d"]
     for w in which:
         globals()[w]()
         print("wrote", w)
