@@ -1,0 +1,406 @@
+// 1D modal DG on the perturbation (dg_with_source.f90, default integrator 'RKi'): compute_update_exact_delta
+// (:1749-2031), riemann_hllc / riemann_llf (:1318-1374 / :1299-1316), the nodal reconstruction and time-step control
+// of the main loop (:173-336).  Basis and quadrature follow the ROOT legendre.f90 (single-precision normalisation
+// constants, hard-coded single-precision GL rules for n <= 3).
+//
+// A correctness configuration of the reference (nx ~ 128): one thread per cell, reference operation order (file
+// compiled with -fmad=false), data kept in the reference's u(nvar,n,nx) layout.  Differences to the CPU restatement
+// come only from exp() in the face equilibria.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace wb { namespace dg1d {
+
+constexpr int NV = 3;
+constexpr int MAXN = 4;
+
+struct Basis1 { double xq[MAXN], wq[MAXN], P[MAXN][MAXN], dP[MAXN][MAXN], Em[MAXN], Ep[MAXN]; double s05, s6, s10; };
+struct P1d { int n, nx, riemann, source; double gamma, boxlen; };
+struct CtrlD { double t, dt, tend, cmax; int iter, max_iter, skip; };
+
+// ---- host: root legendre.f90 ------------------------------------------------------------------------------
+static double h_legendre(double& x, int n) {                         // :1-25
+  x = std::fmin(std::fmax(x, (double)-1.0f), (double)1.0f);
+  switch (n) {
+    case 0: return (double)(1.0f * sqrtf(0.5f));
+    case 1: return x * 0.5 * (double)sqrtf(6.f);
+    case 2: return 0.25 * (3.0 * (x * x) - 1.0) * (double)sqrtf(10.f);
+    case 3: return 0.5 * (5.0 * ((x * x) * x) - 3.0 * x);
+    default: return 0.0;
+  }
+}
+static double h_legendre_prime(double& x, int n) {                   // :27-50
+  x = std::fmin(std::fmax(x, (double)-1.0f), (double)1.0f);
+  switch (n) {
+    case 0: return 0.0;
+    case 1: return (double)(1.0f * 0.5f * sqrtf(6.f));
+    case 2: return 6.0 * x * 0.25 * (double)sqrtf(10.f);
+    case 3: return 0.5 * (15.0 * (x * x) - 3.0);
+    default: return 0.0;
+  }
+}
+static void h_gl_quadrature(double* x, double* w, int n) {           // :77-128 (n <= 3: the hard-coded real(4) rules)
+  if (n == 1) { x[0] = 0.0; w[0] = 2.0; return; }
+  if (n == 2) {
+    x[0] = -1.f / (double)3 * (double)sqrtf(3.f); x[1] = 1.f / (double)3 * (double)sqrtf(3.f);
+    w[0] = 1.; w[1] = 1.;
+    return;
+  }
+  x[0] = (double)(-sqrtf(3.f) / sqrtf(5.f)); x[1] = 0.0; x[2] = (double)(sqrtf(3.f) / sqrtf(5.f));
+  w[0] = (double)(5.f / 9.f); w[1] = (double)(8.f / 9.f); w[2] = (double)(5.f / 9.f);
+}
+static Basis1 make_basis(int n) {
+  Basis1 B;
+  std::memset(&B, 0, sizeof(B));
+  h_gl_quadrature(B.xq, B.wq, n);
+  for (int q = 0; q < n; ++q)
+    for (int m = 0; m < n; ++m) {
+      double x = B.xq[q]; B.P[q][m] = h_legendre(x, m);
+      x = B.xq[q]; B.dP[q][m] = h_legendre_prime(x, m);
+    }
+  for (int m = 0; m < n; ++m) { double a = -1.0, b = 1.0; B.Em[m] = h_legendre(a, m); B.Ep[m] = h_legendre(b, m); }
+  B.s05 = (double)(1.0f * sqrtf(0.5f)); B.s6 = (double)sqrtf(6.f); B.s10 = (double)sqrtf(10.f);   // real(4) constants of legendre.f90
+  return B;
+}
+
+// ---- device physics (dg_with_source.f90:1167-1246) -----------------------------------------------------------
+__device__ __forceinline__ void prim(const double* u, double* w, double gamma) {
+  w[0] = u[0];
+  w[1] = u[1] / w[0];
+  w[2] = (gamma - (double)1.0f) * (u[2] - 0.5 * w[0] * (w[1] * w[1]));
+}
+__device__ __forceinline__ void cons(const double* w, double* u, double gamma) {
+  u[0] = w[0];
+  u[1] = w[0] * w[1];
+  u[2] = w[2] / (gamma - (double)1.0f) + 0.5 * w[0] * (w[1] * w[1]);
+}
+__device__ __forceinline__ void flux(const double* u, double* f, double gamma) {
+  double w[NV];
+  prim(u, w, gamma);
+  f[0] = w[1] * u[0];
+  f[1] = w[1] * u[1] + w[2];
+  f[2] = w[1] * u[2] + w[2] * w[1];
+}
+__device__ __forceinline__ void source_term(const double* u, double* s, double gamma) {
+  double w[NV];
+  prim(u, w, gamma);
+  s[0] = 0;
+  s[1] = -w[0];
+  s[2] = -w[0] * w[1];
+}
+__device__ __forceinline__ double speed(const double* u, double gamma) {
+  double w[NV];
+  prim(u, w, gamma);
+  double cs = sqrt(gamma * fmax(w[2], 1e-10) / fmax(w[0], 1e-10));
+  return fabs(w[1]) + cs;
+}
+__device__ __forceinline__ void riemann_llf(const double* ul, const double* ur, double* fg, double gamma) {   // :1299-1316
+  double cl = speed(ul, gamma), cr = speed(ur, gamma), cmax = fmax(cl, cr), fl[NV], fr[NV];
+  flux(ul, fl, gamma);
+  flux(ur, fr, gamma);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) fg[v] = 0.5 * (fr[v] + fl[v]) - 0.5 * cmax * (ur[v] - ul[v]);
+}
+__device__ __forceinline__ void riemann_hllc(const double* ul, const double* ur, double* fg, double gamma) {  // :1318-1374
+  double wl[NV], wr[NV];
+  prim(ul, wl, gamma);
+  prim(ur, wr, gamma);
+  double cl = sqrt(gamma * fmax(wl[2], 1e-10) / fmax(wl[0], 1e-10));
+  double cr = sqrt(gamma * fmax(wr[2], 1e-10) / fmax(wr[0], 1e-10));
+  double SL = fmin(wl[1], wr[1]) - fmax(cl, cr);
+  double SR = fmax(wl[1], wr[1]) + fmax(cl, cr);
+  double DL = wl[0] * (wl[1] - SL);
+  double DR = wr[0] * (SR - wr[1]);
+  double ws2 = (DR * wr[1] + DL * wl[1] + (wl[2] - wr[2])) / (DL + DR);
+  double ws3 = (DR * wl[2] + DL * wr[2] + DL * DR * (wl[1] - wr[1])) / (DL + DR);
+  double wsl1 = wl[0] * (SL - wl[1]) / (SL - ws2);
+  double usl3 = ((SL - wl[1]) * ul[2] - wl[2] * wl[1] + ws3 * ws2) / (SL - ws2);
+  double wsr1 = wr[0] * (SR - wr[1]) / (SR - ws2);
+  double usr3 = ((SR - wr[1]) * ur[2] - wr[2] * wr[1] + ws3 * ws2) / (SR - ws2);
+  double g1, g2, g3, e3;
+  if (SL > 0.0) { g1 = wl[0]; g2 = wl[1]; g3 = wl[2]; e3 = ul[2]; }
+  else if (ws2 > 0.0) { g1 = wsl1; g2 = ws2; g3 = ws3; e3 = usl3; }
+  else if (SR > 0.0) { g1 = wsr1; g2 = ws2; g3 = ws3; e3 = usr3; }
+  else { g1 = wr[0]; g2 = wr[1]; g3 = wr[2]; e3 = ur[2]; }
+  fg[0] = g1 * g2;
+  fg[1] = g1 * g2 * g2 + g3;
+  fg[2] = g2 * (e3 + g3);
+}
+
+#define M3(a, v, i, c) ((a)[((size_t)(c) * P.n + (i)) * NV + (v)])
+
+// compute_update_exact_delta :1749-2031, one thread per cell
+__global__ void k_dg1_update(const double* __restrict__ du, const double* __restrict__ u_eq, double* __restrict__ dudt,
+                             P1d P, Basis1 B, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;     // 0-based cell
+  if (ic >= P.nx) return;
+  const int n = P.n, nx = P.nx;
+  const double gamma = P.gamma;
+  if (ic == 0 || ic == nx - 1) {                      // dudt(:,:,1) = dudt(:,:,nx) = 0   :2028-2029
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) M3(dudt, v, i, ic) = 0;
+    return;
+  }
+  const double dx = P.boxlen / (double)nx, oneoverdx = 1. / dx;
+  // face equilibria at x = ic*dx and (ic+1)*dx (0-based cell ic has faces ic+1 and ic+2 in the 1-based reference)
+  double ufe[2][NV], ffe[2][NV];
+  for (int k = 0; k < 2; ++k) {
+    double xf = (double)(ic + k) * dx;
+    double w[NV] = {exp(-xf), 0, exp(-xf)};
+    cons(w, ufe[k], gamma);
+    flux(ufe[k], ffe[k], gamma);
+  }
+  // volume terms of the cell
+  double fq[MAXN][NV], fqe[MAXN][NV], sq[MAXN][NV], sqe[MAXN][NV];
+  for (int j = 0; j < n; ++j) {
+    double uq[NV] = {0, 0, 0}, us[NV], ue[NV];
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) uq[v] = uq[v] + M3(du, v, i, ic) * B.P[j][i];
+    for (int v = 0; v < NV; ++v) { ue[v] = M3(u_eq, v, j, ic); us[v] = ue[v] + uq[v]; }
+    flux(us, fq[j], gamma);
+    flux(ue, fqe[j], gamma);
+    source_term(us, sq[j], gamma);
+    source_term(ue, sqe[j], gamma);
+  }
+  // traces: own left/right, left neighbour's right, right neighbour's left
+  auto trace = [&](int c, const double* E, double* out) {
+    for (int v = 0; v < NV; ++v) out[v] = 0.;
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) out[v] = out[v] + M3(du, v, i, c) * E[i];
+  };
+  double dl[NV], dr[NV], dnl[NV], dnr[NV];
+  trace(ic, B.Em, dl); trace(ic, B.Ep, dr);
+  trace(ic - 1, B.Ep, dnl); trace(ic + 1, B.Em, dnr);
+  double u_left[NV], u_right[NV], ul_n[NV], ur_n[NV], F0[NV], F1[NV];
+  for (int v = 0; v < NV; ++v) {
+    u_left[v] = ufe[0][v] + dl[v];        // u_left(icell)  = u_face_eq(icell)   + trace(-1)
+    u_right[v] = ufe[1][v] + dr[v];       // u_right(icell) = u_face_eq(icell+1) + trace(+1)
+    ul_n[v] = ufe[0][v] + dnl[v];         // u_right(icell-1)
+    ur_n[v] = ufe[1][v] + dnr[v];         // u_left(icell+1)
+  }
+  if (P.riemann == 1) { riemann_llf(ul_n, u_left, F0, gamma); riemann_llf(u_right, ur_n, F1, gamma); }
+  else { riemann_hllc(ul_n, u_left, F0, gamma); riemann_hllc(u_right, ur_n, F1, gamma); }
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) {
+      double fv = 0.0, fve = 0.0, sv = 0.0, sve = 0.0;
+      for (int j = 0; j < n; ++j) {
+        fv = fv + fq[j][v] * B.dP[j][i] * B.wq[j];
+        fve = fve + fqe[j][v] * B.dP[j][i] * B.wq[j];
+        if (P.source == 2) {
+          sv = sv + sq[j][v] * B.P[j][i] * B.wq[j] * 0.5;
+          sve = sve + sqe[j][v] * B.P[j][i] * B.wq[j] * 0.5;
+        }
+      }
+      M3(dudt, v, i, ic) = oneoverdx * fv - oneoverdx * fve - oneoverdx * (F1[v] * B.Ep[i] - F0[v] * B.Em[i])
+                           + oneoverdx * (ffe[1][v] * B.Ep[i] - ffe[0][v] * B.Em[i]) + sv - sve;
+    }
+}
+
+// nodal reconstruction :313-330: legendre at the PHYSICAL coordinate (clamped to [-1,1]), as shipped
+__device__ __forceinline__ double d_legendre(const Basis1& B, double& x, int n) {
+  x = fmin(fmax(x, (double)-1.0f), (double)1.0f);
+  switch (n) {
+    case 0: return B.s05;                                     // 1.0*sqrt(0.5) in real(4)
+    case 1: return x * 0.5 * B.s6;                            // sqrt(6.) in real(4)
+    case 2: return 0.25 * (3.0 * (x * x) - 1.0) * B.s10;      // sqrt(10.) in real(4)
+    case 3: return 0.5 * (5.0 * ((x * x) * x) - 3.0 * x);
+    default: return 0.0;
+  }
+}
+__global__ void k_dg1_reconstruct(const double* __restrict__ du, const double* __restrict__ u_eq, double* __restrict__ uinit,
+                                  P1d P, Basis1 B, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ic >= P.nx) return;
+  const double dx = P.boxlen / (double)P.nx;
+  const double xcell = ((double)(ic + 1) - 0.5) * dx;
+  for (int i = 0; i < P.n; ++i) {
+    double xq = xcell + dx / 2.0 * B.xq[i];
+    for (int v = 0; v < NV; ++v) {
+      double a = 0.0;
+      for (int m = 0; m < P.n; ++m) a = a + M3(du, v, m, ic) * d_legendre(B, xq, m);
+      M3(uinit, v, i, ic) = M3(u_eq, v, i, ic) + a;
+    }
+  }
+}
+// compute_max_speed :1136-1152 (first node of each cell) and dt = 0.9*dx/cmax/(2n+1) (:178)
+__global__ void k_dg1_max_speed(const double* __restrict__ u_nodes, P1d P, CtrlD* ctrl, int set_dt) {
+  __shared__ double sh[256];
+  double m = 0.0;
+  for (int c = threadIdx.x; c < P.nx; c += blockDim.x) m = fmax(m, speed(u_nodes + (size_t)c * P.n * NV, P.gamma));
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ctrl->cmax = sh[0];
+    if (set_dt) {
+      const bool done = !(ctrl->t < ctrl->tend) || (ctrl->max_iter >= 0 && ctrl->iter >= ctrl->max_iter);
+      ctrl->skip = done ? 1 : 0;
+      if (!done) ctrl->dt = (double)0.9f * (P.boxlen / (double)P.nx) / sh[0] / (2.0 * (double)P.n + 1.0);
+    }
+  }
+}
+// out = c0*A0 [+ c1*A1] + (cd*dt)*D, left to right
+__global__ void k_dg1_axpy(double* out, const double* A0, double c0, const double* A1, double c1, const double* D, double cd,
+                           int n, int na, const CtrlD* ctrl) {
+  if (ctrl->skip) return;
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double cdt = cd * ctrl->dt;
+  double r = (c0 == 1.0) ? A0[k] : c0 * A0[k];
+  if (na == 2) r = r + c1 * A1[k];
+  out[k] = r + cdt * D[k];
+}
+__global__ void k_dg1_advance(CtrlD* c) { if (c->skip) return; c->t = c->t + c->dt; c->iter = c->iter + 1; }
+__global__ void k_dg1_ctrl_init(CtrlD* c, double tend, int max_iter) {
+  c->t = 0.0; c->iter = 0; c->dt = 0.0; c->tend = tend; c->max_iter = max_iter; c->skip = 0;
+}
+
+}}  // namespace wb::dg1d
+
+using namespace wb;
+using namespace wb::dg1d;
+
+struct wb_dg1d {
+  P1d P;
+  Basis1 B;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  size_t N = 0;
+  double *du = nullptr, *ueq = nullptr, *uinit = nullptr, *dudt = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+  CtrlD* ctrl = nullptr;
+  CtrlD* h_ctrl = nullptr;
+};
+
+#define F32(x) ((double)(x##f))
+
+extern "C" {
+
+int wb_dg1d_create(wb_dg1d** out, const wb_dg1d_params* p) {
+  if (!out || !p) { set_error("null argument"); return WB_ERR_ARG; }
+  *out = nullptr;
+  WB_REQUIRE(p->nvar == 3, "nvar must be 3 (got %d)", p->nvar);
+  WB_REQUIRE(p->n >= 1 && p->n <= 3, "n must be 1..3 (the hard-coded quadrature rules of the root legendre.f90)");
+  WB_REQUIRE(p->nx >= 3, "nx must be >= 3");
+  WB_REQUIRE(p->riemann == 1 || p->riemann == 2, "riemann must be 1 (llf) or 2 (hllc)");
+  WB_REQUIRE(p->source == 1 || p->source == 2, "source must be 1 or 2");
+  WB_REQUIRE(p->gamma > 1.0 && p->boxlen > 0, "gamma>1, boxlen>0 required");
+  int dev = 0;
+  WB_CHECK(select_device(p->device, &dev));
+  wb_dg1d* h = new wb_dg1d;
+  h->dev = dev;
+  h->P.n = p->n; h->P.nx = p->nx; h->P.riemann = p->riemann; h->P.source = p->source; h->P.gamma = p->gamma; h->P.boxlen = p->boxlen;
+  h->B = make_basis(p->n);
+  h->N = (size_t)NV * p->n * p->nx;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  double** bufs[] = {&h->du, &h->ueq, &h->uinit, &h->dudt, &h->w1, &h->w2, &h->w3, &h->w4};
+  for (double** b : bufs)
+    if (e == cudaSuccess) e = cudaMalloc(b, sizeof(double) * h->N);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ctrl, sizeof(CtrlD));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(CtrlD));
+  if (e == cudaSuccess) e = cudaMemset(h->ctrl, 0, sizeof(CtrlD));
+  if (e != cudaSuccess) { set_error("dg1d allocation failed: %s", cudaGetErrorString(e)); wb_dg1d_destroy(h); return WB_ERR_CUDA; }
+  *out = h;
+  return WB_OK;
+}
+int wb_dg1d_destroy(wb_dg1d* h) {
+  if (!h) return WB_OK;
+  cudaSetDevice(h->dev);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  cudaFree(h->du); cudaFree(h->ueq); cudaFree(h->uinit); cudaFree(h->dudt); cudaFree(h->w1); cudaFree(h->w2); cudaFree(h->w3);
+  cudaFree(h->w4); cudaFree(h->ctrl);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  delete h;
+  return WB_OK;
+}
+int wb_dg1d_quadrature(wb_dg1d* h, double* x, double* w) {
+  if (!h || !x || !w) { set_error("null argument"); return WB_ERR_ARG; }
+  for (int i = 0; i < h->P.n; ++i) { x[i] = h->B.xq[i]; w[i] = h->B.wq[i]; }
+  return WB_OK;
+}
+int wb_dg1d_compute_update_exact_delta(wb_dg1d* h, const double* delta_u, const double* u_eq, double* dudt) {
+  if (!h || !delta_u || !u_eq || !dudt) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, delta_u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->ueq, u_eq, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_update<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->du, h->ueq, h->dudt, h->P, h->B, nullptr);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(dudt, h->dudt, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+int wb_dg1d_compute_max_speed(wb_dg1d* h, const double* u_nodes, double* cmax) {
+  if (!h || !u_nodes || !cmax) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CUDA(cudaMemcpyAsync(h->uinit, u_nodes, sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_max_speed<<<1, 256, 0, h->stream>>>(h->uinit, h->P, h->ctrl, 0);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(CtrlD), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  *cmax = h->h_ctrl->cmax;
+  return WB_OK;
+}
+// main loop with integrator 'RKi' (:173-336, :282-305)
+int wb_dg1d_evolve(wb_dg1d* h, double* delta_u, const double* u_eq, double* uinit, double tend, int max_iter, int* iters,
+                   double* t_out, double* dt_out) {
+  if (!h || !delta_u || !u_eq || !uinit) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  const int N = (int)h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, delta_u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->ueq, u_eq, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->uinit, uinit, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, tend, max_iter);
+  WB_LAUNCH_CHECK();
+  dim3 bc(64), gc((h->P.nx + 63) / 64), ba(128), ga((N + 127) / 128);
+  auto upd = [&](const double* in) {
+    k_dg1_update<<<gc, bc, 0, h->stream>>>(in, h->ueq, h->dudt, h->P, h->B, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto axpy = [&](double* out, const double* A0, double c0, const double* A1, double c1, double cd, int na) {
+    k_dg1_axpy<<<ga, ba, 0, h->stream>>>(out, A0, c0, A1, c1, h->dudt, cd, N, na, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  int it = 0;
+  double t = 0.0, dt = 0.0;
+  for (;;) {
+    if (!(t < tend) || (max_iter >= 0 && it >= max_iter)) break;
+    for (int s = 0; s < 16; ++s) {
+      k_dg1_max_speed<<<1, 256, 0, h->stream>>>(h->uinit, h->P, h->ctrl, 1);
+      wb::g_launches.fetch_add(1);
+      upd(h->du);
+      axpy(h->w1, h->du, 1.0, nullptr, 0.0, F32(0.391752226571890), 1);
+      upd(h->w1);
+      axpy(h->w2, h->du, F32(0.444370493651235), h->w1, F32(0.555629506348765), F32(0.368410593050371), 2);
+      upd(h->w2);
+      axpy(h->w3, h->du, F32(0.620101851488403), h->w2, F32(0.379898148511597), F32(0.251891774271694), 2);
+      upd(h->w3);
+      axpy(h->w4, h->du, F32(0.178079954393132), h->w3, F32(0.821920045606868), F32(0.544974750228521), 2);
+      axpy(h->du, h->w2, F32(0.517231671970585), h->w3, F32(0.096059710526147), F32(0.063692468666290), 2);
+      upd(h->w4);
+      axpy(h->du, h->du, 1.0, h->w4, F32(0.386708617503269), F32(0.226007483236906), 2);
+      k_dg1_reconstruct<<<gc, bc, 0, h->stream>>>(h->du, h->ueq, h->uinit, h->P, h->B, h->ctrl);
+      k_dg1_advance<<<1, 1, 0, h->stream>>>(h->ctrl);
+      wb::g_launches.fetch_add(2);
+    }
+    WB_CUDA(cudaGetLastError());
+    WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(CtrlD), cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+    it = h->h_ctrl->iter; t = h->h_ctrl->t; dt = h->h_ctrl->dt;
+  }
+  WB_CUDA(cudaMemcpyAsync(delta_u, h->du, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaMemcpyAsync(uinit, h->uinit, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (iters) *iters = it;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  return WB_OK;
+}
+
+}  // extern "C"

@@ -395,3 +395,46 @@ class FV1D(_Handle):
         _check(lib().wb_fv1d_evolve(self._h, _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter), C.byref(it),
                                     C.byref(t), C.byref(dt)))
         return u, it.value, t.value, dt.value
+
+
+# ================================================================================================== 1D DG
+class DG1DParams(C.Structure):
+    """wb_dg1d_params; defaults follow dg_commons.f90."""
+    _fields_ = [("n", C.c_int), ("nx", C.c_int), ("nvar", C.c_int), ("riemann", C.c_int), ("source", C.c_int),
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("device", C.c_int)]
+
+
+class DG1D(_Handle):
+    """dg_with_source.f90, integrator 'RKi' (perturbation form).  u(nvar,n,nx) == numpy (nx, n, 3)."""
+    _destroy = "wb_dg1d_destroy"
+
+    def __init__(self, n=3, nx=128, riemann=2, source=2, gamma=F32(1.4), boxlen=1.0, device=-1):
+        self.params = DG1DParams(n, nx, 3, riemann, source, gamma, boxlen, device)
+        self._h = C.c_void_p()
+        _check(lib().wb_dg1d_create(C.byref(self._h), C.byref(self.params)))
+        self.shape = (nx, n, 3)
+
+    def quadrature(self):
+        x = np.zeros(self.params.n); w = np.zeros(self.params.n)
+        _check(lib().wb_dg1d_quadrature(self._h, _ptr(x), _ptr(w)))
+        return x, w
+
+    def compute_update_exact_delta(self, delta_u, u_eq):
+        """compute_update_exact_delta(delta_u,u_eq,dudt)  dg_with_source.f90:1749-2031"""
+        d = np.empty(self.shape)
+        _check(lib().wb_dg1d_compute_update_exact_delta(self._h, _ptr(delta_u), _ptr(u_eq), _ptr(d)))
+        return d
+
+    def compute_max_speed(self, u_nodes):
+        c = C.c_double()
+        _check(lib().wb_dg1d_compute_max_speed(self._h, _ptr(u_nodes), C.byref(c)))
+        return c.value
+
+    def evolve(self, delta_u, u_eq, uinit, tend, max_iter=-1):
+        """main loop, integrator 'RKi'  dg_with_source.f90:173-336 -> (delta_u, uinit, iters, t, last_dt)"""
+        d = np.array(delta_u, dtype=np.float64, order="C", copy=True)
+        ui = np.array(uinit, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_dg1d_evolve(self._h, _ptr(d), _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it),
+                                    C.byref(t), C.byref(dt)))
+        return d, ui, it.value, t.value, dt.value

@@ -210,6 +210,34 @@ int wb_fv1d_compute_max_speed(wb_fv1d* h, const double* u, double* cmax);
 int wb_fv1d_evolve(wb_fv1d* h, double* u_inout, const double* w_eq, double tend, int max_iter, int* iters_out,
                    double* t_out, double* last_dt_out);
 
+/* ==========================================================================================
+ * 1D modal DG on the perturbation -- dg_with_source.f90 (module dg_commons.f90, basis: root legendre.f90),
+ * default integrator 'RKi'.  Host layout u(nvar,n,nx) == C double[nx][n][3].
+ * ========================================================================================== */
+typedef struct wb_dg1d wb_dg1d;
+typedef struct {
+  int n;           /* dg_commons.f90:4 (nquad = n), 1..3                          */
+  int nx;          /* :6                                                          */
+  int nvar;        /* must be 3 (:8)                                              */
+  int riemann;     /* :9    1 riemann_llf, 2 riemann_hllc (default)               */
+  int source;      /* :15   1 none, 2 gravity                                     */
+  double gamma;    /* :18                                                         */
+  double boxlen;   /* :17                                                         */
+  int device;
+} wb_dg1d_params;
+int wb_dg1d_create(wb_dg1d** h, const wb_dg1d_params* p);
+int wb_dg1d_destroy(wb_dg1d* h);
+/* gl_quadrature(chsi_quad, w_quad, nquad) of the root legendre.f90:77-128 */
+int wb_dg1d_quadrature(wb_dg1d* h, double* chsi_quad, double* w_quad);
+/* replaces compute_update_exact_delta(delta_u,u_eq,dudt)   dg_with_source.f90:1749-2031 (u_eq = nodal equilibrium) */
+int wb_dg1d_compute_update_exact_delta(wb_dg1d* h, const double* delta_u, const double* u_eq, double* dudt);
+/* replaces compute_max_speed(u,cmax)   dg_with_source.f90:1136-1152 (first node of every cell of a NODAL field) */
+int wb_dg1d_compute_max_speed(wb_dg1d* h, const double* u_nodes, double* cmax);
+/* replaces the main time loop with integrator 'RKi'   dg_with_source.f90:173-336 (:282-305): delta_u (modes) and
+ * uinit (nodal state used for the time step, = u_eq + reconstructed delta) are updated in place */
+int wb_dg1d_evolve(wb_dg1d* h, double* delta_u_inout, const double* u_eq, double* uinit_inout, double tend, int max_iter,
+                   int* iters_out, double* t_out, double* last_dt_out);
+
 #ifdef __cplusplus
 }
 #endif

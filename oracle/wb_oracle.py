@@ -323,3 +323,53 @@ def fv1d_evolve(p, u, w_eq, tend, max_iter=-1):
     lib().orc_fv1d_evolve(C.byref(p), _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t),
                           C.byref(dt))
     return u, it.value, t.value, dt.value
+
+
+# ---------------------------------------------------------------- 1D DG (dg_with_source.f90, root legendre.f90)
+class DG1DParams(C.Structure):
+    _fields_ = [("n", C.c_int), ("nx", C.c_int), ("riemann", C.c_int), ("source", C.c_int), ("ninit", C.c_int),
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("pert", C.c_double)]
+
+
+def dg1d_params(n=3, nx=128, riemann=2, source=2, ninit=8, gamma=F32(1.4), boxlen=1.0, pert=F32(1e-8)):
+    return DG1DParams(n, nx, riemann, source, ninit, gamma, boxlen, pert)
+
+
+def dg1d_quadrature(p):
+    x = np.zeros(p.n); w = np.zeros(p.n)
+    lib().orc_dg1d_quadrature(C.byref(p), _ptr(x), _ptr(w))
+    return x, w
+
+
+def dg1d_legendre(x, n):
+    f = lib().orc_dg1d_legendre; f.restype = C.c_double
+    v = C.c_double(x)
+    return f(C.byref(v), C.c_int(n))
+
+
+def dg1d_setup(p):
+    """Returns (uinit nodal IC, u_eq nodal equilibrium, delta_u projected perturbation)  program dg :33-171."""
+    shp = (p.nx, p.n, 3)
+    a = np.empty(shp); b = np.empty(shp); c = np.empty(shp)
+    lib().orc_dg1d_setup(C.byref(p), _ptr(a), _ptr(b), _ptr(c))
+    return a, b, c
+
+
+def dg1d_compute_update_exact_delta(p, delta_u, u_eq):
+    d = np.empty_like(delta_u)
+    lib().orc_dg1d_compute_update_exact_delta(C.byref(p), _ptr(delta_u), _ptr(u_eq), _ptr(d))
+    return d
+
+
+def dg1d_compute_max_speed(p, u_nodes):
+    c = C.c_double()
+    lib().orc_dg1d_compute_max_speed(C.byref(p), _ptr(u_nodes), C.byref(c))
+    return c.value
+
+
+def dg1d_evolve_rki(p, delta_u, u_eq, uinit, tend, max_iter=-1):
+    d = np.array(delta_u, copy=True); ui = np.array(uinit, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_dg1d_evolve_rki(C.byref(p), _ptr(d), _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it),
+                              C.byref(t), C.byref(dt))
+    return d, ui, it.value, t.value, dt.value

@@ -96,8 +96,26 @@ def fv1d():
     np.savez_compressed(os.path.join(HERE, "fv1d.npz"), **out)
 
 
+def dg1d():
+    out = {}
+    for tag, n, nx, riemann, source, ninit, pert, steps in (("default_hllc", 3, 128, 2, 2, 8, o.F32(1e-8), 4),
+                                                           ("llf_o2", 2, 64, 1, 2, 8, 1e-3, 4),
+                                                           ("hllc_o1", 1, 40, 2, 2, 8, 1e-2, 5),
+                                                           ("sod_nosource", 3, 50, 2, 1, 4, 0.0, 3),
+                                                           ("steady_hllc", 3, 32, 2, 2, 7, 0.0, 3)):
+        p = o.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, ninit=ninit, pert=pert)
+        ui, ueq, du = o.dg1d_setup(p)
+        out[f"{tag}_meta"] = np.array([n, nx, riemann, source, steps])
+        out[f"{tag}_du"] = du; out[f"{tag}_ueq"] = ueq; out[f"{tag}_ui"] = ui
+        out[f"{tag}_dudt"] = o.dg1d_compute_update_exact_delta(p, du, ueq)
+        du2, ui2, it, t, dt = o.dg1d_evolve_rki(p, du, ueq, ui, 1.0, steps)
+        out[f"{tag}_du2"] = du2; out[f"{tag}_ui2"] = ui2; out[f"{tag}_clock"] = np.array([it, t, dt])
+        assert np.all(np.isfinite(du2)), tag
+    np.savez_compressed(os.path.join(HERE, "dg1d.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d"]
+    which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d", "dg1d"]
     for w in which:
         globals()[w]()
         print("wrote", w)
