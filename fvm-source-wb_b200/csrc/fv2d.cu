@@ -4,10 +4,12 @@
 // i contiguous (x), r = local row + 1 (row 0 and row nyl+1 are the slab ghost rows).
 //
 // Kernels
-//   k_stage_ref<MODE,WB>   reference operation order (arith = 1, parity entry points)
-//   k_stage_fast<MODE>     fused RK-stage kernel: delta tile + halo staged in shared memory, each face
-//                          flux computed once, well-balanced source, RK axpy, and (stage 2) the
-//                          warp-shuffle max reduction for the next CFL time step.
+//   k_stage_ref<MODE,WB>   reference operation order (arith = 1, parity triage, plain compute_update)
+//   k_stage_march<MODE>    fused RK-stage kernel (production): warps march up strips of rows, each face flux
+//                          computed once (warp shuffles in x, register carry in y), well-balanced source, RK
+//                          axpy and (stage 2) the warp-shuffle max reduction for the next CFL time step.
+//   (Two earlier designs were measured and dropped: a shared-memory tiled kernel -- 2x slower, barrier and
+//    load-latency bound at 16 warps/SM -- and a two-cells-per-thread march -- same speed at 252 registers.)
 //   MODE 0: out = dudt      MODE 1: out = in + dt*dudt      MODE 2: out = .5*base + .5*in + .5*dt*dudt
 #include "common.cuh"
 #include "fv2d_math.cuh"
@@ -332,23 +334,7 @@ __global__ void __launch_bounds__(128) k_stage_ref(StageArgs A, Grid g, Phys P) 
   }
 }
 
-// ------------------------------------------------------------------------------------ fused fast stage
-// Tile TX x TY cells per CTA, one thread per cell.
-//   phase 1  delta = u - u_eq of the tile and its 4 halo strips -> shared memory
-//   phase 2  every thread evaluates its LEFT and BOTTOM face (2 states each, LLF) -> shared memory;
-//            TX+TY threads then do the tile's right-column / top-row faces in one mixed x/y pass
-//   phase 3  flux differences + well-balanced source + RK axpy (+ stage-2 max wave speed)
-// Face data in shared memory: 4 flux components + the equilibrium face pressure gm1*E_f (the only
-// non-zero entry of the equilibrium flux, velocities being zero in every reference equilibrium).
-template <int TX, int TY>
-struct FastSmem {
-  double d[4][TY + 2][TX + 2];
-  double F[5][TY][TX + 1];
-  double G[5][TY + 1][TX];
-  double red[(TX * TY) / 32];
-  double dt;
-};
-
+// ------------------------------------------------------------------------------------ fused stage: face flux helpers
 // One LLF face in (normal,tangential) form.  lo/hi = delta on the low/high side of the face,
 // (rf,Ef) = conservative equilibrium at the face.  Returns flux (mass, normal mom, tangential mom, energy)
 // and pf = gm1*Ef.
@@ -373,149 +359,27 @@ __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef
   return o;
 }
 
-template <int TX, int TY, int MODE>
-__global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) k_stage_fast(StageArgs A, Grid g, Phys P) {
-  if (MODE != 0) {
-    if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
-      if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0 && A.row_begin == 0)
-        carry_forward(A.ctrl, A.parity);
-      return;
-    }
-  }
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastSmem<TX, TY>& S = *reinterpret_cast<FastSmem<TX, TY>*>(smem_raw);
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * TX + tx;
-  const int i0 = blockIdx.x * TX, jl0 = A.row_begin + blockIdx.y * TY;
-  const int i = i0 + tx, jl = jl0 + ty;
-
-  if (MODE != 0 && tid == 0) {
-    double dt = step_dt(A.ctrl, A.parity, P);
-    S.dt = dt;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && A.row_begin == 0) bookkeeping<MODE>(A.ctrl, A.parity, dt);
-  }
-
-  // ---- phase 1: own cell
-  const int ic = min(i, g.nx - 1);
-  const int jc = min(jl, g.nyl - 1);            // clamp tile overhang (results discarded)
-  const size_t o = (size_t)(jc + 1) * g.pitch + ic;
-  const double u0 = A.in[o], u1 = A.in[g.plane + o], u2 = A.in[2 * g.plane + o], u3 = A.in[3 * g.plane + o];
-  const double re = A.eqz[o], Ee = A.eqz[g.plane + o];
-  S.d[0][ty + 1][tx + 1] = u0 - re;
-  S.d[1][ty + 1][tx + 1] = u1;
-  S.d[2][ty + 1][tx + 1] = u2;
-  S.d[3][ty + 1][tx + 1] = u3 - Ee;
-  // ---- phase 1b: halo strips (bottom, top, left, right)
-  if (tid < 2 * TX + 2 * TY) {
-    int hi, hj, sx, sy;   // cell (local) and smem slot
-    if (tid < TX)               { hi = i0 + tid;            hj = jl0 - 1;               sx = tid + 1;          sy = 0; }
-    else if (tid < 2 * TX)      { hi = i0 + tid - TX;       hj = jl0 + TY;              sx = tid - TX + 1;     sy = TY + 1; }
-    else if (tid < 2 * TX + TY) { hi = i0 - 1;              hj = jl0 + tid - 2 * TX;    sx = 0;                sy = tid - 2 * TX + 1; }
-    else                        { hi = i0 + TX;             hj = jl0 + tid - 2 * TX - TY; sx = TX + 1;         sy = tid - 2 * TX - TY + 1; }
-    hi = max(0, min(hi, g.nx - 1));
-    // valid local rows are -1..nyl (ghost rows) intersected with the global grid
-    int jmin = (g.j0 > 0) ? -1 : 0, jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
-    hj = max(jmin, min(hj, jmax));
-    size_t oh = (size_t)(hj + 1) * g.pitch + hi;
-    S.d[0][sy][sx] = A.in[oh] - A.eqz[oh];
-    S.d[1][sy][sx] = A.in[g.plane + oh];
-    S.d[2][sy][sx] = A.in[2 * g.plane + oh];
-    S.d[3][sy][sx] = A.in[3 * g.plane + oh] - A.eqz[g.plane + oh];
-  }
-  __syncthreads();
-
-  // ---- phase 2: left (x) and bottom (y) faces of the own cell
-  {
-    const double eyc = A.eyc[jc], exc = A.exc[ic];
-    const double ex = A.exf[ic] * eyc;         // exp(-a*xf(i)) * exp(-a*yc(j))
-    FaceFlux fx = face_llf(P, P.rho0 * ex, P.pe1 * ex,
-                           S.d[0][ty + 1][tx], S.d[1][ty + 1][tx], S.d[2][ty + 1][tx], S.d[3][ty + 1][tx],
-                           S.d[0][ty + 1][tx + 1], S.d[1][ty + 1][tx + 1], S.d[2][ty + 1][tx + 1], S.d[3][ty + 1][tx + 1]);
-    S.F[0][ty][tx] = fx.f0; S.F[1][ty][tx] = fx.fn; S.F[2][ty][tx] = fx.ft; S.F[3][ty][tx] = fx.f3; S.F[4][ty][tx] = fx.pf;
-    const double ey = exc * A.eyf[jc];
-    FaceFlux fy = face_llf(P, P.rho0 * ey, P.pe1 * ey,
-                           S.d[0][ty][tx + 1], S.d[2][ty][tx + 1], S.d[1][ty][tx + 1], S.d[3][ty][tx + 1],
-                           S.d[0][ty + 1][tx + 1], S.d[2][ty + 1][tx + 1], S.d[1][ty + 1][tx + 1], S.d[3][ty + 1][tx + 1]);
-    S.G[0][ty][tx] = fy.f0; S.G[1][ty][tx] = fy.ft; S.G[2][ty][tx] = fy.fn; S.G[3][ty][tx] = fy.f3; S.G[4][ty][tx] = fy.pf;
-  }
-  // ---- phase 2b: the tile's outer faces (right column: x faces; top row: y faces), one mixed pass
-  if (tid < TX + TY) {
-    const bool isx = tid < TY;
-    int cx, cy;          // smem coordinates (in the d tile) of the low-side cell
-    double e;
-    if (isx) {           // x-face at i0+TX, row tid
-      cx = TX; cy = tid + 1;
-      int jj = min(jl0 + tid, g.nyl - 1);
-      e = A.exf[min(i0 + TX, g.nx)] * A.eyc[jj];
-    } else {             // y-face at jl0+TY, column tid-TY
-      cx = tid - TY + 1; cy = TY;
-      int ii = min(i0 + tid - TY, g.nx - 1);
-      e = A.exc[ii] * A.eyf[min(jl0 + TY, g.nyl)];
-    }
-    const int hx = isx ? cx + 1 : cx, hy = isx ? cy : cy + 1;
-    const int vn = isx ? 1 : 2, vt = isx ? 2 : 1;
-    FaceFlux f = face_llf(P, P.rho0 * e, P.pe1 * e,
-                          S.d[0][cy][cx], S.d[vn][cy][cx], S.d[vt][cy][cx], S.d[3][cy][cx],
-                          S.d[0][hy][hx], S.d[vn][hy][hx], S.d[vt][hy][hx], S.d[3][hy][hx]);
-    if (isx) {
-      S.F[0][tid][TX] = f.f0; S.F[1][tid][TX] = f.fn; S.F[2][tid][TX] = f.ft; S.F[3][tid][TX] = f.f3; S.F[4][tid][TX] = f.pf;
-    } else {
-      const int c = tid - TY;
-      S.G[0][TY][c] = f.f0; S.G[1][TY][c] = f.ft; S.G[2][TY][c] = f.fn; S.G[3][TY][c] = f.f3; S.G[4][TY][c] = f.pf;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: assemble dudt in the reference's order (benchmark_2d.f90:601-607) and update
-  const int jg = g.j0 + jl;
-  const bool inside = (i < g.nx) && (jl < A.row_end) && (jl < g.nyl);
-  const bool interior = inside && (i > 0) && (i < g.nx - 1) && (jg > 0) && (jg < g.ny - 1);
-  double d0, d1, d2, d3;
-  {
-    const double ax = S.F[4][ty][tx + 1] - S.F[4][ty][tx];   // F_eq(i+1)-F_eq(i)   (x-momentum entry)
-    const double ay = S.G[4][ty + 1][tx] - S.G[4][ty][tx];   // G_eq(j+1)-G_eq(j)   (y-momentum entry)
-    d0 = -((S.F[0][ty][tx + 1] - S.F[0][ty][tx]) * P.odx) - (S.G[0][ty + 1][tx] - S.G[0][ty][tx]) * P.ody;
-    d1 = -((S.F[1][ty][tx + 1] - S.F[1][ty][tx]) * P.odx) - (S.G[1][ty + 1][tx] - S.G[1][ty][tx]) * P.ody;
-    d2 = -((S.F[2][ty][tx + 1] - S.F[2][ty][tx]) * P.odx) - (S.G[2][ty + 1][tx] - S.G[2][ty][tx]) * P.ody;
-    d3 = -((S.F[3][ty][tx + 1] - S.F[3][ty][tx]) * P.odx) - (S.G[3][ty + 1][tx] - S.G[3][ty][tx]) * P.ody;
-    // + s - s_eq : s = (0,-rho,-rho,-rho*(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
-    d1 = (d1 - u0) + re;
-    d2 = (d2 - u0) + re;
-    d3 = d3 - (u1 + u2);
-    // + (F_eq(i+1)-F_eq(i))/dx + (G_eq(j+1)-G_eq(j))/dy
-    d1 = d1 + ax * P.odx;
-    d2 = d2 + ay * P.ody;
-    if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // dudt = 0 on the boundary lines :611-614
-  }
-  double n0, n1, n2, n3;
-  if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
-  if (MODE == 1) {
-    const double dt = S.dt;
-    n0 = fma(dt, d0, u0); n1 = fma(dt, d1, u1); n2 = fma(dt, d2, u2); n3 = fma(dt, d3, u3);
-  }
-  if (MODE == 2) {
-    const double hdt = 0.5 * S.dt;
-    n0 = fma(hdt, d0, 0.5 * (A.base[o] + u0));
-    n1 = fma(hdt, d1, 0.5 * (A.base[g.plane + o] + u1));
-    n2 = fma(hdt, d2, 0.5 * (A.base[2 * g.plane + o] + u2));
-    n3 = fma(hdt, d3, 0.5 * (A.base[3 * g.plane + o] + u3));
-  }
-  if (inside) {
-    A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
-  }
-  if (MODE == 2) {
-    double spd = inside ? fast::speed(P, n0, n1, n2, n3) : 0.0;
-    spd = warp_max(spd);
-    if ((tid & 31) == 0) S.red[tid >> 5] = spd;
-    __syncthreads();
-    if (tid < 32) {
-      double m = (tid < (TX * TY) / 32) ? S.red[tid] : 0.0;
-      m = warp_max(m);
-      if (tid == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], m);
-    }
-  }
+// Two LLF faces at once: the four states are evaluated in lock-step (eval_states<4>); same arithmetic as face_llf.
+struct FaceIn { double rf, Ef, lr, ln, lt, lE, hr, hn, ht, hE; };
+__device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const FaceIn& b, FaceFlux& oa, FaceFlux& ob) {
+  const double rho[4] = {a.rf + a.lr, a.rf + a.hr, b.rf + b.lr, b.rf + b.hr};
+  const double E[4] = {a.Ef + a.lE, a.Ef + a.hE, b.Ef + b.lE, b.Ef + b.hE};
+  const double mn[4] = {a.ln, a.hn, b.ln, b.hn};
+  const double mt[4] = {a.lt, a.ht, b.lt, b.ht};
+  fast::Eval ev[4];
+  fast::eval_states<4>(P, rho, mn, mt, E, ev);
+  const double hca = 0.5 * fmax(ev[0].spd, ev[1].spd), hcb = 0.5 * fmax(ev[2].spd, ev[3].spd);
+  oa.f0 = 0.5 * (ev[1].f0 + ev[0].f0) + hca * (rho[0] - rho[1]);
+  ob.f0 = 0.5 * (ev[3].f0 + ev[2].f0) + hcb * (rho[2] - rho[3]);
+  oa.fn = 0.5 * (ev[1].fn + ev[0].fn) + hca * (a.ln - a.hn);
+  ob.fn = 0.5 * (ev[3].fn + ev[2].fn) + hcb * (b.ln - b.hn);
+  oa.ft = 0.5 * (ev[1].ft + ev[0].ft) + hca * (a.lt - a.ht);
+  ob.ft = 0.5 * (ev[3].ft + ev[2].ft) + hcb * (b.lt - b.ht);
+  oa.f3 = 0.5 * (ev[1].f3 + ev[0].f3) + hca * (E[0] - E[1]);
+  ob.f3 = 0.5 * (ev[3].f3 + ev[2].f3) + hcb * (E[2] - E[3]);
+  oa.pf = P.gm1 * a.Ef;
+  ob.pf = P.gm1 * b.Ef;
 }
-
 
 // ------------------------------------------------------------------------------------ fused marching stage
 // The production RK-stage kernel.  No shared memory, no block barriers:
@@ -550,6 +414,36 @@ __device__ __forceinline__ Cell make_cell(const Raw& r) {
   return c;
 }
 
+// dudt of one cell from its four face fluxes, in the reference's order (benchmark_2d.f90:601-607)
+template <int MODE>
+__device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const FaceFlux& Fl, const FaceFlux& Fr, const FaceFlux& Gb,
+                                            const FaceFlux& Gt, bool interior, double dt, double b0, double b1, double b2,
+                                            double b3, double& n0, double& n1, double& n2, double& n3) {
+  double d0 = -((Fr.f0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
+  double d1 = -((Fr.fn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
+  double d2 = -((Fr.ft - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
+  double d3 = -((Fr.f3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
+  d1 = (d1 - c.u0) + c.re;
+  d2 = (d2 - c.u0) + c.re;
+  d3 = d3 - (c.d1 + c.d2);
+  d1 = d1 + (Fr.pf - Fl.pf) * P.odx;
+  d2 = d2 + (Gt.pf - Gb.pf) * P.ody;
+  if (MODE == 0) {
+    if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }
+    n0 = d0; n1 = d1; n2 = d2; n3 = d3;
+  }
+  // frozen boundary lines (:611-614): dudt = 0 there; d is finite (clamped loads), so a zero time step is exact
+  if (MODE == 1) {
+    const double dtm = interior ? dt : 0.0;
+    n0 = fma(dtm, d0, c.u0); n1 = fma(dtm, d1, c.d1); n2 = fma(dtm, d2, c.d2); n3 = fma(dtm, d3, c.u3);
+  }
+  if (MODE == 2) {
+    const double hdt = interior ? 0.5 * dt : 0.0;
+    n0 = fma(hdt, d0, 0.5 * (b0 + c.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + c.d1));
+    n2 = fma(hdt, d2, 0.5 * (b2 + c.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + c.u3));
+  }
+}
+
 // Per-thread constants of the marching loop.
 struct MarchCtx {
   int lane, ic, ih, jmin, jmax;
@@ -576,49 +470,39 @@ __device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, con
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (MODE == 2) { b0 = A.base[o]; b1 = A.base[g.plane + o]; b2 = A.base[2 * g.plane + o]; b3 = A.base[3 * g.plane + o]; }
 
-  // ---- top y-face (j+1): low side = this cell, high side = the cell above; normal = y
-  const double ey = c.exc_i * A.eyf[min(j + 1, g.nyl)];
-  Gt = face_llf(P, P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3);
-  // ---- left x-face (i): low side = left neighbour (lane-1 / halo), high side = this cell; normal = x
+  // ---- left neighbour's delta (lane-1 / halo), then the top y-face (j+1; normal = y) and the left x-face (i;
+  //      normal = x) together: their four states are evaluated in lock-step
   double l0 = __shfl_up_sync(0xffffffffu, cur.d0, 1), l1 = __shfl_up_sync(0xffffffffu, cur.d1, 1);
   double l2 = __shfl_up_sync(0xffffffffu, cur.d2, 1), l3 = __shfl_up_sync(0xffffffffu, cur.d3, 1);
   if (c.lane == 0) { l0 = hal.d0; l1 = hal.d1; l2 = hal.d2; l3 = hal.d3; }
+  const double ey = c.exc_i * A.eyf[min(j + 1, g.nyl)];
   const double ex = c.exf_i * A.eyc[min(j, g.nyl - 1)];
-  const FaceFlux Fl = face_llf(P, P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3);
+  FaceFlux Fl;
+  {
+    const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3};
+    const FaceIn fx = {P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3};
+    faces_llf2(P, fy, fx, Gt, Fl);
+  }
   // ---- right x-face (i+1) from lane+1
   const double r0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1), rn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
   const double rt = __shfl_down_sync(0xffffffffu, Fl.ft, 1), r3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
   const double rp = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
 
-  // ---- dudt in the reference's order (benchmark_2d.f90:601-607); x-mom: F=fn, G=ft; y-mom: F=ft, G=fn
+  // ---- dudt in the reference's order (benchmark_2d.f90:601-607), RK axpy
   const int jg = g.j0 + j;
   const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
-  double d0 = -((r0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
-  double d1 = -((rn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
-  double d2 = -((rt - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
-  double d3 = -((r3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
-  d1 = (d1 - cur.u0) + cur.re;           // + s - s_eq,  s = (0,-rho,-rho,-rho(vx+vy)), s_eq = (0,-rho_e,-rho_e,-0)
-  d2 = (d2 - cur.u0) + cur.re;
-  d3 = d3 - (cur.d1 + cur.d2);
-  d1 = d1 + (rp - Fl.pf) * P.odx;        // + (F_eq(i+1)-F_eq(i))/dx
-  d2 = d2 + (Gt.pf - Gb.pf) * P.ody;     // + (G_eq(j+1)-G_eq(j))/dy
-  if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }   // frozen boundary lines :611-614
+  FaceFlux Fr;
+  Fr.f0 = r0; Fr.fn = rn; Fr.ft = rt; Fr.f3 = r3; Fr.pf = rp;
   double n0, n1, n2, n3;
-  if (MODE == 0) { n0 = d0; n1 = d1; n2 = d2; n3 = d3; }
-  if (MODE == 1) { n0 = fma(c.dt, d0, cur.u0); n1 = fma(c.dt, d1, cur.d1); n2 = fma(c.dt, d2, cur.d2); n3 = fma(c.dt, d3, cur.u3); }
-  if (MODE == 2) {
-    const double hdt = 0.5 * c.dt;
-    n0 = fma(hdt, d0, 0.5 * (b0 + cur.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + cur.d1));
-    n2 = fma(hdt, d2, 0.5 * (b2 + cur.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + cur.u3));
-  }
+  cell_update<MODE>(P, cur, Fl, Fr, Gb, Gt, interior, c.dt, b0, b1, b2, b3, n0, n1, n2, n3);
   if (c.writer) {
     A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
     if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, MARCH_MIN_BLOCKS) k_stage_march(StageArgs A, Grid g, Phys P, int R) {
+template <int MODE, int MB>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs A, Grid g, Phys P, int R) {
   MarchCtx c;
   c.dt = 0.0;
   if (MODE != 0) {
@@ -673,6 +557,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MARCH_MIN_BLOCKS) k_stage_ma
   }
 }
 
+
 }}  // namespace wb::fv2d
 
 // ============================================================================================ host side
@@ -697,13 +582,10 @@ struct wb_fv2d {
   cudaStream_t comm_stream = nullptr;   // slab mode: boundary rows + NCCL ghost exchange run here, overlapped with the interior
   cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
   int overlap = 1;
-  int kernel_variant = 0;       // 0 = marching kernel (production), 1 = shared-memory tiled kernel (kept for A/B)
   int march_rows = 32;          // rows per strip of the marching kernel
 };
 
 namespace {
-
-constexpr int FTX = 32, FTY = 8;
 
 int fill_phys(const wb_fv2d_params& p, Phys& P) {
   P.gamma = p.gamma;
@@ -791,15 +673,11 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
   A.row_begin = row_begin; A.row_end = row_end;
-  if (use_fast(h) && wb_scheme && h->kernel_variant == 0) {
+  if (use_fast(h) && wb_scheme) {
     const int R = h->march_rows;
     const int ncols = (h->g.nx + MARCH_OUT - 1) / MARCH_OUT;
     dim3 b(MARCH_WARPS * 32), gr((ncols + MARCH_WARPS - 1) / MARCH_WARPS, (A.row_end - A.row_begin + R - 1) / R);
-    k_stage_march<MODE><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
-  } else if (use_fast(h) && wb_scheme) {
-    dim3 b(FTX, FTY), gr((h->g.nx + FTX - 1) / FTX, (row_end - row_begin + FTY - 1) / FTY);
-    size_t smem = sizeof(FastSmem<FTX, FTY>);
-    k_stage_fast<FTX, FTY, MODE><<<gr, b, smem, stream>>>(A, h->g, h->phys);
+    k_stage_march<MODE, MARCH_MIN_BLOCKS><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
   } else {
     dim3 b(128), gr((h->g.nx + 127) / 128, row_end - row_begin);
     if (wb_scheme) k_stage_ref<MODE, true><<<gr, b, 0, stream>>>(A, h->g, h->phys);
@@ -872,7 +750,6 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   h->prm = *p;
   h->dev = dev;
   if (const char* e = getenv("WB_FV2D_OVERLAP")) h->overlap = atoi(e);
-  if (const char* e = getenv("WB_FV2D_KERNEL")) h->kernel_variant = atoi(e);
   if (const char* e = getenv("WB_FV2D_MARCH_ROWS")) h->march_rows = std::max(1, atoi(e));
   fill_phys(*p, h->phys);
   Grid& g = h->g;
@@ -882,7 +759,6 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   g.nyl = j1 - g.j0;
   g.pitch = (p->nx + 15) / 16 * 16;     // 128-byte aligned rows
   g.plane = (size_t)(g.nyl + 2) * g.pitch;
-  int st = WB_OK;
   auto fail = [&](int s) { wb_fv2d_destroy(h); return s; };
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(WB_ERR_CUDA); }
   h->own_stream = true;
@@ -924,15 +800,7 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
     }
     h->exf = h->tab; h->exc = h->tab + nxf; h->eyf = h->tab + nxf + nxc; h->eyc = h->tab + nxf + nxc + nyf;
   }
-  {
-    auto k1 = k_stage_fast<FTX, FTY, 0>; auto k2 = k_stage_fast<FTX, FTY, 1>; auto k3 = k_stage_fast<FTX, FTY, 2>;
-    int sm = (int)sizeof(FastSmem<FTX, FTY>);
-    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
-  (void)st;
   *out = h;
   return WB_OK;
 }
@@ -1013,7 +881,6 @@ int wb_fv2d_get_initial_conditions(wb_fv2d* h, int ninit, double eta, double* u_
   dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
   k_init<<<gr, b, 0, h->stream>>>(scratch_u, scratch_w, h->g, h->phys, ninit, eta, 1, 1);
   wb::g_launches.fetch_add(1);
-  int st = WB_OK;
   if (cudaGetLastError() != cudaSuccess) { set_error("k_init launch failed"); st = WB_ERR_CUDA; }
   if (st == WB_OK && u_out) st = d2h_state(h, scratch_u, u_out);
   if (st == WB_OK && w_eq_out) st = d2h_state(h, scratch_w, w_eq_out);

@@ -134,6 +134,60 @@ __device__ __forceinline__ Eval eval_state(const Phys& P, double rho, double mn,
   o.f3 = vn * (E + p);
   return o;
 }
+// The same evaluation for N independent states in lock-step: every sub-step is issued for all N states before the
+// next one, so the instruction stream carries N independent dependency chains (the kernel is bound by FP64 latency,
+// not by FP64 throughput, when the chains are evaluated one after the other).  Bit-identical to eval_state.
+template <int N>
+__device__ __forceinline__ void eval_states(const Phys& P, const double (&rho)[N], const double (&mn)[N], const double (&mt)[N],
+                                            const double (&E)[N], Eval (&o)[N]) {
+  double r[N], y[N], e[N], t[N], vn[N], vt[N], q[N], p[N], c2[N], cs[N], vm[N], h[N], w[N], qa[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(rho[k]));
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] = fma(-rho[k], y[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(e[k], e[k], e[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = fma(y[k], t[k], y[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) { vn[k] = mn[k] * r[k]; vt[k] = mt[k] * r[k]; }
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(vt[k], vt[k], vn[k] * vn[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = P.gm1 * fma(-0.5 * rho[k], q[k], E[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double pm = fmax(p[k], 1e-10);
+    const double rm = (rho[k] >= 1e-10) ? r[k] : 1e10;
+    c2[k] = (P.gamma * pm) * rm;
+    qa[k] = q[k] + 1e-300;
+  }
+  // two square roots per state, all 2N in lock-step (sqrt_pos)
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(c2[k]));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(w[k]) : "d"(qa[k]));
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) { t[k] = c2[k] * y[k]; e[k] = qa[k] * w[k]; }
+#pragma unroll
+  for (int k = 0; k < N; ++k) { h[k] = fma(-t[k], y[k], 1.0); w[k] = fma(-e[k], w[k], 1.0); }
+#pragma unroll
+  for (int k = 0; k < N; ++k) { y[k] = fma(0.375, h[k], 0.5); vm[k] = fma(0.375, w[k], 0.5); }
+#pragma unroll
+  for (int k = 0; k < N; ++k) { y[k] = y[k] * h[k]; vm[k] = vm[k] * w[k]; }
+#pragma unroll
+  for (int k = 0; k < N; ++k) { cs[k] = fma(t[k], y[k], t[k]); vm[k] = fma(e[k], vm[k], e[k]); }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    o[k].spd = vm[k] + cs[k];
+    o[k].f0 = mn[k];
+    o[k].fn = fma(vn[k], mn[k], p[k]);
+    o[k].ft = vn[k] * mt[k];
+    o[k].f3 = vn[k] * (E[k] + p[k]);
+  }
+}
+
 // max wave speed of a state (stage-2 CFL reduction)
 __device__ __forceinline__ double speed(const Phys& P, double rho, double mx, double my, double E) {
   double r = rcp(rho);
