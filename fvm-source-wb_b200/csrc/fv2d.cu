@@ -881,6 +881,7 @@ int wb_fv2d_get_initial_conditions(wb_fv2d* h, int ninit, double eta, double* u_
   dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
   k_init<<<gr, b, 0, h->stream>>>(scratch_u, scratch_w, h->g, h->phys, ninit, eta, 1, 1);
   wb::g_launches.fetch_add(1);
+  int st = WB_OK;
   if (cudaGetLastError() != cudaSuccess) { set_error("k_init launch failed"); st = WB_ERR_CUDA; }
   if (st == WB_OK && u_out) st = d2h_state(h, scratch_u, u_out);
   if (st == WB_OK && w_eq_out) st = d2h_state(h, scratch_w, w_eq_out);
