@@ -729,6 +729,8 @@ __global__ void k_dg_ctrl_init(DgCtrl* ctrl, double tend, int max_iter, int rese
 
 }}  // namespace wb::dg
 
+#include "dg2d_fast.cuh"
+
 // ============================================================================================ host side
 using namespace wb;
 using namespace wb::dg;
@@ -752,6 +754,8 @@ struct wb_dg2d {
   int nparts = 0;
   bool resident = false;
   bool have_xy = false;
+  FastBasis FB;
+  int arith = 0;               // 0 = fused/sum-factorised stage kernel, 1 = reference operation order
 };
 
 namespace {
@@ -873,8 +877,53 @@ int dg_axpy(wb_dg2d* h, int na, double* out, const double* A0, double c0, const 
   return WB_OK;
 }
 
+// one fused launch: out = limiter(c0*A0 + c1*A1 + cd*dt*L(in)) [+ the optional second combination]
+int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, double c0, const double* A1, double c1, double cd,
+                  double* out2 = nullptr, const double* B0 = nullptr, double k0 = 0, const double* B1 = nullptr, double k1 = 0,
+                  double k2 = 0, double k3 = 0, double ke = 0) {
+  StageCoef C;
+  C.A0 = A0; C.A1 = A1; C.c0 = c0; C.c1 = c1; C.cd = cd; C.na = A1 ? 2 : 1;
+  C.out2 = out2; C.B0 = B0; C.B1 = B1; C.k0 = k0; C.k1 = k1; C.k2 = k2; C.k3 = k3; C.ke = ke;
+  const int onp = (h->prm.limiter_id == 1 && h->g.m > 1) ? 1 : 0;
+  dim3 b(64), gr = elem_grid(h, 64);
+  DISPATCH_M(h, k_dg_stage_fast<MM><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+                                                           h->phys, h->FB, h->ctrl, onp));
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+// the fused flow covers element-local limiters only ('ONP' or none); neighbour-reading limiters use the unfused kernels
+bool dg_use_fused(const wb_dg2d* h) { return h->arith == 0 && (h->prm.limiter_id <= 1); }
+
+int dg_step_fused(wb_dg2d* h) {
+  double *&du = h->du, *&A = h->A, *Bf = h->Bf, *C = h->C;
+  WB_CHECK(dg_max_speed(h, du, 1));
+  const int solver = h->prm.solver_id;
+  if (solver == 3) {                          // 'EQL' :672-681
+    WB_CHECK(dg_stage_fast(h, du, A, du, 1.0, nullptr, 0, 1.0));
+    WB_CHECK(dg_stage_fast(h, A, Bf, du, 0.5, A, 0.5, 0.5));
+    std::swap(h->du, h->Bf);
+  } else if (solver == 1 || solver == 2) {    // SSPRK(5,4) :683-710; 5 launches, L(w3) evaluated once
+    WB_CHECK(dg_stage_fast(h, du, A, du, 1.0, nullptr, 0, F32(0.391752226571890)));                                   // w1 -> A
+    WB_CHECK(dg_stage_fast(h, A, Bf, du, F32(0.444370493651235), A, F32(0.555629506348765), F32(0.368410593050371))); // w2 -> Bf
+    WB_CHECK(dg_stage_fast(h, Bf, A, du, F32(0.620101851488403), Bf, F32(0.379898148511597), F32(0.251891774271694))); // w3 -> A
+    WB_CHECK(dg_stage_fast(h, A, C, du, F32(0.178079954393132), A, F32(0.821920045606868), F32(0.544974750228521),    // w4 -> C
+                           Bf, du, F32(0.00683325884039), Bf, F32(0.51723167208978), F32(0.12759831133288),           // w5 -> Bf
+                           F32(0.34833675773694), F32(0.08460416338212)));
+    WB_CHECK(dg_stage_fast(h, C, A, Bf, 1.0, nullptr, 0, F32(0.22600748319395)));                                     // new delta_u -> A
+    std::swap(h->du, h->A);
+  } else {                                    // 'DEB' :737-747
+    WB_CHECK(dg_stage_fast(h, du, A, du, 1.0, nullptr, 0, 1.0));
+    std::swap(h->du, h->A);
+  }
+  k_dg_advance<<<1, 1, 0, h->stream>>>(h->ctrl);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
 // one time step of evolve (:666-757)
 int dg_step(wb_dg2d* h) {
+  if (dg_use_fused(h)) return dg_step_fused(h);
   double *du = h->du, *A = h->A, *Bf = h->Bf, *C = h->C, *D = h->D;
   WB_CHECK(dg_max_speed(h, du, 1));
   const int solver = h->prm.solver_id;
@@ -936,6 +985,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 4, "limiter_id must be 0..4 (none, ONP, HIO, 1OR, LOW)");
   WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
+  WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fused) or 1 (reference order)");
   int dev = 0;
   WB_CHECK(select_device(p->device, &dev));
   wb_dg2d* h = new wb_dg2d;
@@ -945,6 +995,18 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   g.nx = p->nx; g.ny = p->ny; g.m = p->mx; g.nm = p->mx * p->my; g.ne = (size_t)p->nx * p->ny;
   h->nfield = (size_t)4 * g.nm * g.ne;
   h->B = make_basis(p->mx);
+  {
+    std::memset(&h->FB, 0, sizeof(h->FB));
+    const Basis& B0 = h->B;
+    for (int q = 0; q < MAXM; ++q)
+      for (int n = 0; n < MAXM; ++n) {
+        h->FB.P[q][n] = B0.P[q][n]; h->FB.Pw[q][n] = B0.P[q][n] * B0.wq[q]; h->FB.dPw[q][n] = B0.dP[q][n] * B0.wq[q];
+        h->FB.Pg[q][n] = B0.Pg[q][n];
+      }
+    for (int n = 0; n < MAXM; ++n) { h->FB.Em[n] = B0.Em[n]; h->FB.Ep[n] = B0.Ep[n]; }
+    h->FB.gll = B0.gll;
+  }
+  h->arith = p->arith;
   DgPhys& P = h->phys;
   P.gamma = p->gamma; P.gm1a = p->gamma - (double)1.0f; P.gm1b = p->gamma - (double)1.f;
   P.dx = p->boxlen_x / (double)p->nx;

@@ -1,0 +1,397 @@
+// Fused DG 2D RK-stage kernel ("arith 0"): compute_update + RK combination + element-local positivity limiter
+// ('ONP') in ONE launch per stage.  Same formulas as the reference-order kernels of dg2d.cu, but
+//   * every tensor-product contraction is sum-factorised (2 x M^3 instead of M^4 multiply-adds per variable),
+//     with the quadrature weights folded into the basis tables (Pw = P*w, dPw = P'*w);
+//   * divisions / square roots use the Newton-refined MUFU seeds of the FV kernels, products are fused (FMA);
+//   * dudt never touches memory: the stage output  c0*A0 + c1*A1 + c2*A2 + c3*A3 + cd*dt*L(in)  is formed in
+//     registers, limited, and written once.
+// Results differ from the reference order by a few ulp per operation (parity bar 1e-12, tests/test_dg2d_gpu.py).
+// Included by dg2d.cu (uses its DgGrid / DgPhys / DgCtrl / Basis definitions).
+#pragma once
+
+namespace wb { namespace dg {
+
+struct FastBasis {
+  double P[MAXM][MAXM];     // P[q][n]
+  double Pw[MAXM][MAXM];    // P[q][n] * w[q]
+  double dPw[MAXM][MAXM];   // P'[q][n] * w[q]
+  double Em[MAXM], Ep[MAXM];
+  double Pg[MAXM][MAXM];    // legendre(x_gll(r), n)
+  int gll;
+};
+
+struct StageCoef {          // out = limiter( c0*A0 + c1*A1 + cd*dt*L(in) )
+  const double *A0, *A1;
+  double c0, c1, cd;
+  int na;                   // number of A terms (1 or 2)
+  // optional second result of the same launch (SSPRK(5,4): w5 needs L(w3) again, :700-704):
+  //   out2 = k0*B0 + k1*B1 + k2*in + k3*out + ke*dt*L(in)
+  double* out2;
+  const double *B0, *B1;
+  double k0, k1, k2, k3, ke;
+};
+
+namespace fastm {
+__device__ __forceinline__ double rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+__device__ __forceinline__ double sqrt_pos(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y;
+  double h = fma(-t, y, 1.0);
+  double p = fma(0.375, h, 0.5);
+  p = p * h;
+  return fma(t, p, t);
+}
+// primitive variables with the reference's density floor (2d/benchmark_2d_dg.f90:891-902)
+struct Prim { double w0, vx, vy, p, r; };
+__device__ __forceinline__ Prim prim(const DgPhys& P, double rho, double mx, double my, double E) {
+  Prim w;
+  w.w0 = fmax(rho, (double)10e-10f);
+  w.r = rcp(w.w0);
+  w.vx = mx * w.r;
+  w.vy = my * w.r;
+  w.p = P.gm1a * fma(-0.5 * w.w0, fma(w.vy, w.vy, w.vx * w.vx), E);
+  return w;
+}
+// local Lax-Friedrichs at one face point (compute_llflux :968-988 with compute_flux_int :946-965), DIR 1 = x, 2 = y
+template <int DIR>
+__device__ __forceinline__ void llf(const DgPhys& P, const double ul[4], const double ur[4], double nf[4]) {
+  if (P.flux_id != 1) { nf[0] = nf[1] = nf[2] = nf[3] = 0.0; return; }
+  const Prim a = prim(P, ul[0], ul[1], ul[2], ul[3]);
+  const Prim b = prim(P, ur[0], ur[1], ur[2], ur[3]);
+  // w0 >= 1e-9 > 1e-10, so max(w0,1d-10) = w0 and its reciprocal is already known
+  const double ca = sqrt_pos(P.gamma * fmax(a.p, 1e-10) * a.r), cb = sqrt_pos(P.gamma * fmax(b.p, 1e-10) * b.r);
+  const double vna = (DIR == 1) ? a.vx : a.vy, vnb = (DIR == 1) ? b.vx : b.vy;
+  const double hc = 0.5 * fmax(fabs(vnb + cb), fabs(vna + ca));
+  double fa[4], fb[4];
+  const double ta = a.w0 * a.vx * a.vy, tb = b.w0 * b.vx * b.vy;
+  if (DIR == 1) {
+    fa[0] = a.vx * ul[0]; fa[1] = fma(a.vx, ul[1], a.p); fa[2] = ta; fa[3] = a.vx * (ul[3] + a.p);
+    fb[0] = b.vx * ur[0]; fb[1] = fma(b.vx, ur[1], b.p); fb[2] = tb; fb[3] = b.vx * (ur[3] + b.p);
+  } else {
+    fa[0] = a.vy * ul[0]; fa[1] = ta; fa[2] = fma(a.vy, ul[2], a.p); fa[3] = a.vy * (ul[3] + a.p);
+    fb[0] = b.vy * ur[0]; fb[1] = tb; fb[2] = fma(b.vy, ur[2], b.p); fb[3] = b.vy * (ur[3] + b.p);
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) nf[v] = fma(hc, ul[v] - ur[v], 0.5 * (fb[v] + fa[v]));
+}
+}  // namespace fastm
+
+// trace of one variable on one side: SIDE 0 left, 1 right (points along y), 2 bottom, 3 top (points along x)
+template <int M, int SIDE>
+__device__ __forceinline__ void trace1(const double (&d)[M][M], const FastBasis& B, double (&out)[M]) {
+  double t[M];
+  if (SIDE < 2) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int i = 0; i < M; ++i) a = fma(d[i][j], SIDE == 0 ? B.Em[i] : B.Ep[i], a);
+      t[j] = a;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j) a = fma(d[i][j], SIDE == 2 ? B.Em[j] : B.Ep[j], a);
+      t[i] = a;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < M; ++q) {
+    double a = 0.0;
+#pragma unroll
+    for (int n = 0; n < M; ++n) a = fma(t[n], B.P[q][n], a);
+    out[q] = a;
+  }
+}
+template <int M>
+__device__ __forceinline__ void load_var(const double* __restrict__ u, const DgGrid& g, int v, size_t e, double (&d)[M][M]) {
+#pragma unroll
+  for (int j = 0; j < M; ++j)
+#pragma unroll
+    for (int i = 0; i < M; ++i) d[i][j] = PL(u, g, v, j * M + i)[e];
+}
+// value of one variable at the point (P_x-row px[], P_y-row py[])
+template <int M>
+__device__ __forceinline__ double eval_at(const double (&d)[M][M], const double* px, const double* py) {
+  double a = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) s = fma(d[i][j], py[j], s);
+    a = fma(s, px[i], a);
+  }
+  return a;
+}
+
+// 'ONP' positivity limiter (2d/limiters.f90:478-654) on an element held in registers
+template <int M>
+__device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis& B, double (&el)[4][M][M]) {
+  if (M == 1) return;
+  const double ua[4] = {el[0][0][0], el[1][0][0], el[2][0][0], el[3][0][0]};
+  double p_min = 1e300;
+  for (int q = 0; q < M; ++q)
+    for (int r = 0; r < B.gll; ++r) {
+      p_min = fmin(p_min, eval_at<M>(el[0], B.Pg[r], B.P[q]));     // "left" family: GLL in x, GL in y
+      p_min = fmin(p_min, eval_at<M>(el[0], B.P[q], B.Pg[r]));     // "right" family: GL in x, GLL in y
+    }
+  const double theta = fmin(fabs((ua[0] - P.eps) / (ua[0] - p_min)), 1.0);
+  if (theta != 1.0) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+        if (i != 0 || j != 0) el[0][i][j] = theta * el[0][i][j];
+  }
+  double t_min = 1.;
+  for (int fam = 0; fam < 2; ++fam)
+    for (int q = 0; q < M; ++q)
+      for (int r = 0; r < B.gll; ++r) {
+        const double* px = fam == 0 ? B.Pg[r] : B.P[q];
+        const double* py = fam == 0 ? B.P[q] : B.Pg[r];
+        double pt[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) pt[v] = eval_at<M>(el[v], px, py);
+        const fastm::Prim w = fastm::prim(P, pt[0], pt[1], pt[2], pt[3]);
+        double t = 1.;
+        if (!(w.p > P.eps)) t = solve_for_t(P, pt, ua);      // rare: exact reference routine
+        if (t_min >= t) t_min = t;
+      }
+  if (t_min != 1.0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+          if (i != 0 || j != 0) el[v][i][j] = t_min * el[v][i][j];
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
+                                                      const double* __restrict__ gx, const double* __restrict__ gy,
+                                                      const unsigned char* __restrict__ fz, DgGrid g, DgPhys P, FastBasis B,
+                                                      const DgCtrl* __restrict__ ctrl, int apply_onp) {
+  if (ctrl->skip) return;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.ny), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.ny);
+  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
+
+  // ---- own modes, nodal values (sum-factorised), face traces of the element and of its four neighbours
+  double U[4][M][M];                       // nodal values U[v][qx][qy]
+  double tl[M][4], tr[M][4], tb[M][4], tt[M][4];         // own traces [point][var]
+  double nl[M][4], nr[M][4], nb[M][4], nt[M][4];         // facing traces of the neighbours
+  double acc[4][M][M];                     // dudt accumulators [v][a][b]
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double d[M][M], t1[M];
+    load_var<M>(in, g, v, e, d);
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx) {
+      double a[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) s = fma(d[i][j], B.P[qx][i], s);
+        a[j] = s;
+      }
+#pragma unroll
+      for (int qy = 0; qy < M; ++qy) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
+        U[v][qx][qy] = s;
+      }
+    }
+    trace1<M, 0>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) tl[q][v] = t1[q];
+    trace1<M, 1>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) tr[q][v] = t1[q];
+    trace1<M, 2>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) tb[q][v] = t1[q];
+    trace1<M, 3>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) tt[q][v] = t1[q];
+    load_var<M>(in, g, v, eL, d);
+    trace1<M, 1>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) nl[q][v] = t1[q];
+    load_var<M>(in, g, v, eR, d);
+    trace1<M, 0>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) nr[q][v] = t1[q];
+    load_var<M>(in, g, v, eB, d);
+    trace1<M, 3>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) nb[q][v] = t1[q];
+    load_var<M>(in, g, v, eT, d);
+    trace1<M, 2>(d, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) nt[q][v] = t1[q];
+  }
+
+  // ---- volume terms: fluxes (and source) at the nodes, then vol1 + vol2 (+ source/2, see the final scaling)
+  {
+    double f1[4][M][M], f2[4][M][M];
+#pragma unroll
+    for (int qx = 0; qx < M; ++qx)
+#pragma unroll
+      for (int qy = 0; qy < M; ++qy) {
+        const fastm::Prim w = fastm::prim(P, U[0][qx][qy], U[1][qx][qy], U[2][qx][qy], U[3][qx][qy]);
+        const double t = w.w0 * w.vx * w.vy, Ep = U[3][qx][qy] + w.p;
+        f1[0][qx][qy] = w.w0 * w.vx; f1[1][qx][qy] = fma(w.vx, U[1][qx][qy], w.p); f1[2][qx][qy] = t; f1[3][qx][qy] = w.vx * Ep;
+        f2[0][qx][qy] = w.w0 * w.vy; f2[1][qx][qy] = t; f2[2][qx][qy] = fma(w.vy, U[2][qx][qy], w.p); f2[3][qx][qy] = w.vy * Ep;
+        // source at the node (get_source :1558-1576 / get_adv_source :1579-1596), kept in U (no longer needed)
+        if (P.source == 2) {
+          const double g1 = gx[(size_t)(qy * M + qx) * g.ne + e], g2 = gy[(size_t)(qy * M + qx) * g.ne + e];
+          U[0][qx][qy] = 0.0; U[1][qx][qy] = w.w0 * g1; U[2][qx][qy] = w.w0 * g2; U[3][qx][qy] = w.w0 * fma(w.vx, g1, w.vy * g2);
+        } else if (P.source == 3) {
+          U[0][qx][qy] = -U[0][qx][qy]; U[1][qx][qy] = 0.0; U[2][qx][qy] = 0.0; U[3][qx][qy] = 0.0;
+        }
+      }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      // vol1(a,b) = sum_qx sum_qy f1 dPw[qx][a] Pw[qy][b];  vol2(a,b) = sum f2 Pw[qx][a] dPw[qy][b]
+      double g1[M][M], g2[M][M];      // [a][qy]
+#pragma unroll
+      for (int a = 0; a < M; ++a)
+#pragma unroll
+        for (int qy = 0; qy < M; ++qy) {
+          double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int qx = 0; qx < M; ++qx) { s1 = fma(f1[v][qx][qy], B.dPw[qx][a], s1); s2 = fma(f2[v][qx][qy], B.Pw[qx][a], s2); }
+          g1[a][qy] = s1; g2[a][qy] = s2;
+        }
+#pragma unroll
+      for (int a = 0; a < M; ++a)
+#pragma unroll
+        for (int b = 0; b < M; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], fma(g2[a][qy], B.dPw[qy][b], s));
+          acc[v][a][b] = s;          // vol1 + vol2
+        }
+      if (P.source != 1) {
+        // source_vol(a,b) = sum S Pw[qx][a] Pw[qy][b]; enters dudt as /4 while the flux terms enter as oneoverdx/2
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+#pragma unroll
+          for (int qy = 0; qy < M; ++qy) {
+            double s = 0.0;
+#pragma unroll
+            for (int qx = 0; qx < M; ++qx) s = fma(U[v][qx][qy], B.Pw[qx][a], s);
+            g1[a][qy] = s;
+          }
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+#pragma unroll
+          for (int b = 0; b < M; ++b) {
+            double s = 0.0;
+#pragma unroll
+            for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], s);
+            U[v][a][b] = s;            // source_vol, reusing U
+          }
+      }
+    }
+  }
+
+  // ---- face fluxes (each face is evaluated by both adjacent elements) and edge integrals
+#pragma unroll
+  for (int q = 0; q < M; ++q) {
+    double F[4];
+    fastm::llf<1>(P, nl[q], tl[q], F);        // left face:  (left neighbour's right trace, own left trace)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) nl[q][v] = F[v];
+    fastm::llf<1>(P, tr[q], nr[q], F);        // right face
+#pragma unroll
+    for (int v = 0; v < 4; ++v) nr[q][v] = F[v];
+    fastm::llf<2>(P, nb[q], tb[q], F);        // bottom face
+#pragma unroll
+    for (int v = 0; v < 4; ++v) nb[q][v] = F[v];
+    fastm::llf<2>(P, tt[q], nt[q], F);        // top face
+#pragma unroll
+    for (int v = 0; v < 4; ++v) nt[q][v] = F[v];
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    // e1-e2 (a,b) = Ep[a]*sR[b] - Em[a]*sL[b] with s[b] = sum_q F[q] Pw[q][b]   (x faces: rule in y)
+    // e3-e4 (a,b) = Ep[b]*sT[a] - Em[b]*sB[a] with s[a] = sum_q G[q] Pw[q][a]   (y faces: rule in x)
+    double sR[M], sL[M], sT[M], sB[M];
+#pragma unroll
+    for (int n = 0; n < M; ++n) {
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        a1 = fma(nr[q][v], B.Pw[q][n], a1); a2 = fma(nl[q][v], B.Pw[q][n], a2);
+        a3 = fma(nt[q][v], B.Pw[q][n], a3); a4 = fma(nb[q][v], B.Pw[q][n], a4);
+      }
+      sR[n] = a1; sL[n] = a2; sT[n] = a3; sB[n] = a4;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        const double ex = fma(B.Ep[a], sR[b], -(B.Em[a] * sL[b]));
+        const double ey = fma(B.Ep[b], sT[a], -(B.Em[b] * sB[a]));
+        // dudt = (odx*vol1 + odx*vol2 - odx*(e1-e2) - odx*(e3-e4))/2 + source_vol/4      (:1449-1466)
+        double r = (0.5 * P.oneoverdx) * ((acc[v][a][b] - ex) - ey);
+        if (P.source != 1) r = fma(0.25, U[v][a][b], r);
+        if (fz && fz[(size_t)(b * M + a) * g.ne + e]) r = 0.0;
+        acc[v][a][b] = r;
+      }
+  }
+
+  // ---- RK combination (real(4) coefficients of :683-707), in registers
+  const double cdt = C.cd * ctrl->dt;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int b = 0; b < M; ++b)
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        const int m = b * M + a;
+        const double L = acc[v][a][b];
+        if (C.out2) {     // everything of out2 that does not depend on the limited `out` (U is dead by now)
+          double r2 = C.k0 * PL(C.B0, g, v, m)[e];
+          r2 = fma(C.k1, PL(C.B1, g, v, m)[e], r2);
+          r2 = fma(C.k2, PL(in, g, v, m)[e], r2);
+          U[v][a][b] = fma(C.ke * ctrl->dt, L, r2);
+        }
+        double r = (C.c0 == 1.0) ? PL(C.A0, g, v, m)[e] : C.c0 * PL(C.A0, g, v, m)[e];
+        if (C.na >= 2) r = fma(C.c1, PL(C.A1, g, v, m)[e], r);
+        acc[v][a][b] = fma(cdt, L, r);
+      }
+  if (apply_onp) positivity_fast<M>(P, B, acc);
+  if (C.out2) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int b = 0; b < M; ++b)
+#pragma unroll
+        for (int a = 0; a < M; ++a) PL(C.out2, g, v, b * M + a)[e] = fma(C.k3, acc[v][a][b], U[v][a][b]);
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int b = 0; b < M; ++b)
+#pragma unroll
+      for (int a = 0; a < M; ++a) PL(out, g, v, b * M + a)[e] = acc[v][a][b];
+}
+
+}}  // namespace wb::dg

@@ -184,7 +184,8 @@ class DG2DParams(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("mx", C.c_int), ("my", C.c_int), ("nvar", C.c_int), ("bc", C.c_int),
                 ("source", C.c_int), ("grad_phi_case", C.c_int), ("flux_id", C.c_int), ("limiter_id", C.c_int),
                 ("solver_id", C.c_int), ("ninit", C.c_int), ("gamma", C.c_double), ("boxlen_x", C.c_double),
-                ("boxlen_y", C.c_double), ("cfl", C.c_double), ("eps", C.c_double), ("M", C.c_double), ("device", C.c_int)]
+                ("boxlen_y", C.c_double), ("cfl", C.c_double), ("eps", C.c_double), ("M", C.c_double), ("device", C.c_int),
+                ("arith", C.c_int)]
 
 
 LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4}     # limiter_type (2d/benchmark_2d_dg.f90:1516-1555)
@@ -196,9 +197,9 @@ class DG2D:
     """2D modal DG (2d/benchmark_2d_dg.f90).  Arrays: u(nvar,nx,ny,mx,my) == numpy (my, mx, ny, nx, 4)."""
 
     def __init__(self, nx=8, ny=8, mx=2, my=2, bc=1, source=1, grad_phi_case=2, flux="llf1", limiter="ONP", solver="RK4",
-                 ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, device=-1):
+                 ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, device=-1, arith=0):
         self.params = DG2DParams(nx, ny, mx, my, 4, bc, source, grad_phi_case, FLUXES[flux], LIMITERS[limiter],
-                                 SOLVERS[solver], ninit, gamma, boxlen_x, boxlen_y, cfl, eps, M, device)
+                                 SOLVERS[solver], ninit, gamma, boxlen_x, boxlen_y, cfl, eps, M, device, arith)
         self._h = C.c_void_p()
         _check(lib().wb_dg2d_create(C.byref(self._h), C.byref(self.params)))
         self.shape = (my, mx, ny, nx, 4)

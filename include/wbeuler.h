@@ -130,6 +130,9 @@ typedef struct {
   int ninit;             /* :17   only used for special_boundary_conditions (ninit == 12)                */
   double gamma, boxlen_x, boxlen_y, cfl, eps, M;   /* :23-35                                             */
   int device;
+  int arith;             /* 0 = fused sum-factorised stage kernel (<= 1e-12 of the reference, default; used by evolve /
+                            step_async when the limiter is element-local: 'ONP' or none), 1 = reference operation order
+                            (bit-for-bit with the CPU restatement; also what the stateless entries always run)        */
 } wb_dg2d_params;
 
 int wb_dg2d_create(wb_dg2d** h, const wb_dg2d_params* p);

@@ -10,10 +10,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 lim = sys.argv[4] if len(sys.argv) > 4 else "ONP"
+arith = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 torch.cuda.init()
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
-    s = wbeuler.DG2D(nx=n, ny=n, mx=m, my=m, flux="llf1", limiter=lim, solver="RK4", ninit=1, device=0)
+    s = wbeuler.DG2D(nx=n, ny=n, mx=m, my=m, flux="llf1", limiter=lim, solver="RK4", ninit=1, device=0, arith=arith)
     s.set_stream(st.cuda_stream)
     xq, _ = s.quadrature()
     dx = 1.0 / n
@@ -31,6 +32,6 @@ with torch.cuda.stream(st):
         e0.record(st); s.step_async(steps); e1.record(st); e1.synchronize()
         ms = e0.elapsed_time(e1)
         rate = n * n * 5 * steps / (ms * 1e-3)
-        print(f"DG n={n} m={m} lim={lim} steps={steps} {ms:.2f} ms  {ms/steps:.2f} ms/step  {rate/1e6:.1f} Melem-stage/s  alg {rate*4*m*m*8*16/5/1e9:.0f} GB/s")
+        print(f"DG n={n} m={m} lim={lim} arith={arith} steps={steps} {ms:.2f} ms  {ms/steps:.2f} ms/step  {rate/1e6:.1f} Melem-stage/s  alg {rate*4*m*m*8*16/5/1e9:.0f} GB/s")
     print(s.sync())
     s.close()
