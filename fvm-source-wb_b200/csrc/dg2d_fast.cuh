@@ -177,6 +177,60 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
   }
 }
 
+// One face of the element: traces of the element (SIDE_OWN) and of the neighbour across it (SIDE_NB, modes at eN),
+// local Lax-Friedrichs at the M face points, and the edge integral accumulated into acc with its sign:
+//   x faces: -/+ E[a] * sum_q F[q] Pw[q][b]        y faces: -/+ E[b] * sum_q G[q] Pw[q][a]
+// FACE 0 left, 1 right, 2 bottom, 3 top.  Each face is evaluated by both adjacent elements (no inter-thread traffic).
+template <int M, int FACE>
+__device__ __forceinline__ void face_term(const double* __restrict__ in, const DgGrid& g, const DgPhys& P, const FastBasis& B,
+                                          const double (&d)[4][M][M], size_t eN, double (&acc)[4][M][M]) {
+  constexpr int SIDE_OWN = FACE;                                   // own trace on that side
+  constexpr int SIDE_NB = (FACE == 0) ? 1 : (FACE == 1) ? 0 : (FACE == 2) ? 3 : 2;   // neighbour's facing side
+  double to[M][4], tn[M][4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double t1[M], dn[M][M];
+    trace1<M, SIDE_OWN>(d[v], B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) to[q][v] = t1[q];
+    load_var<M>(in, g, v, eN, dn);
+    trace1<M, SIDE_NB>(dn, B, t1);
+#pragma unroll
+    for (int q = 0; q < M; ++q) tn[q][v] = t1[q];
+  }
+#pragma unroll
+  for (int q = 0; q < M; ++q) {
+    double F[4];
+    // low side first: (neighbour, own) on the left/bottom faces, (own, neighbour) on the right/top faces
+    if (FACE == 0) fastm::llf<1>(P, tn[q], to[q], F);
+    if (FACE == 1) fastm::llf<1>(P, to[q], tn[q], F);
+    if (FACE == 2) fastm::llf<2>(P, tn[q], to[q], F);
+    if (FACE == 3) fastm::llf<2>(P, to[q], tn[q], F);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) to[q][v] = F[v];
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double s[M];
+#pragma unroll
+    for (int n = 0; n < M; ++n) {
+      double a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < M; ++q) a1 = fma(to[q][v], B.Pw[q][n], a1);
+      s[n] = a1;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        if (FACE == 0) acc[v][a][b] = fma(B.Em[a], s[b], acc[v][a][b]);     // + e2
+        if (FACE == 1) acc[v][a][b] = fma(-B.Ep[a], s[b], acc[v][a][b]);    // - e1
+        if (FACE == 2) acc[v][a][b] = fma(B.Em[b], s[a], acc[v][a][b]);     // + e4
+        if (FACE == 3) acc[v][a][b] = fma(-B.Ep[b], s[a], acc[v][a][b]);    // - e3
+      }
+  }
+}
+
 template <int M>
 __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
                                                       const double* __restrict__ gx, const double* __restrict__ gy,
@@ -186,67 +240,47 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.ne) return;
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
-  const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.ny), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.ny);
-  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
-
-  // ---- own modes, nodal values (sum-factorised), face traces of the element and of its four neighbours
-  double U[4][M][M];                       // nodal values U[v][qx][qy]
-  double tl[M][4], tr[M][4], tb[M][4], tt[M][4];         // own traces [point][var]
-  double nl[M][4], nr[M][4], nb[M][4], nt[M][4];         // facing traces of the neighbours
-  double acc[4][M][M];                     // dudt accumulators [v][a][b]
+  double acc[4][M][M];                     // -(e1-e2) - (e3-e4) + vol1 + vol2, then dudt, then the stage result
+  double U[4][M][M];                       // nodal values -> nodal source -> out2 partial
+  {
+    double d[4][M][M];
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    double d[M][M], t1[M];
-    load_var<M>(in, g, v, e, d);
+    for (int v = 0; v < 4; ++v) {
+      load_var<M>(in, g, v, e, d[v]);
 #pragma unroll
-    for (int qx = 0; qx < M; ++qx) {
-      double a[M];
+      for (int a = 0; a < M; ++a)
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < M; ++i) s = fma(d[i][j], B.P[qx][i], s);
-        a[j] = s;
-      }
-#pragma unroll
-      for (int qy = 0; qy < M; ++qy) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
-        U[v][qx][qy] = s;
-      }
+        for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
     }
-    trace1<M, 0>(d, B, t1);
+    // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
+    face_term<M, 0>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.ny), acc);
+    face_term<M, 1>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.ny), acc);
+    face_term<M, 2>(in, g, P, B, d, (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, acc);
+    face_term<M, 3>(in, g, P, B, d, (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic, acc);
+    // ---- nodal values (sum-factorised)
 #pragma unroll
-    for (int q = 0; q < M; ++q) tl[q][v] = t1[q];
-    trace1<M, 1>(d, B, t1);
+    for (int v = 0; v < 4; ++v)
 #pragma unroll
-    for (int q = 0; q < M; ++q) tr[q][v] = t1[q];
-    trace1<M, 2>(d, B, t1);
+      for (int qx = 0; qx < M; ++qx) {
+        double a[M];
 #pragma unroll
-    for (int q = 0; q < M; ++q) tb[q][v] = t1[q];
-    trace1<M, 3>(d, B, t1);
+        for (int j = 0; j < M; ++j) {
+          double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < M; ++q) tt[q][v] = t1[q];
-    load_var<M>(in, g, v, eL, d);
-    trace1<M, 1>(d, B, t1);
+          for (int i = 0; i < M; ++i) s = fma(d[v][i][j], B.P[qx][i], s);
+          a[j] = s;
+        }
 #pragma unroll
-    for (int q = 0; q < M; ++q) nl[q][v] = t1[q];
-    load_var<M>(in, g, v, eR, d);
-    trace1<M, 0>(d, B, t1);
+        for (int qy = 0; qy < M; ++qy) {
+          double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < M; ++q) nr[q][v] = t1[q];
-    load_var<M>(in, g, v, eB, d);
-    trace1<M, 3>(d, B, t1);
-#pragma unroll
-    for (int q = 0; q < M; ++q) nb[q][v] = t1[q];
-    load_var<M>(in, g, v, eT, d);
-    trace1<M, 2>(d, B, t1);
-#pragma unroll
-    for (int q = 0; q < M; ++q) nt[q][v] = t1[q];
+          for (int j = 0; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
+          U[v][qx][qy] = s;
+        }
+      }
   }
 
-  // ---- volume terms: fluxes (and source) at the nodes, then vol1 + vol2 (+ source/2, see the final scaling)
+  // ---- volume terms: fluxes (and source) at the nodes, then vol1 + vol2 (+ (dx/2) source_vol, see the final scaling)
   {
     double f1[4][M][M], f2[4][M][M];
 #pragma unroll
@@ -265,6 +299,7 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
           U[0][qx][qy] = -U[0][qx][qy]; U[1][qx][qy] = 0.0; U[2][qx][qy] = 0.0; U[3][qx][qy] = 0.0;
         }
       }
+    const double src_scale = 0.5 * P.dx;     // source_vol/4 relative to the oneoverdx/2 scaling applied to acc below
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       // vol1(a,b) = sum_qx sum_qy f1 dPw[qx][a] Pw[qy][b];  vol2(a,b) = sum f2 Pw[qx][a] dPw[qy][b]
@@ -282,10 +317,10 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
       for (int a = 0; a < M; ++a)
 #pragma unroll
         for (int b = 0; b < M; ++b) {
-          double s = 0.0;
+          double s = acc[v][a][b];
 #pragma unroll
           for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], fma(g2[a][qy], B.dPw[qy][b], s));
-          acc[v][a][b] = s;          // vol1 + vol2
+          acc[v][a][b] = s;          // vol1 + vol2 - (e1-e2) - (e3-e4)
         }
       if (P.source != 1) {
         // source_vol(a,b) = sum S Pw[qx][a] Pw[qy][b]; enters dudt as /4 while the flux terms enter as oneoverdx/2
@@ -305,57 +340,22 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
             double s = 0.0;
 #pragma unroll
             for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], s);
-            U[v][a][b] = s;            // source_vol, reusing U
+            acc[v][a][b] = fma(src_scale, s, acc[v][a][b]);
           }
       }
     }
   }
-
-  // ---- face fluxes (each face is evaluated by both adjacent elements) and edge integrals
+  // ---- dudt = (odx*vol1 + odx*vol2 - odx*(e1-e2) - odx*(e3-e4))/2 + source_vol/4      (:1449-1466)
 #pragma unroll
-  for (int q = 0; q < M; ++q) {
-    double F[4];
-    fastm::llf<1>(P, nl[q], tl[q], F);        // left face:  (left neighbour's right trace, own left trace)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) nl[q][v] = F[v];
-    fastm::llf<1>(P, tr[q], nr[q], F);        // right face
-#pragma unroll
-    for (int v = 0; v < 4; ++v) nr[q][v] = F[v];
-    fastm::llf<2>(P, nb[q], tb[q], F);        // bottom face
-#pragma unroll
-    for (int v = 0; v < 4; ++v) nb[q][v] = F[v];
-    fastm::llf<2>(P, tt[q], nt[q], F);        // top face
-#pragma unroll
-    for (int v = 0; v < 4; ++v) nt[q][v] = F[v];
-  }
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    // e1-e2 (a,b) = Ep[a]*sR[b] - Em[a]*sL[b] with s[b] = sum_q F[q] Pw[q][b]   (x faces: rule in y)
-    // e3-e4 (a,b) = Ep[b]*sT[a] - Em[b]*sB[a] with s[a] = sum_q G[q] Pw[q][a]   (y faces: rule in x)
-    double sR[M], sL[M], sT[M], sB[M];
-#pragma unroll
-    for (int n = 0; n < M; ++n) {
-      double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
-#pragma unroll
-      for (int q = 0; q < M; ++q) {
-        a1 = fma(nr[q][v], B.Pw[q][n], a1); a2 = fma(nl[q][v], B.Pw[q][n], a2);
-        a3 = fma(nt[q][v], B.Pw[q][n], a3); a4 = fma(nb[q][v], B.Pw[q][n], a4);
-      }
-      sR[n] = a1; sL[n] = a2; sT[n] = a3; sB[n] = a4;
-    }
+  for (int v = 0; v < 4; ++v)
 #pragma unroll
     for (int a = 0; a < M; ++a)
 #pragma unroll
       for (int b = 0; b < M; ++b) {
-        const double ex = fma(B.Ep[a], sR[b], -(B.Em[a] * sL[b]));
-        const double ey = fma(B.Ep[b], sT[a], -(B.Em[b] * sB[a]));
-        // dudt = (odx*vol1 + odx*vol2 - odx*(e1-e2) - odx*(e3-e4))/2 + source_vol/4      (:1449-1466)
-        double r = (0.5 * P.oneoverdx) * ((acc[v][a][b] - ex) - ey);
-        if (P.source != 1) r = fma(0.25, U[v][a][b], r);
+        double r = (0.5 * P.oneoverdx) * acc[v][a][b];
         if (fz && fz[(size_t)(b * M + a) * g.ne + e]) r = 0.0;
         acc[v][a][b] = r;
       }
-  }
 
   // ---- RK combination (real(4) coefficients of :683-707), in registers
   const double cdt = C.cd * ctrl->dt;
