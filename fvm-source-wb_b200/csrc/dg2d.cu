@@ -259,6 +259,44 @@ __global__ void k_freeze_mask(const double* __restrict__ x, const double* __rest
   fz[k] = (sqrt(xd * xd + yd * yd) > 2.0) ? 1 : 0;
 }
 
+// get_coords :93-120 and get_initial_conditions :122-466 (cases 1 and 2) on the device, for grids whose nodal arrays
+// the host cannot reasonably hold.  Case 1 needs the global minimum of the nodal density (w(4) = minval(w(1)), :141):
+// pass 0 computes it (atomicMin on the bit pattern of a positive double), pass 1 writes the state.
+__device__ __forceinline__ void node_xy(const DgGrid& g, const DgPhys& P, const Basis& B, size_t e, int mode, double dy,
+                                         double& x, double& y) {
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const int ni = mode % g.m, nj = mode / g.m;
+  x = (double)((float)(ic + 1) - 0.5f) * P.dx + P.dx / 2.0 * B.xq[ni];
+  y = (double)((float)(jc + 1) - 0.5f) * dy + dy / 2.0 * B.xq[nj];
+}
+__global__ void k_dg_init(double* __restrict__ nodes, double* __restrict__ xy, DgGrid g, DgPhys P, Basis B, int ninit, double eta,
+                          double boxlen_x, double boxlen_y, unsigned long long* minbits, int pass) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int mode = blockIdx.y;
+  if (e >= g.ne) return;
+  const double dy = boxlen_y / (double)g.ny;
+  double x, y;
+  node_xy(g, P, B, e, mode, dy, x, y);
+  double w[4];
+  if (ninit == 1) {
+    const double ax = x - boxlen_x / 2., ay = y - boxlen_y / 2.;
+    w[0] = exp(-((ax * ax + ay * ay) * 10));
+    if (pass == 0) { atomicMin(minbits, (unsigned long long)__double_as_longlong(w[0])); return; }
+    w[1] = 1.0; w[2] = 1.0; w[3] = __longlong_as_double((long long)*minbits);
+  } else {
+    const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
+    const double ee = exp(-(rho_0 * gg / p_0) * (x + y));
+    const double bx = x - (double)0.3f, by = y - (double)0.3f;
+    w[0] = rho_0 * ee; w[1] = 0; w[2] = 0;
+    w[3] = p_0 * ee + eta * exp(-(100 * (rho_0 * gg / p_0) * (bx * bx + by * by)));
+  }
+  double u[4];
+  cons(P, w, u);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) PL(nodes, g, v, mode)[e] = u[v];
+  if (xy) { xy[(size_t)mode * g.ne + e] = x; xy[((size_t)g.nm + mode) * g.ne + e] = y; }
+}
+
 // ------------------------------------------------------------------------------------ compute_update :1137-1479
 template <int M>
 __global__ void __launch_bounds__(128) k_dg_update(const double* __restrict__ du, const double* __restrict__ gx,
@@ -770,7 +808,12 @@ namespace {
 
 inline dim3 elem_grid(const wb_dg2d* h, int block) { return dim3((unsigned)((h->g.ne + block - 1) / block)); }
 
+int dg_ensure(wb_dg2d* h, double** buf) {
+  if (!*buf) WB_CUDA(cudaMalloc(buf, sizeof(double) * h->nfield));
+  return WB_OK;
+}
 int dg_h2d_field(wb_dg2d* h, const double* host, double* soa) {
+  WB_CHECK(dg_ensure(h, &h->stage));
   WB_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * h->nfield, cudaMemcpyHostToDevice, h->stream));
   dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
   k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g);
@@ -778,6 +821,7 @@ int dg_h2d_field(wb_dg2d* h, const double* host, double* soa) {
   return WB_OK;
 }
 int dg_d2h_field(wb_dg2d* h, const double* soa, double* host) {
+  WB_CHECK(dg_ensure(h, &h->stage));
   dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
   k_dg_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g);
   WB_LAUNCH_CHECK();
@@ -816,6 +860,7 @@ int dg_update(wb_dg2d* h, const double* in, double* out, bool use_ctrl) {
 
 int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
   const DgCtrl* c = use_ctrl ? h->ctrl : nullptr;
+  if (h->prm.limiter_id == 2 || h->prm.limiter_id == 3) WB_CHECK(dg_ensure(h, &h->E));
   dim3 b(128), gr = elem_grid(h, 128);
   if (h->g.m == 1) return WB_OK;           // every limiter returns early for mx == my == 1
   switch (h->prm.limiter_id) {
@@ -924,6 +969,7 @@ int dg_step_fused(wb_dg2d* h) {
 // one time step of evolve (:666-757)
 int dg_step(wb_dg2d* h) {
   if (dg_use_fused(h)) return dg_step_fused(h);
+  WB_CHECK(dg_ensure(h, &h->D));
   double *du = h->du, *A = h->A, *Bf = h->Bf, *C = h->C, *D = h->D;
   WB_CHECK(dg_max_speed(h, du, 1));
   const int solver = h->prm.solver_id;
@@ -1024,22 +1070,28 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   const size_t fb = sizeof(double) * h->nfield, nb = sizeof(double) * g.nm * g.ne;
   h->nparts = (int)std::min<size_t>((g.ne + 255) / 256, 148 * 8);
   cudaError_t e = cudaSuccess;
-  double** bufs[] = {&h->du, &h->A, &h->Bf, &h->C, &h->D, &h->E, &h->stage};
+  // dudt (D), limiter scratch (E) and the host staging buffer are allocated on first use: the fused flow needs none of them
+  double** bufs[] = {&h->du, &h->A, &h->Bf, &h->C};
   for (double** b : bufs)
     if (e == cudaSuccess) e = cudaMalloc(b, fb);
-  if (e == cudaSuccess) e = cudaMalloc(&h->gx, nb);
-  if (e == cudaSuccess) e = cudaMalloc(&h->gy, nb);
-  if (e == cudaSuccess) e = cudaMalloc(&h->xy, 2 * nb);
-  if (e == cudaSuccess) e = cudaMalloc(&h->fz, (size_t)g.nm * g.ne);
+  const bool need_xy = (p->source == 2) || (p->ninit == 12);     // grad_phi / freeze mask need the node coordinates
+  if (need_xy) {
+    if (e == cudaSuccess) e = cudaMalloc(&h->gx, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&h->gy, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&h->xy, 2 * nb);
+    if (e == cudaSuccess) e = cudaMalloc(&h->fz, (size_t)g.nm * g.ne);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->ctrl, sizeof(DgCtrl));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(DgCtrl));
   if (e == cudaSuccess) e = cudaMalloc(&h->part1, sizeof(SpeedKey) * h->nparts);
   if (e == cudaSuccess) e = cudaMalloc(&h->part2, sizeof(double) * h->nparts);
   if (e != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
   cudaMemsetAsync(h->ctrl, 0, sizeof(DgCtrl), h->stream);
-  cudaMemsetAsync(h->gx, 0, nb, h->stream);
-  cudaMemsetAsync(h->gy, 0, nb, h->stream);
-  cudaMemsetAsync(h->fz, 0, (size_t)g.nm * g.ne, h->stream);
+  if (need_xy) {
+    cudaMemsetAsync(h->gx, 0, nb, h->stream);
+    cudaMemsetAsync(h->gy, 0, nb, h->stream);
+    cudaMemsetAsync(h->fz, 0, (size_t)g.nm * g.ne, h->stream);
+  }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
   *out = h;
   return WB_OK;
@@ -1099,6 +1151,7 @@ int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, con
   WB_CUDA(cudaSetDevice(h->dev));
   h->resident = false;
   WB_CHECK(dg_set_xy(h, x, y));
+  WB_CHECK(dg_ensure(h, &h->D));
   WB_CHECK(dg_h2d_field(h, modes, h->A));
   WB_CHECK(dg_update(h, h->A, h->D, false));
   return dg_d2h_field(h, h->D, dudt);
@@ -1146,6 +1199,38 @@ int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const dou
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_limiter(h, h->du, false));                                                         // :659
+  h->resident = true;
+  return WB_OK;
+}
+
+int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_REQUIRE(ninit == 1 || ninit == 2, "device-side initial conditions exist for ninit 1 (pulse) and 2 (hydrostatic + bump)");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t n = (size_t)h->g.nm * h->g.ne;
+  const bool need_xy = (h->phys.source == 2) || (h->phys.ninit == 12);
+  unsigned long long* minbits = reinterpret_cast<unsigned long long*>(h->part2);
+  WB_CUDA(cudaMemsetAsync(minbits, 0x7f, sizeof(unsigned long long), h->stream));
+  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
+  if (ninit == 1) {
+    k_dg_init<<<gr, b, 0, h->stream>>>(h->A, nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x, h->prm.boxlen_y, minbits, 0);
+    WB_LAUNCH_CHECK();
+  }
+  k_dg_init<<<gr, b, 0, h->stream>>>(h->A, need_xy ? h->xy : nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x,
+                                     h->prm.boxlen_y, minbits, 1);
+  WB_LAUNCH_CHECK();
+  if (need_xy) {
+    dim3 b2(256), g2((unsigned)((n + 255) / 256));
+    if (h->phys.source == 2) { k_grad_phi<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case); WB_LAUNCH_CHECK(); }
+    if (h->phys.ninit == 12) { k_freeze_mask<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->fz, n, h->prm.boxlen_x / 2., h->prm.boxlen_y / 2.); WB_LAUNCH_CHECK(); }
+  }
+  h->have_xy = true;
+  dim3 be(128), ge = elem_grid(h, 128);
+  DISPATCH_M(h, k_modes_from_nodes<MM><<<ge, be, 0, h->stream>>>(h->A, h->du, h->g, h->B));       // :644
+  WB_LAUNCH_CHECK();
+  k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
+  WB_LAUNCH_CHECK();
+  WB_CHECK(dg_limiter(h, h->du, false));                                                          // :659
   h->resident = true;
   return WB_OK;
 }

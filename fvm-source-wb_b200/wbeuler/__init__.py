@@ -273,6 +273,9 @@ class DG2D:
     def upload(self, u_nodes, x=None, y=None):
         _check(lib().wb_dg2d_upload(self._h, _ptr(u_nodes), _ptr(x) if x is not None else None, _ptr(y) if y is not None else None))
 
+    def init_device(self, ninit, eta=F32(0.1)):
+        _check(lib().wb_dg2d_init_device(self._h, C.c_int(ninit), C.c_double(eta)))
+
     def step_async(self, nsteps, tend=1e300):
         _check(lib().wb_dg2d_step_async(self._h, C.c_int(nsteps), C.c_double(tend)))
 

@@ -157,6 +157,9 @@ int wb_dg2d_evolve(wb_dg2d* h, double* u_nodes_inout, const double* x, const dou
                    int* iters_out, double* t_out, double* last_dt_out);
 /* resident path: upload nodal values (projected to modes and limited on the device, :644,:659), step, download nodes */
 int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const double* y);
+/* get_coords + get_initial_conditions (2d/benchmark_2d_dg.f90:93-120, :139-153; ninit 1 = pulse, 2 = hydrostatic + bump) on the
+ * device, then projection + initial limiter as in evolve -- for grids whose nodal arrays the host cannot hold */
+int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta);
 int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend);
 int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out);
 int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out);
