@@ -16,7 +16,7 @@ constexpr int NV = 3;
 constexpr int MAXN = 4;
 
 struct Basis1 { double xq[MAXN], wq[MAXN], P[MAXN][MAXN], dP[MAXN][MAXN], Em[MAXN], Ep[MAXN]; double s05, s6, s10; };
-struct P1d { int n, nx, riemann, source; double gamma, boxlen; };
+struct P1d { int n, nx, riemann, source, bc, use_limiter; double gamma, boxlen; };
 struct CtrlD { double t, dt, tend, cmax; int iter, max_iter, skip; };
 
 // ---- host: root legendre.f90 ------------------------------------------------------------------------------
@@ -198,6 +198,158 @@ __global__ void k_dg1_update(const double* __restrict__ du, const double* __rest
     }
 }
 
+// compute_update :807-1028 on the full state (bc 1..4), one thread per cell; thread i evaluates the cell
+// ie = (i == 1 ? 2 : i == nx-1 ? nx : i) because dudt(:,:,1) = dudt(:,:,2) and dudt(:,:,nx-1) = dudt(:,:,nx)
+__global__ void k_dg1_update_plain(const double* __restrict__ u, double* __restrict__ dudt, P1d P, Basis1 B, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int it = blockIdx.x * blockDim.x + threadIdx.x + 1;     // 1-based
+  if (it > P.nx) return;
+  const int n = P.n, nx = P.nx;
+  const double gamma = P.gamma;
+  const int ic = (it == 1) ? 2 : (it == nx - 1 ? nx : it);
+  const double dx = P.boxlen / (double)nx, oneoverdx = 1.0 / dx;
+  auto trace = [&](int c, const double* E, double* out) {      // c 1-based
+    for (int v = 0; v < NV; ++v) out[v] = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) out[v] = out[v] + M3(u, v, i, c - 1) * E[i];
+  };
+  auto face = [&](int iface, double* ff) {
+    int ileft = iface - 1, iright = iface;
+    if (P.bc == 1) { if (iface == 1) ileft = nx; if (iface == nx + 1) iright = 1; }
+    if (P.bc == 2 || P.bc == 3) { if (iface == 1) ileft = 1; if (iface == nx + 1) iright = nx; }
+    double a[NV] = {0, 0, 0}, b[NV] = {0, 0, 0};
+    const bool inb = (ileft >= 1 && iright <= nx);
+    if (ileft >= 1) trace(ileft, B.Ep, a);        // u_right(ileft)
+    if (iright <= nx) trace(iright, B.Em, b);     // u_left(iright)
+    for (int v = 0; v < NV; ++v) ff[v] = 0.0;
+    if (inb) { if (P.riemann == 1) riemann_llf(a, b, ff, gamma); else riemann_hllc(a, b, ff, gamma); }
+    if ((P.bc == 3 || P.bc == 4) && iface == 1) {
+      double src[NV], t[NV];
+      if (P.bc == 3) { for (int v = 0; v < NV; ++v) src[v] = b[v]; } else trace(1, B.Ep, src);       // bc 4: u_right(:,1)
+      t[0] = src[0]; t[1] = -src[1]; t[2] = src[2];
+      if (P.riemann == 1) riemann_llf(t, b, ff, gamma); else riemann_hllc(t, b, ff, gamma);
+    }
+    if ((P.bc == 3 || P.bc == 4) && iface == nx + 1) {
+      double src[NV], t[NV];
+      if (P.bc == 3) { for (int v = 0; v < NV; ++v) src[v] = a[v]; } else trace(nx, B.Em, src);       // bc 4: u_left(:,nx)
+      t[0] = src[0]; t[1] = -src[1]; t[2] = src[2];
+      if (P.riemann == 1) riemann_llf(a, t, ff, gamma); else riemann_hllc(a, t, ff, gamma);
+    }
+  };
+  double fq[MAXN][NV], sq[MAXN][NV], F0[NV], F1[NV];
+  for (int j = 0; j < n; ++j) {
+    double uq[NV] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) uq[v] = uq[v] + M3(u, v, i, ic - 1) * B.P[j][i];
+    flux(uq, fq[j], gamma);
+    source_term(uq, sq[j], gamma);
+  }
+  face(ic, F0);
+  face(ic + 1, F1);
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) {
+      double fv = 0.0, sv = 0.0;
+      for (int j = 0; j < n; ++j) {
+        fv = fv + fq[j][v] * B.dP[j][i] * B.wq[j];
+        if (P.source == 2) sv = sv + sq[j][v] * B.P[j][i] * B.wq[j];
+      }
+      M3(dudt, v, i, it - 1) = oneoverdx * (fv - (F1[v] * B.Ep[i] - F0[v] * B.Em[i])) + sv;
+    }
+}
+
+// cons_to_prim :1225-1233, prim_to_cons :1250-1258, cons_to_char :1260-1272, char_to_cons :1274-1286
+__device__ __forceinline__ void cons_to_prim(const double* du, double* dw, const double* w, double gamma) {
+  dw[0] = du[0];
+  dw[1] = (du[1] - w[1] * du[0]) / w[0];
+  dw[2] = (gamma - (double)1.0f) * (0.5 * (w[1] * w[1]) * du[0] - w[1] * du[1] + du[2]);
+}
+__device__ __forceinline__ void prim_to_cons(const double* dw, double* du, const double* w, double gamma) {
+  du[0] = dw[0];
+  du[1] = w[1] * dw[0] + w[0] * dw[1];
+  du[2] = 0.5 * (w[1] * w[1]) * dw[0] + w[0] * w[1] * dw[1] + dw[2] / (gamma - (double)1.0f);
+}
+__device__ __forceinline__ void cons_to_char(const double* du, double* dw, const double* w, double gamma) {
+  double csq = gamma * fmax(w[2], 1e-10) / fmax(w[0], 1e-10), cs = sqrt(csq), dp[NV];
+  cons_to_prim(du, dp, w, gamma);
+  dw[0] = dp[0] - dp[2] / csq;
+  dw[1] = 0.5 * (dp[2] / csq + dp[1] * w[0] / cs);
+  dw[2] = 0.5 * (dp[2] / csq - dp[1] * w[0] / cs);
+}
+__device__ __forceinline__ void char_to_cons(const double* dw, double* du, const double* w, double gamma) {
+  double csq = gamma * fmax(w[2], 1e-10) / fmax(w[0], 1e-10), cs = sqrt(csq), dp[NV];
+  dp[0] = dw[0] + dw[1] + dw[2];
+  dp[1] = (dw[1] - dw[2]) * cs / w[0];
+  dp[2] = (dw[1] + dw[2]) * csq;
+  prim_to_cons(dp, du, w, gamma);
+}
+__device__ __forceinline__ double minmod3(double x, double y, double z) {
+  double s = copysign(1.0, x);
+  if (copysign(1.0, y) == s && copysign(1.0, z) == s) return s * fmin(fmin(fabs(x), fabs(y)), fabs(z));
+  return 0.0;
+}
+// limiter(u) :414-519: reads `u` (un-limited, with neighbours), writes `ul`
+__global__ void k_dg1_limiter(const double* __restrict__ u, double* __restrict__ ul, P1d P, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ic > P.nx) return;
+  const int n = P.n, nx = P.nx;
+  const double gamma = P.gamma;
+  double el[MAXN][NV];
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) el[i][v] = M3(u, v, i, ic - 1);
+  if (P.use_limiter) {
+    int ileft = ic - 1, iright = ic + 1;
+    double switch_left = 1.0, switch_right = 1.0;
+    if (P.bc == 1) { if (ic == 1) ileft = nx; if (ic == nx) iright = 1; }
+    if (P.bc == 2) { if (ic == 1) ileft = 1; if (ic == nx) iright = nx; }
+    if (P.bc == 3) { if (ic == 1) { ileft = 1; switch_left = -1.0; } if (ic == nx) { iright = nx; switch_right = -1.0; } }
+    if (ileft >= 1 && iright <= nx) {
+      double w[NV], wL[MAXN][NV], wM[MAXN][NV], wR[MAXN][NV], w_lim[MAXN][NV];
+      prim(&M3(u, 0, 0, ic - 1), w, gamma);
+      for (int i = n - 1; i >= 1; --i) {
+        double coeff_i = sqrt(2.0 * (double)(i - 1) + 1.0) * (2.0 * (double)i - 1);
+        double coeff_ip1 = sqrt(2.0 * (double)i + 1.0) * (2.0 * (double)i - 1);
+        double uL[NV], uR[NV], uM[NV];
+        for (int v = 0; v < NV; ++v) {
+          uL[v] = (M3(u, v, i - 1, ic - 1) - M3(u, v, i - 1, ileft - 1)) * coeff_i / coeff_ip1;
+          uR[v] = (M3(u, v, i - 1, iright - 1) - M3(u, v, i - 1, ic - 1)) * coeff_i / coeff_ip1;
+          uM[v] = M3(u, v, i, ic - 1);
+        }
+        uL[1] = switch_left * uL[1];
+        uR[1] = switch_right * uR[1];
+        cons_to_char(uL, wL[i], w, gamma);
+        cons_to_char(uR, wR[i], w, gamma);
+        cons_to_char(uM, wM[i], w, gamma);
+      }
+      for (int i = 1; i < n; ++i)
+        for (int v = 0; v < NV; ++v) w_lim[i][v] = wM[i][v];
+      for (int v = 0; v < NV; ++v)
+        for (int i = n - 1; i >= 1; --i) {
+          double w_min = minmod3(wL[i][v], wM[i][v], wR[i][v]);
+          w_lim[i][v] = w_min;
+          if (fabs(w_min - wM[i][v]) < (double)0.01f * fabs(wM[i][v])) break;
+        }
+      for (int i = n - 1; i >= 1; --i) char_to_cons(w_lim[i], el[i], w, gamma);
+    }
+  }
+  {
+    double w[NV], u_left[NV] = {0, 0, 0}, u_right[NV] = {0, 0, 0}, w_left[NV], w_right[NV];
+    prim(el[0], w, gamma);
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        u_left[v] = u_left[v] + el[i - 1][v] * ((i - 1) % 2 == 0 ? 1.0 : -1.0) * sqrt(2.0 * (double)i - 1.0);
+        u_right[v] = u_right[v] + el[i - 1][v] * sqrt(2.0 * (double)i - 1.0);
+      }
+    cons_to_prim(u_left, w_left, w, gamma);
+    cons_to_prim(u_right, w_right, w, gamma);
+    if (w_left[0] < 1e-10 || w_right[0] < 1e-10 || w_left[2] < 1e-10 || w_left[2] < 1e-10)
+      for (int i = 1; i < n; ++i)
+        for (int v = 0; v < NV; ++v) el[i][v] = 0.0;
+  }
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) M3(ul, v, i, ic - 1) = el[i][v];
+}
+
 // nodal reconstruction :313-330: legendre at the PHYSICAL coordinate (clamped to [-1,1]), as shipped
 __device__ __forceinline__ double d_legendre(const Basis1& B, double& x, int n) {
   x = fmin(fmax(x, (double)-1.0f), (double)1.0f);
@@ -245,7 +397,7 @@ __global__ void k_dg1_max_speed(const double* __restrict__ u_nodes, P1d P, CtrlD
     }
   }
 }
-// out = c0*A0 [+ c1*A1] + (cd*dt)*D, left to right
+// out = c0*A0 [+ c1*A1] [+ (cd*dt)*D], left to right (cd == 0: no D term at all)
 __global__ void k_dg1_axpy(double* out, const double* A0, double c0, const double* A1, double c1, const double* D, double cd,
                            int n, int na, const CtrlD* ctrl) {
   if (ctrl->skip) return;
@@ -254,7 +406,7 @@ __global__ void k_dg1_axpy(double* out, const double* A0, double c0, const doubl
   const double cdt = cd * ctrl->dt;
   double r = (c0 == 1.0) ? A0[k] : c0 * A0[k];
   if (na == 2) r = r + c1 * A1[k];
-  out[k] = r + cdt * D[k];
+  out[k] = (cd == 0.0) ? r : r + cdt * D[k];
 }
 __global__ void k_dg1_advance(CtrlD* c) { if (c->skip) return; c->t = c->t + c->dt; c->iter = c->iter + 1; }
 __global__ void k_dg1_ctrl_init(CtrlD* c, double tend, int max_iter) {
@@ -272,7 +424,7 @@ struct wb_dg1d {
   int dev = 0;
   cudaStream_t stream = nullptr;
   size_t N = 0;
-  double *du = nullptr, *ueq = nullptr, *uinit = nullptr, *dudt = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr;
+  double *du = nullptr, *ueq = nullptr, *uinit = nullptr, *dudt = nullptr, *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr, *w6 = nullptr;
   CtrlD* ctrl = nullptr;
   CtrlD* h_ctrl = nullptr;
 };
@@ -290,15 +442,17 @@ int wb_dg1d_create(wb_dg1d** out, const wb_dg1d_params* p) {
   WB_REQUIRE(p->riemann == 1 || p->riemann == 2, "riemann must be 1 (llf) or 2 (hllc)");
   WB_REQUIRE(p->source == 1 || p->source == 2, "source must be 1 or 2");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen > 0, "gamma>1, boxlen>0 required");
+  WB_REQUIRE(p->bc >= 1 && p->bc <= 5, "bc must be 1..5");
   int dev = 0;
   WB_CHECK(select_device(p->device, &dev));
   wb_dg1d* h = new wb_dg1d;
   h->dev = dev;
   h->P.n = p->n; h->P.nx = p->nx; h->P.riemann = p->riemann; h->P.source = p->source; h->P.gamma = p->gamma; h->P.boxlen = p->boxlen;
+  h->P.bc = p->bc; h->P.use_limiter = p->use_limiter ? 1 : 0;
   h->B = make_basis(p->n);
   h->N = (size_t)NV * p->n * p->nx;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  double** bufs[] = {&h->du, &h->ueq, &h->uinit, &h->dudt, &h->w1, &h->w2, &h->w3, &h->w4};
+  double** bufs[] = {&h->du, &h->ueq, &h->uinit, &h->dudt, &h->w1, &h->w2, &h->w3, &h->w4, &h->w5, &h->w6};
   for (double** b : bufs)
     if (e == cudaSuccess) e = cudaMalloc(b, sizeof(double) * h->N);
   if (e == cudaSuccess) e = cudaMalloc(&h->ctrl, sizeof(CtrlD));
@@ -313,7 +467,7 @@ int wb_dg1d_destroy(wb_dg1d* h) {
   cudaSetDevice(h->dev);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   cudaFree(h->du); cudaFree(h->ueq); cudaFree(h->uinit); cudaFree(h->dudt); cudaFree(h->w1); cudaFree(h->w2); cudaFree(h->w3);
-  cudaFree(h->w4); cudaFree(h->ctrl);
+  cudaFree(h->w4); cudaFree(h->w5); cudaFree(h->w6); cudaFree(h->ctrl);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   delete h;
   return WB_OK;
@@ -395,6 +549,110 @@ int wb_dg1d_evolve(wb_dg1d* h, double* delta_u, const double* u_eq, double* uini
     it = h->h_ctrl->iter; t = h->h_ctrl->t; dt = h->h_ctrl->dt;
   }
   WB_CUDA(cudaMemcpyAsync(delta_u, h->du, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaMemcpyAsync(uinit, h->uinit, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (iters) *iters = it;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  return WB_OK;
+}
+
+// replaces compute_update(u,dudt)   dg_with_source.f90:807-1028
+int wb_dg1d_compute_update(wb_dg1d* h, const double* u, double* dudt) {
+  if (!h || !u || !dudt) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(h->P.bc >= 1 && h->P.bc <= 4, "compute_update needs bc 1..4: with bc = 5 the reference reads u_right(:,0) / u_left(:,nx+1) out of bounds");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, u, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_update_plain<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->du, h->dudt, h->P, h->B, nullptr);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(dudt, h->dudt, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+// replaces limiter(u)   dg_with_source.f90:414-519
+int wb_dg1d_limiter(wb_dg1d* h, double* u_inout) {
+  if (!h || !u_inout) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, u_inout, fb, cudaMemcpyHostToDevice, h->stream));
+  if (h->P.n > 1) {
+    k_dg1_limiter<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->du, h->w1, h->P, nullptr);
+    WB_LAUNCH_CHECK();
+    WB_CUDA(cudaMemcpyAsync(u_inout, h->w1, fb, cudaMemcpyDeviceToHost, h->stream));
+  }
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+// main loop with integrator 'RK1' (1), 'RK2' (2), 'RK3' (3), 'RK4' (4)   dg_with_source.f90:173-227, :313-336
+int wb_dg1d_evolve_rk(wb_dg1d* h, int integrator, double* u, const double* delta_u, const double* u_eq, double* uinit, double tend,
+                      int max_iter, int* iters, double* t_out, double* dt_out) {
+  if (!h || !u || !delta_u || !u_eq || !uinit) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(integrator >= 1 && integrator <= 4, "integrator must be 1..4 ('RK1'..'RK4'); 'RKi' is wb_dg1d_evolve");
+  WB_REQUIRE(h->P.bc >= 1 && h->P.bc <= 4, "the plain update needs bc 1..4");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  const int N = (int)h->N;
+  // buffers: w5 holds u, du holds delta_u (constant on these paths), w6 is the limiter scratch
+  double *U = h->w5, *W1 = h->w1, *W2 = h->w2, *W3 = h->w3, *W4 = h->w4, *S = h->w6;
+  WB_CUDA(cudaMemcpyAsync(U, u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->du, delta_u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->ueq, u_eq, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->uinit, uinit, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, tend, max_iter);
+  WB_LAUNCH_CHECK();
+  dim3 bc(64), gc((h->P.nx + 63) / 64), ba(128), ga((N + 127) / 128);
+  auto upd = [&](const double* in) {
+    k_dg1_update_plain<<<gc, bc, 0, h->stream>>>(in, h->dudt, h->P, h->B, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto axpy = [&](double* out, const double* A0, double c0, const double* A1, double c1, double cd, int na) {
+    k_dg1_axpy<<<ga, ba, 0, h->stream>>>(out, A0, c0, A1, c1, h->dudt, cd, N, na, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto lim = [&](double* x) {       // limiter reads neighbours: limit into the scratch, then copy back (skipped steps copy nothing)
+    if (h->P.n == 1) return;
+    k_dg1_limiter<<<gc, bc, 0, h->stream>>>(x, S, h->P, h->ctrl);
+    k_dg1_axpy<<<ga, ba, 0, h->stream>>>(x, S, 1.0, nullptr, 0.0, S, 0.0, N, 1, h->ctrl);
+    wb::g_launches.fetch_add(2);
+  };
+  int it = 0;
+  double t = 0.0, dt = 0.0;
+  for (;;) {
+    if (!(t < tend) || (max_iter >= 0 && it >= max_iter)) break;
+    for (int s = 0; s < 16; ++s) {
+      k_dg1_max_speed<<<1, 256, 0, h->stream>>>(h->uinit, h->P, h->ctrl, 1);
+      wb::g_launches.fetch_add(1);
+      if (integrator == 1) {
+        upd(U); axpy(U, U, 1.0, nullptr, 0.0, 1.0, 1);
+      } else if (integrator == 2) {
+        upd(U); axpy(W1, U, 1.0, nullptr, 0.0, 1.0, 1); lim(W1);
+        upd(W1); axpy(U, U, 0.5, W1, 0.5, 0.5, 2); lim(U);
+      } else if (integrator == 3) {
+        upd(U); axpy(W1, U, 1.0, nullptr, 0.0, 1.0, 1); lim(W1);
+        upd(W1); axpy(W2, U, 0.75, W1, 0.25, 0.25, 2); lim(W2);
+        upd(W2); axpy(U, U, (double)(1.0f / 3.0f), W2, (double)(2.0f / 3.0f), (double)(2.0f / 3.0f), 2); lim(U);
+      } else {
+        // :206 u = u - u_eq (the MODES minus the NODAL equilibrium, as shipped) ... :226 u = u + u_eq
+        axpy(U, U, 1.0, h->ueq, -1.0, 0.0, 2);
+        upd(U); axpy(W1, U, 1.0, nullptr, 0.0, F32(0.391752226571890), 1); lim(W1);
+        upd(W1); axpy(W2, U, F32(0.444370493651235), W1, F32(0.555629506348765), F32(0.368410593050371), 2); lim(W2);
+        upd(W2); axpy(W3, U, F32(0.620101851488403), W2, F32(0.379898148511597), F32(0.251891774271694), 2); lim(W3);
+        upd(W3); axpy(W4, U, F32(0.178079954393132), W3, F32(0.821920045606868), F32(0.544974750228521), 2);
+        axpy(U, W2, F32(0.517231671970585), W3, F32(0.096059710526147), F32(0.063692468666290), 2); lim(W4);
+        upd(W4); axpy(U, U, 1.0, W4, F32(0.386708617503269), F32(0.226007483236906), 2); lim(U);
+        axpy(U, U, 1.0, h->ueq, 1.0, 0.0, 2);
+      }
+      k_dg1_reconstruct<<<gc, bc, 0, h->stream>>>(h->du, h->ueq, h->uinit, h->P, h->B, h->ctrl);
+      k_dg1_advance<<<1, 1, 0, h->stream>>>(h->ctrl);
+      wb::g_launches.fetch_add(2);
+    }
+    WB_CUDA(cudaGetLastError());
+    WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(CtrlD), cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+    it = h->h_ctrl->iter; t = h->h_ctrl->t; dt = h->h_ctrl->dt;
+  }
+  WB_CUDA(cudaMemcpyAsync(u, U, fb, cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaMemcpyAsync(uinit, h->uinit, fb, cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
   if (iters) *iters = it;

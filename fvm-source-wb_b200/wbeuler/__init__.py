@@ -405,15 +405,15 @@ class FV1D(_Handle):
 class DG1DParams(C.Structure):
     """wb_dg1d_params; defaults follow dg_commons.f90."""
     _fields_ = [("n", C.c_int), ("nx", C.c_int), ("nvar", C.c_int), ("riemann", C.c_int), ("source", C.c_int),
-                ("gamma", C.c_double), ("boxlen", C.c_double), ("device", C.c_int)]
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("device", C.c_int), ("bc", C.c_int), ("use_limiter", C.c_int)]
 
 
 class DG1D(_Handle):
     """dg_with_source.f90, integrator 'RKi' (perturbation form).  u(nvar,n,nx) == numpy (nx, n, 3)."""
     _destroy = "wb_dg1d_destroy"
 
-    def __init__(self, n=3, nx=128, riemann=2, source=2, gamma=F32(1.4), boxlen=1.0, device=-1):
-        self.params = DG1DParams(n, nx, 3, riemann, source, gamma, boxlen, device)
+    def __init__(self, n=3, nx=128, riemann=2, source=2, gamma=F32(1.4), boxlen=1.0, device=-1, bc=5, use_limiter=False):
+        self.params = DG1DParams(n, nx, 3, riemann, source, gamma, boxlen, device, bc, int(use_limiter))
         self._h = C.c_void_p()
         _check(lib().wb_dg1d_create(C.byref(self._h), C.byref(self.params)))
         self.shape = (nx, n, 3)
@@ -442,3 +442,24 @@ class DG1D(_Handle):
         _check(lib().wb_dg1d_evolve(self._h, _ptr(d), _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it),
                                     C.byref(t), C.byref(dt)))
         return d, ui, it.value, t.value, dt.value
+
+    def compute_update(self, u):
+        """compute_update(u,dudt)  dg_with_source.f90:807-1028"""
+        d = np.empty(self.shape)
+        _check(lib().wb_dg1d_compute_update(self._h, _ptr(u), _ptr(d)))
+        return d
+
+    def limiter(self, u):
+        """limiter(u)  dg_with_source.f90:414-519"""
+        v = np.array(u, dtype=np.float64, order="C", copy=True)
+        _check(lib().wb_dg1d_limiter(self._h, _ptr(v)))
+        return v
+
+    def evolve_rk(self, integrator, u, delta_u, u_eq, uinit, tend, max_iter=-1):
+        """main loop with 'RK1' | 'RK2' | 'RK3' | 'RK4'  dg_with_source.f90:173-227 -> (u, uinit, iters, t, last_dt)"""
+        uu = np.array(u, dtype=np.float64, order="C", copy=True)
+        ui = np.array(uinit, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_dg1d_evolve_rk(self._h, C.c_int({"RK1": 1, "RK2": 2, "RK3": 3, "RK4": 4}[integrator]), _ptr(uu), _ptr(delta_u),
+                                       _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt)))
+        return uu, ui, it.value, t.value, dt.value

@@ -230,6 +230,9 @@ typedef struct {
   double gamma;    /* :18                                                         */
   double boxlen;   /* :17                                                         */
   int device;
+  int bc;          /* :14   1 periodic, 2 zero gradient, 3|4 reflective, 5 none (default; the delta-form
+                            update freezes the end cells, the plain update needs 1..4)            */
+  int use_limiter; /* :10   moment-limiter part of limiter() on/off (default off)                  */
 } wb_dg1d_params;
 int wb_dg1d_create(wb_dg1d** h, const wb_dg1d_params* p);
 int wb_dg1d_destroy(wb_dg1d* h);
@@ -243,6 +246,15 @@ int wb_dg1d_compute_max_speed(wb_dg1d* h, const double* u_nodes, double* cmax);
  * uinit (nodal state used for the time step, = u_eq + reconstructed delta) are updated in place */
 int wb_dg1d_evolve(wb_dg1d* h, double* delta_u_inout, const double* u_eq, double* uinit_inout, double tend, int max_iter,
                    int* iters_out, double* t_out, double* last_dt_out);
+/* replaces compute_update(u,dudt) on the full state   dg_with_source.f90:807-1028 (bc 1..4) */
+int wb_dg1d_compute_update(wb_dg1d* h, const double* u, double* dudt);
+/* replaces limiter(u)   dg_with_source.f90:414-519 (Krivodonova moment limiter in characteristic variables when
+ * use_limiter, then the positivity fallback) */
+int wb_dg1d_limiter(wb_dg1d* h, double* u_inout);
+/* replaces the main time loop with integrator 'RK1' (1) .. 'RK4' (4)   dg_with_source.f90:173-227, :313-336.
+ * delta_u is constant on these paths; it only feeds the nodal state `uinit` the time step is computed from. */
+int wb_dg1d_evolve_rk(wb_dg1d* h, int integrator, double* u_inout, const double* delta_u, const double* u_eq,
+                      double* uinit_inout, double tend, int max_iter, int* iters_out, double* t_out, double* last_dt_out);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@
 
 #define NV 3
 #define MAXN 4
+#define F32(x) ((double)(x##f))
 
 typedef struct {
   int n;         /* dg_commons.f90:4 (nquad = n) */
@@ -29,6 +30,8 @@ typedef struct {
   double gamma;  /* :18 */
   double boxlen; /* :17 */
   double pert;   /* :19 */
+  int bc;          /* :14  1 periodic, 2 zero gradient, 3 reflective, 4 reflective on the end states; 5 (default) = none */
+  int use_limiter; /* :10 */
 } orc_dg1d_params;
 
 /* root legendre.f90:1-25 (clamps its argument in place) */
@@ -311,7 +314,6 @@ void orc_dg1d_reconstruct(const orc_dg1d_params *p, const double *delta_u, const
   }
 }
 
-#define F32(x) ((double)(x##f))
 /* main loop :173-336 with integrator == 'RKi' (:282-305) */
 void orc_dg1d_evolve_rki(const orc_dg1d_params *p, double *delta_u, const double *u_eq, double *uinit, double tend,
                          int max_iter, int *iters, double *t_out, double *dt_out) {
@@ -343,4 +345,232 @@ void orc_dg1d_evolve_rki(const orc_dg1d_params *p, double *delta_u, const double
   if (t_out) *t_out = t;
   if (dt_out) *dt_out = dt;
   free(dudt); free(w1); free(w2); free(w3); free(w4);
+}
+
+
+/* ==================================================================== plain update, limiter, 'RK1'..'RK4' */
+/* :807-1028 compute_update(u,dudt) on the full state (bc 1..4; with the default bc = 5 the reference reads
+ * u_right(:,0) and u_left(:,nx+1) out of bounds) */
+void orc_dg1d_compute_update(const orc_dg1d_params *p, const double *u, double *dudt) {
+  const int n = p->n, nx = p->nx;
+  const double gamma = p->gamma;
+  basis1_t B; make_basis1(n, &B);
+  const double dx = p->boxlen / (double)nx, oneoverdx = 1.0 / dx;
+  double *u_left = (double *)calloc(NV * nx, sizeof(double)), *u_right = (double *)calloc(NV * nx, sizeof(double));
+  double *flux_face = (double *)calloc(NV * (nx + 1), sizeof(double));
+  double *fv = (double *)calloc(NV * n * nx, sizeof(double)), *sv = (double *)calloc(NV * n * nx, sizeof(double));
+  for (int ic = 0; ic < nx; ++ic) {
+    double fq[MAXN][NV], sq[MAXN][NV];
+    for (int j = 0; j < n; ++j) {
+      double uq[NV] = {0, 0, 0};
+      for (int i = 0; i < n; ++i)
+        for (int v = 0; v < NV; ++v) uq[v] = uq[v] + M3(u, v, i, ic) * B.P[j][i];
+      flux(uq, fq[j], gamma);
+      source_term(uq, sq[j], gamma);
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        for (int v = 0; v < NV; ++v) {
+          M3(fv, v, i, ic) = M3(fv, v, i, ic) + fq[j][v] * B.dP[j][i] * B.wq[j];
+          if (p->source == 2) M3(sv, v, i, ic) = M3(sv, v, i, ic) + sq[j][v] * B.P[j][i] * B.wq[j];
+        }
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        u_left[NV * ic + v] = u_left[NV * ic + v] + M3(u, v, i, ic) * B.Em[i];
+        u_right[NV * ic + v] = u_right[NV * ic + v] + M3(u, v, i, ic) * B.Ep[i];
+      }
+  }
+  for (int iface = 1; iface <= nx + 1; ++iface) {
+    int ileft = iface - 1, iright = iface;
+    if (p->bc == 1) { if (iface == 1) ileft = nx; if (iface == nx + 1) iright = 1; }
+    if (p->bc == 2 || p->bc == 3) { if (iface == 1) ileft = 1; if (iface == nx + 1) iright = nx; }
+    if (ileft < 1 || iright > nx) { if (p->bc != 4) continue; }   /* bc 5: out of bounds in the reference */
+    double *ff = flux_face + NV * (iface - 1);
+    void (*rs)(const double *, const double *, double *, double) = (p->riemann == 1) ? riemann_llf : riemann_hllc;
+    if (ileft >= 1 && iright <= nx) rs(u_right + NV * (ileft - 1), u_left + NV * (iright - 1), ff, gamma);
+    if ((p->bc == 3 || p->bc == 4) && iface == 1) {
+      double t[NV];
+      const double *src = (p->bc == 3) ? u_left + NV * (iright - 1) : u_right + 0;      /* bc 4: u_right(:,1) */
+      t[0] = src[0]; t[1] = -src[1]; t[2] = src[2];
+      rs(t, u_left + NV * (iright - 1), ff, gamma);
+    }
+    if ((p->bc == 3 || p->bc == 4) && iface == nx + 1) {
+      double t[NV];
+      const double *src = (p->bc == 3) ? u_right + NV * (ileft - 1) : u_left + NV * (nx - 1);   /* bc 4: u_left(:,nx) */
+      t[0] = src[0]; t[1] = -src[1]; t[2] = src[2];
+      rs(u_right + NV * (ileft - 1), t, ff, gamma);
+    }
+  }
+  for (int ic = 0; ic < nx; ++ic)
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v)
+        M3(dudt, v, i, ic) = oneoverdx * (M3(fv, v, i, ic) - (flux_face[NV * (ic + 1) + v] * B.Ep[i] - flux_face[NV * ic + v] * B.Em[i]))
+                             + M3(sv, v, i, ic);
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) { M3(dudt, v, i, 0) = M3(dudt, v, i, 1); M3(dudt, v, i, nx - 2) = M3(dudt, v, i, nx - 1); }
+  free(u_left); free(u_right); free(flux_face); free(fv); free(sv);
+}
+
+/* :1225-1233, :1250-1258, :1260-1286 */
+static void cons_to_prim(const double *du, double *dw, const double *w, double gamma) {
+  dw[0] = du[0];
+  dw[1] = (du[1] - w[1] * du[0]) / w[0];
+  dw[2] = (gamma - (double)1.0f) * (0.5 * (w[1] * w[1]) * du[0] - w[1] * du[1] + du[2]);
+}
+static void prim_to_cons(const double *dw, double *du, const double *w, double gamma) {
+  du[0] = dw[0];
+  du[1] = w[1] * dw[0] + w[0] * dw[1];
+  du[2] = 0.5 * (w[1] * w[1]) * dw[0] + w[0] * w[1] * dw[1] + dw[2] / (gamma - (double)1.0f);
+}
+static void cons_to_char(const double *du, double *dw, const double *w, double gamma) {
+  double csq = gamma * fmax(w[2], 1e-10) / fmax(w[0], 1e-10), cs = sqrt(csq), dp[NV];
+  cons_to_prim(du, dp, w, gamma);
+  dw[0] = dp[0] - dp[2] / csq;
+  dw[1] = 0.5 * (dp[2] / csq + dp[1] * w[0] / cs);
+  dw[2] = 0.5 * (dp[2] / csq - dp[1] * w[0] / cs);
+}
+static void char_to_cons(const double *dw, double *du, const double *w, double gamma) {
+  double csq = gamma * fmax(w[2], 1e-10) / fmax(w[0], 1e-10), cs = sqrt(csq), dp[NV];
+  dp[0] = dw[0] + dw[1] + dw[2];
+  dp[1] = (dw[1] - dw[2]) * cs / w[0];
+  dp[2] = (dw[1] + dw[2]) * csq;
+  prim_to_cons(dp, du, w, gamma);
+}
+static double minmod3(double x, double y, double z) {      /* :1155-1165 */
+  double s = copysign(1.0, x);
+  if (copysign(1.0, y) == s && copysign(1.0, z) == s) return s * fmin(fmin(fabs(x), fabs(y)), fabs(z));
+  return 0.0;
+}
+/* :414-519 limiter(u): Krivodonova moment limiter in characteristic variables (if use_limiter) + positivity fallback */
+void orc_dg1d_limiter(const orc_dg1d_params *p, double *u) {
+  const int n = p->n, nx = p->nx;
+  const double gamma = p->gamma;
+  if (n == 1) return;
+  size_t N = (size_t)NV * n * nx;
+  double *ul = (double *)malloc(sizeof(double) * N);
+  memcpy(ul, u, sizeof(double) * N);
+  if (p->use_limiter) {
+    for (int ic = 1; ic <= nx; ++ic) {
+      int ileft = ic - 1, iright = ic + 1;
+      double switch_left = 1.0, switch_right = 1.0;
+      if (p->bc == 1) { if (ic == 1) ileft = nx; if (ic == nx) iright = 1; }
+      if (p->bc == 2) { if (ic == 1) ileft = 1; if (ic == nx) iright = nx; }
+      if (p->bc == 3) { if (ic == 1) { ileft = 1; switch_left = -1.0; } if (ic == nx) { iright = nx; switch_right = -1.0; } }
+      if (ileft < 1 || iright > nx) continue;        /* bc 4/5: out of bounds in the reference */
+      double w[NV], wL[MAXN][NV], wM[MAXN][NV], wR[MAXN][NV], w_lim[MAXN][NV];
+      prim(&M3(u, 0, 0, ic - 1), w, gamma);
+      for (int i = n - 1; i >= 1; --i) {
+        double coeff_i = sqrt(2.0 * (double)(i - 1) + 1.0) * (2.0 * (double)i - 1);
+        double coeff_ip1 = sqrt(2.0 * (double)i + 1.0) * (2.0 * (double)i - 1);
+        double uL[NV], uR[NV], uM[NV];
+        for (int v = 0; v < NV; ++v) {
+          uL[v] = (M3(u, v, i - 1, ic - 1) - M3(u, v, i - 1, ileft - 1)) * coeff_i / coeff_ip1;
+          uR[v] = (M3(u, v, i - 1, iright - 1) - M3(u, v, i - 1, ic - 1)) * coeff_i / coeff_ip1;
+          uM[v] = M3(u, v, i, ic - 1);
+        }
+        uL[1] = switch_left * uL[1];
+        uR[1] = switch_right * uR[1];
+        cons_to_char(uL, wL[i], w, gamma);
+        cons_to_char(uR, wR[i], w, gamma);
+        cons_to_char(uM, wM[i], w, gamma);
+      }
+      for (int i = 1; i < n; ++i) for (int v = 0; v < NV; ++v) w_lim[i][v] = wM[i][v];
+      for (int v = 0; v < NV; ++v)
+        for (int i = n - 1; i >= 1; --i) {
+          double w_min = minmod3(wL[i][v], wM[i][v], wR[i][v]);
+          w_lim[i][v] = w_min;
+          if (fabs(w_min - wM[i][v]) < (double)0.01f * fabs(wM[i][v])) break;
+        }
+      for (int i = n - 1; i >= 1; --i) char_to_cons(w_lim[i], &M3(ul, 0, i, ic - 1), w, gamma);
+    }
+  }
+  for (int ic = 0; ic < nx; ++ic) {
+    double w[NV], u_left[NV] = {0, 0, 0}, u_right[NV] = {0, 0, 0}, w_left[NV], w_right[NV];
+    prim(&M3(ul, 0, 0, ic), w, gamma);
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        u_left[v] = u_left[v] + M3(ul, v, i - 1, ic) * pow((double)-1.0f, i - 1) * sqrt(2.0 * (double)i - 1.0);
+        u_right[v] = u_right[v] + M3(ul, v, i - 1, ic) * sqrt(2.0 * (double)i - 1.0);
+      }
+    cons_to_prim(u_left, w_left, w, gamma);
+    cons_to_prim(u_right, w_right, w, gamma);
+    if (w_left[0] < 1e-10 || w_right[0] < 1e-10 || w_left[2] < 1e-10 || w_left[2] < 1e-10)
+      for (int i = 1; i < n; ++i) for (int v = 0; v < NV; ++v) M3(ul, v, i, ic) = 0.0;
+  }
+  memcpy(u, ul, sizeof(double) * N);
+  free(ul);
+}
+
+/* main loop :173-336 with integrator 'RK1'..'RK4' (id 1..4).  delta_u is never updated on these paths, so the nodal
+ * state `uinit` that feeds the time step becomes u_eq + reconstruct(delta_u) after the first step and stays there. */
+void orc_dg1d_evolve_rk(const orc_dg1d_params *p, int integrator, double *u, const double *delta_u, const double *u_eq,
+                        double *uinit, double tend, int max_iter, int *iters, double *t_out, double *dt_out) {
+  const size_t N = (size_t)NV * p->n * p->nx;
+  const double dx = p->boxlen / (double)p->nx;
+  double *dudt = (double *)malloc(sizeof(double) * N), *w1 = (double *)malloc(sizeof(double) * N), *w2 = (double *)malloc(sizeof(double) * N);
+  double *w3 = (double *)malloc(sizeof(double) * N), *w4 = (double *)malloc(sizeof(double) * N);
+  double t = 0, dt = 0, cmax;
+  int iter = 0;
+  while (t < tend && (max_iter < 0 || iter < max_iter)) {
+    orc_dg1d_compute_max_speed(p, uinit, &cmax);
+    dt = (double)0.9f * dx / cmax / (2.0 * (double)p->n + 1.0);
+    if (integrator == 1) {
+      orc_dg1d_compute_update(p, u, dudt);
+      for (size_t k = 0; k < N; ++k) u[k] = u[k] + dt * dudt[k];
+    } else if (integrator == 2) {
+      orc_dg1d_compute_update(p, u, dudt);
+      for (size_t k = 0; k < N; ++k) w1[k] = u[k] + dt * dudt[k];
+      orc_dg1d_limiter(p, w1);
+      orc_dg1d_compute_update(p, w1, dudt);
+      for (size_t k = 0; k < N; ++k) u[k] = 0.5 * u[k] + 0.5 * w1[k] + 0.5 * dt * dudt[k];
+      orc_dg1d_limiter(p, u);
+    } else if (integrator == 3) {
+      orc_dg1d_compute_update(p, u, dudt);
+      for (size_t k = 0; k < N; ++k) w1[k] = u[k] + dt * dudt[k];
+      orc_dg1d_limiter(p, w1);
+      orc_dg1d_compute_update(p, w1, dudt);
+      for (size_t k = 0; k < N; ++k) w2[k] = 0.75 * u[k] + 0.25 * w1[k] + 0.25 * dt * dudt[k];
+      orc_dg1d_limiter(p, w2);
+      orc_dg1d_compute_update(p, w2, dudt);
+      for (size_t k = 0; k < N; ++k) u[k] = (double)(1.0f / 3.0f) * u[k] + (double)(2.0f / 3.0f) * w2[k] + (double)(2.0f / 3.0f) * dt * dudt[k];
+      orc_dg1d_limiter(p, u);
+    } else {
+      for (size_t k = 0; k < N; ++k) u[k] = u[k] - u_eq[k];            /* :206 (modes minus NODAL equilibrium, as shipped) */
+      orc_dg1d_compute_update(p, u, dudt);
+      for (size_t k = 0; k < N; ++k) w1[k] = u[k] + F32(0.391752226571890) * dt * dudt[k];
+      orc_dg1d_limiter(p, w1);
+      orc_dg1d_compute_update(p, w1, dudt);
+      for (size_t k = 0; k < N; ++k) w2[k] = F32(0.444370493651235) * u[k] + F32(0.555629506348765) * w1[k] + F32(0.368410593050371) * dt * dudt[k];
+      orc_dg1d_limiter(p, w2);
+      orc_dg1d_compute_update(p, w2, dudt);
+      for (size_t k = 0; k < N; ++k) w3[k] = F32(0.620101851488403) * u[k] + F32(0.379898148511597) * w2[k] + F32(0.251891774271694) * dt * dudt[k];
+      orc_dg1d_limiter(p, w3);
+      orc_dg1d_compute_update(p, w3, dudt);
+      for (size_t k = 0; k < N; ++k) w4[k] = F32(0.178079954393132) * u[k] + F32(0.821920045606868) * w3[k] + F32(0.544974750228521) * dt * dudt[k];
+      for (size_t k = 0; k < N; ++k) u[k] = F32(0.517231671970585) * w2[k] + F32(0.096059710526147) * w3[k] + F32(0.063692468666290) * dt * dudt[k];
+      orc_dg1d_limiter(p, w4);
+      orc_dg1d_compute_update(p, w4, dudt);
+      for (size_t k = 0; k < N; ++k) u[k] = u[k] + F32(0.386708617503269) * w4[k] + F32(0.226007483236906) * dt * dudt[k];
+      orc_dg1d_limiter(p, u);
+      for (size_t k = 0; k < N; ++k) u[k] = u[k] + u_eq[k];
+    }
+    orc_dg1d_reconstruct(p, delta_u, u_eq, uinit);
+    t = t + dt;
+    iter = iter + 1;
+  }
+  if (iters) *iters = iter;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  free(dudt); free(w1); free(w2); free(w3); free(w4);
+}
+
+/* program dg :33-47: projection of the full initial state onto the modes `u` */
+void orc_dg1d_project(const orc_dg1d_params *p, const double *u_nodes, double *u_modes) {
+  const int n = p->n, nx = p->nx;
+  basis1_t B; make_basis1(n, &B);
+  memset(u_modes, 0, sizeof(double) * NV * n * nx);
+  for (int ic = 0; ic < nx; ++ic)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        for (int v = 0; v < NV; ++v) M3(u_modes, v, i, ic) = M3(u_modes, v, i, ic) + 0.5 * M3(u_nodes, v, j, ic) * B.P[j][i] * B.wq[j];
 }

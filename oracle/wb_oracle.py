@@ -328,11 +328,11 @@ def fv1d_evolve(p, u, w_eq, tend, max_iter=-1):
 # ---------------------------------------------------------------- 1D DG (dg_with_source.f90, root legendre.f90)
 class DG1DParams(C.Structure):
     _fields_ = [("n", C.c_int), ("nx", C.c_int), ("riemann", C.c_int), ("source", C.c_int), ("ninit", C.c_int),
-                ("gamma", C.c_double), ("boxlen", C.c_double), ("pert", C.c_double)]
+                ("gamma", C.c_double), ("boxlen", C.c_double), ("pert", C.c_double), ("bc", C.c_int), ("use_limiter", C.c_int)]
 
 
-def dg1d_params(n=3, nx=128, riemann=2, source=2, ninit=8, gamma=F32(1.4), boxlen=1.0, pert=F32(1e-8)):
-    return DG1DParams(n, nx, riemann, source, ninit, gamma, boxlen, pert)
+def dg1d_params(n=3, nx=128, riemann=2, source=2, ninit=8, gamma=F32(1.4), boxlen=1.0, pert=F32(1e-8), bc=5, use_limiter=0):
+    return DG1DParams(n, nx, riemann, source, ninit, gamma, boxlen, pert, bc, use_limiter)
 
 
 def dg1d_quadrature(p):
@@ -373,3 +373,32 @@ def dg1d_evolve_rki(p, delta_u, u_eq, uinit, tend, max_iter=-1):
     lib().orc_dg1d_evolve_rki(C.byref(p), _ptr(d), _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it),
                               C.byref(t), C.byref(dt))
     return d, ui, it.value, t.value, dt.value
+
+
+def dg1d_project(p, u_nodes):
+    m = np.empty_like(u_nodes)
+    lib().orc_dg1d_project(C.byref(p), _ptr(u_nodes), _ptr(m))
+    return m
+
+
+def dg1d_compute_update(p, u):
+    d = np.empty_like(u)
+    lib().orc_dg1d_compute_update(C.byref(p), _ptr(u), _ptr(d))
+    return d
+
+
+def dg1d_limiter(p, u):
+    v = np.array(u, copy=True)
+    lib().orc_dg1d_limiter(C.byref(p), _ptr(v))
+    return v
+
+
+INTEGRATORS_1D = {"RK1": 1, "RK2": 2, "RK3": 3, "RK4": 4}
+
+
+def dg1d_evolve_rk(p, integrator, u, delta_u, u_eq, uinit, tend, max_iter=-1):
+    uu = np.array(u, copy=True); ui = np.array(uinit, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_dg1d_evolve_rk(C.byref(p), C.c_int(INTEGRATORS_1D[integrator]), _ptr(uu), _ptr(delta_u), _ptr(u_eq), _ptr(ui),
+                             C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt))
+    return uu, ui, it.value, t.value, dt.value

@@ -111,6 +111,24 @@ def dg1d():
         du2, ui2, it, t, dt = o.dg1d_evolve_rki(p, du, ueq, ui, 1.0, steps)
         out[f"{tag}_du2"] = du2; out[f"{tag}_ui2"] = ui2; out[f"{tag}_clock"] = np.array([it, t, dt])
         assert np.all(np.isfinite(du2)), tag
+    # plain update / limiter / 'RK1'..'RK4' (dg_with_source.f90:807-1028, :414-519, :173-230)
+    rng = np.random.default_rng(11)
+    for tag, n, nx, riemann, source, bc, use_limiter, integ, steps, ninit, pert in (
+            ("rk2_periodic_lim", 3, 48, 2, 2, 1, 1, 2, 3, 8, 1e-2), ("rk3_zerograd", 3, 40, 1, 2, 2, 1, 3, 3, 8, 1e-3),
+            ("rk4_reflect", 2, 33, 2, 2, 3, 1, 4, 2, 8, 1e-3), ("rk1_sod_bc2", 3, 50, 2, 1, 2, 0, 1, 4, 4, 0.0),
+            ("rk3_sod_lim", 3, 50, 2, 1, 2, 1, 3, 4, 4, 0.0), ("rk2_bc4", 2, 20, 1, 2, 4, 0, 2, 2, 8, 1e-2)):
+        p = o.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, ninit=ninit, pert=pert, bc=bc, use_limiter=use_limiter)
+        ui, ueq, du = o.dg1d_setup(p)
+        u = o.dg1d_project(p, ui)
+        if n > 1:
+            u[:, 1:, :] += 1e-3 * rng.standard_normal(u[:, 1:, :].shape)      # exercise the moment limiter
+        out[f"{tag}_pmeta"] = np.array([n, nx, riemann, source, bc, use_limiter, integ, steps])
+        out[f"{tag}_u"] = u; out[f"{tag}_du"] = du; out[f"{tag}_ueq"] = ueq; out[f"{tag}_ui"] = ui
+        out[f"{tag}_dudt"] = o.dg1d_compute_update(p, u)
+        out[f"{tag}_lim"] = o.dg1d_limiter(p, u)
+        u2, ui2, it, t, dt = o.dg1d_evolve_rk(p, f"RK{integ}", u, du, ueq, ui, 1.0, steps)
+        out[f"{tag}_u2"] = u2; out[f"{tag}_ui2"] = ui2; out[f"{tag}_pclock"] = np.array([it, t, dt])
+        assert np.all(np.isfinite(u2)), tag
     np.savez_compressed(os.path.join(HERE, "dg1d.npz"), **out)
 
 

@@ -77,3 +77,45 @@ def test_golden_vectors(wb):
             got, gi, it, t, dt = s.evolve(g[f"{tag}_du"], g[f"{tag}_ueq"], g[f"{tag}_ui"], 1.0, steps)
         assert it == int(g[f"{tag}_clock"][0]), tag
         assert np.abs(gi - g[f"{tag}_ui2"]).max() <= TOL * np.abs(g[f"{tag}_ui2"]).max(), tag
+
+
+# ---------------------------------------------------------------- plain update / limiter / 'RK1'..'RK4'
+def _plain_cases():
+    g = np.load(GOLD)
+    return [k[:-6] for k in g.files if k.endswith("_pmeta")]
+
+
+@pytest.mark.parametrize("tag", _plain_cases())
+def test_plain_update_limiter_and_rk_paths_match_oracle_and_golden(wb, oracle, tag):
+    """compute_update (:807-1028), limiter (:414-519) and the 'RK1'..'RK4' main loop (:173-230): reference operation
+    order on the device -> the update agrees to the last bits of the O(1) fluxes over dx, the limiter bit for bit
+    except through pow/sqrt-free algebra (identical), whole steps to 1e-12."""
+    g = np.load(GOLD)
+    n, nx, riemann, source, bc, use_limiter, integ, steps = (int(v) for v in g[f"{tag}_pmeta"])
+    u, du, ueq, ui = g[f"{tag}_u"], g[f"{tag}_du"], g[f"{tag}_ueq"], g[f"{tag}_ui"]
+    p = oracle.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, bc=bc, use_limiter=use_limiter)
+    scale = max(np.abs(u).max(), 1.0)
+    with wb.DG1D(n=n, nx=nx, riemann=riemann, source=source, bc=bc, use_limiter=bool(use_limiter)) as s:
+        d = s.compute_update(u)
+        dref = oracle.dg1d_compute_update(p, u)
+        assert np.array_equal(dref, g[f"{tag}_dudt"])
+        dt = float(g[f"{tag}_pclock"][2])
+        assert np.abs(dt * (d - dref)).max() <= TOL * scale, tag
+        lim = s.limiter(u)
+        assert np.abs(lim - g[f"{tag}_lim"]).max() <= TOL * scale, tag
+        u2, ui2, it, t, dtl = s.evolve_rk(f"RK{integ}", u, du, ueq, ui, 1.0, steps)
+    assert it == int(g[f"{tag}_pclock"][0]) and abs(t - g[f"{tag}_pclock"][1]) <= 1e-14 * t, tag
+    assert np.abs(u2 - g[f"{tag}_u2"]).max() <= TOL * scale, tag
+    assert np.abs(ui2 - g[f"{tag}_ui2"]).max() <= TOL * np.abs(g[f"{tag}_ui2"]).max(), tag
+
+
+def test_limiter_flattens_cells_with_negative_traces(wb, oracle):
+    p = oracle.dg1d_params(n=3, nx=64, bc=1, use_limiter=0)
+    rng = np.random.default_rng(5)
+    u = np.zeros((64, 3, 3))
+    u[:, 0, 0] = 1.0; u[:, 0, 2] = 2.5
+    u[:, 1:, :] = 0.01 * rng.standard_normal((64, 2, 3))
+    u[10, 1, 0] = 5.0
+    with wb.DG1D(n=3, nx=64, bc=1, use_limiter=False) as s:
+        v = s.limiter(u)
+    assert np.array_equal(v, oracle.dg1d_limiter(p, u)) and np.all(v[10, 1:] == 0)

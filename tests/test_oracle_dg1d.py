@@ -80,3 +80,139 @@ def test_golden_vectors(oracle):
         du2, ui2, it, t, dt = oracle.dg1d_evolve_rki(p, du, ueq, ui, 1.0, steps)
         assert np.array_equal(du2, g[f"{tag}_du2"]) and np.array_equal(ui2, g[f"{tag}_ui2"])
         assert np.array_equal(np.array([it, t, dt]), g[f"{tag}_clock"])
+
+
+# ---------------------------------------------------------------- plain update / limiter / 'RK1'..'RK4' (:807-1028, :414-519, :173-230)
+def _smooth_periodic_modes(oracle, p):
+    """Projection (program dg :33-47, 0.5 factor) of a smooth periodic full state sampled at the quadrature nodes."""
+    x, w = oracle.dg1d_quadrature(p)
+    dx = p.boxlen / p.nx
+    xc = (np.arange(p.nx) + 0.5) * dx
+    xq = xc[:, None] + 0.5 * dx * x[None, :]
+    rho = 1.0 + 0.2 * np.sin(2 * np.pi * xq)
+    v = 0.3 + 0.0 * xq
+    pr = 1.0 + 0.0 * xq
+    un = np.stack([rho, rho * v, pr / (p.gamma - 1.0) + 0.5 * rho * v * v], axis=-1)
+    return oracle.dg1d_project(p, un), un
+
+
+def test_plain_update_constant_state_and_end_cell_copies(oracle):
+    """compute_update on a constant state without source: every face flux equals the physical flux, so the mean mode
+    of dudt is round-off; for the higher modes the volume integral of a constant flux against P'_i only cancels the
+    edge terms up to the real(4) GL weights of the root legendre.f90 (sum = 2 + 6e-8) -> O(6e-8 F/dx),
+    a property of the reference; :1026-1027 copy cell 2 -> 1 and cell nx -> nx-1."""
+    for riemann in (1, 2):
+        p = oracle.dg1d_params(n=3, nx=32, riemann=riemann, source=1, bc=1)
+        un = np.broadcast_to(np.array([1.3, 0.4, 2.2]), (p.nx, p.n, 3)).copy()
+        u = oracle.dg1d_project(p, un)
+        d = oracle.dg1d_compute_update(p, u)
+        assert np.abs(d[:, 0, :]).max() <= 1e-12
+        assert 1e-7 < np.abs(d[:, 1:, :]).max() <= 6e-8 * 5.0 * p.nx * 2
+    p = oracle.dg1d_params(n=3, nx=32, riemann=2, source=2, bc=1)
+    u, _ = _smooth_periodic_modes(oracle, p)
+    d = oracle.dg1d_compute_update(p, u)
+    assert np.array_equal(d[0], d[1]) and np.array_equal(d[-2], d[-1]) and not np.array_equal(d[2], d[3])
+
+
+def test_plain_update_is_consistent_with_the_euler_equations(oracle):
+    """Mean mode of dudt ~ -(F(x+)-F(x-))/dx * P0-projection: for pure advection of a density wave (v, p constant)
+    d(rho)/dt = -v d(rho)/dx.  SURVEY 9.10: with the orthonormal root basis, the 0.5 projection factor and the 1/dx
+    (not 2/dx) in :1019 the scheme is a consistent DG running at HALF speed (the Euler flux is homogeneous of degree 1,
+    so the halved reconstructed state gives a halved flux): the cell-mean rate is 0.5 x the analytic one."""
+    errs = []
+    for nx in (32, 64):
+        p = oracle.dg1d_params(n=3, nx=nx, riemann=1, source=1, bc=1)
+        u, un = _smooth_periodic_modes(oracle, p)
+        d = oracle.dg1d_compute_update(p, u)
+        dx = 1.0 / nx
+        xc = (np.arange(nx) + 0.5) * dx
+        # cell average of -v*rho_x = -0.3*0.2*(sin(2pi x+) - sin(2pi x-))/dx
+        exact = -0.3 * 0.2 * (np.sin(2 * np.pi * (xc + dx / 2)) - np.sin(2 * np.pi * (xc - dx / 2))) / dx
+        # mean mode = 0.5 * P0 * integral over [-1,1] = P0 * cell average (P0 = sqrt(.5) f32)
+        got = d[2:-2, 0, 0] / 0.7071067690849304
+        errs.append(np.abs(got - 0.5 * exact[2:-2]).max())
+    assert errs[0] < 1e-3 and errs[1] < errs[0] / 7          # ~ third-order decay of the mean-rate error
+
+
+def test_limiter_keeps_means_and_smooth_data_and_flattens_negative_cells(oracle):
+    p = oracle.dg1d_params(n=3, nx=64, bc=1, use_limiter=1)
+    u, _ = _smooth_periodic_modes(oracle, p)
+    v = oracle.dg1d_limiter(p, u)
+    assert np.array_equal(v[:, 0, :], u[:, 0, :])                               # means untouched
+    # smooth data: the slopes survive (characteristic round trip only); the curvature moment is clipped where it
+    # changes sign (minmod of neighbour slope differences) by at most its own size, and the 1 % test (:478) then
+    # stops the cascade before it reaches the slope
+    assert np.abs(v[:, 1] - u[:, 1]).max() <= 1e-15
+    assert 0 < np.abs(v[:, 2] - u[:, 2]).max() <= 0.06 * np.abs(u[:, 2]).max()
+    p0 = oracle.dg1d_params(n=3, nx=64, bc=1, use_limiter=0)
+    assert np.array_equal(oracle.dg1d_limiter(p0, u), u)                        # positivity part alone: identity here
+    bad = u.copy()
+    bad[10, 1, 0] = 5.0                                                         # slope that drives rho(-1) negative
+    w = oracle.dg1d_limiter(p0, bad)
+    assert np.all(w[10, 1:, :] == 0.0) and np.array_equal(w[10, 0], bad[10, 0])
+    assert np.array_equal(np.delete(w, 10, axis=0), np.delete(bad, 10, axis=0))
+    p1 = oracle.dg1d_params(n=1, nx=8, bc=1, use_limiter=1)
+    u1 = np.random.default_rng(0).random((8, 1, 3)) + 1
+    assert np.array_equal(oracle.dg1d_limiter(p1, u1), u1)                      # n == 1: return (:431)
+
+
+def test_limiter_on_a_jump_is_tvd_in_the_means_sense(oracle):
+    """Square density pulse projected on order-3 modes: the moment limiter zeroes the higher moments of the cells next
+    to the jump (minmod of differences with opposite signs) and leaves the flat regions alone."""
+    p = oracle.dg1d_params(n=3, nx=40, bc=2, use_limiter=1)
+    un = np.zeros((40, 3, 3))
+    un[..., 0] = 1.0; un[..., 2] = 2.5
+    un[15:25, :, 0] = 2.0
+    u = oracle.dg1d_project(p, un)
+    u[15, 1, 0] = 0.3; u[24, 1, 0] = -0.3                                        # spurious slopes at the extrema
+    v = oracle.dg1d_limiter(p, u)
+    assert abs(v[15, 1, 0]) <= 1e-15 + abs(u[15, 1, 0]) and np.abs(v[5, 1:, :]).max() == 0.0
+    assert np.abs(v[24, 1, 0]) <= abs(u[24, 1, 0])
+
+
+@pytest.mark.parametrize("integ,order", [("RK2", 2), ("RK3", 3)])
+def test_rk_paths_advect_a_density_wave(oracle, integ, order):
+    """'RK2'/'RK3' on the plain update (periodic, no source): a density wave moves with v = 0.3 at half speed
+    (SURVEY 9.10); the cell means after t = 0.05 match the shifted profile with an error that decays at least ~4x per refinement (time step ~ dx)."""
+    errs = []
+    for nx in (16, 32):
+        p = oracle.dg1d_params(n=3, nx=nx, riemann=1, source=1, bc=1)
+        u, un = _smooth_periodic_modes(oracle, p)
+        du = np.zeros_like(u)
+        u2, ui2, it, t, dt = oracle.dg1d_evolve_rk(p, integ, u, du, un, un, 0.05)
+        dx = 1.0 / nx
+        xc = (np.arange(nx) + 0.5) * dx
+        s = 0.5 * 0.3 * t
+        mean = 1.0 - 0.2 * (np.cos(2 * np.pi * (xc + dx / 2 - s)) - np.cos(2 * np.pi * (xc - dx / 2 - s))) / (2 * np.pi * dx)
+        got = u2[3:-3, 0, 0] / 0.7071067690849304
+        errs.append(np.abs(got - mean[3:-3]).max())
+        assert t >= 0.05 and it > 3
+    assert errs[1] < errs[0] / 4 and errs[1] < 2e-4
+
+
+def test_rk4_path_subtracts_the_nodal_equilibrium_as_shipped(oracle):
+    """'RK4' (:205-227) does u = u - u_eq (modes minus NODAL values, as shipped) before the stages and adds it back:
+    with u_eq == 0 it must coincide with running the five stages directly; with a non-zero u_eq it differs."""
+    p = oracle.dg1d_params(n=3, nx=24, riemann=2, source=1, bc=1)
+    u, un = _smooth_periodic_modes(oracle, p)
+    z = np.zeros_like(u)
+    a, _, it, t, dt = oracle.dg1d_evolve_rk(p, "RK4", u, z, z, un, 1.0, 1)
+    b, _, _, _, _ = oracle.dg1d_evolve_rk(p, "RK3", u, z, z, un, 1.0, 1)
+    assert it == 1 and np.abs(a - b).max() < 1e-6 and np.abs(a - b).max() > 0
+    c, _, _, _, _ = oracle.dg1d_evolve_rk(p, "RK4", u, z, 0.01 * un, un, 1.0, 1)
+    assert np.abs(c - a).max() > 1e-8
+
+
+def test_golden_vectors_plain_paths(oracle):
+    g = np.load(GOLD)
+    tags = [k[:-6] for k in g.files if k.endswith("_pmeta")]
+    assert tags
+    for tag in tags:
+        n, nx, riemann, source, bc, use_limiter, integ, steps = (int(v) for v in g[f"{tag}_pmeta"])
+        p = oracle.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, bc=bc, use_limiter=use_limiter)
+        u, du, ueq, ui = g[f"{tag}_u"], g[f"{tag}_du"], g[f"{tag}_ueq"], g[f"{tag}_ui"]
+        assert np.array_equal(oracle.dg1d_compute_update(p, u), g[f"{tag}_dudt"]), tag
+        assert np.array_equal(oracle.dg1d_limiter(p, u), g[f"{tag}_lim"]), tag
+        u2, ui2, it, t, dt = oracle.dg1d_evolve_rk(p, f"RK{integ}", u, du, ueq, ui, 1.0, steps)
+        assert np.array_equal(u2, g[f"{tag}_u2"]) and np.array_equal(ui2, g[f"{tag}_ui2"]), tag
+        assert np.array_equal(np.array([it, t, dt]), g[f"{tag}_pclock"]), tag
