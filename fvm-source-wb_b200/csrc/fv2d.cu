@@ -47,6 +47,7 @@ struct StageArgs {
   double tend;
   int max_iter;
   int row_begin, row_end;   // local rows [row_begin,row_end) covered by this launch
+  int pf_rows;              // marching kernel: L2 prefetch distance in rows (0 = off)
 };
 
 // ------------------------------------------------------------------------------------ layout kernels
@@ -444,6 +445,12 @@ __device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const 
   }
 }
 
+// L2 prefetch of one row segment of one plane (bulk prefetch: one warp-level instruction brings `bytes` contiguous
+// bytes into L2; nothing is written, no completion to wait for).  16-byte aligned address and size.
+__device__ __forceinline__ void l2_prefetch_bulk(const char* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // Per-thread constants of the marching loop.
 struct MarchCtx {
   int lane, ic, ih, jmin, jmax;
@@ -516,7 +523,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs 
       bookkeeping<MODE>(A.ctrl, A.parity, c.dt);
   }
   c.lane = threadIdx.x & 31;
-  const int wc = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // tells the compiler the value is warp-uniform
+  const int wc = blockIdx.x * MARCH_WARPS + warp;
   const int c0 = wc * MARCH_OUT;
   if (c0 >= g.nx) return;                                  // whole warp: no barriers in this kernel
   const int jb = A.row_begin + blockIdx.y * R;
@@ -544,10 +552,44 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs 
     const double e = c.exc_i * A.eyf[jb];
     Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
   }
+  // ---- L2 prefetch stream.  The register prefetch above gives one row of lead, which at 4 warps per scheduler
+  //      does not cover the DRAM latency (the first use of the prefetched row was 40 % of all stall samples).
+  //      So every row each warp also asks L2 for the CTA's 1 KiB segment (4 x 31 columns + halo) of local row
+  //      j + pf_rows of "its" input planes: plane p (u x4, eq x2, u^n x4 in stage 2) belongs to warp p mod 4.
+  //      UBLKPF is a uniform-datapath instruction: one issue per warp, addresses from warp-uniform registers.
+  constexpr int NPF = (MODE == 2) ? 10 : 6;
+  constexpr int NPW = (NPF + MARCH_WARPS - 1) / MARCH_WARPS;
+  const char* pf[NPW];
+  const size_t pitchB = (size_t)g.pitch * sizeof(double);
+  unsigned pf_bytes = 0;
+  int pf_last = -1;                                        // last local row worth prefetching for this strip
+  if (A.pf_rows > 0) {
+    const int s0 = max((int)blockIdx.x * MARCH_WARPS * MARCH_OUT - 1, 0) & ~1;   // even column: 16-byte aligned
+    pf_bytes = (unsigned)(min(128, g.pitch - s0) * (int)sizeof(double));
+    pf_last = min(je, c.jmax);
+#pragma unroll
+    for (int k = 0; k < NPW; ++k) {
+      const int pl = min(warp + k * MARCH_WARPS, NPF - 1);
+      const double* b = (pl < 4) ? A.in + (size_t)pl * g.plane
+                      : (pl < 6) ? A.eqz + (size_t)(pl - 4) * g.plane : A.base + (size_t)(pl - 6) * g.plane;
+      pf[k] = (const char*)(b + s0) + (size_t)(jb + A.pf_rows + 1) * pitchB;
+    }
+  }
+  auto prefetch_row = [&](int jj) {                        // jj = local row to prefetch; all operands warp-uniform
+    if (jj <= pf_last) {
+#pragma unroll
+      for (int k = 0; k < NPW; ++k)
+        if (warp + k * MARCH_WARPS < NPF) l2_prefetch_bulk(pf[k], pf_bytes);
+    }
+#pragma unroll
+    for (int k = 0; k < NPW; ++k) pf[k] += pitchB;
+  };
   double spd = 0.0;
   int j = jb;
   for (; j + 1 < je; j += 2) {           // two rows per trip: (ca,Ga)->(cb,Gb2)->(ca,Ga), no register rotation
+    prefetch_row(j + A.pf_rows);
     march_row<MODE>(A, g, P, c, j, ca, cb, nraw, hraw, Ga, Gb2, spd);
+    prefetch_row(j + 1 + A.pf_rows);
     march_row<MODE>(A, g, P, c, j + 1, cb, ca, nraw, hraw, Gb2, Ga, spd);
   }
   if (j < je) march_row<MODE>(A, g, P, c, j, ca, cb, nraw, hraw, Ga, Gb2, spd);
@@ -559,6 +601,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs 
 
 
 }}  // namespace wb::fv2d
+
+#include "fv2d_tma.cuh"
 
 // ============================================================================================ host side
 using namespace wb;
@@ -583,6 +627,9 @@ struct wb_fv2d {
   cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
   int overlap = 1;
   int march_rows = 32;          // rows per strip of the marching kernel
+  int pf_rows = 4;              // L2 prefetch distance of the LDG marching kernel (rows ahead; 0 = off)
+  bool tma_ok = false;          // tensor maps built: the TMA-fed stage kernel is used
+  CUtensorMap map_u, map_w1, map_eq;
 };
 
 namespace {
@@ -662,6 +709,31 @@ int prepare_eq(wb_fv2d* h) {
 
 bool use_fast(const wb_fv2d* h) { return h->prm.arith == 0 && h->fast_ok; }
 
+// 3-D tensor map (column, row incl. ghosts, plane) of an SoA field for the TMA-fed stage kernel.  The driver entry
+// point is fetched through the runtime, so the library keeps no link-time dependency on libcuda.
+int make_field_map(const wb_fv2d* h, const double* base, int nplanes, CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    WB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return WB_ERR_CUDA; }
+    encode = (encode_fn)fn;
+  }
+  const Grid& g = h->g;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)(g.nyl + 2), (cuuint64_t)nplanes};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)TMA_BOXW, 1u, (cuuint32_t)nplanes};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return WB_ERR_CUDA; }
+  return WB_OK;
+}
+
 template <int MODE>
 int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, double tend, int max_iter,
                  bool wb_scheme = true, int row_begin = 0, int row_end = -1, cudaStream_t stream = nullptr) {
@@ -673,11 +745,25 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
   A.row_begin = row_begin; A.row_end = row_end;
+  A.pf_rows = h->pf_rows;
   if (use_fast(h) && wb_scheme) {
     const int R = h->march_rows;
     const int ncols = (h->g.nx + MARCH_OUT - 1) / MARCH_OUT;
     dim3 b(MARCH_WARPS * 32), gr((ncols + MARCH_WARPS - 1) / MARCH_WARPS, (A.row_end - A.row_begin + R - 1) / R);
-    k_stage_march<MODE, MARCH_MIN_BLOCKS><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
+    const CUtensorMap* m_in = (in == h->u) ? &h->map_u : (in == h->w1) ? &h->map_w1 : nullptr;
+    const CUtensorMap* m_base = (base == h->u) ? &h->map_u : (base == h->w1) ? &h->map_w1 : nullptr;
+    if (h->tma_ok && m_in && (MODE != 2 || m_base)) {
+      static bool configured = false;
+      auto kern = k_stage_tma<MODE, MARCH_MIN_BLOCKS>;
+      if (!configured) {       // 4 CTAs x <= 46.5 KiB of ring buffers per SM
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_WARPS * tma_warp_bytes(MODE)));
+        configured = true;
+      }
+      kern<<<gr, b, MARCH_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, h->map_eq, m_base ? *m_base : *m_in, A, h->g, h->phys, R);
+    } else {
+      k_stage_march<MODE, MARCH_MIN_BLOCKS><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
+    }
   } else {
     dim3 b(128), gr((h->g.nx + 127) / 128, row_end - row_begin);
     if (wb_scheme) k_stage_ref<MODE, true><<<gr, b, 0, stream>>>(A, h->g, h->phys);
@@ -751,6 +837,7 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   h->dev = dev;
   if (const char* e = getenv("WB_FV2D_OVERLAP")) h->overlap = atoi(e);
   if (const char* e = getenv("WB_FV2D_MARCH_ROWS")) h->march_rows = std::max(1, atoi(e));
+  if (const char* e = getenv("WB_FV2D_PF_ROWS")) h->pf_rows = std::max(0, atoi(e));
   fill_phys(*p, h->phys);
   Grid& g = h->g;
   g.nx = p->nx; g.ny = p->ny;
@@ -801,6 +888,17 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
     h->exf = h->tab; h->exc = h->tab + nxf; h->eyf = h->tab + nxf + nxc; h->eyc = h->tab + nxf + nxc + nyf;
   }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
+  // tensor maps for the TMA-fed stage kernel (the box is 34 columns wide; narrower grids use the LDG march)
+  {
+    const char* env = getenv("WB_FV2D_TMA");
+    if (p->arith == 0 && g.nx >= TMA_BOXW && !(env && atoi(env) == 0)) {
+      int st = make_field_map(h, h->u, 4, &h->map_u);
+      if (st == WB_OK) st = make_field_map(h, h->w1, 4, &h->map_w1);
+      if (st == WB_OK) st = make_field_map(h, h->eqz, 2, &h->map_eq);
+      if (st != WB_OK) return fail(st);
+      h->tma_ok = true;
+    }
+  }
   *out = h;
   return WB_OK;
 }

@@ -1,0 +1,238 @@
+// TMA-fed variant of the fused 2D FV RK-stage kernel (production path on sm_100a).
+//
+// Same march as k_stage_march (a warp owns 31 output columns and walks up a strip of rows; every face flux is
+// evaluated once; identical arithmetic, hence bit-identical results), but the rows no longer travel through
+// per-lane global loads and register prefetch buffers:
+//   * lane 0 of every warp issues ONE 3-D TMA tensor load per input array and row
+//     (box = 34 columns x 1 row x all planes, covering the warp's 32 columns plus the left halo) into a per-warp ring of shared-memory row slots, completion signalled on one mbarrier per slot;
+//   * the box may start anywhere whose BYTE offset is a multiple of 16 (measured on B200: an odd FP64 column
+//     coordinate raises "illegal instruction"; negative even ones are fine), so it starts at the even column
+//     x0 <= c0-1, and out-of-range columns (< 0, >= nx) are zero-filled by the hardware: no per-lane address
+//     arithmetic, no index clamping and no lane-0 halo load;
+//   * all lanes read their own column (row j+1) and their left neighbour (row j) from the slot with LDS;
+//     the left-neighbour shuffle and its lane-0 select disappear;
+//   * a slot is re-armed for row p+DEPTH as soon as row p is finished: DEPTH-2 rows are always in flight
+//     without holding registers (the LDG version stalled 40 % of its time on the first use of a prefetched row).
+// Warps stay independent: no block barrier anywhere.
+#pragma once
+#include <cuda.h>
+#include <cstdint>
+
+namespace wb { namespace fv2d {
+
+constexpr int TMA_BOXW = 34;                          // box columns (272 B: multiple of 16 B as TMA requires)
+constexpr int TMA_PLANE_B = TMA_BOXW * 8;             // bytes per plane row in a slot
+constexpr int TMA_IN_B = 4 * TMA_PLANE_B;             // 1088: u / w1 / u^n part of a slot (4 planes)
+constexpr int TMA_EQ_B = 2 * TMA_PLANE_B;             // 544:  (rho_e, E_e) part of a slot
+constexpr int TMA_IN_PAD = 1152;                      // parts start on 128-byte boundaries
+constexpr int TMA_SLOT_B = TMA_IN_PAD + 640;          // 1792 = 14 * 128
+constexpr int TMA_DEPTH = 4;                          // state ring: rows p, p+1 in use, p+2, p+3 in flight
+constexpr int TMA_BDEPTH = 4;                         // u^n ring (stage 2): row q in use, q+1..q+3 in flight
+constexpr int TMA_BARS_B = 128;
+__host__ __device__ constexpr int tma_warp_bytes(int mode) {
+  return TMA_DEPTH * TMA_SLOT_B + (mode == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0) + TMA_BARS_B;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+
+struct TmaCtx {
+  int lane, i, jb, np, nrows, jmin, jmax, x0, own;      // x0: first box column (even); own: this lane's column in the box
+  bool writer, col_interior;
+  double exf_i, exc_i, dt;
+  const unsigned char* wsm;     // this warp's shared-memory region (generic pointer)
+  uint32_t ring, bring, bars;   // shared-space addresses: state ring, u^n ring, mbarriers
+};
+
+// lane 0: arm slot p & (DEPTH-1) and ask TMA for local row jb-1+p (clamped like the LDG kernel: ghost rows exist
+// only where a neighbouring slab does)
+template <int MODE>
+__device__ __forceinline__ void tma_issue_row(const TmaCtx& c, const CUtensorMap* m_in, const CUtensorMap* m_eq, int p) {
+  const int s = p & (TMA_DEPTH - 1);
+  const int row = max(c.jmin, min(c.jb - 1 + p, c.jmax)) + 1;
+  const uint32_t bar = c.bars + 8u * s, dst = c.ring + (uint32_t)(s * TMA_SLOT_B);
+  mbar_expect_tx(bar, TMA_IN_B + TMA_EQ_B);
+  tma_load_3d(dst, m_in, c.x0, row, 0, bar);
+  tma_load_3d(dst + TMA_IN_PAD, m_eq, c.x0, row, 0, bar);
+}
+__device__ __forceinline__ void tma_issue_base(const TmaCtx& c, const CUtensorMap* m_base, int q) {
+  const int s = q & (TMA_BDEPTH - 1);
+  const uint32_t bar = c.bars + 8u * (TMA_DEPTH + s), dst = c.bring + (uint32_t)(s * TMA_IN_PAD);
+  mbar_expect_tx(bar, TMA_IN_B);
+  tma_load_3d(dst, m_base, c.x0, c.jb + q + 1, 0, bar);
+}
+// box column `col` (c.own = this lane's cell, c.own - 1 = its left neighbour) of ring row p
+__device__ __forceinline__ Raw tma_read_row(const TmaCtx& c, int p, int col) {
+  const unsigned char* sp = c.wsm + (p & (TMA_DEPTH - 1)) * TMA_SLOT_B + col * 8;
+  Raw r;
+  r.u0 = *reinterpret_cast<const double*>(sp);
+  r.u1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
+  r.u2 = *reinterpret_cast<const double*>(sp + 2 * TMA_PLANE_B);
+  r.u3 = *reinterpret_cast<const double*>(sp + 3 * TMA_PLANE_B);
+  r.re = *reinterpret_cast<const double*>(sp + TMA_IN_PAD);
+  r.Ee = *reinterpret_cast<const double*>(sp + TMA_IN_PAD + TMA_PLANE_B);
+  return r;
+}
+
+// One row (strip-relative index q, ring row p = q+1, local row j = jb+q).  (cur,Gb) in, (nxt,Gt) out as in march_row.
+template <int MODE>
+__device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c,
+                                        const CUtensorMap* m_in, const CUtensorMap* m_eq, const CUtensorMap* m_base, int q,
+                                        const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& tyf, double& tyc,
+                                        double& spd) {
+  const int p = q + 1, j = c.jb + q;
+  // ---- y tables of this row were loaded one row ago; fetch the next row's now
+  const double ey = c.exc_i * tyf, ex = c.exf_i * tyc;
+  tyf = A.eyf[min(j + 2, g.nyl)];
+  tyc = A.eyc[min(j + 1, g.nyl - 1)];
+  // ---- row j+1 (own column) must have landed; row j (left neighbour) landed a row ago
+  mbar_wait(c.bars + 8u * ((p + 1) & (TMA_DEPTH - 1)), ((p + 1) / TMA_DEPTH) & 1);
+  nxt = make_cell(tma_read_row(c, p + 1, c.own));
+  const Cell lft = make_cell(tma_read_row(c, p, c.own - 1));
+  double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  if (MODE == 2) {
+    mbar_wait(c.bars + 8u * (TMA_DEPTH + (q & (TMA_BDEPTH - 1))), (q / TMA_BDEPTH) & 1);
+    const unsigned char* sp = c.wsm + TMA_DEPTH * TMA_SLOT_B + (q & (TMA_BDEPTH - 1)) * TMA_IN_PAD + c.own * 8;
+    b0 = *reinterpret_cast<const double*>(sp);
+    b1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
+    b2 = *reinterpret_cast<const double*>(sp + 2 * TMA_PLANE_B);
+    b3 = *reinterpret_cast<const double*>(sp + 3 * TMA_PLANE_B);
+  }
+  // ---- top y-face (j+1; normal = y) and left x-face (i; normal = x): four states in lock-step
+  FaceFlux Fl;
+  {
+    const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3};
+    const FaceIn fx = {P.rho0 * ex, P.pe1 * ex, lft.d0, lft.d1, lft.d2, lft.d3, cur.d0, cur.d1, cur.d2, cur.d3};
+    faces_llf2(P, fy, fx, Gt, Fl);
+  }
+  // ---- right x-face (i+1) from lane+1
+  FaceFlux Fr;
+  Fr.f0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1); Fr.fn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
+  Fr.ft = __shfl_down_sync(0xffffffffu, Fl.ft, 1); Fr.f3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
+  Fr.pf = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
+  // ---- ring row p is dead now (every lane's values went into Fl, which all lanes have just exchanged): re-arm it
+  if (c.lane == 0 && p + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, m_eq, p + TMA_DEPTH);
+  // ---- dudt in the reference's order (benchmark_2d.f90:601-607), RK axpy
+  const int jg = g.j0 + j;
+  const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
+  double n0, n1, n2, n3;
+  cell_update<MODE>(P, cur, Fl, Fr, Gb, Gt, interior, c.dt, b0, b1, b2, b3, n0, n1, n2, n3);
+  if (c.writer) {
+    const size_t o = (size_t)(j + 1) * g.pitch + c.i;
+    A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
+    if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
+  }
+  if (MODE == 2) {                       // u^n of this row has been used by every lane: re-arm its slot
+    __syncwarp();
+    if (c.lane == 0 && q + TMA_BDEPTH < c.nrows) tma_issue_base(c, m_base, q + TMA_BDEPTH);
+  }
+}
+
+template <int MODE, int MB>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, MB)
+k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CUtensorMap m_eq,
+            const __grid_constant__ CUtensorMap m_base, StageArgs A, Grid g, Phys P, int R) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  TmaCtx c;
+  c.dt = 0.0;
+  if (MODE != 0) {
+    if (step_done(A.ctrl, A.parity, A.tend, A.max_iter)) {
+      if (MODE == 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+        carry_forward(A.ctrl, A.parity);
+      return;
+    }
+    c.dt = step_dt(A.ctrl, A.parity, P);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && A.row_begin == 0)
+      bookkeeping<MODE>(A.ctrl, A.parity, c.dt);
+  }
+  c.lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler
+  const int c0 = (blockIdx.x * MARCH_WARPS + warp) * MARCH_OUT;
+  if (c0 >= g.nx) return;                                 // whole warp: no block barriers in this kernel
+  c.jb = A.row_begin + blockIdx.y * R;
+  const int je = min(c.jb + R, A.row_end);
+  if (c.jb >= je) return;
+  c.nrows = je - c.jb;
+  c.np = c.nrows + 2;                                       // ring rows p = 0..np-1  <->  local rows jb-1 .. je
+  c.i = c0 + c.lane;
+  c.x0 = (c0 - 1) & ~1;                                     // even: 16-byte aligned box start (also for c0 = 0: -2)
+  c.own = c.i - c.x0;
+  c.jmin = (g.j0 > 0) ? -1 : 0;
+  c.jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
+  const int ic = min(c.i, g.nx - 1);
+  c.exf_i = A.exf[ic];
+  c.exc_i = A.exc[ic];
+  c.writer = (c.lane < MARCH_OUT) && (c.i < g.nx);
+  c.col_interior = (c.i > 0) && (c.i < g.nx - 1);
+  c.wsm = tma_smem + warp * tma_warp_bytes(MODE);
+  c.ring = smem_u32(c.wsm);
+  c.bring = c.ring + TMA_DEPTH * TMA_SLOT_B;
+  c.bars = c.bring + (MODE == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0);
+
+  // ---- barriers, then the first DEPTH rows
+  if (c.lane == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_DEPTH + (MODE == 2 ? TMA_BDEPTH : 0); ++s) mbar_init(c.bars + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int p = 0; p < TMA_DEPTH; ++p)
+      if (p < c.np) tma_issue_row<MODE>(c, &m_in, &m_eq, p);
+    if (MODE == 2) {
+#pragma unroll
+      for (int q = 0; q < TMA_BDEPTH; ++q)
+        if (q < c.nrows) tma_issue_base(c, &m_base, q);
+    }
+  }
+  __syncwarp();
+  double tyf = A.eyf[min(c.jb + 1, g.nyl)], tyc = A.eyc[min(c.jb, g.nyl - 1)];
+
+  // ---- prologue: bottom face of the strip from rows jb-1 (p = 0) and jb (p = 1)
+  Cell ca, cb;
+  FaceFlux Ga, Gb2;
+  {
+    mbar_wait(c.bars, 0);
+    const Cell bel = make_cell(tma_read_row(c, 0, c.own));
+    mbar_wait(c.bars + 8u, 0);
+    ca = make_cell(tma_read_row(c, 1, c.own));
+    const double e = c.exc_i * A.eyf[c.jb];
+    Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
+    // slot 0 is dead: re-arm it for ring row DEPTH
+    if (c.lane == 0 && TMA_DEPTH < c.np) tma_issue_row<MODE>(c, &m_in, &m_eq, TMA_DEPTH);
+  }
+  double spd = 0.0;
+  int q = 0;
+  for (; q + 1 < c.nrows; q += 2) {      // two rows per trip: (ca,Ga)->(cb,Gb2)->(ca,Ga), no register rotation
+    tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
+    tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q + 1, cb, ca, Gb2, Ga, tyf, tyc, spd);
+  }
+  if (q < c.nrows) tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
+  if (MODE == 2) {
+    spd = warp_max(spd);
+    if (c.lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);
+  }
+}
+
+}}  // namespace wb::fv2d

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwbeuler.so")
+LIB_PATH = os.environ.get("WBEULER_LIB") or os.path.join(_HERE, "libwbeuler.so")   # override: A/B builds in development
 
 _lib = None
 _dp = C.POINTER(C.c_double)
