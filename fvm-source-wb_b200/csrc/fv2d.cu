@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(128) k_stage_ref(StageArgs A, Grid g, Phys P) 
 
 // ------------------------------------------------------------------------------------ fused stage: face flux helpers
 // One LLF face in (normal,tangential) form.  lo/hi = delta on the low/high side of the face,
-// (rf,Ef) = conservative equilibrium at the face.  Returns flux (mass, normal mom, tangential mom, energy)
-// and pf = gm1*Ef.
+// (rf,Ef) = conservative equilibrium at the face.  Returns TWICE the flux (mass, normal mom, tangential mom, energy)
+// and pf = 2*gm1*Ef = twice the equilibrium pressure flux (same instruction sequence as fn at delta = 0).
 struct FaceFlux { double f0, fn, ft, f3, pf; };
 __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef, double lr, double ln,
                                              double lt, double lE, double hr, double hn, double ht,
@@ -348,15 +348,15 @@ __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef
   double br = rf + hr, bE = Ef + hE;   // high side ("u_left(i)"   / "u_bottom(j)")
   fast::Eval a = fast::eval_state(P, ar, ln, lt, aE);
   fast::Eval b = fast::eval_state(P, br, hn, ht, bE);
-  double hc = 0.5 * fmax(a.spd, b.spd);
+  const double cm = fmax(a.spd, b.spd);
   FaceFlux o;
-  // 0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)   (benchmark_2d.f90:366)
-  // (kept unfused: a fused multiply-add here flips the last bit of an O(1) flux once in ~1e5 faces)
-  o.f0 = 0.5 * (b.f0 + a.f0) + hc * (ar - br);
-  o.fn = 0.5 * (b.fn + a.fn) + hc * (ln - hn);
-  o.ft = 0.5 * (b.ft + a.ft) + hc * (lt - ht);
-  o.f3 = 0.5 * (b.f3 + a.f3) + hc * (aE - bE);
-  o.pf = P.gm1 * Ef;
+  // 2 x [0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)]   (benchmark_2d.f90:366): the two halvings are exact, so they
+  // are folded into 0.5/dx (Phys::hodx, hody); the remaining a*b+c is one fma (<= 1 ulp of an O(1) flux)
+  o.f0 = fma(cm, ar - br, b.f0 + a.f0);
+  o.fn = fma(cm, ln - hn, b.fn + a.fn);
+  o.ft = fma(cm, lt - ht, b.ft + a.ft);
+  o.f3 = fma(cm, aE - bE, b.f3 + a.f3);
+  o.pf = P.gm1x2 * Ef;
   return o;
 }
 
@@ -369,17 +369,17 @@ __device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const
   const double mt[4] = {a.lt, a.ht, b.lt, b.ht};
   fast::Eval ev[4];
   fast::eval_states<4>(P, rho, mn, mt, E, ev);
-  const double hca = 0.5 * fmax(ev[0].spd, ev[1].spd), hcb = 0.5 * fmax(ev[2].spd, ev[3].spd);
-  oa.f0 = 0.5 * (ev[1].f0 + ev[0].f0) + hca * (rho[0] - rho[1]);
-  ob.f0 = 0.5 * (ev[3].f0 + ev[2].f0) + hcb * (rho[2] - rho[3]);
-  oa.fn = 0.5 * (ev[1].fn + ev[0].fn) + hca * (a.ln - a.hn);
-  ob.fn = 0.5 * (ev[3].fn + ev[2].fn) + hcb * (b.ln - b.hn);
-  oa.ft = 0.5 * (ev[1].ft + ev[0].ft) + hca * (a.lt - a.ht);
-  ob.ft = 0.5 * (ev[3].ft + ev[2].ft) + hcb * (b.lt - b.ht);
-  oa.f3 = 0.5 * (ev[1].f3 + ev[0].f3) + hca * (E[0] - E[1]);
-  ob.f3 = 0.5 * (ev[3].f3 + ev[2].f3) + hcb * (E[2] - E[3]);
-  oa.pf = P.gm1 * a.Ef;
-  ob.pf = P.gm1 * b.Ef;
+  const double cma = fmax(ev[0].spd, ev[1].spd), cmb = fmax(ev[2].spd, ev[3].spd);
+  oa.f0 = fma(cma, rho[0] - rho[1], ev[1].f0 + ev[0].f0);
+  ob.f0 = fma(cmb, rho[2] - rho[3], ev[3].f0 + ev[2].f0);
+  oa.fn = fma(cma, a.ln - a.hn, ev[1].fn + ev[0].fn);
+  ob.fn = fma(cmb, b.ln - b.hn, ev[3].fn + ev[2].fn);
+  oa.ft = fma(cma, a.lt - a.ht, ev[1].ft + ev[0].ft);
+  ob.ft = fma(cmb, b.lt - b.ht, ev[3].ft + ev[2].ft);
+  oa.f3 = fma(cma, E[0] - E[1], ev[1].f3 + ev[0].f3);
+  ob.f3 = fma(cmb, E[2] - E[3], ev[3].f3 + ev[2].f3);
+  oa.pf = P.gm1x2 * a.Ef;
+  ob.pf = P.gm1x2 * b.Ef;
 }
 
 // ------------------------------------------------------------------------------------ fused marching stage
@@ -420,15 +420,18 @@ template <int MODE>
 __device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const FaceFlux& Fl, const FaceFlux& Fr, const FaceFlux& Gb,
                                             const FaceFlux& Gt, bool interior, double dt, double b0, double b1, double b2,
                                             double b3, double& n0, double& n1, double& n2, double& n3) {
-  double d0 = -((Fr.f0 - Fl.f0) * P.odx) - (Gt.f0 - Gb.f0) * P.ody;
-  double d1 = -((Fr.fn - Fl.fn) * P.odx) - (Gt.ft - Gb.ft) * P.ody;
-  double d2 = -((Fr.ft - Fl.ft) * P.odx) - (Gt.fn - Gb.fn) * P.ody;
-  double d3 = -((Fr.f3 - Fl.f3) * P.odx) - (Gt.f3 - Gb.f3) * P.ody;
+  // the face fluxes and pf arrive doubled: hodx = 0.5/dx, hody = 0.5/dy (exact scalings).  The x difference is
+  // rounded as in the reference, the y difference joins it in one fma; at the hydrostatic state one of the two
+  // vanishes identically and the other is cancelled bit for bit by the pf term below.
+  double d0 = fma(Gb.f0 - Gt.f0, P.hody, -((Fr.f0 - Fl.f0) * P.hodx));
+  double d1 = fma(Gb.ft - Gt.ft, P.hody, -((Fr.fn - Fl.fn) * P.hodx));
+  double d2 = fma(Gb.fn - Gt.fn, P.hody, -((Fr.ft - Fl.ft) * P.hodx));
+  double d3 = fma(Gb.f3 - Gt.f3, P.hody, -((Fr.f3 - Fl.f3) * P.hodx));
   d1 = (d1 - c.u0) + c.re;
   d2 = (d2 - c.u0) + c.re;
   d3 = d3 - (c.d1 + c.d2);
-  d1 = d1 + (Fr.pf - Fl.pf) * P.odx;
-  d2 = d2 + (Gt.pf - Gb.pf) * P.ody;
+  d1 = d1 + (Fr.pf - Fl.pf) * P.hodx;
+  d2 = d2 + (Gt.pf - Gb.pf) * P.hody;
   if (MODE == 0) {
     if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }
     n0 = d0; n1 = d1; n2 = d2; n3 = d3;
@@ -641,6 +644,8 @@ int fill_phys(const wb_fv2d_params& p, Phys& P) {
   P.dy = p.boxlen_y / (double)p.ny;
   P.odx = 1 / P.dx;
   P.ody = 1 / P.dy;
+  P.hodx = 0.5 * P.odx;
+  P.hody = 0.5 * P.ody;
   P.cfl = p.cfl;
   P.neq = p.nequilibrium;
   if (p.nequilibrium == 1) { P.rho0 = 1.0; P.p0 = 1.0; P.a = 1.0; }
@@ -648,6 +653,7 @@ int fill_phys(const wb_fv2d_params& p, Phys& P) {
     P.rho0 = (double)1.21f; P.p0 = 1.0; P.a = P.rho0 * 1.0 / 1.0;
   } else { P.rho0 = 0.0; P.p0 = 0.0; P.a = 0.0; }
   P.pe1 = P.p0 / P.gm1;
+  P.gm1x2 = 2.0 * P.gm1;
   return WB_OK;
 }
 

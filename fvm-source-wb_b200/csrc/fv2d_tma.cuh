@@ -27,7 +27,10 @@ constexpr int TMA_EQ_B = 2 * TMA_PLANE_B;             // 544:  (rho_e, E_e) part
 constexpr int TMA_IN_PAD = 1152;                      // parts start on 128-byte boundaries
 constexpr int TMA_SLOT_B = TMA_IN_PAD + 640;          // 1792 = 14 * 128
 constexpr int TMA_DEPTH = 4;                          // state ring: rows p, p+1 in use, p+2, p+3 in flight
-constexpr int TMA_BDEPTH = 4;                         // u^n ring (stage 2): row q in use, q+1..q+3 in flight
+#ifndef TMA_BDEPTH_N
+#define TMA_BDEPTH_N 4
+#endif
+constexpr int TMA_BDEPTH = TMA_BDEPTH_N;             // u^n ring (stage 2): row q in use, the others in flight
 constexpr int TMA_BARS_B = 128;
 __host__ __device__ constexpr int tma_warp_bytes(int mode) {
   return TMA_DEPTH * TMA_SLOT_B + (mode == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0) + TMA_BARS_B;
