@@ -338,8 +338,10 @@ __global__ void __launch_bounds__(128) k_stage_ref(StageArgs A, Grid g, Phys P) 
 // ------------------------------------------------------------------------------------ fused stage: face flux helpers
 // One LLF face in (normal,tangential) form.  lo/hi = delta on the low/high side of the face,
 // (rf,Ef) = conservative equilibrium at the face.  Returns TWICE the flux (mass, normal mom, tangential mom, energy)
-// and pf = 2*gm1*Ef = twice the equilibrium pressure flux (same instruction sequence as fn at delta = 0).
-struct FaceFlux { double f0, fn, ft, f3, pf; };
+// MINUS twice the equilibrium flux of the face, whose only non-zero entry is the pressure 2*gm1*Ef in the normal
+// momentum: at delta = 0 both sides carry p = gm1*Ef from the same instruction sequence, so fn is exactly zero there
+// and the "+ (F_eq(i+1)-F_eq(i))/dx" terms of benchmark_2d.f90:605-606 need no separate evaluation.
+struct FaceFlux { double f0, fn, ft, f3; };
 __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef, double lr, double ln,
                                              double lt, double lE, double hr, double hn, double ht,
                                              double hE) {
@@ -353,33 +355,31 @@ __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef
   // 2 x [0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)]   (benchmark_2d.f90:366): the two halvings are exact, so they
   // are folded into 0.5/dx (Phys::hodx, hody); the remaining a*b+c is one fma (<= 1 ulp of an O(1) flux)
   o.f0 = fma(cm, ar - br, b.f0 + a.f0);
-  o.fn = fma(cm, ln - hn, b.fn + a.fn);
+  o.fn = fma(cm, ln - hn, (b.fn + a.fn) - P.gm1x2 * Ef);
   o.ft = fma(cm, lt - ht, b.ft + a.ft);
   o.f3 = fma(cm, aE - bE, b.f3 + a.f3);
-  o.pf = P.gm1x2 * Ef;
   return o;
 }
 
 // Two LLF faces at once: the four states are evaluated in lock-step (eval_states<4>); same arithmetic as face_llf.
 struct FaceIn { double rf, Ef, lr, ln, lt, lE, hr, hn, ht, hE; };
-__device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const FaceIn& b, FaceFlux& oa, FaceFlux& ob) {
+template <bool EXACT>
+__device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const FaceIn& b, FaceFlux& oa, FaceFlux& ob, bool& ok) {
   const double rho[4] = {a.rf + a.lr, a.rf + a.hr, b.rf + b.lr, b.rf + b.hr};
   const double E[4] = {a.Ef + a.lE, a.Ef + a.hE, b.Ef + b.lE, b.Ef + b.hE};
   const double mn[4] = {a.ln, a.hn, b.ln, b.hn};
   const double mt[4] = {a.lt, a.ht, b.lt, b.ht};
   fast::Eval ev[4];
-  fast::eval_states<4>(P, rho, mn, mt, E, ev);
+  fast::eval_states<4, EXACT>(P, rho, mn, mt, E, ev, ok);
   const double cma = fmax(ev[0].spd, ev[1].spd), cmb = fmax(ev[2].spd, ev[3].spd);
   oa.f0 = fma(cma, rho[0] - rho[1], ev[1].f0 + ev[0].f0);
   ob.f0 = fma(cmb, rho[2] - rho[3], ev[3].f0 + ev[2].f0);
-  oa.fn = fma(cma, a.ln - a.hn, ev[1].fn + ev[0].fn);
-  ob.fn = fma(cmb, b.ln - b.hn, ev[3].fn + ev[2].fn);
+  oa.fn = fma(cma, a.ln - a.hn, (ev[1].fn + ev[0].fn) - P.gm1x2 * a.Ef);
+  ob.fn = fma(cmb, b.ln - b.hn, (ev[3].fn + ev[2].fn) - P.gm1x2 * b.Ef);
   oa.ft = fma(cma, a.lt - a.ht, ev[1].ft + ev[0].ft);
   ob.ft = fma(cmb, b.lt - b.ht, ev[3].ft + ev[2].ft);
   oa.f3 = fma(cma, E[0] - E[1], ev[1].f3 + ev[0].f3);
   ob.f3 = fma(cmb, E[2] - E[3], ev[3].f3 + ev[2].f3);
-  oa.pf = P.gm1x2 * a.Ef;
-  ob.pf = P.gm1x2 * b.Ef;
 }
 
 // ------------------------------------------------------------------------------------ fused marching stage
@@ -420,9 +420,8 @@ template <int MODE>
 __device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const FaceFlux& Fl, const FaceFlux& Fr, const FaceFlux& Gb,
                                             const FaceFlux& Gt, bool interior, double dt, double b0, double b1, double b2,
                                             double b3, double& n0, double& n1, double& n2, double& n3) {
-  // the face fluxes and pf arrive doubled: hodx = 0.5/dx, hody = 0.5/dy (exact scalings).  The x difference is
-  // rounded as in the reference, the y difference joins it in one fma; at the hydrostatic state one of the two
-  // vanishes identically and the other is cancelled bit for bit by the pf term below.
+  // the face fluxes arrive doubled and relative to the equilibrium flux: hodx = 0.5/dx, hody = 0.5/dy (exact
+  // scalings); every term below vanishes identically at the hydrostatic state.
   double d0 = fma(Gb.f0 - Gt.f0, P.hody, -((Fr.f0 - Fl.f0) * P.hodx));
   double d1 = fma(Gb.ft - Gt.ft, P.hody, -((Fr.fn - Fl.fn) * P.hodx));
   double d2 = fma(Gb.fn - Gt.fn, P.hody, -((Fr.ft - Fl.ft) * P.hodx));
@@ -430,8 +429,6 @@ __device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const 
   d1 = (d1 - c.u0) + c.re;
   d2 = (d2 - c.u0) + c.re;
   d3 = d3 - (c.d1 + c.d2);
-  d1 = d1 + (Fr.pf - Fl.pf) * P.hodx;
-  d2 = d2 + (Gt.pf - Gb.pf) * P.hody;
   if (MODE == 0) {
     if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }
     n0 = d0; n1 = d1; n2 = d2; n3 = d3;
@@ -491,18 +488,18 @@ __device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, con
   {
     const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3};
     const FaceIn fx = {P.rho0 * ex, P.pe1 * ex, l0, l1, l2, l3, cur.d0, cur.d1, cur.d2, cur.d3};
-    faces_llf2(P, fy, fx, Gt, Fl);
+    bool ok = true;
+    faces_llf2<true>(P, fy, fx, Gt, Fl, ok);
   }
   // ---- right x-face (i+1) from lane+1
   const double r0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1), rn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
   const double rt = __shfl_down_sync(0xffffffffu, Fl.ft, 1), r3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
-  const double rp = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
 
   // ---- dudt in the reference's order (benchmark_2d.f90:601-607), RK axpy
   const int jg = g.j0 + j;
   const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
   FaceFlux Fr;
-  Fr.f0 = r0; Fr.fn = rn; Fr.ft = rt; Fr.f3 = r3; Fr.pf = rp;
+  Fr.f0 = r0; Fr.fn = rn; Fr.ft = rt; Fr.f3 = r3;
   double n0, n1, n2, n3;
   cell_update<MODE>(P, cur, Fl, Fr, Gb, Gt, interior, c.dt, b0, b1, b2, b3, n0, n1, n2, n3);
   if (c.writer) {

@@ -137,12 +137,14 @@ __device__ __forceinline__ Eval eval_state(const Phys& P, double rho, double mn,
   return o;
 }
 // The same evaluation for N independent states in lock-step: every sub-step is issued for all N states before the
-// next one, so the instruction stream carries N independent dependency chains (the kernel is bound by FP64 latency,
-// not by FP64 throughput, when the chains are evaluated one after the other).  Bit-identical to eval_state.
-// Must be called by all 32 lanes of the warp (one vote inside).
-template <int N>
+// next one, so the instruction stream carries N independent dependency chains.  Bit-identical to eval_state.
+// EXACT = false leaves the floors max(p,1d-10), max(rho,1d-10) out and clears `ok` when any state is close enough to a
+// floor for them to matter (tested on the integer pipe: sign and exponent live in the high word, hi >= hi(1e-10)+1
+// implies value > 1e-10); the caller then re-evaluates with EXACT = true.  Physical states never get there, and the
+// kernel is bound by issue slots (an FP64 instruction takes two), so the floors cost ~5 % if evaluated always.
+template <int N, bool EXACT>
 __device__ __forceinline__ void eval_states(const Phys& P, const double (&rho)[N], const double (&mn)[N], const double (&mt)[N],
-                                            const double (&E)[N], Eval (&o)[N]) {
+                                            const double (&E)[N], Eval (&o)[N], bool& ok) {
   double r[N], y[N], e[N], t[N], vn[N], vt[N], q[N], p[N], c2[N], cs[N], vm[N], h[N], w[N], qa[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(rho[k]));
@@ -158,28 +160,23 @@ __device__ __forceinline__ void eval_states(const Phys& P, const double (&rho)[N
   for (int k = 0; k < N; ++k) q[k] = fma(vt[k], vt[k], vn[k] * vn[k]);
 #pragma unroll
   for (int k = 0; k < N; ++k) p[k] = P.gm1 * fma(-0.5 * rho[k], q[k], E[k]);
-  // floors max(p,1d-10), max(rho,1d-10): never active for physical states, so they are tested on the integer pipe
-  // (sign and exponent live in the high word: hi >= hi(1e-10)+1 implies value > 1e-10) with one warp vote; a warp
-  // in which any state comes close to the floor takes the exact FP64 path.
-  {
-    constexpr int HI_OK = 0x3DDB7CDF + 1;      // high word of 1e-10 is 0x3DDB7CDF
-    bool ok = true;
+  if (EXACT) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) ok = ok && (__double2hiint(p[k]) >= HI_OK) && (__double2hiint(rho[k]) >= HI_OK);
-    if (__all_sync(0xffffffffu, ok)) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) c2[k] = (P.gamma * p[k]) * r[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double pm = fmax(p[k], 1e-10);
-        const double rm = (rho[k] >= 1e-10) ? r[k] : 1e10;
-        c2[k] = (P.gamma * pm) * rm;
-      }
+    for (int k = 0; k < N; ++k) {
+      const double pm = fmax(p[k], 1e-10);
+      const double rm = (rho[k] >= 1e-10) ? r[k] : 1e10;
+      c2[k] = (P.gamma * pm) * rm;
     }
+  } else {
+    constexpr int HI_OK = 0x3DDB7CDF + 1;      // high word of 1e-10 is 0x3DDB7CDF
 #pragma unroll
-    for (int k = 0; k < N; ++k) qa[k] = q[k] + 1e-300;
+    for (int k = 0; k < N; ++k) {
+      ok = ok && (__double2hiint(p[k]) >= HI_OK) && (__double2hiint(rho[k]) >= HI_OK);
+      c2[k] = (P.gamma * p[k]) * r[k];
+    }
   }
+#pragma unroll
+  for (int k = 0; k < N; ++k) qa[k] = q[k] + 1e-300;
   // two square roots per state, all 2N in lock-step (sqrt_pos)
 #pragma unroll
   for (int k = 0; k < N; ++k) {

@@ -61,6 +61,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void st_if(double* p, double v, bool on) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.global.f64 [%0], %1;\n}" ::"l"(p), "d"(v), "r"((int)on) : "memory");
+}
+
 struct TmaCtx {
   int lane, i, jb, np, nrows, jmin, jmax, x0, own;      // x0: first box column (even); own: this lane's column in the box
   bool writer, col_interior;
@@ -99,24 +103,18 @@ __device__ __forceinline__ Raw tma_read_row(const TmaCtx& c, int p, int col) {
   return r;
 }
 
-// One row (strip-relative index q, ring row p = q+1, local row j = jb+q).  (cur,Gb) in, (nxt,Gt) out as in march_row.
-template <int MODE>
-__device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c,
-                                        const CUtensorMap* m_in, const CUtensorMap* m_eq, const CUtensorMap* m_base, int q,
-                                        const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& tyf, double& tyc,
-                                        double& spd) {
+// Arithmetic of one row (strip-relative index q, ring row p = q+1, local row j = jb+q): reads row j+1 (own column),
+// row j (left neighbour) and u^n of row j from the ring; (cur,Gb) in; nxt, Gt and the new cell values out.
+struct RowOut { Cell nxt; FaceFlux Gt; double n0, n1, n2, n3; };
+template <int MODE, bool EXACT>
+__device__ __forceinline__ RowOut tma_row_math(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c, int q,
+                                               const Cell& cur, const FaceFlux& Gb, double ey, double ex, bool& ok) {
   const int p = q + 1, j = c.jb + q;
-  // ---- y tables of this row were loaded one row ago; fetch the next row's now
-  const double ey = c.exc_i * tyf, ex = c.exf_i * tyc;
-  tyf = A.eyf[min(j + 2, g.nyl)];
-  tyc = A.eyc[min(j + 1, g.nyl - 1)];
-  // ---- row j+1 (own column) must have landed; row j (left neighbour) landed a row ago
-  mbar_wait(c.bars + 8u * ((p + 1) & (TMA_DEPTH - 1)), ((p + 1) / TMA_DEPTH) & 1);
-  nxt = make_cell(tma_read_row(c, p + 1, c.own));
+  RowOut o;
+  o.nxt = make_cell(tma_read_row(c, p + 1, c.own));
   const Cell lft = make_cell(tma_read_row(c, p, c.own - 1));
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (MODE == 2) {
-    mbar_wait(c.bars + 8u * (TMA_DEPTH + (q & (TMA_BDEPTH - 1))), (q / TMA_BDEPTH) & 1);
     const unsigned char* sp = c.wsm + TMA_DEPTH * TMA_SLOT_B + (q & (TMA_BDEPTH - 1)) * TMA_IN_PAD + c.own * 8;
     b0 = *reinterpret_cast<const double*>(sp);
     b1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
@@ -126,30 +124,62 @@ __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const
   // ---- top y-face (j+1; normal = y) and left x-face (i; normal = x): four states in lock-step
   FaceFlux Fl;
   {
-    const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3};
+    const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, o.nxt.d0, o.nxt.d2, o.nxt.d1, o.nxt.d3};
     const FaceIn fx = {P.rho0 * ex, P.pe1 * ex, lft.d0, lft.d1, lft.d2, lft.d3, cur.d0, cur.d1, cur.d2, cur.d3};
-    faces_llf2(P, fy, fx, Gt, Fl);
+    faces_llf2<EXACT>(P, fy, fx, o.Gt, Fl, ok);
   }
   // ---- right x-face (i+1) from lane+1
   FaceFlux Fr;
   Fr.f0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1); Fr.fn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
   Fr.ft = __shfl_down_sync(0xffffffffu, Fl.ft, 1); Fr.f3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
-  Fr.pf = __shfl_down_sync(0xffffffffu, Fl.pf, 1);
-  // ---- ring row p is dead now (every lane's values went into Fl, which all lanes have just exchanged): re-arm it
-  if (c.lane == 0 && p + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, m_eq, p + TMA_DEPTH);
   // ---- dudt in the reference's order (benchmark_2d.f90:601-607), RK axpy
   const int jg = g.j0 + j;
   const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
-  double n0, n1, n2, n3;
-  cell_update<MODE>(P, cur, Fl, Fr, Gb, Gt, interior, c.dt, b0, b1, b2, b3, n0, n1, n2, n3);
-  if (c.writer) {
-    const size_t o = (size_t)(j + 1) * g.pitch + c.i;
-    A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
-    if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
+  cell_update<MODE>(P, cur, Fl, Fr, Gb, o.Gt, interior, c.dt, b0, b1, b2, b3, o.n0, o.n1, o.n2, o.n3);
+  return o;
+}
+// cold path, out of line and with by-value arguments only (taking addresses of the kernel's structs would move them
+// to local memory for the whole kernel): some state of the warp's row sits at a floor of the sound-speed formula
+template <int MODE>
+__device__ __noinline__ RowOut tma_row_exact(StageArgs A, Grid g, Phys P, TmaCtx c, int q, Cell cur, FaceFlux Gb, double ey,
+                                             double ex) {
+  bool ok = true;
+  return tma_row_math<MODE, true>(A, g, P, c, q, cur, Gb, ey, ex, ok);
+}
+
+// One row including the ring bookkeeping and the stores.  (cur,Gb) in, (nxt,Gt) out as in march_row.
+template <int MODE>
+__device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c,
+                                        const CUtensorMap* m_in, const CUtensorMap* m_eq, const CUtensorMap* m_base, int q,
+                                        const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& tyf, double& tyc,
+                                        double& spd) {
+  const int p = q + 1, j = c.jb + q;
+  // ---- the previous row left ring row p-1 and u^n row q-1 dead: re-arm their slots (kept next to the barrier wait
+  //      so that the arithmetic of a row stays one basic block for the instruction scheduler)
+  __syncwarp();
+  if (c.lane == 0) {
+    if (q + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, m_eq, q + TMA_DEPTH);
+    if (MODE == 2 && q >= 1 && q - 1 + TMA_BDEPTH < c.nrows) tma_issue_base(c, m_base, q - 1 + TMA_BDEPTH);
   }
-  if (MODE == 2) {                       // u^n of this row has been used by every lane: re-arm its slot
-    __syncwarp();
-    if (c.lane == 0 && q + TMA_BDEPTH < c.nrows) tma_issue_base(c, m_base, q + TMA_BDEPTH);
+  // ---- y tables of this row were loaded one row ago; fetch the next row's now
+  const double ey = c.exc_i * tyf, ex = c.exf_i * tyc;
+  tyf = A.eyf[min(j + 2, g.nyl)];
+  tyc = A.eyc[min(j + 1, g.nyl - 1)];
+  // ---- row j+1 (own column) must have landed; row j (left neighbour) landed a row ago
+  mbar_wait(c.bars + 8u * ((p + 1) & (TMA_DEPTH - 1)), ((p + 1) / TMA_DEPTH) & 1);
+  if (MODE == 2) mbar_wait(c.bars + 8u * (TMA_DEPTH + (q & (TMA_BDEPTH - 1))), (q / TMA_BDEPTH) & 1);
+  bool ok = true;
+  RowOut o = tma_row_math<MODE, false>(A, g, P, c, q, cur, Gb, ey, ex, ok);
+  if (!__all_sync(0xffffffffu, ok)) o = tma_row_exact<MODE>(A, g, P, c, q, cur, Gb, ey, ex);
+  nxt = o.nxt;
+  Gt = o.Gt;
+  // predicated stores (no branch: lane 31 and the lanes beyond nx simply do not write)
+  double* dst = A.out + ((size_t)(j + 1) * g.pitch + c.i);
+  st_if(dst, o.n0, c.writer); st_if(dst + g.plane, o.n1, c.writer); st_if(dst + 2 * g.plane, o.n2, c.writer);
+  st_if(dst + 3 * g.plane, o.n3, c.writer);
+  if (MODE == 2) {
+    const double s = fast::speed(P, o.n0, o.n1, o.n2, o.n3);
+    spd = c.writer ? fmax(spd, s) : spd;
   }
 }
 
@@ -222,8 +252,6 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
     ca = make_cell(tma_read_row(c, 1, c.own));
     const double e = c.exc_i * A.eyf[c.jb];
     Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
-    // slot 0 is dead: re-arm it for ring row DEPTH
-    if (c.lane == 0 && TMA_DEPTH < c.np) tma_issue_row<MODE>(c, &m_in, &m_eq, TMA_DEPTH);
   }
   double spd = 0.0;
   int q = 0;

@@ -196,3 +196,26 @@ def test_full_size_4096_properties(wb):
     assert rel_linf_fields(fast, ref) <= TOL
     sym = fast.transpose(1, 0, 2)[..., [0, 2, 1, 3]]
     assert rel_linf_fields(sym, fast) <= TOL
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 48), (100, 37)])
+def test_floors_of_the_sound_speed_are_honoured(wb, oracle, nx, ny):
+    """compute_speed (benchmark_2d.f90:283-295) floors p and rho at 1d-10.  The fused kernels evaluate a row without
+    the floors and redo it with them when any state of the warp's row comes near one: put cells with (almost) zero and
+    negative pressure into the Riemann problem and compare RHS and one RK2 step with the oracle."""
+    p, u, weq = setup(oracle, nx, ny, 4)
+    rng = np.random.default_rng(3)
+    u = u.copy()
+    for _ in range(12):
+        j, i = int(rng.integers(2, ny - 2)), int(rng.integers(2, nx - 2))
+        ke = 0.5 * (u[j, i, 1] ** 2 + u[j, i, 2] ** 2) / u[j, i, 0]
+        u[j, i, 3] = ke + rng.choice([0.0, 1e-11, -1e-3, 2e-10]) / (p.gamma - 1.0)      # p = 0, 1e-11, < 0, 2e-10
+    dref = oracle.fv2d_compute_update_exact(p, u, weq)
+    assert np.all(np.isfinite(dref))
+    with wb.FV2D(nx, ny) as s:
+        d = s.compute_update_exact(u, weq)
+        assert rhs_err(oracle, p, u, d, dref) <= TOL
+        got, it, t, dt = s.evolve(u, weq, 1.0, 1)
+    ref, it0, t0, dt0, _ = oracle.fv2d_evolve(p, u, weq, 1.0, 1)
+    assert it == it0 == 1 and abs(dt - dt0) <= 1e-14 * dt0
+    assert rel_linf_fields(got, ref) <= TOL
