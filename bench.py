@@ -295,7 +295,7 @@ def run_ours(args):
                 "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (tr * cells_local_max if tr else None),
-                             "kernel": "k_stage_march<1|2> (one fused RK-stage kernel per launch, 2 per step)",
+                             "kernel": "k_stage_tma<1|2> (one fused, TMA-fed RK-stage kernel per launch, 2 per step)",
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE * cells_local_max,
                              "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
                              "note": "per GPU; achieved = 80 B x cells of the largest slab / mean stage-kernel time "
