@@ -1174,6 +1174,7 @@ int wb_dg2d_compute_max_speed(wb_dg2d* h, const double* mean_mode, double* cs_ma
   WB_CUDA(cudaSetDevice(h->dev));
   h->resident = false;
   // mean mode (nvar,nx,ny) -> planes (v, mode 0) of buffer A
+  WB_CHECK(dg_ensure(h, &h->stage));
   WB_CUDA(cudaMemcpyAsync(h->stage, mean_mode, sizeof(double) * 4 * h->g.ne, cudaMemcpyHostToDevice, h->stream));
   dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), 1);
   k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, h->A, h->g);
