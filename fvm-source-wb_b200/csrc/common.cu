@@ -158,6 +158,21 @@ int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* l
   return WB_OK;
 }
 
+// one contiguous message per side; the order (send lo, send hi, receive hi, receive lo) pairs the messages correctly
+// also when both neighbours are the same rank (periodic ring of two)
+int nccl_ring_exchange(Nccl* c, int lo_peer, int hi_peer, const double* send_lo, const double* send_hi, double* recv_lo,
+                       double* recv_hi, size_t count, cudaStream_t s) {
+  if (lo_peer < 0 && hi_peer < 0) return WB_OK;
+  if (!c) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
+  WB_NCCL(g_nccl.GroupStart());
+  if (lo_peer >= 0) WB_NCCL(g_nccl.Send(send_lo, count, ncclDouble, lo_peer, c->comm, s));
+  if (hi_peer >= 0) WB_NCCL(g_nccl.Send(send_hi, count, ncclDouble, hi_peer, c->comm, s));
+  if (hi_peer >= 0) WB_NCCL(g_nccl.Recv(recv_hi, count, ncclDouble, hi_peer, c->comm, s));
+  if (lo_peer >= 0) WB_NCCL(g_nccl.Recv(recv_lo, count, ncclDouble, lo_peer, c->comm, s));
+  WB_NCCL(g_nccl.GroupEnd());
+  return WB_OK;
+}
+
 int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, double* recv_lo,
                        const double* send_hi, double* recv_hi, size_t count, cudaStream_t s) {
   HaloSeg lo{send_lo, recv_lo, count}, hi{send_hi, recv_hi, count};

@@ -59,6 +59,8 @@ int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, dou
 struct HaloSeg { const double* send; double* recv; size_t count; };
 int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* lo, int nlo,
                              const HaloSeg* hi, int nhi, cudaStream_t s);
+int nccl_ring_exchange(Nccl* c, int lo_peer, int hi_peer, const double* send_lo, const double* send_hi, double* recv_lo,
+                       double* recv_hi, size_t count, cudaStream_t s);
 int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s);
 int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
 int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);

@@ -20,8 +20,15 @@
 namespace wb { namespace dg {
 
 struct DgGrid {
-  int nx, ny, m, nm;      // elements, order per direction, modes per element (m*m)
-  size_t ne;              // nx*ny
+  int nx, ny, m, nm;      // elements (ny = LOCAL rows incl. the two ghost rows in slab mode), order, modes per element (m*m)
+  size_t ne;              // nx*ny: elements per plane as allocated
+  // slab decomposition along y (one process per GPU).  Ghost rows are ordinary rows of the local arrays: every kernel
+  // treats them like any other row (their results are garbage and are overwritten by the exchange), only the
+  // neighbour rule, the wave-speed scan and the host <-> device copies know about them.
+  int nyg;                // global ny (the reference wraps x-face neighbours with it, 2d/benchmark_2d_dg.f90:1338)
+  int j0;                 // global row index of local row 0 (0 without slabs, first owned row - 1 with slabs)
+  int slab;               // 1: y neighbours are jc +- 1 clamped to the local array; 0: boundary condition applied in y
+  size_t e_off, ne_own;   // first owned element (nx in slab mode) and number of owned elements
 };
 struct DgPhys {
   double gamma, gm1a, gm1b;   // gamma, gamma-1.0 (real(4) literal) and gamma-1. -- the same value, kept apart for clarity
@@ -114,6 +121,11 @@ __device__ __forceinline__ int bc_index(int bc, int idx, int n) {
   return idx;
 }
 
+// row of the y neighbour: boundary condition on a whole grid, plain +-1 (ghost rows) on a slab
+__device__ __forceinline__ int y_nb(const DgGrid& g, int bc, int jc) {
+  return g.slab ? min(max(jc, 0), g.ny - 1) : bc_index(bc, jc, g.ny);
+}
+
 template <int M>
 __device__ __forceinline__ void load_modes(const double* __restrict__ u, const DgGrid& g, size_t e, double d[4][M][M]) {
 #pragma unroll
@@ -149,18 +161,20 @@ __device__ __forceinline__ void trace(const double d[4][M][M], const Basis& B, d
 // ------------------------------------------------------------------------------------ layout kernels
 // host u(nvar,nx,ny,mx,my) == [mode][jc][ic][4]  <->  device planes
 __global__ void k_dg_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, DgGrid g) {
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t eh = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // host arrays hold the owned rows only
   int mode = blockIdx.y;
-  if (e >= g.ne) return;
-  const double2* src = reinterpret_cast<const double2*>(aos + ((size_t)mode * g.ne + e) * 4);
+  if (eh >= g.ne_own) return;
+  const size_t e = eh + g.e_off;
+  const double2* src = reinterpret_cast<const double2*>(aos + ((size_t)mode * g.ne_own + eh) * 4);
   double2 a = src[0], b = src[1];
   PL(soa, g, 0, mode)[e] = a.x; PL(soa, g, 1, mode)[e] = a.y; PL(soa, g, 2, mode)[e] = b.x; PL(soa, g, 3, mode)[e] = b.y;
 }
 __global__ void k_dg_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, DgGrid g) {
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t eh = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int mode = blockIdx.y;
-  if (e >= g.ne) return;
-  double2* dst = reinterpret_cast<double2*>(aos + ((size_t)mode * g.ne + e) * 4);
+  if (eh >= g.ne_own) return;
+  const size_t e = eh + g.e_off;
+  double2* dst = reinterpret_cast<double2*>(aos + ((size_t)mode * g.ne_own + eh) * 4);
   dst[0] = make_double2(PL(soa, g, 0, mode)[e], PL(soa, g, 1, mode)[e]);
   dst[1] = make_double2(PL(soa, g, 2, mode)[e], PL(soa, g, 3, mode)[e]);
 }
@@ -267,21 +281,24 @@ __device__ __forceinline__ void node_xy(const DgGrid& g, const DgPhys& P, const 
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
   const int ni = mode % g.m, nj = mode / g.m;
   x = (double)((float)(ic + 1) - 0.5f) * P.dx + P.dx / 2.0 * B.xq[ni];
-  y = (double)((float)(jc + 1) - 0.5f) * dy + dy / 2.0 * B.xq[nj];
+  y = (double)((float)(g.j0 + jc + 1) - 0.5f) * dy + dy / 2.0 * B.xq[nj];
 }
 __global__ void k_dg_init(double* __restrict__ nodes, double* __restrict__ xy, DgGrid g, DgPhys P, Basis B, int ninit, double eta,
                           double boxlen_x, double boxlen_y, unsigned long long* minbits, int pass) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int mode = blockIdx.y;
   if (e >= g.ne) return;
-  const double dy = boxlen_y / (double)g.ny;
+  const double dy = boxlen_y / (double)g.nyg;
   double x, y;
   node_xy(g, P, B, e, mode, dy, x, y);
   double w[4];
   if (ninit == 1) {
     const double ax = x - boxlen_x / 2., ay = y - boxlen_y / 2.;
     w[0] = exp(-((ax * ax + ay * ay) * 10));
-    if (pass == 0) { atomicMin(minbits, (unsigned long long)__double_as_longlong(w[0])); return; }
+    if (pass == 0) {      // minimum over the owned rows only (ghost rows lie outside the box or belong to a neighbour)
+      if (e >= g.e_off && e < g.e_off + g.ne_own) atomicMin(minbits, (unsigned long long)__double_as_longlong(w[0]));
+      return;
+    }
     w[1] = 1.0; w[2] = 1.0; w[3] = __longlong_as_double((long long)*minbits);
   } else {
     const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
@@ -350,8 +367,8 @@ __global__ void __launch_bounds__(128) k_dg_update(const double* __restrict__ du
   double FL[M][4], FR[M][4], GB[M][4], GT[M][4];
   {
     double nb[4][M][M], tn[M][4];
-    const int il = bc_index(P.bc, ic - 1, g.ny), ir = bc_index(P.bc, ic + 1, g.ny);
-    const int jb = bc_index(P.bc, jc - 1, g.ny), jt = bc_index(P.bc, jc + 1, g.ny);
+    const int il = bc_index(P.bc, ic - 1, g.nyg), ir = bc_index(P.bc, ic + 1, g.nyg);
+    const int jb = y_nb(g, P.bc, jc - 1), jt = y_nb(g, P.bc, jc + 1);
     load_modes<M>(du, g, (size_t)jc * g.nx + il, nb);
     trace<M, 1>(nb, B, tn);                            // left neighbour's right trace
 #pragma unroll
@@ -677,12 +694,12 @@ __device__ __forceinline__ bool key_less(const SpeedKey& a, const SpeedKey& b) {
 }
 __global__ void k_speed_phase1(const double* __restrict__ u, DgGrid g, DgPhys P, SpeedKey* __restrict__ part) {
   SpeedKey best{-1.0, -1, 0.0, 0.0, 0.0};
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne; e += (size_t)gridDim.x * blockDim.x) {
+  for (size_t e = g.e_off + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.e_off + g.ne_own; e += (size_t)gridDim.x * blockDim.x) {
     const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
     double uu[4] = {PL(u, g, 0, 0)[e], PL(u, g, 1, 0)[e], PL(u, g, 2, 0)[e], PL(u, g, 3, 0)[e]};
     SpeedKey c;
     speed(P, uu, c.cs, c.vx, c.vy, c.speed);
-    c.k = (long long)ic * g.ny + jc;
+    c.k = (long long)ic * g.nyg + (g.j0 + jc);          // position in the reference's scan (i outer, j inner), global
     if (key_less(best, c)) best = c;
   }
   __shared__ SpeedKey sh[256];
@@ -715,9 +732,9 @@ __global__ void k_speed_phase2(const double* __restrict__ u, DgGrid g, DgPhys P,
                                double* __restrict__ part) {
   const long long kstar = ctrl->kstar;
   double m = ctrl->cs_max;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.ne; e += (size_t)gridDim.x * blockDim.x) {
+  for (size_t e = g.e_off + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.e_off + g.ne_own; e += (size_t)gridDim.x * blockDim.x) {
     const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
-    if ((long long)ic * g.ny + jc <= kstar) continue;
+    if ((long long)ic * g.nyg + (g.j0 + jc) <= kstar) continue;
     double uu[4] = {PL(u, g, 0, 0)[e], PL(u, g, 1, 0)[e], PL(u, g, 2, 0)[e], PL(u, g, 3, 0)[e]};
     double cs, vx, vy, sp;
     speed(P, uu, cs, vx, vy, sp);
@@ -733,6 +750,16 @@ __global__ void k_speed_phase2(const double* __restrict__ u, DgGrid g, DgPhys P,
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
 // final: cs_max and the time step of evolve (:671) -- dt = min(tend-t, cfl*min(1/9, gll_w_1/2)/((|vx|+cs)/dx + (|vy|+cs)/dx))
+__device__ __forceinline__ void speed_finish(DgCtrl* ctrl, const DgPhys& P, int set_dt) {
+  if (set_dt) {
+    const bool done = !(ctrl->t < ctrl->tend) || (ctrl->max_iter >= 0 && ctrl->iter >= ctrl->max_iter);
+    ctrl->skip = done ? 1 : 0;
+    if (!done) {
+      const double cs = ctrl->cs_max;
+      ctrl->dt = fmin(ctrl->tend - ctrl->t, P.dt_num / ((fabs(ctrl->vx) + (cs)) / P.dx + (fabs(ctrl->vy) + (cs)) / P.dx));
+    }
+  }
+}
 __global__ void k_speed_phase2b(const double* __restrict__ part, int nparts, DgCtrl* ctrl, DgPhys P, int set_dt) {
   __shared__ double sh[256];
   double m = ctrl->cs_max;
@@ -745,15 +772,42 @@ __global__ void k_speed_phase2b(const double* __restrict__ part, int nparts, DgC
   }
   if (threadIdx.x == 0) {
     ctrl->cs_max = sh[0];
-    if (set_dt) {
-      const bool done = !(ctrl->t < ctrl->tend) || (ctrl->max_iter >= 0 && ctrl->iter >= ctrl->max_iter);
-      ctrl->skip = done ? 1 : 0;
-      if (!done) {
-        const double cs = sh[0];
-        ctrl->dt = fmin(ctrl->tend - ctrl->t, P.dt_num / ((fabs(ctrl->vx) + (cs)) / P.dx + (fabs(ctrl->vy) + (cs)) / P.dx));
-      }
-    }
+    if (set_dt >= 0) speed_finish(ctrl, P, set_dt);      // slab mode: set_dt < 0, the minimum is all-reduced first
   }
+}
+__global__ void k_speed_finish(DgCtrl* ctrl, DgPhys P, int set_dt) { speed_finish(ctrl, P, set_dt); }
+
+// ---- slab mode: the two phases of the scan across ranks (lexicographic max of (speed, k), then the
+//      minimum of cs over k >= k*), each a tiny all-reduce on `red`
+__global__ void k_speed_red_a(const DgCtrl* ctrl, double* red) { red[0] = ctrl->speed_max; }
+__global__ void k_speed_red_b(const DgCtrl* ctrl, double* red) {      // red[0] = global max speed -> my candidate k
+  red[1] = (ctrl->speed_max == red[0]) ? (double)ctrl->kstar : -1.0;
+}
+__global__ void k_speed_red_c(const DgCtrl* ctrl, double* red) {      // red[1] = global k* -> the owner publishes its state
+  const bool owner = (ctrl->speed_max == red[0]) && ((double)ctrl->kstar == red[1]);
+  red[2] = owner ? ctrl->vx : -1.7976931348623157e308;
+  red[3] = owner ? ctrl->vy : -1.7976931348623157e308;
+  red[4] = owner ? ctrl->cs_max : -1.7976931348623157e308;
+}
+__global__ void k_speed_red_d(DgCtrl* ctrl, const double* red) {
+  ctrl->speed_max = red[0]; ctrl->kstar = (long long)red[1]; ctrl->vx = red[2]; ctrl->vy = red[3]; ctrl->cs_max = red[4];
+}
+
+// ---- slab mode: ghost rows.  pack: first and last owned row of all 4*nm planes -> contiguous send buffers;
+//      unpack: receive buffers -> ghost rows (row 0 and row ny-1)
+__global__ void k_dg_pack_rows(const double* __restrict__ u, DgGrid g, double* __restrict__ lo, double* __restrict__ hi) {
+  const int ic = blockIdx.x * blockDim.x + threadIdx.x, pl = blockIdx.y;
+  if (ic >= g.nx) return;
+  const double* p = u + (size_t)pl * g.ne;
+  lo[(size_t)pl * g.nx + ic] = p[(size_t)1 * g.nx + ic];
+  hi[(size_t)pl * g.nx + ic] = p[(size_t)(g.ny - 2) * g.nx + ic];
+}
+__global__ void k_dg_unpack_rows(double* __restrict__ u, DgGrid g, const double* __restrict__ lo, const double* __restrict__ hi) {
+  const int ic = blockIdx.x * blockDim.x + threadIdx.x, pl = blockIdx.y;
+  if (ic >= g.nx) return;
+  double* p = u + (size_t)pl * g.ne;
+  p[ic] = lo[(size_t)pl * g.nx + ic];
+  p[(size_t)(g.ny - 1) * g.nx + ic] = hi[(size_t)pl * g.nx + ic];
 }
 __global__ void k_dg_advance(DgCtrl* ctrl) {
   if (ctrl->skip) return;
@@ -794,6 +848,10 @@ struct wb_dg2d {
   bool have_xy = false;
   FastBasis FB;
   int arith = 0;               // 0 = fused/sum-factorised stage kernel, 1 = reference operation order
+  // slab mode (nranks > 1): NCCL communicator, packed boundary rows (send lo/hi, receive lo/hi), all-reduce scratch
+  wb::Nccl* comm = nullptr;
+  double *sbuf_lo = nullptr, *sbuf_hi = nullptr, *rbuf_lo = nullptr, *rbuf_hi = nullptr, *red = nullptr;
+  int rank = 0, nranks = 1, nyl = 0;
 };
 
 namespace {
@@ -814,18 +872,18 @@ int dg_ensure(wb_dg2d* h, double** buf) {
 }
 int dg_h2d_field(wb_dg2d* h, const double* host, double* soa) {
   WB_CHECK(dg_ensure(h, &h->stage));
-  WB_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * h->nfield, cudaMemcpyHostToDevice, h->stream));
-  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
+  WB_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * 4 * h->g.nm * h->g.ne_own, cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((unsigned)((h->g.ne_own + 127) / 128), h->g.nm);
   k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g);
   WB_LAUNCH_CHECK();
   return WB_OK;
 }
 int dg_d2h_field(wb_dg2d* h, const double* soa, double* host) {
   WB_CHECK(dg_ensure(h, &h->stage));
-  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
+  dim3 b(128), gr((unsigned)((h->g.ne_own + 127) / 128), h->g.nm);
   k_dg_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g);
   WB_LAUNCH_CHECK();
-  WB_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * h->nfield, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * 4 * h->g.nm * h->g.ne_own, cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
   return WB_OK;
 }
@@ -836,8 +894,13 @@ int dg_set_xy(wb_dg2d* h, const double* x, const double* y) {
   h->have_xy = true;
   if (!need) return WB_OK;
   WB_REQUIRE(x && y, "x and y are required when source == 2 or ninit == 12");
-  WB_CUDA(cudaMemcpyAsync(h->xy, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  WB_CUDA(cudaMemcpyAsync(h->xy + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  if (h->g.slab) WB_CUDA(cudaMemsetAsync(h->xy, 0, sizeof(double) * 2 * n, h->stream));      // ghost rows: finite coordinates
+  for (int m = 0; m < h->g.nm; ++m) {         // host x,y hold the owned rows of every node plane
+    WB_CUDA(cudaMemcpyAsync(h->xy + (size_t)m * h->g.ne + h->g.e_off, x + (size_t)m * h->g.ne_own, sizeof(double) * h->g.ne_own,
+                            cudaMemcpyHostToDevice, h->stream));
+    WB_CUDA(cudaMemcpyAsync(h->xy + n + (size_t)m * h->g.ne + h->g.e_off, y + (size_t)m * h->g.ne_own, sizeof(double) * h->g.ne_own,
+                            cudaMemcpyHostToDevice, h->stream));
+  }
   dim3 b(256), gr((unsigned)((n + 255) / 256));
   if (h->phys.source == 2) {
     k_grad_phi<<<gr, b, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case);
@@ -896,16 +959,53 @@ int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
   return WB_OK;
 }
 
+// slab mode: fill the two ghost rows of a 4*nm-plane field.  Periodic box (bc = 1): ring of ranks; index clamp
+// (bc = 2, 3): chain, and the ghost row at a global edge is the rank's own boundary row (the clamped neighbour).
+int dg_exchange(wb_dg2d* h, double* field) {
+  if (!h->g.slab) return WB_OK;
+  if (h->nranks > 1 && !h->comm) { set_error("nranks > 1 but wb_dg2d_comm_init was not called"); return WB_ERR_STATE; }
+  const int npl = 4 * h->g.nm;
+  const size_t cnt = (size_t)npl * h->g.nx;
+  dim3 b(128), gr((h->g.nx + 127) / 128, npl);
+  k_dg_pack_rows<<<gr, b, 0, h->stream>>>(field, h->g, h->sbuf_lo, h->sbuf_hi);
+  WB_LAUNCH_CHECK();
+  const bool periodic = (h->phys.bc == 1);
+  const int lo_peer = (h->rank > 0) ? h->rank - 1 : (periodic ? h->nranks - 1 : -1);
+  const int hi_peer = (h->rank < h->nranks - 1) ? h->rank + 1 : (periodic ? 0 : -1);
+  WB_CHECK(nccl_ring_exchange(h->comm, lo_peer, hi_peer, h->sbuf_lo, h->sbuf_hi, h->rbuf_lo, h->rbuf_hi, cnt, h->stream));
+  k_dg_unpack_rows<<<gr, b, 0, h->stream>>>(field, h->g, lo_peer >= 0 ? h->rbuf_lo : h->sbuf_lo, hi_peer >= 0 ? h->rbuf_hi : h->sbuf_hi);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
 // max speed of the mean mode of `u` into ctrl (and, if set_dt, the step's dt / skip flag)
 int dg_max_speed(wb_dg2d* h, const double* u, int set_dt) {
+  const bool multi = h->nranks > 1;
   k_speed_phase1<<<h->nparts, 256, 0, h->stream>>>(u, h->g, h->phys, h->part1);
   WB_LAUNCH_CHECK();
   k_speed_phase1b<<<1, 256, 0, h->stream>>>(h->part1, h->nparts, h->ctrl);
   WB_LAUNCH_CHECK();
+  if (multi) {      // (speed, k) lexicographic max over ranks, then the owner's (vx, vy, cs)
+    if (!h->comm) { set_error("nranks > 1 but wb_dg2d_comm_init was not called"); return WB_ERR_STATE; }
+    k_speed_red_a<<<1, 1, 0, h->stream>>>(h->ctrl, h->red);
+    WB_CHECK(nccl_allreduce_max_f64(h->comm, h->red, 1, h->stream));
+    k_speed_red_b<<<1, 1, 0, h->stream>>>(h->ctrl, h->red);
+    WB_CHECK(nccl_allreduce_max_f64(h->comm, h->red + 1, 1, h->stream));
+    k_speed_red_c<<<1, 1, 0, h->stream>>>(h->ctrl, h->red);
+    WB_CHECK(nccl_allreduce_max_f64(h->comm, h->red + 2, 3, h->stream));
+    k_speed_red_d<<<1, 1, 0, h->stream>>>(h->ctrl, h->red);
+    wb::g_launches.fetch_add(4);
+    WB_CUDA(cudaGetLastError());
+  }
   k_speed_phase2<<<h->nparts, 256, 0, h->stream>>>(u, h->g, h->phys, h->ctrl, h->part2);
   WB_LAUNCH_CHECK();
-  k_speed_phase2b<<<1, 256, 0, h->stream>>>(h->part2, h->nparts, h->ctrl, h->phys, set_dt);
+  k_speed_phase2b<<<1, 256, 0, h->stream>>>(h->part2, h->nparts, h->ctrl, h->phys, multi ? -1 : set_dt);
   WB_LAUNCH_CHECK();
+  if (multi) {
+    WB_CHECK(nccl_allreduce_min_f64(h->comm, &h->ctrl->cs_max, 1, h->stream));
+    k_speed_finish<<<1, 1, 0, h->stream>>>(h->ctrl, h->phys, set_dt);
+    WB_LAUNCH_CHECK();
+  }
   return WB_OK;
 }
 
@@ -934,6 +1034,8 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   DISPATCH_M(h, k_dg_stage_fast<MM><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
                                                            h->phys, h->FB, h->ctrl, onp));
   WB_LAUNCH_CHECK();
+  WB_CHECK(dg_exchange(h, out));
+  if (out2) WB_CHECK(dg_exchange(h, out2));
   return WB_OK;
 }
 
@@ -1032,13 +1134,28 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
   WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fused) or 1 (reference order)");
+  const int nranks = p->nranks <= 0 ? 1 : p->nranks;      // 0 (zero-initialised struct) means "no slabs"
+  WB_REQUIRE(p->rank >= 0 && p->rank < nranks, "bad rank/nranks %d/%d", p->rank, p->nranks);
+  WB_REQUIRE(nranks == 1 || (p->arith == 0 && p->limiter_id <= 1),
+             "slab mode (nranks > 1) is built for the fused stage kernel: arith 0 with limiter 'ONP' or none");
+  WB_REQUIRE(nranks == 1 || p->ny / nranks >= 1, "each slab needs at least one row");
   int dev = 0;
   WB_CHECK(select_device(p->device, &dev));
   wb_dg2d* h = new wb_dg2d;
   h->prm = *p;
   h->dev = dev;
+  h->rank = p->rank; h->nranks = nranks;
   DgGrid& g = h->g;
-  g.nx = p->nx; g.ny = p->ny; g.m = p->mx; g.nm = p->mx * p->my; g.ne = (size_t)p->nx * p->ny;
+  g.nx = p->nx; g.m = p->mx; g.nm = p->mx * p->my; g.nyg = p->ny;
+  if (nranks > 1) {        // y slabs: rank r owns global rows [ny*r/R, ny*(r+1)/R) plus one ghost row on each side
+    const int ja = (int)((long long)p->ny * p->rank / nranks), jb = (int)((long long)p->ny * (p->rank + 1) / nranks);
+    h->nyl = jb - ja;
+    g.ny = h->nyl + 2; g.j0 = ja - 1; g.slab = 1; g.e_off = (size_t)p->nx; g.ne_own = (size_t)p->nx * h->nyl;
+  } else {
+    h->nyl = p->ny;
+    g.ny = p->ny; g.j0 = 0; g.slab = 0; g.e_off = 0; g.ne_own = (size_t)p->nx * p->ny;
+  }
+  g.ne = (size_t)g.nx * g.ny;
   h->nfield = (size_t)4 * g.nm * g.ne;
   h->B = make_basis(p->mx);
   {
@@ -1085,6 +1202,13 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(DgCtrl));
   if (e == cudaSuccess) e = cudaMalloc(&h->part1, sizeof(SpeedKey) * h->nparts);
   if (e == cudaSuccess) e = cudaMalloc(&h->part2, sizeof(double) * h->nparts);
+  if (g.slab) {
+    const size_t rb = sizeof(double) * 4 * g.nm * g.nx;
+    double** rows[] = {&h->sbuf_lo, &h->sbuf_hi, &h->rbuf_lo, &h->rbuf_hi};
+    for (double** b : rows)
+      if (e == cudaSuccess) e = cudaMalloc(b, rb);
+    if (e == cudaSuccess) e = cudaMalloc(&h->red, sizeof(double) * 8);
+  }
   if (e != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
   cudaMemsetAsync(h->ctrl, 0, sizeof(DgCtrl), h->stream);
   if (need_xy) {
@@ -1103,6 +1227,8 @@ int wb_dg2d_destroy(wb_dg2d* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->du); cudaFree(h->A); cudaFree(h->Bf); cudaFree(h->C); cudaFree(h->D); cudaFree(h->E); cudaFree(h->stage);
   cudaFree(h->gx); cudaFree(h->gy); cudaFree(h->xy); cudaFree(h->fz); cudaFree(h->ctrl); cudaFree(h->part1); cudaFree(h->part2);
+  cudaFree(h->sbuf_lo); cudaFree(h->sbuf_hi); cudaFree(h->rbuf_lo); cudaFree(h->rbuf_hi); cudaFree(h->red);
+  nccl_comm_destroy(h->comm);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1115,6 +1241,21 @@ int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream) {
   WB_CUDA(cudaStreamSynchronize(h->stream));
   if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
   h->stream = (cudaStream_t)cuda_stream;
+  return WB_OK;
+}
+
+int wb_dg2d_comm_init(wb_dg2d* h, const void* id128) {
+  if (!h || !id128) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(h->nranks > 1, "comm_init needs nranks > 1");
+  WB_CUDA(cudaSetDevice(h->dev));
+  if (h->comm) { nccl_comm_destroy(h->comm); h->comm = nullptr; }
+  return nccl_comm_create(&h->comm, id128, h->rank, h->nranks);
+}
+
+int wb_dg2d_local_rows(const wb_dg2d* h, int* j0, int* nrows) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  if (j0) *j0 = h->g.slab ? h->g.j0 + 1 : 0;
+  if (nrows) *nrows = h->nyl;
   return WB_OK;
 }
 
@@ -1175,8 +1316,8 @@ int wb_dg2d_compute_max_speed(wb_dg2d* h, const double* mean_mode, double* cs_ma
   h->resident = false;
   // mean mode (nvar,nx,ny) -> planes (v, mode 0) of buffer A
   WB_CHECK(dg_ensure(h, &h->stage));
-  WB_CUDA(cudaMemcpyAsync(h->stage, mean_mode, sizeof(double) * 4 * h->g.ne, cudaMemcpyHostToDevice, h->stream));
-  dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), 1);
+  WB_CUDA(cudaMemcpyAsync(h->stage, mean_mode, sizeof(double) * 4 * h->g.ne_own, cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((unsigned)((h->g.ne_own + 127) / 128), 1);
   k_dg_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, h->A, h->g);
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_max_speed(h, h->A, 0));
@@ -1200,6 +1341,7 @@ int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const dou
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_limiter(h, h->du, false));                                                         // :659
+  WB_CHECK(dg_exchange(h, h->du));
   h->resident = true;
   return WB_OK;
 }
@@ -1216,6 +1358,10 @@ int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
   if (ninit == 1) {
     k_dg_init<<<gr, b, 0, h->stream>>>(h->A, nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x, h->prm.boxlen_y, minbits, 0);
     WB_LAUNCH_CHECK();
+    if (h->nranks > 1) {       // minval over the whole box (positive doubles: the bit patterns order like the values)
+      if (!h->comm) { set_error("nranks > 1 but wb_dg2d_comm_init was not called"); return WB_ERR_STATE; }
+      WB_CHECK(nccl_allreduce_min_f64(h->comm, h->part2, 1, h->stream));
+    }
   }
   k_dg_init<<<gr, b, 0, h->stream>>>(h->A, need_xy ? h->xy : nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x,
                                      h->prm.boxlen_y, minbits, 1);
@@ -1232,6 +1378,7 @@ int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_limiter(h, h->du, false));                                                          // :659
+  WB_CHECK(dg_exchange(h, h->du));
   h->resident = true;
   return WB_OK;
 }

@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
         for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
     }
     // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
-    face_term<M, 0>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.ny), acc);
-    face_term<M, 1>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.ny), acc);
-    face_term<M, 2>(in, g, P, B, d, (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, acc);
-    face_term<M, 3>(in, g, P, B, d, (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic, acc);
+    face_term<M, 0>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), acc);
+    face_term<M, 1>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg), acc);
+    face_term<M, 2>(in, g, P, B, d, (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, acc);
+    face_term<M, 3>(in, g, P, B, d, (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic, acc);
     // ---- nodal values (sum-factorised)
 #pragma unroll
     for (int v = 0; v < 4; ++v)

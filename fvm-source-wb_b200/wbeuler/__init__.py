@@ -185,7 +185,7 @@ class DG2DParams(C.Structure):
                 ("source", C.c_int), ("grad_phi_case", C.c_int), ("flux_id", C.c_int), ("limiter_id", C.c_int),
                 ("solver_id", C.c_int), ("ninit", C.c_int), ("gamma", C.c_double), ("boxlen_x", C.c_double),
                 ("boxlen_y", C.c_double), ("cfl", C.c_double), ("eps", C.c_double), ("M", C.c_double), ("device", C.c_int),
-                ("arith", C.c_int)]
+                ("arith", C.c_int), ("rank", C.c_int), ("nranks", C.c_int)]
 
 
 LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4}     # limiter_type (2d/benchmark_2d_dg.f90:1516-1555)
@@ -197,12 +197,20 @@ class DG2D:
     """2D modal DG (2d/benchmark_2d_dg.f90).  Arrays: u(nvar,nx,ny,mx,my) == numpy (my, mx, ny, nx, 4)."""
 
     def __init__(self, nx=8, ny=8, mx=2, my=2, bc=1, source=1, grad_phi_case=2, flux="llf1", limiter="ONP", solver="RK4",
-                 ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, device=-1, arith=0):
+                 ninit=1, gamma=F32(1.4), boxlen_x=1.0, boxlen_y=1.0, cfl=F32(0.2), eps=F32(1e-10), M=0.0, device=-1, arith=0,
+                 rank=0, nranks=1):
         self.params = DG2DParams(nx, ny, mx, my, 4, bc, source, grad_phi_case, FLUXES[flux], LIMITERS[limiter],
-                                 SOLVERS[solver], ninit, gamma, boxlen_x, boxlen_y, cfl, eps, M, device, arith)
+                                 SOLVERS[solver], ninit, gamma, boxlen_x, boxlen_y, cfl, eps, M, device, arith, rank, nranks)
         self._h = C.c_void_p()
         _check(lib().wb_dg2d_create(C.byref(self._h), C.byref(self.params)))
-        self.shape = (my, mx, ny, nx, 4)
+        j0 = C.c_int(); nr = C.c_int()
+        _check(lib().wb_dg2d_local_rows(self._h, C.byref(j0), C.byref(nr)))
+        self.j0, self.nrows = j0.value, nr.value             # this rank's slab: global rows [j0, j0 + nrows)
+        self.shape = (my, mx, self.nrows, nx, 4)             # host arrays hold the rank's own rows
+
+    def comm_init(self, unique_id_bytes):
+        """slab mode: wire the NCCL communicator (every rank, same 128-byte id)"""
+        _check(lib().wb_dg2d_comm_init(self._h, C.c_char_p(unique_id_bytes)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

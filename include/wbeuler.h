@@ -133,11 +133,19 @@ typedef struct {
   int arith;             /* 0 = fused sum-factorised stage kernel (<= 1e-12 of the reference, default; used by evolve /
                             step_async when the limiter is element-local: 'ONP' or none), 1 = reference operation order
                             (bit-for-bit with the CPU restatement; also what the stateless entries always run)        */
+  int rank, nranks;      /* y-slab decomposition, one process per GPU: rank r owns global rows [ny*r/R, ny*(r+1)/R);
+                            host arrays of a handle hold its own rows only.  nranks <= 1: whole grid (default).
+                            Built for the fused stage kernel (arith 0, limiter 'ONP' or none).                        */
 } wb_dg2d_params;
 
 int wb_dg2d_create(wb_dg2d** h, const wb_dg2d_params* p);
 int wb_dg2d_destroy(wb_dg2d* h);
 int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream);
+/* slab mode: NCCL communicator from the 128-byte id of wb_nccl_get_unique_id (same id on every rank); the ghost rows of
+ * modes travel once per RK stage (periodic box: ring, bc 2|3: chain), the order-dependent max-speed scan of
+ * compute_max_speed is all-reduced in its two-phase form */
+int wb_dg2d_comm_init(wb_dg2d* h, const void* nccl_unique_id_128);
+int wb_dg2d_local_rows(const wb_dg2d* h, int* j0, int* nrows);
 /* Gauss-Legendre nodes/weights exactly as gl_quadrature computes them (2d/legendre.f90:77-108) */
 int wb_dg2d_quadrature(wb_dg2d* h, double* x_quad, double* w_quad);
 /* replaces get_modes_from_nodes / get_nodes_from_modes   2d/benchmark_2d_dg.f90:497-542 / :544-592

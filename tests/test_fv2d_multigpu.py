@@ -28,3 +28,20 @@ def test_slab_evolve_equals_single_gpu_and_oracle(nx, ny, steps):
            "--master-port", str(port), os.path.join(ROOT, "tools", "slab_parity.py"), str(nx), str(ny), str(steps)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n,m,steps", [(24, 3, 3), (17, 2, 4)])
+def test_dg_slab_evolve_equals_single_gpu_and_oracle(n, m, steps):
+    """2D DG on y slabs: ghost rows of modes once per RK stage (ring for the periodic box, chain for the clamped one),
+    two-phase all-reduce of the order-dependent max-speed scan -> bit-identical to the single-GPU run."""
+    ng = _ngpu()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import __graft_entry__ as ge
+    ge.build()
+    world = 2 if ng < 4 else 4
+    port = 29300 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "dg_slab_parity.py"), str(n), str(m), str(steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
