@@ -397,6 +397,182 @@ __global__ void k_dg1_max_speed(const double* __restrict__ u_nodes, P1d P, CtrlD
     }
   }
 }
+
+// compute_update_exact :1380-1744 (integrator 'RKw'): full-state modes u, equilibrium MODES u_eq; bc 4 | 5 only (any
+// other bc uses the out-of-bounds reads u_right(:,0) / u_left(:,nx+1) of the reference).  One thread per cell.
+__device__ __forceinline__ void eq_cons(double x, double* u, double gamma) {
+  double w[NV] = {exp(-x), 0, exp(-x)};
+  cons(w, u, gamma);
+}
+__global__ void k_dg1_update_exact(const double* __restrict__ u, const double* __restrict__ u_eq, double* __restrict__ dudt, P1d P,
+                                   Basis1 B, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;     // 0-based cell
+  if (ic >= P.nx) return;
+  const int n = P.n, nx = P.nx;
+  const double gamma = P.gamma;
+  const double dx = P.boxlen / (double)nx, oneoverdx = 1. / dx;
+  double ufe[2][NV], ffe[2][NV];                       // face equilibria at x = ic*dx and (ic+1)*dx
+  for (int k = 0; k < 2; ++k) { eq_cons((double)(ic + k) * dx, ufe[k], gamma); flux(ufe[k], ffe[k], gamma); }
+  double fq[MAXN][NV], fqe[MAXN][NV], sq[MAXN][NV], sqe[MAXN][NV];
+  for (int j = 0; j < n; ++j) {
+    double uq[NV] = {0, 0, 0}, uqe[NV] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        uq[v] = uq[v] + M3(u, v, i, ic) * B.P[j][i];
+        uqe[v] = uqe[v] + M3(u_eq, v, i, ic) * B.P[j][i];
+      }
+    flux(uq, fq[j], gamma);
+    flux(uqe, fqe[j], gamma);
+    source_term(uq, sq[j], gamma);
+    source_term(uqe, sqe[j], gamma);
+  }
+  // u_left(c) = u_face_eq(c) + (trace_-(c) - U_eq(x_left(c))),  u_right(c) = u_face_eq(c+1) + (trace_+(c) - U_eq(x_right(c)))
+  auto side = [&](int c, int right, double* out) {       // c 0-based
+    double t[NV] = {0, 0, 0}, ue[NV], uf[NV];
+    const double* E = right ? B.Ep : B.Em;
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) t[v] = t[v] + M3(u, v, i, c) * E[i];
+    eq_cons((double)(c + right) * dx, ue, gamma);
+    eq_cons((double)(c + right) * dx, uf, gamma);        // u_face_eq(c + right + 1): the same point, the same arithmetic
+    for (int v = 0; v < NV; ++v) out[v] = uf[v] + (t[v] - ue[v]);
+  };
+  double F0[NV], F1[NV], a[NV], b[NV], t[NV], s0[NV], s1[NV];
+  // left face of the cell (1-based face ic+1)
+  if (ic == 0) {
+    if (P.bc == 4) {
+      eq_cons((double)-0.5f * dx + dx / 2.0 * (double)(1), a, gamma);
+      eq_cons((double)0.5f * dx + dx / 2.0 * (double)(-1), b, gamma);
+      side(0, 0, s0);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + s0[v] - b[v];
+    } else {
+      eq_cons((double)-0.5f * dx, a, gamma);
+      eq_cons((double)0.5f * dx, b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + M3(u, v, 0, 0) - b[v];
+    }
+    flux(t, F0, gamma);
+  } else {
+    side(ic - 1, 1, s0); side(ic, 0, s1);
+    if (P.riemann == 1) riemann_llf(s0, s1, F0, gamma); else riemann_hllc(s0, s1, F0, gamma);
+  }
+  // right face (1-based face ic+2)
+  if (ic == nx - 1) {
+    if (P.bc == 4) {
+      eq_cons((double)((float)nx + 0.5f) * dx + dx / 2.0 * (double)(-1), a, gamma);
+      eq_cons((double)nx * dx, b, gamma);
+      side(nx - 1, 1, s0);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + s0[v] - b[v];
+    } else {
+      eq_cons((double)((float)nx + 0.5f) * dx, a, gamma);
+      eq_cons((double)((float)nx - 0.5f) * dx, b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + M3(u, v, 0, nx - 1) - b[v];
+    }
+    flux(t, F1, gamma);
+  } else {
+    side(ic, 1, s0); side(ic + 1, 0, s1);
+    if (P.riemann == 1) riemann_llf(s0, s1, F1, gamma); else riemann_hllc(s0, s1, F1, gamma);
+  }
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) {
+      double fv = 0.0, fve = 0.0, sv = 0.0, sve = 0.0;
+      for (int j = 0; j < n; ++j) {
+        fv = fv + fq[j][v] * B.dP[j][i] * B.wq[j];
+        fve = fve + fqe[j][v] * B.dP[j][i] * B.wq[j];
+        if (P.source == 2) {
+          sv = sv + sq[j][v] * B.P[j][i] * B.wq[j];
+          sve = sve + sqe[j][v] * B.P[j][i] * B.wq[j];
+        }
+      }
+      M3(dudt, v, i, ic) = oneoverdx * fv - oneoverdx * fve - oneoverdx * (F1[v] * B.Ep[i] - F0[v] * B.Em[i])
+                           + oneoverdx * (ffe[1][v] * B.Ep[i] - ffe[0][v] * B.Em[i]) + sv - sve;
+    }
+}
+// limiter_TDV :520-600 with use_limiter = .false. on delta = w - q: w = q + limited(w - q)   (dg_with_source.f90:232-235)
+__global__ void k_dg1_limiter_tdv(double* __restrict__ w, const double* __restrict__ q, double* __restrict__ delta_out, P1d P,
+                                  const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ic >= P.nx) return;
+  const int n = P.n;
+  double d[MAXN][NV];
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) d[i][v] = M3(w, v, i, ic) - M3(q, v, i, ic);
+  if (n > 1) {
+    double ul[NV] = {0, 0, 0}, ur[NV] = {0, 0, 0};
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        ul[v] = ul[v] + d[i - 1][v] * ((i - 1) % 2 == 0 ? 1.0 : -1.0) * sqrt(2.0 * (double)i - 1.0);
+        ur[v] = ur[v] + d[i - 1][v] * sqrt(2.0 * (double)i - 1.0);
+      }
+    if (ul[0] < 1e-10 || ur[0] < 1e-10 || ul[2] < 1e-10 || ul[2] < 1e-10)
+      for (int i = 1; i < n; ++i)
+        for (int v = 0; v < NV; ++v) d[i][v] = 0.0;
+  }
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) {
+      M3(w, v, i, ic) = M3(q, v, i, ic) + d[i][v];
+      if (delta_out) M3(delta_out, v, i, ic) = d[i][v];
+    }
+}
+// limiter_cons :602-734: reads `u` (with neighbours), writes `ul`
+__global__ void k_dg1_limiter_cons(const double* __restrict__ u, double* __restrict__ ul, P1d P, const CtrlD* ctrl) {
+  if (ctrl && ctrl->skip) return;
+  int ic = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ic > P.nx) return;
+  const int n = P.n, nx = P.nx;
+  const double gamma = P.gamma;
+  double el[MAXN][NV];
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) el[i][v] = M3(u, v, i, ic - 1);
+  if (n > 1 && P.use_limiter) {
+    int ileft = ic - 1, iright = ic + 1;
+    double switch_left = 1.0, switch_right = 1.0;
+    if (P.bc == 1) { if (ic == 1) ileft = nx; if (ic == nx) iright = 1; }
+    if (P.bc == 2 || P.bc == 4) { if (ic == 1) ileft = 1; if (ic == nx) iright = nx; }
+    if (P.bc == 3) { if (ic == 1) { ileft = 1; switch_left = -1.0; } if (ic == nx) { iright = nx; switch_right = -1.0; } }
+    if (ileft >= 1 && iright <= nx) {
+      double wL[MAXN][NV], wM[MAXN][NV], wR[MAXN][NV], w_lim[MAXN][NV];
+      for (int i = n - 1; i >= 1; --i) {
+        double coeff_i = sqrt(2.0 * (double)(i - 1) + 1.0) * (2.0 * (double)i - 1);
+        double coeff_ip1 = sqrt(2.0 * (double)i + 1.0) * (2.0 * (double)i - 1);
+        for (int v = 0; v < NV; ++v) {
+          wL[i][v] = (M3(u, v, i - 1, ic - 1) - M3(u, v, i - 1, ileft - 1)) * coeff_i / coeff_ip1;
+          wR[i][v] = (M3(u, v, i - 1, iright - 1) - M3(u, v, i - 1, ic - 1)) * coeff_i / coeff_ip1;
+          wM[i][v] = M3(u, v, i, ic - 1);
+        }
+        wL[i][1] = switch_left * wL[i][1];
+        wR[i][1] = switch_right * wR[i][1];
+      }
+      for (int i = 1; i < n; ++i)
+        for (int v = 0; v < NV; ++v) w_lim[i][v] = wM[i][v];
+      for (int v = 0; v < NV; ++v)
+        for (int i = n - 1; i >= 1; --i) {
+          double w_min = minmod3(wL[i][v], wM[i][v], wR[i][v]);
+          w_lim[i][v] = w_min;
+          if (fabs(w_min - wM[i][v]) < (double)0.01f * fabs(wM[i][v])) break;
+        }
+      for (int i = n - 1; i >= 1; --i)
+        for (int v = 0; v < NV; ++v) el[i][v] = w_lim[i][v];
+    }
+  }
+  if (n > 1) {
+    double w[NV], u_left[NV] = {0, 0, 0}, u_right[NV] = {0, 0, 0}, w_left[NV], w_right[NV];
+    prim(el[0], w, gamma);
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        u_left[v] = u_left[v] + el[i - 1][v] * ((i - 1) % 2 == 0 ? 1.0 : -1.0) * sqrt(2.0 * (double)i - 1.0);
+        u_right[v] = u_right[v] + el[i - 1][v] * sqrt(2.0 * (double)i - 1.0);
+      }
+    cons_to_prim(u_left, w_left, w, gamma);
+    cons_to_prim(u_right, w_right, w, gamma);
+    if (w_left[0] < 1e-10 || w_right[0] < 1e-10 || w_left[2] < 1e-10 || w_left[2] < 1e-10)
+      for (int i = 1; i < n; ++i)
+        for (int v = 0; v < NV; ++v) el[i][v] = 0.0;
+  }
+  for (int i = 0; i < n; ++i)
+    for (int v = 0; v < NV; ++v) M3(ul, v, i, ic - 1) = el[i][v];
+}
+
 // out = c0*A0 [+ c1*A1] [+ (cd*dt)*D], left to right (cd == 0: no D term at all)
 __global__ void k_dg1_axpy(double* out, const double* A0, double c0, const double* A1, double c1, const double* D, double cd,
                            int n, int na, const CtrlD* ctrl) {
@@ -653,6 +829,125 @@ int wb_dg1d_evolve_rk(wb_dg1d* h, int integrator, double* u, const double* delta
     it = h->h_ctrl->iter; t = h->h_ctrl->t; dt = h->h_ctrl->dt;
   }
   WB_CUDA(cudaMemcpyAsync(u, U, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaMemcpyAsync(uinit, h->uinit, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (iters) *iters = it;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  return WB_OK;
+}
+
+
+// replaces compute_update_exact(u,u_eq_modes,dudt)   dg_with_source.f90:1380-1744 (bc 4 | 5)
+int wb_dg1d_compute_update_exact(wb_dg1d* h, const double* u, const double* u_eq_modes, double* dudt) {
+  if (!h || !u || !u_eq_modes || !dudt) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(h->P.bc == 4 || h->P.bc == 5, "compute_update_exact is defined for bc 4 and 5 only (other bc use out-of-bounds reads in the reference)");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->ueq, u_eq_modes, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_update_exact<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->du, h->ueq, h->dudt, h->P, h->B, nullptr);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(dudt, h->dudt, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+// replaces limiter_TDV(u) (:520-600, use_limiter = .false.: positivity fallback on the traces) and limiter_cons(u) (:602-734)
+int wb_dg1d_limiter_tdv(wb_dg1d* h, double* u_inout) {
+  if (!h || !u_inout) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(!h->P.use_limiter, "limiter_TDV with use_limiter = .true. indexes its neighbours with a stale loop variable in the "
+                                "reference (dg_with_source.f90:550-552): undefined, not built");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->w1, u_inout, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemsetAsync(h->w2, 0, fb, h->stream));
+  k_dg1_limiter_tdv<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->w1, h->w2, nullptr, h->P, nullptr);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(u_inout, h->w1, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+int wb_dg1d_limiter_cons(wb_dg1d* h, double* u_inout) {
+  if (!h || !u_inout) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  WB_CUDA(cudaMemcpyAsync(h->du, u_inout, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_limiter_cons<<<(h->P.nx + 63) / 64, 64, 0, h->stream>>>(h->du, h->w1, h->P, nullptr);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(u_inout, h->w1, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  return WB_OK;
+}
+// main loop with integrator 'RKw' (5, :229-270) or 'RKe' (6, :273-280)   dg_with_source.f90:173-336
+int wb_dg1d_evolve_w(wb_dg1d* h, int integrator, double* u, double* delta_u, const double* u_eq_nodes, const double* u_eq_modes,
+                     double* uinit, double tend, int max_iter, int* iters, double* t_out, double* dt_out) {
+  if (!h || !u || !delta_u || !u_eq_nodes || !u_eq_modes || !uinit) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(integrator == 5 || integrator == 6, "integrator must be 5 ('RKw') or 6 ('RKe')");
+  WB_REQUIRE(integrator == 6 || h->P.bc == 4 || h->P.bc == 5, "'RKw' (compute_update_exact) is defined for bc 4 and 5 only");
+  WB_REQUIRE(integrator == 6 || !h->P.use_limiter, "'RKw' with use_limiter = .true. is undefined in the reference (limiter_TDV)");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t fb = sizeof(double) * h->N;
+  const int N = (int)h->N;
+  double *U = h->w5, *W1 = h->w1, *W2 = h->w2, *W3 = h->w3, *W4 = h->w4, *Q = h->w6, *D = h->du;
+  WB_CUDA(cudaMemcpyAsync(U, u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(D, delta_u, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->ueq, u_eq_nodes, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(Q, u_eq_modes, fb, cudaMemcpyHostToDevice, h->stream));
+  WB_CUDA(cudaMemcpyAsync(h->uinit, uinit, fb, cudaMemcpyHostToDevice, h->stream));
+  k_dg1_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, tend, max_iter);
+  WB_LAUNCH_CHECK();
+  dim3 bc(64), gc((h->P.nx + 63) / 64), ba(128), ga((N + 127) / 128);
+  auto updw = [&](const double* in) {
+    k_dg1_update_exact<<<gc, bc, 0, h->stream>>>(in, Q, h->dudt, h->P, h->B, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto updd = [&](const double* in) {
+    k_dg1_update<<<gc, bc, 0, h->stream>>>(in, h->ueq, h->dudt, h->P, h->B, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto axpy = [&](double* out, const double* A0, double c0, const double* A1, double c1, double cd, int na) {
+    k_dg1_axpy<<<ga, ba, 0, h->stream>>>(out, A0, c0, A1, c1, h->dudt, cd, N, na, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto limw = [&](double* x, double* delta_out) {     // delta = x - q; limiter_TDV(delta); x = q + delta
+    k_dg1_limiter_tdv<<<gc, bc, 0, h->stream>>>(x, Q, delta_out, h->P, h->ctrl);
+    wb::g_launches.fetch_add(1);
+  };
+  auto limc = [&](double* x, double* scratch) {       // limiter_cons reads neighbours: limit into the scratch, copy back
+    if (h->P.n == 1) return;
+    k_dg1_limiter_cons<<<gc, bc, 0, h->stream>>>(x, scratch, h->P, h->ctrl);
+    k_dg1_axpy<<<ga, ba, 0, h->stream>>>(x, scratch, 1.0, nullptr, 0.0, scratch, 0.0, N, 1, h->ctrl);
+    wb::g_launches.fetch_add(2);
+  };
+  int it = 0;
+  double t = 0.0, dt = 0.0;
+  for (;;) {
+    if (!(t < tend) || (max_iter >= 0 && it >= max_iter)) break;
+    for (int s = 0; s < 16; ++s) {
+      k_dg1_max_speed<<<1, 256, 0, h->stream>>>(h->uinit, h->P, h->ctrl, 1);
+      wb::g_launches.fetch_add(1);
+      if (integrator == 5) {
+        updw(U); axpy(W1, U, 1.0, nullptr, 0.0, F32(0.391752226571890), 1); limw(W1, nullptr);
+        updw(W1); axpy(W2, U, F32(0.444370493651235), W1, F32(0.555629506348765), F32(0.368410593050371), 2); limw(W2, nullptr);
+        updw(W2); axpy(W3, U, F32(0.620101851488403), W2, F32(0.379898148511597), F32(0.251891774271694), 2); limw(W3, nullptr);
+        updw(W3); axpy(W4, U, F32(0.178079954393132), W3, F32(0.821920045606868), F32(0.544974750228521), 2);
+        axpy(U, W2, F32(0.517231671970585), W3, F32(0.096059710526147), F32(0.063692468666290), 2); limw(W4, nullptr);
+        updw(W4); axpy(U, U, 1.0, W4, F32(0.386708617503269), F32(0.226007483236906), 2); limw(U, D);
+      } else {
+        updd(D); limc(D, W2); axpy(W1, D, 1.0, nullptr, 0.0, 1.0, 1);
+        updd(W1); limc(W1, W2); axpy(D, D, 0.5, W1, 0.5, 0.5, 2);
+      }
+      k_dg1_reconstruct<<<gc, bc, 0, h->stream>>>(D, h->ueq, h->uinit, h->P, h->B, h->ctrl);
+      k_dg1_advance<<<1, 1, 0, h->stream>>>(h->ctrl);
+      wb::g_launches.fetch_add(2);
+    }
+    WB_CUDA(cudaGetLastError());
+    WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(CtrlD), cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+    it = h->h_ctrl->iter; t = h->h_ctrl->t; dt = h->h_ctrl->dt;
+  }
+  WB_CUDA(cudaMemcpyAsync(u, U, fb, cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaMemcpyAsync(delta_u, D, fb, cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaMemcpyAsync(uinit, h->uinit, fb, cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
   if (iters) *iters = it;

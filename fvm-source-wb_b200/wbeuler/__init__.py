@@ -471,3 +471,32 @@ class DG1D(_Handle):
         _check(lib().wb_dg1d_evolve_rk(self._h, C.c_int({"RK1": 1, "RK2": 2, "RK3": 3, "RK4": 4}[integrator]), _ptr(uu), _ptr(delta_u),
                                        _ptr(u_eq), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt)))
         return uu, ui, it.value, t.value, dt.value
+
+    def compute_update_exact(self, u, u_eq_modes):
+        """compute_update_exact(u,u_eq_modes,dudt)  dg_with_source.f90:1380-1744 (bc 4 | 5)"""
+        d = np.empty(self.shape)
+        _check(lib().wb_dg1d_compute_update_exact(self._h, _ptr(u), _ptr(u_eq_modes), _ptr(d)))
+        return d
+
+    def limiter_TDV(self, u):
+        """limiter_TDV(u)  dg_with_source.f90:520-600 (use_limiter = .false.)"""
+        v = np.array(u, dtype=np.float64, order="C", copy=True)
+        _check(lib().wb_dg1d_limiter_tdv(self._h, _ptr(v)))
+        return v
+
+    def limiter_cons(self, u):
+        """limiter_cons(u)  dg_with_source.f90:602-734"""
+        v = np.array(u, dtype=np.float64, order="C", copy=True)
+        _check(lib().wb_dg1d_limiter_cons(self._h, _ptr(v)))
+        return v
+
+    def evolve_w(self, integrator, u, delta_u, u_eq_nodes, u_eq_modes, uinit, tend, max_iter=-1):
+        """main loop with 'RKw' | 'RKe'  dg_with_source.f90:229-280 -> (u, delta_u, uinit, iters, t, last_dt)"""
+        uu = np.array(u, dtype=np.float64, order="C", copy=True)
+        dd = np.array(delta_u, dtype=np.float64, order="C", copy=True)
+        ui = np.array(uinit, dtype=np.float64, order="C", copy=True)
+        it = C.c_int(); t = C.c_double(); dt = C.c_double()
+        _check(lib().wb_dg1d_evolve_w(self._h, C.c_int({"RKw": 5, "RKe": 6}[integrator]), _ptr(uu), _ptr(dd), _ptr(u_eq_nodes),
+                                      _ptr(u_eq_modes), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t),
+                                      C.byref(dt)))
+        return uu, dd, ui, it.value, t.value, dt.value

@@ -263,6 +263,19 @@ int wb_dg1d_limiter(wb_dg1d* h, double* u_inout);
  * delta_u is constant on these paths; it only feeds the nodal state `uinit` the time step is computed from. */
 int wb_dg1d_evolve_rk(wb_dg1d* h, int integrator, double* u_inout, const double* delta_u, const double* u_eq,
                       double* uinit_inout, double tend, int max_iter, int* iters_out, double* t_out, double* last_dt_out);
+/* replaces compute_update_exact(u,u_eq_modes,dudt)   dg_with_source.f90:1380-1744: full-state modes against the
+ * equilibrium MODES; bc 4 | 5 (with any other bc the reference uses out-of-bounds face states) */
+int wb_dg1d_compute_update_exact(wb_dg1d* h, const double* u, const double* u_eq_modes, double* dudt);
+/* replaces limiter_TDV(u)   :520-600 -- only with use_limiter = .false. (the shipped value): its moment-limiting block
+ * indexes the neighbours with a stale loop variable (:550-552), what remains is the positivity fallback on the traces */
+int wb_dg1d_limiter_tdv(wb_dg1d* h, double* u_inout);
+/* replaces limiter_cons(u)   :602-734 */
+int wb_dg1d_limiter_cons(wb_dg1d* h, double* u_inout);
+/* replaces the main time loop with integrator 'RKw' (5, :229-270) or 'RKe' (6, :273-280).  u (full-state modes, 'RKw'),
+ * delta_u (perturbation modes; input of 'RKe', output of both) and uinit are updated in place */
+int wb_dg1d_evolve_w(wb_dg1d* h, int integrator, double* u_inout, double* delta_u_inout, const double* u_eq_nodes,
+                     const double* u_eq_modes, double* uinit_inout, double tend, int max_iter, int* iters_out, double* t_out,
+                     double* last_dt_out);
 
 #ifdef __cplusplus
 }

@@ -574,3 +574,224 @@ void orc_dg1d_project(const orc_dg1d_params *p, const double *u_nodes, double *u
       for (int j = 0; j < n; ++j)
         for (int v = 0; v < NV; ++v) M3(u_modes, v, i, ic) = M3(u_modes, v, i, ic) + 0.5 * M3(u_nodes, v, j, ic) * B.P[j][i] * B.wq[j];
 }
+
+
+/* ==================================================================== 'RKw' / 'RKe': compute_update_exact, limiter_TDV,
+ * limiter_cons.  get_eq_solution :1031-1048 is w = (exp(-x), 0, exp(-x)). */
+static void eq_cons(double x, double *u, double gamma) {
+  double w[NV] = {exp(-x), 0, exp(-x)};
+  cons(w, u, gamma);
+}
+/* :1380-1744 compute_update_exact(u,u_eq,dudt): full-state modes `u`, equilibrium MODES `u_eq`.  Faces 1 and nx+1 read
+ * u_right(:,0) / u_left(:,nx+1) out of bounds; with bc = 4 or 5 that Riemann result is discarded and replaced by the
+ * physical flux of a boundary state (:1516-1620), with any other bc it would be used -> only bc 4, 5 are defined. */
+void orc_dg1d_compute_update_exact(const orc_dg1d_params *p, const double *u, const double *u_eq, double *dudt) {
+  const int n = p->n, nx = p->nx;
+  const double gamma = p->gamma;
+  basis1_t B; make_basis1(n, &B);
+  const double dx = p->boxlen / (double)nx, oneoverdx = 1. / dx;
+  double *u_face_eq = (double *)malloc(sizeof(double) * NV * (nx + 1)), *flux_face_eq = (double *)malloc(sizeof(double) * NV * (nx + 1));
+  double *flux_face = (double *)calloc(NV * (nx + 1), sizeof(double));
+  double *u_left = (double *)malloc(sizeof(double) * NV * nx), *u_right = (double *)malloc(sizeof(double) * NV * nx);
+  double *fv = (double *)calloc(NV * n * nx, sizeof(double)), *fve = (double *)calloc(NV * n * nx, sizeof(double));
+  double *sv = (double *)calloc(NV * n * nx, sizeof(double)), *sve = (double *)calloc(NV * n * nx, sizeof(double));
+  for (int i = 1; i <= nx + 1; ++i) {
+    eq_cons((double)(i - 1) * dx, u_face_eq + NV * (i - 1), gamma);
+    flux(u_face_eq + NV * (i - 1), flux_face_eq + NV * (i - 1), gamma);
+  }
+  for (int ic = 0; ic < nx; ++ic) {
+    double fq[MAXN][NV], fqe[MAXN][NV], sq[MAXN][NV], sqe[MAXN][NV];
+    for (int j = 0; j < n; ++j) {
+      double uq[NV] = {0, 0, 0}, uqe[NV] = {0, 0, 0};
+      for (int i = 0; i < n; ++i)
+        for (int v = 0; v < NV; ++v) {
+          uq[v] = uq[v] + M3(u, v, i, ic) * B.P[j][i];
+          uqe[v] = uqe[v] + M3(u_eq, v, i, ic) * B.P[j][i];
+        }
+      flux(uq, fq[j], gamma);
+      flux(uqe, fqe[j], gamma);
+      source_term(uq, sq[j], gamma);
+      source_term(uqe, sqe[j], gamma);
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        for (int v = 0; v < NV; ++v) {
+          M3(fv, v, i, ic) = M3(fv, v, i, ic) + fq[j][v] * B.dP[j][i] * B.wq[j];
+          M3(fve, v, i, ic) = M3(fve, v, i, ic) + fqe[j][v] * B.dP[j][i] * B.wq[j];
+          if (p->source == 2) {
+            M3(sv, v, i, ic) = M3(sv, v, i, ic) + sq[j][v] * B.P[j][i] * B.wq[j];
+            M3(sve, v, i, ic) = M3(sve, v, i, ic) + sqe[j][v] * B.P[j][i] * B.wq[j];
+          }
+        }
+    double dl[NV] = {0, 0, 0}, dr[NV] = {0, 0, 0}, uul[NV], uur[NV];
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        dl[v] = dl[v] + M3(u, v, i, ic) * B.Em[i];
+        dr[v] = dr[v] + M3(u, v, i, ic) * B.Ep[i];
+      }
+    eq_cons((double)(ic + 1) * dx, uur, gamma);      /* x_right = icell*dx */
+    eq_cons((double)ic * dx, uul, gamma);            /* x_left = (icell-1)*dx */
+    for (int v = 0; v < NV; ++v) {
+      u_left[NV * ic + v] = u_face_eq[NV * ic + v] + (dl[v] - uul[v]);
+      u_right[NV * ic + v] = u_face_eq[NV * (ic + 1) + v] + (dr[v] - uur[v]);
+    }
+  }
+  void (*rs)(const double *, const double *, double *, double) = (p->riemann == 1) ? riemann_llf : riemann_hllc;
+  for (int iface = 2; iface <= nx; ++iface) rs(u_right + NV * (iface - 2), u_left + NV * (iface - 1), flux_face + NV * (iface - 1), gamma);
+  {
+    double a[NV], b[NV], t[NV];
+    if (p->bc == 4) {
+      eq_cons((double)-0.5f * dx + dx / 2.0 * (double)(1), a, gamma);
+      eq_cons((double)0.5f * dx + dx / 2.0 * (double)(-1), b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + u_left[v] - b[v];
+      flux(t, flux_face, gamma);
+      eq_cons((double)((float)nx + 0.5f) * dx + dx / 2.0 * (double)(-1), a, gamma);
+      eq_cons((double)nx * dx, b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + u_right[NV * (nx - 1) + v] - b[v];
+      flux(t, flux_face + NV * nx, gamma);
+    } else {                                               /* bc 5 "mimic FVM": the MEAN MODE of the end cell (sic) */
+      eq_cons((double)-0.5f * dx, a, gamma);
+      eq_cons((double)0.5f * dx, b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + M3(u, v, 0, 0) - b[v];
+      flux(t, flux_face, gamma);
+      eq_cons((double)((float)nx + 0.5f) * dx, a, gamma);
+      eq_cons((double)((float)nx - 0.5f) * dx, b, gamma);
+      for (int v = 0; v < NV; ++v) t[v] = a[v] + M3(u, v, 0, nx - 1) - b[v];
+      flux(t, flux_face + NV * nx, gamma);
+    }
+  }
+  for (int ic = 0; ic < nx; ++ic)
+    for (int i = 0; i < n; ++i)
+      for (int v = 0; v < NV; ++v)
+        M3(dudt, v, i, ic) = oneoverdx * M3(fv, v, i, ic) - oneoverdx * M3(fve, v, i, ic)
+                             - oneoverdx * (flux_face[NV * (ic + 1) + v] * B.Ep[i] - flux_face[NV * ic + v] * B.Em[i])
+                             + oneoverdx * (flux_face_eq[NV * (ic + 1) + v] * B.Ep[i] - flux_face_eq[NV * ic + v] * B.Em[i])
+                             + M3(sv, v, i, ic) - M3(sve, v, i, ic);
+  free(u_face_eq); free(flux_face_eq); free(flux_face); free(u_left); free(u_right); free(fv); free(fve); free(sv); free(sve);
+}
+
+/* :520-600 limiter_TDV(u).  Its moment-limiting block indexes the neighbours with the loop variable of ANOTHER loop
+ * (`u(1:nvar,1,i-1)`, :550-552: undefined behaviour), so only use_limiter = .false. (the shipped value) is defined:
+ * what remains is the positivity fallback on the TRACES of the conserved variables (no cons_to_prim here). */
+void orc_dg1d_limiter_tdv(const orc_dg1d_params *p, double *u) {
+  const int n = p->n, nx = p->nx;
+  if (n == 1) return;
+  for (int ic = 0; ic < nx; ++ic) {
+    double ul[NV] = {0, 0, 0}, ur[NV] = {0, 0, 0};
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        ul[v] = ul[v] + M3(u, v, i - 1, ic) * pow((double)-1.0f, i - 1) * sqrt(2.0 * (double)i - 1.0);
+        ur[v] = ur[v] + M3(u, v, i - 1, ic) * sqrt(2.0 * (double)i - 1.0);
+      }
+    if (ul[0] < 1e-10 || ur[0] < 1e-10 || ul[2] < 1e-10 || ul[2] < 1e-10)
+      for (int i = 1; i < n; ++i) for (int v = 0; v < NV; ++v) M3(u, v, i, ic) = 0.0;
+  }
+}
+
+/* :602-734 limiter_cons(u): the moment limiter of limiter() applied to the conserved moments directly */
+void orc_dg1d_limiter_cons(const orc_dg1d_params *p, double *u) {
+  const int n = p->n, nx = p->nx;
+  const double gamma = p->gamma;
+  if (n == 1) return;
+  size_t N = (size_t)NV * n * nx;
+  double *ul = (double *)malloc(sizeof(double) * N);
+  memcpy(ul, u, sizeof(double) * N);
+  if (p->use_limiter) {
+    for (int ic = 1; ic <= nx; ++ic) {
+      int ileft = ic - 1, iright = ic + 1;
+      double switch_left = 1.0, switch_right = 1.0;
+      if (p->bc == 1) { if (ic == 1) ileft = nx; if (ic == nx) iright = 1; }
+      if (p->bc == 2 || p->bc == 4) { if (ic == 1) ileft = 1; if (ic == nx) iright = nx; }
+      if (p->bc == 3) { if (ic == 1) { ileft = 1; switch_left = -1.0; } if (ic == nx) { iright = nx; switch_right = -1.0; } }
+      if (ileft < 1 || iright > nx) continue;        /* bc 5: out of bounds in the reference */
+      double wL[MAXN][NV], wM[MAXN][NV], wR[MAXN][NV], w_lim[MAXN][NV];
+      for (int i = n - 1; i >= 1; --i) {
+        double coeff_i = sqrt(2.0 * (double)(i - 1) + 1.0) * (2.0 * (double)i - 1);
+        double coeff_ip1 = sqrt(2.0 * (double)i + 1.0) * (2.0 * (double)i - 1);
+        for (int v = 0; v < NV; ++v) {
+          wL[i][v] = (M3(u, v, i - 1, ic - 1) - M3(u, v, i - 1, ileft - 1)) * coeff_i / coeff_ip1;
+          wR[i][v] = (M3(u, v, i - 1, iright - 1) - M3(u, v, i - 1, ic - 1)) * coeff_i / coeff_ip1;
+          wM[i][v] = M3(u, v, i, ic - 1);
+        }
+        wL[i][1] = switch_left * wL[i][1];
+        wR[i][1] = switch_right * wR[i][1];
+      }
+      for (int i = 1; i < n; ++i) for (int v = 0; v < NV; ++v) w_lim[i][v] = wM[i][v];
+      for (int v = 0; v < NV; ++v)
+        for (int i = n - 1; i >= 1; --i) {
+          double w_min = minmod3(wL[i][v], wM[i][v], wR[i][v]);
+          w_lim[i][v] = w_min;
+          if (fabs(w_min - wM[i][v]) < (double)0.01f * fabs(wM[i][v])) break;
+        }
+      for (int i = n - 1; i >= 1; --i) for (int v = 0; v < NV; ++v) M3(ul, v, i, ic - 1) = w_lim[i][v];
+    }
+  }
+  for (int ic = 0; ic < nx; ++ic) {
+    double w[NV], u_left[NV] = {0, 0, 0}, u_right[NV] = {0, 0, 0}, w_left[NV], w_right[NV];
+    prim(&M3(ul, 0, 0, ic), w, gamma);
+    for (int i = 1; i <= n; ++i)
+      for (int v = 0; v < NV; ++v) {
+        u_left[v] = u_left[v] + M3(ul, v, i - 1, ic) * pow((double)-1.0f, i - 1) * sqrt(2.0 * (double)i - 1.0);
+        u_right[v] = u_right[v] + M3(ul, v, i - 1, ic) * sqrt(2.0 * (double)i - 1.0);
+      }
+    cons_to_prim(u_left, w_left, w, gamma);
+    cons_to_prim(u_right, w_right, w, gamma);
+    if (w_left[0] < 1e-10 || w_right[0] < 1e-10 || w_left[2] < 1e-10 || w_left[2] < 1e-10)
+      for (int i = 1; i < n; ++i) for (int v = 0; v < NV; ++v) M3(ul, v, i, ic) = 0.0;
+  }
+  memcpy(u, ul, sizeof(double) * N);
+  free(ul);
+}
+
+/* main loop :173-336 with integrator 'RKw' (5, :229-270: SSPRK(5,4) on the full state, limiter_TDV on u - u_eq_modes
+ * after every stage; delta_u ends as u - u_eq_modes and feeds `uinit`) or 'RKe' (6, :273-280: RK2 on the perturbation
+ * with limiter_cons; u_eq are the NODAL equilibrium values as in 'RKi'). */
+void orc_dg1d_evolve_w(const orc_dg1d_params *p, int integrator, double *u, double *delta_u, const double *u_eq_nodes,
+                       const double *u_eq_modes, double *uinit, double tend, int max_iter, int *iters, double *t_out, double *dt_out) {
+  const size_t N = (size_t)NV * p->n * p->nx;
+  const double dx = p->boxlen / (double)p->nx;
+  double *dudt = (double *)malloc(sizeof(double) * N), *w1 = (double *)malloc(sizeof(double) * N), *w2 = (double *)malloc(sizeof(double) * N);
+  double *w3 = (double *)malloc(sizeof(double) * N), *w4 = (double *)malloc(sizeof(double) * N);
+  double t = 0, dt = 0, cmax;
+  int iter = 0;
+  const double *q = u_eq_modes;
+#define LIM_W(w) do { for (size_t k = 0; k < N; ++k) delta_u[k] = (w)[k] - q[k]; orc_dg1d_limiter_tdv(p, delta_u); \
+                      for (size_t k = 0; k < N; ++k) (w)[k] = q[k] + delta_u[k]; } while (0)
+  while (t < tend && (max_iter < 0 || iter < max_iter)) {
+    orc_dg1d_compute_max_speed(p, uinit, &cmax);
+    dt = (double)0.9f * dx / cmax / (2.0 * (double)p->n + 1.0);
+    if (integrator == 5) {
+      orc_dg1d_compute_update_exact(p, u, q, dudt);
+      for (size_t k = 0; k < N; ++k) w1[k] = u[k] + F32(0.391752226571890) * dt * dudt[k];
+      LIM_W(w1);
+      orc_dg1d_compute_update_exact(p, w1, q, dudt);
+      for (size_t k = 0; k < N; ++k) w2[k] = F32(0.444370493651235) * u[k] + F32(0.555629506348765) * w1[k] + F32(0.368410593050371) * dt * dudt[k];
+      LIM_W(w2);
+      orc_dg1d_compute_update_exact(p, w2, q, dudt);
+      for (size_t k = 0; k < N; ++k) w3[k] = F32(0.620101851488403) * u[k] + F32(0.379898148511597) * w2[k] + F32(0.251891774271694) * dt * dudt[k];
+      LIM_W(w3);
+      orc_dg1d_compute_update_exact(p, w3, q, dudt);
+      for (size_t k = 0; k < N; ++k) w4[k] = F32(0.178079954393132) * u[k] + F32(0.821920045606868) * w3[k] + F32(0.544974750228521) * dt * dudt[k];
+      for (size_t k = 0; k < N; ++k) u[k] = F32(0.517231671970585) * w2[k] + F32(0.096059710526147) * w3[k] + F32(0.063692468666290) * dt * dudt[k];
+      LIM_W(w4);                                                     /* :262 writes delta_u + u_eq_modes: the sum commutes */
+      orc_dg1d_compute_update_exact(p, w4, q, dudt);
+      for (size_t k = 0; k < N; ++k) u[k] = u[k] + F32(0.386708617503269) * w4[k] + F32(0.226007483236906) * dt * dudt[k];
+      LIM_W(u);
+    } else {
+      orc_dg1d_compute_update_exact_delta(p, delta_u, u_eq_nodes, dudt);
+      orc_dg1d_limiter_cons(p, delta_u);
+      for (size_t k = 0; k < N; ++k) w1[k] = delta_u[k] + dt * dudt[k];
+      orc_dg1d_compute_update_exact_delta(p, w1, u_eq_nodes, dudt);
+      orc_dg1d_limiter_cons(p, w1);
+      for (size_t k = 0; k < N; ++k) delta_u[k] = 0.5 * delta_u[k] + 0.5 * w1[k] + 0.5 * dt * dudt[k];
+    }
+    orc_dg1d_reconstruct(p, delta_u, u_eq_nodes, uinit);
+    t = t + dt;
+    iter = iter + 1;
+  }
+#undef LIM_W
+  if (iters) *iters = iter;
+  if (t_out) *t_out = t;
+  if (dt_out) *dt_out = dt;
+  free(dudt); free(w1); free(w2); free(w3); free(w4);
+}

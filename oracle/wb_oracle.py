@@ -402,3 +402,29 @@ def dg1d_evolve_rk(p, integrator, u, delta_u, u_eq, uinit, tend, max_iter=-1):
     lib().orc_dg1d_evolve_rk(C.byref(p), C.c_int(INTEGRATORS_1D[integrator]), _ptr(uu), _ptr(delta_u), _ptr(u_eq), _ptr(ui),
                              C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt))
     return uu, ui, it.value, t.value, dt.value
+
+
+def dg1d_compute_update_exact(p, u, u_eq_modes):
+    d = np.empty_like(u)
+    lib().orc_dg1d_compute_update_exact(C.byref(p), _ptr(u), _ptr(u_eq_modes), _ptr(d))
+    return d
+
+
+def dg1d_limiter_tdv(p, u):
+    v = np.array(u, copy=True)
+    lib().orc_dg1d_limiter_tdv(C.byref(p), _ptr(v))
+    return v
+
+
+def dg1d_limiter_cons(p, u):
+    v = np.array(u, copy=True)
+    lib().orc_dg1d_limiter_cons(C.byref(p), _ptr(v))
+    return v
+
+
+def dg1d_evolve_w(p, integrator, u, delta_u, u_eq_nodes, u_eq_modes, uinit, tend, max_iter=-1):
+    uu = np.array(u, copy=True); dd = np.array(delta_u, copy=True); ui = np.array(uinit, copy=True)
+    it = C.c_int(); t = C.c_double(); dt = C.c_double()
+    lib().orc_dg1d_evolve_w(C.byref(p), C.c_int({"RKw": 5, "RKe": 6}[integrator]), _ptr(uu), _ptr(dd), _ptr(u_eq_nodes),
+                            _ptr(u_eq_modes), _ptr(ui), C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt))
+    return uu, dd, ui, it.value, t.value, dt.value

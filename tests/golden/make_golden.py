@@ -129,6 +129,29 @@ def dg1d():
         u2, ui2, it, t, dt = o.dg1d_evolve_rk(p, f"RK{integ}", u, du, ueq, ui, 1.0, steps)
         out[f"{tag}_u2"] = u2; out[f"{tag}_ui2"] = ui2; out[f"{tag}_pclock"] = np.array([it, t, dt])
         assert np.all(np.isfinite(u2)), tag
+    # 'RKw' / 'RKe': compute_update_exact, limiter_TDV, limiter_cons (dg_with_source.f90:1380-1744, :520-734, :229-280)
+    for tag, n, nx, riemann, source, bc, use_limiter, integ, steps, ninit, pert in (
+            ("rkw_default_bc5", 3, 64, 2, 2, 5, 0, 5, 3, 8, 1e-3), ("rkw_llf_bc4", 2, 40, 1, 2, 4, 0, 5, 3, 8, 1e-2),
+            ("rke_bc5", 3, 64, 2, 2, 5, 0, 6, 4, 8, 1e-3), ("rke_lim_bc2", 3, 48, 1, 2, 2, 1, 6, 3, 8, 1e-2),
+            ("rke_o1", 1, 32, 2, 2, 5, 0, 6, 3, 8, 1e-2)):
+        p = o.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, ninit=ninit, pert=pert, bc=bc, use_limiter=use_limiter)
+        ui, ueq, du = o.dg1d_setup(p)
+        u = o.dg1d_project(p, ui); q = o.dg1d_project(p, ueq)
+        lin = u.copy()
+        if n > 1:
+            lin[:, 1:, :] += 1e-3 * rng.standard_normal(lin[:, 1:, :].shape)
+            lin[3, 1, 0] = 5.0                                                 # a cell with a negative density trace
+        out[f"{tag}_wmeta"] = np.array([n, nx, riemann, source, bc, use_limiter, integ, steps])
+        out[f"{tag}_u"] = u; out[f"{tag}_du"] = du; out[f"{tag}_ueq"] = ueq; out[f"{tag}_q"] = q; out[f"{tag}_ui"] = ui
+        out[f"{tag}_lin"] = lin
+        if bc in (4, 5):
+            out[f"{tag}_dudt"] = o.dg1d_compute_update_exact(p, u, q)
+        out[f"{tag}_lcons"] = o.dg1d_limiter_cons(p, lin)
+        if not use_limiter:
+            out[f"{tag}_ltdv"] = o.dg1d_limiter_tdv(p, lin)
+        uu, dd, ui2, it, t, dt = o.dg1d_evolve_w(p, "RKw" if integ == 5 else "RKe", u, du, ueq, q, ui, 1.0, steps)
+        out[f"{tag}_u2"] = uu; out[f"{tag}_du2"] = dd; out[f"{tag}_ui2"] = ui2; out[f"{tag}_wclock"] = np.array([it, t, dt])
+        assert np.all(np.isfinite(uu)) and np.all(np.isfinite(dd)), tag
     np.savez_compressed(os.path.join(HERE, "dg1d.npz"), **out)
 
 

@@ -119,3 +119,47 @@ def test_limiter_flattens_cells_with_negative_traces(wb, oracle):
     with wb.DG1D(n=3, nx=64, bc=1, use_limiter=False) as s:
         v = s.limiter(u)
     assert np.array_equal(v, oracle.dg1d_limiter(p, u)) and np.all(v[10, 1:] == 0)
+
+
+# ---------------------------------------------------------------- 'RKw' / 'RKe'
+def _w_cases():
+    g = np.load(GOLD)
+    return [k[:-6] for k in g.files if k.endswith("_wmeta")]
+
+
+@pytest.mark.parametrize("tag", _w_cases())
+def test_w_paths_match_oracle_and_golden(wb, oracle, tag):
+    """compute_update_exact (:1380-1744), limiter_TDV / limiter_cons (:520-734) and the 'RKw' / 'RKe' main loops (:229-280):
+    reference operation order on the device; differences come from exp() in the face equilibria alone."""
+    g = np.load(GOLD)
+    n, nx, riemann, source, bc, use_limiter, integ, steps = (int(v) for v in g[f"{tag}_wmeta"])
+    u, du, ueq, q, ui = g[f"{tag}_u"], g[f"{tag}_du"], g[f"{tag}_ueq"], g[f"{tag}_q"], g[f"{tag}_ui"]
+    scale = max(np.abs(u).max(), 1.0)
+    dt = float(g[f"{tag}_wclock"][2])
+    with wb.DG1D(n=n, nx=nx, riemann=riemann, source=source, bc=bc, use_limiter=bool(use_limiter)) as s:
+        if bc in (4, 5):
+            d = s.compute_update_exact(u, q)
+            assert np.abs(dt * (d - g[f"{tag}_dudt"])).max() <= TOL * scale, tag
+        else:
+            with pytest.raises(wb.WBError):
+                s.compute_update_exact(u, q)
+        assert np.array_equal(s.limiter_cons(g[f"{tag}_lin"]), g[f"{tag}_lcons"]), tag
+        if not use_limiter:
+            assert np.array_equal(s.limiter_TDV(g[f"{tag}_lin"]), g[f"{tag}_ltdv"]), tag
+        else:
+            with pytest.raises(wb.WBError):
+                s.limiter_TDV(g[f"{tag}_lin"])
+        uu, dd, ui2, it, t, dtl = s.evolve_w("RKw" if integ == 5 else "RKe", u, du, ueq, q, ui, 1.0, steps)
+    assert it == int(g[f"{tag}_wclock"][0]) and abs(t - g[f"{tag}_wclock"][1]) <= 1e-14 * t, tag
+    assert np.abs(uu - g[f"{tag}_u2"]).max() <= TOL * scale, tag
+    assert np.abs(dd - g[f"{tag}_du2"]).max() <= TOL * scale, tag
+    assert np.abs(ui2 - g[f"{tag}_ui2"]).max() <= TOL * np.abs(g[f"{tag}_ui2"]).max(), tag
+
+
+def test_rke_keeps_the_discrete_steady_state(wb, oracle):
+    p = oracle.dg1d_params(n=3, nx=64, riemann=1, source=2, ninit=7, bc=5)
+    ui, ueq, du = oracle.dg1d_setup(p)
+    u, q = oracle.dg1d_project(p, ui), oracle.dg1d_project(p, ueq)
+    with wb.DG1D(n=3, nx=64, riemann=1, source=2, bc=5) as s:
+        uu, dd, ui2, it, t, dt = s.evolve_w("RKe", u, du, ueq, q, ui, 0.05)
+    assert it > 20 and np.all(dd == 0.0) and np.array_equal(ui2, ueq)

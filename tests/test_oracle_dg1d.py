@@ -216,3 +216,88 @@ def test_golden_vectors_plain_paths(oracle):
         u2, ui2, it, t, dt = oracle.dg1d_evolve_rk(p, f"RK{integ}", u, du, ueq, ui, 1.0, steps)
         assert np.array_equal(u2, g[f"{tag}_u2"]) and np.array_equal(ui2, g[f"{tag}_ui2"]), tag
         assert np.array_equal(np.array([it, t, dt]), g[f"{tag}_pclock"]), tag
+
+
+# ---------------------------------------------------------------- 'RKw' / 'RKe': compute_update_exact, limiter_TDV, limiter_cons
+def _w_setup(oracle, **kw):
+    p = oracle.dg1d_params(**kw)
+    ui, ueq, du = oracle.dg1d_setup(p)
+    return p, ui, ueq, du, oracle.dg1d_project(p, ui), oracle.dg1d_project(p, ueq)
+
+
+def test_update_exact_interior_is_independent_of_the_end_treatment(oracle):
+    """compute_update_exact (:1380-1744): bc 4 and bc 5 differ only in the boundary states that replace the out-of-bounds
+    Riemann problems of faces 1 and nx+1 (:1516-1620) -> every cell but the two end cells gets the same dudt, bit for bit."""
+    out = {}
+    for bc in (4, 5):
+        p, ui, ueq, du, u, q = _w_setup(oracle, n=3, nx=48, riemann=2, source=2, ninit=8, pert=1e-3, bc=bc)
+        out[bc] = oracle.dg1d_compute_update_exact(p, u, q)
+        assert np.all(np.isfinite(out[bc]))
+    assert np.array_equal(out[4][1:-1], out[5][1:-1])
+    assert not np.array_equal(out[4][0], out[5][0]) and not np.array_equal(out[4][-1], out[5][-1])
+
+
+def test_update_exact_volume_and_source_terms_cancel_at_u_equal_u_eq(oracle):
+    """With u == u_eq_modes the volume and source integrals of the state and of the equilibrium are the same numbers, so
+    dudt is the face part alone.  As shipped that part does NOT vanish: the modes carry Teyssier's 0.5 projection factor
+    (traces = half the state) while flux_face_eq is the flux of the full equilibrium (:1411-1416), so the
+    mean mode of an interior cell is left with (1/dx) * P0 * 0.5 * (p(x_right) - p(x_left)) ~ -0.5 P0 exp(-x):
+    'RKw' is not well balanced in the reference, which is why 'RKi' is its default."""
+    p, ui, ueq, du, u, q = _w_setup(oracle, n=3, nx=64, riemann=1, source=2, ninit=7, bc=5)
+    d = oracle.dg1d_compute_update_exact(p, q, q)
+    dx = 1.0 / 64
+    xl = np.arange(64) * dx
+    expect = 0.5 * 0.7071067690849304 * (np.exp(-(xl + dx)) - np.exp(-xl)) / dx
+    assert np.allclose(d[1:-1, 0, 1], expect[1:-1], rtol=2e-6)            # momentum equation, mean mode
+    assert np.abs(d[1:-1, 0, 0]).max() < 1e-6 * np.abs(d[1:-1, 0, 1]).max() + 1e-7   # mass: only LLF dissipation of the jump
+
+
+def test_limiter_tdv_and_cons_positivity_parts(oracle):
+    p = oracle.dg1d_params(n=3, nx=32, bc=5, use_limiter=0)
+    rng = np.random.default_rng(4)
+    u = np.zeros((32, 3, 3)); u[:, 0, 0] = 1.0; u[:, 0, 2] = 2.5
+    u[:, 1:, :] = 0.01 * rng.standard_normal((32, 2, 3))
+    assert np.array_equal(oracle.dg1d_limiter_tdv(p, u), u)                      # positive traces: untouched
+    bad = u.copy(); bad[7, 1, 0] = 5.0; bad[20, 1, 2] = 30.0                      # negative density / energy trace on the left
+    v = oracle.dg1d_limiter_tdv(p, bad)
+    for c in (7, 20):
+        assert np.all(v[c, 1:] == 0) and np.array_equal(v[c, 0], bad[c, 0])
+    assert np.array_equal(np.delete(v, (7, 20), axis=0), np.delete(bad, (7, 20), axis=0))
+    # limiter_cons without the moment part is the positivity fallback of limiter() (the same lines, :480-517 / :715-732)
+    assert np.array_equal(oracle.dg1d_limiter_cons(p, bad), oracle.dg1d_limiter(p, bad))
+    p1 = oracle.dg1d_params(n=3, nx=32, bc=2, use_limiter=1)
+    w = oracle.dg1d_limiter_cons(p1, u)
+    assert np.array_equal(w[:, 0], u[:, 0]) and np.all(np.abs(w[:, 1:]) <= np.abs(u[:, 1:]) + 1e-300)   # minmod never grows a moment
+
+
+def test_rke_keeps_the_discrete_steady_state_and_rkw_runs_as_shipped(oracle):
+    p, ui, ueq, du, u, q = _w_setup(oracle, n=3, nx=64, riemann=1, source=2, ninit=7, bc=5)
+    uu, dd, ui2, it, t, dt = oracle.dg1d_evolve_w(p, "RKe", u, du, ueq, q, ui, 0.05)
+    assert it > 20 and np.all(dd == 0.0) and np.array_equal(ui2, ueq)            # delta-form + LLF: exactly steady
+    p, ui, ueq, du, u, q = _w_setup(oracle, n=3, nx=64, riemann=2, source=2, ninit=8, pert=1e-3, bc=5)
+    c = oracle.dg1d_compute_max_speed(p, ui)
+    uu, dd, ui2, it, t, dt = oracle.dg1d_evolve_w(p, "RKw", u, du, ueq, q, ui, 1.0, 1)
+    assert it == 1 and dt == f32(0.9) * (1.0 / 64) / c / 7.0 and np.all(np.isfinite(uu))
+    # the limiter acts on u - u_eq_modes: what comes back as delta_u is exactly that difference or its flattened version
+    diff = uu - q
+    same = np.isclose(dd, diff, rtol=0, atol=1e-15).all(axis=(1, 2))
+    flat = (dd[:, 1:] == 0).all(axis=(1, 2))
+    assert np.all(same | flat)
+
+
+def test_golden_vectors_w_paths(oracle):
+    g = np.load(GOLD)
+    tags = [k[:-6] for k in g.files if k.endswith("_wmeta")]
+    assert tags
+    for tag in tags:
+        n, nx, riemann, source, bc, use_limiter, integ, steps = (int(v) for v in g[f"{tag}_wmeta"])
+        p = oracle.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, bc=bc, use_limiter=use_limiter)
+        u, du, ueq, q, ui = g[f"{tag}_u"], g[f"{tag}_du"], g[f"{tag}_ueq"], g[f"{tag}_q"], g[f"{tag}_ui"]
+        if bc in (4, 5):
+            assert np.array_equal(oracle.dg1d_compute_update_exact(p, u, q), g[f"{tag}_dudt"]), tag
+        assert np.array_equal(oracle.dg1d_limiter_cons(p, g[f"{tag}_lin"]), g[f"{tag}_lcons"]), tag
+        if not use_limiter:
+            assert np.array_equal(oracle.dg1d_limiter_tdv(p, g[f"{tag}_lin"]), g[f"{tag}_ltdv"]), tag
+        uu, dd, ui2, it, t, dt = oracle.dg1d_evolve_w(p, "RKw" if integ == 5 else "RKe", u, du, ueq, q, ui, 1.0, steps)
+        assert np.array_equal(uu, g[f"{tag}_u2"]) and np.array_equal(dd, g[f"{tag}_du2"]) and np.array_equal(ui2, g[f"{tag}_ui2"]), tag
+        assert np.array_equal(np.array([it, t, dt]), g[f"{tag}_wclock"]), tag
