@@ -138,6 +138,31 @@ template <int M>
 __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis& B, double (&el)[4][M][M]) {
   if (M == 1) return;
   const double ua[4] = {el[0][0][0], el[1][0][0], el[2][0][0], el[3][0][0]};
+  // ---- cheap sufficient test.  |P_i| <= P_i(1) = sqrt(2i+1) on [-1,1], so every point value of variable v lies within
+  //      R_v = sum_{(i,j) != (0,0)} |mode_ij| P_i(1) P_j(1) of its mean.  If the resulting lower bounds of the density and of
+  //      the pressure stay above eps (with a margin far above the rounding of the point evaluations), every point of the
+  //      set gives theta = 1 and t = 1 exactly and the limiter leaves the element untouched -- the common case on
+  //      resolved data, ~60 instead of ~1400 FP64 instructions.
+  {
+    double R[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double r = 0.0;
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+          if (i != 0 || j != 0) r = fma(fabs(el[v][i][j]), B.Ep[i] * B.Ep[j], r);
+      R[v] = r;
+    }
+    const double rho_lo = ua[0] - R[0];
+    const double mx_hi = fabs(ua[1]) + R[1], my_hi = fabs(ua[2]) + R[2], E_lo = ua[3] - R[3];
+    const double margin = 1e-9 * (fabs(ua[0]) + R[0] + fabs(ua[3]) + R[3]);
+    if (rho_lo > P.eps + margin && rho_lo > (double)10e-10f) {
+      const double p_lo = P.gm1a * (E_lo - 0.5 * (mx_hi * mx_hi + my_hi * my_hi) / rho_lo);
+      if (p_lo > P.eps + margin) return;
+    }
+  }
   double p_min = 1e300;
   for (int q = 0; q < M; ++q)
     for (int r = 0; r < B.gll; ++r) {
