@@ -822,6 +822,7 @@ __global__ void k_dg_ctrl_init(DgCtrl* ctrl, double tend, int max_iter, int rese
 }}  // namespace wb::dg
 
 #include "dg2d_fast.cuh"
+#include "dg2d_tma.cuh"
 
 // ============================================================================================ host side
 using namespace wb;
@@ -852,6 +853,10 @@ struct wb_dg2d {
   wb::Nccl* comm = nullptr;
   double *sbuf_lo = nullptr, *sbuf_hi = nullptr, *rbuf_lo = nullptr, *rbuf_hi = nullptr, *red = nullptr;
   int rank = 0, nranks = 1, nyl = 0;
+  // TMA-staged stage kernel: one 3-D tensor map (column, row, plane) per state buffer
+  bool tma_ok = false;
+  const double* map_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  CUtensorMap map[4];
 };
 
 namespace {
@@ -1022,6 +1027,30 @@ int dg_axpy(wb_dg2d* h, int na, double* out, const double* A0, double c0, const 
   return WB_OK;
 }
 
+// 3-D tensor map (column, local row, plane) of a state buffer for k_dg_stage_tma
+int dg_make_map(const wb_dg2d* h, const double* base, CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    WB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return WB_ERR_CUDA; }
+    encode = (encode_fn)fn;
+  }
+  const DgGrid& g = h->g;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)(4 * g.nm)};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.nx * sizeof(double), (cuuint64_t)g.ne * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)DGT_W, 1u, (cuuint32_t)(4 * g.nm)};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return WB_ERR_CUDA; }
+  return WB_OK;
+}
+
 // one fused launch: out = limiter(c0*A0 + c1*A1 + cd*dt*L(in)) [+ the optional second combination]
 int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, double c0, const double* A1, double c1, double cd,
                   double* out2 = nullptr, const double* B0 = nullptr, double k0 = 0, const double* B1 = nullptr, double k1 = 0,
@@ -1030,9 +1059,28 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   C.A0 = A0; C.A1 = A1; C.c0 = c0; C.c1 = c1; C.cd = cd; C.na = A1 ? 2 : 1;
   C.out2 = out2; C.B0 = B0; C.B1 = B1; C.k0 = k0; C.k1 = k1; C.k2 = k2; C.k3 = k3; C.ke = ke;
   const int onp = (h->prm.limiter_id == 1 && h->g.m > 1) ? 1 : 0;
-  dim3 b(64), gr = elem_grid(h, 64);
-  DISPATCH_M(h, k_dg_stage_fast<MM><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
-                                                           h->phys, h->FB, h->ctrl, onp));
+  const CUtensorMap* m_in = nullptr;
+  if (h->tma_ok)
+    for (int k = 0; k < 4; ++k)
+      if (h->map_ptr[k] == in) m_in = &h->map[k];
+  if (m_in) {
+    dim3 b(32), gr((unsigned)(h->g.ne / 32));
+    DISPATCH_M(h, {
+      auto kern = k_dg_stage_tma<MM>;
+      static bool configured = false;
+      if (!configured) {
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
+        configured = true;
+      }
+      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+                                                          h->phys, h->FB, h->ctrl, onp);
+    });
+  } else {
+    dim3 b(64), gr = elem_grid(h, 64);
+    DISPATCH_M(h, k_dg_stage_fast<MM><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+                                                             h->phys, h->FB, h->ctrl, onp));
+  }
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_exchange(h, out));
   if (out2) WB_CHECK(dg_exchange(h, out2));
@@ -1217,6 +1265,18 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
     cudaMemsetAsync(h->fz, 0, (size_t)g.nm * g.ne, h->stream);
   }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
+  {      // TMA-staged stage kernel: blocks of 32 elements must lie in one row
+    const char* env = getenv("WB_DG2D_TMA");
+    if (p->arith == 0 && g.nx % 32 == 0 && g.nx >= DGT_W && !(env && atoi(env) == 0)) {
+      const double* bufs4[4] = {h->du, h->A, h->Bf, h->C};
+      for (int k = 0; k < 4; ++k) {
+        int st = dg_make_map(h, bufs4[k], &h->map[k]);
+        if (st != WB_OK) return fail(st);
+        h->map_ptr[k] = bufs4[k];
+      }
+      h->tma_ok = true;
+    }
+  }
   *out = h;
   return WB_OK;
 }

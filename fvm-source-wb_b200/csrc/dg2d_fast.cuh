@@ -206,9 +206,11 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
 // local Lax-Friedrichs at the M face points, and the edge integral accumulated into acc with its sign:
 //   x faces: -/+ E[a] * sum_q F[q] Pw[q][b]        y faces: -/+ E[b] * sum_q G[q] Pw[q][a]
 // FACE 0 left, 1 right, 2 bottom, 3 top.  Each face is evaluated by both adjacent elements (no inter-thread traffic).
-template <int M, int FACE>
-__device__ __forceinline__ void face_term(const double* __restrict__ in, const DgGrid& g, const DgPhys& P, const FastBasis& B,
-                                          const double (&d)[4][M][M], size_t eN, double (&acc)[4][M][M]) {
+// `src.template nb<FACE>(v, dn)` delivers the modes of variable v of the neighbour across the face (global memory or the
+// TMA-staged shared-memory rows, see the two sources below).
+template <int M, int FACE, class Src>
+__device__ __forceinline__ void face_term(Src& src, const DgPhys& P, const FastBasis& B, const double (&d)[4][M][M],
+                                          double (&acc)[4][M][M]) {
   constexpr int SIDE_OWN = FACE;                                   // own trace on that side
   constexpr int SIDE_NB = (FACE == 0) ? 1 : (FACE == 1) ? 0 : (FACE == 2) ? 3 : 2;   // neighbour's facing side
   double to[M][4], tn[M][4];
@@ -218,7 +220,7 @@ __device__ __forceinline__ void face_term(const double* __restrict__ in, const D
     trace1<M, SIDE_OWN>(d[v], B, t1);
 #pragma unroll
     for (int q = 0; q < M; ++q) to[q][v] = t1[q];
-    load_var<M>(in, g, v, eN, dn);
+    src.template nb<FACE>(v, dn);
     trace1<M, SIDE_NB>(dn, B, t1);
 #pragma unroll
     for (int q = 0; q < M; ++q) tn[q][v] = t1[q];
@@ -256,32 +258,42 @@ __device__ __forceinline__ void face_term(const double* __restrict__ in, const D
   }
 }
 
+// neighbour modes straight from global memory (L1/L2): the original data path
 template <int M>
-__global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
-                                                      const double* __restrict__ gx, const double* __restrict__ gy,
-                                                      const unsigned char* __restrict__ fz, DgGrid g, DgPhys P, FastBasis B,
-                                                      const DgCtrl* __restrict__ ctrl, int apply_onp) {
-  if (ctrl->skip) return;
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.ne) return;
-  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+struct GlobalSrc {
+  const double* __restrict__ in;
+  const DgGrid& g;
+  size_t e, eN[4];
+  __device__ __forceinline__ void own(int v, double (&d)[M][M]) const { load_var<M>(in, g, v, e, d); }
+  template <int FACE>
+  __device__ __forceinline__ void nb(int v, double (&d)[M][M]) const { load_var<M>(in, g, v, eN[FACE], d); }
+  __device__ __forceinline__ void x_faces_done() const {}
+};
+
+// One element of one RK stage (everything but where the modes come from).
+template <int M, class Src>
+__device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict__ in, const StageCoef& C, double* __restrict__ out,
+                                              const double* __restrict__ gx, const double* __restrict__ gy,
+                                              const unsigned char* __restrict__ fz, const DgGrid& g, const DgPhys& P,
+                                              const FastBasis& B, const DgCtrl* __restrict__ ctrl, int apply_onp, size_t e) {
   double acc[4][M][M];                     // -(e1-e2) - (e3-e4) + vol1 + vol2, then dudt, then the stage result
   double U[4][M][M];                       // nodal values -> nodal source -> out2 partial
   {
     double d[4][M][M];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      load_var<M>(in, g, v, e, d[v]);
+      src.own(v, d[v]);
 #pragma unroll
       for (int a = 0; a < M; ++a)
 #pragma unroll
         for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
     }
     // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
-    face_term<M, 0>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), acc);
-    face_term<M, 1>(in, g, P, B, d, (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg), acc);
-    face_term<M, 2>(in, g, P, B, d, (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, acc);
-    face_term<M, 3>(in, g, P, B, d, (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic, acc);
+    face_term<M, 0>(src, P, B, d, acc);
+    face_term<M, 1>(src, P, B, d, acc);
+    src.x_faces_done();
+    face_term<M, 2>(src, P, B, d, acc);
+    face_term<M, 3>(src, P, B, d, acc);
     // ---- nodal values (sum-factorised)
 #pragma unroll
     for (int v = 0; v < 4; ++v)
@@ -417,6 +429,21 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
     for (int b = 0; b < M; ++b)
 #pragma unroll
       for (int a = 0; a < M; ++a) PL(out, g, v, b * M + a)[e] = acc[v][a][b];
+}
+
+template <int M>
+__global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
+                                                      const double* __restrict__ gx, const double* __restrict__ gy,
+                                                      const unsigned char* __restrict__ fz, DgGrid g, DgPhys P, FastBasis B,
+                                                      const DgCtrl* __restrict__ ctrl, int apply_onp) {
+  if (ctrl->skip) return;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  GlobalSrc<M> src{in, g, e,
+                   {(size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg),
+                    (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic}};
+  dg_stage_body<M>(src, in, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
 }
 
 }}  // namespace wb::dg

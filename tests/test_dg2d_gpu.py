@@ -166,6 +166,13 @@ def field_err(a, b):
     (6, 2, 1, dict(flux="llf", limiter="ONP", solver="RK4", ninit=1)),
     (4, 4, 2, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=5, bc=3)),
     (32, 3, 4, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+    # nx % 32 == 0: the TMA-staged stage kernel (rows through shared memory; the wrapped x neighbours of a row's two end
+    # elements through global memory) -- periodic, clamped, with gravity, orders 2..4, two blocks per row
+    (32, 3, 3, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=3, bc=2)),
+    (64, 2, 3, dict(flux="llf1", limiter="ONP", solver="EQL", ninit=1, bc=1)),
+    (32, 3, 2, dict(flux="llf1", limiter="ONP", solver="SS4", ninit=2, bc=2, source=2, grad_phi_case=1)),
+    (32, 4, 2, dict(flux="llf1", limiter="none", solver="RK4", ninit=1, bc=1)),
+    (64, 3, 2, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=5, bc=3)),
 ])
 def test_evolve_fused_kernel_matches_oracle(wb, oracle, nx, mx, steps, kw):
     """arith = 0: one fused launch per RK stage (update + RK combination + ONP), sum-factorised, FMA, Newton rcp/rsqrt:
@@ -253,3 +260,17 @@ def test_larger_grid_properties(wb, oracle):
     with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, flux="llf1", ninit=1, limiter="ONP", arith=1) as s1:
         ref, it1, t1, dt1 = s1.evolve(u0, x, y, 1.0, 2)          # fused vs reference-order kernels at a size with no CPU run
     assert it1 == 2 and abs(t1 - t) <= 1e-13 * t and field_err(got, ref) <= 1e-12
+
+
+
+def test_tma_staged_kernel_equals_the_global_memory_one(wb, oracle, monkeypatch):
+    """Same arithmetic, different data path: with nx % 32 == 0 the modes travel through TMA + shared memory; switching that
+    off (WB_DG2D_TMA=0) must give the same bits."""
+    p, s, x, y = mk(oracle, wb, 64, 3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    with s:
+        a, it, t, dt = s.evolve(u0, x, y, 1.0, 3)
+    monkeypatch.setenv("WB_DG2D_TMA", "0")
+    with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s2:
+        b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 3)
+    assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
