@@ -190,7 +190,7 @@ def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
                                                "periodic Gaussian pulse (ninit=1), device-initialised", "grid": [n, n],
                                    "parallelism": f"y-slabs x{world} (ring)" if world > 1 else "single GPU"},
                         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                     "traffic": None, "kernel": "k_dg_stage_fast<3> (fused update + RK combination + ONP, 5 launches/step)",
+                                     "traffic": None, "kernel": "k_dg_stage_tma<3> (fused update + RK combination + ONP, rows staged by TMA, 5 launches/step)",
                                      "algorithmic_bytes_per_launch": 921.6 * n * n / world, "peak_source": src,
                                      "note": "the launch time includes the 4 small max-speed reduction kernels of each step"},
                         "sim": {"iters": it, "t": t, "dt": dt}})

@@ -268,6 +268,12 @@ struct GlobalSrc {
   template <int FACE>
   __device__ __forceinline__ void nb(int v, double (&d)[M][M]) const { load_var<M>(in, g, v, eN[FACE], d); }
   __device__ __forceinline__ void x_faces_done() const {}
+  __device__ __forceinline__ void bottom_face_done(const StageCoef&) const {}
+  __device__ __forceinline__ void top_face_done(const StageCoef&) const {}
+  // operands of the RK combination: A0, A1 and (for the second result) the stage input itself, mode m of variable v
+  __device__ __forceinline__ double rk_a0(const StageCoef& C, int v, int m) const { return PL(C.A0, g, v, m)[e]; }
+  __device__ __forceinline__ double rk_a1(const StageCoef& C, int v, int m) const { return PL(C.A1, g, v, m)[e]; }
+  __device__ __forceinline__ double rk_in(int v, int m) const { return PL(in, g, v, m)[e]; }
 };
 
 // One element of one RK stage (everything but where the modes come from).
@@ -293,7 +299,9 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
     face_term<M, 1>(src, P, B, d, acc);
     src.x_faces_done();
     face_term<M, 2>(src, P, B, d, acc);
+    src.bottom_face_done(C);
     face_term<M, 3>(src, P, B, d, acc);
+    src.top_face_done(C);
     // ---- nodal values (sum-factorised)
 #pragma unroll
     for (int v = 0; v < 4; ++v)
@@ -407,11 +415,12 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
         if (C.out2) {     // everything of out2 that does not depend on the limited `out` (U is dead by now)
           double r2 = C.k0 * PL(C.B0, g, v, m)[e];
           r2 = fma(C.k1, PL(C.B1, g, v, m)[e], r2);
-          r2 = fma(C.k2, PL(in, g, v, m)[e], r2);
+          r2 = fma(C.k2, src.rk_in(v, m), r2);
           U[v][a][b] = fma(C.ke * ctrl->dt, L, r2);
         }
-        double r = (C.c0 == 1.0) ? PL(C.A0, g, v, m)[e] : C.c0 * PL(C.A0, g, v, m)[e];
-        if (C.na >= 2) r = fma(C.c1, PL(C.A1, g, v, m)[e], r);
+        const double a0 = src.rk_a0(C, v, m);
+        double r = (C.c0 == 1.0) ? a0 : C.c0 * a0;
+        if (C.na >= 2) r = fma(C.c1, src.rk_a1(C, v, m), r);
         acc[v][a][b] = fma(cdt, L, r);
       }
   if (apply_onp) positivity_fast<M>(P, B, acc);
