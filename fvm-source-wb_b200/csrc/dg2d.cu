@@ -100,13 +100,68 @@ __device__ __forceinline__ void speed(const DgPhys& P, const double u[4], double
   vy = w[2];
   spd = sqrt(w[1] * w[1] + w[2] * w[2]) + cs;
 }
-// compute_num_flux :991-1006 -> compute_llflux :968-988; flux_id 0 leaves the flux at its initial 0
+// compute_hllflux :1008-1026 ('hll2'): isotropic speeds |v| +- cs, the direction only enters through fl, fr
+__device__ __forceinline__ void hllflux(const DgPhys& P, const double ul[4], const double ur[4], const double fl[4], const double fr[4],
+                                        double fh[4]) {
+  double csl, csr, vxl, vyl, vxr, vyr, sl, sr;
+  speed(P, ul, csl, vxl, vyl, sl);
+  speed(P, ur, csr, vxr, vyr, sr);
+  const double ml = sqrt(vxl * vxl + vyl * vyl), mr = sqrt(vxr * vxr + vyr * vyr);
+  const double a_plus = fmax(0.0, fmax(csl + ml, csr + mr));
+  const double a_minus = fmax(0.0, fmax(-(csl - ml), -(csr - mr)));
+#pragma unroll
+  for (int v = 0; v < 4; ++v) fh[v] = (a_plus * fl[v] + a_minus * fr[v] - a_plus * a_minus * (ur[v] - ul[v])) / (a_plus + a_minus);
+}
+// compute_hllcflux :1030-1134 ('hllc') as shipped: misplaced parenthesis in the right star energy (:1075, :1116), wleft(2)
+// in the right star state of the y branch (:1114), fluxes of compute_flux (:919-944); untouched output when no branch fires
+template <int DIR>
+__device__ __forceinline__ void hllcflux(const DgPhys& P, const double ul[4], const double ur[4], double fh[4]) {
+  double wl[4], wr[4], csl, csr, vxl, vyl, vxr, vyr, sl, sr, f1[4], f2[4], usl[4], usr[4];
+  prim(P, ul, wl);
+  prim(P, ur, wr);
+  speed(P, ul, csl, vxl, vyl, sl);
+  speed(P, ur, csr, vxr, vyr, sr);
+  constexpr int n = (DIR == 1) ? 1 : 2, t = (DIR == 1) ? 2 : 1;
+  const double v_l = (DIR == 1) ? vxl : vyl, v_r = (DIR == 1) ? vxr : vyr;
+  const double SL = fmin(v_l, v_r) - fmax(csl, csr), SR = fmax(v_l, v_r) + fmax(csl, csr);
+  const double SM = (wr[0] * v_r * (SR - v_r) - wl[0] * v_l * (SL - v_l) + wl[3] - wr[3]) / (wr[0] * (SR - v_r) - wl[0] * (SL - v_l));
+  usl[0] = ul[0] * (SL - v_l) / (SL - SM);
+  usl[n] = usl[0] * SM;
+  usl[t] = usl[0] * wl[t];
+  usl[3] = usl[0] * (ul[3] / ul[0] + (SM - wl[n]) * (SM + wl[3] / (wl[0] * (SL - wl[n]))));
+  usr[0] = ur[0] * (SR - v_r) / (SR - SM);
+  usr[n] = usr[0] * SM;
+  usr[t] = usr[0] * ((DIR == 1) ? wr[t] : wl[t]);
+  usr[3] = usr[0] * (ur[3] / ur[0] + (SM - wr[n] * (SM + wr[3] / (wr[0] * (SR - wr[n])))));
+  if (SL > 0.0) {
+    flux_nodes(P, ul, f1, f2);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) fh[v] = (DIR == 1) ? f1[v] : f2[v];
+  } else if (SL <= 0 && SM > 0) {
+    flux_nodes(P, ul, f1, f2);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) fh[v] = ((DIR == 1) ? f1[v] : f2[v]) + SL * (usl[v] - ul[v]);
+  } else if (SR >= 0 && SM <= 0) {
+    flux_nodes(P, ur, f1, f2);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) fh[v] = ((DIR == 1) ? f1[v] : f2[v]) + SR * (usr[v] - ur[v]);
+  } else if (SR < 0) {
+    flux_nodes(P, ur, f1, f2);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) fh[v] = (DIR == 1) ? f1[v] : f2[v];
+  }
+}
+// compute_num_flux :991-1006 -> compute_llflux :968-988 | compute_hllflux | compute_hllcflux; flux_id 0 ('llf', the shipped
+// value, matches no branch) leaves the flux at its initial 0
 template <int DIR>
 __device__ __forceinline__ void num_flux(const DgPhys& P, const double ul[4], const double ur[4], double nf[4]) {
-  if (P.flux_id != 1) { nf[0] = nf[1] = nf[2] = nf[3] = 0.0; return; }
+  nf[0] = nf[1] = nf[2] = nf[3] = 0.0;
+  if (P.flux_id == 0) return;
+  if (P.flux_id == 3) { hllcflux<DIR>(P, ul, ur, nf); return; }
   double fl[4], fr[4], csl, csr, vxl, vyl, vxr, vyr, sl, sr;
   flux_int<DIR>(P, ul, fl);
   flux_int<DIR>(P, ur, fr);
+  if (P.flux_id == 2) { hllflux(P, ul, ur, fl, fr, nf); return; }
   speed(P, ul, csl, vxl, vyl, sl);
   speed(P, ur, csr, vxr, vyr, sr);
   double cmax = (DIR == 1) ? fmax(fabs(vxr + csr), fabs(vxl + csl)) : fmax(fabs(vyr + csr), fabs(vyl + csl));
@@ -1066,20 +1121,25 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   if (m_in) {
     dim3 b(32), gr((unsigned)(h->g.ne / 32));
     DISPATCH_M(h, {
-      auto kern = k_dg_stage_tma<MM>;
-      static bool configured = false;
-      if (!configured) {
+      auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_tma<MM, true> : k_dg_stage_tma<MM, false>;
+      static bool configured[2] = {false, false};
+      if (!configured[h->phys.flux_id >= 2]) {
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
-        configured = true;
+        configured[h->phys.flux_id >= 2] = true;
       }
       kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
                                                           h->phys, h->FB, h->ctrl, onp);
     });
   } else {
     dim3 b(64), gr = elem_grid(h, 64);
-    DISPATCH_M(h, k_dg_stage_fast<MM><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
-                                                             h->phys, h->FB, h->ctrl, onp));
+    if (h->phys.flux_id >= 2) {
+      DISPATCH_M(h, (k_dg_stage_fast<MM, true><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
+                                                                      h->g, h->phys, h->FB, h->ctrl, onp)));
+    } else {
+      DISPATCH_M(h, (k_dg_stage_fast<MM, false><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
+                                                                       h->g, h->phys, h->FB, h->ctrl, onp)));
+    }
   }
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_exchange(h, out));
@@ -1177,7 +1237,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->bc >= 1 && p->bc <= 3, "bc must be 1..3");
   WB_REQUIRE(p->source >= 1 && p->source <= 3, "source must be 1..3");
   WB_REQUIRE(p->grad_phi_case == 1 || p->grad_phi_case == 2, "grad_phi_case must be 1 or 2");
-  WB_REQUIRE(p->flux_id == 0 || p->flux_id == 1, "flux_id must be 0 (as shipped) or 1 (llf1); hll2/hllc are not built yet");
+  WB_REQUIRE(p->flux_id >= 0 && p->flux_id <= 3, "flux_id must be 0 (as shipped), 1 (llf1), 2 (hll2) or 3 (hllc)");
   WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 4, "limiter_id must be 0..4 (none, ONP, HIO, 1OR, LOW)");
   WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");

@@ -59,10 +59,29 @@ __device__ __forceinline__ Prim prim(const DgPhys& P, double rho, double mx, dou
   w.p = P.gm1a * fma(-0.5 * w.w0, fma(w.vy, w.vy, w.vx * w.vx), E);
   return w;
 }
-// local Lax-Friedrichs at one face point (compute_llflux :968-988 with compute_flux_int :946-965), DIR 1 = x, 2 = y
+// 'hll2' / 'hllc' (compute_hllflux :1008-1026, compute_hllcflux :1030-1134): the reference-order routines of dg2d.cu, out of
+// line and with by-value arguments so that the fused kernel's registers and instruction stream do not pay for them
+struct Flux4 { double f[4]; };
 template <int DIR>
+__device__ __noinline__ Flux4 other_flux(DgPhys P, double a0, double a1, double a2, double a3, double b0, double b1, double b2,
+                                         double b3) {
+  const double ul[4] = {a0, a1, a2, a3}, ur[4] = {b0, b1, b2, b3};
+  Flux4 r;
+  num_flux<DIR>(P, ul, ur, r.f);
+  return r;
+}
+// local Lax-Friedrichs at one face point (compute_llflux :968-988 with compute_flux_int :946-965), DIR 1 = x, 2 = y
+// ANYFLUX = false: kernel instantiation for flux_id 0 | 1 only (no call in the instruction stream of the hot path)
+template <int DIR, bool ANYFLUX>
 __device__ __forceinline__ void llf(const DgPhys& P, const double ul[4], const double ur[4], double nf[4]) {
-  if (P.flux_id != 1) { nf[0] = nf[1] = nf[2] = nf[3] = 0.0; return; }
+  if (P.flux_id != 1) {
+    nf[0] = nf[1] = nf[2] = nf[3] = 0.0;
+    if (ANYFLUX && P.flux_id != 0) {
+      const Flux4 r = other_flux<DIR>(P, ul[0], ul[1], ul[2], ul[3], ur[0], ur[1], ur[2], ur[3]);
+      nf[0] = r.f[0]; nf[1] = r.f[1]; nf[2] = r.f[2]; nf[3] = r.f[3];
+    }
+    return;
+  }
   const Prim a = prim(P, ul[0], ul[1], ul[2], ul[3]);
   const Prim b = prim(P, ur[0], ur[1], ur[2], ur[3]);
   // w0 >= 1e-9 > 1e-10, so max(w0,1d-10) = w0 and its reciprocal is already known
@@ -208,7 +227,7 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
 // FACE 0 left, 1 right, 2 bottom, 3 top.  Each face is evaluated by both adjacent elements (no inter-thread traffic).
 // `src.template nb<FACE>(v, dn)` delivers the modes of variable v of the neighbour across the face (global memory or the
 // TMA-staged shared-memory rows, see the two sources below).
-template <int M, int FACE, class Src>
+template <int M, int FACE, bool ANYFLUX, class Src>
 __device__ __forceinline__ void face_term(Src& src, const DgPhys& P, const FastBasis& B, const double (&d)[4][M][M],
                                           double (&acc)[4][M][M]) {
   constexpr int SIDE_OWN = FACE;                                   // own trace on that side
@@ -229,10 +248,10 @@ __device__ __forceinline__ void face_term(Src& src, const DgPhys& P, const FastB
   for (int q = 0; q < M; ++q) {
     double F[4];
     // low side first: (neighbour, own) on the left/bottom faces, (own, neighbour) on the right/top faces
-    if (FACE == 0) fastm::llf<1>(P, tn[q], to[q], F);
-    if (FACE == 1) fastm::llf<1>(P, to[q], tn[q], F);
-    if (FACE == 2) fastm::llf<2>(P, tn[q], to[q], F);
-    if (FACE == 3) fastm::llf<2>(P, to[q], tn[q], F);
+    if (FACE == 0) fastm::llf<1, ANYFLUX>(P, tn[q], to[q], F);
+    if (FACE == 1) fastm::llf<1, ANYFLUX>(P, to[q], tn[q], F);
+    if (FACE == 2) fastm::llf<2, ANYFLUX>(P, tn[q], to[q], F);
+    if (FACE == 3) fastm::llf<2, ANYFLUX>(P, to[q], tn[q], F);
 #pragma unroll
     for (int v = 0; v < 4; ++v) to[q][v] = F[v];
   }
@@ -277,7 +296,7 @@ struct GlobalSrc {
 };
 
 // One element of one RK stage (everything but where the modes come from).
-template <int M, class Src>
+template <int M, bool ANYFLUX, class Src>
 __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict__ in, const StageCoef& C, double* __restrict__ out,
                                               const double* __restrict__ gx, const double* __restrict__ gy,
                                               const unsigned char* __restrict__ fz, const DgGrid& g, const DgPhys& P,
@@ -295,12 +314,12 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
         for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
     }
     // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
-    face_term<M, 0>(src, P, B, d, acc);
-    face_term<M, 1>(src, P, B, d, acc);
+    face_term<M, 0, ANYFLUX>(src, P, B, d, acc);
+    face_term<M, 1, ANYFLUX>(src, P, B, d, acc);
     src.x_faces_done();
-    face_term<M, 2>(src, P, B, d, acc);
+    face_term<M, 2, ANYFLUX>(src, P, B, d, acc);
     src.bottom_face_done(C);
-    face_term<M, 3>(src, P, B, d, acc);
+    face_term<M, 3, ANYFLUX>(src, P, B, d, acc);
     src.top_face_done(C);
     // ---- nodal values (sum-factorised)
 #pragma unroll
@@ -440,7 +459,7 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
       for (int a = 0; a < M; ++a) PL(out, g, v, b * M + a)[e] = acc[v][a][b];
 }
 
-template <int M>
+template <int M, bool ANYFLUX>
 __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
                                                       const double* __restrict__ gx, const double* __restrict__ gy,
                                                       const unsigned char* __restrict__ fz, DgGrid g, DgPhys P, FastBasis B,
@@ -452,7 +471,7 @@ __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__
   GlobalSrc<M> src{in, g, e,
                    {(size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg),
                     (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic}};
-  dg_stage_body<M>(src, in, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
+  dg_stage_body<M, ANYFLUX>(src, in, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
 }
 
 }}  // namespace wb::dg

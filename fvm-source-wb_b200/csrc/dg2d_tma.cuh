@@ -93,7 +93,7 @@ struct SmemSrc {
   __device__ __forceinline__ double rk_in(int v, int m) const { return PL(in, g, v, m)[e]; }
 };
 
-template <int M>
+template <int M, bool ANYFLUX>
 __global__ void __launch_bounds__(32) k_dg_stage_tma(const __grid_constant__ CUtensorMap m_in, const double* __restrict__ in, StageCoef C,
                                                      double* __restrict__ out, const double* __restrict__ gx,
                                                      const double* __restrict__ gy, const unsigned char* __restrict__ fz, DgGrid g,
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) k_dg_stage_tma(const __grid_constant__ CUt
                  r1, bars, lane, ic0, jt, e,
                  (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg),
                  ic == 0, ic == g.nx - 1};
-  dg_stage_body<M>(src, in, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
+  dg_stage_body<M, ANYFLUX>(src, in, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
 }
 
 template <int M>

@@ -123,7 +123,8 @@ typedef struct {
   int source;            /* :20   1 none, 2 gravity (get_source + grad_phi), 3 advection sink            */
   int grad_phi_case;     /* :21   1: g=(x,y) [sic], 2: softened Keplerian centred at (3,3)               */
   int flux_id;           /* :15   0 = as shipped ('llf' matches no branch: numerical flux stays 0),
-                                  1 = 'llf1' local Lax-Friedrichs                                       */
+                                  1 = 'llf1' local Lax-Friedrichs, 2 = 'hll2' (compute_hllflux :1008-1026),
+                                  3 = 'hllc' (compute_hllcflux :1030-1134, as shipped incl. its typos)   */
   int limiter_id;        /* :14   0 = use_limiter .false., 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW'            */
   int solver_id;         /* :13   1 'RK4' SSPRK(5,4), 2 'SS4' (same after real(4) rounding), 3 'EQL' RK2,
                                   4 'DEB' forward Euler                                                  */

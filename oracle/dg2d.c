@@ -29,7 +29,7 @@ typedef struct {
   int bc;                   /* :18  1 periodic, 2/3 clamp */
   int source;               /* :20  1 none, 2 gravity (get_source), 3 advection sink */
   int grad_phi_case;        /* :21 */
-  int flux_id;              /* :15  0 = as shipped ('llf ' matches nothing -> numerical flux stays 0), 1 = 'llf1' */
+  int flux_id;              /* :15  0 = as shipped ('llf ' matches nothing -> numerical flux stays 0), 1 = 'llf1', 2 = 'hll2', 3 = 'hllc' */
   int limiter_id;           /* :14  0 = use_limiter false, 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW' */
   int solver_id;            /* :13  1 'RK4', 2 'SS4', 3 'EQL', 4 'DEB' */
   int ninit;                /* :17 */
@@ -338,10 +338,67 @@ static void llflux(const orc_dg2d_params *p, const double *ul, const double *ur,
   else if (flag == 2) cmax = fmax(fabs(vyr + cs_r), fabs(vyl + cs_l));
   for (int v = 0; v < NV; ++v) fg[v] = 0.5 * (fr[v] + fl[v]) + 0.5 * cmax * (ul[v] - ur[v]);
 }
+/* :1008-1026 compute_hllflux ('hll2'): isotropic speeds |v| +- cs in both directions, `flag` unused */
+static void hllflux(const orc_dg2d_params *p, const double *ul, const double *ur, const double *fl, const double *fr, double *fh) {
+  double cs_l, cs_r, vxl, vyl, vxr, vyr, sl, sr;
+  compute_speed(p, ul, &cs_l, &vxl, &vyl, &sl);
+  compute_speed(p, ur, &cs_r, &vxr, &vyr, &sr);
+  const double ml = sqrt(vxl * vxl + vyl * vyl), mr = sqrt(vxr * vxr + vyr * vyr);
+  const double a_plus = fmax(0.0, fmax(cs_l + ml, cs_r + mr));
+  const double a_minus = fmax(0.0, fmax(-(cs_l - ml), -(cs_r - mr)));
+  for (int v = 0; v < NV; ++v) fh[v] = (a_plus * fl[v] + a_minus * fr[v] - a_plus * a_minus * (ur[v] - ul[v])) / (a_plus + a_minus);
+}
+/* :1030-1134 compute_hllcflux ('hllc'), as shipped: the star energies carry a misplaced parenthesis on the right side
+ * (:1075, :1116), the y-direction right star state takes its x momentum from the LEFT state (:1114), p* is computed and
+ * never used, and the fluxes are the volume ones of compute_flux (floored density in the mass flux).  The trailing
+ * compute_flux(uhllc,...) of the x branch (:1092) reads an uninitialised state and only overwrites the caller's
+ * temporaries: no effect on the result.  A state for which no branch fires (NaN) leaves the output untouched. */
+static void hllcflux(const orc_dg2d_params *p, const double *ul, const double *ur, double *fh, int flag) {
+  double wl[NV], wr[NV], cs_l, cs_r, vxl, vyl, vxr, vyr, sl, sr, f1[NV], f2[NV], usl[NV], usr[NV];
+  prim1(p, ul, wl);
+  prim1(p, ur, wr);
+  compute_speed(p, ul, &cs_l, &vxl, &vyl, &sl);
+  compute_speed(p, ur, &cs_r, &vxr, &vyr, &sr);
+  const int n = (flag == 1) ? 1 : 2, t = (flag == 1) ? 2 : 1;          /* normal / tangential momentum */
+  const double v_l = (flag == 1) ? vxl : vyl, v_r = (flag == 1) ? vxr : vyr;
+  const double SL = fmin(v_l, v_r) - fmax(cs_l, cs_r), SR = fmax(v_l, v_r) + fmax(cs_l, cs_r);
+  const double SM = (wr[0] * v_r * (SR - v_r) - wl[0] * v_l * (SL - v_l) + wl[3] - wr[3]) / (wr[0] * (SR - v_r) - wl[0] * (SL - v_l));
+  usl[0] = ul[0] * (SL - v_l) / (SL - SM);
+  usl[n] = usl[0] * SM;
+  usl[t] = usl[0] * wl[t];
+  usl[3] = usl[0] * (ul[3] / ul[0] + (SM - wl[n]) * (SM + wl[3] / (wl[0] * (SL - wl[n]))));
+  usr[0] = ur[0] * (SR - v_r) / (SR - SM);
+  usr[n] = usr[0] * SM;
+  usr[t] = usr[0] * ((flag == 1) ? wr[t] : wl[t]);                         /* :1114 wleft(2) in the y branch */
+  usr[3] = usr[0] * (ur[3] / ur[0] + (SM - wr[n] * (SM + wr[3] / (wr[0] * (SR - wr[n])))));
+  if (SL > 0.0) {
+    flux_nodes(p, ul, f1, f2);
+    for (int v = 0; v < NV; ++v) fh[v] = (flag == 1) ? f1[v] : f2[v];
+  } else if (SL <= 0 && SM > 0) {
+    flux_nodes(p, ul, f1, f2);
+    for (int v = 0; v < NV; ++v) fh[v] = ((flag == 1) ? f1[v] : f2[v]) + SL * (usl[v] - ul[v]);
+  } else if (SR >= 0 && SM <= 0) {
+    flux_nodes(p, ur, f1, f2);
+    for (int v = 0; v < NV; ++v) fh[v] = ((flag == 1) ? f1[v] : f2[v]) + SR * (usr[v] - ur[v]);
+  } else if (SR < 0) {
+    flux_nodes(p, ur, f1, f2);
+    for (int v = 0; v < NV; ++v) fh[v] = (flag == 1) ? f1[v] : f2[v];
+  }
+}
 /* :991-1006 compute_num_flux: flux_type that matches none of 'llf1','hll2','hllc' leaves the output untouched */
 static void num_flux(const orc_dg2d_params *p, const double *ul, const double *ur, const double *fl, const double *fr,
                      double *nf, int flag) {
   if (p->flux_id == 1) llflux(p, ul, ur, fl, fr, nf, flag);
+  else if (p->flux_id == 2) hllflux(p, ul, ur, fl, fr, nf);
+  else if (p->flux_id == 3) hllcflux(p, ul, ur, nf, flag);
+}
+/* test hook: the numerical flux of one face point, f_left / f_right from compute_flux_int as in compute_update :1324-1366 */
+void orc_dg2d_num_flux(const orc_dg2d_params *p, const double *ul, const double *ur, int flag, double *nf) {
+  double fl1[NV], fl2[NV], fr1[NV], fr2[NV];
+  flux_int(p, ul, fl1, fl2);
+  flux_int(p, ur, fr1, fr2);
+  for (int v = 0; v < NV; ++v) nf[v] = 0.0;
+  num_flux(p, ul, ur, flag == 1 ? fl1 : fl2, flag == 1 ? fr1 : fr2, nf, flag);
 }
 
 /* :1599-1644 grad_phi at one node */

@@ -138,7 +138,7 @@ class DG2DParams(C.Structure):
 
 LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4}
 SOLVERS = {"RK4": 1, "SS4": 2, "EQL": 3, "DEB": 4}
-FLUXES = {"llf": 0, "llf1": 1}   # 'llf' is the shipped default that matches no branch (numerical flux stays 0)
+FLUXES = {"llf": 0, "llf1": 1, "hll2": 2, "hllc": 3}   # 'llf' is the shipped default that matches no branch (numerical flux stays 0)
 
 
 def dg2d_params(nx=8, ny=8, mx=2, my=2, bc=1, source=1, grad_phi_case=2, flux="llf1", limiter="ONP", solver="RK4",
@@ -192,6 +192,14 @@ def dg2d_get_nodes_from_modes(p, modes):
     u = np.empty_like(modes)
     lib().orc_dg2d_get_nodes_from_modes(C.byref(p), _ptr(modes), _ptr(u))
     return u
+
+
+def dg2d_num_flux(p, ul, ur, flag):
+    """compute_num_flux at one face point (flag 1 = x face, 2 = y face)"""
+    a = np.ascontiguousarray(ul, dtype=np.float64); b = np.ascontiguousarray(ur, dtype=np.float64)
+    nf = np.zeros(4)
+    lib().orc_dg2d_num_flux(C.byref(p), _ptr(a), _ptr(b), C.c_int(flag), _ptr(nf))
+    return nf
 
 
 def dg2d_compute_update(p, modes, x, y):

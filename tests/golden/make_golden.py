@@ -51,6 +51,8 @@ def dg2d():
         ("riemann_o3_low", 6, 3, 2, 1, 2, "llf1", "LOW", "DEB", 4, 3),
         ("advsink_o2", 6, 2, 1, 3, 2, "llf1", "none", "SS4", 1, 2),
         ("riemann_o4_onp", 4, 4, 3, 1, 2, "llf1", "ONP", "RK4", 5, 2),
+        ("pulse_o3_hll2", 6, 3, 1, 1, 2, "hll2", "ONP", "RK4", 1, 2),
+        ("riemann_o2_hllc", 8, 2, 2, 1, 2, "hllc", "ONP", "RK4", 3, 2),
     ]
     for tag, nx, mx, bc, source, gcase, flux, lim, solver, ninit, steps in cases:
         p = o.dg2d_params(nx=nx, ny=nx, mx=mx, my=mx, bc=bc, source=source, grad_phi_case=gcase, flux=flux, limiter=lim,

@@ -24,7 +24,7 @@ def wb():
 
 INV_L = {0: "none", 1: "ONP", 2: "HIO", 3: "1OR", 4: "LOW"}
 INV_S = {1: "RK4", 2: "SS4", 3: "EQL", 4: "DEB"}
-INV_F = {0: "llf", 1: "llf1"}
+INV_F = {0: "llf", 1: "llf1", 2: "hll2", 3: "hllc"}
 
 
 def mk(o, wb, nx, mx, arith=1, **kw):
@@ -77,6 +77,11 @@ CASES = [  # nx, mx, kwargs
     (8, 2, dict(flux="llf1", ninit=4, bc=3)),
     (6, 2, dict(flux="llf1", ninit=1, source=3)),
     (33, 3, dict(flux="llf1", ninit=1)),
+    (8, 3, dict(flux="hll2", ninit=1)),
+    (8, 2, dict(flux="hll2", ninit=3, bc=2)),
+    (8, 3, dict(flux="hllc", ninit=1)),
+    (8, 2, dict(flux="hllc", ninit=4, bc=3)),
+    (6, 3, dict(flux="hllc", ninit=2, bc=2, source=2, grad_phi_case=1)),
 ]
 
 
@@ -128,6 +133,8 @@ def test_max_speed_order_dependence(wb, oracle):
     (6, 3, 2, dict(flux="llf1", limiter="ONP", solver="SS4", ninit=2, bc=2, source=2, grad_phi_case=1)),
     (6, 2, 2, dict(flux="llf", limiter="ONP", solver="RK4", ninit=1)),
     (16, 3, 2, dict(flux="llf1", limiter="none", solver="RK4", ninit=1)),
+    (8, 3, 2, dict(flux="hll2", limiter="ONP", solver="RK4", ninit=1)),
+    (8, 2, 3, dict(flux="hllc", limiter="ONP", solver="EQL", ninit=3, bc=2)),
 ])
 def test_evolve_bitwise(wb, oracle, nx, mx, steps, kw):
     p, s, x, y = mk(oracle, wb, nx, mx, **kw)
@@ -166,6 +173,9 @@ def field_err(a, b):
     (6, 2, 1, dict(flux="llf", limiter="ONP", solver="RK4", ninit=1)),
     (4, 4, 2, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=5, bc=3)),
     (32, 3, 4, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+    (8, 3, 2, dict(flux="hll2", limiter="ONP", solver="RK4", ninit=1)),
+    (8, 3, 2, dict(flux="hllc", limiter="ONP", solver="RK4", ninit=3, bc=2)),
+    (32, 2, 2, dict(flux="hllc", limiter="ONP", solver="RK4", ninit=1)),
     # nx % 32 == 0: the TMA-staged stage kernel (rows through shared memory; the wrapped x neighbours of a row's two end
     # elements through global memory) -- periodic, clamped, with gravity, orders 2..4, two blocks per row
     (32, 3, 3, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=3, bc=2)),

@@ -198,3 +198,75 @@ def test_golden_vectors(oracle):
         assert np.array_equal(oracle.dg2d_apply_limiter(p, m0), g[f"{tag}_lim"])
         un, it, t, dt = oracle.dg2d_evolve(p, u0, x, y, 1.0, steps)
         assert np.array_equal(un, g[f"{tag}_un"]) and np.array_equal(np.array([it, t, dt]), g[f"{tag}_clock"])
+
+
+# ---------------------------------------------------------------- 'hll2' / 'hllc' (compute_hllflux :1008-1026, compute_hllcflux :1030-1134)
+def _phys_flux(u, flag, gamma=float(np.float32(1.4))):
+    rho, mx, my, E = u
+    vx, vy = mx / rho, my / rho
+    p = (gamma - 1.0) * (E - 0.5 * rho * (vx * vx + vy * vy))
+    return np.array([mx, mx * vx + p, mx * vy, vx * (E + p)]) if flag == 1 else np.array([my, mx * vy, my * vy + p, vy * (E + p)])
+
+
+def test_hll2_as_shipped_is_consistent_and_left_upwind_for_subsonic_states(oracle):
+    """compute_hllflux (:1008-1026) builds its wave speeds from the isotropic |v| and c: a_plus = max(0, c + |v|) and
+    a_minus = max(0, -(c - |v|)) = max(0, |v| - c).  For subsonic states a_minus is therefore ZERO and the formula
+    collapses to f_left, whatever the right state; only when some |v| exceeds c does the right state enter."""
+    p = oracle.dg2d_params(flux="hll2")
+    u = np.array([1.3, 0.4, -0.2, 2.0])
+    for flag in (1, 2):
+        assert np.allclose(oracle.dg2d_num_flux(p, u, u, flag), _phys_flux(u, flag), rtol=1e-14)
+    ul = np.array([1.3, 0.4, -0.2, 2.0]); ur = np.array([0.9, -0.3, 0.1, 1.7])                    # both subsonic
+    for flag in (1, 2):
+        assert np.allclose(oracle.dg2d_num_flux(p, ul, ur, flag), _phys_flux(ul, flag), rtol=1e-14)
+    ul = np.array([1.0, 3.0, 0.0, 7.0]); ur = np.array([0.5, 1.6, 0.0, 3.31])                      # |v| > c on both sides
+    g = float(np.float32(1.4))
+    sp = lambda q: (abs(q[1] / q[0]), np.sqrt(g * (g - 1) * (q[3] - 0.5 * q[1] ** 2 / q[0]) / q[0]))
+    (vl, cl), (vr, cr) = sp(ul), sp(ur)
+    ap, am = max(cl + vl, cr + vr), max(vl - cl, vr - cr)
+    expect = (ap * _phys_flux(ul, 1) + am * _phys_flux(ur, 1) - ap * am * (ur - ul)) / (ap + am)
+    assert am > 0 and np.allclose(oracle.dg2d_num_flux(p, ul, ur, 1), expect, rtol=1e-14)
+
+
+def test_hllc_as_shipped_consistent_only_where_its_typos_are_silent(oracle):
+    """Equal left and right states: S_M = v_n and the left star state is the state itself, so the branches that use it
+    (v_n > 0) return the physical flux.  The right star ENERGY carries a misplaced parenthesis (:1075, :1116):
+    E* - E = rho (v_n - v_n (v_n + p / (rho c))) != 0, so for -c <= v_n <= 0 the energy flux is off by S_R times that --
+    except at v_n = 0, where it vanishes.  The y branch also takes the x momentum of the right star state from the LEFT
+    velocity (:1114): silent for equal states."""
+    p = oracle.dg2d_params(flux="hllc")
+    g = float(np.float32(1.4))
+    for u, flag in ((np.array([1.3, 0.4, -0.2, 2.0]), 1), (np.array([1.3, 0.4, 0.2, 2.0]), 2), (np.array([1.3, 0.4, 0.0, 2.0]), 2)):
+        assert np.allclose(oracle.dg2d_num_flux(p, u, u, flag), _phys_flux(u, flag), rtol=1e-13, atol=1e-15)
+    u = np.array([1.3, 0.4, -0.2, 2.0])                               # y face, v_y = -0.154 (subsonic, negative)
+    rho, vx, vy = u[0], u[1] / u[0], u[2] / u[0]
+    pr = (g - 1.0) * (u[3] - 0.5 * rho * (vx * vx + vy * vy)); c = np.sqrt(g * pr / rho)
+    SR = vy + c
+    dE = rho * (vy - vy * (vy + pr / (rho * (SR - vy)))) 
+    expect = _phys_flux(u, 2) + SR * np.array([0.0, 0.0, 0.0, dE])
+    assert np.allclose(oracle.dg2d_num_flux(p, u, u, 2), expect, rtol=1e-13)
+    # :1114 -- different x velocities on the two sides of a y face with S_M <= 0 <= S_R: the x momentum of the right star
+    # state is rho* times the LEFT x velocity
+    ul = np.array([1.0, 0.5, -0.1, 2.5]); ur = np.array([1.0, -0.3, -0.1, 2.5])
+    f = oracle.dg2d_num_flux(p, ul, ur, 2)
+    # momentum-x flux = f2(ur)[1] + S_R (rho*_R vx_L - mx_R)
+    wl = ul[1] / ul[0]; vyr = ur[2] / ur[0]
+    prl = (g - 1) * (ul[3] - 0.5 * (ul[1] ** 2 + ul[2] ** 2) / ul[0]); prr = (g - 1) * (ur[3] - 0.5 * (ur[1] ** 2 + ur[2] ** 2) / ur[0])
+    cl, cr = np.sqrt(g * prl / ul[0]), np.sqrt(g * prr / ur[0])
+    SL, SR = min(-0.1, vyr) - max(cl, cr), max(-0.1, vyr) + max(cl, cr)
+    SM = (ur[0] * vyr * (SR - vyr) - ul[0] * (-0.1) * (SL + 0.1) + prl - prr) / (ur[0] * (SR - vyr) - ul[0] * (SL + 0.1))
+    rs = ur[0] * (SR - vyr) / (SR - SM)
+    assert SM <= 0 <= SR and np.isclose(f[1], ur[1] * vyr + SR * (rs * wl - ur[1]), rtol=1e-13)
+
+
+@pytest.mark.parametrize("flux", ["hll2", "hllc"])
+def test_hll_fluxes_keep_the_scheme_conservative_and_convergent(oracle, flux):
+    """Whatever its formula, a numerical flux that is single valued per face point conserves the mean on the periodic box;
+    and for a right-moving smooth state (every branch the typos spare) both give the llf1 RHS up to the dissipation."""
+    p = oracle.dg2d_params(nx=8, ny=8, mx=3, my=3, flux=flux)
+    x, y, u = smooth_state(oracle, p)
+    m = oracle.dg2d_get_modes_from_nodes(p, u)
+    d = oracle.dg2d_compute_update(p, m, x, y)
+    assert np.all(np.isfinite(d)) and np.abs(d[0, 0].sum(axis=(0, 1))).max() < 1e-11
+    d1 = oracle.dg2d_compute_update(oracle.dg2d_params(nx=8, ny=8, mx=3, my=3, flux="llf1"), m, x, y)
+    assert 0 < np.abs(d - d1).max() < 0.2 * np.abs(d1).max()
