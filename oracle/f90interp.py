@@ -668,26 +668,21 @@ class Var:
         self.clen = clen
 
 
+_TCLS = {np.float64: "r8", float: "r8", np.float32: "r4", int: "i", np.int64: "i", np.int32: "i", bool: "l", np.bool_: "l",
+         str: "c", np.str_: "c"}
+_ADT = {"f8": "r8", "f4": "r4", "i8": "i", "i4": "i", "b1": "l"}
+
+
 def _tcls(x):
+    t = _TCLS.get(type(x))
+    if t is not None:
+        return t
     if isinstance(x, np.ndarray):
-        k = x.dtype.kind
-        if k == "f":
-            return "r8" if x.dtype.itemsize == 8 else "r4"
-        if k in "iu":
-            return "i"
-        if k == "b":
-            return "l"
-        return "c"
-    if isinstance(x, (bool, np.bool_)):
-        return "l"
-    if isinstance(x, (int, np.integer)):
+        return _ADT.get(x.dtype.str[1:], "c")
+    if isinstance(x, np.integer):
         return "i"
-    if isinstance(x, np.float32):
-        return "r4"
-    if isinstance(x, (float, np.floating)):
+    if isinstance(x, np.floating):
         return "r8"
-    if isinstance(x, str):
-        return "c"
     raise FortranError(f"unknown value type {type(x)}")
 
 
@@ -700,6 +695,8 @@ def _conv(x, t):
 
 
 def _promote(a, b):
+    if type(a) is np.float64 and type(b) is np.float64:
+        return a, b, "r8"
     ta, tb = _tcls(a), _tcls(b)
     if ta == tb:
         return a, b, ta
@@ -1424,7 +1421,12 @@ class Interp:
         if u.kind == "function":
             r = fr[u.result]
             return r.a[()] if r.a.ndim == 0 else r.a.copy()
-        return None
+        return {k: (v.a[()] if v.a.ndim == 0 else v.a) for k, v in fr.items()}     # the callee's variables at return
+
+    def run_program(self, name):
+        """Execute a main program; returns its variables at the end."""
+        fr = self.invoke(self.units[name], [])
+        return {k: (v.a[()] if v.a.ndim == 0 else v.a) for k, v in fr.items()}
 
     # ---- statements
     def assign(self, lhs, val, fr):

@@ -64,7 +64,7 @@ void orc_fvm1d_condinit(const orc_fvm1d_params *p, int ninit, double x, double *
     case 1: ww[0] = 1.0 + 0.5 * sin(2.0 * dpi * x); ww[1] = 1.0; ww[2] = 1.0; break;
     case 2: ww[0] = (fabs(x - 0.5) < 0.25) ? 2. : 1.0; ww[1] = 1.0; ww[2] = 1.0; break;
     case 3:
-      ww[0] = 1. + exp(-((x - 0.25) * (x - 0.25)) / 2.0 / ((double)0.05f * (double)0.05f));
+      ww[0] = 1. + exp(-((x - 0.25) * (x - 0.25)) / 2.0 / (double)(0.05f * 0.05f)  /* 0.05**2 is real(4)**integer: folded in single precision */);
       if (fabs(x - (double)0.7f) < (double)0.1f) ww[0] = ww[0] + 1.;
       ww[1] = 1.0; ww[2] = 1.0; break;
     case 4:

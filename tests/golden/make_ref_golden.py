@@ -1,0 +1,283 @@
+"""Golden vectors produced by THE REFERENCE'S OWN SOURCE TEXT.
+
+The image has no Fortran compiler, so instead of building the reference this script executes its .f90 files, unmodified,
+where they lie under /root/reference, with the small Fortran-90 interpreter in oracle/f90interp.py (semantics of
+gfortran on x86-64 without FMA contraction: real(4) literals, mixed-mode promotion, sequence association, libm
+transcendentals).  Sizes and switches are set the way the reference is configured -- by giving the `parameter`
+constants of its parameter modules other values (Interp.override; the files are not touched).
+
+Inputs and outputs of the hot-path routines are stored in the ORACLE's array layout (C order = the Fortran array
+transposed) under tests/golden/ref_*.npz; tests/test_reference_pins.py checks the C oracle (oracle/*.c) against
+them, and the GPU tests check the CUDA path against some of them directly.  /root/reference is only needed to
+RE-GENERATE the vectors:      python tests/golden/make_ref_golden.py [fv2d dg2d fv1d dg1d]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.f90interp import FortranBoundsError, Interp  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("WB_REFERENCE", "/root/reference")
+
+
+def F(*shape):
+    return np.zeros(shape, order="F")
+
+
+def C(a):
+    """Fortran array -> the oracle's C-order array (same bytes)."""
+    return np.array(np.asarray(a).T, order="C", copy=True)
+
+
+def scalar(v=0.0):
+    return np.array(v, dtype=np.float64)
+
+
+def note_calls(out, tag, it):
+    out[f"{tag}/calls"] = np.array(sorted(f"{k}:{v}" for k, v in it.calls.items()))
+    it.calls.clear()
+
+
+# ------------------------------------------------------------------------------------------------ 2D FV
+def fv2d_interp(**kv):
+    it = Interp()
+    it.load(f"{REF}/parameters_2d.f90").load(f"{REF}/benchmark_2d.f90")
+    it.override("parameters_2d", **kv)
+    return it
+
+
+def fv2d():
+    out = {}
+    rng = np.random.default_rng(20161017)
+    cases = [  # tag, nx, ny, ninit, nequilibrium, steps, random perturbation
+        ("pert", 12, 12, 3, 2, 3, 0.0), ("ragged", 13, 9, 3, 2, 2, 0.0), ("riemann", 12, 10, 4, 2, 3, 0.0),
+        ("eq1", 8, 10, 1, 1, 2, 0.0), ("hydro", 10, 10, 2, 2, 2, 0.0), ("random", 9, 11, 3, 2, 2, 0.1),
+        ("eq3_rand", 10, 8, 2, 3, 1, 0.05),
+    ]
+    for tag, nx, ny, ninit, neq, steps, amp in cases:
+        it = fv2d_interp(nx=nx, ny=ny, ninit=ninit, nequilibrium=neq)
+        x, y = F(nx, ny), F(nx, ny)
+        it.call("get_coords", x, y, nx, ny)
+        u, weq = F(4, nx, ny), F(4, nx, ny)
+        it.call("get_initial_conditions", x, y, u, nx, ny)
+        it.call("get_equilibrium_solution", x, y, weq, nx, ny)
+        out[f"{tag}/u_ic"] = C(u)
+        if amp:
+            u *= 1.0 + amp * rng.standard_normal(u.shape)
+            u[1] = amp * 3 * rng.standard_normal((nx, ny))
+            u[2] = amp * 2 * rng.standard_normal((nx, ny))
+        w = F(4, nx, ny)
+        it.call("compute_primitive", u, w, nx, ny)
+        u_back = F(4, nx, ny)
+        it.call("compute_conservative", w, u_back, nx, ny)
+        cmax = scalar()
+        it.call("compute_max_speed", u, cmax)
+        dudt, dplain = F(4, nx, ny), F(4, nx, ny)
+        it.call("compute_update_exact", u, weq, dudt)
+        try:
+            it.call("compute_update", u, weq, dplain)
+            plain_ok = True
+        except FortranBoundsError:       # benchmark_2d.f90:418 `iright = ny` indexes x with ny: out of bounds when nx < ny
+            assert nx < ny
+            plain_ok = False
+        out[f"{tag}/meta"] = np.array([nx, ny, ninit, neq, steps])
+        for k, v in (("x", x), ("y", y), ("u", u), ("weq", weq), ("w", w), ("u_back", u_back), ("dudt", dudt), ("dudt_plain", dplain)):
+            if k != "dudt_plain" or plain_ok:
+                out[f"{tag}/{k}"] = C(v)
+        out[f"{tag}/cmax"] = cmax.copy()
+        # evolve: reproduce the clock of `steps` steps by choosing tend just below the time reached after them
+        # (the reference has no iteration limit; `tend` is a module variable)
+        un = np.array(u, order="F", copy=True)
+        # first find the dt sequence: tend tiny -> 1 step; we simply run with a huge step budget bounded by tend
+        t_end = 0.0
+        probe = np.array(u, order="F", copy=True)
+        it.override("parameters_2d", nx=nx, ny=ny, ninit=ninit, nequilibrium=neq, tend=1e-300)
+        dts = []
+        for _ in range(steps):
+            c = scalar()
+            it.call("compute_max_speed", probe, c)
+            dx = 1.0 / nx
+            dts.append(0.5 * dx / float(c) * 0.5)
+            it.call("evolve", probe, weq)       # tend=1e-300: exactly one step
+        t_end = sum(dts[:-1]) + 0.5 * dts[-1]   # the loop `do while (t<tend)` then takes exactly `steps` steps
+        it.override("parameters_2d", nx=nx, ny=ny, ninit=ninit, nequilibrium=neq, tend=t_end)
+        it.call("evolve", un, weq)
+        assert np.array_equal(un, probe), "one-step-at-a-time evolve differs from the tend-bounded one"
+        out[f"{tag}/u_evolved"] = C(un)
+        out[f"{tag}/tend"] = np.array(t_end)
+        note_calls(out, tag, it)
+        print(f"fv2d {tag}: max|dudt| = {np.abs(dudt).max():.3e}, steps = {steps}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_fv2d.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------------------ 2D DG
+def dg2d_interp(**kv):
+    it = Interp()
+    for f in ("parameters_dg_2d.f90", "legendre.f90", "limiters.f90", "benchmark_2d_dg.f90"):
+        it.load(f"{REF}/2d/{f}")
+    it.override("parameters_dg_2d", **kv)
+    return it
+
+
+DG2D_CASES = [  # tag, n (nx=ny), m (mx=my), bc, source, grad_phi_case, flux_type, limiter_type, solver, ninit, steps
+    ("pulse_o3_onp", 3, 3, 1, 1, 2, "llf1", "ONP", "RK4", 1, 2),
+    ("pulse_o2_onp", 4, 2, 1, 1, 2, "llf1", "ONP", "RK4", 1, 2),
+    ("pulse_o1", 4, 1, 1, 1, 2, "llf1", "ONP", "RK4", 1, 2),
+    ("shipped_flux", 3, 2, 1, 1, 2, "llf", "ONP", "RK4", 1, 1),
+    ("hydro_o3_g1", 3, 3, 2, 2, 1, "llf1", "ONP", "RK4", 2, 1),
+    ("hydro_o2_kepler", 4, 2, 2, 2, 2, "llf1", "ONP", "EQL", 2, 2),
+    ("riemann_o3_hio", 4, 3, 2, 1, 2, "llf1", "HIO", "RK4", 3, 1),
+    ("riemann_o2_1or", 4, 2, 2, 1, 2, "llf1", "1OR", "EQL", 4, 2),
+    ("riemann_o3_low", 3, 3, 2, 1, 2, "llf1", "LOW", "DEB", 4, 2),
+    ("advsink_o2", 3, 2, 1, 3, 2, "llf1", "ONP", "SS4", 1, 1),
+    ("riemann_o4_onp", 3, 4, 3, 1, 2, "llf1", "ONP", "RK4", 5, 1),
+    ("pulse_o3_hll2", 3, 3, 1, 1, 2, "hll2", "ONP", "RK4", 1, 1),
+    ("riemann_o2_hllc", 4, 2, 2, 1, 2, "hllc", "ONP", "RK4", 3, 1),
+]
+
+
+def dg2d(only=None):
+    out = {}
+    path = os.path.join(HERE, "ref_dg2d.npz")
+    if only and os.path.exists(path):
+        out = dict(np.load(path))
+    for tag, n, m, bc, source, gcase, flux, lim, solver, ninit, steps in DG2D_CASES:
+        if only and tag not in only:
+            continue
+        t0 = time.time()
+        kv = dict(nx=n, ny=n, mx=m, my=m, bc=bc, source=source, grad_phi_case=gcase, flux_type=flux, limiter_type=lim,
+                  solver=solver, ninit=ninit)
+        it = dg2d_interp(**kv)
+        x, y = F(n, n, m, m), F(n, n, m, m)
+        it.call("get_coords", x, y, n, n, m, m)
+        nodes = F(4, n, n, m, m)
+        it.call("get_initial_conditions", x, y, nodes, n, n, m, m)
+        modes = F(4, n, n, m, m)
+        it.call("get_modes_from_nodes", nodes, modes, n, n, m, m)
+        back = F(4, n, n, m, m)
+        it.call("get_nodes_from_modes", modes, back, n, n, m, m)
+        ueq = F(4, n, n, m, m)
+        dudt = F(4, n, n, m, m)
+        it.call("compute_update", modes, x, y, ueq, dudt)
+        lim_modes = np.array(modes, order="F", copy=True)
+        it.call("apply_limiter", lim_modes)
+        # a rougher state for the limiter: the update direction added with a large step
+        rough = np.asfortranarray(modes + 0.05 * dudt / max(np.abs(dudt).max(), 1e-300) * np.abs(modes[0]).max())
+        rough_in = rough.copy(order="F")
+        it.call("apply_limiter", rough)
+        sp = [scalar() for _ in range(4)]
+        mean = np.asfortranarray(modes[:, :, :, 0, 0])
+        it.call("compute_max_speed", mean, *sp)
+        out[f"{tag}/meta"] = np.array([n, m, bc, source, gcase, ninit, steps])
+        out[f"{tag}/names"] = np.array([flux, lim, solver])
+        for k, v in (("x", x), ("y", y), ("nodes", nodes), ("modes", modes), ("nodes_back", back), ("dudt", dudt),
+                     ("limited", lim_modes), ("rough_in", rough_in), ("rough_limited", rough)):
+            out[f"{tag}/{k}"] = C(v)
+        out[f"{tag}/speeds"] = np.array([float(s) for s in sp])
+        # evolve: the reference loop has no iteration limit; bound it with `tend` (module variable).  dt of the first step:
+        cs, vx, vy, _ = (float(s) for s in sp)
+        # the limiter runs before the first step and can change the mean-mode speeds only through the modes it scales
+        # (never the means), so the first dt is known; later ones are not needed: tend = (steps - 0.5) * dt0 gives
+        # `steps` steps unless dt grows by more than 2x, and the last step is clipped by min(tend - t, ...).
+        gll = (2 * (m - 1) + 3) // 2
+        gll_w_1 = 1.0 if m == 1 else 1.0 / (float(gll * (gll - 1)) + float(np.float32(1e-10)))
+        dx = 1.0 / n
+        cfl = float(np.float32(0.2))
+        dt0 = cfl * min(1.0 / 9.0, gll_w_1 / 2.0) / ((abs(vx) + cs) / dx + (abs(vy) + cs) / dx)
+        tend = (steps - 0.5) * dt0
+        it.override("parameters_dg_2d", tend=tend, **kv)
+        un = np.array(nodes, order="F", copy=True)
+        it.call("evolve", un, x, y, ueq)
+        out[f"{tag}/tend"] = np.array(tend)
+        out[f"{tag}/nodes_evolved"] = C(un)
+        out[f"{tag}/updates_in_evolve"] = np.array(it.calls.get("compute_update", 0))
+        note_calls(out, tag, it)
+        print(f"dg2d {tag}: {time.time() - t0:.1f} s, max|dudt| = {np.abs(dudt).max():.3e}, limiter changed "
+              f"{np.abs(rough - rough_in).max():.2e}, evolve changed {np.abs(un - nodes).max():.2e}", flush=True)
+        np.savez_compressed(path, **out)
+
+
+# ------------------------------------------------------------------------------------------------ 1D FV
+def fv1d():
+    out = {}
+    # fvm.f90 (program fvm: condinit, compute_update, compute_max_speed, RK2 main loop)
+    for tag, nx, bc, source, ninit, steps in (("fvm_sod", 60, 2, 2, 4, 4), ("fvm_sine_periodic", 32, 1, 1, 1, 4),
+                                              ("fvm_hydro", 40, 2, 2, 7, 3), ("fvm_ninit2_bc1_src2", 24, 1, 2, 2, 3),
+                                              ("fvm_ninit3", 24, 2, 1, 3, 2), ("fvm_ninit5", 30, 2, 2, 5, 2),
+                                              ("fvm_ninit6", 30, 2, 2, 6, 2)):
+        it = Interp().load(f"{REF}/fvm_commons.f90").load(f"{REF}/fvm.f90")
+        kv = dict(nx=nx, bc=bc, source=source, ninit=ninit)
+        it.override("fvm_commons", tend=0.0, **kv)
+        u0 = np.array(it.run_program("fvm")["u"], order="F", copy=True)       # tend = 0: the loop body never runs
+        dudt = F(3, nx)
+        it.call("compute_update", u0, dudt)
+        c = scalar()
+        it.call("compute_max_speed", u0, c)
+        dt0 = float(np.float32(0.8)) * (1.0 / nx) / float(c) / 7.0
+        tend = (steps - 0.5) * dt0
+        it.override("fvm_commons", tend=tend, **kv)
+        fr = it.run_program("fvm")
+        out[f"{tag}/meta"] = np.array([0, nx, bc, source, ninit, int(fr["iter"])])
+        out[f"{tag}/u0"] = C(u0); out[f"{tag}/dudt"] = C(dudt); out[f"{tag}/cmax"] = c.copy()
+        out[f"{tag}/tend"] = np.array(tend); out[f"{tag}/un"] = C(fr["u"]); out[f"{tag}/clock"] = np.array([float(fr["t"]), float(fr["dt"])])
+        note_calls(out, tag, it)
+        print(f"fv1d {tag}: {int(fr['iter'])} steps, max|dudt| = {np.abs(dudt).max():.3e}", flush=True)
+    # benchmark_1d.f90 ('FVM', 'EQL', 'WB1')
+    rng = np.random.default_rng(7)
+    for tag, nx, bc, neq, solver, ninit, eta, steps, amp in (
+            ("b1_wb1_default", 64, 2, 2, "WB1", 2, None, 4, 0.0), ("b1_wb1_isentropic", 48, 2, 3, "WB1", 3, 0.0, 3, 0.0),
+            ("b1_eql_bump", 48, 2, 2, "EQL", 2, 1e-3, 4, 0.0), ("b1_eql_bc3", 40, 3, 2, "EQL", 2, 1e-3, 3, 0.0),
+            ("b1_fvm_bump", 37, 1, 2, "FVM", 2, 1e-3, 3, 0.0), ("b1_wb1_random", 32, 2, 2, "WB1", 2, 1e-2, 3, 0.05),
+            ("b1_eql_random_bc1", 32, 1, 2, "EQL", 2, 1e-2, 2, 0.05), ("b1_fvm_bc3", 30, 3, 1, "FVM", 1, 0.0, 2, 0.02),
+            ("b1_wb1_neq1", 32, 2, 1, "WB1", 1, 0.0, 2, 0.0)):
+        it = Interp().load(f"{REF}/parameters.f90").load(f"{REF}/benchmark_1d.f90")
+        kv = dict(nx=nx, bc=bc, nequilibrium=neq, solver=solver, ninit=ninit)
+        if eta is not None:
+            kv["eta"] = eta
+        it.override("parameters", **kv)
+        x = F(nx); u = F(3, nx); weq = F(3, nx)
+        it.call("get_x", x, nx)
+        it.call("get_initial_conditions", x, u, nx)
+        it.call("get_equilibrium_solution", x, weq, nx)
+        out[f"{tag}/u_ic"] = C(u)
+        if amp:
+            u *= 1.0 + amp * rng.standard_normal(u.shape)
+            u[1] = amp * rng.standard_normal(nx)
+        d = {}
+        for name in ("compute_update", "compute_update_fvm", "compute_update_sr"):
+            d[name] = F(3, nx)
+            it.call(name, u, weq, d[name])
+        c = scalar()
+        it.call("compute_max_speed", u, c)
+        dt0 = float(np.float32(0.8)) * (1.0 / nx) / float(c) / 3.0
+        tend = (steps - 0.5) * dt0
+        it.override("parameters", tend=tend, **kv)
+        un = np.array(u, order="F", copy=True)
+        fr = it.call("evolve", un, weq, x)
+        out[f"{tag}/meta"] = np.array([1, nx, bc, neq, ninit, int(fr["iter"])])
+        out[f"{tag}/solver"] = np.array(solver)
+        out[f"{tag}/eta"] = np.array(float(it.get("parameters", "eta")))
+        for k, v in (("x", x), ("u", u), ("weq", weq), ("dudt_eql", d["compute_update"]), ("dudt_fvm", d["compute_update_fvm"]),
+                     ("dudt_sr", d["compute_update_sr"]), ("un", un)):
+            out[f"{tag}/{k}"] = C(v)
+        out[f"{tag}/cmax"] = c.copy(); out[f"{tag}/tend"] = np.array(tend)
+        out[f"{tag}/clock"] = np.array([float(fr["t"]), float(fr["dt"])])
+        note_calls(out, tag, it)
+        print(f"fv1d {tag}: {int(fr['iter'])} steps, max|dudt_sr| = {np.abs(d['compute_update_sr']).max():.3e}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_fv1d.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d", "dg1d"]
+    np.seterr(all="ignore")
+    for w in which:
+        if ":" in w:
+            fam, tags = w.split(":")
+            globals()[fam](only=tags.split(","))
+        else:
+            globals()[w]()

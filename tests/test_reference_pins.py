@@ -1,0 +1,127 @@
+"""Pins the C oracle (oracle/*.c) to the reference itself.
+
+tests/golden/ref_*.npz were produced by executing the reference's own .f90 source text (unmodified, read from
+/root/reference) with the Fortran-90 interpreter in oracle/f90interp.py -- see tests/golden/make_ref_golden.py.
+Here the C restatement must reproduce those outputs on the same inputs.  The bar is BITWISE equality (`==` on
+every double): the interpreter implements gfortran's arithmetic without FMA contraction and calls the same glibc
+`exp`/`pow` the oracle does.  /root/reference is NOT needed to run these tests; when it is present one small case is
+also re-executed live, so the committed vectors cannot drift from the script that made them.
+"""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("WB_REFERENCE", "/root/reference")
+
+
+def gold(name):
+    return np.load(os.path.join(HERE, "golden", name))
+
+
+def tags(name):
+    return sorted({k.split("/")[0] for k in gold(name).files})
+
+
+def same(a, b):
+    """bitwise equality of two double arrays (NaN == NaN, +0 == -0 is NOT accepted unless both are zero-valued)"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+def maxdiff(a, b):
+    return float(np.nanmax(np.abs(np.asarray(a) - np.asarray(b)))) if np.asarray(a).size else 0.0
+
+
+# ------------------------------------------------------------------------------------------------ 2D FV
+@pytest.mark.parametrize("tag", tags("ref_fv2d.npz"))
+def test_fv2d_oracle_equals_reference_source(oracle, tag):
+    """benchmark_2d.f90: get_coords :25-43, get_initial_conditions :45-113, get_equilibrium_solution :174-218,
+    compute_primitive :145-157, compute_conservative :159-171, compute_max_speed :264-279,
+    compute_update_exact :465-618, compute_update :370-463, evolve :221-260."""
+    g = gold("ref_fv2d.npz")
+    nx, ny, ninit, neq, steps = (int(v) for v in g[f"{tag}/meta"])
+    o = oracle
+    p = o.fv2d_params(nx, ny, neq)
+    x, y = o.fv2d_get_coords(p)
+    assert same(x, g[f"{tag}/x"]) and same(y, g[f"{tag}/y"])
+    assert same(o.fv2d_get_equilibrium_solution(p, x, y), g[f"{tag}/weq"])
+    assert same(o.fv2d_get_initial_conditions(p, ninit, x, y), g[f"{tag}/u_ic"])
+    u, weq = g[f"{tag}/u"], g[f"{tag}/weq"]
+    assert same(o.fv2d_compute_primitive(p, u), g[f"{tag}/w"])
+    assert same(o.fv2d_compute_conservative(p, g[f"{tag}/w"]), g[f"{tag}/u_back"])
+    assert o.fv2d_compute_max_speed(p, u) == float(g[f"{tag}/cmax"])
+    d = o.fv2d_compute_update_exact(p, u, weq)
+    assert same(d, g[f"{tag}/dudt"]), maxdiff(d, g[f"{tag}/dudt"])
+    if f"{tag}/dudt_plain" in g.files:      # for nx < ny the reference itself indexes out of bounds (:418)
+        d = o.fv2d_compute_update(p, u, weq)
+        assert same(d, g[f"{tag}/dudt_plain"]), maxdiff(d, g[f"{tag}/dudt_plain"])
+    un, it, t, dt, cm = o.fv2d_evolve(p, u, weq, float(g[f"{tag}/tend"]), -1)
+    assert it == steps
+    assert same(un, g[f"{tag}/u_evolved"]), maxdiff(un, g[f"{tag}/u_evolved"])
+
+
+def test_fv2d_goldens_exercised_the_reference_routines():
+    g = gold("ref_fv2d.npz")
+    called = {c.split(":")[0] for c in g["random/calls"]}
+    assert {"compute_update_exact", "compute_update", "compute_llflux", "compute_speed", "compute_flux", "get_source",
+            "compute_max_speed", "evolve", "get_equilibrium_solution", "compute_conservative", "compute_primitive"} <= called
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+def test_fv2d_live_interpretation_matches_committed_vectors():
+    from oracle.f90interp import Interp
+    g = gold("ref_fv2d.npz")
+    tag = "ragged"
+    nx, ny, ninit, neq, _ = (int(v) for v in g[f"{tag}/meta"])
+    it = Interp().load(f"{REF}/parameters_2d.f90").load(f"{REF}/benchmark_2d.f90")
+    it.override("parameters_2d", nx=nx, ny=ny, ninit=ninit, nequilibrium=neq)
+    u = np.asfortranarray(g[f"{tag}/u"].T)
+    weq = np.asfortranarray(g[f"{tag}/weq"].T)
+    dudt = np.zeros_like(u)
+    it.call("compute_update_exact", u, weq, dudt)
+    assert same(dudt.T, g[f"{tag}/dudt"])
+
+
+# ------------------------------------------------------------------------------------------------ 1D FV
+@pytest.mark.parametrize("tag", [t for t in tags("ref_fv1d.npz") if t.startswith("fvm_")])
+def test_fvm1d_oracle_equals_reference_source(oracle, tag):
+    """fvm.f90: condinit :99-174, compute_update :188-251 (+ compute_source, compute_llflux, compute_flux,
+    compute_speed), compute_max_speed :320-336, the RK2 main loop of program fvm :56-76."""
+    g = gold("ref_fv1d.npz")
+    _, nx, bc, source, ninit, iters = (int(v) for v in g[f"{tag}/meta"])
+    o = oracle
+    p = o.fvm1d_params(nx=nx, bc=bc, source=source)
+    u0 = g[f"{tag}/u0"]
+    assert same(o.fvm1d_initial_conditions(p, ninit), u0)
+    assert o.fvm1d_compute_max_speed(p, u0) == float(g[f"{tag}/cmax"])
+    d = o.fvm1d_compute_update(p, u0)
+    assert same(d, g[f"{tag}/dudt"]), maxdiff(d, g[f"{tag}/dudt"])
+    un, it, t, dt = o.fvm1d_evolve(p, u0, float(g[f"{tag}/tend"]), -1)
+    assert it == iters and (t, dt) == tuple(g[f"{tag}/clock"])
+    assert same(un, g[f"{tag}/un"]), maxdiff(un, g[f"{tag}/un"])
+
+
+@pytest.mark.parametrize("tag", [t for t in tags("ref_fv1d.npz") if t.startswith("b1_")])
+def test_fv1d_oracle_equals_reference_source(oracle, tag):
+    """benchmark_1d.f90: get_x :24-38, get_initial_conditions :40-67, get_equilibrium_solution :127-155,
+    compute_max_speed :157-170, compute_update ('EQL') :263-377, compute_update_fvm :454-549,
+    compute_update_sr ('WB1') :553-747, evolve :200-261."""
+    g = gold("ref_fv1d.npz")
+    _, nx, bc, neq, ninit, iters = (int(v) for v in g[f"{tag}/meta"])
+    solver = str(g[f"{tag}/solver"])
+    o = oracle
+    p = o.fv1d_params(nx=nx, bc=bc, nequilibrium=neq, solver=solver)
+    x = o.fv1d_get_x(p)
+    assert same(x, g[f"{tag}/x"])
+    assert same(o.fv1d_get_equilibrium_solution(p, x), g[f"{tag}/weq"])
+    assert same(o.fv1d_get_initial_conditions(p, ninit, x, float(g[f"{tag}/eta"])), g[f"{tag}/u_ic"])
+    u, weq = g[f"{tag}/u"], g[f"{tag}/weq"]
+    assert o.fv1d_compute_max_speed(p, u) == float(g[f"{tag}/cmax"])
+    for key, fn in (("dudt_eql", o.fv1d_compute_update), ("dudt_fvm", o.fv1d_compute_update_fvm), ("dudt_sr", o.fv1d_compute_update_sr)):
+        d = fn(p, u, weq)
+        assert same(d, g[f"{tag}/{key}"]), (key, maxdiff(d, g[f"{tag}/{key}"]))
+    un, it, t, dt = o.fv1d_evolve(p, u, weq, float(g[f"{tag}/tend"]), -1)
+    assert it == iters and (t, dt) == tuple(g[f"{tag}/clock"])
+    assert same(un, g[f"{tag}/un"]), maxdiff(un, g[f"{tag}/un"])
