@@ -930,6 +930,7 @@ class Interp:
         self.calls = {}           # procedure name -> number of calls (coverage evidence for the goldens)
         self.hooks = {}           # procedure name -> python callable(interp, frame) replacing the body (unused by default)
         self.files = []
+        self.probes = {}          # line number -> callable(dict of the running unit's variables): test harness taps
         self.depth = 0
         self.trace = trace
 
@@ -1226,8 +1227,12 @@ class Interp:
                     return _Actual("elem", var=v, idx=idx)
                 if not ok:
                     self.oob_count += 1
-                    raise FortranBoundsError(f"actual argument: section of {e[1]} with a subscript out of bounds "
-                                             f"(0-based {idx}, shape {v.a.shape})")
+                    if self.oob == "raise" or v.a.dtype.kind != "f":
+                        raise FortranBoundsError(f"actual argument: section of {e[1]} with a subscript out of bounds "
+                                                 f"(0-based {idx}, shape {v.a.shape})")
+                    # memory outside the array: undefined values in, stores lost
+                    shp = tuple(len(range(*i.indices(n))) for i, n in zip(idx, v.a.shape) if isinstance(i, slice))
+                    return _Actual("value", value=np.full(shp, np.nan, dtype=v.a.dtype, order="F"))
                 return _Actual("section", var=v, idx=idx)
         return _Actual("value", value=self.ev(e, fr))
 
@@ -1466,6 +1471,8 @@ class Interp:
     def run(self, body, fr):
         for st in body:
             k = st[0]
+            if self.probes and st[-1] in self.probes:
+                self.probes[st[-1]]({n: v.a for n, v in fr.items()})
             try:
                 if k == "assign":
                     self.assign(st[1], self.ev(st[2], fr), fr)

@@ -272,6 +272,112 @@ def fv1d():
     np.savez_compressed(os.path.join(HERE, "ref_fv1d.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------ 1D DG
+DG1D_CASES = [  # tag, n, nx, riemann, source, ninit, pert, bc, use_limiter, integrator, steps
+    ("rki_default_hllc", 3, 32, 2, 2, 8, None, 5, False, "RKi", 2),
+    ("rki_llf_o2", 2, 24, 1, 2, 8, 1e-3, 5, False, "RKi", 2),
+    ("rki_hllc_o1", 1, 20, 2, 2, 8, 1e-2, 5, False, "RKi", 3),
+    ("rki_sod_nosource", 3, 20, 2, 1, 4, 0.0, 5, False, "RKi", 2),
+    ("rki_steady_hllc", 3, 16, 2, 2, 7, 0.0, 5, False, "RKi", 2),
+    ("rk2_periodic_lim", 3, 24, 2, 2, 8, 1e-2, 1, True, "RK2", 2),
+    ("rk3_zerograd", 3, 20, 1, 2, 8, 1e-3, 2, True, "RK3", 2),
+    ("rk4_reflect", 2, 17, 2, 2, 8, 1e-3, 3, True, "RK4", 2),
+    ("rk1_sod_bc2", 3, 20, 2, 1, 4, 0.0, 2, False, "RK1", 3),
+    ("rk3_sod_lim", 3, 24, 2, 1, 4, 0.0, 2, True, "RK3", 3),
+    ("rk2_bc4", 2, 16, 1, 2, 8, 1e-2, 4, False, "RK2", 2),
+    ("rkw_bc5", 3, 20, 2, 2, 8, 1e-3, 5, False, "RKw", 2),
+    ("rkw_bc4_llf", 2, 16, 1, 2, 8, 1e-2, 4, False, "RKw", 2),
+    ("rke_bc5", 3, 20, 1, 2, 8, 1e-3, 5, False, "RKe", 2),
+    ("rke_lim_bc2", 3, 20, 2, 2, 8, 1e-2, 2, True, "RKe", 2),
+]
+
+
+def dg1d(only=None):
+    out = {}
+    path = os.path.join(HERE, "ref_dg1d.npz")
+    if only and os.path.exists(path):
+        out = dict(np.load(path))
+    rng = np.random.default_rng(5)
+    for tag, n, nx, riemann, source, ninit, pert, bc, use_limiter, integ, steps in DG1D_CASES:
+        if only and tag not in only:
+            continue
+        t0 = time.time()
+        it = Interp(oob="nan").load(f"{REF}/dg_commons.f90").load(f"{REF}/legendre.f90").load(f"{REF}/dg_with_source.f90")
+        kv = dict(n=n, nx=nx, riemann=riemann, source=source, ninit=ninit, bc=bc, use_limiter=use_limiter, integrator=integ)
+        if pert is not None:
+            kv["pert"] = pert
+        it.override("dg_commons", tend=0.0, **kv)
+        # program dg projects the initial condition into `u` (:36-55) and then ZEROES `u` again in the set-up of delta_u
+        # (:152), so as shipped every integrator but 'RKi'/'RKe' starts from u = 0 (0/0 = NaN).  The harness taps the
+        # projection before it is zeroed (statement at line 62) and, for the timed run below, puts it back when the
+        # clock is initialised (statement `t=0`, line 171): inputs are injected, no statement is changed or skipped.
+        tap = {}
+        it.probes = {62: lambda v: tap.setdefault("u", np.array(v["u"], order="F", copy=True))}
+        fr = it.run_program("dg")              # tend = 0: set-up only (projections, equilibrium, module quadrature tables)
+        it.probes = {}
+        assert not np.any(fr["u"]), "the reference zeroes u before its main loop"
+        u = tap["u"]
+        du, ueq, q, ui = (np.array(fr[k], order="F", copy=True) for k in ("delta_u", "u_eq", "u_eq_modes", "u_init"))
+        out[f"{tag}/meta"] = np.array([n, nx, riemann, source, ninit, bc, int(use_limiter), steps])
+        out[f"{tag}/integrator"] = np.array(integ)
+        out[f"{tag}/pert"] = np.array(float(it.get("dg_commons", "pert")))
+        out[f"{tag}/quad"] = np.array([it.get("dg_commons", "chsi_quad"), it.get("dg_commons", "w_quad")])
+        for k, v in (("u", u), ("du", du), ("ueq", ueq), ("q", q), ("ui", ui)):
+            out[f"{tag}/{k}"] = C(v)
+        c = scalar()
+        it.call("compute_max_speed", ui, c)
+        out[f"{tag}/cmax"] = c.copy()
+        oob0 = it.oob_count
+        d = F(3, n, nx)
+        it.call("compute_update_exact_delta", du, ueq, d)
+        out[f"{tag}/dudt_delta"] = C(d)
+        out[f"{tag}/oob_delta"] = np.array(it.oob_count - oob0)
+        # rougher modes for the limiters and the plain updates
+        rough = np.array(u, order="F", copy=True)
+        if n > 1:
+            rough[:, 1:, :] += 1e-3 * rng.standard_normal(rough[:, 1:, :].shape)
+            rough[0, 1, nx // 3] += 3.0 * rough[0, 0, nx // 3]          # a negative density trace
+            rough[2, 1, 2 * nx // 3] += 30.0 * rough[2, 0, 2 * nx // 3]  # a negative energy trace
+        out[f"{tag}/rough"] = C(rough)
+        for name, key in (("compute_update", "dudt_plain"),):
+            oob0 = it.oob_count
+            d = F(3, n, nx)
+            it.call(name, u, d)
+            if it.oob_count == oob0:
+                out[f"{tag}/{key}"] = C(d)
+        oob0 = it.oob_count
+        d = F(3, n, nx)
+        it.call("compute_update_exact", u, q, d)
+        if it.oob_count == oob0 or bc in (4, 5):
+            out[f"{tag}/dudt_exact"] = C(d)
+        out[f"{tag}/oob_exact"] = np.array(it.oob_count - oob0)
+        for name, key in (("limiter", "lim"), ("limiter_cons", "lim_cons")) + ((("limiter_tdv", "lim_tdv"),) if not use_limiter else ()):
+            v = np.array(rough, order="F", copy=True)
+            oob0 = it.oob_count
+            it.call(name, v)
+            if it.oob_count == oob0:
+                out[f"{tag}/{key}"] = C(v)
+        dt0 = float(np.float32(0.9)) * (1.0 / nx) / float(c) / (2.0 * n + 1.0)
+        tend = (steps - 0.5) * dt0
+        it.override("dg_commons", tend=tend, **kv)
+
+        def inject(v, u=u):
+            v["u"][...] = u
+        it.probes = {171: inject}
+        fr = it.run_program("dg")
+        it.probes = {}
+        out[f"{tag}/tend"] = np.array(tend)
+        out[f"{tag}/iters"] = np.array(int(fr["iter"]))
+        out[f"{tag}/clock"] = np.array([float(fr["t"]), float(fr["dt"])])
+        for k, v in (("u_end", fr["u"]), ("du_end", fr["delta_u"]), ("ureal_end", fr["ureal"])):
+            out[f"{tag}/{k}"] = C(v)
+        out[f"{tag}/oob_total"] = np.array(it.oob_count)
+        note_calls(out, tag, it)
+        print(f"dg1d {tag}: {time.time() - t0:.1f} s, {int(fr['iter'])} steps, oob reads {it.oob_count}, keys "
+              f"{sorted(k.split('/')[1] for k in out if k.startswith(tag + '/') and 'dudt' in k or k.startswith(tag + '/lim'))}", flush=True)
+        np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d", "dg1d"]
     np.seterr(all="ignore")

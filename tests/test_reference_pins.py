@@ -125,3 +125,66 @@ def test_fv1d_oracle_equals_reference_source(oracle, tag):
     un, it, t, dt = o.fv1d_evolve(p, u, weq, float(g[f"{tag}/tend"]), -1)
     assert it == iters and (t, dt) == tuple(g[f"{tag}/clock"])
     assert same(un, g[f"{tag}/un"]), maxdiff(un, g[f"{tag}/un"])
+
+
+# ------------------------------------------------------------------------------------------------ 1D DG
+def _nan_aware_same(got, ref):
+    """Entries the reference computes from memory outside its arrays (faces 1 and nx+1 without an index clamp,
+    dg_with_source.f90:1903-1914) are NaN in the interpreted run; everything else must agree bit for bit."""
+    ref = np.asarray(ref)
+    m = ~np.isnan(ref)
+    return got.shape == ref.shape and np.array_equal(np.asarray(got)[m], ref[m]), int((~m).sum())
+
+
+@pytest.mark.parametrize("tag", tags("ref_dg1d.npz"))
+def test_dg1d_oracle_equals_reference_source(oracle, tag):
+    """dg_with_source.f90: set-up of program dg :26-171 (projections with root legendre.f90's single-precision basis and
+    quadrature), compute_max_speed :1136-1153, compute_update_exact_delta :1749-2031, compute_update :807-1028,
+    compute_update_exact :1380-1744, limiter :414-519, limiter_TDV :523-608, limiter_cons :610-734,
+    riemann_llf/hllc :1299-1374, and the main loop :173-336 for every integrator."""
+    g = gold("ref_dg1d.npz")
+    n, nx, riemann, source, ninit, bc, use_limiter, steps = (int(v) for v in g[f"{tag}/meta"])
+    integ = str(g[f"{tag}/integrator"])
+    o = oracle
+    p = o.dg1d_params(n=n, nx=nx, riemann=riemann, source=source, ninit=ninit, pert=float(g[f"{tag}/pert"]), bc=bc,
+                      use_limiter=use_limiter)
+    xq, wq = o.dg1d_quadrature(p)
+    assert same(xq, g[f"{tag}/quad"][0]) and same(wq, g[f"{tag}/quad"][1])
+    ui, ueq, du = o.dg1d_setup(p)
+    assert same(ui, g[f"{tag}/ui"]) and same(ueq, g[f"{tag}/ueq"])
+    assert same(du, g[f"{tag}/du"]), maxdiff(du, g[f"{tag}/du"])
+    u, q = o.dg1d_project(p, ui), o.dg1d_project(p, ueq)
+    assert same(u, g[f"{tag}/u"]) and same(q, g[f"{tag}/q"])
+    assert o.dg1d_compute_max_speed(p, ui) == float(g[f"{tag}/cmax"])
+    d = o.dg1d_compute_update_exact_delta(p, du, ueq)
+    assert same(d, g[f"{tag}/dudt_delta"]), maxdiff(d, g[f"{tag}/dudt_delta"])
+    if f"{tag}/dudt_plain" in g.files:
+        d = o.dg1d_compute_update(p, u)
+        assert same(d, g[f"{tag}/dudt_plain"]), maxdiff(d, g[f"{tag}/dudt_plain"])
+    if f"{tag}/dudt_exact" in g.files:
+        d = o.dg1d_compute_update_exact(p, u, q)
+        ok, nans = _nan_aware_same(d, g[f"{tag}/dudt_exact"])
+        assert ok and nans <= 2 * 3 * n, (nans, maxdiff(d, g[f"{tag}/dudt_exact"]))
+    rough = g[f"{tag}/rough"]
+    for key, fn in (("lim", o.dg1d_limiter), ("lim_cons", o.dg1d_limiter_cons), ("lim_tdv", o.dg1d_limiter_tdv)):
+        if f"{tag}/{key}" in g.files:
+            v = fn(p, rough)
+            assert same(v, g[f"{tag}/{key}"]), (key, maxdiff(v, g[f"{tag}/{key}"]))
+    tend = float(g[f"{tag}/tend"])
+    if integ == "RKi":
+        dd, ui2, it, t, dt = o.dg1d_evolve_rki(p, du, ueq, ui, tend)
+        uu = None
+    elif integ in ("RKw", "RKe"):
+        uu, dd, ui2, it, t, dt = o.dg1d_evolve_w(p, integ, u, du, ueq, q, ui, tend)
+    else:
+        uu, ui2, it, t, dt = o.dg1d_evolve_rk(p, integ, u, du, ueq, ui, tend)
+        dd = None
+    assert it == int(g[f"{tag}/iters"]) and (t, dt) == tuple(g[f"{tag}/clock"])
+    if dd is not None:
+        ok, nans = _nan_aware_same(dd, g[f"{tag}/du_end"])
+        assert ok, maxdiff(dd, g[f"{tag}/du_end"])
+    if uu is not None:
+        ok, nans = _nan_aware_same(uu, g[f"{tag}/u_end"])
+        assert ok, maxdiff(uu, g[f"{tag}/u_end"])
+    ok, nans = _nan_aware_same(ui2, g[f"{tag}/ureal_end"])
+    assert ok, maxdiff(ui2, g[f"{tag}/ureal_end"])
