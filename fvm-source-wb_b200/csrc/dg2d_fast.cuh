@@ -459,14 +459,25 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
       for (int a = 0; a < M; ++a) PL(out, g, v, b * M + a)[e] = acc[v][a][b];
 }
 
+// A step enqueued past `tend` is skipped on the device, but the host has already rotated its buffer pointers for it
+// (new delta_u = the last stage's `out`): a skipped stage therefore hands its input through unchanged, so that after
+// any number of skipped steps the buffer the host calls delta_u holds delta_u.
+template <int M>
+__device__ __forceinline__ void dg_stage_pass_through(const double* __restrict__ in, double* __restrict__ out, const DgGrid& g, size_t e) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int m = 0; m < M * M; ++m) PL(out, g, v, m)[e] = PL(in, g, v, m)[e];
+}
+
 template <int M, bool ANYFLUX>
 __global__ void __launch_bounds__(64) k_dg_stage_fast(const double* __restrict__ in, StageCoef C, double* __restrict__ out,
                                                       const double* __restrict__ gx, const double* __restrict__ gy,
                                                       const unsigned char* __restrict__ fz, DgGrid g, DgPhys P, FastBasis B,
                                                       const DgCtrl* __restrict__ ctrl, int apply_onp) {
-  if (ctrl->skip) return;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.ne) return;
+  if (ctrl->skip) { dg_stage_pass_through<M>(in, out, g, e); return; }
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
   GlobalSrc<M> src{in, g, e,
                    {(size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nyg), (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nyg),

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(32) k_dg_stage_tma(const __grid_constant__ CUt
                                                      const double* __restrict__ gy, const unsigned char* __restrict__ fz, DgGrid g,
                                                      DgPhys P, FastBasis B, const DgCtrl* __restrict__ ctrl, int apply_onp) {
   extern __shared__ __align__(128) unsigned char dgt_smem[];
-  if (ctrl->skip) return;
+  if (ctrl->skip) { dg_stage_pass_through<M>(in, out, g, (size_t)blockIdx.x * 32 + threadIdx.x); return; }
   constexpr int REGION_B = SmemSrc<M>::REGION_B;
   const int lane = threadIdx.x;
   const size_t e0 = (size_t)blockIdx.x * 32;          // nx % 32 == 0: the 32 elements of a block lie in one row

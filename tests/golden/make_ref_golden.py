@@ -202,6 +202,39 @@ def dg2d(only=None):
         np.savez_compressed(path, **out)
 
 
+def dg2d_limiters():
+    """apply_limiter on rough data: every limiter has to act (negative density / pressure points, steep linear modes)."""
+    out = {}
+    rng = np.random.default_rng(99)
+    for lim in ("ONP", "HIO", "1OR", "LOW"):
+        for n, m, bc in ((3, 3, 1), (4, 2, 2), (3, 2, 3)):
+            tag = f"{lim.lower()}_n{n}_m{m}_bc{bc}"
+            t0 = time.time()
+            it = dg2d_interp(nx=n, ny=n, mx=m, my=m, bc=bc, limiter_type=lim, flux_type="llf1", ninit=1)
+            modes = F(4, n, n, m, m)
+            modes[0, :, :, 0, 0] = 1.0 + 0.5 * rng.random((n, n))
+            modes[1, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n))
+            modes[2, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n))
+            modes[3, :, :, 0, 0] = 2.5 + rng.random((n, n))
+            hi = 0.08 * rng.standard_normal((4, n, n, m, m))
+            hi[:, :, :, 0, 0] = 0.0
+            modes += hi
+            modes[0, 0, 1, 0, 1] = 0.9            # density dips below zero at a face point of cell (1,2)
+            modes[3, 1, 0, 1, 0] = -2.0           # energy (pressure) dips in cell (2,1)
+            if m > 2:
+                modes[0, 2, 2, 2, 2] = 0.4
+            inp = modes.copy(order="F")
+            it.call("apply_limiter", modes)
+            out[f"{tag}/meta"] = np.array([n, m, bc])
+            out[f"{tag}/limiter"] = np.array(lim)
+            out[f"{tag}/in"] = C(inp)
+            out[f"{tag}/out"] = C(modes)
+            note_calls(out, tag, it)
+            print(f"dg2d limiter {tag}: {time.time() - t0:.1f} s, changed {np.abs(modes - inp).max():.3e} in "
+                  f"{int((np.abs(modes - inp).reshape(4, n * n, m * m).max(axis=(0, 2)) > 0).sum())}/{n * n} cells", flush=True)
+            np.savez_compressed(os.path.join(HERE, "ref_dg2d_limiters.npz"), **out)
+
+
 # ------------------------------------------------------------------------------------------------ 1D FV
 def fv1d():
     out = {}

@@ -216,6 +216,26 @@ def test_fused_limiter_acts_like_the_reference_one(wb, oracle):
     assert it2 == it == 2 and field_err(got, ref) <= 1e-12
 
 
+@pytest.mark.parametrize("nx", [8, 32])
+@pytest.mark.parametrize("solver", ["RK4", "EQL", "DEB"])
+@pytest.mark.parametrize("steps", [1, 2, 3])
+def test_steps_enqueued_past_tend_leave_the_state_alone(wb, oracle, nx, solver, steps):
+    """wb_dg2d_evolve enqueues steps in batches and the device skips those past tend; the host rotates its buffers for
+    every enqueued step, so a skipped stage has to hand its input through (found by the reference pins: with an odd
+    number of skipped steps the fused path returned a stale RK work array).  nx = 32 runs the TMA-staged kernel."""
+    p, s, x, y = mk(oracle, wb, nx, 2, arith=0, flux="llf1", limiter="ONP", solver=solver, ninit=1, bc=1)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    _, _, _, dt0 = oracle.dg2d_evolve(p, u0, x, y, 1.0, 1)
+    tend = (steps - 0.5) * dt0
+    ref, it, t, dt = oracle.dg2d_evolve(p, u0, x, y, tend, -1)
+    with s:
+        got, it2, t2, dt2 = s.evolve(u0, x, y, tend, -1)          # batches of 8: 8 - steps skipped steps
+        got_b, it3, _, _ = s.evolve(u0, x, y, tend, it)           # exactly the steps needed enqueued
+    assert it == it2 == it3 and 1 <= it <= steps and t2 == tend
+    assert np.array_equal(got, got_b)
+    assert field_err(got, ref) <= 1e-12
+
+
 def test_evolve_until_tend_clamps_the_last_step(wb, oracle):
     """dt = min(tend - t, ...) (:671): t lands on tend exactly."""
     p, s, x, y = mk(oracle, wb, 8, 2, flux="llf1", ninit=1)

@@ -188,3 +188,56 @@ def test_dg1d_oracle_equals_reference_source(oracle, tag):
         assert ok, maxdiff(uu, g[f"{tag}/u_end"])
     ok, nans = _nan_aware_same(ui2, g[f"{tag}/ureal_end"])
     assert ok, maxdiff(ui2, g[f"{tag}/ureal_end"])
+
+
+# ------------------------------------------------------------------------------------------------ 2D DG
+def _dg2d_params(o, g, tag):
+    n, m, bc, source, gcase, ninit, steps = (int(v) for v in g[f"{tag}/meta"])
+    flux, lim, solver = (str(s) for s in g[f"{tag}/names"])
+    return o.dg2d_params(nx=n, ny=n, mx=m, my=m, bc=bc, source=source, grad_phi_case=gcase, flux=flux, limiter=lim,
+                         solver=solver, ninit=ninit), steps
+
+
+@pytest.mark.parametrize("tag", tags("ref_dg2d.npz"))
+def test_dg2d_oracle_equals_reference_source(oracle, tag):
+    """2d/benchmark_2d_dg.f90: get_coords :93-120, get_initial_conditions :122-466, get_modes_from_nodes :497-542,
+    get_nodes_from_modes :544-592, compute_update :1137-1479 (+ compute_flux, compute_flux_int, compute_num_flux,
+    compute_llflux / compute_hllflux / compute_hllcflux, get_boundary_conditions, get_source, grad_phi,
+    special_boundary_conditions), compute_max_speed :826-870, apply_limiter :1516-1555, evolve :624-775;
+    2d/legendre.f90 legendre, legendre_prime, gl_quadrature, gll_quadrature; 2d/limiters.f90 compute_positivity,
+    compute_set, solve_for_t, high_order_limiter, limiting, minmod2d, generalized_minmod, compute_limiter,
+    limiter_low_order."""
+    g = gold("ref_dg2d.npz")
+    o = oracle
+    p, steps = _dg2d_params(o, g, tag)
+    x, y = o.dg2d_get_coords(p)
+    assert same(x, g[f"{tag}/x"]) and same(y, g[f"{tag}/y"])
+    nodes = o.dg2d_get_initial_conditions(p, x, y)
+    assert same(nodes, g[f"{tag}/nodes"]), maxdiff(nodes, g[f"{tag}/nodes"])
+    modes = o.dg2d_get_modes_from_nodes(p, nodes)
+    assert same(modes, g[f"{tag}/modes"])
+    assert same(o.dg2d_get_nodes_from_modes(p, modes), g[f"{tag}/nodes_back"])
+    d = o.dg2d_compute_update(p, modes, x, y)
+    assert same(d, g[f"{tag}/dudt"]), maxdiff(d, g[f"{tag}/dudt"])
+    assert o.dg2d_compute_max_speed(p, modes) == tuple(g[f"{tag}/speeds"])
+    v = o.dg2d_apply_limiter(p, modes)
+    assert same(v, g[f"{tag}/limited"]), maxdiff(v, g[f"{tag}/limited"])
+    v = o.dg2d_apply_limiter(p, g[f"{tag}/rough_in"])
+    assert same(v, g[f"{tag}/rough_limited"]), maxdiff(v, g[f"{tag}/rough_limited"])
+    if f"{tag}/nodes_evolved" in g.files:
+        un, it, t, dt = o.dg2d_evolve(p, nodes, x, y, float(g[f"{tag}/tend"]), -1)
+        assert it == steps and t == float(g[f"{tag}/tend"])
+        assert same(un, g[f"{tag}/nodes_evolved"]), maxdiff(un, g[f"{tag}/nodes_evolved"])
+
+
+@pytest.mark.parametrize("tag", tags("ref_dg2d_limiters.npz"))
+def test_dg2d_limiters_on_rough_data_equal_reference_source(oracle, tag):
+    """apply_limiter on data where every limiter acts: negative density / pressure at points of the Zhang-Shu set
+    (2d/limiters.f90 compute_positivity :478-654), steep modes (high_order_limiter :1478-1583, compute_limiter :203-309,
+    limiter_low_order :769-860)."""
+    g = gold("ref_dg2d_limiters.npz")
+    n, m, bc = (int(v) for v in g[f"{tag}/meta"])
+    p = oracle.dg2d_params(nx=n, ny=n, mx=m, my=m, bc=bc, limiter=str(g[f"{tag}/limiter"]), flux="llf1", ninit=1)
+    v = oracle.dg2d_apply_limiter(p, g[f"{tag}/in"])
+    assert not same(g[f"{tag}/in"], g[f"{tag}/out"])
+    assert same(v, g[f"{tag}/out"]), maxdiff(v, g[f"{tag}/out"])
