@@ -4,10 +4,13 @@
  * dg_with_source.f90 (module dg_commons.f90, basis in the ROOT legendre.f90): integrator 'RKi' = SSPRK(5,4) on the
  * perturbation delta_u with compute_update_exact_delta (:1749-2031), riemann_hllc (:1318-1374, default riemann=2) or
  * riemann_llf (:1299-1316), source term, nodal reconstruction and time-step control of the main loop (:173-336).
- * Not restated (yet): 'RK1'..'RK4' (compute_update), 'RKw' (compute_update_exact) and the limiters (use_limiter=F).
+ * Also restated: 'RK1'..'RK4' (compute_update + limiter), 'RKw' (compute_update_exact + limiter_TDV), 'RKe' (limiter_cons).
  *
- * PARITY UNPINNED by reference artefacts; pinned by the invariants of SURVEY section 4.2: with ninit=7 (delta_u == 0)
- * the RHS is exactly zero for riemann_llf and O(ulp/dx) for HLLC (tests/test_oracle_dg1d.py).
+ * PARITY PINNED TO THE REFERENCE'S OWN SOURCE TEXT: dg_with_source.f90 + the root legendre.f90 are EXECUTED, unmodified,
+ * by the Fortran-90 interpreter oracle/f90interp.py (no Fortran compiler in the image); this file reproduces the vectors
+ * (tests/golden/ref_dg1d.npz, generator tests/golden/make_ref_golden.py) BIT FOR BIT: the set-up of program dg, all
+ * three update routines, the three limiters and the main loop with every integrator (tests/test_reference_pins.py).
+ * Additional pins: the invariants of SURVEY section 4.2 (tests/test_oracle_dg1d.py).
  *
  * Layout: Fortran u(nvar,n,nx) == C double[nx][n][3].
  * Literal kinds: root legendre.f90 normalises P0..P2 with SINGLE-precision sqrt constants; its gl_quadrature

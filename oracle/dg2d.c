@@ -3,10 +3,13 @@
  * CPU restatement (plain C, FP64, -ffp-contract=off) of the 2D modal discontinuous-Galerkin path of the
  * reference: 2d/benchmark_2d_dg.f90, 2d/legendre.f90, 2d/limiters.f90 (module 2d/parameters_dg_2d.f90).
  *
- * PARITY UNPINNED by reference artefacts (no Fortran compiler in the image, no golden vectors in the
- * reference).  Pinned by: the fixed point of 2d/test2d.f90 (modes<->nodes round trip), exactness of the
- * projection for polynomials, conservation/periodicity invariants and the textbook GL nodes
- * (tests/test_oracle_dg2d.py).
+ * PARITY PINNED TO THE REFERENCE'S OWN SOURCE TEXT (no Fortran compiler in the image, no golden vectors in the
+ * reference): 2d/benchmark_2d_dg.f90, 2d/legendre.f90 and 2d/limiters.f90 are EXECUTED, unmodified, by the Fortran-90
+ * interpreter oracle/f90interp.py; this file reproduces the vectors (tests/golden/ref_dg2d.npz, ref_dg2d_limiters.npz,
+ * ref_test2d.npz; generator tests/golden/make_ref_golden.py) BIT FOR BIT: transforms, compute_update with every
+ * flux / source / bc, compute_max_speed, the four limiters on rough data, whole evolve runs with every solver
+ * (tests/test_reference_pins.py).  Additional pins: the fixed point of 2d/test2d.f90, exactness of the projection
+ * for polynomials, conservation/periodicity invariants and the textbook GL nodes (tests/test_oracle_dg2d.py).
  *
  * Layout: Fortran u(nvar,nx,ny,mx,my) == C double[my][mx][ny][nx][4]; x,y(nx,ny,mx,my) == double[my][mx][ny][nx].
  * Literal kinds: un-suffixed reals are real(4) promoted: gamma, cfl, eps, eta, the SSPRK(5,4)

@@ -4,7 +4,10 @@
  *   fvm.f90          (module fvm_commons.f90)  plain first-order FV + centred gravity source, SSP-RK2
  *   benchmark_1d.f90 (module parameters.f90)   three schemes: 'FVM' plain, 'EQL' equilibrium subtraction,
  *                                              'WB1' local hydrostatic reconstruction (default), SSP-RK2
- * PARITY UNPINNED by reference artefacts (no Fortran compiler here, no golden vectors there); pinned by the
+ * PARITY PINNED TO THE REFERENCE'S OWN SOURCE TEXT: fvm.f90 and benchmark_1d.f90 are EXECUTED, unmodified, by the
+ * Fortran-90 interpreter oracle/f90interp.py (no Fortran compiler in the image); this file reproduces the vectors
+ * (tests/golden/ref_fv1d.npz, generator tests/golden/make_ref_golden.py) BIT FOR BIT: initial conditions, the update
+ * routines of all schemes, max speed and whole time loops (tests/test_reference_pins.py).  Additional pins: the
  * invariants in tests/test_oracle_fv1d.py (EQL: bitwise-zero RHS at the discrete equilibrium; WB1: isentropic
  * equilibrium preserved to round-off, isothermal to O(dx^2); first-order convergence).
  *

@@ -5,10 +5,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
  * load this file's shared object.
  *
- * PARITY UNPINNED: the reference ships no golden vectors for this path and cannot be compiled in
- * this image (no Fortran compiler).  The restatement is pinned by (i) the analytic invariants the
- * reference code implies (dudt == 0 bitwise at the discrete hydrostatic state)
- * and (ii) an independent numpy restatement in tests/test_oracle_fv2d.py.
+ * PARITY PINNED TO THE REFERENCE'S OWN SOURCE TEXT: the image has no Fortran compiler (so no oracle/_ref build) and
+ * the reference ships no golden vectors, but benchmark_2d.f90 itself is EXECUTED, unmodified, by the Fortran-90
+ * interpreter oracle/f90interp.py; the vectors it produces (tests/golden/ref_fv2d.npz, generator
+ * tests/golden/make_ref_golden.py) are reproduced by this file BIT FOR BIT (tests/test_reference_pins.py:
+ * coordinates, initial conditions, equilibria, primitive/conservative, max speed, compute_update_exact,
+ * compute_update, whole evolve runs).  Additional pins: dudt == 0 bitwise at the discrete hydrostatic state
+ *  and an independent numpy restatement (tests/test_oracle_fv2d.py).
  *
  * Conventions reproduced from the reference (all citations relative to /root/reference):
  *   - arrays are Fortran u(nvar,nx,ny): C offset ((j*nx)+i)*4+v with 0-based i,j,v;

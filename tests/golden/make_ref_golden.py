@@ -235,6 +235,21 @@ def dg2d_limiters():
             np.savez_compressed(os.path.join(HERE, "ref_dg2d_limiters.npz"), **out)
 
 
+def test2d():
+    """2d/test2d.f90 -- the reference's only test program -- run as shipped (nx = ny = 8, mx = my = 2, 1000 round trips
+    modes <-> nodes through 2d/commons.f90); it prints maxval(u - nodes) and minval(u - nodes)."""
+    it = Interp()
+    for f in ("parameters_dg_2d.f90", "legendre.f90", "commons.f90", "test2d.f90"):
+        it.load(f"{REF}/2d/{f}")
+    t0 = time.time()
+    fr = it.run_program("dg")
+    out = {"u": C(fr["u"]), "nodes": C(fr["nodes"]), "modes": C(fr["modes"]),
+           "printed": np.array([np.max(fr["u"] - fr["nodes"]), np.min(fr["u"] - fr["nodes"])]),
+           "calls": np.array(sorted(f"{k}:{v}" for k, v in it.calls.items()))}
+    print(f"test2d: {time.time() - t0:.0f} s, max diff {out['printed'][0]:.3e}, min diff {out['printed'][1]:.3e}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_test2d.npz"), **out)
+
+
 # ------------------------------------------------------------------------------------------------ 1D FV
 def fv1d():
     out = {}
