@@ -878,6 +878,7 @@ __global__ void k_dg_ctrl_init(DgCtrl* ctrl, double tend, int max_iter, int rese
 
 #include "dg2d_fast.cuh"
 #include "dg2d_tma.cuh"
+#include "dg2d_march.cuh"
 
 // ============================================================================================ host side
 using namespace wb;
@@ -910,6 +911,8 @@ struct wb_dg2d {
   int rank = 0, nranks = 1, nyl = 0;
   // TMA-staged stage kernel: one 3-D tensor map (column, row, plane) per state buffer
   bool tma_ok = false;
+  bool march_ok = false;       // marching kernel (every face once): nx even, nx >= DGT_W
+  int march_rows = 32;         // rows per strip
   const double* map_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
   CUtensorMap map[4];
 };
@@ -1118,7 +1121,22 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   if (h->tma_ok)
     for (int k = 0; k < 4; ++k)
       if (h->map_ptr[k] == in) m_in = &h->map[k];
-  if (m_in) {
+  if (m_in && h->march_ok) {
+    dim3 b(32), gr((unsigned)((h->g.nx + DGM_COLS - 1) / DGM_COLS), (unsigned)((h->g.ny + h->march_rows - 1) / h->march_rows));
+    DISPATCH_M(h, {
+      auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_march<MM, true> : k_dg_stage_march<MM, false>;
+      static bool configured[2] = {false, false};
+      if (!configured[h->phys.flux_id >= 2]) {
+        // 8 resident warps (255 registers) x 2 row slots: no more shared memory than that, the rest stays L1 for the spills
+        const char* envc = getenv("WB_DG2D_CARVEOUT");
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : 80));
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
+        configured[h->phys.flux_id >= 2] = true;
+      }
+      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+                                                          h->phys, h->FB, h->ctrl, onp, h->march_rows);
+    });
+  } else if (m_in && h->tma_ok && h->g.nx % 32 == 0) {
     dim3 b(32), gr((unsigned)(h->g.ne / 32));
     DISPATCH_M(h, {
       auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_tma<MM, true> : k_dg_stage_tma<MM, false>;
@@ -1327,7 +1345,11 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
   {      // TMA-staged stage kernel: blocks of 32 elements must lie in one row
     const char* env = getenv("WB_DG2D_TMA");
-    if (p->arith == 0 && g.nx % 32 == 0 && g.nx >= DGT_W && !(env && atoi(env) == 0)) {
+    const char* envm = getenv("WB_DG2D_MARCH");
+    const char* envr = getenv("WB_DG2D_ROWS");
+    const bool want_march = p->arith == 0 && g.nx % 2 == 0 && g.nx >= DGT_W && (envm && atoi(envm) == 1) && !(env && atoi(env) == 0);
+    if (envr && atoi(envr) > 0) h->march_rows = atoi(envr);
+    if (want_march || (p->arith == 0 && g.nx % 32 == 0 && g.nx >= DGT_W && !(env && atoi(env) == 0))) {
       const double* bufs4[4] = {h->du, h->A, h->Bf, h->C};
       for (int k = 0; k < 4; ++k) {
         int st = dg_make_map(h, bufs4[k], &h->map[k]);
@@ -1335,6 +1357,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
         h->map_ptr[k] = bufs4[k];
       }
       h->tma_ok = true;
+      h->march_ok = want_march;
     }
   }
   *out = h;

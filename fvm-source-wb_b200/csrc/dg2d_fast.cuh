@@ -227,6 +227,45 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
 // FACE 0 left, 1 right, 2 bottom, 3 top.  Each face is evaluated by both adjacent elements (no inter-thread traffic).
 // `src.template nb<FACE>(v, dn)` delivers the modes of variable v of the neighbour across the face (global memory or the
 // TMA-staged shared-memory rows, see the two sources below).
+// numerical flux at the M points of one face from the modes of the two elements that share it (low side first)
+template <int M, int FACE, bool ANYFLUX>
+__device__ __forceinline__ void face_flux_from_traces(const DgPhys& P, double (&to)[M][4], const double (&tn)[M][4]) {
+#pragma unroll
+  for (int q = 0; q < M; ++q) {
+    double F[4];
+    // low side first: (neighbour, own) on the left/bottom faces, (own, neighbour) on the right/top faces
+    if (FACE == 0) fastm::llf<1, ANYFLUX>(P, tn[q], to[q], F);
+    if (FACE == 1) fastm::llf<1, ANYFLUX>(P, to[q], tn[q], F);
+    if (FACE == 2) fastm::llf<2, ANYFLUX>(P, tn[q], to[q], F);
+    if (FACE == 3) fastm::llf<2, ANYFLUX>(P, to[q], tn[q], F);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) to[q][v] = F[v];
+  }
+}
+// edge integral of the face flux F[q][v] accumulated into acc with its sign (see face_term)
+template <int M, int FACE>
+__device__ __forceinline__ void face_accum(const FastBasis& B, const double (&F)[M][4], double (&acc)[4][M][M]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double s[M];
+#pragma unroll
+    for (int n = 0; n < M; ++n) {
+      double a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < M; ++q) a1 = fma(F[q][v], B.Pw[q][n], a1);
+      s[n] = a1;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        if (FACE == 0) acc[v][a][b] = fma(B.Em[a], s[b], acc[v][a][b]);     // + e2
+        if (FACE == 1) acc[v][a][b] = fma(-B.Ep[a], s[b], acc[v][a][b]);    // - e1
+        if (FACE == 2) acc[v][a][b] = fma(B.Em[b], s[a], acc[v][a][b]);     // + e4
+        if (FACE == 3) acc[v][a][b] = fma(-B.Ep[b], s[a], acc[v][a][b]);    // - e3
+      }
+  }
+}
 template <int M, int FACE, bool ANYFLUX, class Src>
 __device__ __forceinline__ void face_term(Src& src, const DgPhys& P, const FastBasis& B, const double (&d)[4][M][M],
                                           double (&acc)[4][M][M]) {
@@ -244,37 +283,8 @@ __device__ __forceinline__ void face_term(Src& src, const DgPhys& P, const FastB
 #pragma unroll
     for (int q = 0; q < M; ++q) tn[q][v] = t1[q];
   }
-#pragma unroll
-  for (int q = 0; q < M; ++q) {
-    double F[4];
-    // low side first: (neighbour, own) on the left/bottom faces, (own, neighbour) on the right/top faces
-    if (FACE == 0) fastm::llf<1, ANYFLUX>(P, tn[q], to[q], F);
-    if (FACE == 1) fastm::llf<1, ANYFLUX>(P, to[q], tn[q], F);
-    if (FACE == 2) fastm::llf<2, ANYFLUX>(P, tn[q], to[q], F);
-    if (FACE == 3) fastm::llf<2, ANYFLUX>(P, to[q], tn[q], F);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) to[q][v] = F[v];
-  }
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    double s[M];
-#pragma unroll
-    for (int n = 0; n < M; ++n) {
-      double a1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < M; ++q) a1 = fma(to[q][v], B.Pw[q][n], a1);
-      s[n] = a1;
-    }
-#pragma unroll
-    for (int a = 0; a < M; ++a)
-#pragma unroll
-      for (int b = 0; b < M; ++b) {
-        if (FACE == 0) acc[v][a][b] = fma(B.Em[a], s[b], acc[v][a][b]);     // + e2
-        if (FACE == 1) acc[v][a][b] = fma(-B.Ep[a], s[b], acc[v][a][b]);    // - e1
-        if (FACE == 2) acc[v][a][b] = fma(B.Em[b], s[a], acc[v][a][b]);     // + e4
-        if (FACE == 3) acc[v][a][b] = fma(-B.Ep[b], s[a], acc[v][a][b]);    // - e3
-      }
-  }
+  face_flux_from_traces<M, FACE, ANYFLUX>(P, to, tn);
+  face_accum<M, FACE>(B, to, acc);
 }
 
 // neighbour modes straight from global memory (L1/L2): the original data path
@@ -295,6 +305,25 @@ struct GlobalSrc {
   __device__ __forceinline__ double rk_in(int v, int m) const { return PL(in, g, v, m)[e]; }
 };
 
+template <int M, class Src, class Modes>
+__device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (&acc)[4][M][M], const StageCoef& C,
+                                              double* __restrict__ out, const double* __restrict__ gx,
+                                              const double* __restrict__ gy, const unsigned char* __restrict__ fz, const DgGrid& g,
+                                              const DgPhys& P, const FastBasis& B, const DgCtrl* __restrict__ ctrl, int apply_onp,
+                                              size_t e);
+
+// the element's own modes held in registers (k_dg_stage_fast / k_dg_stage_tma)
+template <int M>
+struct RegModes {
+  const double (&d)[4][M][M];
+  __device__ __forceinline__ void get(int v, double (&o)[M][M]) const {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) o[i][j] = d[v][i][j];
+  }
+};
+
 // One element of one RK stage (everything but where the modes come from).
 template <int M, bool ANYFLUX, class Src>
 __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict__ in, const StageCoef& C, double* __restrict__ out,
@@ -302,28 +331,41 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
                                               const unsigned char* __restrict__ fz, const DgGrid& g, const DgPhys& P,
                                               const FastBasis& B, const DgCtrl* __restrict__ ctrl, int apply_onp, size_t e) {
   double acc[4][M][M];                     // -(e1-e2) - (e3-e4) + vol1 + vol2, then dudt, then the stage result
+  double d[4][M][M];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    src.own(v, d[v]);
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
+  }
+  // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
+  face_term<M, 0, ANYFLUX>(src, P, B, d, acc);
+  face_term<M, 1, ANYFLUX>(src, P, B, d, acc);
+  src.x_faces_done();
+  face_term<M, 2, ANYFLUX>(src, P, B, d, acc);
+  src.bottom_face_done(C);
+  face_term<M, 3, ANYFLUX>(src, P, B, d, acc);
+  src.top_face_done(C);
+  dg_stage_rest<M>(src, RegModes<M>{d}, acc, C, out, gx, gy, fz, g, P, B, ctrl, apply_onp, e);
+}
+
+// Everything of a stage after the face terms: nodal values, volume and source integrals, RK combination, 'ONP', stores.
+// d = the element's modes (dead after the nodal evaluation), acc = the four edge integrals with their signs.
+template <int M, class Src, class Modes>
+__device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (&acc)[4][M][M], const StageCoef& C,
+                                              double* __restrict__ out, const double* __restrict__ gx,
+                                              const double* __restrict__ gy, const unsigned char* __restrict__ fz, const DgGrid& g,
+                                              const DgPhys& P, const FastBasis& B, const DgCtrl* __restrict__ ctrl, int apply_onp,
+                                              size_t e) {
   double U[4][M][M];                       // nodal values -> nodal source -> out2 partial
   {
-    double d[4][M][M];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      src.own(v, d[v]);
-#pragma unroll
-      for (int a = 0; a < M; ++a)
-#pragma unroll
-        for (int b = 0; b < M; ++b) acc[v][a][b] = 0.0;
-    }
-    // ---- faces first (they need the neighbours' modes; nothing of them stays live afterwards)
-    face_term<M, 0, ANYFLUX>(src, P, B, d, acc);
-    face_term<M, 1, ANYFLUX>(src, P, B, d, acc);
-    src.x_faces_done();
-    face_term<M, 2, ANYFLUX>(src, P, B, d, acc);
-    src.bottom_face_done(C);
-    face_term<M, 3, ANYFLUX>(src, P, B, d, acc);
-    src.top_face_done(C);
     // ---- nodal values (sum-factorised)
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
+    for (int v = 0; v < 4; ++v) {
+      double dv[M][M];
+      d.get(v, dv);
 #pragma unroll
       for (int qx = 0; qx < M; ++qx) {
         double a[M];
@@ -331,7 +373,7 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
         for (int j = 0; j < M; ++j) {
           double s = 0.0;
 #pragma unroll
-          for (int i = 0; i < M; ++i) s = fma(d[v][i][j], B.P[qx][i], s);
+          for (int i = 0; i < M; ++i) s = fma(dv[i][j], B.P[qx][i], s);
           a[j] = s;
         }
 #pragma unroll
@@ -342,6 +384,7 @@ __device__ __forceinline__ void dg_stage_body(Src& src, const double* __restrict
           U[v][qx][qy] = s;
         }
       }
+    }
   }
 
   // ---- volume terms: fluxes (and source) at the nodes, then vol1 + vol2 (+ (dx/2) source_vol, see the final scaling)

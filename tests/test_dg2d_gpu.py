@@ -304,3 +304,29 @@ def test_tma_staged_kernel_equals_the_global_memory_one(wb, oracle, monkeypatch)
     with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s2:
         b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 3)
     assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
+
+
+@pytest.mark.parametrize("nx,mx,bc,kw", [
+    (64, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+    (62, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),        # 31-column strips end exactly at nx
+    (40, 2, 2, dict(flux="llf1", limiter="ONP", solver="EQL", ninit=3)),        # ragged last strip, clamped boundaries
+    (96, 3, 3, dict(flux="hllc", limiter="none", solver="DEB", ninit=5)),
+    (38, 4, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1, source=2, grad_phi_case=1)),
+    (36, 1, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+])
+@pytest.mark.parametrize("rows", [32, 5, 1])
+def test_marching_kernel_equals_the_two_sided_ones(wb, oracle, monkeypatch, nx, mx, bc, kw, rows):
+    """k_dg_stage_march evaluates every face once (left face by the lane, right face from lane+1, top flux carried to the
+    next row); the traces, the LLF call and the accumulation order are those of k_dg_stage_fast, so the bits must be too.
+    rows = strip height (1: every row is a first row, 5: ragged strips, 32: default)."""
+    p, _, x, y = mk(oracle, wb, nx, mx, arith=0, bc=bc, **kw)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    monkeypatch.setenv("WB_DG2D_ROWS", str(rows))
+    monkeypatch.setenv("WB_DG2D_MARCH", "1")       # opt-in kernel (measured slower than the TMA-staged one, DESIGN.md 4.3)
+    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s:
+        a, it, t, dt = s.evolve(u0, x, y, 1.0, 2)
+    monkeypatch.setenv("WB_DG2D_TMA", "0")
+    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s2:
+        b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 2)
+    assert np.all(np.isfinite(a))
+    assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
