@@ -93,8 +93,11 @@ struct SmemSrc {
   __device__ __forceinline__ double rk_in(int v, int m) const { return PL(in, g, v, m)[e]; }
 };
 
+#ifndef DGT_MINB
+#define DGT_MINB 1
+#endif
 template <int M, bool ANYFLUX>
-__global__ void __launch_bounds__(32) k_dg_stage_tma(const __grid_constant__ CUtensorMap m_in, const double* __restrict__ in, StageCoef C,
+__global__ void __launch_bounds__(32, DGT_MINB) k_dg_stage_tma(const __grid_constant__ CUtensorMap m_in, const double* __restrict__ in, StageCoef C,
                                                      double* __restrict__ out, const double* __restrict__ gx,
                                                      const double* __restrict__ gy, const unsigned char* __restrict__ fz, DgGrid g,
                                                      DgPhys P, FastBasis B, const DgCtrl* __restrict__ ctrl, int apply_onp) {

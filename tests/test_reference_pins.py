@@ -241,3 +241,33 @@ def test_dg2d_limiters_on_rough_data_equal_reference_source(oracle, tag):
     v = oracle.dg2d_apply_limiter(p, g[f"{tag}/in"])
     assert not same(g[f"{tag}/in"], g[f"{tag}/out"])
     assert same(v, g[f"{tag}/out"]), maxdiff(v, g[f"{tag}/out"])
+
+
+def test_reference_test_program_test2d_as_shipped(oracle):
+    """2d/test2d.f90, the reference's only test program, interpreted as shipped (nx = ny = 8, mx = my = 2): exp(-x+y) at
+    the GL nodes, projection, reconstruction, then 1000 round trips through 2d/commons.f90's get_modes_from_nodes /
+    get_nodes_from_modes; it prints maxval(u - nodes) and minval(u - nodes).  The oracle must land on the same nodes,
+    bit for bit, after the same 1000 trips (and therefore print the same two numbers)."""
+    g = gold("ref_test2d.npz")
+    o = oracle
+    p = o.dg2d_params(nx=8, ny=8, mx=2, my=2)
+    x, y = o.dg2d_get_coords(p)
+    u = g["u"]
+    assert u.shape == (2, 2, 8, 8, 4)
+    # test2d builds x with dx/dble(2) instead of get_coords' dx/2.0 -- the same number; u must be exp(-x+y) of those points
+    ref_u = np.empty_like(u)
+    import math
+    for idx in np.ndindex(x.shape):
+        ref_u[idx] = math.exp(-x[idx] + y[idx])
+    assert same(u, ref_u)
+    modes = o.dg2d_get_modes_from_nodes(p, u)
+    nodes = o.dg2d_get_nodes_from_modes(p, modes)
+    for _ in range(1000):
+        modes = o.dg2d_get_modes_from_nodes(p, nodes)
+        nodes = o.dg2d_get_nodes_from_modes(p, modes)
+    assert same(nodes, g["nodes"]), maxdiff(nodes, g["nodes"])
+    assert same(modes, g["modes"])
+    printed = np.array([np.max(u - nodes), np.min(u - nodes)])
+    assert same(printed, g["printed"]) and 0 < printed[1] < printed[0] < 2e-12
+    called = {c.split(":")[0]: int(c.split(":")[1]) for c in g["calls"]}
+    assert called["get_modes_from_nodes"] == 1000 and called["get_nodes_from_modes"] == 1000
