@@ -738,6 +738,81 @@ __global__ void k_limiter_1or_b(const double* __restrict__ w, double* __restrict
   store_modes<M>(u, g, e, md);
 }
 
+// limiter_positivity ('POS', 2d/limiters.f90:863-1036), reference operation order, one thread per element, u -> out.
+// minmod on the two linear modes of the conserved variables against the CLAMPED neighbour means of the unlimited input
+// (the clamp ignores bc; the reference writes the y pass with the cell indices swapped and runs both loops to nx), then
+// the nodal primitive density / pressure are reset to the real(4) literal 1e-5 wherever the first or last node of their
+// row or column is below 1d-10 -- the loop re-reads nodes it may already have reset, so it is kept sequential -- and the
+// element goes back through compute_conservative and the projection.
+template <int M>
+__global__ void k_limiter_pos(const double* __restrict__ u, double* __restrict__ out, DgGrid g, DgPhys P, Basis B,
+                              const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + max(ic - 1, 0), eR = (size_t)jc * g.nx + min(ic + 1, g.nx - 1);
+  const size_t eB = (size_t)max(jc - 1, 0) * g.nx + ic, eT = (size_t)min(jc + 1, g.ny - 1) * g.nx + ic;
+  double md[4][M][M], nd[4][M][M];
+  load_modes<M>(u, g, e, md);
+  if (M > 1) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const double u_center = 0.5 * md[v][0][0];
+      {   // x pass (:899-935): mode (2,1), drops u(2:mx,1)
+        const double u_left = 0.5 * PL(u, g, v, 0)[eL], u_right = 0.5 * PL(u, g, v, 0)[eR], u_deriv = md[v][1][0];
+        const double l = minmod(u_deriv, (u_center - u_left) / P.dx, (u_right - u_center) / P.dx);
+        const bool drop = fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv);
+        md[v][1][0] = l;
+        if (drop) {
+#pragma unroll
+          for (int i = 1; i < M; ++i) md[v][i][0] = 0.0;
+        }
+      }
+      {   // y pass (:941-978): mode (1,2), drops u(1,2:my)
+        const double u_left = 0.5 * PL(u, g, v, 0)[eB], u_right = 0.5 * PL(u, g, v, 0)[eT], u_deriv = md[v][0][1];
+        const double l = minmod(u_deriv, (u_center - u_left) / P.dx, (u_right - u_center) / P.dx);
+        const bool drop = fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv);
+        md[v][0][1] = l;
+        if (drop) {
+#pragma unroll
+          for (int j = 1; j < M; ++j) md[v][0][j] = 0.0;
+        }
+      }
+    }
+  }
+  nodes_from_modes_el<M>(md, B, nd);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double uu[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]}, ww[4];
+      prim(P, uu, ww);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) nd[v][i][j] = ww[v];
+    }
+#pragma unroll
+  for (int v = 0; v < 4; v += 3)      // density and pressure only (:996-1012)
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        const double u_left = nd[v][0][j], u_right = nd[v][M - 1][j], u_top = nd[v][i][0], u_bottom = nd[v][i][M - 1];
+        if (u_left < 1e-10 || u_right < 1e-10 || u_top < 1e-10 || u_bottom < 1e-10) nd[v][i][j] = (double)1e-5f;
+      }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double ww[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]}, uu[4];
+      cons(P, ww, uu);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) nd[v][i][j] = uu[v];
+    }
+  modes_from_nodes_el<M>(nd, B, md);
+  store_modes<M>(out, g, e, md);
+}
+
 // ------------------------------------------------------------------------------------ compute_max_speed :826-870
 // The reference scan (i outer, j inner; `>=` keeps the LAST maximum; every later cell with a smaller cs lowers
 // cs_max) in its commutative two-phase form:
@@ -986,7 +1061,7 @@ int dg_update(wb_dg2d* h, const double* in, double* out, bool use_ctrl) {
 
 int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
   const DgCtrl* c = use_ctrl ? h->ctrl : nullptr;
-  if (h->prm.limiter_id == 2 || h->prm.limiter_id == 3) WB_CHECK(dg_ensure(h, &h->E));
+  if (h->prm.limiter_id == 2 || h->prm.limiter_id == 3 || h->prm.limiter_id == 5) WB_CHECK(dg_ensure(h, &h->E));
   dim3 b(128), gr = elem_grid(h, 128);
   if (h->g.m == 1) return WB_OK;           // every limiter returns early for mx == my == 1
   switch (h->prm.limiter_id) {
@@ -1016,6 +1091,16 @@ int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
     case 4:
       DISPATCH_M(h, k_limiter_low<MM><<<gr, b, 0, h->stream>>>(u, h->g, c));
       WB_LAUNCH_CHECK();
+      break;
+    case 5:
+      DISPATCH_M(h, k_limiter_pos<MM><<<gr, b, 0, h->stream>>>(u, h->E, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      {     // u = u_lim (:1035); a skipped step must not copy a stale scratch buffer
+        dim3 gb((unsigned)std::min<size_t>((h->nfield + 255) / 256, 148 * 16));
+        k_dg_axpy<0><<<gb, 256, 0, h->stream>>>(u, h->E, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, h->E, 0.0, h->nfield,
+                                                c ? c : h->ctrl);
+        WB_LAUNCH_CHECK();
+      }
       break;
     default: break;
   }
@@ -1256,7 +1341,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->source >= 1 && p->source <= 3, "source must be 1..3");
   WB_REQUIRE(p->grad_phi_case == 1 || p->grad_phi_case == 2, "grad_phi_case must be 1 or 2");
   WB_REQUIRE(p->flux_id >= 0 && p->flux_id <= 3, "flux_id must be 0 (as shipped), 1 (llf1), 2 (hll2) or 3 (hllc)");
-  WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 4, "limiter_id must be 0..4 (none, ONP, HIO, 1OR, LOW)");
+  WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 5, "limiter_id must be 0..5 (none, ONP, HIO, 1OR, LOW, POS)");
   WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
   WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fused) or 1 (reference order)");

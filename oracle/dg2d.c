@@ -33,7 +33,7 @@ typedef struct {
   int source;               /* :20  1 none, 2 gravity (get_source), 3 advection sink */
   int grad_phi_case;        /* :21 */
   int flux_id;              /* :15  0 = as shipped ('llf ' matches nothing -> numerical flux stays 0), 1 = 'llf1', 2 = 'hll2', 3 = 'hllc' */
-  int limiter_id;           /* :14  0 = use_limiter false, 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW' */
+  int limiter_id;           /* :14  0 = use_limiter false, 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW', 5 'POS' */
   int solver_id;            /* :13  1 'RK4', 2 'SS4', 3 'EQL', 4 'DEB' */
   int ninit;                /* :17 */
   double gamma, boxlen_x, boxlen_y, cfl, eps, M, eta;  /* :23-35 */
@@ -787,6 +787,61 @@ void orc_dg2d_limiter_low_order(const orc_dg2d_params *p, double *u) {
       }
 }
 
+/* :863-1036 limiter_positivity ('POS'): minmod on the two linear modes of the CONSERVED variables against the clamped
+ * neighbour means (the x pass drops u(2:mx,1), the "y" pass -- written with the cell indices swapped -- u(1,2:my)), then the
+ * nodal PRIMITIVE values of density and pressure are reset to the real(4) literal 1e-5 wherever the first / last node of
+ * their row or column is below 1d-10 (the test reads nodes the same loop may already have reset), and the result goes
+ * back through compute_conservative and the projection.  The neighbour clamp ignores bc; both loops run to nx (nx == ny). */
+void orc_dg2d_limiter_positivity(const orc_dg2d_params *p, double *u) {
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  if (mx == 1 && my == 1) return;
+  const double dx = p->boxlen_x / (double)nx;
+  size_t n5 = nelem5(p);
+  double *u_lim = (double *)malloc(sizeof(double) * NV * n5), *nodes = (double *)malloc(sizeof(double) * NV * n5);
+  double *nodes_cons = (double *)malloc(sizeof(double) * NV * n5);
+  memcpy(u_lim, u, sizeof(double) * NV * n5);
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= nx; ++jc) {
+        int left = ic - 1, right = ic + 1;
+        if (ic == 1) left = 1; else if (ic == nx) right = nx;
+        double u_left = 0.5 * U5(u, p, v, left - 1, jc - 1, 0, 0), u_right = 0.5 * U5(u, p, v, right - 1, jc - 1, 0, 0);
+        double u_center = 0.5 * U5(u, p, v, ic - 1, jc - 1, 0, 0), u_deriv = U5(u, p, v, ic - 1, jc - 1, 1, 0);
+        double l = minmod(u_deriv, (u_center - u_left) / dx, (u_right - u_center) / dx);
+        U5(u_lim, p, v, ic - 1, jc - 1, 1, 0) = l;
+        if (fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv))
+          for (int i = 1; i < mx; ++i) U5(u_lim, p, v, ic - 1, jc - 1, i, 0) = 0.0;
+      }
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= nx; ++jc) {
+        int left = ic - 1, right = ic + 1;
+        if (ic == 1) left = 1; else if (ic == nx) right = nx;
+        double u_left = 0.5 * U5(u, p, v, jc - 1, left - 1, 0, 0), u_right = 0.5 * U5(u, p, v, jc - 1, right - 1, 0, 0);
+        double u_center = 0.5 * U5(u, p, v, jc - 1, ic - 1, 0, 0), u_deriv = U5(u, p, v, jc - 1, ic - 1, 0, 1);
+        double l = minmod(u_deriv, (u_center - u_left) / dx, (u_right - u_center) / dx);
+        U5(u_lim, p, v, jc - 1, ic - 1, 0, 1) = l;
+        if (fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv))
+          for (int j = 1; j < my; ++j) U5(u_lim, p, v, jc - 1, ic - 1, 0, j) = 0.0;
+      }
+  orc_dg2d_get_nodes_from_modes(p, u_lim, nodes_cons);
+  orc_dg2d_compute_primitive(p, nodes_cons, nodes, (long)n5);
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 0; ic < nx; ++ic)
+      for (int jc = 0; jc < ny; ++jc)
+        for (int i = 0; i < mx; ++i)
+          for (int j = 0; j < my; ++j) {
+            double u_left = U5(nodes, p, v, ic, jc, 0, j), u_right = U5(nodes, p, v, ic, jc, mx - 1, j);
+            double u_top = U5(nodes, p, v, ic, jc, i, 0), u_bottom = U5(nodes, p, v, ic, jc, i, my - 1);
+            int dp = (v == 0) || (v == 3);
+            if ((u_left < 1e-10 && dp) || (u_right < 1e-10 && dp) || (u_top < 1e-10 && dp) || (u_bottom < 1e-10 && dp))
+              U5(nodes, p, v, ic, jc, i, j) = (double)1e-5f;
+          }
+  orc_dg2d_compute_conservative(p, nodes, nodes_cons, (long)n5);
+  orc_dg2d_get_modes_from_nodes(p, nodes_cons, u);
+  free(u_lim); free(nodes); free(nodes_cons);
+}
+
 /* 2d/benchmark_2d_dg.f90:1516-1555 apply_limiter */
 void orc_dg2d_apply_limiter(const orc_dg2d_params *p, double *u) {
   switch (p->limiter_id) {
@@ -794,6 +849,7 @@ void orc_dg2d_apply_limiter(const orc_dg2d_params *p, double *u) {
     case 2: orc_dg2d_high_order_limiter(p, u); break;
     case 3: orc_dg2d_compute_limiter(p, u); break;
     case 4: orc_dg2d_limiter_low_order(p, u); break;
+    case 5: orc_dg2d_limiter_positivity(p, u); break;
     default: break;
   }
 }

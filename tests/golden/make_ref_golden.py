@@ -138,6 +138,7 @@ DG2D_CASES = [  # tag, n (nx=ny), m (mx=my), bc, source, grad_phi_case, flux_typ
     ("riemann_o4_onp", 3, 4, 3, 1, 2, "llf1", "ONP", "RK4", 5, 1),
     ("pulse_o3_hll2", 3, 3, 1, 1, 2, "hll2", "ONP", "RK4", 1, 1),
     ("riemann_o2_hllc", 4, 2, 2, 1, 2, "hllc", "ONP", "RK4", 3, 1),
+    ("riemann_o3_pos", 4, 3, 2, 1, 2, "llf1", "POS", "EQL", 3, 2),
 ]
 
 
@@ -206,7 +207,7 @@ def dg2d_limiters():
     """apply_limiter on rough data: every limiter has to act (negative density / pressure points, steep linear modes)."""
     out = {}
     rng = np.random.default_rng(99)
-    for lim in ("ONP", "HIO", "1OR", "LOW"):
+    for lim in ("ONP", "HIO", "1OR", "LOW", "POS"):
         for n, m, bc in ((3, 3, 1), (4, 2, 2), (3, 2, 3)):
             tag = f"{lim.lower()}_n{n}_m{m}_bc{bc}"
             t0 = time.time()
