@@ -41,6 +41,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_dg_traffic_bytes_per_element_stage():
+    """dram read+write per element-stage of the DG stage kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "dg2d_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_element_stage"])
+    except Exception:
+        return None
+
+
 def ncu_traffic_bytes_per_cell_stage():
     """dram read+write per cell-stage from the committed ncu capture (profiles/fv2d_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "fv2d_traffic.json")
@@ -65,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -190,7 +199,8 @@ def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
                                                "periodic Gaussian pulse (ninit=1), device-initialised", "grid": [n, n],
                                    "parallelism": f"y-slabs x{world} (ring)" if world > 1 else "single GPU"},
                         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                     "traffic": None, "kernel": "k_dg_stage_tma<3> (fused update + RK combination + ONP, rows staged by TMA, 5 launches/step)",
+                                     "traffic": (ncu_dg_traffic_bytes_per_element_stage() or 0) * n * n / world or None,
+                                     "kernel": "k_dg_stage_tma<3> (fused update + RK combination + ONP, rows staged by TMA, 5 launches/step)",
                                      "algorithmic_bytes_per_launch": 921.6 * n * n / world, "peak_source": src,
                                      "note": "the launch time includes the 4 small max-speed reduction kernels of each step"},
                         "sim": {"iters": it, "t": t, "dt": dt}})
@@ -328,8 +338,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="override the grid edge (default 4096 at N=1, 16384 at N>1)")
     ap.add_argument("--ref-grid", type=int, default=1024, help="grid edge of the reference arm's bounded sample")
