@@ -813,6 +813,54 @@ __global__ void k_limiter_pos(const double* __restrict__ u, double* __restrict__
   store_modes<M>(out, g, e, md);
 }
 
+// compute_error :23-89.  Per element the reference's accumulators (same order, both directions weighted with w_x_quad,
+// :52) -- the per-variable sums over the elements are order dependent in the reference (i outer, j inner); here they are
+// a fixed-shape tree (grid-stride partial sums per thread, block tree, one final block), i.e. deterministic and equal to
+// the reference to a few ulp of the sum.  part: [gridDim.x][12] = lmax[4], l1[4], l2[4].
+template <int M>
+__global__ void k_dg_error(const double* __restrict__ u, const double* __restrict__ u0, DgGrid g, Basis B, double scale,
+                           double* __restrict__ part) {
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  for (size_t e = g.e_off + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < g.e_off + g.ne_own; e += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      double a1 = 0.0, a2 = 0.0, m = acc[v];
+#pragma unroll
+      for (int qi = 0; qi < M; ++qi)
+#pragma unroll
+        for (int qj = 0; qj < M; ++qj) {
+          const double d = PL(u, g, v, qj * M + qi)[e] - PL(u0, g, v, qj * M + qi)[e];
+          a1 = a1 + fabs(d) * B.wq[qi] * B.wq[qj];
+          a2 = a2 + d * d * B.wq[qi] * B.wq[qj];
+          m = fmax(m, fabs(d));
+        }
+      acc[v] = m;
+      acc[4 + v] = acc[4 + v] + a1 * scale * 0.25;
+      acc[8 + v] = acc[8 + v] + a2 * scale * 0.25;
+    }
+  }
+  __shared__ double sh[128][12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) sh[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 12; ++k)
+        sh[threadIdx.x][k] = (k < 4) ? fmax(sh[threadIdx.x][k], sh[threadIdx.x + s][k]) : sh[threadIdx.x][k] + sh[threadIdx.x + s][k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 12) part[(size_t)blockIdx.x * 12 + threadIdx.x] = sh[0][threadIdx.x];
+}
+__global__ void k_dg_error_final(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= 12) return;
+  double r = 0.0;
+  for (int b = 0; b < nparts; ++b) r = (k < 4) ? fmax(r, part[(size_t)b * 12 + k]) : r + part[(size_t)b * 12 + k];
+  out[k] = r;
+}
+
 // ------------------------------------------------------------------------------------ compute_max_speed :826-870
 // The reference scan (i outer, j inner; `>=` keeps the LAST maximum; every later cell with a smaller cs lowers
 // cs_max) in its commutative two-phase form:
@@ -1502,6 +1550,28 @@ int wb_dg2d_get_modes_from_nodes(wb_dg2d* h, const double* nodes, double* modes)
   DISPATCH_M(h, k_modes_from_nodes<MM><<<gr, b, 0, h->stream>>>(h->A, h->Bf, h->g, h->B));
   WB_LAUNCH_CHECK();
   return dg_d2h_field(h, h->Bf, modes);
+}
+
+int wb_dg2d_compute_error(wb_dg2d* h, const double* u_nodes, const double* u_init_nodes, double* lmax4, double* l1_4, double* l2_4) {
+  if (!h || !u_nodes || !u_init_nodes || !lmax4 || !l1_4 || !l2_4) { set_error("null argument"); return WB_ERR_ARG; }
+  if (h->nranks > 1) { set_error("wb_dg2d_compute_error: single-GPU handles only"); return WB_ERR_STATE; }
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;
+  WB_CHECK(dg_h2d_field(h, u_nodes, h->A));
+  WB_CHECK(dg_h2d_field(h, u_init_nodes, h->Bf));
+  const int nb = (int)std::min<size_t>((h->g.ne_own + 127) / 128, 148 * 4);
+  double* part = nullptr;
+  WB_CUDA(cudaMalloc(&part, sizeof(double) * 12 * (nb + 1)));
+  const double scale = (1.0 / (double)h->prm.nx) * (1.0 / (double)h->prm.ny);      // dx*dy with dx = 1./dble(nx) (:35-36)
+  DISPATCH_M(h, k_dg_error<MM><<<nb, 128, 0, h->stream>>>(h->A, h->Bf, h->g, h->B, scale, part));
+  k_dg_error_final<<<1, 32, 0, h->stream>>>(part, nb, part + (size_t)12 * nb);
+  double r[12];
+  cudaError_t e1 = cudaMemcpyAsync(r, part + (size_t)12 * nb, sizeof(r), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cudaFree(part);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("wb_dg2d_compute_error: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return WB_ERR_CUDA; }
+  for (int k = 0; k < 4; ++k) { lmax4[k] = r[k]; l1_4[k] = r[4 + k]; l2_4[k] = r[8 + k]; }
+  return WB_OK;
 }
 
 int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes) {

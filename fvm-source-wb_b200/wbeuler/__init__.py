@@ -250,6 +250,12 @@ class DG2D:
         _check(lib().wb_dg2d_get_nodes_from_modes(self._h, _ptr(modes), _ptr(out)))
         return out
 
+    def compute_error(self, u_nodes, u_init_nodes):
+        """compute_error(u,x,y,t,u_anal)  2d/benchmark_2d_dg.f90:23-89 -> (lmax[4], l1[4], l2[4] before the sqrt)"""
+        a = np.zeros(4); b = np.zeros(4); c = np.zeros(4)
+        _check(lib().wb_dg2d_compute_error(self._h, _ptr(u_nodes), _ptr(u_init_nodes), _ptr(a), _ptr(b), _ptr(c)))
+        return a, b, c
+
     def compute_update(self, modes, x=None, y=None):
         """compute_update(delta_u,x,y,u_eq,dudt)  2d/benchmark_2d_dg.f90:1137-1479"""
         out = np.empty(self.shape)

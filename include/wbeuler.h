@@ -153,6 +153,12 @@ int wb_dg2d_quadrature(wb_dg2d* h, double* x_quad, double* w_quad);
  * (also 2d/commons.f90, the routines 2d/test2d.f90 exercises) */
 int wb_dg2d_get_modes_from_nodes(wb_dg2d* h, const double* nodes, double* modes);
 int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes);
+/* replaces the arithmetic of compute_error(u,x,y,t,u_anal)   2d/benchmark_2d_dg.f90:23-89: the reference compares the nodal
+ * state with get_initial_conditions(x,y) (its `t` and `u_anal` are never used) and prints max |u - u_init|, the L1 sums and
+ * sqrt of the L2 sums per variable.  The caller passes the initial nodes (the Fortran initialiser stays on the Fortran side);
+ * returned: lmax[4], l1[4] and l2[4] = the accumulators BEFORE the sqrt.  Sums over elements are a fixed-shape tree on the
+ * device (deterministic; equal to the reference's sequential sums to a few ulp). */
+int wb_dg2d_compute_error(wb_dg2d* h, const double* u_nodes, const double* u_init_nodes, double* lmax4, double* l1_4, double* l2_4);
 /* replaces compute_update(delta_u,x,y,u_eq,dudt)   2d/benchmark_2d_dg.f90:1137-1479 (u_eq is never read there) */
 int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, const double* y, double* dudt);
 /* replaces apply_limiter(u)   2d/benchmark_2d_dg.f90:1516-1555 -> 2d/limiters.f90 */

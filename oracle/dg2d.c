@@ -581,6 +581,31 @@ void orc_dg2d_compute_update(const orc_dg2d_params *p, const double *delta_u, co
   free(u_left); free(u_right); free(u_top); free(u_bottom); free(fl1); free(fr1); free(ft2); free(fb2); free(F); free(G);
 }
 
+/* 2d/benchmark_2d_dg.f90:23-89 compute_error: the reference compares the nodal state with get_initial_conditions(x,y) (not
+ * with a solution at time t; `t` and `u_anal` are never used) and PRINTS max error, the L1 sums and sqrt of the L2 sums.
+ * Returned here: lmax[4], l1[4], l2[4] (the accumulators before the sqrt).  Both quadrature directions use w_x_quad (:52). */
+void orc_dg2d_compute_error(const orc_dg2d_params *p, const double *u, const double *u_init, double *lmax, double *l1, double *l2) {
+  basis_t B; make_basis(p, &B);
+  const double dx = (double)1.f / (double)p->nx, dy = (double)1.f / (double)p->ny;
+  for (int v = 0; v < NV; ++v) {
+    double m = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < p->nx; ++i)
+      for (int j = 0; j < p->ny; ++j) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int qi = 0; qi < p->mx; ++qi)
+          for (int qj = 0; qj < p->my; ++qj) {
+            double d = U5(u, p, v, i, j, qi, qj) - U5(u_init, p, v, i, j, qi, qj);
+            a1 = a1 + fabs(d) * B.wx[qi] * B.wx[qj];
+            a2 = a2 + d * d * B.wx[qi] * B.wx[qj];
+            if (fabs(d) > m) m = fabs(d);
+          }
+        s1 = s1 + a1 * (dx * dy) * 0.25;
+        s2 = s2 + a2 * (dx * dy) * 0.25;
+      }
+    lmax[v] = m; l1[v] = s1; l2[v] = s2;
+  }
+}
+
 /* ------------------------------------------------------------------ 2d/limiters.f90 */
 static inline double sign1(double x) { return copysign(1.0, x); }
 /* :18-28 */

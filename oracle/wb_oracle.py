@@ -220,6 +220,13 @@ def dg2d_apply_limiter(p, modes):
     return u
 
 
+def dg2d_compute_error(p, u_nodes, u_init):
+    """compute_error :23-89 -> (lmax[4], l1[4], l2[4]); l2 is the accumulator before the sqrt"""
+    a = np.zeros(4); b = np.zeros(4); c = np.zeros(4)
+    lib().orc_dg2d_compute_error(C.byref(p), _ptr(u_nodes), _ptr(u_init), _ptr(a), _ptr(b), _ptr(c))
+    return a, b, c
+
+
 def dg2d_evolve_modes(p, modes, x, y, tend, max_iter=-1):
     u = np.array(modes, copy=True)
     it = C.c_int(); t = C.c_double(); dt = C.c_double()

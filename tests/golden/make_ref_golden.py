@@ -236,6 +236,57 @@ def dg2d_limiters():
             np.savez_compressed(os.path.join(HERE, "ref_dg2d_limiters.npz"), **out)
 
 
+def dg2d_other_limiters():
+    """The limiter_type branches of apply_limiter that are NOT built, and why -- observed by running them:
+    'ROS' and 'KRI' index out of bounds / pass a rank-1 section to a rank-5 dummy (undefined behaviour in the reference),
+    'COC' overwrites the nodal pressure with the literal 10e-5 (an abandoned experiment), 'PO3' returns NaN at order 3,
+    '1DL' calls limiter_1d, which does not exist."""
+    import json
+    from oracle.f90interp import FortranError
+    rng = np.random.default_rng(3)
+    facts = {}
+    for lim in ("ROS", "KRI", "COC", "PO3", "1DL"):
+        for n, m, bc in ((3, 3, 1), (4, 2, 2)):
+            it = dg2d_interp(nx=n, ny=n, mx=m, my=m, bc=bc, limiter_type=lim, flux_type="llf1", ninit=1)
+            modes = F(4, n, n, m, m)
+            modes[0, :, :, 0, 0] = 1 + 0.5 * rng.random((n, n)); modes[3, :, :, 0, 0] = 2.5 + rng.random((n, n))
+            modes[1, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n)); modes[2, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n))
+            hi = 0.08 * rng.standard_normal((4, n, n, m, m)); hi[:, :, :, 0, 0] = 0; modes += hi
+            key = f"{lim}_n{n}_m{m}_bc{bc}"
+            try:
+                it.call("apply_limiter", modes)
+                nodes = F(4, n, n, m, m); w = F(4, n, n, m, m)
+                it.call("get_nodes_from_modes", modes, nodes, n, n, m, m)
+                it.call("compute_primitive", nodes, w, n, n, m, m)
+                facts[key] = {"status": "ran", "nan": int(np.isnan(modes).sum()),
+                              "pressure_min": float(np.nanmin(w[3])) if not np.isnan(w[3]).all() else None,
+                              "pressure_max": float(np.nanmax(w[3])) if not np.isnan(w[3]).all() else None}
+            except FortranError as e:
+                facts[key] = {"status": "error", "message": str(e)[:160]}
+            print(key, facts[key], flush=True)
+    json.dump(facts, open(os.path.join(HERE, "ref_dg2d_other_limiters.json"), "w"), indent=1)
+
+
+def dg2d_error_norms():
+    """compute_error (2d/benchmark_2d_dg.f90:23-89): L1 / L2 accumulators (before the sqrt) and the max errors it prints."""
+    out = {}
+    rng = np.random.default_rng(17)
+    for tag, n, m, ninit in (("pulse_o3", 4, 3, 1), ("pulse_o2", 5, 2, 1), ("hydro_o3", 3, 3, 2)):
+        it = dg2d_interp(nx=n, ny=n, mx=m, my=m, ninit=ninit, flux_type="llf1")
+        x, y = F(n, n, m, m), F(n, n, m, m)
+        it.call("get_coords", x, y, n, n, m, m)
+        u0 = F(4, n, n, m, m)
+        it.call("get_initial_conditions", x, y, u0, n, n, m, m)
+        u = np.asfortranarray(u0 * (1 + 0.01 * rng.standard_normal(u0.shape)) + 0.003 * rng.standard_normal(u0.shape))
+        fr = it.call("compute_error", u, x, y, np.array(0.3), F(4, n, n, m, m))
+        out[f"{tag}/meta"] = np.array([n, m, ninit])
+        out[f"{tag}/x"] = C(x); out[f"{tag}/y"] = C(y); out[f"{tag}/u"] = C(u); out[f"{tag}/u_init"] = C(fr["u_init"])
+        out[f"{tag}/l1"] = np.array(fr["l1norm"]); out[f"{tag}/l2"] = np.array(fr["l2norm"])
+        out[f"{tag}/lmax"] = np.array([np.abs(u[v] - u0[v]).max() for v in range(4)])
+        print(f"dg2d compute_error {tag}: l1 {fr['l1norm']}, l2 {fr['l2norm']}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_dg2d_error_norms.npz"), **out)
+
+
 def test2d():
     """2d/test2d.f90 -- the reference's only test program -- run as shipped (nx = ny = 8, mx = my = 2, 1000 round trips
     modes <-> nodes through 2d/commons.f90); it prints maxval(u - nodes) and minval(u - nodes)."""

@@ -271,3 +271,40 @@ def test_reference_test_program_test2d_as_shipped(oracle):
     assert same(printed, g["printed"]) and 0 < printed[1] < printed[0] < 2e-12
     called = {c.split(":")[0]: int(c.split(":")[1]) for c in g["calls"]}
     assert called["get_modes_from_nodes"] == 1000 and called["get_nodes_from_modes"] == 1000
+
+
+@pytest.mark.parametrize("tag", tags("ref_dg2d_error_norms.npz"))
+def test_dg2d_compute_error_equals_reference_source(oracle, tag):
+    """compute_error (2d/benchmark_2d_dg.f90:23-89): the L1 / L2 accumulators of the interpreted reference, bit for bit
+    (sequential sums in the reference's loop order), and the max errors it prints."""
+    g = gold("ref_dg2d_error_norms.npz")
+    n, m, ninit = (int(v) for v in g[f"{tag}/meta"])
+    p = oracle.dg2d_params(nx=n, ny=n, mx=m, my=m, ninit=ninit)
+    u_init = oracle.dg2d_get_initial_conditions(p, g[f"{tag}/x"], g[f"{tag}/y"])
+    assert same(u_init, g[f"{tag}/u_init"])
+    lmax, l1, l2 = oracle.dg2d_compute_error(p, g[f"{tag}/u"], u_init)
+    assert same(l1, g[f"{tag}/l1"]) and same(l2, g[f"{tag}/l2"]) and same(lmax, g[f"{tag}/lmax"])
+
+
+def test_limiter_branches_that_are_not_built_and_why():
+    """apply_limiter (2d/benchmark_2d_dg.f90:1516-1555) has ten branches.  ONP, HIO, 1OR, LOW and POS are built.  What the
+    interpreted reference does with the other five (tests/golden/ref_dg2d_other_limiters.json): 'ROS' indexes u_avg(.., 0),
+    'KRI' passes a 4-element section where a whole 5-D array is expected, '1DL' calls a subroutine that does not exist --
+    undefined behaviour or no program at all; 'COC' ends by overwriting the nodal pressure with the literal 10e-5 (an
+    abandoned experiment); 'PO3' runs (characteristic-variable minmod) and is the one candidate left for widening."""
+    import json
+    f = json.load(open(os.path.join(HERE, "golden", "ref_dg2d_other_limiters.json")))
+    for k, v in f.items():
+        lim = k.split("_")[0]
+        if lim in ("ROS", "KRI", "1DL"):
+            assert v["status"] == "error"
+        else:
+            assert v["status"] == "ran"
+        if lim == "ROS":
+            assert "u_avg" in v["message"] and "out of bounds" in v["message"]
+        if lim == "KRI":
+            assert "get_nodes_from_modes" in v["message"]
+        if lim == "1DL":
+            assert "limiter_1d" in v["message"]
+        if lim == "COC":
+            assert abs(v["pressure_min"] - 1e-4) < 1e-11 and abs(v["pressure_max"] - 1e-4) < 1e-11

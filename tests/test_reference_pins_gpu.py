@@ -199,3 +199,30 @@ def test_dg1d_cuda_equals_reference_source(wb, tag):
     if uu is not None:
         assert rel(uu, g[f"{tag}/u_end"]) <= TOL
     assert rel(ui2, g[f"{tag}/ureal_end"]) <= TOL
+
+
+@pytest.mark.parametrize("tag", tags("ref_dg2d_error_norms.npz"))
+def test_dg2d_compute_error_cuda_equals_reference_source(wb, tag):
+    """wb_dg2d_compute_error vs compute_error of the interpreted reference: max errors exact, sums to 1e-13 relative (the
+    per-element accumulators are the reference's; the sum over elements is a tree instead of a sequential loop)."""
+    g = gold("ref_dg2d_error_norms.npz")
+    n, m, ninit = (int(v) for v in g[f"{tag}/meta"])
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, ninit=ninit, device=0, arith=1) as s:
+        lmax, l1, l2 = s.compute_error(g[f"{tag}/u"], g[f"{tag}/u_init"])
+    assert np.array_equal(lmax, g[f"{tag}/lmax"])
+    assert np.abs(l1 / g[f"{tag}/l1"] - 1).max() <= 1e-13 and np.abs(l2 / g[f"{tag}/l2"] - 1).max() <= 1e-13
+
+
+def test_dg2d_compute_error_large_grid_against_numpy(wb):
+    n, m = 256, 3
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal((m, m, n, n, 4)); u0 = rng.standard_normal((m, m, n, n, 4))
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, device=0) as s:
+        xq, wq = s.quadrature()
+        lmax, l1, l2 = s.compute_error(u, u0)
+    d = u - u0
+    w2 = wq[:, None] * wq[None, :]                       # [qj][qi]: both directions use the same rule
+    ref1 = (np.abs(d) * w2[:, :, None, None, None]).sum(axis=(0, 1, 2, 3)) * (1.0 / n) ** 2 * 0.25
+    ref2 = (d * d * w2[:, :, None, None, None]).sum(axis=(0, 1, 2, 3)) * (1.0 / n) ** 2 * 0.25
+    assert np.array_equal(lmax, np.abs(d).max(axis=(0, 1, 2, 3)))
+    assert np.abs(l1 / ref1 - 1).max() <= 1e-12 and np.abs(l2 / ref2 - 1).max() <= 1e-12
