@@ -9,6 +9,10 @@
 // Included by dg2d.cu (uses its DgGrid / DgPhys / DgCtrl / Basis definitions).
 #pragma once
 
+#ifndef DG_ONP_SLOW_ATTR
+#define DG_ONP_SLOW_ATTR __forceinline__   /* measured: __noinline__ puts the accumulators in local memory, 2.6e9 -> 1.65e9 */
+#endif
+
 namespace wb { namespace dg {
 
 struct FastBasis {
@@ -154,6 +158,9 @@ __device__ __forceinline__ double eval_at(const double (&d)[M][M], const double*
 
 // 'ONP' positivity limiter (2d/limiters.f90:478-654) on an element held in registers
 template <int M>
+__device__ DG_ONP_SLOW_ATTR void positivity_slow(const DgPhys& P, const FastBasis& B, double (&el)[4][M][M]);
+
+template <int M>
 __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis& B, double (&el)[4][M][M]) {
   if (M == 1) return;
   const double ua[4] = {el[0][0][0], el[1][0][0], el[2][0][0], el[3][0][0]};
@@ -182,6 +189,14 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
       if (p_lo > P.eps + margin) return;
     }
   }
+  positivity_slow<M>(P, B, el);
+}
+
+// the point evaluations of 'ONP' (elements that fail the sufficient test): out of line, so that the stage kernel's register
+// allocation is not sized for them
+template <int M>
+__device__ DG_ONP_SLOW_ATTR void positivity_slow(const DgPhys& P, const FastBasis& B, double (&el)[4][M][M]) {
+  const double ua[4] = {el[0][0][0], el[1][0][0], el[2][0][0], el[3][0][0]};
   double p_min = 1e300;
   for (int q = 0; q < M; ++q)
     for (int r = 0; r < B.gll; ++r) {

@@ -139,6 +139,9 @@ DG2D_CASES = [  # tag, n (nx=ny), m (mx=my), bc, source, grad_phi_case, flux_typ
     ("pulse_o3_hll2", 3, 3, 1, 1, 2, "hll2", "ONP", "RK4", 1, 1),
     ("riemann_o2_hllc", 4, 2, 2, 1, 2, "hllc", "ONP", "RK4", 3, 1),
     ("riemann_o3_pos", 4, 3, 2, 1, 2, "llf1", "POS", "EQL", 3, 2),
+    # rotating disk in a 6 x 6 box (boxlen is a module variable): Keplerian grad_phi with the softened core and
+    # special_boundary_conditions (:1481-1514), which freezes the update outside r = 2
+    ("disk_o2_ninit12", 6, 2, 2, 2, 2, "llf1", "ONP", "RK4", 12, 1),
 ]
 
 
@@ -153,6 +156,9 @@ def dg2d(only=None):
         t0 = time.time()
         kv = dict(nx=n, ny=n, mx=m, my=m, bc=bc, source=source, grad_phi_case=gcase, flux_type=flux, limiter_type=lim,
                   solver=solver, ninit=ninit)
+        box = 6.0 if ninit == 12 else 1.0
+        if box != 1.0:
+            kv.update(boxlen_x=box, boxlen_y=box)
         it = dg2d_interp(**kv)
         x, y = F(n, n, m, m), F(n, n, m, m)
         it.call("get_coords", x, y, n, n, m, m)
@@ -176,6 +182,7 @@ def dg2d(only=None):
         it.call("compute_max_speed", mean, *sp)
         out[f"{tag}/meta"] = np.array([n, m, bc, source, gcase, ninit, steps])
         out[f"{tag}/names"] = np.array([flux, lim, solver])
+        out[f"{tag}/boxlen"] = np.array(box)
         for k, v in (("x", x), ("y", y), ("nodes", nodes), ("modes", modes), ("nodes_back", back), ("dudt", dudt),
                      ("limited", lim_modes), ("rough_in", rough_in), ("rough_limited", rough)):
             out[f"{tag}/{k}"] = C(v)
@@ -187,7 +194,7 @@ def dg2d(only=None):
         # `steps` steps unless dt grows by more than 2x, and the last step is clipped by min(tend - t, ...).
         gll = (2 * (m - 1) + 3) // 2
         gll_w_1 = 1.0 if m == 1 else 1.0 / (float(gll * (gll - 1)) + float(np.float32(1e-10)))
-        dx = 1.0 / n
+        dx = box / n
         cfl = float(np.float32(0.2))
         dt0 = cfl * min(1.0 / 9.0, gll_w_1 / 2.0) / ((abs(vx) + cs) / dx + (abs(vy) + cs) / dx)
         tend = (steps - 0.5) * dt0

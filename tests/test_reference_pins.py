@@ -194,8 +194,9 @@ def test_dg1d_oracle_equals_reference_source(oracle, tag):
 def _dg2d_params(o, g, tag):
     n, m, bc, source, gcase, ninit, steps = (int(v) for v in g[f"{tag}/meta"])
     flux, lim, solver = (str(s) for s in g[f"{tag}/names"])
+    box = float(g[f"{tag}/boxlen"]) if f"{tag}/boxlen" in g.files else 1.0
     return o.dg2d_params(nx=n, ny=n, mx=m, my=m, bc=bc, source=source, grad_phi_case=gcase, flux=flux, limiter=lim,
-                         solver=solver, ninit=ninit), steps
+                         solver=solver, ninit=ninit, boxlen_x=box, boxlen_y=box), steps
 
 
 @pytest.mark.parametrize("tag", tags("ref_dg2d.npz"))
@@ -212,8 +213,10 @@ def test_dg2d_oracle_equals_reference_source(oracle, tag):
     p, steps = _dg2d_params(o, g, tag)
     x, y = o.dg2d_get_coords(p)
     assert same(x, g[f"{tag}/x"]) and same(y, g[f"{tag}/y"])
-    nodes = o.dg2d_get_initial_conditions(p, x, y)
-    assert same(nodes, g[f"{tag}/nodes"]), maxdiff(nodes, g[f"{tag}/nodes"])
+    if p.ninit <= 5:                       # the oracle restates initial conditions 1-5; the others come from the vectors
+        nodes = o.dg2d_get_initial_conditions(p, x, y)
+        assert same(nodes, g[f"{tag}/nodes"]), maxdiff(nodes, g[f"{tag}/nodes"])
+    nodes = g[f"{tag}/nodes"]
     modes = o.dg2d_get_modes_from_nodes(p, nodes)
     assert same(modes, g[f"{tag}/modes"])
     assert same(o.dg2d_get_nodes_from_modes(p, modes), g[f"{tag}/nodes_back"])

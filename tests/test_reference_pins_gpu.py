@@ -73,8 +73,9 @@ def test_fv2d_cuda_equals_reference_source(wb, tag, arith):
 def _dg2d(wb, g, tag, arith):
     n, m, bc, source, gcase, ninit, steps = (int(v) for v in g[f"{tag}/meta"])
     flux, lim, solver = (str(s) for s in g[f"{tag}/names"])
+    box = float(g[f"{tag}/boxlen"]) if f"{tag}/boxlen" in g.files else 1.0
     return wb.DG2D(nx=n, ny=n, mx=m, my=m, bc=bc, source=source, grad_phi_case=gcase, flux=flux, limiter=lim, solver=solver,
-                   ninit=ninit, device=0, arith=arith), steps, gcase, source
+                   ninit=ninit, device=0, arith=arith, boxlen_x=box, boxlen_y=box), steps, gcase, source
 
 
 @pytest.mark.parametrize("tag", tags("ref_dg2d.npz"))
