@@ -64,3 +64,43 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"\boracle\b", open(os.path.join(d, f), errors="ignore").read()):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def _c_struct_members(name):
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\}\s*" + name + r"\s*;", txt, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        out += [(ctype, n.strip()) for n in names.split(",")]
+    return out
+
+
+def _fortran_type_members(path, name):
+    txt = re.sub(r"!.*", "", open(path).read())
+    body = re.search(r"type,\s*bind\(C\)\s*::\s*" + name + r"(.*?)end type", txt, flags=re.S | re.I).group(1)
+    out = []
+    for line in body.strip().splitlines():
+        m = re.match(r"\s*(integer\(c_int\)|real\(c_double\))\s*::\s*(.*)", line.strip(), flags=re.I)
+        if m:
+            ctype = "int" if "c_int" in m.group(1).lower() else "double"
+            out += [(ctype, n.strip()) for n in m.group(2).split(",")]
+    return out
+
+
+@pytest.mark.parametrize("shim,struct", [("wb_shim_2d.f90", "wb_fv2d_params"), ("wb_shim_dg2d.f90", "wb_dg2d_params")])
+def test_fortran_shims_mirror_the_c_structs_and_bind_exported_symbols(lib, shim, struct):
+    """The ISO_C_BINDING shims cannot be compiled here (no Fortran compiler), so the parts that would fail silently are
+    checked textually: the bind(C) derived type has the C struct's members in the same order with the same types, every
+    bind(C, name=...) is a symbol the library exports, and the ctypes mirror used by the tests has the same layout."""
+    path = os.path.join(ROOT, "fvm-source-wb_b200", "fortran", shim)
+    c_members = _c_struct_members(struct)
+    assert _fortran_type_members(path, struct) == c_members
+    bound = re.findall(r'bind\(C,\s*name="(wb_[a-z0-9_]+)"\)', open(path).read())
+    assert bound and all(hasattr(lib, s) for s in bound), [s for s in bound if not hasattr(lib, s)]
+    import wbeuler
+    ct = {"wb_fv2d_params": wbeuler.FV2DParams, "wb_dg2d_params": wbeuler.DG2DParams}[struct]
+    assert [(("int" if t is C.c_int else "double"), n) for n, t in ct._fields_] == c_members
