@@ -58,6 +58,8 @@ def fv2d():
         ("pert", 12, 12, 3, 2, 3, 0.0), ("ragged", 13, 9, 3, 2, 2, 0.0), ("riemann", 12, 10, 4, 2, 3, 0.0),
         ("eq1", 8, 10, 1, 1, 2, 0.0), ("hydro", 10, 10, 2, 2, 2, 0.0), ("random", 9, 11, 3, 2, 2, 0.1),
         ("eq3_rand", 10, 8, 2, 3, 1, 0.05),
+        # the headline workload (BASELINE config 3: ninit 3, nequilibrium 2) on larger grids, more steps
+        ("headline_32", 32, 32, 3, 2, 6, 0.0), ("headline_48x40_rand", 48, 40, 3, 2, 4, 0.02),
     ]
     for tag, nx, ny, ninit, neq, steps, amp in cases:
         it = fv2d_interp(nx=nx, ny=ny, ninit=ninit, nequilibrium=neq)
@@ -142,6 +144,8 @@ DG2D_CASES = [  # tag, n (nx=ny), m (mx=my), bc, source, grad_phi_case, flux_typ
     # rotating disk in a 6 x 6 box (boxlen is a module variable): Keplerian grad_phi with the softened core and
     # special_boundary_conditions (:1481-1514), which freezes the update outside r = 2
     ("disk_o2_ninit12", 6, 2, 2, 2, 2, "llf1", "ONP", "RK4", 12, 1),
+    # the headline workload (BASELINE config 4: order 3, llf1, ONP, SSPRK(5,4), periodic pulse) on a larger grid, 3 steps
+    ("headline_o3_n6", 6, 3, 1, 1, 2, "llf1", "ONP", "RK4", 1, 3),
 ]
 
 
