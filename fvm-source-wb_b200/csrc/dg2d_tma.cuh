@@ -16,6 +16,9 @@
 
 namespace wb { namespace dg {
 
+#ifndef DGT_STAGE_RK
+#define DGT_STAGE_RK 0      /* measured on B200 (4096^2, order 3): 2.84e9 without, 2.19e9 with -- see stage_operand below */
+#endif
 constexpr int DGT_W = 36;                     // box columns: 2 (alignment) + 32 + 2
 
 namespace tma {
@@ -86,10 +89,38 @@ struct SmemSrc {
     }
   }
   // (staging the RK operands A0 / in through TMA as well was measured: 1.99e9 instead of 2.59e9 element-stages/s)
+#if DGT_STAGE_RK
+  // EXPERIMENT, off by default (slower, like the TMA-staged variant tried earlier: 1.99e9).
+  // The RK operands are needed at the very end of the block's life and their first use waits a full DRAM round trip
+  // (ncu: 13 % of the stall samples).  Each lane copies its own 36 values with cp.async into a region that has become
+  // free -- A0 into R2 once the bottom face is done, A1 into R1 once the top face is done -- and reads them back with LDS.
+  // A lane only reads what it copied itself, so cp.async.wait_group is all the synchronisation needed after the copy.
+  __device__ __forceinline__ void stage_operand(const double* A, uint32_t region) const {
+    const uint32_t dst = region + (lane + 2) * 8;
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * DGT_W * 8), "l"(A + (size_t)k * g.ne + e));
+    asm volatile("cp.async.commit_group;");
+  }
+  __device__ __forceinline__ void bottom_face_done(const StageCoef& C) const {
+    __syncwarp();                                  // every lane has read the row below
+    stage_operand(C.A0, r1 + REGION_B);
+  }
+  __device__ __forceinline__ void top_face_done(const StageCoef& C) const {
+    __syncwarp();                                  // every lane has read the row above
+    if (C.na >= 2) stage_operand(C.A1, r1);
+  }
+  __device__ __forceinline__ double rk_a0(const StageCoef& C, int v, int m) const {
+    if (v == 0 && m == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return R2[(v * M * M + m) * DGT_W + lane + 2];
+  }
+  __device__ __forceinline__ double rk_a1(const StageCoef& C, int v, int m) const { return R1[(v * M * M + m) * DGT_W + lane + 2]; }
+#else
   __device__ __forceinline__ void bottom_face_done(const StageCoef&) const {}
   __device__ __forceinline__ void top_face_done(const StageCoef&) const {}
   __device__ __forceinline__ double rk_a0(const StageCoef& C, int v, int m) const { return PL(C.A0, g, v, m)[e]; }
   __device__ __forceinline__ double rk_a1(const StageCoef& C, int v, int m) const { return PL(C.A1, g, v, m)[e]; }
+#endif
   __device__ __forceinline__ double rk_in(int v, int m) const { return PL(in, g, v, m)[e]; }
 };
 
