@@ -114,7 +114,12 @@ def run_reference(args):
         return
     from oracle import wb_oracle as o
     n = args.ref_grid
-    cores = o.max_threads()
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
+    # turn the N > 1 reference arm into a single-threaded run
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     o.set_num_threads(cores)
     p = o.fv2d_params(n, n)
     x, y = o.fv2d_get_coords(p)
@@ -125,7 +130,8 @@ def run_reference(args):
     u = o.fv2d_evolve(p, u, weq, 1e300, args.steps)[0]
     dt = time.perf_counter() - t0
     value = n * n * 2 * args.steps / dt
-    sample = f"{n}x{n} grid ({n*n/4096**2:.4f} of the 4096^2 workload's cells) per step, hydrostatic atmosphere + pressure bump"
+    wn = args.grid or (4096 if args.gpus == 1 else 16384)
+    sample = f"{n}x{n} grid ({n*n/wn**2:.4f} of the {wn}^2 workload's cells) per step, hydrostatic atmosphere + pressure bump"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
