@@ -311,3 +311,28 @@ def test_limiter_branches_that_are_not_built_and_why():
             assert "limiter_1d" in v["message"]
         if lim == "COC":
             assert abs(v["pressure_min"] - 1e-4) < 1e-11 and abs(v["pressure_max"] - 1e-4) < 1e-11
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("src,ranges,gone,kept", [
+    ("benchmark_2d.f90", ["221-260", "264-279", "465-618"], {"evolve", "compute_max_speed", "compute_update_exact"},
+     {"main", "get_coords", "get_initial_conditions", "get_equilibrium_solution", "compute_flux", "output_file"}),
+    ("2d/benchmark_2d_dg.f90", ["23-89", "497-592", "624-775", "826-870", "1137-1479", "1516-1555"],
+     {"compute_error", "get_modes_from_nodes", "get_nodes_from_modes", "evolve", "compute_max_speed", "compute_update", "apply_limiter"},
+     {"main", "get_coords", "get_initial_conditions", "get_equilibrium_solution", "output_file", "compute_num_flux"}),
+])
+def test_splitter_ranges_of_the_integration_recipes_cut_whole_routines(tmp_path, src, ranges, gone, kept):
+    """INTEGRATION.md / the Fortran shims tell a maintainer which line ranges tools/split_reference.py must drop.  The image
+    has no Fortran compiler, so the result is parsed with the Fortran-90 front end of oracle/f90interp.py instead: the
+    remainder must still be a sequence of complete program units, the replaced routines must be gone and the driver parts
+    (program, initialisers, output) must still be there."""
+    import subprocess
+    import sys
+    from oracle.f90interp import Interp
+    out = tmp_path / "driver.f90"
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "split_reference.py"),
+                           os.path.join(REF, src), str(out)] + ranges)
+    it = Interp().load(str(out))
+    names = set(it.units)
+    assert not (gone & names), gone & names
+    assert kept <= names, kept - names
