@@ -759,7 +759,8 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
       static bool configured = false;
       auto kern = k_stage_tma<MODE, MARCH_MIN_BLOCKS>;
       if (!configured) {       // 4 CTAs x <= 46.5 KiB of ring buffers per SM
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const char* envc = getenv("WB_FV2D_CARVEOUT");
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : (int)cudaSharedmemCarveoutMaxShared));
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_WARPS * tma_warp_bytes(MODE)));
         configured = true;
       }
