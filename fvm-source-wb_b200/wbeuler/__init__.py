@@ -232,6 +232,13 @@ class DG2D:
     def set_stream(self, cuda_stream_ptr):
         _check(lib().wb_dg2d_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def stage_kernel(self):
+        """name of the RK-stage kernel this handle launches ("split", "tma", "march", "fast", "reference")"""
+        f = lib().wb_dg2d_stage_kernel
+        f.restype = C.c_char_p
+        f.argtypes = [C.c_void_p]
+        return f(self._h).decode()
+
     def quadrature(self):
         """gl_quadrature(x_quad, w_quad, mx)  2d/legendre.f90:77-108"""
         x = np.zeros(self.params.mx); w = np.zeros(self.params.mx)

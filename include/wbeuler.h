@@ -147,6 +147,10 @@ int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream);
  * compute_max_speed is all-reduced in its two-phase form */
 int wb_dg2d_comm_init(wb_dg2d* h, const void* nccl_unique_id_128);
 int wb_dg2d_local_rows(const wb_dg2d* h, int* j0, int* nrows);
+/* which RK-stage kernel evolve / step_async launch on this handle: "split" (k_dg_stage_split: element split over four
+ * threads, faces once, rows staged by TMA; nx % 32 == 0), "tma" / "march" / "fast" (one thread per element: earlier
+ * data paths, same bits), "reference" (reference operation order: arith 1 or a neighbour-reading limiter) */
+const char* wb_dg2d_stage_kernel(const wb_dg2d* h);
 /* Gauss-Legendre nodes/weights exactly as gl_quadrature computes them (2d/legendre.f90:77-108) */
 int wb_dg2d_quadrature(wb_dg2d* h, double* x_quad, double* w_quad);
 /* replaces get_modes_from_nodes / get_nodes_from_modes   2d/benchmark_2d_dg.f90:497-542 / :544-592

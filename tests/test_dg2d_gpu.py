@@ -296,14 +296,74 @@ def test_larger_grid_properties(wb, oracle):
 def test_tma_staged_kernel_equals_the_global_memory_one(wb, oracle, monkeypatch):
     """Same arithmetic, different data path: with nx % 32 == 0 the modes travel through TMA + shared memory; switching that
     off (WB_DG2D_TMA=0) must give the same bits."""
+    monkeypatch.setenv("WB_DG2D_SPLIT", "0")       # the one-thread-per-element TMA kernel (superseded by k_dg_stage_split)
     p, s, x, y = mk(oracle, wb, 64, 3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1)
     u0 = oracle.dg2d_get_initial_conditions(p, x, y)
     with s:
         a, it, t, dt = s.evolve(u0, x, y, 1.0, 3)
+        assert s.stage_kernel() == "tma"
     monkeypatch.setenv("WB_DG2D_TMA", "0")
     with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s2:
         b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 3)
     assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
+
+
+@pytest.mark.parametrize("nx,mx,bc,kw", [
+    (64, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+    (64, 3, 2, dict(flux="llf1", limiter="ONP", solver="SS4", ninit=2, source=2, grad_phi_case=1)),   # gravity, clamped
+    (64, 2, 2, dict(flux="llf1", limiter="ONP", solver="EQL", ninit=3)),                             # clamped boundaries
+    (96, 3, 3, dict(flux="hllc", limiter="none", solver="DEB", ninit=5)),
+    (64, 4, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1, source=2, grad_phi_case=2)),
+    (64, 2, 1, dict(flux="hll2", limiter="ONP", solver="RK4", ninit=1, source=3)),
+    (64, 1, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
+])
+@pytest.mark.parametrize("rows", [32, 5, 1])
+def test_split_kernel_equals_the_two_sided_ones(wb, oracle, monkeypatch, nx, mx, bc, kw, rows):
+    """k_dg_stage_split (production, nx % 32 == 0): the element is split over four threads (one per variable), the pointwise
+    parts are dealt to all threads through shared memory, every face is evaluated once while the block marches up a strip
+    of `rows` rows.  Operation order of every sum, the LLF call and the limiter test are those of k_dg_stage_fast, so the
+    bits must be too.  rows = 1: every row is the first row of a strip; 5: ragged strips."""
+    p, _, x, y = mk(oracle, wb, nx, mx, arith=0, bc=bc, **kw)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    monkeypatch.setenv("WB_DG2D_ROWS", str(rows))
+    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s:
+        a, it, t, dt = s.evolve(u0, x, y, 1.0, 2)
+        assert s.stage_kernel() == "split"
+    monkeypatch.setenv("WB_DG2D_TMA", "0")
+    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s2:
+        b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 2)
+        assert s2.stage_kernel() == "fast"
+    assert np.all(np.isfinite(a))
+    assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
+
+
+@pytest.mark.parametrize("mx", [2, 3, 4])
+def test_split_kernel_limiter_point_evaluations(wb, oracle, monkeypatch, mx):
+    """Elements that fail the sufficient test of 'ONP' take the point evaluations of compute_positivity
+    (2d/limiters.f90:478-654), which the split kernel does with the element's four threads together: same bits as the
+    one-thread version over two SSPRK(5,4) steps of a violently oscillating state, and the reference's clipping to 1e-12
+    (forward-Euler 'DEB' steps: the rough state is chaotic under the five-stage scheme)."""
+    nx = 64
+    for solver, check_oracle in (("RK4", False), ("DEB", True)):
+        kw = dict(flux="llf1", limiter="ONP", solver=solver, ninit=5, bc=2)
+        p, _, x, y = mk(oracle, wb, nx, mx, arith=0, **kw)
+        u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+        rng = np.random.default_rng(5)
+        u0[..., 0] *= 1 + 0.9 * np.sign(rng.standard_normal(u0[..., 0].shape))       # violent nodal density oscillation
+        u0 = np.ascontiguousarray(u0)
+        monkeypatch.delenv("WB_DG2D_TMA", raising=False)
+        with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, **kw) as s:
+            a, it, t, dt = s.evolve(u0, x, y, 1.0, 2)
+            assert s.stage_kernel() == "split"
+        monkeypatch.setenv("WB_DG2D_TMA", "0")
+        with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, **kw) as s2:
+            b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 2)
+        assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
+        if check_oracle:
+            ref, it3, t3, dt3 = oracle.dg2d_evolve(p, u0, x, y, 1.0, 2)
+            # 1e-12 holds on the 8x8 grid of test_fused_limiter_acts_like_the_reference_one (same bits as this kernel); at
+            # dx = 1/64 the clipped, oscillating state amplifies the last-bit differences of rcp/rsqrt up to 3e-11 (order 4)
+            assert it == it3 == 2 and field_err(a, ref) <= 1e-10
 
 
 @pytest.mark.parametrize("nx,mx,bc,kw", [
@@ -336,7 +396,7 @@ def test_large_grid_properties(wb, monkeypatch):
     """2048^2 elements, order 3, llf1 + ONP + SSPRK(5,4), device-initialised periodic pulse (BASELINE config 4 is the same
     workload at 8192^2 = 19 GB per array; this size keeps the host copies at 1.2 GB).  No CPU run involved:
     (1) the fused production kernel agrees with the reference-order kernels to 1e-12 after a full step;
-    (2) the three data paths of the fused kernel (TMA-staged, marching, global loads) give the same bits;
+    (2) the four data paths of the fused stage (split over four threads, TMA-staged, marching, global loads) give the same bits;
     (3) the pulse's x <-> y mirror symmetry (momenta swapped, mode indices transposed) is kept to rounding;
     (4) the mean density changes only by the ~1e-8/step drift of the real(4) SSPRK weights (reference behaviour)."""
     n, m = 2048, 3
@@ -356,6 +416,8 @@ def test_large_grid_properties(wb, monkeypatch):
     assert dt == dt_ref
     assert field_err(fast, ref) <= 1e-12
     del ref
+    monkeypatch.setenv("WB_DG2D_SPLIT", "0")      # `fast` came from k_dg_stage_split; now the one-thread-per-element kernels
+    assert np.array_equal(run(0)[0], fast)
     monkeypatch.setenv("WB_DG2D_MARCH", "1")
     assert np.array_equal(run(0)[0], fast)
     monkeypatch.setenv("WB_DG2D_MARCH", "0")
