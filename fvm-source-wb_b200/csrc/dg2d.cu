@@ -1232,6 +1232,11 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
         h->FB.Pwh[q][n] = 0.5 * h->FB.Pw[q][n];
       }
     for (int n = 0; n < MAXM; ++n) { h->FB.Em[n] = B0.Em[n]; h->FB.Ep[n] = B0.Ep[n]; }
+    // the fused kernels drop the terms these identities make trivial (dg2d_fast.cuh, trace1)
+    for (int q = 0; q < p->mx; ++q)
+      if (B0.Em[0] != 1.0 || B0.Ep[0] != 1.0 || B0.P[q][0] != 1.0 || h->FB.dPw[q][0] != 0.0) {
+        set_error("basis tables: P_0 is not identically 1"); delete h; return WB_ERR_STATE;
+      }
     h->FB.gll = B0.gll;
   }
   h->arith = p->arith;

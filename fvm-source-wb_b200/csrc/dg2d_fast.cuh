@@ -136,31 +136,34 @@ __device__ __noinline__ Flux4 llf_call(double gamma, double gm1a, double a0, dou
 }  // namespace fastm
 
 // trace of one variable on one side: SIDE 0 left, 1 right (points along y), 2 bottom, 3 top (points along x)
+// Structural constants of the basis (checked at create, dg2d.cu): P_0 = 1, so Em[0] = Ep[0] = P[q][0] = 1 and dPw[q][0] = 0
+// exactly.  The fused kernels use them: a sum that starts with fma(x, 1, 0) starts with x, terms with a zero factor are
+// dropped (equal results up to the sign of an exact zero).
 template <int M, int SIDE>
 __device__ __forceinline__ void trace1(const double (&d)[M][M], const FastBasis& B, double (&out)[M]) {
   double t[M];
   if (SIDE < 2) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      double a = 0.0;
+      double a = d[0][j];
 #pragma unroll
-      for (int i = 0; i < M; ++i) a = fma(d[i][j], SIDE == 0 ? B.Em[i] : B.Ep[i], a);
+      for (int i = 1; i < M; ++i) a = fma(d[i][j], SIDE == 0 ? B.Em[i] : B.Ep[i], a);
       t[j] = a;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      double a = 0.0;
+      double a = d[i][0];
 #pragma unroll
-      for (int j = 0; j < M; ++j) a = fma(d[i][j], SIDE == 2 ? B.Em[j] : B.Ep[j], a);
+      for (int j = 1; j < M; ++j) a = fma(d[i][j], SIDE == 2 ? B.Em[j] : B.Ep[j], a);
       t[i] = a;
     }
   }
 #pragma unroll
   for (int q = 0; q < M; ++q) {
-    double a = 0.0;
+    double a = t[0];
 #pragma unroll
-    for (int n = 0; n < M; ++n) a = fma(t[n], B.P[q][n], a);
+    for (int n = 1; n < M; ++n) a = fma(t[n], B.P[q][n], a);
     out[q] = a;
   }
 }
@@ -429,16 +432,16 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
         double a[M];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-          double s = 0.0;
+          double s = dv[0][j];
 #pragma unroll
-          for (int i = 0; i < M; ++i) s = fma(dv[i][j], B.P[qx][i], s);
+          for (int i = 1; i < M; ++i) s = fma(dv[i][j], B.P[qx][i], s);
           a[j] = s;
         }
 #pragma unroll
         for (int qy = 0; qy < M; ++qy) {
-          double s = 0.0;
+          double s = a[0];
 #pragma unroll
-          for (int j = 0; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
+          for (int j = 1; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
           U[v][qx][qy] = s;
         }
       }
@@ -475,7 +478,10 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
         for (int qy = 0; qy < M; ++qy) {
           double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-          for (int qx = 0; qx < M; ++qx) { s1 = fma(f1[v][qx][qy], B.dPw[qx][a], s1); s2 = fma(f2[v][qx][qy], B.Pw[qx][a], s2); }
+          for (int qx = 0; qx < M; ++qx) {
+            if (a > 0) s1 = fma(f1[v][qx][qy], B.dPw[qx][a], s1);      // dPw[.][0] = 0
+            s2 = fma(f2[v][qx][qy], B.Pw[qx][a], s2);
+          }
           g1[a][qy] = s1; g2[a][qy] = s2;
         }
 #pragma unroll
@@ -484,7 +490,10 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
         for (int b = 0; b < M; ++b) {
           double s = acc[v][a][b];
 #pragma unroll
-          for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], fma(g2[a][qy], B.dPw[qy][b], s));
+          for (int qy = 0; qy < M; ++qy) {
+            if (b > 0) s = fma(g2[a][qy], B.dPw[qy][b], s);
+            if (a > 0) s = fma(g1[a][qy], B.Pw[qy][b], s);
+          }
           acc[v][a][b] = s;          // vol1 + vol2 - (e1-e2) - (e3-e4)
         }
       if (P.source != 1) {

@@ -1,6 +1,7 @@
 // Translation unit of k_dg_stage_split (dg2d_split.cuh): instantiations + launcher, kept apart from dg2d.cu so that the
 // production stage kernel of the 2D DG path (2d/benchmark_2d_dg.f90:1137-1479 fused with :683-707 and 2d/limiters.f90:478-654)
 // rebuilds in seconds.
+#include <cstdlib>
 #include "dg2d_common.cuh"
 #include "dg2d_fast.cuh"
 #include "dg2d_tma.cuh"
@@ -28,7 +29,9 @@ int launch1(const CUtensorMap* map, const double* in, const StageCoef& C, double
   const int nrows = row_end - row_begin;
   if (nrows <= 0) return WB_OK;
   dim3 b(128), gr((unsigned)(g.nx / 32), (unsigned)((nrows + rows - 1) / rows));
-  kern<<<gr, b, SplitLayout<M>::template bytes<SRC>(), stream>>>(*map, in, C, out, gx, gy, fz, g, P, B, ctrl, onp, rows, row_begin, row_end);
+  static const int variant = getenv("WB_DG2D_SCHED") ? atoi(getenv("WB_DG2D_SCHED")) : 0;      // phase-B schedule (development knob)
+  kern<<<gr, b, SplitLayout<M>::template bytes<SRC>(), stream>>>(*map, in, C, out, gx, gy, fz, g, P, B, ctrl, onp, rows | (variant << 16), row_begin,
+                                                                 row_end);
   WB_LAUNCH_CHECK();
   return WB_OK;
 }

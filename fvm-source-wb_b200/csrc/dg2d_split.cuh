@@ -41,12 +41,10 @@ struct SplitLayout {                                   // shared memory, in doub
   static constexpr int OFF_TR = OFF_TL + M * 4 * TW;   // [M][4][TW] right traces of columns -1..31 (index c+1)
   static constexpr int OFF_TT = OFF_TR + M * 4 * TW;   // [2][M][4][32] top traces -> top-face fluxes, by row parity
   static constexpr int OFF_TB = OFF_TT + 2 * M * 4 * 32;   // [M][4][32] bottom traces of the row above
-  static constexpr int OFF_SW = OFF_TB + M * 4 * 32;   // [NM nodes][3][32] w0, vx, vy (kernels with a source term only)
-  static constexpr int OFF_LIM = OFF_TR;               // [8][32] mean and mode bound of every variable ('ONP' test):
-                                                       // phase C only, when the right traces are dead
-  static constexpr int OFF_BAR_SRC = OFF_SW + NM * 3 * 32, OFF_BAR_NOSRC = OFF_SW;      // 2 mbarriers
-  template <bool SRC> static constexpr int bytes() { return ((SRC ? OFF_BAR_SRC : OFF_BAR_NOSRC) + 2) * 8; }
-  static_assert(M * 4 * TW >= 8 * 32 || M == 1, "LIM must fit into the right-trace array");
+  static constexpr int OFF_LIM = OFF_TB + M * 4 * 32;  // [8][32] mean and mode bound of every variable ('ONP' test)
+  static constexpr int OFF_SW = OFF_LIM + 8 * 32;      // [NM nodes][3][32] w0, vx, vy (kernels with a source term only)
+  static constexpr int OFF_BAR_SRC = OFF_SW + NM * 3 * 32, OFF_BAR_NOSRC = OFF_SW;      // 2 mbarriers + the step's dt
+  template <bool SRC> static constexpr int bytes() { return ((SRC ? OFF_BAR_SRC : OFF_BAR_NOSRC) + 3) * 8; }
   // work items of phase B: [0, NM) volume nodes, [NM, NM+M) left-face points, [NM+M, NM+2M) top-face points,
   // NM+2M: the x face behind the last column (M points, lanes 0..M-1)
   static constexpr int NTYPES = NM + 2 * M + 1;
@@ -58,12 +56,15 @@ struct SplitLayout {                                   // shared memory, in doub
 // slots (an FP64 instruction takes two): volume node ~65, face item ~175 (two prim() + two sound speeds + LLF).
 // M = 3: w0: x 0,1 + nodes 0,1 | w1: x 2, y 0 + nodes 2,3 | w2: y 1 + nodes 4..7 | w3: x 3 (extra), y 2 + node 8
 template <int M>
-__device__ __forceinline__ unsigned split_schedule(int w) {
+__device__ __forceinline__ unsigned split_schedule(int w, int variant) {
   constexpr int NM = M * M;
   auto pack = [](int x0, int x1, int y0, int y1, int n0, int n1) {
     return (unsigned)(x0 | (x1 << 4) | (y0 << 8) | (y1 << 12) | (n0 << 16) | (n1 << 21));
   };
   if (M == 3) {
+    if (variant == 1) return w == 0 ? pack(0, 2, 0, 0, 0, 1) : w == 1 ? pack(2, 3, 0, 1, 1, 2) : w == 2 ? pack(3, 3, 1, 2, 2, 7) : pack(3, 4, 2, 3, 7, 9);
+    if (variant == 2) return w == 0 ? pack(0, 2, 0, 0, 0, 0) : w == 1 ? pack(2, 3, 0, 1, 0, 0) : w == 2 ? pack(3, 3, 1, 2, 0, 6) : pack(3, 4, 2, 3, 6, 9);
+    if (variant == 3) return w == 0 ? pack(0, 2, 0, 0, 0, 3) : w == 1 ? pack(2, 3, 0, 1, 3, 5) : w == 2 ? pack(3, 3, 1, 2, 5, 8) : pack(3, 4, 2, 3, 8, 9);
     return w == 0 ? pack(0, 2, 0, 0, 0, 2) : w == 1 ? pack(2, 3, 0, 1, 2, 4) : w == 2 ? pack(3, 3, 1, 2, 4, 8) : pack(3, 4, 2, 3, 8, 9);
   }
   return pack(w * (M + 1) / 4, (w + 1) * (M + 1) / 4, w * M / 4, (w + 1) * M / 4, w * NM / 4, (w + 1) * NM / 4);
@@ -98,7 +99,7 @@ template <int M, bool ANYFLUX, bool SRC, bool OUT2>
 __global__ void __launch_bounds__(128, (M <= 3 ? DGS_MINB : 2))
 k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restrict__ in, StageCoef C, double* __restrict__ out,
                  const double* __restrict__ gx, const double* __restrict__ gy, const unsigned char* __restrict__ fz, DgGrid g,
-                 DgPhys P, const __grid_constant__ FastBasis B, const DgCtrl* __restrict__ ctrl, int apply_onp, int rows,
+                 DgPhys P, const __grid_constant__ FastBasis B, const DgCtrl* __restrict__ ctrl, int apply_onp, int rows_sched,
                  int row_begin, int row_end) {
   using L = SplitLayout<M>;
   constexpr int NM = L::NM, NS = L::NS;
@@ -106,6 +107,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
   double* sm = reinterpret_cast<double*>(dgs_smem);
   const int lane = threadIdx.x & 31, v = threadIdx.x >> 5;
   const int ic0 = blockIdx.x * 32;
+  const int rows = rows_sched & 0xffff;                      // strip height; bits 16.. = phase-B schedule variant
   const int j0 = row_begin + blockIdx.y * rows, j1 = min(j0 + rows, row_end);
   if (j0 >= j1) return;
   if (ctrl->skip) {
@@ -135,6 +137,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     arm_slot(0, y_nb(g, P.bc, j0 - 1));                      // row below the strip: only its top trace is needed
     arm_slot(1, j0);
+    sm[(SRC ? L::OFF_BAR_SRC : L::OFF_BAR_NOSRC) + 2] = ctrl->dt;      // read from shared memory once per row: no global-load latency there
   }
   __syncthreads();
   // Iteration `it` handles row j = j0-1+it (it = 0 is the prologue: top face of the row below the strip only).  Row j lies
@@ -142,7 +145,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
   // for row j+1 in iteration `it` is load number (it+1)>>1 of slot (it+1)&1.
   tma::mbar_wait(bars, 0);
   const int nit = j1 - j0 + 1;
-  const unsigned sched = split_schedule<M>(v);
+  const unsigned sched = split_schedule<M>(v, rows_sched >> 16);
 #pragma unroll 1
   for (int it = 0; it < nit; ++it) {
     const int j = j0 - 1 + it;
@@ -150,6 +153,16 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
     const int par = it & 1;
     double* TTp = TT + par * (M * 4 * 32);
     double U[SRC ? M : 1][SRC ? M : 1];                      // nodal values of the own variable (source terms only)
+    // RK operands of the NEXT row: ask L2 for them now (a plane's 32 columns are two 128-byte lines: lane l of warp v touches
+    // line l&1 of plane v*NM + l/2), so that phase C of the next iteration finds them in L2 instead of waiting for DRAM
+    // (ncu: long_scoreboard on the first use of A0 was 5-15 % of the stall samples).  Per-lane prefetch.global.L2, not the
+    // bulk form: that one takes a uniform address and costs a loop over the lanes.
+    if (lane < 2 * NM && j + 1 < j1) {
+      const size_t po = ((size_t)v * NM + (lane >> 1)) * g.ne + (size_t)(j + 1) * g.nx + ic0 + (lane & 1) * 16;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A0 + po));
+      if (C.na >= 2 && C.A1 != in) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A1 + po));
+      if (OUT2) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.B1 + po));
+    }
     // ------------------------------------------------------------------ phase A
     {
       const double* Sc = sm + par * L::SLOT_D + lane + 2;    // own column of row j
@@ -170,19 +183,19 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         for (int q = 0; q < M; ++q) TR[(q * 4 + v) * L::TW + lane + 1] = t1[q];
 #pragma unroll
         for (int qx = 0; qx < M; ++qx) {
-          double a[M];
+          double a[M];                                         // P[q][0] = 1: the sums start with their first term
 #pragma unroll
           for (int jm = 0; jm < M; ++jm) {
-            double s = 0.0;
+            double s = d[0][jm];
 #pragma unroll
-            for (int im = 0; im < M; ++im) s = fma(d[im][jm], B.P[qx][im], s);
+            for (int im = 1; im < M; ++im) s = fma(d[im][jm], B.P[qx][im], s);
             a[jm] = s;
           }
 #pragma unroll
           for (int qy = 0; qy < M; ++qy) {
-            double s = 0.0;
+            double s = a[0];
 #pragma unroll
-            for (int jm = 0; jm < M; ++jm) s = fma(a[jm], B.P[qy][jm], s);
+            for (int jm = 1; jm < M; ++jm) s = fma(a[jm], B.P[qy][jm], s);
             if (SRC) U[SRC ? qx : 0][SRC ? qy : 0] = s;
             UB[((qx * M + qy) * NS + v) * 32 + lane] = s;
           }
@@ -335,12 +348,14 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
           double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
           for (int qx = 0; qx < M; ++qx) {
-            s1 = fma(f1[qx], B.dPw[qx][a], s1); s2 = fma(f2[qx], B.Pw[qx][a], s2);
+            if (a > 0) s1 = fma(f1[qx], B.dPw[qx][a], s1);   // dPw[.][0] = 0 exactly: those terms are dropped
+            s2 = fma(f2[qx], B.Pw[qx][a], s2);
             if (SRC) s3 = fma(S[qx], B.Pw[qx][a], s3);
           }
 #pragma unroll
           for (int b = 0; b < M; ++b) {
-            acc[a][b] = fma(s1, B.Pw[qy][b], fma(s2, B.dPw[qy][b], acc[a][b]));
+            if (b > 0) acc[a][b] = fma(s2, B.dPw[qy][b], acc[a][b]);
+            if (a > 0) acc[a][b] = fma(s1, B.Pw[qy][b], acc[a][b]);
             if (SRC) sv[SRC ? a : 0][SRC ? b : 0] = fma(s3, B.Pw[qy][b], sv[SRC ? a : 0][SRC ? b : 0]);
           }
         }
@@ -355,7 +370,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
     }
     // ---- dudt scaling (:1449-1466), RK combination (:683-707).  c0*a0 with c0 == 1 is a0 exactly, so the first stage needs
     //      no special case; the frozen modes of special_boundary_conditions (:1481-1514) are a separate, rarely taken pass.
-    const double dt = ctrl->dt;
+    const double dt = sm[(SRC ? L::OFF_BAR_SRC : L::OFF_BAR_NOSRC) + 2];
 #pragma unroll
     for (int b = 0; b < M; ++b)
 #pragma unroll
