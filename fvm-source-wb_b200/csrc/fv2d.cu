@@ -40,7 +40,8 @@ struct StageArgs {
   const double* base;   // MODE 2: u^n (4 planes)
   double* out;          // 4 planes
   const double* weq;    // ref kernels: supplied primitive equilibrium at centres (4 planes)
-  const double* eqz;    // fast kernels: (rho_e, E_e) planes
+  const double* eqz;    // (rho_e, E_e) planes at the cell centres: conversions to / from the delta form, exact CFL speed
+  int eq_exact;         // fused kernels: 1 = the supplied centre equilibrium is not the analytic one, read eqz for the CFL speed
   const double* exf; const double* exc; const double* eyf; const double* eyc;  // separable exp tables
   Ctrl* ctrl;
   int parity;
@@ -51,25 +52,38 @@ struct StageArgs {
 };
 
 // ------------------------------------------------------------------------------------ layout kernels
-__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, Grid g) {
+// eqz != nullptr: the planes hold the DELTA FORM (u - u_eq at the cell centre, benchmark_2d.f90:499; the momenta of u_eq are
+// zero), which is what the fused stage kernels keep resident -- the subtraction happens once here instead of in every stage
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, Grid g, const double* __restrict__ eqz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y;
   if (i >= g.nx) return;
   const double2* src = reinterpret_cast<const double2*>(aos + ((size_t)j * g.nx + i) * 4);
   double2 a = src[0], b = src[1];
   size_t o = (size_t)(j + 1) * g.pitch + i;
+  if (eqz) { a.x = a.x - eqz[o]; b.y = b.y - eqz[g.plane + o]; }
   soa[o] = a.x;
   soa[g.plane + o] = a.y;
   soa[2 * g.plane + o] = b.x;
   soa[3 * g.plane + o] = b.y;
 }
-__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, Grid g) {
+// in place, all rows incl. ghosts: u -> u - u_eq (device-initialised states)
+__global__ void k_to_delta(double* __restrict__ u, const double* __restrict__ eqz, Grid g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (i >= g.nx) return;
+  size_t o = (size_t)r * g.pitch + i;
+  u[o] = u[o] - eqz[o];
+  u[3 * g.plane + o] = u[3 * g.plane + o] - eqz[g.plane + o];
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, Grid g, const double* __restrict__ eqz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y;
   if (i >= g.nx) return;
   size_t o = (size_t)(j + 1) * g.pitch + i;
   double2 a = make_double2(soa[o], soa[g.plane + o]);
   double2 b = make_double2(soa[2 * g.plane + o], soa[3 * g.plane + o]);
+  if (eqz) { a.x = eqz[o] + a.x; b.y = eqz[g.plane + o] + b.y; }      // u = u_eq + delta
   double2* dst = reinterpret_cast<double2*>(aos + ((size_t)j * g.nx + i) * 4);
   dst[0] = a;
   dst[1] = b;
@@ -78,7 +92,7 @@ __global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict_
 // (rho_e, E_e) planes from the supplied primitive equilibrium, all rows incl. ghosts
 // (compute_conservative, benchmark_2d.f90:159-171, :496); flags non-zero equilibrium velocity.
 __global__ void k_prepare_eq(const double* __restrict__ weq, double* __restrict__ eqz, Grid g, Phys P,
-                             Ctrl* ctrl) {
+                             Ctrl* ctrl, const double* __restrict__ exc, const double* __restrict__ eyc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int r = blockIdx.y;
   if (i >= g.nx) return;
@@ -90,6 +104,12 @@ __global__ void k_prepare_eq(const double* __restrict__ weq, double* __restrict_
   eqz[g.plane + o] = u[3];
   int jg = g.j0 + r - 1;
   if ((w[1] != 0.0 || w[2] != 0.0) && jg >= 0 && jg < g.ny) atomicOr(&ctrl->nonzero_vel, 1);
+  // is the supplied centre equilibrium the analytic one (to rounding)?  The fused stage-2 kernel then rebuilds it from the
+  // separable tables for the CFL speed; otherwise it reads these planes (bit 1 of the flag)
+  if (r >= 1 && r <= g.nyl) {
+    const double e = exc[i] * eyc[r - 1];
+    if (!(fabs(u[0] - P.rho0 * e) <= 1e-9 * fabs(u[0])) || !(fabs(u[3] - P.pe1 * e) <= 1e-9 * fabs(u[3]))) atomicOr(&ctrl->nonzero_vel, 2);
+  }
 }
 
 // ------------------------------------------------------------------------------------ IC on device
@@ -142,14 +162,16 @@ __global__ void k_init(double* __restrict__ u, double* __restrict__ weq, Grid g,
 // compute_max_speed (benchmark_2d.f90:264-279): max over all cells (boundary included) of
 // sqrt(vx^2+vy^2) + sqrt(gamma*max(p,1d-10)/max(rho,1d-10)); warp-shuffle + one atomicMax per block.
 template <bool FAST>
-__global__ void k_max_speed(const double* __restrict__ u, Grid g, Phys P, unsigned long long* out) {
+__global__ void k_max_speed(const double* __restrict__ u, Grid g, Phys P, unsigned long long* out, const double* __restrict__ eqz) {
   double m = 0.0;
   for (int r = blockIdx.y + 1; r <= g.nyl; r += gridDim.y)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nx; i += gridDim.x * blockDim.x) {
       size_t o = (size_t)r * g.pitch + i;
       double s;
       if (FAST) {
-        s = fast::speed(P, u[o], u[g.plane + o], u[2 * g.plane + o], u[3 * g.plane + o]);
+        double u0 = u[o], u3 = u[3 * g.plane + o];
+        if (eqz) { u0 = eqz[o] + u0; u3 = eqz[g.plane + o] + u3; }      // delta form
+        s = fast::speed(P, u0, u[g.plane + o], u[2 * g.plane + o], u3);
       } else {
         double uu[4] = {u[o], u[g.plane + o], u[2 * g.plane + o], u[3 * g.plane + o]};
         s = ref::speed(P, uu);
@@ -390,29 +412,34 @@ __device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const
 //     the left neighbour's delta from lane l-1 (lane 0 loads its halo column itself);
 //   * the bottom y-face flux is carried in registers from the previous row;
 //   * rows j+2 are prefetched while row j is computed (software pipelining instead of occupancy).
-// HBM traffic per cell: read u (4 doubles) + (rho_e,E_e) (2) [+ u^n (4) in stage 2], write 4.
+// HBM traffic per cell: read 4 doubles [+ u^n (4) in stage 2], write 4 (delta form, see Cell).
 constexpr int MARCH_WARPS = 4;      // warps per CTA (independent of each other)
 constexpr int MARCH_OUT = 31;       // output columns per warp
 #ifndef MARCH_MIN_BLOCKS
 #define MARCH_MIN_BLOCKS 4
 #endif
 
-struct Raw { double u0, u1, u2, u3, re, Ee; };       // one cell as loaded: u (4 planes) and (rho_e, E_e)
-struct Cell { double d0, d1, d2, d3, u0, u3, re; };   // delta, and what the source/update need of u, u_eq
+// The fused kernels keep the state in DELTA FORM: planes (rho - rho_e, mx, my, E - E_e) with (rho_e, E_e) the conservative
+// equilibrium at the cell centre (benchmark_2d.f90:496-499; its momenta are zero).  The subtraction is done once at upload
+// (k_aos_to_soa / k_to_delta) and undone at download, so a stage reads 32 B and writes 32 B per cell and nothing else:
+// the face equilibria come from the separable exp tables, the source term  s - s_eq = -(rho - rho_e)  is the density
+// perturbation itself, and the RK combination is linear, so it acts on the perturbation unchanged.
+struct Cell { double d0, d1, d2, d3; };
 
-__device__ __forceinline__ Raw load_raw(const StageArgs& A, const Grid& g, size_t o) {
-  Raw r;
-  r.u0 = A.in[o]; r.u1 = A.in[g.plane + o]; r.u2 = A.in[2 * g.plane + o]; r.u3 = A.in[3 * g.plane + o];
-  r.re = A.eqz[o]; r.Ee = A.eqz[g.plane + o];
-  return r;
-}
-// delta_u = u - u_eq (benchmark_2d.f90:499); the momenta of u_eq are zero
-__device__ __forceinline__ Cell make_cell(const Raw& r) {
+__device__ __forceinline__ Cell load_cell(const StageArgs& A, const Grid& g, size_t o) {
   Cell c;
-  c.u0 = r.u0; c.d1 = r.u1; c.d2 = r.u2; c.u3 = r.u3; c.re = r.re;
-  c.d0 = r.u0 - r.re;
-  c.d3 = r.u3 - r.Ee;
+  c.d0 = A.in[o]; c.d1 = A.in[g.plane + o]; c.d2 = A.in[2 * g.plane + o]; c.d3 = A.in[3 * g.plane + o];
   return c;
+}
+
+// Max wave speed of the updated cell (stage-2 CFL reduction, benchmark_2d.f90:264-295) from its delta form: the centre
+// equilibrium is rho0*e, p0/(gamma-1)*e with e = exp(-a xc) exp(-a yc) from the separable tables -- or, when the caller's
+// w_eq is not the analytic equilibrium, the planes it was given.
+__device__ __forceinline__ double centre_speed(const StageArgs& A, const Grid& g, const Phys& P, size_t o, double e, double n0,
+                                               double n1, double n2, double n3) {
+  double re = P.rho0 * e, Ee = P.pe1 * e;
+  if (A.eq_exact) { re = A.eqz[o]; Ee = A.eqz[g.plane + o]; }
+  return fast::speed(P, re + n0, n1, n2, Ee + n3);
 }
 
 // dudt of one cell from its four face fluxes, in the reference's order (benchmark_2d.f90:601-607)
@@ -426,22 +453,24 @@ __device__ __forceinline__ void cell_update(const Phys& P, const Cell& c, const 
   double d1 = fma(Gb.ft - Gt.ft, P.hody, -((Fr.fn - Fl.fn) * P.hodx));
   double d2 = fma(Gb.fn - Gt.fn, P.hody, -((Fr.ft - Fl.ft) * P.hodx));
   double d3 = fma(Gb.f3 - Gt.f3, P.hody, -((Fr.f3 - Fl.f3) * P.hodx));
-  d1 = (d1 - c.u0) + c.re;
-  d2 = (d2 - c.u0) + c.re;
+  d1 = d1 - c.d0;                      // s - s_eq = -(rho - rho_e)   (benchmark_2d.f90:327-350, :603-604)
+  d2 = d2 - c.d0;
   d3 = d3 - (c.d1 + c.d2);
   if (MODE == 0) {
     if (!interior) { d0 = 0.0; d1 = 0.0; d2 = 0.0; d3 = 0.0; }
     n0 = d0; n1 = d1; n2 = d2; n3 = d3;
   }
-  // frozen boundary lines (:611-614): dudt = 0 there; d is finite (clamped loads), so a zero time step is exact
+  // frozen boundary lines (:611-614): dudt = 0 there, selected (not multiplied by a zero time step: on a zero-filled halo
+  // column d may be NaN)
   if (MODE == 1) {
-    const double dtm = interior ? dt : 0.0;
-    n0 = fma(dtm, d0, c.u0); n1 = fma(dtm, d1, c.d1); n2 = fma(dtm, d2, c.d2); n3 = fma(dtm, d3, c.u3);
+    n0 = interior ? fma(dt, d0, c.d0) : c.d0; n1 = interior ? fma(dt, d1, c.d1) : c.d1;
+    n2 = interior ? fma(dt, d2, c.d2) : c.d2; n3 = interior ? fma(dt, d3, c.d3) : c.d3;
   }
   if (MODE == 2) {
-    const double hdt = interior ? 0.5 * dt : 0.0;
-    n0 = fma(hdt, d0, 0.5 * (b0 + c.u0)); n1 = fma(hdt, d1, 0.5 * (b1 + c.d1));
-    n2 = fma(hdt, d2, 0.5 * (b2 + c.d2)); n3 = fma(hdt, d3, 0.5 * (b3 + c.u3));
+    const double hdt = 0.5 * dt;
+    const double a0 = 0.5 * (b0 + c.d0), a1 = 0.5 * (b1 + c.d1), a2 = 0.5 * (b2 + c.d2), a3 = 0.5 * (b3 + c.d3);
+    n0 = interior ? fma(hdt, d0, a0) : a0; n1 = interior ? fma(hdt, d1, a1) : a1;
+    n2 = interior ? fma(hdt, d2, a2) : a2; n3 = interior ? fma(hdt, d3, a3) : a3;
   }
 }
 
@@ -463,16 +492,16 @@ struct MarchCtx {
 // `Gt` the top face flux (out).  The caller alternates (cur,Gb) <-> (nxt,Gt) so that no register is moved.
 template <int MODE>
 __device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, const Phys& P, const MarchCtx& c, int j,
-                                          const Cell& cur, Cell& nxt, Raw& nraw, Raw& hraw, const FaceFlux& Gb,
+                                          const Cell& cur, Cell& nxt, Cell& nraw, Cell& hraw, const FaceFlux& Gb,
                                           FaceFlux& Gt, double& spd) {
   auto row_off = [&](int jj) { return (size_t)(max(c.jmin, min(jj, c.jmax)) + 1) * g.pitch; };
   // ---- rows loaded during the previous call become usable now ...
-  nxt = make_cell(nraw);
-  const Cell hal = make_cell(hraw);
+  nxt = nraw;
+  const Cell hal = hraw;
   // ---- ... and this row's loads are issued before any arithmetic: row j+2, lane 0's halo of row j+1, u^n of
   //      row j (stage 2).  They are consumed one row (~250 FP64 instructions) later.
-  nraw = load_raw(A, g, row_off(j + 2) + c.ic);
-  if (c.lane == 0) hraw = load_raw(A, g, row_off(j + 1) + c.ih);
+  nraw = load_cell(A, g, row_off(j + 2) + c.ic);
+  if (c.lane == 0) hraw = load_cell(A, g, row_off(j + 1) + c.ih);
   const size_t o = row_off(j) + c.ic;
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (MODE == 2) { b0 = A.base[o]; b1 = A.base[g.plane + o]; b2 = A.base[2 * g.plane + o]; b3 = A.base[3 * g.plane + o]; }
@@ -482,8 +511,9 @@ __device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, con
   double l0 = __shfl_up_sync(0xffffffffu, cur.d0, 1), l1 = __shfl_up_sync(0xffffffffu, cur.d1, 1);
   double l2 = __shfl_up_sync(0xffffffffu, cur.d2, 1), l3 = __shfl_up_sync(0xffffffffu, cur.d3, 1);
   if (c.lane == 0) { l0 = hal.d0; l1 = hal.d1; l2 = hal.d2; l3 = hal.d3; }
+  const double tyc = A.eyc[min(j, g.nyl - 1)];
   const double ey = c.exc_i * A.eyf[min(j + 1, g.nyl)];
-  const double ex = c.exf_i * A.eyc[min(j, g.nyl - 1)];
+  const double ex = c.exf_i * tyc;
   FaceFlux Fl;
   {
     const FaceIn fy = {P.rho0 * ey, P.pe1 * ey, cur.d0, cur.d2, cur.d1, cur.d3, nxt.d0, nxt.d2, nxt.d1, nxt.d3};
@@ -504,7 +534,7 @@ __device__ __forceinline__ void march_row(const StageArgs& A, const Grid& g, con
   cell_update<MODE>(P, cur, Fl, Fr, Gb, Gt, interior, c.dt, b0, b1, b2, b3, n0, n1, n2, n3);
   if (c.writer) {
     A.out[o] = n0; A.out[g.plane + o] = n1; A.out[2 * g.plane + o] = n2; A.out[3 * g.plane + o] = n3;
-    if (MODE == 2) spd = fmax(spd, fast::speed(P, n0, n1, n2, n3));
+    if (MODE == 2) spd = fmax(spd, centre_speed(A, g, P, o, c.exc_i * tyc, n0, n1, n2, n3));
   }
 }
 
@@ -543,21 +573,21 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs 
   c.col_interior = (i > 0) && (i < g.nx - 1);
 
   // ---- prologue: rows jb-1, jb, jb+1 and lane 0's halo of row jb; bottom face of the strip
-  Cell ca = make_cell(load_raw(A, g, row_off(jb) + c.ic)), cb;
-  Raw nraw = load_raw(A, g, row_off(jb + 1) + c.ic);
-  Raw hraw = load_raw(A, g, row_off(jb) + (c.lane == 0 ? c.ih : c.ic));
+  Cell ca = load_cell(A, g, row_off(jb) + c.ic), cb;
+  Cell nraw = load_cell(A, g, row_off(jb + 1) + c.ic);
+  Cell hraw = load_cell(A, g, row_off(jb) + (c.lane == 0 ? c.ih : c.ic));
   FaceFlux Ga, Gb2;
   {
-    const Cell bel = make_cell(load_raw(A, g, row_off(jb - 1) + c.ic));
+    const Cell bel = load_cell(A, g, row_off(jb - 1) + c.ic);
     const double e = c.exc_i * A.eyf[jb];
     Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
   }
   // ---- L2 prefetch stream.  The register prefetch above gives one row of lead, which at 4 warps per scheduler
   //      does not cover the DRAM latency (the first use of the prefetched row was 40 % of all stall samples).
   //      So every row each warp also asks L2 for the CTA's 1 KiB segment (4 x 31 columns + halo) of local row
-  //      j + pf_rows of "its" input planes: plane p (u x4, eq x2, u^n x4 in stage 2) belongs to warp p mod 4.
+  //      j + pf_rows of "its" input planes: plane p (u x4, u^n x4 in stage 2) belongs to warp p mod 4.
   //      UBLKPF is a uniform-datapath instruction: one issue per warp, addresses from warp-uniform registers.
-  constexpr int NPF = (MODE == 2) ? 10 : 6;
+  constexpr int NPF = (MODE == 2) ? 8 : 4;
   constexpr int NPW = (NPF + MARCH_WARPS - 1) / MARCH_WARPS;
   const char* pf[NPW];
   const size_t pitchB = (size_t)g.pitch * sizeof(double);
@@ -570,8 +600,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, MB) k_stage_march(StageArgs 
 #pragma unroll
     for (int k = 0; k < NPW; ++k) {
       const int pl = min(warp + k * MARCH_WARPS, NPF - 1);
-      const double* b = (pl < 4) ? A.in + (size_t)pl * g.plane
-                      : (pl < 6) ? A.eqz + (size_t)(pl - 4) * g.plane : A.base + (size_t)(pl - 6) * g.plane;
+      const double* b = (pl < 4) ? A.in + (size_t)pl * g.plane : A.base + (size_t)(pl - 4) * g.plane;
       pf[k] = (const char*)(b + s0) + (size_t)(jb + A.pf_rows + 1) * pitchB;
     }
   }
@@ -615,12 +644,13 @@ struct wb_fv2d {
   bool own_stream = false;
   Grid g;
   Phys phys;
-  double *u = nullptr, *w1 = nullptr, *weq = nullptr, *eqz = nullptr, *stage = nullptr, *tab = nullptr;
+  double *u = nullptr, *w1 = nullptr, *weq = nullptr, *eqz = nullptr, *stage = nullptr, *tab = nullptr, *eqflag = nullptr;
   const double *exf = nullptr, *exc = nullptr, *eyf = nullptr, *eyc = nullptr;
   Ctrl* ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;       // pinned
   bool resident = false;
   bool fast_ok = true;          // supplied equilibrium has zero velocity -> fused kernels usable
+  bool eq_analytic = true;      // ... and is the analytic one at the cell centres (else the CFL speed reads the eqz planes)
   int parity = 0;
   wb::Nccl* comm = nullptr;
   cudaStream_t comm_stream = nullptr;   // slab mode: boundary rows + NCCL ghost exchange run here, overlapped with the interior
@@ -629,7 +659,7 @@ struct wb_fv2d {
   int march_rows = 32;          // rows per strip of the marching kernel
   int pf_rows = 4;              // L2 prefetch distance of the LDG marching kernel (rows ahead; 0 = off)
   bool tma_ok = false;          // tensor maps built: the TMA-fed stage kernel is used
-  CUtensorMap map_u, map_w1, map_eq;
+  CUtensorMap map_u, map_w1;
 };
 
 namespace {
@@ -662,18 +692,19 @@ int ensure_stage(wb_fv2d* h) {
 }
 
 // host AoS (Fortran u(nvar,nx,ny_local)) -> device SoA planes
-int h2d_state(wb_fv2d* h, const double* host, double* soa) {
+// (delta = true: stored as u - u_eq, the resident form of the fused kernels -- needs the eqz planes, i.e. prepare_eq first)
+int h2d_state(wb_fv2d* h, const double* host, double* soa, bool delta = false) {
   WB_CHECK(ensure_stage(h));
   WB_CUDA(cudaMemcpyAsync(h->stage, host, stage_bytes(h), cudaMemcpyHostToDevice, h->stream));
   dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
-  k_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g);
+  k_aos_to_soa<<<gr, b, 0, h->stream>>>(h->stage, soa, h->g, delta ? h->eqz : nullptr);
   WB_LAUNCH_CHECK();
   return WB_OK;
 }
-int d2h_state(wb_fv2d* h, const double* soa, double* host) {
+int d2h_state(wb_fv2d* h, const double* soa, double* host, bool delta = false) {
   WB_CHECK(ensure_stage(h));
   dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
-  k_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g);
+  k_soa_to_aos<<<gr, b, 0, h->stream>>>(soa, h->stage, h->g, delta ? h->eqz : nullptr);
   WB_LAUNCH_CHECK();
   WB_CUDA(cudaMemcpyAsync(host, h->stage, stage_bytes(h), cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
@@ -701,12 +732,22 @@ int prepare_eq(wb_fv2d* h) {
   WB_CHECK(exchange_ghost_rows(h, h->weq, 4));
   WB_CUDA(cudaMemsetAsync(&h->ctrl->nonzero_vel, 0, sizeof(int), h->stream));
   dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl + 2);
-  k_prepare_eq<<<gr, b, 0, h->stream>>>(h->weq, h->eqz, h->g, h->phys, h->ctrl);
+  k_prepare_eq<<<gr, b, 0, h->stream>>>(h->weq, h->eqz, h->g, h->phys, h->ctrl, h->exc, h->eyc);
   WB_LAUNCH_CHECK();
   int nz = 0;
   WB_CUDA(cudaMemcpyAsync(&nz, &h->ctrl->nonzero_vel, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
-  h->fast_ok = (nz == 0);
+  if (h->prm.nranks > 1 && h->comm) {      // every rank must take the same kernels (and the same CFL formula)
+    unsigned long long v[2] = {(unsigned long long)(nz & 1), (unsigned long long)((nz >> 1) & 1)};
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(h->eqflag);
+    WB_CUDA(cudaMemcpyAsync(d, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+    WB_CHECK(nccl_allreduce_max_u64(h->comm, d, 2, h->stream));
+    WB_CUDA(cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+    nz = (int)(v[0] | (v[1] << 1));
+  }
+  h->fast_ok = (nz & 1) == 0;
+  h->eq_analytic = (nz & 2) == 0;
   return WB_OK;
 }
 
@@ -744,7 +785,7 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   if (!stream) stream = h->stream;
   if (row_begin >= row_end) return WB_OK;
   StageArgs A;
-  A.in = in; A.base = base; A.out = out; A.weq = h->weq; A.eqz = h->eqz;
+  A.in = in; A.base = base; A.out = out; A.weq = h->weq; A.eqz = h->eqz; A.eq_exact = h->eq_analytic ? 0 : 1;
   A.exf = h->exf; A.exc = h->exc; A.eyf = h->eyf; A.eyc = h->eyc;
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
   A.row_begin = row_begin; A.row_end = row_end;
@@ -764,7 +805,7 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_WARPS * tma_warp_bytes(MODE)));
         configured = true;
       }
-      kern<<<gr, b, MARCH_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, h->map_eq, m_base ? *m_base : *m_in, A, h->g, h->phys, R);
+      kern<<<gr, b, MARCH_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, m_base ? *m_base : *m_in, A, h->g, h->phys, R);
     } else {
       k_stage_march<MODE, MARCH_MIN_BLOCKS><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
     }
@@ -778,11 +819,11 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
 }
 
 // max wave speed of `field` into ctrl->cmax_bits[slot] (all-reduced over ranks)
-int launch_max_speed(wb_fv2d* h, const double* field, int slot) {
+int launch_max_speed(wb_fv2d* h, const double* field, int slot, bool delta = false) {
   WB_CUDA(cudaMemsetAsync(&h->ctrl->cmax_bits[slot], 0, sizeof(unsigned long long), h->stream));
   dim3 b(256), gr(std::min((h->g.nx + 255) / 256, 64), std::min(h->g.nyl, 592));
-  if (h->prm.arith == 0) k_max_speed<true><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot]);
-  else k_max_speed<false><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot]);
+  if (h->prm.arith == 0) k_max_speed<true><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot], delta ? h->eqz : nullptr);
+  else k_max_speed<false><<<gr, b, 0, h->stream>>>(field, h->g, h->phys, &h->ctrl->cmax_bits[slot], nullptr);
   WB_LAUNCH_CHECK();
   if (h->prm.nranks > 1) {
     if (!h->comm) { set_error("nranks > 1 but wb_fv2d_comm_init was not called"); return WB_ERR_STATE; }
@@ -795,7 +836,7 @@ int reset_clock(wb_fv2d* h) {
   k_ctrl_reset<<<1, 1, 0, h->stream>>>(h->ctrl);
   WB_LAUNCH_CHECK();
   h->parity = 0;
-  return launch_max_speed(h, h->u, 0);
+  return launch_max_speed(h, h->u, 0, use_fast(h));
 }
 
 // One RK stage in slab mode: the two boundary rows first (on the comm stream, followed by the NCCL send/recv of
@@ -865,7 +906,7 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   cudaError_t e;
   if ((e = cudaMalloc(&h->u, fb)) != cudaSuccess || (e = cudaMalloc(&h->w1, fb)) != cudaSuccess ||
       (e = cudaMalloc(&h->weq, fb)) != cudaSuccess || (e = cudaMalloc(&h->eqz, fb / 2)) != cudaSuccess ||
-      (e = cudaMalloc(&h->ctrl, sizeof(Ctrl))) != cudaSuccess ||
+      (e = cudaMalloc(&h->ctrl, sizeof(Ctrl))) != cudaSuccess || (e = cudaMalloc(&h->eqflag, 16)) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl))) != cudaSuccess) {
     set_error("device allocation failed: %s", cudaGetErrorString(e));
     return fail(WB_ERR_CUDA);
@@ -898,7 +939,6 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
     if (p->arith == 0 && g.nx >= TMA_BOXW && !(env && atoi(env) == 0)) {
       int st = make_field_map(h, h->u, 4, &h->map_u);
       if (st == WB_OK) st = make_field_map(h, h->w1, 4, &h->map_w1);
-      if (st == WB_OK) st = make_field_map(h, h->eqz, 2, &h->map_eq);
       if (st != WB_OK) return fail(st);
       h->tma_ok = true;
     }
@@ -913,7 +953,7 @@ int wb_fv2d_destroy(wb_fv2d* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   nccl_comm_destroy(h->comm);
   cudaFree(h->u); cudaFree(h->w1); cudaFree(h->weq); cudaFree(h->eqz); cudaFree(h->stage); cudaFree(h->tab);
-  cudaFree(h->ctrl);
+  cudaFree(h->ctrl); cudaFree(h->eqflag);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
@@ -952,7 +992,7 @@ int wb_fv2d_upload(wb_fv2d* h, const double* u, const double* w_eq) {
   WB_CUDA(cudaSetDevice(h->dev));
   WB_CHECK(h2d_state(h, w_eq, h->weq));
   WB_CHECK(prepare_eq(h));
-  WB_CHECK(h2d_state(h, u, h->u));
+  WB_CHECK(h2d_state(h, u, h->u, use_fast(h)));        // fused kernels: resident state in delta form
   WB_CHECK(exchange_ghost_rows(h, h->u, 4));
   WB_CHECK(reset_clock(h));
   h->resident = true;
@@ -967,6 +1007,10 @@ int wb_fv2d_init_device(wb_fv2d* h, int ninit, double eta) {
   k_init<<<gr, b, 0, h->stream>>>(h->u, h->weq, h->g, h->phys, ninit, eta, 1, 1);
   WB_LAUNCH_CHECK();
   WB_CHECK(prepare_eq(h));
+  if (use_fast(h)) {
+    k_to_delta<<<gr, b, 0, h->stream>>>(h->u, h->eqz, h->g);
+    WB_LAUNCH_CHECK();
+  }
   WB_CHECK(reset_clock(h));
   h->resident = true;
   return WB_OK;
@@ -1031,7 +1075,7 @@ int wb_fv2d_download(wb_fv2d* h, double* u_out) {
   if (!h || !u_out) { set_error("null argument"); return WB_ERR_ARG; }
   if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
   WB_CUDA(cudaSetDevice(h->dev));
-  return d2h_state(h, h->u, u_out);
+  return d2h_state(h, h->u, u_out, use_fast(h));
 }
 
 int wb_fv2d_evolve(wb_fv2d* h, double* u_inout, const double* w_eq, double tend, int max_iter, int* iters_out,
@@ -1062,7 +1106,7 @@ static int update_common(wb_fv2d* h, const double* u, const double* w_eq, double
   h->resident = false;
   WB_CHECK(h2d_state(h, w_eq, h->weq));
   WB_CHECK(prepare_eq(h));
-  WB_CHECK(h2d_state(h, u, h->u));
+  WB_CHECK(h2d_state(h, u, h->u, use_fast(h) && wb_scheme));
   WB_CHECK(exchange_ghost_rows(h, h->u, 4));
   WB_CHECK(launch_stage<0>(h, h->u, nullptr, h->w1, 0.0, -1, wb_scheme));
   return d2h_state(h, h->w1, dudt);

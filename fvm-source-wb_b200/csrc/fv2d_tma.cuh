@@ -4,7 +4,7 @@
 // evaluated once; identical arithmetic, hence bit-identical results), but the rows no longer travel through
 // per-lane global loads and register prefetch buffers:
 //   * lane 0 of every warp issues ONE 3-D TMA tensor load per input array and row
-//     (box = 34 columns x 1 row x all planes, covering the warp's 32 columns plus the left halo) into a per-warp ring of shared-memory row slots, completion signalled on one mbarrier per slot;
+//     (box = 34 columns x 1 row x the 4 planes of the delta-form state, covering the warp's 32 columns plus the left halo) into a per-warp ring of shared-memory row slots, completion signalled on one mbarrier per slot;
 //   * the box may start anywhere whose BYTE offset is a multiple of 16 (measured on B200: an odd FP64 column
 //     coordinate raises "illegal instruction"; negative even ones are fine), so it starts at the even column
 //     x0 <= c0-1, and out-of-range columns (< 0, >= nx) are zero-filled by the hardware: no per-lane address
@@ -22,10 +22,9 @@ namespace wb { namespace fv2d {
 
 constexpr int TMA_BOXW = 34;                          // box columns (272 B: multiple of 16 B as TMA requires)
 constexpr int TMA_PLANE_B = TMA_BOXW * 8;             // bytes per plane row in a slot
-constexpr int TMA_IN_B = 4 * TMA_PLANE_B;             // 1088: u / w1 / u^n part of a slot (4 planes)
-constexpr int TMA_EQ_B = 2 * TMA_PLANE_B;             // 544:  (rho_e, E_e) part of a slot
-constexpr int TMA_IN_PAD = 1152;                      // parts start on 128-byte boundaries
-constexpr int TMA_SLOT_B = TMA_IN_PAD + 640;          // 1792 = 14 * 128
+constexpr int TMA_IN_B = 4 * TMA_PLANE_B;             // 1088: one row of a 4-plane field (delta form)
+constexpr int TMA_IN_PAD = 1152;                      // slots start on 128-byte boundaries
+constexpr int TMA_SLOT_B = TMA_IN_PAD;
 constexpr int TMA_DEPTH = 4;                          // state ring: rows p, p+1 in use, p+2, p+3 in flight
 #ifndef TMA_BDEPTH_N
 #define TMA_BDEPTH_N 4
@@ -76,13 +75,12 @@ struct TmaCtx {
 // lane 0: arm slot p & (DEPTH-1) and ask TMA for local row jb-1+p (clamped like the LDG kernel: ghost rows exist
 // only where a neighbouring slab does)
 template <int MODE>
-__device__ __forceinline__ void tma_issue_row(const TmaCtx& c, const CUtensorMap* m_in, const CUtensorMap* m_eq, int p) {
+__device__ __forceinline__ void tma_issue_row(const TmaCtx& c, const CUtensorMap* m_in, int p) {
   const int s = p & (TMA_DEPTH - 1);
   const int row = max(c.jmin, min(c.jb - 1 + p, c.jmax)) + 1;
   const uint32_t bar = c.bars + 8u * s, dst = c.ring + (uint32_t)(s * TMA_SLOT_B);
-  mbar_expect_tx(bar, TMA_IN_B + TMA_EQ_B);
+  mbar_expect_tx(bar, TMA_IN_B);
   tma_load_3d(dst, m_in, c.x0, row, 0, bar);
-  tma_load_3d(dst + TMA_IN_PAD, m_eq, c.x0, row, 0, bar);
 }
 __device__ __forceinline__ void tma_issue_base(const TmaCtx& c, const CUtensorMap* m_base, int q) {
   const int s = q & (TMA_BDEPTH - 1);
@@ -91,15 +89,13 @@ __device__ __forceinline__ void tma_issue_base(const TmaCtx& c, const CUtensorMa
   tma_load_3d(dst, m_base, c.x0, c.jb + q + 1, 0, bar);
 }
 // box column `col` (c.own = this lane's cell, c.own - 1 = its left neighbour) of ring row p
-__device__ __forceinline__ Raw tma_read_row(const TmaCtx& c, int p, int col) {
+__device__ __forceinline__ Cell tma_read_row(const TmaCtx& c, int p, int col) {
   const unsigned char* sp = c.wsm + (p & (TMA_DEPTH - 1)) * TMA_SLOT_B + col * 8;
-  Raw r;
-  r.u0 = *reinterpret_cast<const double*>(sp);
-  r.u1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
-  r.u2 = *reinterpret_cast<const double*>(sp + 2 * TMA_PLANE_B);
-  r.u3 = *reinterpret_cast<const double*>(sp + 3 * TMA_PLANE_B);
-  r.re = *reinterpret_cast<const double*>(sp + TMA_IN_PAD);
-  r.Ee = *reinterpret_cast<const double*>(sp + TMA_IN_PAD + TMA_PLANE_B);
+  Cell r;
+  r.d0 = *reinterpret_cast<const double*>(sp);
+  r.d1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
+  r.d2 = *reinterpret_cast<const double*>(sp + 2 * TMA_PLANE_B);
+  r.d3 = *reinterpret_cast<const double*>(sp + 3 * TMA_PLANE_B);
   return r;
 }
 
@@ -111,8 +107,8 @@ __device__ __forceinline__ RowOut tma_row_math(const StageArgs& A, const Grid& g
                                                const Cell& cur, const FaceFlux& Gb, double ey, double ex, bool& ok) {
   const int p = q + 1, j = c.jb + q;
   RowOut o;
-  o.nxt = make_cell(tma_read_row(c, p + 1, c.own));
-  const Cell lft = make_cell(tma_read_row(c, p, c.own - 1));
+  o.nxt = tma_read_row(c, p + 1, c.own);
+  const Cell lft = tma_read_row(c, p, c.own - 1);
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (MODE == 2) {
     const unsigned char* sp = c.wsm + TMA_DEPTH * TMA_SLOT_B + (q & (TMA_BDEPTH - 1)) * TMA_IN_PAD + c.own * 8;
@@ -150,7 +146,7 @@ __device__ __noinline__ RowOut tma_row_exact(StageArgs A, Grid g, Phys P, TmaCtx
 // One row including the ring bookkeeping and the stores.  (cur,Gb) in, (nxt,Gt) out as in march_row.
 template <int MODE>
 __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c,
-                                        const CUtensorMap* m_in, const CUtensorMap* m_eq, const CUtensorMap* m_base, int q,
+                                        const CUtensorMap* m_in, const CUtensorMap* m_base, int q,
                                         const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& tyf, double& tyc,
                                         double& spd) {
   const int p = q + 1, j = c.jb + q;
@@ -158,11 +154,11 @@ __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const
   //      so that the arithmetic of a row stays one basic block for the instruction scheduler)
   __syncwarp();
   if (c.lane == 0) {
-    if (q + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, m_eq, q + TMA_DEPTH);
+    if (q + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, q + TMA_DEPTH);
     if (MODE == 2 && q >= 1 && q - 1 + TMA_BDEPTH < c.nrows) tma_issue_base(c, m_base, q - 1 + TMA_BDEPTH);
   }
   // ---- y tables of this row were loaded one row ago; fetch the next row's now
-  const double ey = c.exc_i * tyf, ex = c.exf_i * tyc;
+  const double ey = c.exc_i * tyf, ex = c.exf_i * tyc, ec = c.exc_i * tyc;
   tyf = A.eyf[min(j + 2, g.nyl)];
   tyc = A.eyc[min(j + 1, g.nyl - 1)];
   // ---- row j+1 (own column) must have landed; row j (left neighbour) landed a row ago
@@ -178,15 +174,15 @@ __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const
   st_if(dst, o.n0, c.writer); st_if(dst + g.plane, o.n1, c.writer); st_if(dst + 2 * g.plane, o.n2, c.writer);
   st_if(dst + 3 * g.plane, o.n3, c.writer);
   if (MODE == 2) {
-    const double s = fast::speed(P, o.n0, o.n1, o.n2, o.n3);
+    const double s = centre_speed(A, g, P, (size_t)(j + 1) * g.pitch + min(c.i, g.nx - 1), ec, o.n0, o.n1, o.n2, o.n3);
     spd = c.writer ? fmax(spd, s) : spd;
   }
 }
 
 template <int MODE, int MB>
 __global__ void __launch_bounds__(MARCH_WARPS * 32, MB)
-k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CUtensorMap m_eq,
-            const __grid_constant__ CUtensorMap m_base, StageArgs A, Grid g, Phys P, int R) {
+k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CUtensorMap m_base, StageArgs A, Grid g, Phys P,
+            int R) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
   TmaCtx c;
   c.dt = 0.0;
@@ -232,7 +228,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
     for (int p = 0; p < TMA_DEPTH; ++p)
-      if (p < c.np) tma_issue_row<MODE>(c, &m_in, &m_eq, p);
+      if (p < c.np) tma_issue_row<MODE>(c, &m_in, p);
     if (MODE == 2) {
 #pragma unroll
       for (int q = 0; q < TMA_BDEPTH; ++q)
@@ -247,19 +243,19 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
   FaceFlux Ga, Gb2;
   {
     mbar_wait(c.bars, 0);
-    const Cell bel = make_cell(tma_read_row(c, 0, c.own));
+    const Cell bel = tma_read_row(c, 0, c.own);
     mbar_wait(c.bars + 8u, 0);
-    ca = make_cell(tma_read_row(c, 1, c.own));
+    ca = tma_read_row(c, 1, c.own);
     const double e = c.exc_i * A.eyf[c.jb];
     Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
   }
   double spd = 0.0;
   int q = 0;
   for (; q + 1 < c.nrows; q += 2) {      // two rows per trip: (ca,Ga)->(cb,Gb2)->(ca,Ga), no register rotation
-    tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
-    tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q + 1, cb, ca, Gb2, Ga, tyf, tyc, spd);
+    tma_row<MODE>(A, g, P, c, &m_in, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
+    tma_row<MODE>(A, g, P, c, &m_in, &m_base, q + 1, cb, ca, Gb2, Ga, tyf, tyc, spd);
   }
-  if (q < c.nrows) tma_row<MODE>(A, g, P, c, &m_in, &m_eq, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
+  if (q < c.nrows) tma_row<MODE>(A, g, P, c, &m_in, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
   if (MODE == 2) {
     spd = warp_max(spd);
     if (c.lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);

@@ -1,6 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_dg2d_gpu.py tests/test_reference_pins_gpu.py -x -q 2>&1 | tail -5 > gpurun_out/r2_c10_tests.log
-cat gpurun_out/r2_c10_tests.log
-( for n in 4096 8192 8192; do timeout 200 python tools/dg2d_rate.py $n 3 4; done ) 2>&1 | grep "^DG" | tee gpurun_out/r2_c10_rates.log
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_stage_tma -s 8 -c 2 -o gpurun_out/r2_fv_a python bench.py --steps 3 --warmup 3 --no-dg --no-cpu --no-e2e > gpurun_out/r2_c12_ncu.log 2>&1
+tail -2 gpurun_out/r2_c12_ncu.log | cut -c1-300
