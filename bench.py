@@ -41,13 +41,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_dg_traffic_bytes_per_element_stage():
-    """dram read+write per element-stage of the DG stage kernel from the committed ncu capture, or None."""
+def ncu_dg_profile():
+    """The committed ncu capture of the DG stage kernel (profiles/dg2d_traffic.json): dram bytes per element-stage and the
+    FP64-pipe utilisation BASELINE.md section 3 asks for; {} if absent."""
     p = os.path.join(ROOT, "profiles", "dg2d_traffic.json")
     try:
-        return float(json.load(open(p))["dram_bytes_per_element_stage"])
+        return json.load(open(p))
     except Exception:
-        return None
+        return {}
 
 
 def ncu_traffic_bytes_per_cell_stage():
@@ -106,14 +107,16 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """The reference's own algorithm on the host cores: the C oracle port of benchmark_2d.f90 (the Fortran
-    cannot be compiled in this image), all host threads, on a bounded sample (a 1024^2 grid of the same
-    atmosphere) per step."""
+    """The reference's own algorithm on the host cores: the C oracle port of benchmark_2d.f90 (the Fortran cannot be
+    compiled in this image), all host threads.  N = 1: the workload's own 4096^2 grid (same size as our arm; ~2 s per
+    RK2 step on 16 cores).  N > 1: rank 0 alone, a bounded 1024^2 sample of the 16384^2 workload per step (the full grid
+    would take minutes per step) -- said so in `config` and `cpu_baseline.sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import wb_oracle as o
-    n = args.ref_grid
+    wn = args.grid or (4096 if args.gpus == 1 else 16384)
+    n = args.ref_grid or (wn if args.gpus == 1 else 1024)
     # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
     # turn the N > 1 reference arm into a single-threaded run
     try:
@@ -125,17 +128,21 @@ def run_reference(args):
     x, y = o.fv2d_get_coords(p)
     weq = o.fv2d_get_equilibrium_solution(p, x, y)
     u = o.fv2d_get_initial_conditions(p, 3, x, y)
-    u = o.fv2d_evolve(p, u, weq, 1e300, max(args.warmup, 1))[0]
+    u = o.fv2d_evolve(p, u, weq, 1e300, max(1, min(args.warmup, 2)))[0]      # warm-up: page in, spin up the thread team
     t0 = time.perf_counter()
     u = o.fv2d_evolve(p, u, weq, 1e300, args.steps)[0]
     dt = time.perf_counter() - t0
     value = n * n * 2 * args.steps / dt
-    wn = args.grid or (4096 if args.gpus == 1 else 16384)
-    sample = f"{n}x{n} grid ({n*n/wn**2:.4f} of the {wn}^2 workload's cells) per step, hydrostatic atmosphere + pressure bump"
+    same = (n == wn)
+    sample = (f"the workload's own {n}x{n} grid, {args.steps} RK2 steps" if same else
+              f"{n}x{n} grid ({n*n/wn**2:.4f} of the {wn}^2 workload's cells) per step") + ", hydrostatic atmosphere + pressure bump"
+    cfg = workload_config(args.gpus, args)
+    cfg["reference_arm_grid"] = [n, n]
+    cfg["reference_arm_same_size"] = same
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, args),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -168,10 +175,63 @@ def cpu_baseline(sample_n=1024, steps=3):
                       f"gcc -O3 -ffp-contract=off, 1 thread; host has {os.cpu_count()} cores)"}
 
 
+def dg2d_cpu_baseline(n=64, steps=2):
+    """Serial C port of 2d/benchmark_2d_dg.f90 (oracle/dg2d.c) on a bounded sample: the same pulse on an n x n grid."""
+    from oracle import wb_oracle as o
+    o.set_num_threads(1)
+    p = o.dg2d_params(nx=n, ny=n, mx=3, my=3, flux="llf1", limiter="ONP", solver="RK4", ninit=1, bc=1)
+    x, y = o.dg2d_get_coords(p)
+    u0 = o.dg2d_get_initial_conditions(p, x, y)
+    t0 = time.perf_counter()
+    o.dg2d_evolve(p, u0, x, y, 1e300, steps)
+    dt = time.perf_counter() - t0
+    o.set_num_threads(o.max_threads())
+    return {"value": n * n * 5 * steps / dt, "unit": "element-stage-updates/s", "cores": 1, "kind": "port",
+            "sample": f"{n}x{n} elements, order 3, {steps} SSPRK(5,4) steps of the same pulse (C port of 2d/benchmark_2d_dg.f90, "
+                      f"gcc -O3 -ffp-contract=off, 1 thread; host has {os.cpu_count()} cores); counted as 5 stages per step "
+                      "although the reference evaluates the RHS 6 times"}
+
+
+def dg2d_e2e(args, stream, n=4096, steps=3):
+    """wb_dg2d_evolve(u_nodes_host, ...) with pinned host buffers: H2D of the nodal state, modes_from_nodes, `steps` SSPRK(5,4)
+    steps, nodes_from_modes, D2H -- at the largest grid whose nodal array (n^2 x 36 doubles) is reasonable to pin."""
+    import numpy as np
+    import torch
+    import wbeuler
+    import ctypes as C
+    lib = wbeuler.lib()
+    with wbeuler.DG2D(nx=n, ny=n, mx=3, my=3, flux="llf1", limiter="ONP", solver="RK4", ninit=1, bc=1, device=0) as s:
+        s.set_stream(stream.cuda_stream)
+        s.init_device(1)
+        u_h = torch.empty(s.shape, dtype=torch.float64).pin_memory()
+        u_np = u_h.numpy()
+        u0 = s.download()
+        it = C.c_int(); tt = C.c_double(); dd = C.c_double()
+
+        def evolve_call(k):      # the C-ABI call itself: the Python wrapper would copy the (pinned) array first
+            st = lib.wb_dg2d_evolve(s._h, wbeuler._ptr(u_np), None, None, C.c_double(1e300), C.c_int(k), C.byref(it), C.byref(tt),
+                                    C.byref(dd))
+            if st != 0:
+                raise RuntimeError(lib.wb_last_error().decode())
+        u_np[...] = u0
+        evolve_call(1)           # warm the staging buffers
+        u_np[...] = u0
+        del u0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        evolve_call(steps)
+        el = time.perf_counter() - t0
+        nbytes = u_np.nbytes
+    return {"value": n * n * 5 * steps / el, "unit": "element-stage-updates/s", "h2d_bytes_per_step": nbytes / steps,
+            "d2h_bytes_per_step": nbytes / steps, "seconds": el, "grid": [n, n],
+            "call": f"wb_dg2d_evolve(u_nodes_host, max_iter={steps}) once at {n}x{n}: H2D nodal state from pinned memory, projection, "
+                    f"{steps} SSPRK(5,4) steps, reconstruction, D2H"}
+
+
 def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
     """BASELINE config 4 (2D modal DG order 3, SSPRK(5,4), LLF, 'ONP' limiter, periodic pulse): element-stage updates/s
     with the state resident in HBM; 921.6 algorithmic bytes per element-stage.  Reported as an extra object of
-    the same JSON line; the headline metric stays the FV one."""
+    the same JSON line (with its own roofline / cpu_baseline / e2e); the headline metric stays the FV one."""
     import torch
     import wbeuler
     from wbeuler import dist as wd
@@ -183,40 +243,128 @@ def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
                                     solver="RK4", ninit=1, bc=1)
             s.set_stream(stream.cuda_stream)
             s.init_device(1)
-            s.step_async(2); s.sync()
-            steps = max(2, min(args.steps, 5))
+            s.step_async(5); s.sync()
+            steps = max(2, min(args.steps, 10))
+            sampler = ClockSampler(local_rank)
+            if rank == 0:
+                sampler.start()
+                time.sleep(0.2)
             l0 = wbeuler.kernel_launch_count()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             if world > 1:
                 import torch.distributed as dist
                 dist.barrier()
             torch.cuda.synchronize()
+            w0 = time.time()
             e0.record(stream); s.step_async(steps); e1.record(stream); e1.synchronize()
+            w1 = time.time()
             ms = e0.elapsed_time(e1)
             if world > 1:
                 ms = wd.max_over_ranks(ms, device=dev)
+            clocks = sampler.stop(w0, w1) if rank == 0 else None
             it, t, dt = s.sync()
             peak, src = measured_peak_gbs()
             rate = n * n * 5 * steps / (ms * 1e-3)
             stage_launches = 5 * steps
             achieved = 921.6 * n * n / world / (ms * 1e-3 / stage_launches) / 1e9      # per GPU
+            prof = ncu_dg_profile()
+            kern = s.stage_kernel()
             out.update({"value": rate, "ms_per_step": ms / steps, "steps": steps, "gpu_launches": wbeuler.kernel_launch_count() - l0,
                         "config": {"workload": f"2D modal DG, {n}x{n} elements, mx=my=3 (36 dof/element), SSPRK(5,4), llf1, ONP limiter, "
                                                "periodic Gaussian pulse (ninit=1), device-initialised", "grid": [n, n],
                                    "parallelism": f"y-slabs x{world} (ring)" if world > 1 else "single GPU"},
                         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                     "traffic": (ncu_dg_traffic_bytes_per_element_stage() or 0) * n * n / world or None,
-                                     "kernel": "k_dg_stage_tma<3> (fused update + RK combination + ONP, rows staged by TMA, 5 launches/step)",
+                                     "traffic": (prof.get("dram_bytes_per_element_stage") or 0) * n * n / world or None,
+                                     "kernel": f"k_dg_stage_{kern}<3> (fused update + RK combination + ONP: element split over four threads, "
+                                               "every face once, rows staged by TMA; 5 launches/step)",
                                      "algorithmic_bytes_per_launch": 921.6 * n * n / world, "peak_source": src,
-                                     "note": "the launch time includes the 4 small max-speed reduction kernels of each step"},
-                        "sim": {"iters": it, "t": t, "dt": dt}})
+                                     "fp64_pipe_frac": prof.get("fp64_pipe_active_frac"),
+                                     "fp64_pipe_source": prof.get("fp64_pipe_source"),
+                                     "note": "the launch time includes the 4 small max-speed reduction kernels of each step; the kernel "
+                                             "sits above the FP64 ridge, fp64_pipe_frac (ncu, committed capture) is the other roofline"},
+                        "clocks": clocks, "sim": {"iters": it, "t": t, "dt": dt}})
             s.close()
+            s = None
+            if world == 1 and rank == 0:
+                if not args.no_cpu:
+                    out["cpu_baseline"] = dg2d_cpu_baseline()
+                if not args.no_e2e:
+                    try:
+                        out["e2e"] = dg2d_e2e(args, stream)
+                    except Exception as e:
+                        out["e2e"] = {"skipped": str(e)}
             return out
         except Exception as e:  # e.g. out of memory at 8192^2: fall back to the next size
             out.setdefault("skipped", []).append(f"{n}: {e}")
             if s is not None:
                 s.close()
     return out
+
+
+def slab_parity(world, rank, local_rank):
+    """N > 1 only, before anything is timed: a small slab-decomposed run of both 2D paths must reproduce the single-GPU run
+    BIT FOR BIT (every rank computes the single-GPU reference on its own device; fields are gathered over the ranks)."""
+    import numpy as np
+    import torch.distributed as dist
+    import wbeuler
+    from wbeuler import dist as wd
+    res = {}
+    nx, ny, steps = 512, 384, 4
+    with wbeuler.FV2D(nx, ny, device=local_rank) as one:
+        u, weq = one.get_initial_conditions(3)
+        ref, it1, t1, dt1 = one.evolve(u, weq, 1.0, steps)
+    s = wd.make_slab_solver(wbeuler.FV2D, world, rank, local_rank, nx=nx, ny=ny)
+    got, it, t, dt = s.evolve(wd.scatter_rows(u, rank, world), wd.scatter_rows(weq, rank, world), 1.0, steps)
+    full = wd.gather_rows(got, ny)
+    s.close()
+    ok = bool(np.array_equal(full, ref) and (it, t, dt) == (it1, t1, dt1))
+    res["fv_bitwise"] = ok
+    res["fv_case"] = f"FV {nx}x{ny}, {steps} RK2 steps, ninit=3: fields and (iters, t, dt) of the {world}-slab run == single-GPU run"
+    n, dsteps = 64, 2
+    kw = dict(nx=n, ny=n, mx=3, my=3, flux="llf1", limiter="ONP", solver="RK4", ninit=1, bc=1)
+    with wbeuler.DG2D(device=local_rank, **kw) as one:
+        one.init_device(1); one.step_async(dsteps); r1 = one.sync(); refm = one.download_modes()
+    s = wd.make_slab_solver(wbeuler.DG2D, world, rank, local_rank, **kw)
+    s.init_device(1); s.step_async(dsteps); r2 = s.sync()
+    parts = [None] * world
+    dist.all_gather_object(parts, s.download_modes())
+    s.close()
+    okd = bool(np.array_equal(np.concatenate(parts, axis=2), refm) and r1 == r2)
+    res["dg_bitwise"] = okd
+    res["dg_case"] = f"DG {n}x{n} order 3, {dsteps} SSPRK(5,4) steps, ninit=1: modes and (iters, t, dt) of the {world}-slab run == single-GPU run"
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, okd))
+    res["fv_bitwise"] = all(f[0] for f in flags)
+    res["dg_bitwise"] = all(f[1] for f in flags)
+    return res
+
+
+def fv2d_big_n1(args, stream, n=16384, steps=5):
+    """N = 1 only: the 16384^2 grid of BASELINE config 5 on ONE GPU (30 GB resident), so that the 2/4/8-GPU lines have a
+    same-grid denominator.  Also written to a scratch file the N > 1 runs of the same box read back."""
+    import torch
+    import wbeuler
+    with wbeuler.FV2D(n, n, device=0) as s:
+        s.set_stream(stream.cuda_stream)
+        s.init_device(3)
+        s.step_async(3); s.sync()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream); s.step_async(steps); e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+    peak, src = measured_peak_gbs()
+    value = n * n * 2 * steps / (ms * 1e-3)
+    achieved = ALG_BYTES_PER_CELL_STAGE * n * n / (ms * 1e-3 / (2 * steps)) / 1e9
+    out = {"value": value, "unit": UNIT, "grid": [n, n], "steps": steps, "ms_per_step": ms / steps,
+           "roofline_frac": achieved / peak, "note": "same grid as the N > 1 lines (config 5) on one GPU: denominator of efficiency_same_grid"}
+    try:
+        json.dump(out, open(N1_BIG_FILE, "w"))
+    except Exception:
+        pass
+    return out
+
+
+N1_BIG_FILE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "wbeuler_fv2d_16384_n1.json")
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -240,6 +388,7 @@ def run_ours(args):
     cfg = workload_config(ngpu, args)
     n = cfg["grid"][0]
     stream = torch.cuda.current_stream()
+    parity = slab_parity(world, rank, local_rank) if (world > 1 and not args.no_parity) else None
 
     solver = wd.make_slab_solver(wbeuler.FV2D, world, rank, local_rank, nx=n, ny=n)
     solver.set_stream(stream.cuda_stream)
@@ -321,7 +470,7 @@ def run_ours(args):
                 "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (tr * cells_local_max if tr else None),
-                             "kernel": "k_stage_tma<1|2> (one fused, TMA-fed RK-stage kernel per launch, 2 per step)",
+                             "kernel": "k_stage_tma<1|2> (one fused, TMA-fed RK-stage kernel per launch, 2 per step; state resident in delta form)",
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE * cells_local_max,
                              "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
                              "note": "per GPU; achieved = 80 B x cells of the largest slab / mean stage-kernel time "
@@ -329,7 +478,27 @@ def run_ours(args):
                 "sim": {"iters": iters, "t": t_sim, "dt": dt_sim, "cmax": cmax}}
         if ngpu == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
+        if parity is not None:
+            line["slab_parity"] = parity
+        if ngpu > 1:
+            # same-grid efficiency against the single-GPU run of the SAME 16384^2 grid, when this box has produced one
+            # (bench.py --gpus 1 writes it; the driver runs N = 1, 2, 4, 8 back to back on one box)
+            try:
+                n1 = json.load(open(N1_BIG_FILE))
+                if n1.get("grid") == [n, n]:
+                    line["efficiency_same_grid"] = value / (ngpu * n1["value"])
+                    line["n1_same_grid"] = n1
+            except Exception:
+                line["efficiency_same_grid"] = None
+            line["scaling_note"] = (f"strong scaling of the {n}^2 grid over N > 1 GPUs; the N = 1 line of this bench is BASELINE config 3 "
+                                    "(4096^2), a different grid -- compare N > 1 values with `fv2d_16384_n1` of the N = 1 line "
+                                    "(or `efficiency_same_grid` here), not with its headline value")
     solver.close()
+    if ngpu == 1 and rank == 0 and not args.no_big:
+        try:
+            line["fv2d_16384_n1"] = fv2d_big_n1(args, stream)
+        except Exception as e:
+            line["fv2d_16384_n1"] = {"skipped": str(e)}
     if not args.no_dg:      # BASELINE config 4 rides along as an extra object (every rank takes part in slab mode)
         dg = dg2d_section(args, stream, world, rank, local_rank, dev)
         if rank == 0:
@@ -348,10 +517,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="override the grid edge (default 4096 at N=1, 16384 at N>1)")
-    ap.add_argument("--ref-grid", type=int, default=1024, help="grid edge of the reference arm's bounded sample")
+    ap.add_argument("--ref-grid", type=int, default=0, help="grid edge of the reference arm (default: the workload's 4096 at N=1, a 1024 sample at N>1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dg", action="store_true", help="skip the extra 2D DG (config 4) measurement at N=1")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the in-process slab == single-GPU bitwise check")
+    ap.add_argument("--no-big", action="store_true", help="N=1: skip the 16384^2 single-GPU run (same-grid denominator of N>1)")
     ap.add_argument("--dg-grid", type=int, default=8192)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

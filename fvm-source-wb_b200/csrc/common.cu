@@ -141,21 +141,39 @@ void nccl_comm_destroy(Nccl* c) {
   delete c;
 }
 
+// Inside an ncclGroupStart/End region an error must not return before the group is closed: every later NCCL call of the
+// thread would be queued into the open group and never issued.  `r` keeps the first failure, GroupEnd always runs.
+#define WB_NCCL_IN_GROUP(r, expr)                       \
+  do {                                                  \
+    if ((r) == ncclSuccess) (r) = (expr);               \
+  } while (0)
+
+static int nccl_group_result(ncclResult_t r, ncclResult_t end, const char* where) {
+  if (r == ncclSuccess) r = end;
+  if (r != ncclSuccess) {
+    set_error("NCCL error in %s: %s", where, g_nccl.GetErrorString(r));
+    return WB_ERR_NCCL;
+  }
+  return WB_OK;
+}
+
 int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* lo, int nlo,
                              const HaloSeg* hi, int nhi, cudaStream_t s) {
+  if (lo_peer < 0 && hi_peer < 0) return WB_OK;
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.GroupStart());
+  ncclResult_t r = ncclSuccess;
   if (lo_peer >= 0)
     for (int k = 0; k < nlo; ++k) {
-      WB_NCCL(g_nccl.Send(lo[k].send, lo[k].count, ncclDouble, lo_peer, c->comm, s));
-      WB_NCCL(g_nccl.Recv(lo[k].recv, lo[k].count, ncclDouble, lo_peer, c->comm, s));
+      WB_NCCL_IN_GROUP(r, g_nccl.Send(lo[k].send, lo[k].count, ncclDouble, lo_peer, c->comm, s));
+      WB_NCCL_IN_GROUP(r, g_nccl.Recv(lo[k].recv, lo[k].count, ncclDouble, lo_peer, c->comm, s));
     }
   if (hi_peer >= 0)
     for (int k = 0; k < nhi; ++k) {
-      WB_NCCL(g_nccl.Send(hi[k].send, hi[k].count, ncclDouble, hi_peer, c->comm, s));
-      WB_NCCL(g_nccl.Recv(hi[k].recv, hi[k].count, ncclDouble, hi_peer, c->comm, s));
+      WB_NCCL_IN_GROUP(r, g_nccl.Send(hi[k].send, hi[k].count, ncclDouble, hi_peer, c->comm, s));
+      WB_NCCL_IN_GROUP(r, g_nccl.Recv(hi[k].recv, hi[k].count, ncclDouble, hi_peer, c->comm, s));
     }
-  WB_NCCL(g_nccl.GroupEnd());
-  return WB_OK;
+  return nccl_group_result(r, g_nccl.GroupEnd(), "nccl_halo_exchange_multi");
 }
 
 // one contiguous message per side; the order (send lo, send hi, receive hi, receive lo) pairs the messages correctly
@@ -163,14 +181,14 @@ int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* l
 int nccl_ring_exchange(Nccl* c, int lo_peer, int hi_peer, const double* send_lo, const double* send_hi, double* recv_lo,
                        double* recv_hi, size_t count, cudaStream_t s) {
   if (lo_peer < 0 && hi_peer < 0) return WB_OK;
-  if (!c) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.GroupStart());
-  if (lo_peer >= 0) WB_NCCL(g_nccl.Send(send_lo, count, ncclDouble, lo_peer, c->comm, s));
-  if (hi_peer >= 0) WB_NCCL(g_nccl.Send(send_hi, count, ncclDouble, hi_peer, c->comm, s));
-  if (hi_peer >= 0) WB_NCCL(g_nccl.Recv(recv_hi, count, ncclDouble, hi_peer, c->comm, s));
-  if (lo_peer >= 0) WB_NCCL(g_nccl.Recv(recv_lo, count, ncclDouble, lo_peer, c->comm, s));
-  WB_NCCL(g_nccl.GroupEnd());
-  return WB_OK;
+  ncclResult_t r = ncclSuccess;
+  if (lo_peer >= 0) WB_NCCL_IN_GROUP(r, g_nccl.Send(send_lo, count, ncclDouble, lo_peer, c->comm, s));
+  if (hi_peer >= 0) WB_NCCL_IN_GROUP(r, g_nccl.Send(send_hi, count, ncclDouble, hi_peer, c->comm, s));
+  if (hi_peer >= 0) WB_NCCL_IN_GROUP(r, g_nccl.Recv(recv_hi, count, ncclDouble, hi_peer, c->comm, s));
+  if (lo_peer >= 0) WB_NCCL_IN_GROUP(r, g_nccl.Recv(recv_lo, count, ncclDouble, lo_peer, c->comm, s));
+  return nccl_group_result(r, g_nccl.GroupEnd(), "nccl_ring_exchange");
 }
 
 int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, double* recv_lo,
@@ -182,18 +200,22 @@ int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, dou
 }
 
 int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s) {
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint64, ncclMax, c->comm, s));
   return WB_OK;
 }
 int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s) {
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclMin, c->comm, s));
   return WB_OK;
 }
 int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s) {
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclMax, c->comm, s));
   return WB_OK;
 }
 int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s) {
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.Broadcast(buf, buf, count, ncclDouble, root, c->comm, s));
   return WB_OK;
 }

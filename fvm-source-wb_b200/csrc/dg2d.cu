@@ -1058,7 +1058,8 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
     dim3 b(32), gr((unsigned)((h->g.nx + DGM_COLS - 1) / DGM_COLS), (unsigned)((h->g.ny + h->march_rows - 1) / h->march_rows));
     DISPATCH_M(h, {
       auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_march<MM, true> : k_dg_stage_march<MM, false>;
-      static bool configured[2] = {false, false};
+      static bool configured_dev[64][2] = {};      // function attributes are per device
+      bool* configured = configured_dev[h->dev & 63];
       if (!configured[h->phys.flux_id >= 2]) {
         // 8 resident warps (255 registers) x 2 row slots: no more shared memory than that, the rest stays L1 for the spills
         const char* envc = getenv("WB_DG2D_CARVEOUT");
@@ -1073,7 +1074,8 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
     dim3 b(32), gr((unsigned)(h->g.ne / 32));
     DISPATCH_M(h, {
       auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_tma<MM, true> : k_dg_stage_tma<MM, false>;
-      static bool configured[2] = {false, false};
+      static bool configured_dev[64][2] = {};      // function attributes are per device
+      bool* configured = configured_dev[h->dev & 63];
       if (!configured[h->phys.flux_id >= 2]) {
         // 8 resident one-warp blocks (255 registers) need 8 x 21.9 KB = 175 KB of shared memory: ask for the 196 KB
         // configuration, not the maximum -- the 60 KB of L1 that remain serve the spills and the RK operand loads.
@@ -1417,6 +1419,7 @@ int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, con
   WB_CHECK(dg_set_xy(h, x, y));
   WB_CHECK(dg_ensure(h, &h->D));
   WB_CHECK(dg_h2d_field(h, modes, h->A));
+  WB_CHECK(dg_exchange(h, h->A));      // slab handles: the y neighbours of the first / last owned row live on other ranks
   WB_CHECK(dg_update(h, h->A, h->D, false));
   return dg_d2h_field(h, h->D, dudt);
 }
@@ -1428,6 +1431,7 @@ int wb_dg2d_apply_limiter(wb_dg2d* h, double* modes_inout) {
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 0);
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_h2d_field(h, modes_inout, h->A));
+  WB_CHECK(dg_exchange(h, h->A));      // (neighbour-reading limiters on slabs)
   WB_CHECK(dg_limiter(h, h->A, false));
   return dg_d2h_field(h, h->A, modes_inout);
 }

@@ -797,9 +797,10 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
     const CUtensorMap* m_in = (in == h->u) ? &h->map_u : (in == h->w1) ? &h->map_w1 : nullptr;
     const CUtensorMap* m_base = (base == h->u) ? &h->map_u : (base == h->w1) ? &h->map_w1 : nullptr;
     if (h->tma_ok && m_in && (MODE != 2 || m_base)) {
-      static bool configured = false;
+      static bool configured_dev[64] = {};      // function attributes are per device
+      bool& configured = configured_dev[h->dev & 63];
       auto kern = k_stage_tma<MODE, MARCH_MIN_BLOCKS>;
-      if (!configured) {       // 4 CTAs x <= 46.5 KiB of ring buffers per SM
+      if (!configured) {       // 4 CTAs x <= 37 KiB of ring buffers per SM
         const char* envc = getenv("WB_FV2D_CARVEOUT");
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : (int)cudaSharedmemCarveoutMaxShared));
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_WARPS * tma_warp_bytes(MODE)));

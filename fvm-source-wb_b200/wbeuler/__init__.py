@@ -58,9 +58,15 @@ def nccl_get_unique_id():
     return buf.raw
 
 
-def _ptr(a):
+def _ptr(a, shape=None):
+    """Pointer to a C-contiguous float64 array; with `shape`, the array must have exactly that shape (the library copies
+    prod(shape) doubles from the pointer: a wrong-sized array would be an out-of-bounds host read)."""
+    if not isinstance(a, np.ndarray):
+        raise WBError(f"expected a numpy array, got {type(a).__name__}")
     if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
         raise WBError("arrays must be C-contiguous float64")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise WBError(f"array of shape {tuple(a.shape)} where {tuple(shape)} is expected")
     return a.ctypes.data_as(_dp)
 
 
@@ -123,26 +129,26 @@ class FV2D:
     def compute_update_exact(self, u, w_eq):
         """compute_update_exact(u,w_eq,dudt)  benchmark_2d.f90:465-618"""
         dudt = np.empty(self.local_shape)
-        _check(lib().wb_fv2d_compute_update_exact(self._h, _ptr(u), _ptr(w_eq), _ptr(dudt)))
+        _check(lib().wb_fv2d_compute_update_exact(self._h, _ptr(u, self.local_shape), _ptr(w_eq, self.local_shape), _ptr(dudt)))
         return dudt
 
     def compute_update(self, u, w_eq):
         """compute_update(u,w_eq,dudt)  benchmark_2d.f90:370-463 (plain scheme)"""
         dudt = np.empty(self.local_shape)
-        _check(lib().wb_fv2d_compute_update(self._h, _ptr(u), _ptr(w_eq), _ptr(dudt)))
+        _check(lib().wb_fv2d_compute_update(self._h, _ptr(u, self.local_shape), _ptr(w_eq, self.local_shape), _ptr(dudt)))
         return dudt
 
     def compute_max_speed(self, u):
         """compute_max_speed(u,cmax)  benchmark_2d.f90:264-279"""
         c = C.c_double()
-        _check(lib().wb_fv2d_compute_max_speed(self._h, _ptr(u), C.byref(c)))
+        _check(lib().wb_fv2d_compute_max_speed(self._h, _ptr(u, self.local_shape), C.byref(c)))
         return c.value
 
     def evolve(self, u, w_eq, tend, max_iter=-1):
         """evolve(u,u_eq)  benchmark_2d.f90:221-260.  Returns (u_new, iters, t, last_dt)."""
         u = np.array(u, dtype=np.float64, order="C", copy=True)
         it = C.c_int(); t = C.c_double(); dt = C.c_double()
-        _check(lib().wb_fv2d_evolve(self._h, _ptr(u), _ptr(w_eq), C.c_double(tend), C.c_int(max_iter),
+        _check(lib().wb_fv2d_evolve(self._h, _ptr(u, self.local_shape), _ptr(w_eq, self.local_shape), C.c_double(tend), C.c_int(max_iter),
                                     C.byref(it), C.byref(t), C.byref(dt)))
         return u, it.value, t.value, dt.value
 
@@ -150,12 +156,12 @@ class FV2D:
         """get_initial_conditions + get_equilibrium_solution at centres (benchmark_2d.f90:45-113,:174-218).
         Returns (u, w_eq) for the local rows."""
         u = np.empty(self.local_shape); w = np.empty(self.local_shape)
-        _check(lib().wb_fv2d_get_initial_conditions(self._h, C.c_int(ninit), C.c_double(eta), _ptr(u), _ptr(w)))
+        _check(lib().wb_fv2d_get_initial_conditions(self._h, C.c_int(ninit), C.c_double(eta), _ptr(u, self.local_shape), _ptr(w)))
         return u, w
 
     # -- resident path ------------------------------------------------------------------------------
     def upload(self, u, w_eq):
-        _check(lib().wb_fv2d_upload(self._h, _ptr(u), _ptr(w_eq)))
+        _check(lib().wb_fv2d_upload(self._h, _ptr(u, self.local_shape), _ptr(w_eq, self.local_shape)))
 
     def init_device(self, ninit, eta=F32(0.00001)):
         _check(lib().wb_fv2d_init_device(self._h, C.c_int(ninit), C.c_double(eta)))
@@ -171,7 +177,7 @@ class FV2D:
 
     def download(self):
         u = np.empty(self.local_shape)
-        _check(lib().wb_fv2d_download(self._h, _ptr(u)))
+        _check(lib().wb_fv2d_download(self._h, _ptr(u, self.local_shape)))
         return u
 
     def reset_clock(self):
@@ -248,32 +254,32 @@ class DG2D:
     def get_modes_from_nodes(self, nodes):
         """2d/benchmark_2d_dg.f90:497-542"""
         out = np.empty(self.shape)
-        _check(lib().wb_dg2d_get_modes_from_nodes(self._h, _ptr(nodes), _ptr(out)))
+        _check(lib().wb_dg2d_get_modes_from_nodes(self._h, _ptr(nodes, self.shape), _ptr(out)))
         return out
 
     def get_nodes_from_modes(self, modes):
         """2d/benchmark_2d_dg.f90:544-592"""
         out = np.empty(self.shape)
-        _check(lib().wb_dg2d_get_nodes_from_modes(self._h, _ptr(modes), _ptr(out)))
+        _check(lib().wb_dg2d_get_nodes_from_modes(self._h, _ptr(modes, self.shape), _ptr(out)))
         return out
 
     def compute_error(self, u_nodes, u_init_nodes):
         """compute_error(u,x,y,t,u_anal)  2d/benchmark_2d_dg.f90:23-89 -> (lmax[4], l1[4], l2[4] before the sqrt)"""
         a = np.zeros(4); b = np.zeros(4); c = np.zeros(4)
-        _check(lib().wb_dg2d_compute_error(self._h, _ptr(u_nodes), _ptr(u_init_nodes), _ptr(a), _ptr(b), _ptr(c)))
+        _check(lib().wb_dg2d_compute_error(self._h, _ptr(u_nodes, self.shape), _ptr(u_init_nodes, self.shape), _ptr(a), _ptr(b), _ptr(c)))
         return a, b, c
 
     def compute_update(self, modes, x=None, y=None):
         """compute_update(delta_u,x,y,u_eq,dudt)  2d/benchmark_2d_dg.f90:1137-1479"""
         out = np.empty(self.shape)
-        _check(lib().wb_dg2d_compute_update(self._h, _ptr(modes), _ptr(x) if x is not None else None,
-                                            _ptr(y) if y is not None else None, _ptr(out)))
+        _check(lib().wb_dg2d_compute_update(self._h, _ptr(modes, self.shape), _ptr(x, self.shape[:-1]) if x is not None else None,
+                                            _ptr(y, self.shape[:-1]) if y is not None else None, _ptr(out)))
         return out
 
     def apply_limiter(self, modes):
         """apply_limiter(u)  2d/benchmark_2d_dg.f90:1516-1555"""
         u = np.array(modes, dtype=np.float64, order="C", copy=True)
-        _check(lib().wb_dg2d_apply_limiter(self._h, _ptr(u)))
+        _check(lib().wb_dg2d_apply_limiter(self._h, _ptr(u, self.shape)))
         return u
 
     def compute_max_speed(self, mean_mode):
@@ -287,12 +293,12 @@ class DG2D:
         """evolve(u,x,y,u_eq)  2d/benchmark_2d_dg.f90:624-775 -> (u_nodes_new, iters, t, last_dt)"""
         u = np.array(u_nodes, dtype=np.float64, order="C", copy=True)
         it = C.c_int(); t = C.c_double(); dt = C.c_double()
-        _check(lib().wb_dg2d_evolve(self._h, _ptr(u), _ptr(x) if x is not None else None, _ptr(y) if y is not None else None,
+        _check(lib().wb_dg2d_evolve(self._h, _ptr(u, self.shape), _ptr(x, self.shape[:-1]) if x is not None else None, _ptr(y, self.shape[:-1]) if y is not None else None,
                                     C.c_double(tend), C.c_int(max_iter), C.byref(it), C.byref(t), C.byref(dt)))
         return u, it.value, t.value, dt.value
 
     def upload(self, u_nodes, x=None, y=None):
-        _check(lib().wb_dg2d_upload(self._h, _ptr(u_nodes), _ptr(x) if x is not None else None, _ptr(y) if y is not None else None))
+        _check(lib().wb_dg2d_upload(self._h, _ptr(u_nodes, self.shape), _ptr(x, self.shape[:-1]) if x is not None else None, _ptr(y, self.shape[:-1]) if y is not None else None))
 
     def init_device(self, ninit, eta=F32(0.1)):
         _check(lib().wb_dg2d_init_device(self._h, C.c_int(ninit), C.c_double(eta)))

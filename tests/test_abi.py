@@ -104,3 +104,20 @@ def test_fortran_shims_mirror_the_c_structs_and_bind_exported_symbols(lib, shim,
     import wbeuler
     ct = {"wb_fv2d_params": wbeuler.FV2DParams, "wb_dg2d_params": wbeuler.DG2DParams}[struct]
     assert [(("int" if t is C.c_int else "double"), n) for n, t in ct._fields_] == c_members
+
+
+def test_python_binding_rejects_wrong_shapes():
+    """The library copies prod(shape) doubles from every array pointer it is handed: the binding checks dtype, layout AND
+    shape before a pointer leaves Python (no GPU needed)."""
+    import numpy as np
+    import wbeuler
+    a = np.zeros((4, 3, 4))
+    assert wbeuler._ptr(a, (4, 3, 4))
+    with pytest.raises(wbeuler.WBError):
+        wbeuler._ptr(a, (3, 4, 4))              # transposed-but-contiguous
+    with pytest.raises(wbeuler.WBError):
+        wbeuler._ptr(a[:2], (4, 3, 4))          # too small
+    with pytest.raises(wbeuler.WBError):
+        wbeuler._ptr(a.astype(np.float32), (4, 3, 4))
+    with pytest.raises(wbeuler.WBError):
+        wbeuler._ptr([[0.0]], (1, 1))           # not an ndarray

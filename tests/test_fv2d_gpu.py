@@ -51,6 +51,23 @@ def rel_linf_fields(a, b):
     return worst
 
 
+def own_norm_errs(a, b):
+    """Linf(a_v - b_v) / Linf(b_v) for every conserved field with a non-zero norm: the error of a field against ITS OWN
+    size (the momenta of the 1e-5 pressure bump are ~1e-7 of the state and are the only signal of the bump)."""
+    out = []
+    for v in range(4):
+        den = np.abs(b[..., v]).max()
+        out.append(np.abs(a[..., v] - b[..., v]).max() / den if den > 0 else 0.0)
+    return out
+
+
+# Stated bound for the own-norm error of the small fields: the reference's own rounding noise in the momenta is
+# O(ulp(p)/dx * dt) per stage ~ 1e-16 absolute, i.e. ~1e-9 of momenta of size 1e-7; a regression of the fused kernels from
+# there to 1e-7 would still pass the state-norm bar, so it is asserted separately.  Measured on B200 (256^2, 4 steps):
+# 2.8e-10 for the fused kernels, 1.8e-10 for the reference-order kernels (CUDA vs glibc exp alone).
+OWN_NORM_TOL = 1e-9
+
+
 def rhs_err(o, p, u, d, dref):
     dt = 0.5 * (p.boxlen_x / p.nx) / o.fv2d_compute_max_speed(p, u) * p.cfl
     return np.abs(dt * (d - dref)).max() / np.abs(u).max()
@@ -104,6 +121,9 @@ def test_evolve_matches_oracle(wb, oracle, nx, ny, ninit, steps, arith):
     assert it2 == it == steps
     assert abs(t2 - t) <= 1e-13 * t and abs(dt2 - dt) <= 1e-13 * dt
     assert rel_linf_fields(got, ref) <= TOL
+    own = own_norm_errs(got, ref)
+    print(f"own-norm errors (rho, mx, my, E) {nx}x{ny} ninit={ninit} arith={arith}: " + " ".join(f"{e:.2e}" for e in own))
+    assert max(own) <= OWN_NORM_TOL
 
 
 def test_evolve_until_tend_overshoots_like_the_reference(wb, oracle):
