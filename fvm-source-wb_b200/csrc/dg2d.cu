@@ -1234,6 +1234,16 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
         h->FB.Pwh[q][n] = 0.5 * h->FB.Pw[q][n];
       }
     for (int n = 0; n < MAXM; ++n) { h->FB.Em[n] = B0.Em[n]; h->FB.Ep[n] = B0.Ep[n]; }
+    // odd number of Gauss points: the middle node is the origin (the reference's Newton iterate is 0 or ~1e-17).  In the
+    // fused tables the odd polynomials and the derivatives of the even ones are exactly 0 there (dg2d_fast.cuh, zP / zD)
+    if (p->mx & 1) {
+      const int qm = p->mx / 2;
+      if (std::fabs(B0.xq[qm]) > 1e-14) { set_error("basis tables: middle Gauss node is not the origin"); delete h; return WB_ERR_STATE; }
+      for (int n = 0; n < MAXM; ++n) {
+        if (n & 1) { h->FB.P[qm][n] = 0.0; h->FB.Pw[qm][n] = 0.0; h->FB.Pwh[qm][n] = 0.0; }
+        else h->FB.dPw[qm][n] = 0.0;
+      }
+    }
     // the fused kernels drop the terms these identities make trivial (dg2d_fast.cuh, trace1)
     for (int q = 0; q < p->mx; ++q)
       if (B0.Em[0] != 1.0 || B0.Ep[0] != 1.0 || B0.P[q][0] != 1.0 || h->FB.dPw[q][0] != 0.0) {

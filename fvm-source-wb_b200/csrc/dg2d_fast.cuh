@@ -138,7 +138,11 @@ __device__ __noinline__ Flux4 llf_call(double gamma, double gm1a, double a0, dou
 // trace of one variable on one side: SIDE 0 left, 1 right (points along y), 2 bottom, 3 top (points along x)
 // Structural constants of the basis (checked at create, dg2d.cu): P_0 = 1, so Em[0] = Ep[0] = P[q][0] = 1 and dPw[q][0] = 0
 // exactly.  The fused kernels use them: a sum that starts with fma(x, 1, 0) starts with x, terms with a zero factor are
-// dropped (equal results up to the sign of an exact zero).
+// dropped (equal results up to the sign of an exact zero).  For an odd number of Gauss points the middle node is the origin
+// (the reference's Newton iterate is 0 or ~1e-17: snapped to 0 in the FUSED tables only), where the odd polynomials and the
+// derivatives of the even ones vanish: zP / zD name those table entries, and their terms are dropped as well.
+template <int M> __host__ __device__ constexpr bool zP(int q, int n) { return (M & 1) && q == M / 2 && (n & 1); }    // P, Pw, Pwh
+template <int M> __host__ __device__ constexpr bool zD(int q, int n) { return (M & 1) && q == M / 2 && !(n & 1); }   // dPw
 template <int M, int SIDE>
 __device__ __forceinline__ void trace1(const double (&d)[M][M], const FastBasis& B, double (&out)[M]) {
   double t[M];
@@ -163,7 +167,8 @@ __device__ __forceinline__ void trace1(const double (&d)[M][M], const FastBasis&
   for (int q = 0; q < M; ++q) {
     double a = t[0];
 #pragma unroll
-    for (int n = 1; n < M; ++n) a = fma(t[n], B.P[q][n], a);
+    for (int n = 1; n < M; ++n)
+      if (!zP<M>(q, n)) a = fma(t[n], B.P[q][n], a);
     out[q] = a;
   }
 }
@@ -313,7 +318,8 @@ __device__ __forceinline__ void face_accum(const FastBasis& B, const double (&F)
     for (int n = 0; n < M; ++n) {
       double a1 = 0.0;
 #pragma unroll
-      for (int q = 0; q < M; ++q) a1 = fma(F[q][v], B.Pw[q][n], a1);
+      for (int q = 0; q < M; ++q)
+        if (!zP<M>(q, n)) a1 = fma(F[q][v], B.Pw[q][n], a1);
       s[n] = a1;
     }
 #pragma unroll
@@ -434,14 +440,16 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
         for (int j = 0; j < M; ++j) {
           double s = dv[0][j];
 #pragma unroll
-          for (int i = 1; i < M; ++i) s = fma(dv[i][j], B.P[qx][i], s);
+          for (int i = 1; i < M; ++i)
+            if (!zP<M>(qx, i)) s = fma(dv[i][j], B.P[qx][i], s);
           a[j] = s;
         }
 #pragma unroll
         for (int qy = 0; qy < M; ++qy) {
           double s = a[0];
 #pragma unroll
-          for (int j = 1; j < M; ++j) s = fma(a[j], B.P[qy][j], s);
+          for (int j = 1; j < M; ++j)
+            if (!zP<M>(qy, j)) s = fma(a[j], B.P[qy][j], s);
           U[v][qx][qy] = s;
         }
       }
@@ -479,8 +487,8 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
           double s1 = 0.0, s2 = 0.0;
 #pragma unroll
           for (int qx = 0; qx < M; ++qx) {
-            if (a > 0) s1 = fma(f1[v][qx][qy], B.dPw[qx][a], s1);      // dPw[.][0] = 0
-            s2 = fma(f2[v][qx][qy], B.Pw[qx][a], s2);
+            if (a > 0 && !zD<M>(qx, a)) s1 = fma(f1[v][qx][qy], B.dPw[qx][a], s1);      // dPw[.][0] = 0
+            if (!zP<M>(qx, a)) s2 = fma(f2[v][qx][qy], B.Pw[qx][a], s2);
           }
           g1[a][qy] = s1; g2[a][qy] = s2;
         }
@@ -491,8 +499,8 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
           double s = acc[v][a][b];
 #pragma unroll
           for (int qy = 0; qy < M; ++qy) {
-            if (b > 0) s = fma(g2[a][qy], B.dPw[qy][b], s);
-            if (a > 0) s = fma(g1[a][qy], B.Pw[qy][b], s);
+            if (b > 0 && !zD<M>(qy, b)) s = fma(g2[a][qy], B.dPw[qy][b], s);
+            if (a > 0 && !zP<M>(qy, b)) s = fma(g1[a][qy], B.Pw[qy][b], s);
           }
           acc[v][a][b] = s;          // vol1 + vol2 - (e1-e2) - (e3-e4)
         }
@@ -504,7 +512,8 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
           for (int qy = 0; qy < M; ++qy) {
             double s = 0.0;
 #pragma unroll
-            for (int qx = 0; qx < M; ++qx) s = fma(U[v][qx][qy], B.Pw[qx][a], s);
+            for (int qx = 0; qx < M; ++qx)
+              if (!zP<M>(qx, a)) s = fma(U[v][qx][qy], B.Pw[qx][a], s);
             g1[a][qy] = s;
           }
 #pragma unroll
@@ -513,7 +522,8 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
           for (int b = 0; b < M; ++b) {
             double s = 0.0;
 #pragma unroll
-            for (int qy = 0; qy < M; ++qy) s = fma(g1[a][qy], B.Pw[qy][b], s);
+            for (int qy = 0; qy < M; ++qy)
+              if (!zP<M>(qy, b)) s = fma(g1[a][qy], B.Pw[qy][b], s);
             acc[v][a][b] = fma(src_scale, s, acc[v][a][b]);
           }
       }

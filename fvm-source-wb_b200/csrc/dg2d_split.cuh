@@ -77,7 +77,8 @@ __device__ __forceinline__ void face_accum1(const FastBasis& B, const double (&F
   for (int n = 0; n < M; ++n) {
     double a1 = 0.0;
 #pragma unroll
-    for (int q = 0; q < M; ++q) a1 = fma(F[q], B.Pwh[q][n], a1);      // F = 2 * flux, Pwh = Pw / 2
+    for (int q = 0; q < M; ++q)
+      if (!zP<M>(q, n)) a1 = fma(F[q], B.Pwh[q][n], a1);               // F = 2 * flux, Pwh = Pw / 2
     s[n] = a1;
   }
 #pragma unroll
@@ -188,14 +189,16 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
           for (int jm = 0; jm < M; ++jm) {
             double s = d[0][jm];
 #pragma unroll
-            for (int im = 1; im < M; ++im) s = fma(d[im][jm], B.P[qx][im], s);
+            for (int im = 1; im < M; ++im)
+              if (!zP<M>(qx, im)) s = fma(d[im][jm], B.P[qx][im], s);
             a[jm] = s;
           }
 #pragma unroll
           for (int qy = 0; qy < M; ++qy) {
             double s = a[0];
 #pragma unroll
-            for (int jm = 1; jm < M; ++jm) s = fma(a[jm], B.P[qy][jm], s);
+            for (int jm = 1; jm < M; ++jm)
+              if (!zP<M>(qy, jm)) s = fma(a[jm], B.P[qy][jm], s);
             if (SRC) U[SRC ? qx : 0][SRC ? qy : 0] = s;
             UB[((qx * M + qy) * NS + v) * 32 + lane] = s;
           }
@@ -348,15 +351,15 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
           double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
           for (int qx = 0; qx < M; ++qx) {
-            if (a > 0) s1 = fma(f1[qx], B.dPw[qx][a], s1);   // dPw[.][0] = 0 exactly: those terms are dropped
-            s2 = fma(f2[qx], B.Pw[qx][a], s2);
-            if (SRC) s3 = fma(S[qx], B.Pw[qx][a], s3);
+            if (a > 0 && !zD<M>(qx, a)) s1 = fma(f1[qx], B.dPw[qx][a], s1);   // exact zeros of the tables: terms dropped
+            if (!zP<M>(qx, a)) s2 = fma(f2[qx], B.Pw[qx][a], s2);
+            if (SRC && !zP<M>(qx, a)) s3 = fma(S[qx], B.Pw[qx][a], s3);
           }
 #pragma unroll
           for (int b = 0; b < M; ++b) {
-            if (b > 0) acc[a][b] = fma(s2, B.dPw[qy][b], acc[a][b]);
-            if (a > 0) acc[a][b] = fma(s1, B.Pw[qy][b], acc[a][b]);
-            if (SRC) sv[SRC ? a : 0][SRC ? b : 0] = fma(s3, B.Pw[qy][b], sv[SRC ? a : 0][SRC ? b : 0]);
+            if (b > 0 && !zD<M>(qy, b)) acc[a][b] = fma(s2, B.dPw[qy][b], acc[a][b]);
+            if (a > 0 && !zP<M>(qy, b)) acc[a][b] = fma(s1, B.Pw[qy][b], acc[a][b]);
+            if (SRC && !zP<M>(qy, b)) sv[SRC ? a : 0][SRC ? b : 0] = fma(s3, B.Pw[qy][b], sv[SRC ? a : 0][SRC ? b : 0]);
           }
         }
       }
