@@ -203,7 +203,7 @@ int wb_fvm1d_create(wb_fvm1d** h, const wb_fvm1d_params* p);
 int wb_fvm1d_destroy(wb_fvm1d* h);
 /* replaces compute_update(u,dudt)      fvm.f90:188-251 */
 int wb_fvm1d_compute_update(wb_fvm1d* h, const double* u, double* dudt);
-/* replaces compute_max_speed(u,cmax)   fvm.f90:314-330 */
+/* replaces compute_max_speed(u,cmax)   fvm.f90:320-336 */
 int wb_fvm1d_compute_max_speed(wb_fvm1d* h, const double* u, double* cmax);
 /* replaces the main time loop          fvm.f90:56-76 */
 int wb_fvm1d_evolve(wb_fvm1d* h, double* u_inout, double tend, int max_iter, int* iters_out, double* t_out,
@@ -229,7 +229,7 @@ int wb_fv1d_compute_update(wb_fv1d* h, const double* u, const double* w_eq, doub
 int wb_fv1d_compute_update_fvm(wb_fv1d* h, const double* u, const double* w_eq, double* dudt);
 /* replaces compute_update_sr(u,w_eq,dudt) ('WB1')     benchmark_1d.f90:553-747 (w_eq is not read, may be NULL) */
 int wb_fv1d_compute_update_sr(wb_fv1d* h, const double* u, const double* w_eq, double* dudt);
-/* replaces compute_max_speed(u,cmax)                  benchmark_1d.f90:154-165 */
+/* replaces compute_max_speed(u,cmax)                  benchmark_1d.f90:157-170 */
 int wb_fv1d_compute_max_speed(wb_fv1d* h, const double* u, double* cmax);
 /* replaces evolve(u,u_eq,x)                           benchmark_1d.f90:200-261 (scheme = params.solver) */
 int wb_fv1d_evolve(wb_fv1d* h, double* u_inout, const double* w_eq, double tend, int max_iter, int* iters_out,
@@ -277,10 +277,10 @@ int wb_dg1d_evolve_rk(wb_dg1d* h, int integrator, double* u_inout, const double*
 /* replaces compute_update_exact(u,u_eq_modes,dudt)   dg_with_source.f90:1380-1744: full-state modes against the
  * equilibrium MODES; bc 4 | 5 (with any other bc the reference uses out-of-bounds face states) */
 int wb_dg1d_compute_update_exact(wb_dg1d* h, const double* u, const double* u_eq_modes, double* dudt);
-/* replaces limiter_TDV(u)   :520-600 -- only with use_limiter = .false. (the shipped value): its moment-limiting block
+/* replaces limiter_TDV(u)   :523-606 -- only with use_limiter = .false. (the shipped value): its moment-limiting block
  * indexes the neighbours with a stale loop variable (:550-552), what remains is the positivity fallback on the traces */
 int wb_dg1d_limiter_tdv(wb_dg1d* h, double* u_inout);
-/* replaces limiter_cons(u)   :602-734 */
+/* replaces limiter_cons(u)   :610-734 */
 int wb_dg1d_limiter_cons(wb_dg1d* h, double* u_inout);
 /* replaces the main time loop with integrator 'RKw' (5, :229-270) or 'RKe' (6, :273-280).  u (full-state modes, 'RKw'),
  * delta_u (perturbation modes; input of 'RKe', output of both) and uinit are updated in place */

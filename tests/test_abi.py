@@ -91,8 +91,13 @@ def _fortran_type_members(path, name):
     return out
 
 
-@pytest.mark.parametrize("shim,struct", [("wb_shim_2d.f90", "wb_fv2d_params"), ("wb_shim_dg2d.f90", "wb_dg2d_params")])
-def test_fortran_shims_mirror_the_c_structs_and_bind_exported_symbols(lib, shim, struct):
+SHIMS = [("wb_shim_2d.f90", "wb_fv2d_params", "FV2DParams"), ("wb_shim_dg2d.f90", "wb_dg2d_params", "DG2DParams"),
+         ("wb_shim_fvm1d.f90", "wb_fvm1d_params", "FVM1DParams"), ("wb_shim_fv1d.f90", "wb_fv1d_params", "FV1DParams"),
+         ("wb_shim_dg1d.f90", "wb_dg1d_params", "DG1DParams")]
+
+
+@pytest.mark.parametrize("shim,struct,mirror", SHIMS)
+def test_fortran_shims_mirror_the_c_structs_and_bind_exported_symbols(lib, shim, struct, mirror):
     """The ISO_C_BINDING shims cannot be compiled here (no Fortran compiler), so the parts that would fail silently are
     checked textually: the bind(C) derived type has the C struct's members in the same order with the same types, every
     bind(C, name=...) is a symbol the library exports, and the ctypes mirror used by the tests has the same layout."""
@@ -102,8 +107,87 @@ def test_fortran_shims_mirror_the_c_structs_and_bind_exported_symbols(lib, shim,
     bound = re.findall(r'bind\(C,\s*name="(wb_[a-z0-9_]+)"\)', open(path).read())
     assert bound and all(hasattr(lib, s) for s in bound), [s for s in bound if not hasattr(lib, s)]
     import wbeuler
-    ct = {"wb_fv2d_params": wbeuler.FV2DParams, "wb_dg2d_params": wbeuler.DG2DParams}[struct]
+    ct = getattr(wbeuler, mirror)
     assert [(("int" if t is C.c_int else "double"), n) for n, t in ct._fields_] == c_members
+
+
+def _c_prototypes():
+    """name -> list of argument kinds of every `int wb_*(...)` / `const char* wb_*(...)` prototype of the header"""
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const\s+char\s*\*|long\s+long)\s+(wb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        kinds = []
+        for a in m.group(2).split(","):
+            a = " ".join(a.split())
+            if a in ("", "void"):
+                continue
+            if "**" in a:
+                kinds.append("handle_out")
+            elif re.search(r"wb_\w+_params\s*\*", a):
+                kinds.append("struct_in")
+            elif re.search(r"\bwb_\w+\s*\*", a):
+                kinds.append("handle")
+            elif re.search(r"\bdouble\s*\*", a):
+                kinds.append("ptr_double")
+            elif re.search(r"\bint\s*\*", a):
+                kinds.append("ptr_int")
+            elif re.search(r"\bvoid\s*\*", a):
+                kinds.append("ptr_void")
+            elif re.search(r"\bdouble\b", a):
+                kinds.append("val_double")
+            elif re.search(r"\bint\b", a):
+                kinds.append("val_int")
+            else:
+                kinds.append("?" + a)
+        out[m.group(1)] = kinds
+    return out
+
+
+def _fortran_interfaces(path):
+    """name -> list of argument kinds of every bind(C) function interface of a shim (dummy order of the function statement)"""
+    txt = re.sub(r"!.*", "", open(path).read())
+    txt = re.sub(r"&\s*\n\s*", " ", txt)                       # continuation lines
+    out = {}
+    for m in re.finditer(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)(.*?)end function", txt, flags=re.S | re.I):
+        dummies = [d.strip().lower() for d in m.group(2).split(",") if d.strip()]
+        kind = {}
+        for line in m.group(4).splitlines():
+            d = re.match(r"\s*(type\(c_ptr\)|type\(wb_\w+\)|real\(c_double\)|integer\(c_int\))\s*(,[^:]*)?::\s*(.*)", line, flags=re.I)
+            if not d:
+                continue
+            base, attrs, names = d.group(1).lower(), (d.group(2) or "").lower(), d.group(3)
+            for nm in re.split(r",(?![^(]*\))", names):
+                nm = re.sub(r"\(.*\)", "", nm).strip().lower()
+                byval = "value" in attrs
+                if base == "type(c_ptr)":
+                    k = "handle" if byval else "handle_out"
+                elif base.startswith("type(wb_"):
+                    k = "struct_in"
+                elif base == "real(c_double)":
+                    k = "val_double" if byval else "ptr_double"
+                else:
+                    k = "val_int" if byval else "ptr_int"
+                kind[nm] = k
+        assert m.group(1).lower() == m.group(3).lower()
+        out[m.group(3)] = [kind.get(d, "?" + d) for d in dummies]
+    return out
+
+
+@pytest.mark.parametrize("shim", [s[0] for s in SHIMS])
+def test_fortran_interface_blocks_match_the_c_prototypes(shim):
+    """Every bind(C) interface of a shim against the prototype of include/wbeuler.h: same number of arguments, and for each
+    one the same passing convention -- `value` for C scalars, by reference (no `value`) for C pointers, type(c_ptr),value
+    for the opaque handle and type(c_ptr),intent(out) for the handle** of *_create.  A mismatch here is exactly what a
+    Fortran compiler would NOT catch (the interface is trusted) and what would corrupt the call at run time."""
+    protos = _c_prototypes()
+    ifs = _fortran_interfaces(os.path.join(ROOT, "fvm-source-wb_b200", "fortran", shim))
+    assert len(ifs) >= 4
+    for name, kinds in ifs.items():
+        if name == "wb_last_error":
+            assert kinds == []
+            continue
+        assert name in protos, name
+        assert kinds == protos[name], (name, kinds, protos[name])
 
 
 def test_python_binding_rejects_wrong_shapes():

@@ -320,6 +320,17 @@ def test_limiter_branches_that_are_not_built_and_why():
     ("2d/benchmark_2d_dg.f90", ["23-89", "497-592", "624-775", "826-870", "1137-1479", "1516-1555"],
      {"compute_error", "get_modes_from_nodes", "get_nodes_from_modes", "evolve", "compute_max_speed", "compute_update", "apply_limiter"},
      {"main", "get_coords", "get_initial_conditions", "get_equilibrium_solution", "output_file", "compute_num_flux"}),
+    # 1D programs: fvm.f90 and dg_with_source.f90 keep their time loop in the main program -> replaced by one call
+    ("fvm.f90", ["188-251", "320-336", "56-76=  call wb_fvm1d_time_loop(u,t,dt,iter)"], {"compute_update", "compute_max_speed"},
+     {"fvm", "condinit", "compute_primitive", "compute_llflux", "compute_flux", "compute_speed"}),
+    ("benchmark_1d.f90", ["157-170", "200-261", "263-377", "454-549", "553-747"],
+     {"compute_max_speed", "evolve", "compute_update", "compute_update_fvm", "compute_update_sr"},
+     {"main", "get_x", "get_initial_conditions", "get_equilibrium_solution", "output_file", "compute_llflux"}),
+    ("dg_with_source.f90", ["414-519", "523-606", "610-734", "807-1028", "1136-1152", "1380-1744", "1749-2031",
+                            "173-336=  call wb_dg1d_time_loop(u,delta_u,u_eq,u_eq_modes,uinit,t,dt,iter)"],
+     {"limiter", "limiter_tdv", "limiter_cons", "compute_update", "compute_max_speed", "compute_update_exact",
+      "compute_update_exact_delta"},
+     {"dg", "condinit", "get_eq_solution", "modes_to_nodes", "nodes_to_modes", "riemann_hllc"}),
 ])
 def test_splitter_ranges_of_the_integration_recipes_cut_whole_routines(tmp_path, src, ranges, gone, kept):
     """INTEGRATION.md / the Fortran shims tell a maintainer which line ranges tools/split_reference.py must drop.  The image
@@ -336,3 +347,10 @@ def test_splitter_ranges_of_the_integration_recipes_cut_whole_routines(tmp_path,
     names = set(it.units)
     assert not (gone & names), gone & names
     assert kept <= names, kept - names
+    text = out.read_text()
+    for r in ranges:                 # a replaced time loop: the call into the shim stands where the loop was
+        if "=" in r:
+            call = r.split("=", 1)[1].strip()
+            assert call in text
+            first = int(r.split("-")[0])
+            assert "do while" in open(os.path.join(REF, src)).read().splitlines()[first - 1]
