@@ -145,30 +145,139 @@ __device__ __forceinline__ void node_xy(const DgGrid& g, const DgPhys& P, const 
   x = (double)((float)(ic + 1) - 0.5f) * P.dx + P.dx / 2.0 * B.xq[ni];
   y = (double)((float)(g.j0 + jc + 1) - 0.5f) * dy + dy / 2.0 * B.xq[nj];
 }
+// Keplerian velocity profile of the rotating disks (cases 7 and 11, :290-306, :405-420); the reference's second branch can
+// never fire (its condition is contained in the first one)
+__device__ __forceinline__ void disk_velocity(double x_dash, double y_dash, double r, double delta_r, double& w2, double& w3) {
+  const double r32 = pow(r, 1.5);
+  if (r <= (double)0.5f - delta_r) { w2 = 0.; w3 = 0.; }
+  else if ((r > (double)0.5f - delta_r) && (r <= 2 + delta_r)) { w2 = -(y_dash / r32); w3 = x_dash / r32; }
+  else if ((r > 2 + delta_r) && (r <= 2 + 2 * delta_r)) {
+    w2 = y_dash / r32 / delta_r * (r - (2 + delta_r)) - y_dash / r32;
+    w3 = -(x_dash / r32 / delta_r * (r - (2 + delta_r))) + x_dash / r32;
+  } else { w2 = 0.; w3 = 0.; }
+}
+// primitive initial state at one node, get_initial_conditions :122-466, all twelve cases; returns true when w[3] is the
+// global minimum of w[0] (cases 1, 10, 11: filled in by the caller's second pass)
+__device__ __forceinline__ bool dg_ic_prim(int ninit, double x, double y, const DgPhys& P, double boxlen_x, double boxlen_y, double eta,
+                                           double w[4]) {
+  const double dpi = 3.141592653589793;       // acos(-1d0)
+  w[0] = 0.; w[1] = 0.; w[2] = 0.; w[3] = 0.;
+  switch (ninit) {
+    case 1: {
+      const double ax = x - boxlen_x / 2., ay = y - boxlen_y / 2.;
+      w[0] = exp(-((ax * ax + ay * ay) * 10));
+      w[1] = 1.0; w[2] = 1.0;
+      return true;
+    }
+    case 2: {
+      const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
+      const double ee = exp(-(rho_0 * gg / p_0) * (x + y));
+      const double bx = x - (double)0.3f, by = y - (double)0.3f;
+      w[0] = rho_0 * ee;
+      w[3] = p_0 * ee + eta * exp(-(100 * (rho_0 * gg / p_0) * (bx * bx + by * by)));
+      return false;
+    }
+    case 3:
+      if (x >= 0.5 && y >= 0.5) { w[0] = 1.; w[3] = 1.; }
+      else if (x < 0.5 && y >= 0.5) { w[0] = (double)0.5197f; w[1] = (double)-0.7259f; w[3] = (double)0.4f; }
+      else if (x < 0.5 && y < 0.5) { w[0] = (double)0.1072f; w[1] = (double)-0.7259f; w[2] = (double)-1.4045f; w[3] = (double)0.0439f; }
+      else { w[0] = (double)0.2579f; w[2] = (double)-1.4045f; w[3] = (double)0.15f; }
+      return false;
+    case 4:
+      if (x >= 0.5 && y >= 0.5) { w[0] = 1.5; w[3] = 1.5; }
+      else if (x < 0.5 && y >= 0.5) { w[0] = (double)0.5323f; w[1] = (double)1.206f; w[3] = (double)0.3f; }
+      else if (x < 0.5 && y < 0.5) { w[0] = (double)0.138f; w[1] = (double)1.206f; w[2] = (double)1.206f; w[3] = (double)0.029f; }
+      else { w[0] = (double)0.5323f; w[2] = (double)1.206f; w[3] = (double)0.3f; }
+      return false;
+    case 5:
+      if (x + y >= 0.5) { w[0] = 1.; w[3] = 1.; }
+      else { w[0] = 0.125; w[3] = (double)0.4f; }
+      return false;
+    case 6: {      // isentropic vortex
+      const double r2 = (x - 5) * (x - 5) + (y - 5) * (y - 5);
+      w[0] = 1. * pow(1. - (P.gamma - 1.) * 5 / (8 * P.gamma * (dpi * dpi)) * exp(1 - r2), 1 / (P.gamma - 1));
+      w[1] = 2 + 5. / (2 * dpi) * exp(-1 - r2 / 2.) * (-y + 5.);
+      w[2] = 2 + 5. / (2 * dpi) * exp(-1 - r2 / 2.) * (x - 5.);
+      w[3] = pow(w[0], P.gamma);
+      return false;
+    }
+    case 7: {      // smooth rotating disk (boxlen 6 x 6)
+      const double p_0 = (double)10e-5f, rho_0 = (double)10e-5f, rho_d = 1., delta_r = (double)0.1f;
+      const double x_dash = x - 3., y_dash = y - 3.;
+      const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+      w[3] = p_0;
+      if (r < (double)0.5f - delta_r / 2.) w[0] = rho_0;
+      else if ((r < (double)0.5f + delta_r / 2.) && (r > (double)0.5f - delta_r / 2.))
+        w[0] = (rho_d - rho_0) / delta_r * (r - ((double)0.5f - delta_r / 2.)) + rho_0;
+      else if ((r >= (double)0.5f + delta_r / 2.) && (r <= 2 - delta_r / 2.)) w[0] = rho_d;
+      else if ((r > 2 - delta_r / 2.) && (r < 2 + delta_r / 2.)) w[0] = (rho_0 - rho_d) / delta_r * (r - (2 - delta_r / 2.)) + rho_d;
+      else if (r >= 2 + delta_r / 2.) w[0] = rho_0;
+      disk_velocity(x_dash, y_dash, r, delta_r, w[1], w[2]);
+      return false;
+    }
+    case 8: {      // square advection
+      const double x_dash = x - 0.5, y_dash = y - 0.5;
+      w[0] = ((fabs(x_dash) <= 0.25) && (fabs(y_dash) <= 0.25)) ? 4.0 : 1.0;
+      w[2] = 10.0; w[3] = 1.0;
+      return false;
+    }
+    case 9: {      // 1-d discontinuous pulse advection
+      w[0] = (fabs(y - 0.5) <= 0.25) ? 4. : 1.;
+      w[2] = 1.0; w[3] = 1.;
+      return false;
+    }
+    case 10: {     // Gaussian density, w(4) = minval(w(1))
+      const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
+      const double ax = x - boxlen_x / 2., ay = y - boxlen_y / 2.;
+      w[0] = rho_0 * exp(-(rho_0 * gg / p_0) * (ax * ax + ay * ay) * 20);
+      w[1] = 1.0; w[2] = 1.0;
+      return true;
+    }
+    case 11: {     // 100 % smooth rotating disk, w(4) = minval(w(1))
+      const double delta_r = (double)0.1f;
+      const double x_dash = x - 3., y_dash = y - 3.;
+      const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+      const double e = exp(-2 * ((r - 2.) * (r - 2.)));
+      w[0] = e * e;
+      disk_velocity(x_dash, y_dash, r, delta_r, w[1], w[2]);
+      return true;
+    }
+    default: {     // case 12: Keplerian disk, softened potential
+      const double rho_d = 1.0, GM = 1., H = (double)0.05f, epsilon = 0.25;
+      const double x_dash = x - 0.5 * boxlen_x, y_dash = y - 0.5 * boxlen_y;
+      const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+      const double q = sqrt(r * r + epsilon * epsilon);
+      const double cs_m = H * sqrt(GM / q);
+      w[0] = rho_d;
+      w[3] = cs_m * cs_m * rho_d;
+      w[1] = -(y_dash * sqrt(GM / q - H * H * GM / q));
+      w[2] = x_dash * sqrt(GM / q - H * H * GM / q);
+      return false;
+    }
+  }
+}
+// pass 0 (cases whose pressure is the global minimum of the nodal density, w(4) = minval(w(1)) :141, :377, :428): that minimum
+// (atomicMin on the bit pattern of a positive double); pass 1 writes the conservative nodal state
 __global__ void k_dg_init(double* __restrict__ nodes, double* __restrict__ xy, DgGrid g, DgPhys P, Basis B, int ninit, double eta,
-                          double boxlen_x, double boxlen_y, unsigned long long* minbits, int pass) {
+                          double boxlen_x, double boxlen_y, unsigned long long* minbits, int pass, double shift_x = 0.0,
+                          double shift_y = 0.0) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int mode = blockIdx.y;
   if (e >= g.ne) return;
   const double dy = boxlen_y / (double)g.nyg;
   double x, y;
   node_xy(g, P, B, e, mode, dy, x, y);
-  double w[4];
-  if (ninit == 1) {
-    const double ax = x - boxlen_x / 2., ay = y - boxlen_y / 2.;
-    w[0] = exp(-((ax * ax + ay * ay) * 10));
-    if (pass == 0) {      // minimum over the owned rows only (ghost rows lie outside the box or belong to a neighbour)
-      if (e >= g.e_off && e < g.e_off + g.ne_own) atomicMin(minbits, (unsigned long long)__double_as_longlong(w[0]));
-      return;
-    }
-    w[1] = 1.0; w[2] = 1.0; w[3] = __longlong_as_double((long long)*minbits);
-  } else {
-    const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
-    const double ee = exp(-(rho_0 * gg / p_0) * (x + y));
-    const double bx = x - (double)0.3f, by = y - (double)0.3f;
-    w[0] = rho_0 * ee; w[1] = 0; w[2] = 0;
-    w[3] = p_0 * ee + eta * exp(-(100 * (rho_0 * gg / p_0) * (bx * bx + by * by)));
+  if (shift_x != 0.0 || shift_y != 0.0) {      // the initial state translated by (shift_x, shift_y) in the periodic box
+    x = x - shift_x; y = y - shift_y;
+    x = x - boxlen_x * floor(x / boxlen_x); y = y - boxlen_y * floor(y / boxlen_y);
   }
+  double w[4];
+  const bool needs_min = dg_ic_prim(ninit, x, y, P, boxlen_x, boxlen_y, eta, w);
+  if (pass == 0) {      // minimum over the owned rows only (ghost rows lie outside the box or belong to a neighbour)
+    if (needs_min && e >= g.e_off && e < g.e_off + g.ne_own) atomicMin(minbits, (unsigned long long)__double_as_longlong(w[0]));
+    return;
+  }
+  if (needs_min) w[3] = __longlong_as_double((long long)*minbits);
   double u[4];
   cons(P, w, u);
 #pragma unroll
@@ -1389,6 +1498,26 @@ int wb_dg2d_get_modes_from_nodes(wb_dg2d* h, const double* nodes, double* modes)
   return dg_d2h_field(h, h->Bf, modes);
 }
 
+static int dg_fill_initial_nodes(wb_dg2d* h, int ninit, double eta, bool want_xy, double shift_x, double shift_y);
+
+// compute_error :23-89 of the nodal fields in buffers a and b
+static int dg_error_of(wb_dg2d* h, const double* a, const double* b, double* lmax4, double* l1_4, double* l2_4) {
+  const int nb = (int)std::min<size_t>((h->g.ne_own + 127) / 128, 148 * 4);
+  double* part = nullptr;
+  WB_CUDA(cudaMalloc(&part, sizeof(double) * 12 * (nb + 1)));
+  const double scale = (1.0 / (double)h->prm.nx) * (1.0 / (double)h->prm.ny);      // dx*dy with dx = 1./dble(nx) (:35-36)
+  DISPATCH_M(h, k_dg_error<MM><<<nb, 128, 0, h->stream>>>(a, b, h->g, h->B, scale, part));
+  k_dg_error_final<<<1, 32, 0, h->stream>>>(part, nb, part + (size_t)12 * nb);
+  wb::g_launches.fetch_add(2);
+  double r[12];
+  cudaError_t e1 = cudaMemcpyAsync(r, part + (size_t)12 * nb, sizeof(r), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cudaFree(part);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("compute_error: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return WB_ERR_CUDA; }
+  for (int k = 0; k < 4; ++k) { lmax4[k] = r[k]; l1_4[k] = r[4 + k]; l2_4[k] = r[8 + k]; }
+  return WB_OK;
+}
+
 int wb_dg2d_compute_error(wb_dg2d* h, const double* u_nodes, const double* u_init_nodes, double* lmax4, double* l1_4, double* l2_4) {
   if (!h || !u_nodes || !u_init_nodes || !lmax4 || !l1_4 || !l2_4) { set_error("null argument"); return WB_ERR_ARG; }
   if (h->nranks > 1) { set_error("wb_dg2d_compute_error: single-GPU handles only"); return WB_ERR_STATE; }
@@ -1396,19 +1525,21 @@ int wb_dg2d_compute_error(wb_dg2d* h, const double* u_nodes, const double* u_ini
   h->resident = false;
   WB_CHECK(dg_h2d_field(h, u_nodes, h->A));
   WB_CHECK(dg_h2d_field(h, u_init_nodes, h->Bf));
-  const int nb = (int)std::min<size_t>((h->g.ne_own + 127) / 128, 148 * 4);
-  double* part = nullptr;
-  WB_CUDA(cudaMalloc(&part, sizeof(double) * 12 * (nb + 1)));
-  const double scale = (1.0 / (double)h->prm.nx) * (1.0 / (double)h->prm.ny);      // dx*dy with dx = 1./dble(nx) (:35-36)
-  DISPATCH_M(h, k_dg_error<MM><<<nb, 128, 0, h->stream>>>(h->A, h->Bf, h->g, h->B, scale, part));
-  k_dg_error_final<<<1, 32, 0, h->stream>>>(part, nb, part + (size_t)12 * nb);
-  double r[12];
-  cudaError_t e1 = cudaMemcpyAsync(r, part + (size_t)12 * nb, sizeof(r), cudaMemcpyDeviceToHost, h->stream);
-  cudaError_t e2 = cudaStreamSynchronize(h->stream);
-  cudaFree(part);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("wb_dg2d_compute_error: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return WB_ERR_CUDA; }
-  for (int k = 0; k < 4; ++k) { lmax4[k] = r[k]; l1_4[k] = r[4 + k]; l2_4[k] = r[8 + k]; }
-  return WB_OK;
+  return dg_error_of(h, h->A, h->Bf, lmax4, l1_4, l2_4);
+}
+
+int wb_dg2d_compute_error_resident(wb_dg2d* h, int ninit, double eta, double shift_x, double shift_y, double* lmax4, double* l1_4,
+                                   double* l2_4) {
+  if (!h || !lmax4 || !l1_4 || !l2_4) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  if (h->nranks > 1) { set_error("wb_dg2d_compute_error_resident: single-GPU handles only"); return WB_ERR_STATE; }
+  WB_REQUIRE(ninit >= 1 && ninit <= 12, "ninit must be 1..12 (got %d)", ninit);
+  WB_CUDA(cudaSetDevice(h->dev));
+  WB_CHECK(dg_fill_initial_nodes(h, ninit, eta, false, shift_x, shift_y));                        // u_anal -> A
+  dim3 b(128), gr = elem_grid(h, 128);
+  DISPATCH_M(h, k_nodes_from_modes<MM><<<gr, b, 0, h->stream>>>(h->du, h->Bf, h->g, h->B));      // nodes of the state -> Bf
+  WB_LAUNCH_CHECK();
+  return dg_error_of(h, h->Bf, h->A, lmax4, l1_4, l2_4);
 }
 
 int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes) {
@@ -1483,26 +1614,33 @@ int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const dou
   return WB_OK;
 }
 
-int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
-  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
-  WB_REQUIRE(ninit == 1 || ninit == 2, "device-side initial conditions exist for ninit 1 (pulse) and 2 (hydrostatic + bump)");
-  WB_CUDA(cudaSetDevice(h->dev));
-  const size_t n = (size_t)h->g.nm * h->g.ne;
-  const bool need_xy = (h->phys.source == 2) || (h->phys.ninit == 12);
+// nodal initial state of get_initial_conditions (ninit 1..12) into buffer A (and the node coordinates into h->xy)
+static int dg_fill_initial_nodes(wb_dg2d* h, int ninit, double eta, bool want_xy, double shift_x, double shift_y) {
   unsigned long long* minbits = reinterpret_cast<unsigned long long*>(h->part2);
   WB_CUDA(cudaMemsetAsync(minbits, 0x7f, sizeof(unsigned long long), h->stream));
   dim3 b(128), gr((unsigned)((h->g.ne + 127) / 128), h->g.nm);
-  if (ninit == 1) {
-    k_dg_init<<<gr, b, 0, h->stream>>>(h->A, nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x, h->prm.boxlen_y, minbits, 0);
+  if (ninit == 1 || ninit == 10 || ninit == 11) {      // w(4) = minval(w(1)) over the whole box
+    k_dg_init<<<gr, b, 0, h->stream>>>(h->A, nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x, h->prm.boxlen_y, minbits, 0,
+                                       shift_x, shift_y);
     WB_LAUNCH_CHECK();
-    if (h->nranks > 1) {       // minval over the whole box (positive doubles: the bit patterns order like the values)
+    if (h->nranks > 1) {       // positive doubles: the bit patterns order like the values
       if (!h->comm) { set_error("nranks > 1 but wb_dg2d_comm_init was not called"); return WB_ERR_STATE; }
       WB_CHECK(nccl_allreduce_min_f64(h->comm, h->part2, 1, h->stream));
     }
   }
-  k_dg_init<<<gr, b, 0, h->stream>>>(h->A, need_xy ? h->xy : nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x,
-                                     h->prm.boxlen_y, minbits, 1);
+  k_dg_init<<<gr, b, 0, h->stream>>>(h->A, want_xy ? h->xy : nullptr, h->g, h->phys, h->B, ninit, eta, h->prm.boxlen_x,
+                                     h->prm.boxlen_y, minbits, 1, shift_x, shift_y);
   WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
+int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  WB_REQUIRE(ninit >= 1 && ninit <= 12, "ninit must be 1..12 (got %d)", ninit);
+  WB_CUDA(cudaSetDevice(h->dev));
+  const size_t n = (size_t)h->g.nm * h->g.ne;
+  const bool need_xy = (h->phys.source == 2) || (h->phys.ninit == 12);
+  WB_CHECK(dg_fill_initial_nodes(h, ninit, eta, need_xy, 0.0, 0.0));
   if (need_xy) {
     dim3 b2(256), g2((unsigned)((n + 255) / 256));
     if (h->phys.source == 2) { k_grad_phi<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case); WB_LAUNCH_CHECK(); }
@@ -1518,6 +1656,15 @@ int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
   WB_CHECK(dg_exchange(h, h->du));
   h->resident = true;
   return WB_OK;
+}
+
+int wb_dg2d_get_initial_conditions(wb_dg2d* h, int ninit, double eta, double* u_nodes_out) {
+  if (!h || !u_nodes_out) { set_error("null argument"); return WB_ERR_ARG; }
+  WB_REQUIRE(ninit >= 1 && ninit <= 12, "ninit must be 1..12 (got %d)", ninit);
+  WB_CUDA(cudaSetDevice(h->dev));
+  h->resident = false;                 // buffer A is scratch of the resident path too
+  WB_CHECK(dg_fill_initial_nodes(h, ninit, eta, false, 0.0, 0.0));
+  return dg_d2h_field(h, h->A, u_nodes_out);
 }
 
 int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend) {

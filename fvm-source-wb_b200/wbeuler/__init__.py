@@ -303,6 +303,20 @@ class DG2D:
     def init_device(self, ninit, eta=F32(0.1)):
         _check(lib().wb_dg2d_init_device(self._h, C.c_int(ninit), C.c_double(eta)))
 
+    def compute_error_resident(self, ninit, shift_x=0.0, shift_y=0.0, eta=F32(0.1)):
+        """compute_error of the resident state against initial condition `ninit` translated by (shift_x, shift_y), on the device
+        -> (lmax[4], l1[4], l2[4] before the sqrt)"""
+        a = np.zeros(4); b = np.zeros(4); c = np.zeros(4)
+        _check(lib().wb_dg2d_compute_error_resident(self._h, C.c_int(ninit), C.c_double(eta), C.c_double(shift_x), C.c_double(shift_y),
+                                                    _ptr(a), _ptr(b), _ptr(c)))
+        return a, b, c
+
+    def get_initial_conditions(self, ninit, eta=F32(0.1)):
+        """get_initial_conditions(x,y,u,...)  2d/benchmark_2d_dg.f90:122-466, ninit 1..12 -> nodal conserved state (owned rows)"""
+        out = np.empty(self.shape)
+        _check(lib().wb_dg2d_get_initial_conditions(self._h, C.c_int(ninit), C.c_double(eta), _ptr(out)))
+        return out
+
     def step_async(self, nsteps, tend=1e300):
         _check(lib().wb_dg2d_step_async(self._h, C.c_int(nsteps), C.c_double(tend)))
 

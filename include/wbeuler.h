@@ -163,6 +163,11 @@ int wb_dg2d_get_nodes_from_modes(wb_dg2d* h, const double* modes, double* nodes)
  * returned: lmax[4], l1[4] and l2[4] = the accumulators BEFORE the sqrt.  Sums over elements are a fixed-shape tree on the
  * device (deterministic; equal to the reference's sequential sums to a few ulp). */
 int wb_dg2d_compute_error(wb_dg2d* h, const double* u_nodes, const double* u_init_nodes, double* lmax4, double* l1_4, double* l2_4);
+/* the same norms between the RESIDENT state (reconstructed at the nodes) and the initial condition `ninit` translated by
+ * (shift_x, shift_y) in the periodic box, both evaluated on the device: u_anal of an advected profile at time t is the
+ * initial state shifted by v*t -- convergence studies at grids whose nodal arrays the host does not hold */
+int wb_dg2d_compute_error_resident(wb_dg2d* h, int ninit, double eta, double shift_x, double shift_y, double* lmax4, double* l1_4,
+                                   double* l2_4);
 /* replaces compute_update(delta_u,x,y,u_eq,dudt)   2d/benchmark_2d_dg.f90:1137-1479 (u_eq is never read there) */
 int wb_dg2d_compute_update(wb_dg2d* h, const double* modes, const double* x, const double* y, double* dudt);
 /* replaces apply_limiter(u)   2d/benchmark_2d_dg.f90:1516-1555 -> 2d/limiters.f90 */
@@ -176,9 +181,12 @@ int wb_dg2d_evolve(wb_dg2d* h, double* u_nodes_inout, const double* x, const dou
                    int* iters_out, double* t_out, double* last_dt_out);
 /* resident path: upload nodal values (projected to modes and limited on the device, :644,:659), step, download nodes */
 int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const double* y);
-/* get_coords + get_initial_conditions (2d/benchmark_2d_dg.f90:93-120, :139-153; ninit 1 = pulse, 2 = hydrostatic + bump) on the
+/* get_coords + get_initial_conditions (2d/benchmark_2d_dg.f90:93-120, :122-466; every ninit 1..12 of the reference: pulse,
+ * hydrostatic + bump, the Riemann problems, isentropic vortex, rotating disks, advection tests, Keplerian disk) on the
  * device, then projection + initial limiter as in evolve -- for grids whose nodal arrays the host cannot hold */
 int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta);
+/* the same nodal initial state returned to the host (owned rows), without touching the clock: u(nvar,nx,ny,mx,my) */
+int wb_dg2d_get_initial_conditions(wb_dg2d* h, int ninit, double eta, double* u_nodes_out);
 int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend);
 int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out);
 int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out);

@@ -199,10 +199,29 @@ void orc_dg2d_compute_conservative(const orc_dg2d_params *p, const double *w, do
   for (long k = 0; k < n; ++k) cons1(p, w + NV * k, u + NV * k);
 }
 
-/* :122-466 get_initial_conditions, cases 1-5 (nodal conservative values) */
+/* Keplerian velocity profile shared by cases 7 and 11 (2d/benchmark_2d_dg.f90:290-306, :405-420); the second branch of
+ * the reference can never fire (its condition is contained in the first) and is kept for the record */
+static void disk_velocity(double x_dash, double y_dash, double r, double delta_r, double *w2, double *w3) {
+  if (r <= (double)0.5f - delta_r) { *w2 = 0.; *w3 = 0.; }
+  else if ((r <= (double)0.5f - delta_r) && (r > (double)0.5f - 2 * delta_r)) {
+    *w2 = -(y_dash / pow(r, (double)(3.f / 2.f)) / (delta_r) * (r - ((double)0.5f - 2 * delta_r)));
+    *w3 = x_dash / pow(r, (double)(3.f / 2.f)) / (delta_r) * (r - ((double)0.5f - 2 * delta_r));
+  } else if ((r > (double)0.5f - delta_r) && (r <= 2 + delta_r)) {
+    *w2 = -(y_dash / pow(r, (double)(3.f / 2.f)));
+    *w3 = x_dash / pow(r, (double)(3.f / 2.f));
+  } else if ((r > 2 + delta_r) && (r <= 2 + 2 * delta_r)) {
+    *w2 = y_dash / pow(r, (double)(3.f / 2.f)) / delta_r * (r - (2 + delta_r)) - y_dash / pow(r, (double)(3.f / 2.f));
+    *w3 = -(x_dash / pow(r, (double)(3.f / 2.f)) / delta_r * (r - (2 + delta_r))) + x_dash / pow(r, (double)(3.f / 2.f));
+  } else if (r > 2 + 2 * delta_r) { *w2 = 0.; *w3 = 0.; }
+}
+
+/* :122-466 get_initial_conditions, all twelve cases (nodal conservative values).  Literals keep their kinds: an
+ * un-suffixed real literal is real(4) and is promoted when it meets a real(8) operand.  Where the reference
+ * leaves a node unassigned (case 7 at r == 0.5 - delta_r/2 exactly) the value stays 0. */
 void orc_dg2d_get_initial_conditions(const orc_dg2d_params *p, const double *x, const double *y, double *u) {
   size_t n = nelem5(p);
-  double *w = (double *)malloc(sizeof(double) * NV * n);
+  double *w = (double *)calloc(NV * n, sizeof(double));
+  const double dpi = acos(-1.0);
   for (size_t k = 0; k < n; ++k) {
     double xx = x[k], yy = y[k];
     double *ww = w + NV * k;
@@ -231,13 +250,67 @@ void orc_dg2d_get_initial_conditions(const orc_dg2d_params *p, const double *x, 
         else if (xx < 0.5 && yy < 0.5) { ww[0] = (double)0.138f; ww[1] = (double)1.206f; ww[2] = (double)1.206f; ww[3] = (double)0.029f; }
         else { ww[0] = (double)0.5323f; ww[1] = 0.0; ww[2] = (double)1.206f; ww[3] = (double)0.3f; }
         break;
-      default: /* case 5 */
+      case 5:
         if (xx + yy >= 0.5) { ww[0] = 1.; ww[1] = 0.; ww[2] = 0.; ww[3] = 1.; }
         else { ww[0] = 0.125; ww[1] = 0.; ww[2] = 0.; ww[3] = (double)0.4f; }
         break;
+      case 6: {   /* isentropic vortex :230-252 */
+        const double r2 = (xx - 5) * (xx - 5) + (yy - 5) * (yy - 5);
+        ww[0] = 1. * pow(1. - (p->gamma - 1.) * 5 / (8 * p->gamma * (dpi * dpi)) * exp(1 - r2), 1 / (p->gamma - 1));
+        ww[1] = 2 + 5. / (2 * dpi) * exp(-1 - r2 / 2.) * (-yy + 5.);
+        ww[2] = 2 + 5. / (2 * dpi) * exp(-1 - r2 / 2.) * (xx - 5.);
+        ww[3] = pow(ww[0], p->gamma);
+      } break;
+      case 7: {   /* smooth rotating disk :253-312 */
+        const double p_0 = (double)10e-5f, rho_0 = (double)10e-5f, rho_d = 1., delta_r = (double)0.1f;
+        const double x_dash = xx - 3., y_dash = yy - 3.;
+        const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+        ww[3] = p_0;
+        if (r < (double)0.5f - delta_r / 2.) ww[0] = rho_0;
+        else if ((r < (double)0.5f + delta_r / 2.) && (r > (double)0.5f - delta_r / 2.))
+          ww[0] = (rho_d - rho_0) / delta_r * (r - ((double)0.5f - delta_r / 2.)) + rho_0;
+        else if ((r >= (double)0.5f + delta_r / 2.) && (r <= 2 - delta_r / 2.)) ww[0] = rho_d;
+        else if ((r > 2 - delta_r / 2.) && (r < 2 + delta_r / 2.)) ww[0] = (rho_0 - rho_d) / delta_r * (r - (2 - delta_r / 2.)) + rho_d;
+        else if (r >= 2 + delta_r / 2.) ww[0] = rho_0;
+        disk_velocity(x_dash, y_dash, r, delta_r, &ww[1], &ww[2]);
+      } break;
+      case 8: {   /* square advection :314-342 */
+        const double x_dash = xx - 0.5, y_dash = yy - 0.5;
+        ww[0] = ((fabs(x_dash) <= 0.25) && (fabs(y_dash) <= 0.25)) ? 4.0 : 1.0;
+        ww[1] = 0.0; ww[2] = 10.0; ww[3] = 1.0;
+      } break;
+      case 9: {   /* 1d discontinuous pulse advection :344-370 */
+        const double y_dash = yy - 0.5;
+        ww[0] = (fabs(y_dash) <= 0.25) ? 4. : 1.;
+        ww[1] = 0.0; ww[2] = 1.0; ww[3] = 1.;
+      } break;
+      case 10: {  /* Gaussian density, w(4) = minval(w(1)) :371-378 */
+        const double rho_0 = (double)1.21f, p_0 = 1., g = 1.;
+        const double ax = xx - p->boxlen_x / 2., ay = yy - p->boxlen_y / 2.;
+        ww[0] = rho_0 * exp(-(rho_0 * g / p_0) * (ax * ax + ay * ay) * 20);
+        ww[1] = 1.0; ww[2] = 1.0;
+      } break;
+      case 11: {  /* 100% smooth rotating disk :379-429 */
+        const double delta_r = (double)0.1f;
+        const double x_dash = xx - 3., y_dash = yy - 3.;
+        const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+        const double e = exp(-2 * ((r - 2.) * (r - 2.)));
+        ww[0] = e * e;
+        disk_velocity(x_dash, y_dash, r, delta_r, &ww[1], &ww[2]);
+      } break;
+      default: {  /* case 12: Keplerian disk with softened potential :430-459 */
+        const double rho_d = 1.0, GM = 1., H = (double)0.05f, epsilon = 0.25;
+        const double x_dash = xx - 0.5 * p->boxlen_x, y_dash = yy - 0.5 * p->boxlen_y;
+        const double r = sqrt(x_dash * x_dash + y_dash * y_dash);
+        const double cs_m = H * sqrt(GM / sqrt(r * r + epsilon * epsilon));
+        ww[0] = rho_d;
+        ww[3] = cs_m * cs_m * rho_d;
+        ww[1] = -(y_dash * sqrt(GM / sqrt(r * r + epsilon * epsilon) - H * H * GM / sqrt(r * r + epsilon * epsilon)));
+        ww[2] = x_dash * sqrt(GM / sqrt(r * r + epsilon * epsilon) - H * H * GM / sqrt(r * r + epsilon * epsilon));
+      } break;
     }
   }
-  if (p->ninit == 1) {
+  if (p->ninit == 1 || p->ninit == 10 || p->ninit == 11) {
     double mn = w[0];
     for (size_t k = 0; k < n; ++k) mn = fmin(mn, w[NV * k]);
     for (size_t k = 0; k < n; ++k) w[NV * k + 3] = mn;

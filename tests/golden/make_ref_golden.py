@@ -489,6 +489,34 @@ def dg1d(only=None):
         np.savez_compressed(path, **out)
 
 
+# ------------------------------------------------------------------------------------------------ 2D DG initial conditions
+DG2D_IC_CASES = [  # ninit, n (nx=ny), m (mx=my), boxlen
+    (3, 4, 2, 1.0), (4, 4, 3, 1.0), (5, 5, 2, 1.0), (6, 4, 3, 10.0), (7, 8, 2, 6.0), (8, 6, 2, 1.0), (9, 6, 3, 1.0),
+    (10, 4, 3, 1.0), (11, 8, 2, 6.0), (12, 6, 2, 6.0),
+]
+
+
+def dg2d_ics(only=None):
+    """get_coords + get_initial_conditions (2d/benchmark_2d_dg.f90:93-120, :122-466) for ninit 3..12 -> ref_dg2d_ics.npz"""
+    out = {}
+    for ninit, n, m, box in DG2D_IC_CASES:
+        t0 = time.time()
+        kv = dict(nx=n, ny=n, mx=m, my=m, ninit=ninit)
+        if box != 1.0:
+            kv.update(boxlen_x=box, boxlen_y=box)
+        it = dg2d_interp(**kv)
+        x, y = F(n, n, m, m), F(n, n, m, m)
+        it.call("get_coords", x, y, n, n, m, m)
+        nodes = F(4, n, n, m, m)
+        it.call("get_initial_conditions", x, y, nodes, n, n, m, m)
+        tag = f"ninit{ninit}"
+        out[f"{tag}/meta"] = np.array([ninit, n, m])
+        out[f"{tag}/boxlen"] = np.array(box)
+        out[f"{tag}/x"] = C(x); out[f"{tag}/y"] = C(y); out[f"{tag}/nodes"] = C(nodes)
+        print(f"dg2d_ics {tag}: {time.time() - t0:.1f} s, |u|max {np.abs(nodes).max():.4g}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_dg2d_ics.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fv2d", "dg2d", "fv1d", "dg1d"]
     np.seterr(all="ignore")

@@ -428,3 +428,68 @@ def test_large_grid_properties(wb, monkeypatch):
     assert field_err(mirror, fast) <= 1e-12
     mean0, mean1 = m0[0, 0, :, :, 0].sum(), fast[0, 0, :, :, 0].sum()
     assert abs(mean1 / mean0 - 1) < 1e-7
+
+
+IC_BOX = {6: 10.0, 7: 6.0, 11: 6.0, 12: 6.0}
+
+
+@pytest.mark.parametrize("ninit", list(range(1, 13)))
+def test_device_initial_conditions_all_twelve(wb, oracle, ninit):
+    """get_initial_conditions (2d/benchmark_2d_dg.f90:122-466) evaluated ON THE DEVICE for every ninit of the reference
+    (Riemann problems, isentropic vortex, rotating disks, advection tests, Keplerian disk; 1, 10 and 11 need the global
+    minimum of the nodal density): equal to the oracle up to the last bits of exp / pow (CUDA vs glibc), and to the vectors
+    produced by executing the reference text (tests/golden/ref_dg2d_ics.npz)."""
+    box = IC_BOX.get(ninit, 1.0)
+    n, m = 24, 3
+    p = oracle.dg2d_params(nx=n, ny=n, mx=m, my=m, ninit=ninit, boxlen_x=box, boxlen_y=box)
+    x, y = oracle.dg2d_get_coords(p)
+    ref = oracle.dg2d_get_initial_conditions(p, x, y)
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, ninit=ninit, boxlen_x=box, boxlen_y=box) as s:
+        got = s.get_initial_conditions(ninit)
+    assert np.all(np.isfinite(got))
+    assert np.abs(got - ref).max() <= 2e-15 * np.abs(ref).max()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_dg2d_ics.npz"))
+    tag = f"ninit{ninit}"
+    if f"{tag}/meta" in g.files:
+        _, n2, m2 = (int(v) for v in g[f"{tag}/meta"])
+        with wb.DG2D(nx=n2, ny=n2, mx=m2, my=m2, ninit=ninit, boxlen_x=box, boxlen_y=box) as s:
+            got2 = s.get_initial_conditions(ninit)
+        assert np.abs(got2 - g[f"{tag}/nodes"]).max() <= 2e-15 * np.abs(g[f"{tag}/nodes"]).max()
+
+
+def _advect_pulse_errors(wb, m, box, tend, sizes, limiter):
+    errs = []
+    for n in sizes:
+        with wb.DG2D(nx=n, ny=n, mx=m, my=m, bc=1, flux="llf1", limiter=limiter, solver="RK4", ninit=1, boxlen_x=box, boxlen_y=box) as s:
+            s.init_device(1)
+            it, t, dt = 0, 0.0, 0.0
+            while t < tend:
+                s.step_async(200, tend)
+                it, t, dt = s.sync()
+            assert abs(t - tend) <= 1e-12
+            lmax, l1, l2 = s.compute_error_resident(1, t, t)
+            errs.append(float(l1[0]))
+    return errs, [float(np.log2(errs[k] / errs[k + 1])) for k in range(len(errs) - 1)]
+
+
+@pytest.mark.parametrize("m", [2, 3])
+def test_convergence_order_on_the_gpu(wb, m):
+    """Convergence study run entirely on the GPU (north star: "the reference's convergence orders are reproduced"): the
+    reference's linear-advection test (ninit = 1: Gaussian density pulse exp(-10 r^2), velocity (1, 1), constant pressure
+    = min(rho) -- the translated pulse is an exact solution of the Euler equations) run to t = 0.1 on 32^2 .. 128^2 elements.
+    The exact solution is the initial state translated by (t, t), evaluated on the device and compared in compute_error's
+    weighted L1 norm (2d/benchmark_2d_dg.f90:23-89).  On the shipped unit box the periodic extension of the pulse has a kink
+    at the boundary (rho = 0.08 there) at which the convergence stalls (measured orders 1.8 -> 1.5 for m = 2, 1.3 -> 0.9 for
+    m = 3: the reference's own test behaves like this, printed only); on a 2 x 2 box the kink is 1e-3 of that and the design
+    order m of polynomial degree m-1 shows.  (The reference's vortex, ninit = 6, is not a steady
+    vortex -- its velocity carries exp(-1 - r^2/2) instead of exp((1 - r^2)/2) -- so a translated copy is not its solution:
+    measured plateau 2.4e-4.  A 3 x 3 box makes the constant pressure min(rho) = 3e-20 and the run ill-conditioned.)"""
+    errs1, ord1 = _advect_pulse_errors(wb, m, 1.0, 0.1, (32, 64, 128), "ONP")
+    print(f"order {m}, unit box (as shipped): density L1 errors {errs1}, observed orders {ord1}")
+    assert np.all(np.isfinite(errs1)) and errs1[0] > errs1[1] > errs1[2]
+    errs, orders = _advect_pulse_errors(wb, m, 2.0, 0.1, (32, 64, 128), "ONP")
+    print(f"order {m}, 2 x 2 box: density L1 errors {errs}, observed orders {orders}")
+    assert np.all(np.isfinite(errs)) and errs[0] > errs[1] > errs[2]
+    # m = 3 reaches the floor left by the real(4) SSPRK weights (the ~1e-8 per step drift of the mean, SURVEY 9.1: ~1100
+    # steps at 128^2) after the first refinement: 2.93 from 32^2 to 64^2, then 1.2e-6
+    assert max(orders) >= m - 0.5, (errs, orders)
