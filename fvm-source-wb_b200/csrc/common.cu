@@ -3,6 +3,10 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types/enums only; the symbols are resolved at run time with dlsym
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cmath>
 
 namespace wb {
 
@@ -220,12 +224,99 @@ int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s)
   return WB_OK;
 }
 
+// ---------------------------------------------------------------- output path
+void format_1pe12_5(double v, char out[16]) {
+  if (std::isnan(v)) { snprintf(out, 16, "%12s", "NaN"); return; }
+  if (std::isinf(v)) { snprintf(out, 16, "%12s", v > 0 ? "Infinity" : "-Infinity"); return; }
+  char tmp[32];
+  snprintf(tmp, sizeof(tmp), "%.5E", v);            // [-]d.dddddE[+-]ee[e]
+  char* e = strchr(tmp, 'E');
+  const int ex = atoi(e + 1);
+  if (ex >= 100 || ex <= -100) {                    // Fortran drops the letter: d.ddddd+eee
+    *e = 0;
+    char t2[32];
+    snprintf(t2, sizeof(t2), "%s%c%03d", tmp, ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+    snprintf(out, 16, "%12.12s", t2);
+  } else {
+    snprintf(out, 16, "%12.12s", tmp);
+  }
+}
+
+struct OutputJob {
+  std::thread th;
+  int status = WB_OK;
+  std::string err;
+};
+
+static void output_thread(OutputJob* job, int dev, cudaEvent_t ready, double* dbuf, size_t nrows, int ncols, std::string path) {
+  auto fail = [&](const char* what, cudaError_t e) {
+    job->status = WB_ERR_CUDA;
+    job->err = std::string(what) + ": " + cudaGetErrorString(e);
+  };
+  cudaError_t e = cudaSetDevice(dev);
+  cudaStream_t s = nullptr;
+  double* hbuf = nullptr;
+  const size_t bytes = sizeof(double) * nrows * ncols;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ready, 0);
+  if (e == cudaSuccess) e = cudaMallocHost(&hbuf, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hbuf, dbuf, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) fail("output_file copy", e);
+  if (e == cudaSuccess) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) { job->status = WB_ERR_ARG; job->err = "cannot open " + path; }
+    else {
+      std::vector<char> line((size_t)ncols * 13 + 2);
+      for (size_t r = 0; r < nrows; ++r) {
+        char* p = line.data();
+        for (int c = 0; c < ncols; ++c) {
+          char num[16];
+          format_1pe12_5(hbuf[r * ncols + c], num);
+          memcpy(p, num, 12); p += 12;
+          if (c + 1 < ncols) *p++ = ' ';            // 1X between the fields; a trailing 1X writes nothing
+        }
+        *p++ = '\n';
+        fwrite(line.data(), 1, (size_t)(p - line.data()), f);
+      }
+      fclose(f);
+    }
+  }
+  if (hbuf) cudaFreeHost(hbuf);
+  if (s) cudaStreamDestroy(s);
+  cudaFree(dbuf);
+  cudaEventDestroy(ready);
+}
+
+int output_start(OutputJob** job, int dev, cudaStream_t producer, double* dbuf, size_t nrows, int ncols, const char* path) {
+  WB_CHECK(output_wait(job));                       // one job per handle at a time
+  cudaEvent_t ready;
+  WB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  WB_CUDA(cudaEventRecord(ready, producer));
+  OutputJob* j = new OutputJob;
+  j->th = std::thread(output_thread, j, dev, ready, dbuf, nrows, ncols, std::string(path));
+  *job = j;
+  return WB_OK;
+}
+
+int output_wait(OutputJob** job) {
+  if (!job || !*job) return WB_OK;
+  OutputJob* j = *job;
+  if (j->th.joinable()) j->th.join();
+  const int st = j->status;
+  if (st != WB_OK) set_error("%s", j->err.c_str());
+  delete j;
+  *job = nullptr;
+  return st;
+}
+
 }  // namespace wb
 
 extern "C" {
 const char* wb_last_error(void) { return wb::t_err; }
 const char* wb_version(void) { return "wbeuler-b200 0.1 (sm_100a, FP64)"; }
 long long wb_kernel_launch_count(void) { return wb::g_launches.load(); }
+void wb_format_1pe12_5(double v, char* out13) { char b[16]; wb::format_1pe12_5(v, b); memcpy(out13, b, 13); }
 int wb_nccl_get_unique_id(void* id128) {
   if (!id128) { wb::set_error("null id buffer"); return WB_ERR_ARG; }
   return wb::nccl_get_unique_id(id128);

@@ -66,6 +66,16 @@ int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
 int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
 int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s);
 
+// ---------------------------------------------------------------- output path (output_file of the reference drivers)
+// A table of `nrows` x `ncols` doubles that a packing kernel has written to `dbuf` (device memory owned by the job from
+// here on) is copied to the host on a private stream once `ready` has fired and written to `path` in the reference's
+// format '(7(1PE12.5,1X))' by a host thread: the solver's stream is never blocked.  output_wait joins and reports.
+struct OutputJob;
+int output_start(OutputJob** job, int dev, cudaStream_t producer, double* dbuf, size_t nrows, int ncols, const char* path);
+int output_wait(OutputJob** job);      // joins (no-op on nullptr); WB_OK or the error the thread met
+// one number in Fortran's 1PE12.5 (12 characters + NUL): d.dddddE+ee, or d.ddddd+eee when the exponent needs three digits
+void format_1pe12_5(double v, char out[16]);
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 // max-reduction of non-negative doubles through their (order-preserving) bit patterns

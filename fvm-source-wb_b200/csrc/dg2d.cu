@@ -285,6 +285,41 @@ __global__ void k_dg_init(double* __restrict__ nodes, double* __restrict__ xy, D
   if (xy) { xy[(size_t)mode * g.ne + e] = x; xy[((size_t)g.nm + mode) * g.ne + e] = y; }
 }
 
+// output_file (2d/benchmark_2d_dg.f90:468-495): one row per element, icell outer / jcell inner: x, y of node (1,1) and
+// w - w_eq for the variables var..nvar there (compute_primitive of the nodal value; get_equilibrium_solution :594-622)
+template <int M>
+__global__ void k_dg_pack_output(const double* __restrict__ modes, DgGrid g, DgPhys P, Basis B, double boxlen_y, int var, int nequilibrium,
+                                 double* __restrict__ tab) {
+  size_t eo = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (eo >= g.ne_own) return;
+  const size_t e = eo + g.e_off;
+  double d[4][M][M], u[4], w[4];
+  load_modes<M>(modes, g, e, d);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {            // node (1,1) as get_nodes_from_modes evaluates it (:575-587)
+    double a = 0.0;
+#pragma unroll
+    for (int in = 0; in < M; ++in)
+#pragma unroll
+      for (int jn = 0; jn < M; ++jn) a = a + d[v][in][jn] * B.P[0][in] * B.P[0][jn];
+    u[v] = a;
+  }
+  prim(P, u, w);
+  double x, y;
+  node_xy(g, P, B, e, 0, boxlen_y / (double)g.nyg, x, y);
+  double weq[4] = {0.0, 0.0, 0.0, 0.0};
+  if (nequilibrium == 1) { weq[0] = exp(-(x + y)); weq[3] = exp(-(x + y)); }
+  else if (nequilibrium == 2) {
+    const double rho_0 = (double)1.21f, p_0 = 1., gg = 1.;
+    weq[0] = rho_0 * exp(-(rho_0 * gg / p_0) * (x + y)); weq[3] = p_0 * exp(-(rho_0 * gg / p_0) * (x + y));
+  }
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx) - (g.slab ? 1 : 0);
+  const int ncol = 2 + (4 - var + 1);
+  double* row = tab + ((size_t)ic * (g.ne_own / g.nx) + jc) * ncol;
+  row[0] = x; row[1] = y;
+  for (int v = var; v <= 4; ++v) row[2 + v - var] = w[v - 1] - weq[v - 1];
+}
+
 // ------------------------------------------------------------------------------------ compute_update :1137-1479
 template <int M>
 __global__ void __launch_bounds__(128) k_dg_update(const double* __restrict__ du, const double* __restrict__ gx,
@@ -943,6 +978,7 @@ struct wb_dg2d {
   bool split_ok = false;       // k_dg_stage_split (element split over four threads, every face once): nx % 32 == 0
   const double* map_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
   CUtensorMap map[4];
+  wb::OutputJob* out_job = nullptr;   // output_file in flight (host thread)
 };
 
 namespace {
@@ -1438,6 +1474,7 @@ int wb_dg2d_destroy(wb_dg2d* h) {
   if (!h) return WB_OK;
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  output_wait(&h->out_job);
   cudaFree(h->du); cudaFree(h->A); cudaFree(h->Bf); cudaFree(h->C); cudaFree(h->D); cudaFree(h->E); cudaFree(h->stage);
   cudaFree(h->gx); cudaFree(h->gy); cudaFree(h->xy); cudaFree(h->fz); cudaFree(h->ctrl); cudaFree(h->part1); cudaFree(h->part2);
   cudaFree(h->sbuf_lo); cudaFree(h->sbuf_hi); cudaFree(h->rbuf_lo); cudaFree(h->rbuf_hi); cudaFree(h->red);
@@ -1686,6 +1723,27 @@ int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out)
   if (t_out) *t_out = h->h_ctrl->t;
   if (last_dt_out) *last_dt_out = h->h_ctrl->dt;
   return WB_OK;
+}
+
+int wb_dg2d_output_file(wb_dg2d* h, int var, int nequilibrium, const char* path) {
+  if (!h || !path) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  WB_REQUIRE(var >= 1 && var <= 4, "var must be 1..4 (got %d)", var);
+  WB_REQUIRE(nequilibrium >= 1 && nequilibrium <= 3, "nequilibrium must be 1..3 (got %d)", nequilibrium);
+  WB_REQUIRE(h->nranks == 1, "output_file: single-GPU handles only (a slab holds part of the table)");
+  WB_CUDA(cudaSetDevice(h->dev));
+  const int ncol = 2 + (4 - var + 1);
+  double* tab = nullptr;
+  WB_CUDA(cudaMalloc(&tab, sizeof(double) * ncol * h->g.ne_own));
+  dim3 b(128), gr((unsigned)((h->g.ne_own + 127) / 128));
+  DISPATCH_M(h, k_dg_pack_output<MM><<<gr, b, 0, h->stream>>>(h->du, h->g, h->phys, h->B, h->prm.boxlen_y, var, nequilibrium, tab));
+  WB_LAUNCH_CHECK();
+  return output_start(&h->out_job, h->dev, h->stream, tab, h->g.ne_own, ncol, path);
+}
+
+int wb_dg2d_output_wait(wb_dg2d* h) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  return output_wait(&h->out_job);
 }
 
 int wb_dg2d_download_modes(wb_dg2d* h, double* modes_out) {

@@ -190,6 +190,23 @@ __global__ void k_max_speed(const double* __restrict__ u, Grid g, Phys P, unsign
   }
 }
 
+// output_file (benchmark_2d.f90:115-143): one row (x, y, p - p_eq) per cell, icell outer / jcell inner, from the resident
+// state (delta form when eqz != nullptr); equilibrium by get_equilibrium_solution at the centre, pressure by compute_primitive
+__global__ void k_pack_output(const double* __restrict__ u, const double* __restrict__ eqz, Grid g, Phys P, double* __restrict__ tab) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y;
+  if (i >= g.nx) return;
+  const size_t o = (size_t)(j + 1) * g.pitch + i;
+  double uu[4] = {u[o], u[g.plane + o], u[2 * g.plane + o], u[3 * g.plane + o]}, w[4];
+  if (eqz) { uu[0] = eqz[o] + uu[0]; uu[3] = eqz[g.plane + o] + uu[3]; }
+  ref::prim(P, uu, w);
+  const double x = x_cent(i, P.dx), y = x_cent(g.j0 + j, P.dy);
+  double rho_e, p_e;
+  ref::eq_prim(P, x, y, rho_e, p_e);
+  double* row = tab + ((size_t)i * g.nyl + j) * 3;
+  row[0] = x; row[1] = y; row[2] = w[3] - p_e;
+}
+
 __global__ void k_ctrl_reset(Ctrl* c) {
   c->cmax_bits[0] = 0ull; c->cmax_bits[1] = 0ull;
   c->t[0] = 0.0; c->t[1] = 0.0;
@@ -660,6 +677,7 @@ struct wb_fv2d {
   int pf_rows = 4;              // L2 prefetch distance of the LDG marching kernel (rows ahead; 0 = off)
   bool tma_ok = false;          // tensor maps built: the TMA-fed stage kernel is used
   CUtensorMap map_u, map_w1;
+  wb::OutputJob* out_job = nullptr;   // output_file in flight (host thread)
 };
 
 namespace {
@@ -952,6 +970,7 @@ int wb_fv2d_destroy(wb_fv2d* h) {
   if (!h) return WB_OK;
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  output_wait(&h->out_job);
   nccl_comm_destroy(h->comm);
   cudaFree(h->u); cudaFree(h->w1); cudaFree(h->weq); cudaFree(h->eqz); cudaFree(h->stage); cudaFree(h->tab);
   cudaFree(h->ctrl); cudaFree(h->eqflag);
@@ -1098,6 +1117,24 @@ int wb_fv2d_evolve(wb_fv2d* h, double* u_inout, const double* w_eq, double tend,
   if (t_out) *t_out = t;
   if (last_dt_out) *last_dt_out = dt;
   return WB_OK;
+}
+
+int wb_fv2d_output_file(wb_fv2d* h, const char* path) {
+  if (!h || !path) { set_error("null argument"); return WB_ERR_ARG; }
+  if (!h->resident) { set_error("no resident state"); return WB_ERR_STATE; }
+  WB_REQUIRE(h->prm.nranks == 1, "output_file: single-GPU handles only (a slab holds part of the table)");
+  WB_CUDA(cudaSetDevice(h->dev));
+  double* tab = nullptr;
+  WB_CUDA(cudaMalloc(&tab, sizeof(double) * 3 * (size_t)h->g.nx * h->g.nyl));
+  dim3 b(128), gr((h->g.nx + 127) / 128, h->g.nyl);
+  k_pack_output<<<gr, b, 0, h->stream>>>(h->u, use_fast(h) ? h->eqz : nullptr, h->g, h->phys, tab);
+  WB_LAUNCH_CHECK();
+  return output_start(&h->out_job, h->dev, h->stream, tab, (size_t)h->g.nx * h->g.nyl, 3, path);
+}
+
+int wb_fv2d_output_wait(wb_fv2d* h) {
+  if (!h) { set_error("null handle"); return WB_ERR_ARG; }
+  return output_wait(&h->out_job);
 }
 
 static int update_common(wb_fv2d* h, const double* u, const double* w_eq, double* dudt, bool wb_scheme) {

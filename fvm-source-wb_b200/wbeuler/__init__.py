@@ -183,6 +183,15 @@ class FV2D:
     def reset_clock(self):
         _check(lib().wb_fv2d_reset_clock(self._h))
 
+    def output_file(self, path, wait=True):
+        """output_file(x,y,u,filen)  benchmark_2d.f90:115-143 of the resident state (asynchronous writer; wait=False returns at once)"""
+        _check(lib().wb_fv2d_output_file(self._h, C.c_char_p(os.fsencode(path))))
+        if wait:
+            self.output_wait()
+
+    def output_wait(self):
+        _check(lib().wb_fv2d_output_wait(self._h))
+
 
 # ================================================================================================== 2D DG
 class DG2DParams(C.Structure):
@@ -310,6 +319,15 @@ class DG2D:
         _check(lib().wb_dg2d_compute_error_resident(self._h, C.c_int(ninit), C.c_double(eta), C.c_double(shift_x), C.c_double(shift_y),
                                                     _ptr(a), _ptr(b), _ptr(c)))
         return a, b, c
+
+    def output_file(self, path, var=1, nequilibrium=3, wait=True):
+        """output_file(x,y,nodes,var,filen)  2d/benchmark_2d_dg.f90:468-495 of the resident state (asynchronous writer)"""
+        _check(lib().wb_dg2d_output_file(self._h, C.c_int(var), C.c_int(nequilibrium), C.c_char_p(os.fsencode(path))))
+        if wait:
+            self.output_wait()
+
+    def output_wait(self):
+        _check(lib().wb_dg2d_output_wait(self._h))
 
     def get_initial_conditions(self, ninit, eta=F32(0.1)):
         """get_initial_conditions(x,y,u,...)  2d/benchmark_2d_dg.f90:122-466, ninit 1..12 -> nodal conserved state (owned rows)"""

@@ -37,6 +37,8 @@ const char* wb_last_error(void);
 const char* wb_version(void);
 /* number of kernel launches issued by this process' library calls so far (for bench.py gpu_launches) */
 long long wb_kernel_launch_count(void);
+/* one number in the reference's output format 1PE12.5 (benchmark_2d.f90:139, 2d/benchmark_2d_dg.f90:489): 12 characters + NUL */
+void wb_format_1pe12_5(double v, char* out13);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU plumbing: one process per GPU.  Rank 0 calls wb_nccl_get_unique_id(), ships the
@@ -103,6 +105,12 @@ int wb_fv2d_step_async(wb_fv2d* h, int nsteps, double tend);
 /* wait for the stream and read the bookkeeping */
 int wb_fv2d_sync(wb_fv2d* h, int* iters_out, double* t_out, double* last_dt_out, double* last_cmax_out);
 int wb_fv2d_download(wb_fv2d* h, double* u_out);
+/* replaces output_file(x,y,u,filen)   benchmark_2d.f90:115-143 for the RESIDENT state: one line '(7(1PE12.5,1X))' per cell,
+ * icell outer / jcell inner: x, y, p - p_eq (compute_primitive of the cell, get_equilibrium_solution at its centre).
+ * Asynchronous: a packing kernel on the handle's stream, the D2H copy on a private stream and the formatting + file I/O on
+ * a host thread, so stepping continues meanwhile (movie snapshots); wb_fv2d_output_wait joins and reports. */
+int wb_fv2d_output_file(wb_fv2d* h, const char* path);
+int wb_fv2d_output_wait(wb_fv2d* h);
 /* reset t = 0, iter = 0 and recompute the max wave speed of the resident state */
 int wb_fv2d_reset_clock(wb_fv2d* h);
 
@@ -191,6 +199,12 @@ int wb_dg2d_step_async(wb_dg2d* h, int nsteps, double tend);
 int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out);
 int wb_dg2d_download(wb_dg2d* h, double* u_nodes_out);
 int wb_dg2d_download_modes(wb_dg2d* h, double* modes_out);
+/* replaces output_file(x,y,nodes,var,filen)   2d/benchmark_2d_dg.f90:468-495 for the RESIDENT state: per element (icell
+ * outer) x, y of node (1,1) and w - w_eq of the variables var..nvar there; `nequilibrium` is the module parameter that
+ * selects get_equilibrium_solution (:594-622; the shipped 3 = zero).  The movie frames of evolve (:759-766) are this call
+ * every `interval` steps between wb_dg2d_step_async calls.  Asynchronous like wb_fv2d_output_file. */
+int wb_dg2d_output_file(wb_dg2d* h, int var, int nequilibrium, const char* path);
+int wb_dg2d_output_wait(wb_dg2d* h);
 
 /* ==========================================================================================
  * 1D finite volumes.  Host layout u(nvar,nx) == C double[nx][3].

@@ -182,6 +182,14 @@ def dg2d_get_initial_conditions(p, x, y):
     return u
 
 
+def dg2d_compute_primitive(p, u):
+    """compute_primitive  2d/benchmark_2d_dg.f90:891-902 on an array of states (..., 4)"""
+    u = np.ascontiguousarray(u)
+    w = np.empty_like(u)
+    lib().orc_dg2d_compute_primitive(C.byref(p), _ptr(u), _ptr(w), C.c_long(u.size // 4))
+    return w
+
+
 def dg2d_get_modes_from_nodes(p, nodes):
     u = np.empty_like(nodes)
     lib().orc_dg2d_get_modes_from_nodes(C.byref(p), _ptr(nodes), _ptr(u))

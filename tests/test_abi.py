@@ -205,3 +205,17 @@ def test_python_binding_rejects_wrong_shapes():
         wbeuler._ptr(a.astype(np.float32), (4, 3, 4))
     with pytest.raises(wbeuler.WBError):
         wbeuler._ptr([[0.0]], (1, 1))           # not an ndarray
+
+
+def test_output_number_format_is_fortrans_1pe12_5(lib):
+    """output_file writes '(7(1PE12.5,1X))' (benchmark_2d.f90:139): one digit before the point, five after, two-digit
+    exponent -- and gfortran's three-digit form without the letter when the exponent needs it."""
+    def f(v):
+        buf = C.create_string_buffer(16)
+        lib.wb_format_1pe12_5(C.c_double(v), buf)
+        return buf.value.decode()
+    assert f(1.0) == " 1.00000E+00" and f(-0.5) == "-5.00000E-01" and f(0.0) == " 0.00000E+00"
+    assert f(123456.789) == " 1.23457E+05" and f(-9.999996e-7) == "-1.00000E-06"
+    assert f(1e-100) == " 1.00000-100" and f(-2.5e120) == "-2.50000+120"
+    assert f(float("nan")).strip() == "NaN" and f(float("inf")).strip() == "Infinity"
+    assert all(len(f(v)) == 12 for v in (1.0, -1e-300, 3e200, float("nan")))

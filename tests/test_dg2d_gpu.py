@@ -493,3 +493,37 @@ def test_convergence_order_on_the_gpu(wb, m):
     # m = 3 reaches the floor left by the real(4) SSPRK weights (the ~1e-8 per step drift of the mean, SURVEY 9.1: ~1100
     # steps at 128^2) after the first refinement: 2.93 from 32^2 to 64^2, then 1.2e-6
     assert max(orders) >= m - 0.5, (errs, orders)
+
+
+def test_output_file_of_the_resident_state(wb, oracle, tmp_path):
+    """output_file(x,y,nodes,var,filen) (2d/benchmark_2d_dg.f90:468-495) from the resident state: per element x, y of node
+    (1,1) and the primitive variables var..nvar there minus the equilibrium (nequilibrium = 3: zero, 2: the isothermal
+    atmosphere); the movie frames of evolve are this call between step_async calls."""
+    n, m = 12, 3
+    p = oracle.dg2d_params(nx=n, ny=n, mx=m, my=m, flux="llf1", limiter="ONP", solver="RK4", ninit=1)
+    x, y = oracle.dg2d_get_coords(p)
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s:
+        s.init_device(1)
+        s.step_async(2)
+        s.output_file(str(tmp_path / "SIM00001.dat"), var=1, nequilibrium=3, wait=False)
+        s.step_async(1)
+        s.output_wait()
+        s.output_file(str(tmp_path / "p2.dat"), var=4, nequilibrium=2)
+        nodes3 = s.download()
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s:
+        s.init_device(1)
+        s.step_async(2)
+        nodes2 = s.download()
+    lines = (tmp_path / "SIM00001.dat").read_text().splitlines()
+    assert len(lines) == n * n and all(len(l) == 6 * 12 + 5 for l in lines)
+    tab = np.array([[float(v) for v in l.split()] for l in lines]).reshape(n, n, 6)
+    w = oracle.dg2d_compute_primitive(p, nodes2)[0, 0]           # node (1,1): (ny, nx, 4)
+    assert np.allclose(tab[..., 0], x[0, 0].T, rtol=1e-5) and np.allclose(tab[..., 1], y[0, 0].T, rtol=1e-5)
+    for v in range(4):
+        assert np.abs(tab[..., 2 + v] - w[..., v].T).max() <= 1e-5 * np.abs(w[..., v]).max()
+    lines = (tmp_path / "p2.dat").read_text().splitlines()
+    assert len(lines) == n * n and all(len(l) == 3 * 12 + 2 for l in lines)
+    tab = np.array([[float(v) for v in l.split()] for l in lines]).reshape(n, n, 3)
+    w = oracle.dg2d_compute_primitive(p, nodes3)[0, 0]
+    peq = np.exp(-float(np.float32(1.21)) * (x[0, 0] + y[0, 0]))
+    assert np.abs(tab[..., 2] - (w[..., 3] - peq).T).max() <= 1e-5 * np.abs(w[..., 3] - peq).max()

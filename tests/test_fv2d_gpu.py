@@ -239,3 +239,27 @@ def test_floors_of_the_sound_speed_are_honoured(wb, oracle, nx, ny):
     ref, it0, t0, dt0, _ = oracle.fv2d_evolve(p, u, weq, 1.0, 1)
     assert it == it0 == 1 and abs(dt - dt0) <= 1e-14 * dt0
     assert rel_linf_fields(got, ref) <= TOL
+
+
+def test_output_file_of_the_resident_state(wb, oracle, tmp_path):
+    """output_file(x,y,u,filen) (benchmark_2d.f90:115-143) from the resident state: x, y, p - p_eq per cell in
+    '(7(1PE12.5,1X))', icell outer / jcell inner; packing kernel + asynchronous D2H + host writer thread."""
+    nx, ny = 48, 36
+    p, u, weq = setup(oracle, nx, ny, 3)
+    ref, it, t, dt, cm = oracle.fv2d_evolve(p, u, weq, 1.0, 3)
+    with wb.FV2D(nx, ny) as s:
+        s.upload(u, weq)
+        s.step_async(3)
+        s.output_file(str(tmp_path / "fi.dat"), wait=False)      # the writer runs while the next steps are enqueued
+        s.step_async(2)
+        s.output_wait()
+        s.sync()
+    lines = (tmp_path / "fi.dat").read_text().splitlines()
+    assert len(lines) == nx * ny and all(len(l) == 3 * 12 + 2 for l in lines)
+    tab = np.array([[float(v) for v in l.split()] for l in lines]).reshape(nx, ny, 3)
+    x, y = oracle.fv2d_get_coords(p)
+    w = oracle.fv2d_compute_primitive(p, ref)
+    dp = (w[..., 3] - weq[..., 3]).T                      # (nx, ny): the file runs icell outer, jcell inner
+    assert np.allclose(tab[..., 0], x.T if x.ndim == 2 else x[:, None], rtol=1e-5, atol=0)
+    assert np.abs(tab[..., 2] - dp).max() <= 1e-5 * np.abs(dp).max() + 1e-17
+    assert lines[0][:12] == "%12.5E" % float(x.flat[0])
