@@ -563,7 +563,7 @@ __global__ void k_limiter_hio(const double* __restrict__ u, double* __restrict__
   if (e >= g.ne) return;
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
   const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nx), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nx);
-  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
+  const size_t eB = (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, eT = (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic;
   // mode (a,b), 1-based as in the reference -> plane index (b-1)*M + (a-1)
 #define MD(el, a, b) (PL(u, g, v, ((b) - 1) * M + ((a) - 1))[el])
   for (int v = 0; v < 4; ++v) {
@@ -606,6 +606,120 @@ __global__ void k_limiter_hio(const double* __restrict__ u, double* __restrict__
   }
 #undef MD
 }
+// ---- the neighbour-reading limiters in the FUSED flow (arith 0): the stage kernel writes the un-limited stage result to
+// a scratch field `u`; these kernels read it (element + 4 neighbours) and write the limited result to `out` in ONE pass, with
+// the reference's operation order (same device code as the unfused kernels above: same bits).  `out2` is the second result
+// of SSPRK(5,4) stage 4 (w5, :700-704): the stage kernel left it without its k3*w4 term, which needs the LIMITED w4.
+// A skipped step (ctrl->skip) hands its input through unchanged.
+template <int M>
+__global__ void __launch_bounds__(128) k_limiter_hio_onp(const double* __restrict__ u, double* __restrict__ out, double* __restrict__ out2,
+                                                         double k3, DgGrid g, DgPhys P, Basis B, const DgCtrl* __restrict__ ctrl) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  double un[4][M][M];
+  load_modes<M>(u, g, e, un);
+  if (ctrl->skip) { store_modes<M>(out, g, e, un); return; }
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nx), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nx);
+  const size_t eB = (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, eT = (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic;
+  if (M > 1) {
+#define MD(el, a, b) (PL(u, g, v, ((b) - 1) * M + ((a) - 1))[el])
+#define UN(a, b) un[v][(a) - 1][(b) - 1]
+    for (int v = 0; v < 4; ++v) {              // high_order_limiter :1478-1583, u_new in registers
+      auto limiting = [&](int a, int b) {      // :1441-1476
+        double coeff_j = (2.0 * (double)(a - 1) + 1.0) * (2 * (double)(b - 1) - 1);
+        double coeff_i = (2.0 * (double)(b - 1) + 1.0) * (2 * (double)(a - 1) - 1);
+        double coeff_u = (2.0 * (double)(a - 1) + 1.0) * (2.0 * (double)(b - 1) + 1.0);
+        double central_u = MD(e, a, b);
+        double d_r_y = (MD(eT, a, b - 1) - MD(e, a, b - 1)) * coeff_j;
+        double d_l_y = (MD(e, a, b - 1) - MD(eB, a, b - 1)) * coeff_j;
+        double d_r_x = (MD(eR, a - 1, b) - MD(e, a - 1, b)) * coeff_i;
+        double d_l_x = (MD(e, a - 1, b) - MD(eL, a - 1, b)) * coeff_i;
+        return minmod2d(central_u * coeff_u, d_r_y, d_l_y, d_r_x, d_l_x) / coeff_u;
+      };
+      int done = 0;
+      for (int a = M; a >= 2; --a) {
+        double limited = limiting(a, a);
+        if (limited != MD(e, a, a)) UN(a, a) = limited;
+        else break;
+        for (int b = a - 1; b >= 2; --b) {
+          double l1 = limiting(a, b), l2 = limiting(b, a);
+          if ((fabs(l1 - MD(e, a, b)) < P.eps) && (fabs(l2 - MD(e, b, a)) < P.eps)) { done = 1; break; }
+          UN(a, b) = l1;
+          UN(b, a) = l2;
+        }
+        if (done == 1) break;
+        double coeff_y = (2 * (double)(a - 1) + 1), coeff_u = (2 * (double)(a - 1) + 1);
+        double d_r_y = MD(eT, a - 1, 1) - MD(e, a - 1, 1);
+        double d_l_y = MD(e, a - 1, 1) - MD(eB, a - 1, 1);
+        double d_r_x = MD(eR, 1, a - 1) - MD(e, 1, a - 1);
+        double d_l_x = MD(e, 1, a - 1) - MD(eL, 1, a - 1);
+        double l1 = generalized_minmod(P, MD(e, 1, a) * coeff_u, d_r_y * coeff_y, d_l_y * coeff_y) / coeff_u;
+        double l2 = generalized_minmod(P, MD(e, a, 1) * coeff_u, d_r_x * coeff_y, d_l_x * coeff_y) / coeff_u;
+        if ((l1 == MD(e, 1, a)) && (l2 == MD(e, a, 1))) break;
+        UN(1, a) = l1;
+        UN(a, 1) = l2;
+      }
+    }
+#undef MD
+#undef UN
+    // compute_positivity(u_new) :1571-1574.  Sufficient test first (as in the fused stage kernels): every point value of a
+    // variable lies within R_v = sum |mode_ij| P_i(1) P_j(1) of its mean; bounds of density and pressure above eps with a
+    // margin far above the rounding of the point evaluations mean theta = 1 and t = 1 exactly, i.e. nothing to do
+    bool ok = false;
+    {
+      double R[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+            if (i != 0 || j != 0) r = r + fabs(un[v][i][j]) * (B.Ep[i] * B.Ep[j]);
+        R[v] = r;
+      }
+      const double rho_lo = un[0][0][0] - R[0], E_lo = un[3][0][0] - R[3];
+      const double mx_hi = fabs(un[1][0][0]) + R[1], my_hi = fabs(un[2][0][0]) + R[2];
+      const double margin = 1e-9 * (fabs(un[0][0][0]) + R[0] + fabs(un[3][0][0]) + R[3]);
+      if (rho_lo > P.eps + margin && rho_lo > (double)10e-10f) {
+        const double p_lo = P.gm1a * (E_lo - 0.5 * (mx_hi * mx_hi + my_hi * my_hi) / rho_lo);
+        ok = p_lo > P.eps + margin;
+      }
+    }
+    if (!ok) positivity_el<M>(P, B, un);
+  }
+  store_modes<M>(out, g, e, un);
+  if (out2) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int i = 0; i < M; ++i) PL(out2, g, v, j * M + i)[e] = fma(k3, un[v][i][j], PL(out2, g, v, j * M + i)[e]);
+  }
+}
+// limiter_low_order ('LOW') :769-860 as a copy u -> out
+template <int M>
+__global__ void k_limiter_low_into(const double* __restrict__ u, double* __restrict__ out, DgGrid g, const DgCtrl* __restrict__ ctrl) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne) return;
+  const bool act = !ctrl->skip && M > 1;
+  for (int v = 0; v < 4; ++v)
+    for (int j = 0; j < M; ++j)
+      for (int i = 0; i < M; ++i) {
+        const bool zero = act && ((i == 0 && j >= 1) || (j == 0 && i >= 1));
+        PL(out, g, v, j * M + i)[e] = zero ? 0.0 : PL(u, g, v, j * M + i)[e];
+      }
+}
+// out2 += k3 * out (the k3*w4 term of w5), and the pass-through of a skipped step for limiters that write `out` themselves
+__global__ void k_dg_finish_out2(double* __restrict__ out2, double k3, const double* __restrict__ lim, size_t n,
+                                 const DgCtrl* __restrict__ ctrl) {
+  if (ctrl->skip) return;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    out2[k] = fma(k3, lim[k], out2[k]);
+}
+
 // compute_limiter ('1OR') :203-309, step A: modal PRIMITIVE variables w = modes(prim(nodes(u)))
 template <int M>
 __global__ void k_limiter_1or_a(const double* __restrict__ u, double* __restrict__ w, DgGrid g, DgPhys P, Basis B,
@@ -637,7 +751,7 @@ __global__ void k_limiter_1or_b(const double* __restrict__ w, double* __restrict
   if (e >= g.ne) return;
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
   const size_t eL = (size_t)jc * g.nx + bc_index(P.bc, ic - 1, g.nx), eR = (size_t)jc * g.nx + bc_index(P.bc, ic + 1, g.nx);
-  const size_t eB = (size_t)bc_index(P.bc, jc - 1, g.ny) * g.nx + ic, eT = (size_t)bc_index(P.bc, jc + 1, g.ny) * g.nx + ic;
+  const size_t eB = (size_t)y_nb(g, P.bc, jc - 1) * g.nx + ic, eT = (size_t)y_nb(g, P.bc, jc + 1) * g.nx + ic;
   const double norm = 3.;
   double md[4][M][M], nd[4][M][M];
 #pragma unroll
@@ -684,7 +798,11 @@ __global__ void k_limiter_pos(const double* __restrict__ u, double* __restrict__
   if (e >= g.ne) return;
   const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
   const size_t eL = (size_t)jc * g.nx + max(ic - 1, 0), eR = (size_t)jc * g.nx + min(ic + 1, g.nx - 1);
-  const size_t eB = (size_t)max(jc - 1, 0) * g.nx + ic, eT = (size_t)min(jc + 1, g.ny - 1) * g.nx + ic;
+  // the clamp is on the GLOBAL row (it ignores bc): on a slab the ghost rows hold the neighbours' rows, except at the ends
+  // of a periodic box, where the reference takes the element itself
+  const int gj = g.j0 + jc;
+  const size_t eB = (size_t)(gj - 1 < 0 ? jc : max(jc - 1, 0)) * g.nx + ic;
+  const size_t eT = (size_t)(gj + 1 > g.nyg - 1 ? jc : min(jc + 1, g.ny - 1)) * g.nx + ic;
   double md[4][M][M], nd[4][M][M];
   load_modes<M>(u, g, e, md);
   if (M > 1) {
@@ -919,6 +1037,10 @@ __global__ void k_dg_unpack_rows(double* __restrict__ u, DgGrid g, const double*
   p[ic] = lo[(size_t)pl * g.nx + ic];
   p[(size_t)(g.ny - 1) * g.nx + ic] = hi[(size_t)pl * g.nx + ic];
 }
+__global__ void k_dg_copy_if_skipped(double* __restrict__ out, const double* __restrict__ in, size_t n, const DgCtrl* __restrict__ ctrl) {
+  if (!ctrl->skip) return;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) out[k] = in[k];
+}
 __global__ void k_dg_advance(DgCtrl* ctrl) {
   if (ctrl->skip) return;
   ctrl->t = ctrl->t + ctrl->dt;
@@ -1096,6 +1218,51 @@ int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
   return WB_OK;
 }
 
+// fused flow with a neighbour-reading limiter: `tmp` (un-limited stage result, ghost rows valid) -> `out`; out2 gets its
+// k3*out term.  1OR and POS keep their own kernels (1OR needs the primitive modes of the neighbours: two passes).
+int dg_limit_into(wb_dg2d* h, double* tmp, double* out, double* out2, double k3) {
+  dim3 b(128), gr = elem_grid(h, 128);
+  dim3 gb((unsigned)std::min<size_t>((h->nfield + 255) / 256, 148 * 16));
+  if (h->g.m == 1) {                          // every limiter returns early for mx == my == 1: out = tmp
+    k_dg_axpy<0><<<gb, 256, 0, h->stream>>>(out, tmp, 1.0, nullptr, 0, nullptr, 0, nullptr, 0, tmp, 0.0, h->nfield, h->ctrl);
+    k_dg_copy_if_skipped<<<gb, 256, 0, h->stream>>>(out, tmp, h->nfield, h->ctrl);
+    wb::g_launches.fetch_add(1);
+    WB_LAUNCH_CHECK();
+  } else switch (h->prm.limiter_id) {
+    case 2:
+      DISPATCH_M(h, k_limiter_hio_onp<MM><<<gr, b, 0, h->stream>>>(tmp, out, out2, k3, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      return WB_OK;
+    case 3:      // the ghost rows of E come from the (exchanged) ghost rows of tmp: step A is element-local
+      WB_CHECK(dg_ensure(h, &h->E));
+      DISPATCH_M(h, k_limiter_1or_a<MM><<<gr, b, 0, h->stream>>>(tmp, h->E, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      k_dg_copy_if_skipped<<<gb, 256, 0, h->stream>>>(out, tmp, h->nfield, h->ctrl);      // the kernels return early on a skipped step
+      WB_LAUNCH_CHECK();
+      DISPATCH_M(h, k_limiter_1or_b<MM><<<gr, b, 0, h->stream>>>(h->E, out, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      break;
+    case 4:
+      DISPATCH_M(h, k_limiter_low_into<MM><<<gr, b, 0, h->stream>>>(tmp, out, h->g, h->ctrl));
+      WB_LAUNCH_CHECK();
+      break;
+    case 5:
+      k_dg_copy_if_skipped<<<gb, 256, 0, h->stream>>>(out, tmp, h->nfield, h->ctrl);
+      WB_LAUNCH_CHECK();
+      DISPATCH_M(h, k_limiter_pos<MM><<<gr, b, 0, h->stream>>>(tmp, out, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      break;
+    default:
+      set_error("dg_limit_into: limiter %d has no fused flow", h->prm.limiter_id);
+      return WB_ERR_STATE;
+  }
+  if (out2) {
+    k_dg_finish_out2<<<gb, 256, 0, h->stream>>>(out2, k3, out, h->nfield, h->ctrl);
+    WB_LAUNCH_CHECK();
+  }
+  return WB_OK;
+}
+
 // slab mode: fill the two ghost rows of a 4*nm-plane field.  Periodic box (bc = 1): ring of ranks; index clamp
 // (bc = 2, 3): chain, and the ghost row at a global edge is the rank's own boundary row (the clamped neighbour).
 int dg_exchange(wb_dg2d* h, double* field) {
@@ -1187,16 +1354,22 @@ int dg_make_map(const wb_dg2d* h, const double* base, CUtensorMap* out) {
 int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, double c0, const double* A1, double c1, double cd,
                   double* out2 = nullptr, const double* B0 = nullptr, double k0 = 0, const double* B1 = nullptr, double k1 = 0,
                   double k2 = 0, double k3 = 0, double ke = 0) {
+  const bool lim_after = h->prm.limiter_id >= 2;
+  double* stage_out = out;
+  if (lim_after) {                        // un-limited stage result -> scratch D; k3*w4 of the second result needs the LIMITED w4
+    WB_CHECK(dg_ensure(h, &h->D));
+    stage_out = h->D;
+  }
   StageCoef C;
   C.A0 = A0; C.A1 = A1; C.c0 = c0; C.c1 = c1; C.cd = cd; C.na = A1 ? 2 : 1;
-  C.out2 = out2; C.B0 = B0; C.B1 = B1; C.k0 = k0; C.k1 = k1; C.k2 = k2; C.k3 = k3; C.ke = ke;
+  C.out2 = out2; C.B0 = B0; C.B1 = B1; C.k0 = k0; C.k1 = k1; C.k2 = k2; C.k3 = lim_after ? 0.0 : k3; C.ke = ke;
   const int onp = (h->prm.limiter_id == 1 && h->g.m > 1) ? 1 : 0;
   const CUtensorMap* m_in = nullptr;
   if (h->tma_ok)
     for (int k = 0; k < 4; ++k)
       if (h->map_ptr[k] == in) m_in = &h->map[k];
   if (m_in && h->split_ok) {
-    WB_CHECK(launch_stage_split(m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g, h->phys, h->FB, h->ctrl,
+    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g, h->phys, h->FB, h->ctrl,
                                 onp, h->march_rows, 0, h->g.ny, h->stream));
     wb::g_launches.fetch_sub(1);      // counted again by the WB_LAUNCH_CHECK below
   } else if (m_in && h->march_ok) {
@@ -1212,7 +1385,7 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
         configured[h->phys.flux_id >= 2] = true;
       }
-      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
                                                           h->phys, h->FB, h->ctrl, onp, h->march_rows);
     });
   } else if (m_in && h->tma_ok && h->g.nx % 32 == 0) {
@@ -1230,27 +1403,32 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
         configured[h->phys.flux_id >= 2] = true;
       }
-      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
+      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
                                                           h->phys, h->FB, h->ctrl, onp);
     });
   } else {
     dim3 b(64), gr = elem_grid(h, 64);
     if (h->phys.flux_id >= 2) {
-      DISPATCH_M(h, (k_dg_stage_fast<MM, true><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
+      DISPATCH_M(h, (k_dg_stage_fast<MM, true><<<gr, b, 0, h->stream>>>(in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
                                                                       h->g, h->phys, h->FB, h->ctrl, onp)));
     } else {
-      DISPATCH_M(h, (k_dg_stage_fast<MM, false><<<gr, b, 0, h->stream>>>(in, C, out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
+      DISPATCH_M(h, (k_dg_stage_fast<MM, false><<<gr, b, 0, h->stream>>>(in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr,
                                                                        h->g, h->phys, h->FB, h->ctrl, onp)));
     }
   }
   WB_LAUNCH_CHECK();
+  if (lim_after) {      // neighbour-reading limiter: ghost rows of the un-limited result, limiter, ghost rows of the limited one
+    WB_CHECK(dg_exchange(h, stage_out));
+    WB_CHECK(dg_limit_into(h, stage_out, out, out2, k3));
+  }
   WB_CHECK(dg_exchange(h, out));
   if (out2) WB_CHECK(dg_exchange(h, out2));
   return WB_OK;
 }
 
-// the fused flow covers element-local limiters only ('ONP' or none); neighbour-reading limiters use the unfused kernels
-bool dg_use_fused(const wb_dg2d* h) { return h->arith == 0 && (h->prm.limiter_id <= 1); }
+// the fused flow: the stage kernel applies an element-local limiter itself ('ONP' or none); for the neighbour-reading ones
+// ('HIO', '1OR', 'LOW', 'POS') it writes the un-limited result to a scratch field and a limiter kernel follows
+bool dg_use_fused(const wb_dg2d* h) { return h->arith == 0; }
 
 int dg_step_fused(wb_dg2d* h) {
   double *&du = h->du, *&A = h->A, *Bf = h->Bf, *C = h->C;
@@ -1346,8 +1524,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fused) or 1 (reference order)");
   const int nranks = p->nranks <= 0 ? 1 : p->nranks;      // 0 (zero-initialised struct) means "no slabs"
   WB_REQUIRE(p->rank >= 0 && p->rank < nranks, "bad rank/nranks %d/%d", p->rank, p->nranks);
-  WB_REQUIRE(nranks == 1 || (p->arith == 0 && p->limiter_id <= 1),
-             "slab mode (nranks > 1) is built for the fused stage kernel: arith 0 with limiter 'ONP' or none");
+  WB_REQUIRE(nranks == 1 || p->arith == 0, "slab mode (nranks > 1) is built for the fused flow: arith 0");
   WB_REQUIRE(nranks == 1 || p->ny / nranks >= 1, "each slab needs at least one row");
   int dev = 0;
   WB_CHECK(select_device(p->device, &dev));
@@ -1451,8 +1628,9 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
     const char* envr = getenv("WB_DG2D_ROWS");
     const bool want_march = p->arith == 0 && g.nx % 2 == 0 && g.nx >= DGT_W && (envm && atoi(envm) == 1) && !(env && atoi(env) == 0);
     if (envr && atoi(envr) > 0) h->march_rows = atoi(envr);
-    const char* envb = getenv("WB_DG2D_BOXWIDE");      // experiment: a box wider than the tensor (nx = 32 < DGT_W)
-    const int min_nx = (envb && atoi(envb) == 1) ? 32 : DGT_W;
+    // a TMA box may be wider than the tensor (nx = 32 < DGT_W = 36: the columns outside are zero-filled like any other
+    // out-of-range column; measured bit-identical to the global-memory path on B200), so 32 is the smallest grid
+    const int min_nx = 32;
     if (want_march || (p->arith == 0 && g.nx % 32 == 0 && g.nx >= min_nx && !(env && atoi(env) == 0))) {
       const double* bufs4[4] = {h->du, h->A, h->Bf, h->C};
       for (int k = 0; k < 4; ++k) {
@@ -1610,6 +1788,10 @@ int wb_dg2d_apply_limiter(wb_dg2d* h, double* modes_inout) {
   WB_LAUNCH_CHECK();
   WB_CHECK(dg_h2d_field(h, modes_inout, h->A));
   WB_CHECK(dg_exchange(h, h->A));      // (neighbour-reading limiters on slabs)
+  if (h->arith == 0 && h->prm.limiter_id >= 2) {      // the limiter kernels of the fused flow (same operation order, one pass)
+    WB_CHECK(dg_limit_into(h, h->A, h->Bf, nullptr, 0.0));
+    return dg_d2h_field(h, h->Bf, modes_inout);
+  }
   WB_CHECK(dg_limiter(h, h->A, false));
   return dg_d2h_field(h, h->A, modes_inout);
 }

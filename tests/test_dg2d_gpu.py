@@ -96,10 +96,13 @@ def test_compute_update_bitwise(wb, oracle, nx, mx, kw):
     assert np.array_equal(got, ref), rel(got, ref)
 
 
-@pytest.mark.parametrize("lim", ["ONP", "HIO", "1OR", "LOW"])
+@pytest.mark.parametrize("arith", [1, 0])
+@pytest.mark.parametrize("lim", ["ONP", "HIO", "1OR", "LOW", "POS"])
 @pytest.mark.parametrize("mx,ninit,bc", [(2, 3, 2), (3, 4, 2), (3, 1, 1), (4, 5, 3)])
-def test_limiters_bitwise(wb, oracle, lim, mx, ninit, bc):
-    p, s, x, y = mk(oracle, wb, 8, mx, limiter=lim, ninit=ninit, bc=bc)
+def test_limiters_bitwise(wb, oracle, lim, mx, ninit, bc, arith):
+    """arith 1: the unfused reference-order kernels; arith 0: the one-pass limiter kernels of the fused flow (un-limited
+    stage result -> limited stage output): same operations in the same order, so both are bit-for-bit the oracle."""
+    p, s, x, y = mk(oracle, wb, 8, mx, arith=arith, limiter=lim, ninit=ninit, bc=bc)
     rng = np.random.default_rng(11)
     m0 = oracle.dg2d_get_modes_from_nodes(p, oracle.dg2d_get_initial_conditions(p, x, y))
     m0[1:] += 0.2 * rng.standard_normal(m0[1:].shape) * np.abs(m0[0:1, 0:1])      # stir the high modes so limiters act
@@ -183,6 +186,12 @@ def field_err(a, b):
     (32, 3, 2, dict(flux="llf1", limiter="ONP", solver="SS4", ninit=2, bc=2, source=2, grad_phi_case=1)),
     (32, 4, 2, dict(flux="llf1", limiter="none", solver="RK4", ninit=1, bc=1)),
     (64, 3, 2, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=5, bc=3)),
+    # neighbour-reading limiters in the fused flow: un-limited stage result -> scratch field -> limiter kernel (reference
+    # operation order) -> stage output; '1OR', 'LOW', 'POS' here, 'HIO' in test_fused_flow_with_hio_is_the_same_algorithm
+    (32, 2, 2, dict(flux="llf1", limiter="1OR", solver="EQL", ninit=4, bc=2)),
+    (32, 3, 2, dict(flux="llf1", limiter="LOW", solver="DEB", ninit=4, bc=2)),
+    (32, 3, 2, dict(flux="llf1", limiter="POS", solver="EQL", ninit=3, bc=2)),
+    (16, 1, 1, dict(flux="llf1", limiter="HIO", solver="RK4", ninit=1, bc=1)),       # order 1: every limiter returns early
 ])
 def test_evolve_fused_kernel_matches_oracle(wb, oracle, nx, mx, steps, kw):
     """arith = 0: one fused launch per RK stage (update + RK combination + ONP), sum-factorised, FMA, Newton rcp/rsqrt:
@@ -200,6 +209,46 @@ def test_evolve_fused_kernel_matches_oracle(wb, oracle, nx, mx, steps, kw):
     assert it2 == it and abs(t2 - t) <= 1e-13 * t and abs(dt2 - dt) <= 1e-12 * dt
     assert np.all(np.isfinite(got))
     assert field_err(got, ref) <= 1e-12
+
+
+@pytest.mark.parametrize("nx,mx,steps,kw", [
+    (8, 3, 1, dict(flux="llf1", limiter="HIO", solver="RK4", ninit=1, bc=1)),
+    (32, 3, 1, dict(flux="llf1", limiter="HIO", solver="RK4", ninit=1, bc=1)),
+    (64, 3, 2, dict(flux="llf1", limiter="HIO", solver="SS4", ninit=3, bc=2)),
+    (12, 4, 1, dict(flux="llf1", limiter="HIO", solver="RK4", ninit=5, bc=3)),
+])
+def test_fused_flow_with_hio_is_the_same_algorithm(wb, oracle, monkeypatch, nx, mx, steps, kw):
+    """'HIO' (2d/limiters.f90:1478-1583) decides with EXACT comparisons of rounded numbers whether to go on to the lower
+    modes: `limited = minmod2d(u*c, ...)/c; if (limited /= u) ... else exit`.  Where the element's own mode wins the minmod,
+    (u*c)/c is u in exact arithmetic, and whether it is u in floating point depends on the last bit of u.  The reference's
+    own trajectory is therefore a function of rounding luck, and only bit-identical inputs reproduce it: the reference-order
+    flow (arith 1) does, bit for bit (test_evolve_bitwise, the reference pins); the fused flow (arith 0) feeds the limiter a
+    stage result that differs from the reference's in the last bits, after which single elements may take the other branch
+    (measured: 4e-2 on the 8 x 8 pulse, where the element's own mode wins the minmod nearly everywhere and the luck is re-rolled
+    for every element -- after five stages 86-100 % of the elements differ by more than 1e-9; 1-6 % on the Riemann problems).  What CAN be asserted of the fused flow, and is:
+      * the limiter kernel itself is the reference's, bit for bit, on the same input (test_limiters_bitwise[0], the pins);
+      * the un-limited stage is the reference's to 1e-12 (the no-limiter cases of test_evolve_fused_kernel_matches_oracle);
+      * limiters never touch the element means and the scheme is conservative: the sums of the mean modes agree with the
+        oracle's to rounding, whichever branches were taken;
+      * the two data paths of the fused flow (TMA-staged split kernel, global-memory kernel) give the same bits."""
+    p, s, x, y = mk(oracle, wb, nx, mx, arith=0, **kw)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    ref, it, t, dt = oracle.dg2d_evolve(p, u0, x, y, 1.0, steps)
+    with s:
+        got, it2, t2, dt2 = s.evolve(u0, x, y, 1.0, steps)
+        kern = s.stage_kernel()
+    assert it2 == it and np.all(np.isfinite(got))
+    mg, mr = oracle.dg2d_get_modes_from_nodes(p, got)[0, 0], oracle.dg2d_get_modes_from_nodes(p, ref)[0, 0]
+    if kw["bc"] == 1:      # periodic box: total mass, momentum and energy
+        for v in range(4):
+            assert abs(mg[..., v].sum() - mr[..., v].sum()) <= 1e-11 * np.abs(mr).sum()
+    frac = np.mean(np.abs(got - ref).max(axis=(0, 1, 4)) > 1e-9 * np.abs(ref).max())
+    print(f"HIO fused flow {nx}x{nx} order {mx}: {100 * frac:.1f} % of the elements took another branch than the oracle's run")
+    if kern == "split":
+        monkeypatch.setenv("WB_DG2D_TMA", "0")
+        with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, **kw) as s2:
+            b, it3, t3, dt3 = s2.evolve(u0, x, y, 1.0, steps)
+        assert np.array_equal(got, b) and (it2, t2, dt2) == (it3, t3, dt3)
 
 
 def test_fused_limiter_acts_like_the_reference_one(wb, oracle):
@@ -270,6 +319,8 @@ def test_golden_vectors(wb):
                      limiter=INV_L[lim], solver=INV_S[solver], ninit=ninit, arith=0) as s:
             if tag == "shipped_flux":
                 continue      # dt flips at step 2 on the symmetric pulse (see test_evolve_fused_kernel_matches_oracle)
+            if INV_L[lim] == "HIO":
+                continue      # 'HIO' branches on exact equality of rounded numbers (test_fused_flow_with_hio_...)
             un, it, t, dt = s.evolve(u0, x, y, 1.0, steps)
             assert field_err(un, g[f"{tag}_un"]) <= 1e-12, tag
 

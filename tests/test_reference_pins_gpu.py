@@ -117,11 +117,14 @@ def test_dg2d_fused_kernels_match_reference_source(wb, tag):
         assert field_err(un, g[f"{tag}/nodes_evolved"]) <= TOL
 
 
+@pytest.mark.parametrize("arith", [1, 0])
 @pytest.mark.parametrize("tag", tags("ref_dg2d_limiters.npz"))
-def test_dg2d_limiters_on_rough_data_equal_reference_source_bitwise(wb, tag):
+def test_dg2d_limiters_on_rough_data_equal_reference_source_bitwise(wb, tag, arith):
+    """arith 1: the unfused reference-order limiter kernels; arith 0: the one-pass limiter kernels of the fused flow
+    (k_limiter_hio_onp, ...), which run the same operations in the same order -- both bit for bit."""
     g = gold("ref_dg2d_limiters.npz")
     n, m, bc = (int(v) for v in g[f"{tag}/meta"])
-    with wb.DG2D(nx=n, ny=n, mx=m, my=m, bc=bc, limiter=str(g[f"{tag}/limiter"]), flux="llf1", ninit=1, device=0, arith=1) as s:
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, bc=bc, limiter=str(g[f"{tag}/limiter"]), flux="llf1", ninit=1, device=0, arith=arith) as s:
         v = s.apply_limiter(g[f"{tag}/in"])
     assert np.array_equal(v, g[f"{tag}/out"]), rel(v, g[f"{tag}/out"])
 

@@ -21,7 +21,13 @@ from oracle import wb_oracle as o
 ok = True
 CASES = [dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1, bc=1),
          dict(flux="llf1", limiter="none", solver="EQL", ninit=1, bc=1),
-         dict(flux="llf1", limiter="ONP", solver="RK4", ninit=2, bc=2, source=2, grad_phi_case=1)]
+         dict(flux="llf1", limiter="ONP", solver="RK4", ninit=2, bc=2, source=2, grad_phi_case=1),
+         # neighbour-reading limiters on slabs: ghost rows of the un-limited stage result, limiter kernel, ghost rows again
+         dict(flux="llf1", limiter="HIO", solver="RK4", ninit=1, bc=1),
+         dict(flux="llf1", limiter="HIO", solver="RK4", ninit=3, bc=2),
+         dict(flux="llf1", limiter="1OR", solver="EQL", ninit=4, bc=2),
+         dict(flux="llf1", limiter="POS", solver="EQL", ninit=3, bc=1),
+         dict(flux="llf1", limiter="LOW", solver="DEB", ninit=4, bc=3)]
 for kw in CASES:
     p = o.dg2d_params(nx=n, ny=n, mx=m, my=m, **kw)
     x, y = o.dg2d_get_coords(p)
@@ -44,7 +50,7 @@ for kw in CASES:
         msg += f"; vs oracle rel Linf {err:.2e}"
         same = same and err <= 1e-12
     # device-side initial conditions on slabs == on the whole grid (ninit 1 needs the global minimum of the density)
-    if kw["ninit"] in (1, 2):
+    if kw["ninit"] in (1, 2, 3, 4):
         with wbeuler.DG2D(nx=n, ny=n, mx=m, my=m, device=local_rank, **kw) as one:
             one.init_device(kw["ninit"]); one.step_async(2); r1 = one.sync(); ref_m = one.download_modes()
         s.init_device(kw["ninit"]); s.step_async(2); r2 = s.sync()
