@@ -606,6 +606,146 @@ __global__ void k_limiter_hio(const double* __restrict__ u, double* __restrict__
   }
 #undef MD
 }
+// limiter_positivity_2 ('PO3', 2d/limiters.f90:1587-1711) in two element-parallel passes, reference operation order.
+// get_matrix_decomp (2d/benchmark_2d_dg.f90:2096-2177) with k = (0, 1); rows as in the reference's literals.
+__device__ __forceinline__ void po3_matrices(const DgPhys& P, const double wa[4], double lev[4][4], double rev[4][4]) {
+  const double kappa = P.gamma - 1;
+  const double k1 = (double)0.f, k2 = (double)1.f;
+  const double ca = sqrt(P.gamma * wa[3] / wa[0]);
+  const double phis = sqrt(1 / 2.f * kappa * (wa[1] * wa[1] + wa[2] * wa[2]));
+  const double beta = 1.f / (2 * (ca * ca));
+  const double theta = k1 * wa[1] + k2 * wa[2];
+  rev[0][0] = 1 - phis * phis / (ca * ca); rev[0][1] = kappa * wa[1] / (ca * ca); rev[0][2] = kappa * wa[2] / (ca * ca); rev[0][3] = -kappa / (ca * ca);
+  rev[1][0] = -(k2 * wa[1] - k1 * wa[2]); rev[1][1] = k2; rev[1][2] = -k1; rev[1][3] = 0.0;
+  rev[2][0] = beta * (phis * phis - ca * theta); rev[2][1] = beta * (k1 * ca - kappa * wa[1]); rev[2][2] = beta * (k2 * ca - kappa * wa[2]); rev[2][3] = beta * kappa;
+  rev[3][0] = beta * (phis * phis + ca * theta); rev[3][1] = -beta * (k1 * ca + kappa * wa[1]); rev[3][2] = -beta * (k2 * ca + kappa * wa[2]); rev[3][3] = beta * kappa;
+  lev[0][0] = 1.0; lev[0][1] = 0.0; lev[0][2] = 1.0; lev[0][3] = 1.0;
+  lev[1][0] = wa[1]; lev[1][1] = k2; lev[1][2] = wa[1] + k1 * ca; lev[1][3] = wa[1] - k1 * ca;
+  lev[2][0] = wa[2]; lev[2][1] = -k1; lev[2][2] = wa[2] + k2 * ca; lev[2][3] = wa[2] - k2 * ca;
+  lev[3][0] = phis * phis / (kappa); lev[3][1] = k2 * wa[1] - k1 * wa[2];
+  lev[3][2] = (phis * phis + ca * ca) / kappa + ca * theta; lev[3][3] = (phis * phis + ca * ca) / kappa - ca * theta;
+}
+// nodal values of the element, and the (1,1) mode of its modal PRIMITIVE variables (compute_characteristics :2031-2040)
+template <int M>
+__device__ __forceinline__ void po3_prepare(const DgPhys& P, const Basis& B, const double md[4][M][M], double nd[4][M][M], double wa[4]) {
+  nodes_from_modes_el<M>(md, B, nd);
+  double wn[4][M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double uu[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]}, ww[4];
+      prim(P, uu, ww);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) wn[v][i][j] = ww[v];
+    }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double a = 0.0;
+#pragma unroll
+    for (int xq = 0; xq < M; ++xq)
+#pragma unroll
+      for (int yq = 0; yq < M; ++yq) a = a + 0.25 * wn[v][xq][yq] * B.P[xq][0] * B.P[yq][0] * B.wq[xq] * B.wq[yq];
+    wa[v] = a;
+  }
+}
+// pass A: modes of the characteristic variables lev * u_n of every element -> cm
+template <int M>
+__global__ void __launch_bounds__(128) k_limiter_po3_a(const double* __restrict__ u, double* __restrict__ cm, DgGrid g, DgPhys P, Basis B,
+                                                       const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne || M == 1) return;
+  double md[4][M][M], nd[4][M][M], wa[4], lev[4][4], rev[4][4];
+  load_modes<M>(u, g, e, md);
+  po3_prepare<M>(P, B, md, nd, wa);
+  po3_matrices(P, wa, lev, rev);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double un[4] = {nd[0][i][j], nd[1][i][j], nd[2][i][j], nd[3][i][j]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = s + lev[r][k] * un[k];
+        nd[r][i][j] = s;
+      }
+    }
+  modes_from_nodes_el<M>(nd, B, md);
+  store_modes<M>(cm, g, e, md);
+}
+// pass B: minmod of the linear characteristic modes against the PERIODIC neighbours' means (the reference wraps with nx in
+// both passes whatever bc is), back through rev, nodal reset of density / pressure below 1d-10, projection -> out
+template <int M>
+__global__ void __launch_bounds__(128) k_limiter_po3_b(const double* u, const double* __restrict__ cm, double* out,      /* u may be out (in place) */
+                                                       DgGrid g, DgPhys P, Basis B, const DgCtrl* __restrict__ ctrl) {
+  if (ctrl && ctrl->skip) return;
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ne || M == 1) return;
+  const int ic = (int)(e % g.nx), jc = (int)(e / g.nx);
+  const size_t eL = (size_t)jc * g.nx + (ic == 0 ? g.nx - 1 : ic - 1), eR = (size_t)jc * g.nx + (ic == g.nx - 1 ? 0 : ic + 1);
+  // y neighbours: a slab finds them in its ghost rows (ring of ranks), a whole grid wraps
+  const int jb = g.slab ? max(jc - 1, 0) : (jc == 0 ? g.ny - 1 : jc - 1), jt = g.slab ? min(jc + 1, g.ny - 1) : (jc == g.ny - 1 ? 0 : jc + 1);
+  const size_t eB = (size_t)jb * g.nx + ic, eT = (size_t)jt * g.nx + ic;
+  double ul[4][M][M];
+  load_modes<M>(cm, g, e, ul);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const double u_center = PL(cm, g, v, 0)[e];
+    {      // x pass: mode (2,1)
+      const double u_left = PL(cm, g, v, 0)[eL], u_right = PL(cm, g, v, 0)[eR], u_deriv = PL(cm, g, v, 1)[e];
+      const double l = minmod(u_deriv, (u_center - u_left), (u_right - u_center));
+      const bool drop = fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv);
+      ul[v][1][0] = l;
+      if (drop) {
+#pragma unroll
+        for (int i = 1; i < M; ++i) ul[v][i][0] = 0.0;
+        ul[v][M - 1][M - 1] = 0.0;
+      }
+    }
+    {      // y pass: mode (1,2)
+      const double u_left = PL(cm, g, v, 0)[eB], u_right = PL(cm, g, v, 0)[eT], u_deriv = PL(cm, g, v, M)[e];
+      const double l = minmod(u_deriv, (u_center - u_left), (u_right - u_center));
+      const bool drop = fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv);
+      ul[v][0][1] = l;
+      if (drop) {
+#pragma unroll
+        for (int j = 1; j < M; ++j) ul[v][0][j] = 0.0;
+        ul[v][M - 1][M - 1] = 0.0;
+      }
+    }
+  }
+  double md[4][M][M], nd[4][M][M], ch[4][M][M], wa[4], lev[4][4], rev[4][4];
+  load_modes<M>(u, g, e, md);
+  po3_prepare<M>(P, B, md, nd, wa);
+  po3_matrices(P, wa, lev, rev);
+  nodes_from_modes_el<M>(ul, B, ch);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const double c[4] = {ch[0][i][j], ch[1][i][j], ch[2][i][j], ch[3][i][j]};
+      double uc[4], ww[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = s + rev[r][k] * c[k];
+        uc[r] = s;
+      }
+      prim(P, uc, ww);
+      if (ww[0] < 1e-10) ww[0] = (double)1e-5f;
+      if (ww[3] < 1e-10) ww[3] = (double)1e-5f;
+      cons(P, ww, uc);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) nd[r][i][j] = uc[r];
+    }
+  modes_from_nodes_el<M>(nd, B, md);
+  store_modes<M>(out, g, e, md);
+}
+
 // ---- the neighbour-reading limiters in the FUSED flow (arith 0): the stage kernel writes the un-limited stage result to
 // a scratch field `u`; these kernels read it (element + 4 neighbours) and write the limited result to `out` in ONE pass, with
 // the reference's operation order (same device code as the unfused kernels above: same bits).  `out2` is the second result
@@ -1172,7 +1312,7 @@ int dg_update(wb_dg2d* h, const double* in, double* out, bool use_ctrl) {
 
 int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
   const DgCtrl* c = use_ctrl ? h->ctrl : nullptr;
-  if (h->prm.limiter_id == 2 || h->prm.limiter_id == 3 || h->prm.limiter_id == 5) WB_CHECK(dg_ensure(h, &h->E));
+  if (h->prm.limiter_id == 2 || h->prm.limiter_id == 3 || h->prm.limiter_id >= 5) WB_CHECK(dg_ensure(h, &h->E));
   dim3 b(128), gr = elem_grid(h, 128);
   if (h->g.m == 1) return WB_OK;           // every limiter returns early for mx == my == 1
   switch (h->prm.limiter_id) {
@@ -1213,6 +1353,12 @@ int dg_limiter(wb_dg2d* h, double* u, bool use_ctrl) {
         WB_LAUNCH_CHECK();
       }
       break;
+    case 6:      // pass B reads only the element's own modes of u (the neighbours through the scratch field): in place
+      DISPATCH_M(h, k_limiter_po3_a<MM><<<gr, b, 0, h->stream>>>(u, h->E, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      DISPATCH_M(h, k_limiter_po3_b<MM><<<gr, b, 0, h->stream>>>(u, h->E, u, h->g, h->phys, h->B, c));
+      WB_LAUNCH_CHECK();
+      break;
     default: break;
   }
   return WB_OK;
@@ -1250,6 +1396,15 @@ int dg_limit_into(wb_dg2d* h, double* tmp, double* out, double* out2, double k3)
       k_dg_copy_if_skipped<<<gb, 256, 0, h->stream>>>(out, tmp, h->nfield, h->ctrl);
       WB_LAUNCH_CHECK();
       DISPATCH_M(h, k_limiter_pos<MM><<<gr, b, 0, h->stream>>>(tmp, out, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      break;
+    case 6:
+      WB_CHECK(dg_ensure(h, &h->E));
+      DISPATCH_M(h, k_limiter_po3_a<MM><<<gr, b, 0, h->stream>>>(tmp, h->E, h->g, h->phys, h->B, h->ctrl));
+      WB_LAUNCH_CHECK();
+      k_dg_copy_if_skipped<<<gb, 256, 0, h->stream>>>(out, tmp, h->nfield, h->ctrl);
+      WB_LAUNCH_CHECK();
+      DISPATCH_M(h, k_limiter_po3_b<MM><<<gr, b, 0, h->stream>>>(tmp, h->E, out, h->g, h->phys, h->B, h->ctrl));
       WB_LAUNCH_CHECK();
       break;
     default:
@@ -1518,13 +1673,14 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   WB_REQUIRE(p->source >= 1 && p->source <= 3, "source must be 1..3");
   WB_REQUIRE(p->grad_phi_case == 1 || p->grad_phi_case == 2, "grad_phi_case must be 1 or 2");
   WB_REQUIRE(p->flux_id >= 0 && p->flux_id <= 3, "flux_id must be 0 (as shipped), 1 (llf1), 2 (hll2) or 3 (hllc)");
-  WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 5, "limiter_id must be 0..5 (none, ONP, HIO, 1OR, LOW, POS)");
+  WB_REQUIRE(p->limiter_id >= 0 && p->limiter_id <= 6, "limiter_id must be 0..6 (none, ONP, HIO, 1OR, LOW, POS, PO3)");
   WB_REQUIRE(p->solver_id >= 1 && p->solver_id <= 4, "solver_id must be 1..4 (RK4, SS4, EQL, DEB)");
   WB_REQUIRE(p->gamma > 1.0 && p->boxlen_x > 0 && p->boxlen_y > 0 && p->cfl > 0, "gamma>1, boxlen>0, cfl>0 required");
   WB_REQUIRE(p->arith == 0 || p->arith == 1, "arith must be 0 (fused) or 1 (reference order)");
   const int nranks = p->nranks <= 0 ? 1 : p->nranks;      // 0 (zero-initialised struct) means "no slabs"
   WB_REQUIRE(p->rank >= 0 && p->rank < nranks, "bad rank/nranks %d/%d", p->rank, p->nranks);
   WB_REQUIRE(nranks == 1 || p->arith == 0, "slab mode (nranks > 1) is built for the fused flow: arith 0");
+  WB_REQUIRE(nranks == 1 || p->limiter_id != 6 || p->bc == 1, "limiter 'PO3' wraps periodically whatever bc is: on slabs only with bc = 1 (ring of ranks)");
   WB_REQUIRE(nranks == 1 || p->ny / nranks >= 1, "each slab needs at least one row");
   int dev = 0;
   WB_CHECK(select_device(p->device, &dev));

@@ -16,8 +16,8 @@
 !            -L<repo>/fvm-source-wb_b200/wbeuler -lwbeuler -Wl,-rpath,<repo>/fvm-source-wb_b200/wbeuler -o dg2d_gpu
 !
 ! 2d/limiters.f90 is no longer needed (apply_limiter was its only caller).  Strings of the parameter module are mapped to
-! the ids of include/wbeuler.h; a limiter_type the library does not provide ('ROS', 'KRI', 'COC', 'PO3', '1DL' -- the first
-! three are undefined or abandoned in the reference itself, see DESIGN.md section 0) stops with a message instead of
+! the ids of include/wbeuler.h; a limiter_type the library does not provide ('ROS', 'KRI', 'COC', '1DL' -- undefined or
+! abandoned in the reference itself, see DESIGN.md section 0) stops with a message instead of
 ! silently running something else.
 ! (This image has no Fortran compiler, so this file is provided as the integration recipe; the C-ABI it binds is
 !  exercised by the ctypes tests, tests/test_dg2d_gpu.py and tests/test_reference_pins_gpu.py.)
@@ -128,6 +128,7 @@ contains
        case ('1OR'); p%limiter_id = 3
        case ('LOW'); p%limiter_id = 4
        case ('POS'); p%limiter_id = 5
+       case ('PO3'); p%limiter_id = 6
        case default
           write(*,*) 'wbeuler: limiter_type ', limiter_type, ' is not provided (undefined or abandoned in the reference)'
           stop 1

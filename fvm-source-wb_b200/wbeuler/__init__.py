@@ -203,7 +203,7 @@ class DG2DParams(C.Structure):
                 ("arith", C.c_int), ("rank", C.c_int), ("nranks", C.c_int)]
 
 
-LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4, "POS": 5}     # limiter_type (2d/benchmark_2d_dg.f90:1516-1555)
+LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4, "POS": 5, "PO3": 6}     # limiter_type (2d/benchmark_2d_dg.f90:1516-1555)
 SOLVERS = {"RK4": 1, "SS4": 2, "EQL": 3, "DEB": 4}                 # solver (:672-747)
 FLUXES = {"llf": 0, "llf1": 1, "hll2": 2, "hllc": 3}                                     # flux_type; 'llf' is the shipped value that matches no branch
 

@@ -133,7 +133,7 @@ typedef struct {
   int flux_id;           /* :15   0 = as shipped ('llf' matches no branch: numerical flux stays 0),
                                   1 = 'llf1' local Lax-Friedrichs, 2 = 'hll2' (compute_hllflux :1008-1026),
                                   3 = 'hllc' (compute_hllcflux :1030-1134, as shipped incl. its typos)   */
-  int limiter_id;        /* :14   0 = use_limiter .false., 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW', 5 'POS'   */
+  int limiter_id;        /* :14   0 = use_limiter .false., 1 'ONP', 2 'HIO', 3 '1OR', 4 'LOW', 5 'POS', 6 'PO3' */
   int solver_id;         /* :13   1 'RK4' SSPRK(5,4), 2 'SS4' (same after real(4) rounding), 3 'EQL' RK2,
                                   4 'DEB' forward Euler                                                  */
   int ninit;             /* :17   only used for special_boundary_conditions (ninit == 12)                */

@@ -940,6 +940,127 @@ void orc_dg2d_limiter_positivity(const orc_dg2d_params *p, double *u) {
   free(u_lim); free(nodes); free(nodes_cons);
 }
 
+/* 2d/benchmark_2d_dg.f90:2096-2177 get_matrix_decomp with k = (0, 1): the two 4x4 matrices the characteristic limiter uses
+ * (`lev` multiplies the conserved nodal state, `rev` the characteristic one; names as in the reference).  Rows are the rows
+ * of the reference's transpose(reshape((/.../))) literals. */
+static void get_matrix_decomp(const orc_dg2d_params *p, const double *ua, const double *wa, double lev[4][4], double rev[4][4]) {
+  (void)ua;
+  const double kappa = p->gamma - 1;
+  const double k1 = (double)0.f, k2 = (double)1.f;
+  const double ca = sqrt(p->gamma * wa[3] / wa[0]);
+  const double phis = sqrt(1 / 2.f * kappa * (wa[1] * wa[1] + wa[2] * wa[2]));
+  const double beta = 1.f / (2 * (ca * ca));
+  const double theta = k1 * wa[1] + k2 * wa[2];
+  const double r[4][4] = {
+      {1 - phis * phis / (ca * ca), kappa * wa[1] / (ca * ca), kappa * wa[2] / (ca * ca), -kappa / (ca * ca)},
+      {-(k2 * wa[1] - k1 * wa[2]), k2, -k1, 0.0},
+      {beta * (phis * phis - ca * theta), beta * (k1 * ca - kappa * wa[1]), beta * (k2 * ca - kappa * wa[2]), beta * kappa},
+      {beta * (phis * phis + ca * theta), -beta * (k1 * ca + kappa * wa[1]), -beta * (k2 * ca + kappa * wa[2]), beta * kappa}};
+  const double l[4][4] = {
+      {1.0, 0.0, 1.0, 1.0},
+      {wa[1], k2, wa[1] + k1 * ca, wa[1] - k1 * ca},
+      {wa[2], -k1, wa[2] + k2 * ca, wa[2] - k2 * ca},
+      {phis * phis / (kappa), k2 * wa[1] - k1 * wa[2], (phis * phis + ca * ca) / kappa + ca * theta,
+       (phis * phis + ca * ca) / kappa - ca * theta}};
+  memcpy(rev, r, sizeof(r));
+  memcpy(lev, l, sizeof(l));
+}
+/* matmul(a, x), 4x4 times 4: sum from 0 in ascending column order */
+static void matvec4(const double a[4][4], const double *x, double *y) {
+  for (int i = 0; i < 4; ++i) {
+    double s = 0.0;
+    for (int k = 0; k < 4; ++k) s = s + a[i][k] * x[k];
+    y[i] = s;
+  }
+}
+/* element averages the decomposition is built from: u(:,1,1) and the (1,1) mode of the modal PRIMITIVE variables
+ * (2d/benchmark_2d_dg.f90:2031-2040) */
+static void po3_matrices(const orc_dg2d_params *p, const double *u, const double *w_m, int ic, int jc, double lev[4][4], double rev[4][4]) {
+  double au[NV], aw[NV];
+  for (int v = 0; v < NV; ++v) { au[v] = U5(u, p, v, ic, jc, 0, 0); aw[v] = U5(w_m, p, v, ic, jc, 0, 0); }
+  get_matrix_decomp(p, au, aw, lev, rev);
+}
+/* 2d/limiters.f90:1587-1711 limiter_positivity_2 ('PO3'): minmod limiting of the linear modes of the CHARACTERISTIC
+ * variables (compute_characteristics :2021-2053: lev * nodal state, matrices from the element averages) against the periodic
+ * neighbours' means -- both passes run to nx and wrap with nx, the second with the cell indices swapped, as written --,
+ * back through rev (compute_cons_from_characteristics :2056-2093), nodal density / pressure below 1d-10 reset to the
+ * real(4) literal 1e-5, projection. */
+void orc_dg2d_limiter_positivity_2(const orc_dg2d_params *p, double *u) {
+  const int nx = p->nx, ny = p->ny, mx = p->mx, my = p->my;
+  if (mx == 1 && my == 1) return;
+  const size_t n5 = nelem5(p), nb = sizeof(double) * NV * n5;
+  double *nodes = (double *)malloc(nb), *w_nodes = (double *)malloc(nb), *w_m = (double *)malloc(nb), *chars = (double *)malloc(nb);
+  double *chars_m = (double *)malloc(nb), *u_lim = (double *)malloc(nb), *nodes_cons = (double *)malloc(nb);
+  orc_dg2d_get_nodes_from_modes(p, u, nodes);
+  orc_dg2d_compute_primitive(p, nodes, w_nodes, (long)n5);
+  orc_dg2d_get_modes_from_nodes(p, w_nodes, w_m);
+  for (int ic = 0; ic < nx; ++ic)            /* compute_characteristics */
+    for (int jc = 0; jc < ny; ++jc) {
+      double lev[4][4], rev[4][4];
+      po3_matrices(p, u, w_m, ic, jc, lev, rev);
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j) {
+          double un[NV], c[NV];
+          for (int v = 0; v < NV; ++v) un[v] = U5(nodes, p, v, ic, jc, i, j);
+          matvec4(lev, un, c);
+          for (int v = 0; v < NV; ++v) U5(chars, p, v, ic, jc, i, j) = c[v];
+        }
+    }
+  orc_dg2d_get_modes_from_nodes(p, chars, chars_m);
+  memcpy(u_lim, chars_m, nb);
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= nx; ++jc) {
+        int left = ic - 1, right = ic + 1;
+        if (ic == 1) left = nx; else if (ic == nx) right = 1;
+        double u_left = U5(chars_m, p, v, left - 1, jc - 1, 0, 0), u_right = U5(chars_m, p, v, right - 1, jc - 1, 0, 0);
+        double u_center = U5(chars_m, p, v, ic - 1, jc - 1, 0, 0), u_deriv = U5(chars_m, p, v, ic - 1, jc - 1, 1, 0);
+        double l = minmod(u_deriv, (u_center - u_left), (u_right - u_center));
+        U5(u_lim, p, v, ic - 1, jc - 1, 1, 0) = l;
+        if (fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv)) {
+          for (int i = 1; i < mx; ++i) U5(u_lim, p, v, ic - 1, jc - 1, i, 0) = 0.0;
+          U5(u_lim, p, v, ic - 1, jc - 1, mx - 1, mx - 1) = 0.0;
+        }
+      }
+  for (int v = 0; v < NV; ++v)
+    for (int ic = 1; ic <= nx; ++ic)
+      for (int jc = 1; jc <= nx; ++jc) {
+        int left = ic - 1, right = ic + 1;
+        if (ic == 1) left = nx; else if (ic == nx) right = 1;
+        double u_left = U5(chars_m, p, v, jc - 1, left - 1, 0, 0), u_right = U5(chars_m, p, v, jc - 1, right - 1, 0, 0);
+        double u_center = U5(chars_m, p, v, jc - 1, ic - 1, 0, 0), u_deriv = U5(chars_m, p, v, jc - 1, ic - 1, 0, 1);
+        double l = minmod(u_deriv, (u_center - u_left), (u_right - u_center));
+        U5(u_lim, p, v, jc - 1, ic - 1, 0, 1) = l;
+        if (fabs(l - u_deriv) > (double)0.01f * fabs(u_deriv)) {
+          for (int j = 1; j < mx; ++j) U5(u_lim, p, v, jc - 1, ic - 1, 0, j) = 0.0;
+          U5(u_lim, p, v, jc - 1, ic - 1, mx - 1, mx - 1) = 0.0;
+        }
+      }
+  orc_dg2d_get_nodes_from_modes(p, u_lim, chars);
+  for (int ic = 0; ic < nx; ++ic)            /* compute_cons_from_characteristics(chars, u_temp = the input modes, nodes_cons) */
+    for (int jc = 0; jc < ny; ++jc) {
+      double lev[4][4], rev[4][4];
+      po3_matrices(p, u, w_m, ic, jc, lev, rev);
+      for (int i = 0; i < mx; ++i)
+        for (int j = 0; j < my; ++j) {
+          double c[NV], un[NV];
+          for (int v = 0; v < NV; ++v) c[v] = U5(chars, p, v, ic, jc, i, j);
+          matvec4(rev, c, un);
+          for (int v = 0; v < NV; ++v) U5(nodes_cons, p, v, ic, jc, i, j) = un[v];
+        }
+    }
+  orc_dg2d_compute_primitive(p, nodes_cons, nodes, (long)n5);
+  for (int v = 0; v < NV; v += 3)
+    for (int ic = 0; ic < nx; ++ic)
+      for (int jc = 0; jc < ny; ++jc)
+        for (int i = 0; i < mx; ++i)
+          for (int j = 0; j < my; ++j)
+            if (U5(nodes, p, v, ic, jc, i, j) < 1e-10) U5(nodes, p, v, ic, jc, i, j) = (double)1e-5f;
+  orc_dg2d_compute_conservative(p, nodes, nodes_cons, (long)n5);
+  orc_dg2d_get_modes_from_nodes(p, nodes_cons, u);
+  free(nodes); free(w_nodes); free(w_m); free(chars); free(chars_m); free(u_lim); free(nodes_cons);
+}
+
 /* 2d/benchmark_2d_dg.f90:1516-1555 apply_limiter */
 void orc_dg2d_apply_limiter(const orc_dg2d_params *p, double *u) {
   switch (p->limiter_id) {
@@ -948,6 +1069,7 @@ void orc_dg2d_apply_limiter(const orc_dg2d_params *p, double *u) {
     case 3: orc_dg2d_compute_limiter(p, u); break;
     case 4: orc_dg2d_limiter_low_order(p, u); break;
     case 5: orc_dg2d_limiter_positivity(p, u); break;
+    case 6: orc_dg2d_limiter_positivity_2(p, u); break;
     default: break;
   }
 }

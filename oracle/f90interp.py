@@ -788,16 +788,20 @@ def _pow_real(a, b):
 
 
 def _minmax(args, is_max):
+    """MAX / MIN as gfortran expands them on x86-64 (trans-intrinsic.c, gfc_conv_intrinsic_minmax):
+    mvar = a1;  if (a2 .op. mvar || isnan(mvar)) mvar = a2;  ...   -- a NaN is dropped whichever side it comes from."""
     r = args[0]
     for b in args[1:]:
         r, b, _ = _promote(r, b)
         if isinstance(r, np.ndarray) or isinstance(b, np.ndarray):
-            r = np.where(b > r, b, r) if is_max else np.where(b < r, b, r)
+            nan_r = np.isnan(r) if np.asarray(r).dtype.kind == "f" else False
+            r = np.where((b > r) | nan_r, b, r) if is_max else np.where((b < r) | nan_r, b, r)
         else:
+            nan_r = (r != r)
             if is_max:
-                r = b if b > r else r
+                r = b if (b > r or nan_r) else r
             else:
-                r = b if b < r else r
+                r = b if (b < r or nan_r) else r
     return r
 
 

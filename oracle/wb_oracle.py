@@ -136,7 +136,7 @@ class DG2DParams(C.Structure):
                 ("eta", C.c_double)]
 
 
-LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4, "POS": 5}
+LIMITERS = {"none": 0, "ONP": 1, "HIO": 2, "1OR": 3, "LOW": 4, "POS": 5, "PO3": 6}
 SOLVERS = {"RK4": 1, "SS4": 2, "EQL": 3, "DEB": 4}
 FLUXES = {"llf": 0, "llf1": 1, "hll2": 2, "hllc": 3}   # 'llf' is the shipped default that matches no branch (numerical flux stays 0)
 

@@ -247,6 +247,37 @@ def dg2d_limiters():
             np.savez_compressed(os.path.join(HERE, "ref_dg2d_limiters.npz"), **out)
 
 
+def dg2d_po3():
+    """limiter_type 'PO3' (limiter_positivity_2, 2d/limiters.f90:1587-1711): characteristic-variable minmod + nodal reset,
+    on rough data and on smooth data -> ref_dg2d_po3.npz"""
+    out = {}
+    rng = np.random.default_rng(1587)
+    for n, m, bc, rough in ((3, 3, 1, True), (4, 2, 2, True), (4, 3, 1, False), (3, 4, 3, True), (5, 2, 1, False)):
+        tag = f"po3_n{n}_m{m}_bc{bc}_{'rough' if rough else 'smooth'}"
+        t0 = time.time()
+        it = dg2d_interp(nx=n, ny=n, mx=m, my=m, bc=bc, limiter_type="PO3", flux_type="llf1", ninit=1)
+        modes = F(4, n, n, m, m)
+        modes[0, :, :, 0, 0] = 1.0 + 0.5 * rng.random((n, n))
+        modes[1, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n))
+        modes[2, :, :, 0, 0] = 0.3 * rng.standard_normal((n, n))
+        modes[3, :, :, 0, 0] = 2.5 + rng.random((n, n))
+        hi = (0.08 if rough else 0.004) * rng.standard_normal((4, n, n, m, m))
+        hi[:, :, :, 0, 0] = 0.0
+        modes += hi
+        if rough:
+            modes[0, 0, 1, 0, 1] = 0.9            # density dips below zero at a node of cell (1,2)
+            modes[3, 1, 0, 1, 0] = -2.0           # energy (pressure) dips in cell (2,1)
+        inp = modes.copy(order="F")
+        it.call("apply_limiter", modes)
+        out[f"{tag}/meta"] = np.array([n, m, bc])
+        out[f"{tag}/limiter"] = np.array("PO3")
+        out[f"{tag}/in"] = C(inp)
+        out[f"{tag}/out"] = C(modes)
+        note_calls(out, tag, it)
+        print(f"dg2d PO3 {tag}: {time.time() - t0:.1f} s, changed {np.abs(modes - inp).max():.3e}, nan {int(np.isnan(modes).sum())}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "ref_dg2d_po3.npz"), **out)
+
+
 def dg2d_other_limiters():
     """The limiter_type branches of apply_limiter that are NOT built, and why -- observed by running them:
     'ROS' and 'KRI' index out of bounds / pass a rank-1 section to a rank-5 dummy (undefined behaviour in the reference),

@@ -232,6 +232,20 @@ def test_dg2d_oracle_equals_reference_source(oracle, tag):
         assert same(un, g[f"{tag}/nodes_evolved"]), maxdiff(un, g[f"{tag}/nodes_evolved"])
 
 
+@pytest.mark.parametrize("tag", tags("ref_dg2d_po3.npz"))
+def test_dg2d_po3_limiter_equals_reference_source(oracle, tag):
+    """limiter_type 'PO3' = limiter_positivity_2 (2d/limiters.f90:1587-1711) with compute_characteristics,
+    compute_cons_from_characteristics and get_matrix_decomp (2d/benchmark_2d_dg.f90:2021-2177), executed from the reference
+    text on rough and on smooth modes.  Where an element's mean pressure is negative the sound speed of its matrix
+    decomposition is NaN and the reference returns NaN for that element: reproduced (same doubles, same NaNs)."""
+    g = gold("ref_dg2d_po3.npz")
+    n, m, bc = (int(v) for v in g[f"{tag}/meta"])
+    p = oracle.dg2d_params(nx=n, ny=n, mx=m, my=m, bc=bc, limiter="PO3", flux="llf1", ninit=1)
+    v = oracle.dg2d_apply_limiter(p, g[f"{tag}/in"])
+    assert np.array_equal(v, g[f"{tag}/out"], equal_nan=True), maxdiff(v, g[f"{tag}/out"])
+    assert not np.array_equal(v, g[f"{tag}/in"], equal_nan=True)
+
+
 @pytest.mark.parametrize("tag", tags("ref_dg2d_ics.npz"))
 def test_dg2d_initial_conditions_equal_reference_source(oracle, tag):
     """get_initial_conditions (2d/benchmark_2d_dg.f90:122-466), cases 3..12 -- Riemann problems, isentropic vortex, the two
@@ -308,7 +322,7 @@ def test_limiter_branches_that_are_not_built_and_why():
     interpreted reference does with the other five (tests/golden/ref_dg2d_other_limiters.json): 'ROS' indexes u_avg(.., 0),
     'KRI' passes a 4-element section where a whole 5-D array is expected, '1DL' calls a subroutine that does not exist --
     undefined behaviour or no program at all; 'COC' ends by overwriting the nodal pressure with the literal 10e-5 (an
-    abandoned experiment); 'PO3' runs (characteristic-variable minmod) and is the one candidate left for widening."""
+    abandoned experiment); 'PO3' runs (characteristic-variable minmod) and is built (test_dg2d_po3_limiter_equals_reference_source)."""
     import json
     f = json.load(open(os.path.join(HERE, "golden", "ref_dg2d_other_limiters.json")))
     for k, v in f.items():

@@ -129,6 +129,19 @@ def test_dg2d_limiters_on_rough_data_equal_reference_source_bitwise(wb, tag, ari
     assert np.array_equal(v, g[f"{tag}/out"]), rel(v, g[f"{tag}/out"])
 
 
+@pytest.mark.parametrize("arith", [1, 0])
+@pytest.mark.parametrize("tag", tags("ref_dg2d_po3.npz"))
+def test_dg2d_po3_limiter_equals_reference_source_bitwise(wb, tag, arith):
+    """limiter_type 'PO3' (limiter_positivity_2, 2d/limiters.f90:1587-1711): the two-pass CUDA limiter in the unfused (arith 1)
+    and in the fused (arith 0) flow against the vectors produced by executing the reference text -- same doubles, and the
+    same NaNs where an element's mean pressure is negative (the reference's matrix decomposition takes sqrt of it)."""
+    g = gold("ref_dg2d_po3.npz")
+    n, m, bc = (int(v) for v in g[f"{tag}/meta"])
+    with wb.DG2D(nx=n, ny=n, mx=m, my=m, bc=bc, limiter="PO3", flux="llf1", ninit=1, device=0, arith=arith) as s:
+        v = s.apply_limiter(g[f"{tag}/in"])
+    assert np.array_equal(v, g[f"{tag}/out"], equal_nan=True), rel(np.nan_to_num(v), np.nan_to_num(g[f"{tag}/out"]))
+
+
 # ------------------------------------------------------------------------------------------------ 1D FV
 @pytest.mark.parametrize("tag", tags("ref_fv1d.npz", "fvm_"))
 def test_fvm1d_cuda_equals_reference_source_bitwise(wb, tag):
