@@ -234,7 +234,7 @@ void format_1pe12_5(double v, char out[16]) {
   const int ex = atoi(e + 1);
   if (ex >= 100 || ex <= -100) {                    // Fortran drops the letter: d.ddddd+eee
     *e = 0;
-    char t2[32];
+    char t2[64];
     snprintf(t2, sizeof(t2), "%s%c%03d", tmp, ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
     snprintf(out, 16, "%12.12s", t2);
   } else {

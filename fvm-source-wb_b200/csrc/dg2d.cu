@@ -1195,7 +1195,6 @@ __global__ void k_dg_ctrl_init(DgCtrl* ctrl, double tend, int max_iter, int rese
 
 #include "dg2d_fast.cuh"
 #include "dg2d_tma.cuh"
-#include "dg2d_march.cuh"
 
 namespace wb { namespace dg {
 // k_dg_stage_split lives in its own translation unit (dg2d_split.cu)
@@ -1235,8 +1234,7 @@ struct wb_dg2d {
   int rank = 0, nranks = 1, nyl = 0;
   // TMA-staged stage kernel: one 3-D tensor map (column, row, plane) per state buffer
   bool tma_ok = false;
-  bool march_ok = false;       // marching kernel (every face once): nx even, nx >= DGT_W
-  int march_rows = 32;         // rows per strip
+  int march_rows = 32;         // rows per strip of k_dg_stage_split
   bool split_ok = false;       // k_dg_stage_split (element split over four threads, every face once): nx % 32 == 0
   const double* map_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
   CUtensorMap map[4];
@@ -1527,40 +1525,6 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
     WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g, h->phys, h->FB, h->ctrl,
                                 onp, h->march_rows, 0, h->g.ny, h->stream));
     wb::g_launches.fetch_sub(1);      // counted again by the WB_LAUNCH_CHECK below
-  } else if (m_in && h->march_ok) {
-    dim3 b(32), gr((unsigned)((h->g.nx + DGM_COLS - 1) / DGM_COLS), (unsigned)((h->g.ny + h->march_rows - 1) / h->march_rows));
-    DISPATCH_M(h, {
-      auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_march<MM, true> : k_dg_stage_march<MM, false>;
-      static bool configured_dev[64][2] = {};      // function attributes are per device
-      bool* configured = configured_dev[h->dev & 63];
-      if (!configured[h->phys.flux_id >= 2]) {
-        // 8 resident warps (255 registers) x 2 row slots: no more shared memory than that, the rest stays L1 for the spills
-        const char* envc = getenv("WB_DG2D_CARVEOUT");
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : 80));
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
-        configured[h->phys.flux_id >= 2] = true;
-      }
-      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
-                                                          h->phys, h->FB, h->ctrl, onp, h->march_rows);
-    });
-  } else if (m_in && h->tma_ok && h->g.nx % 32 == 0) {
-    dim3 b(32), gr((unsigned)(h->g.ne / 32));
-    DISPATCH_M(h, {
-      auto kern = (h->phys.flux_id >= 2) ? k_dg_stage_tma<MM, true> : k_dg_stage_tma<MM, false>;
-      static bool configured_dev[64][2] = {};      // function attributes are per device
-      bool* configured = configured_dev[h->dev & 63];
-      if (!configured[h->phys.flux_id >= 2]) {
-        // 8 resident one-warp blocks (255 registers) need 8 x 21.9 KB = 175 KB of shared memory: ask for the 196 KB
-        // configuration, not the maximum -- the 60 KB of L1 that remain serve the spills and the RK operand loads.
-        // Measured at 4096^2, order 3 (element-stages/s): carve-out 100 %: 2.83e9, 77-85 %: 3.02e9, 70 % (7 blocks): 2.71e9
-        const char* envc = getenv("WB_DG2D_CARVEOUT");
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : 80));
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_tma_smem_bytes<MM>()));
-        configured[h->phys.flux_id >= 2] = true;
-      }
-      kern<<<gr, b, dg_tma_smem_bytes<MM>(), h->stream>>>(*m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g,
-                                                          h->phys, h->FB, h->ctrl, onp);
-    });
   } else {
     dim3 b(64), gr = elem_grid(h, 64);
     if (h->phys.flux_id >= 2) {
@@ -1778,16 +1742,13 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
     cudaMemsetAsync(h->fz, 0, (size_t)g.nm * g.ne, h->stream);
   }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { set_error("init failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
-  {      // TMA-staged stage kernel: blocks of 32 elements must lie in one row
+  {      // k_dg_stage_split: TMA-staged rows, blocks of 32 elements of a row x 4 variables (WB_DG2D_TMA=0: global-memory kernel)
     const char* env = getenv("WB_DG2D_TMA");
-    const char* envm = getenv("WB_DG2D_MARCH");
     const char* envr = getenv("WB_DG2D_ROWS");
-    const bool want_march = p->arith == 0 && g.nx % 2 == 0 && g.nx >= DGT_W && (envm && atoi(envm) == 1) && !(env && atoi(env) == 0);
     if (envr && atoi(envr) > 0) h->march_rows = atoi(envr);
     // a TMA box may be wider than the tensor (nx = 32 < DGT_W = 36: the columns outside are zero-filled like any other
     // out-of-range column; measured bit-identical to the global-memory path on B200), so 32 is the smallest grid
-    const int min_nx = 32;
-    if (want_march || (p->arith == 0 && g.nx % 32 == 0 && g.nx >= min_nx && !(env && atoi(env) == 0))) {
+    if (p->arith == 0 && g.nx % 32 == 0 && g.nx >= 32 && !(env && atoi(env) == 0)) {
       const double* bufs4[4] = {h->du, h->A, h->Bf, h->C};
       for (int k = 0; k < 4; ++k) {
         int st = dg_make_map(h, bufs4[k], &h->map[k]);
@@ -1795,9 +1756,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
         h->map_ptr[k] = bufs4[k];
       }
       h->tma_ok = true;
-      h->march_ok = want_march;
-      const char* envs = getenv("WB_DG2D_SPLIT");
-      h->split_ok = !want_march && g.nx % 32 == 0 && !(envs && atoi(envs) == 0);
+      h->split_ok = true;
     }
   }
   *out = h;
@@ -1847,8 +1806,6 @@ const char* wb_dg2d_stage_kernel(const wb_dg2d* h) {
   if (!h) return "";
   if (!dg_use_fused(h)) return "reference";
   if (h->tma_ok && h->split_ok) return "split";
-  if (h->tma_ok && h->march_ok) return "march";
-  if (h->tma_ok && h->g.nx % 32 == 0) return "tma";
   return "fast";
 }
 
@@ -1983,6 +1940,7 @@ int wb_dg2d_upload(wb_dg2d* h, const double* u_nodes, const double* x, const dou
   WB_LAUNCH_CHECK();
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
   WB_LAUNCH_CHECK();
+  if (h->prm.limiter_id >= 2) WB_CHECK(dg_exchange(h, h->du));      // neighbour-reading limiters need the ghost rows
   WB_CHECK(dg_limiter(h, h->du, false));                                                         // :659
   WB_CHECK(dg_exchange(h, h->du));
   h->resident = true;
@@ -2027,6 +1985,7 @@ int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
   WB_LAUNCH_CHECK();
   k_dg_ctrl_init<<<1, 1, 0, h->stream>>>(h->ctrl, 0.0, -1, 1);
   WB_LAUNCH_CHECK();
+  if (h->prm.limiter_id >= 2) WB_CHECK(dg_exchange(h, h->du));      // neighbour-reading limiters need the ghost rows
   WB_CHECK(dg_limiter(h, h->du, false));                                                          // :659
   WB_CHECK(dg_exchange(h, h->du));
   h->resident = true;

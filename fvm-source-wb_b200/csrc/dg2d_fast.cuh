@@ -1,4 +1,6 @@
-// Fused DG 2D RK-stage kernel ("arith 0"): compute_update + RK combination + element-local positivity limiter
+// Fused DG 2D RK-stage arithmetic ("arith 0") and its one-thread-per-element kernel k_dg_stage_fast (any grid; the
+// production kernel for nx % 32 == 0 is k_dg_stage_split, dg2d_split.cuh, which runs the same arithmetic with the element
+// split over four threads): compute_update + RK combination + element-local positivity limiter
 // ('ONP') in ONE launch per stage.  Same formulas as the reference-order kernels of dg2d.cu, but
 //   * every tensor-product contraction is sum-factorised (2 x M^3 instead of M^4 multiply-adds per variable),
 //     with the quadrature weights folded into the basis tables (Pw = P*w, dPw = P'*w);
@@ -379,7 +381,7 @@ __device__ __forceinline__ void dg_stage_rest(Src& src, const Modes& d, double (
                                               const DgPhys& P, const FastBasis& B, const DgCtrl* __restrict__ ctrl, int apply_onp,
                                               size_t e);
 
-// the element's own modes held in registers (k_dg_stage_fast / k_dg_stage_tma)
+// the element's own modes held in registers (k_dg_stage_fast)
 template <int M>
 struct RegModes {
   const double (&d)[4][M][M];

@@ -344,21 +344,6 @@ def test_larger_grid_properties(wb, oracle):
 
 
 
-def test_tma_staged_kernel_equals_the_global_memory_one(wb, oracle, monkeypatch):
-    """Same arithmetic, different data path: with nx % 32 == 0 the modes travel through TMA + shared memory; switching that
-    off (WB_DG2D_TMA=0) must give the same bits."""
-    monkeypatch.setenv("WB_DG2D_SPLIT", "0")       # the one-thread-per-element TMA kernel (superseded by k_dg_stage_split)
-    p, s, x, y = mk(oracle, wb, 64, 3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1)
-    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
-    with s:
-        a, it, t, dt = s.evolve(u0, x, y, 1.0, 3)
-        assert s.stage_kernel() == "tma"
-    monkeypatch.setenv("WB_DG2D_TMA", "0")
-    with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, flux="llf1", limiter="ONP", solver="RK4", ninit=1) as s2:
-        b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 3)
-    assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
-
-
 @pytest.mark.parametrize("nx,mx,bc,kw", [
     (64, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
     (64, 3, 2, dict(flux="llf1", limiter="ONP", solver="SS4", ninit=2, source=2, grad_phi_case=1)),   # gravity, clamped
@@ -417,37 +402,12 @@ def test_split_kernel_limiter_point_evaluations(wb, oracle, monkeypatch, mx):
             assert it == it3 == 2 and field_err(a, ref) <= 1e-10
 
 
-@pytest.mark.parametrize("nx,mx,bc,kw", [
-    (64, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
-    (62, 3, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),        # 31-column strips end exactly at nx
-    (40, 2, 2, dict(flux="llf1", limiter="ONP", solver="EQL", ninit=3)),        # ragged last strip, clamped boundaries
-    (96, 3, 3, dict(flux="hllc", limiter="none", solver="DEB", ninit=5)),
-    (38, 4, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1, source=2, grad_phi_case=1)),
-    (36, 1, 1, dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1)),
-])
-@pytest.mark.parametrize("rows", [32, 5, 1])
-def test_marching_kernel_equals_the_two_sided_ones(wb, oracle, monkeypatch, nx, mx, bc, kw, rows):
-    """k_dg_stage_march evaluates every face once (left face by the lane, right face from lane+1, top flux carried to the
-    next row); the traces, the LLF call and the accumulation order are those of k_dg_stage_fast, so the bits must be too.
-    rows = strip height (1: every row is a first row, 5: ragged strips, 32: default)."""
-    p, _, x, y = mk(oracle, wb, nx, mx, arith=0, bc=bc, **kw)
-    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
-    monkeypatch.setenv("WB_DG2D_ROWS", str(rows))
-    monkeypatch.setenv("WB_DG2D_MARCH", "1")       # opt-in kernel (measured slower than the TMA-staged one, DESIGN.md 4.3)
-    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s:
-        a, it, t, dt = s.evolve(u0, x, y, 1.0, 2)
-    monkeypatch.setenv("WB_DG2D_TMA", "0")
-    with wb.DG2D(nx=nx, ny=nx, mx=mx, my=mx, arith=0, bc=bc, **kw) as s2:
-        b, it2, t2, dt2 = s2.evolve(u0, x, y, 1.0, 2)
-    assert np.all(np.isfinite(a))
-    assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
-
-
 def test_large_grid_properties(wb, monkeypatch):
     """2048^2 elements, order 3, llf1 + ONP + SSPRK(5,4), device-initialised periodic pulse (BASELINE config 4 is the same
     workload at 8192^2 = 19 GB per array; this size keeps the host copies at 1.2 GB).  No CPU run involved:
     (1) the fused production kernel agrees with the reference-order kernels to 1e-12 after a full step;
-    (2) the four data paths of the fused stage (split over four threads, TMA-staged, marching, global loads) give the same bits;
+    (2) the two data paths of the fused stage (k_dg_stage_split: element split over four threads, rows staged by TMA;
+        k_dg_stage_fast: one thread per element, global loads) give the same bits;
     (3) the pulse's x <-> y mirror symmetry (momenta swapped, mode indices transposed) is kept to rounding;
     (4) the mean density changes only by the ~1e-8/step drift of the real(4) SSPRK weights (reference behaviour)."""
     n, m = 2048, 3
@@ -467,12 +427,7 @@ def test_large_grid_properties(wb, monkeypatch):
     assert dt == dt_ref
     assert field_err(fast, ref) <= 1e-12
     del ref
-    monkeypatch.setenv("WB_DG2D_SPLIT", "0")      # `fast` came from k_dg_stage_split; now the one-thread-per-element kernels
-    assert np.array_equal(run(0)[0], fast)
-    monkeypatch.setenv("WB_DG2D_MARCH", "1")
-    assert np.array_equal(run(0)[0], fast)
-    monkeypatch.setenv("WB_DG2D_MARCH", "0")
-    monkeypatch.setenv("WB_DG2D_TMA", "0")
+    monkeypatch.setenv("WB_DG2D_TMA", "0")        # `fast` came from k_dg_stage_split; now the global-memory kernel
     assert np.array_equal(run(0)[0], fast)
     # modes[b][a][j][i][v]: mirror = swap (a,b), (i,j) and the two momenta
     mirror = fast.transpose(1, 0, 3, 2, 4)[..., [0, 2, 1, 3]]

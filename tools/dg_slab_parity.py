@@ -44,8 +44,8 @@ for kw in CASES:
     full = np.concatenate(parts, axis=2)
     same = np.array_equal(full, ref) and it == it1 and t == t1 and dt == dt1
     msg = f"rank {rank}/{world} {kw}: slab == single-GPU bitwise: {same} (iters {it}, t {t:.6e}, dt {dt:.6e})"
-    if rank == 0:
-        oref = o.dg2d_evolve(p, u0, x, y, 1.0, steps)[0]
+    if rank == 0 and kw["limiter"] != "HIO":      # 'HIO' branches on exact equality of rounded numbers: only bit-identical
+        oref = o.dg2d_evolve(p, u0, x, y, 1.0, steps)[0]      # inputs reproduce the oracle's trajectory (tests/test_dg2d_gpu.py)
         err = np.abs(full - oref).max() / np.abs(oref).max()
         msg += f"; vs oracle rel Linf {err:.2e}"
         same = same and err <= 1e-12
