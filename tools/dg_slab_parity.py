@@ -26,7 +26,7 @@ CASES = [dict(flux="llf1", limiter="ONP", solver="RK4", ninit=1, bc=1),
          dict(flux="llf1", limiter="HIO", solver="RK4", ninit=1, bc=1),
          dict(flux="llf1", limiter="HIO", solver="RK4", ninit=3, bc=2),
          dict(flux="llf1", limiter="1OR", solver="EQL", ninit=4, bc=2),
-         dict(flux="llf1", limiter="POS", solver="EQL", ninit=3, bc=1),
+         dict(flux="llf1", limiter="POS", solver="EQL", ninit=1, bc=1),      # (the Riemann problem ninit=3 on the periodic box collapses dt at order 2: no reference point)
          dict(flux="llf1", limiter="LOW", solver="DEB", ninit=4, bc=3)]
 for kw in CASES:
     p = o.dg2d_params(nx=n, ny=n, mx=m, my=m, **kw)
