@@ -389,7 +389,7 @@ __device__ __forceinline__ FaceFlux face_llf(const Phys& P, double rf, double Ef
   double br = rf + hr, bE = Ef + hE;   // high side ("u_left(i)"   / "u_bottom(j)")
   fast::Eval a = fast::eval_state(P, ar, ln, lt, aE);
   fast::Eval b = fast::eval_state(P, br, hn, ht, bE);
-  const double cm = fmax(a.spd, b.spd);
+  const double cm = fast::max_speed2(a.spd, b.spd);
   FaceFlux o;
   // 2 x [0.5*(f_right+f_left)+0.5*cmax*(uleft-uright)]   (benchmark_2d.f90:366): the two halvings are exact, so they
   // are folded into 0.5/dx (Phys::hodx, hody); the remaining a*b+c is one fma (<= 1 ulp of an O(1) flux)
@@ -410,7 +410,7 @@ __device__ __forceinline__ void faces_llf2(const Phys& P, const FaceIn& a, const
   const double mt[4] = {a.lt, a.ht, b.lt, b.ht};
   fast::Eval ev[4];
   fast::eval_states<4, EXACT>(P, rho, mn, mt, E, ev, ok);
-  const double cma = fmax(ev[0].spd, ev[1].spd), cmb = fmax(ev[2].spd, ev[3].spd);
+  const double cma = fast::max_speed2(ev[0].spd, ev[1].spd), cmb = fast::max_speed2(ev[2].spd, ev[3].spd);
   oa.f0 = fma(cma, rho[0] - rho[1], ev[1].f0 + ev[0].f0);
   ob.f0 = fma(cmb, rho[2] - rho[3], ev[3].f0 + ev[2].f0);
   oa.fn = fma(cma, a.ln - a.hn, (ev[1].fn + ev[0].fn) - P.gm1x2 * a.Ef);
@@ -818,13 +818,15 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
       static bool configured_dev[64] = {};      // function attributes are per device
       bool& configured = configured_dev[h->dev & 63];
       auto kern = k_stage_tma<MODE, MARCH_MIN_BLOCKS>;
-      if (!configured) {       // 4 CTAs x <= 37 KiB of ring buffers per SM
+      if (!configured) {       // 16 warps x <= 9.3 KiB of ring buffers per SM
         const char* envc = getenv("WB_FV2D_CARVEOUT");
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, envc ? atoi(envc) : (int)cudaSharedmemCarveoutMaxShared));
-        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MARCH_WARPS * tma_warp_bytes(MODE)));
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_WARPS * tma_warp_bytes(MODE)));
         configured = true;
       }
-      kern<<<gr, b, MARCH_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, m_base ? *m_base : *m_in, A, h->g, h->phys, R);
+      const int Rt = std::min(R, TMA_MAX_ROWS);      // the per-warp y tables hold one strip
+      const dim3 bt(TMA_WARPS * 32), gt((ncols + TMA_WARPS - 1) / TMA_WARPS, (A.row_end - A.row_begin + Rt - 1) / Rt);
+      kern<<<gt, bt, TMA_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, m_base ? *m_base : *m_in, A, h->g, h->phys, Rt);
     } else {
       k_stage_march<MODE, MARCH_MIN_BLOCKS><<<gr, b, 0, stream>>>(A, h->g, h->phys, R);
     }

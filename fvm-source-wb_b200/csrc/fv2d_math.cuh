@@ -95,6 +95,11 @@ __device__ __forceinline__ void source(const double w[4], double s[4]) {
 
 namespace fast {
 
+// max of two wave speeds (finite, non-negative): one compare and a select.  fmax() costs nine instructions on sm_100a (there
+// is no FP64 min/max instruction: DSETP.MAX plus the NaN and signed-zero fix-ups), this costs three and gives the same
+// number for every pair of finite values; a NaN in `b` still propagates, and a NaN state poisons the fluxes anyway.
+__device__ __forceinline__ double max_speed2(double a, double b) { return a > b ? a : b; }
+
 // 1/x: MUFU.RCP64H seed (~2^-20) + one cubic Newton step; relative error ~2^-53.
 __device__ __forceinline__ double rcp(double x) {
   double y;
@@ -169,11 +174,13 @@ __device__ __forceinline__ void eval_states(const Phys& P, const double (&rho)[N
     }
   } else {
     constexpr int HI_OK = 0x3DDB7CDF + 1;      // high word of 1e-10 is 0x3DDB7CDF
+    int lo = 0x7fffffff;                       // signed minimum of the high words: negative values are caught as well
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      ok = ok && (__double2hiint(p[k]) >= HI_OK) && (__double2hiint(rho[k]) >= HI_OK);
+      lo = min(lo, min(__double2hiint(p[k]), __double2hiint(rho[k])));
       c2[k] = (P.gamma * p[k]) * r[k];
     }
+    ok = ok && (lo >= HI_OK);
   }
 #pragma unroll
   for (int k = 0; k < N; ++k) qa[k] = q[k] + 1e-300;

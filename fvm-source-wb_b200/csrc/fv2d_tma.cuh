@@ -31,8 +31,18 @@ constexpr int TMA_DEPTH = 4;                          // state ring: rows p, p+1
 #endif
 constexpr int TMA_BDEPTH = TMA_BDEPTH_N;             // u^n ring (stage 2): row q in use, the others in flight
 constexpr int TMA_BARS_B = 128;
+constexpr int TMA_MAX_ROWS = 64;                      // rows per strip the per-warp y tables are sized for
+constexpr int TMA_TAB_N = TMA_MAX_ROWS + 4;           // entries per table
+constexpr int TMA_TAB_B = 2 * TMA_TAB_N * 8;          // exp(-a yf), exp(-a yc) of the strip's rows (read with LDS, one per row)
+// Warps per CTA.  The warps never talk to each other, so a CTA is ONE warp: its column block then follows from blockIdx
+// alone, every TMA operand (box coordinates, slot and barrier addresses) is provably warp-uniform, and ptxas issues
+// UTMALDG straight from uniform registers instead of wrapping it in an ELECT / R2UR / BRA.U.ANY uniformisation loop.
+#ifndef TMA_WARPS_N
+#define TMA_WARPS_N 1
+#endif
+constexpr int TMA_WARPS = TMA_WARPS_N;
 __host__ __device__ constexpr int tma_warp_bytes(int mode) {
-  return TMA_DEPTH * TMA_SLOT_B + (mode == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0) + TMA_BARS_B;
+  return TMA_DEPTH * TMA_SLOT_B + (mode == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0) + TMA_BARS_B + TMA_TAB_B;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,7 +80,10 @@ struct TmaCtx {
   double exf_i, exc_i, dt;
   const unsigned char* wsm;     // this warp's shared-memory region (generic pointer)
   uint32_t ring, bring, bars;   // shared-space addresses: state ring, u^n ring, mbarriers
+  const double* tab;            // y tables of the strip: tab[q] = exp(-a yf(jb+q+1)), tab[TMA_TAB_N + q] = exp(-a yc(jb+q))
 };
+
+static_assert(TMA_DEPTH == 4 && TMA_BDEPTH == 4, "the slot arithmetic of the unrolled loop assumes rings of four");
 
 // lane 0: arm slot p & (DEPTH-1) and ask TMA for local row jb-1+p (clamped like the LDG kernel: ghost rows exist
 // only where a neighbouring slab does)
@@ -88,9 +101,35 @@ __device__ __forceinline__ void tma_issue_base(const TmaCtx& c, const CUtensorMa
   mbar_expect_tx(bar, TMA_IN_B);
   tma_load_3d(dst, m_base, c.x0, c.jb + q + 1, 0, bar);
 }
-// box column `col` (c.own = this lane's cell, c.own - 1 = its left neighbour) of ring row p
-__device__ __forceinline__ Cell tma_read_row(const TmaCtx& c, int p, int col) {
-  const unsigned char* sp = c.wsm + (p & (TMA_DEPTH - 1)) * TMA_SLOT_B + col * 8;
+// The main loop is unrolled four rows deep, so a row knows S = q & 3 at compile time and every slot below is
+// `base + immediate`; S = -1 (the ragged tail of a strip, the cold exact path) computes the slots from q.
+template <int S> __device__ __forceinline__ int ring_slot(int q, int ahead) {
+  return (S >= 0) ? ((S + ahead) & 3) : ((q + ahead) & 3);
+}
+// Re-arm for row q: ring row q (slot q & 3, dead since the previous row) takes ring row q + DEPTH, the slot of u^n row
+// q - 1 takes u^n row q + 3.  No lower clamp here: jb - 1 + p >= 3 > jmin for p >= DEPTH.
+// Everything but the lane test is computed by the whole warp (row, arm): values the compiler can see are warp-uniform live
+// in uniform registers, and UTMALDG then needs no uniformisation loop.
+template <int MODE, int S>
+__device__ __forceinline__ void tma_rearm(const TmaCtx& c, const CUtensorMap* m_in, const CUtensorMap* m_base, int q) {
+  const int row = min(c.jb + q + TMA_DEPTH - 1, c.jmax) + 1;
+  const bool arm = (q + TMA_DEPTH < c.np), arm_b = (MODE == 2) && (q >= 1) && (q + 3 < c.nrows);
+  if (c.lane == 0 && arm) {
+    const int s = ring_slot<S>(q, 0);
+    const uint32_t bar = c.bars + 8u * s, dst = c.ring + (uint32_t)(s * TMA_SLOT_B);
+    mbar_expect_tx(bar, TMA_IN_B);
+    tma_load_3d(dst, m_in, c.x0, row, 0, bar);
+  }
+  if (MODE == 2 && c.lane == 0 && arm_b) {
+    const int s = ring_slot<S>(q, 3);
+    const uint32_t bar = c.bars + 8u * (TMA_DEPTH + s), dst = c.bring + (uint32_t)(s * TMA_IN_PAD);
+    mbar_expect_tx(bar, TMA_IN_B);
+    tma_load_3d(dst, m_base, c.x0, c.jb + q + 4, 0, bar);
+  }
+}
+// box column `col` (c.own = this lane's cell, c.own - 1 = its left neighbour) of the ring slot s
+__device__ __forceinline__ Cell tma_read_slot(const TmaCtx& c, int s, int col) {
+  const unsigned char* sp = c.wsm + col * 8 + s * TMA_SLOT_B;
   Cell r;
   r.d0 = *reinterpret_cast<const double*>(sp);
   r.d1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
@@ -102,16 +141,16 @@ __device__ __forceinline__ Cell tma_read_row(const TmaCtx& c, int p, int col) {
 // Arithmetic of one row (strip-relative index q, ring row p = q+1, local row j = jb+q): reads row j+1 (own column),
 // row j (left neighbour) and u^n of row j from the ring; (cur,Gb) in; nxt, Gt and the new cell values out.
 struct RowOut { Cell nxt; FaceFlux Gt; double n0, n1, n2, n3; };
-template <int MODE, bool EXACT>
+template <int MODE, bool EXACT, int S>
 __device__ __forceinline__ RowOut tma_row_math(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c, int q,
                                                const Cell& cur, const FaceFlux& Gb, double ey, double ex, bool& ok) {
-  const int p = q + 1, j = c.jb + q;
+  const int j = c.jb + q;
   RowOut o;
-  o.nxt = tma_read_row(c, p + 1, c.own);
-  const Cell lft = tma_read_row(c, p, c.own - 1);
+  o.nxt = tma_read_slot(c, ring_slot<S>(q, 2), c.own);
+  const Cell lft = tma_read_slot(c, ring_slot<S>(q, 1), c.own - 1);
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (MODE == 2) {
-    const unsigned char* sp = c.wsm + TMA_DEPTH * TMA_SLOT_B + (q & (TMA_BDEPTH - 1)) * TMA_IN_PAD + c.own * 8;
+    const unsigned char* sp = c.wsm + c.own * 8 + (TMA_DEPTH * TMA_SLOT_B + ring_slot<S>(q, 0) * TMA_IN_PAD);
     b0 = *reinterpret_cast<const double*>(sp);
     b1 = *reinterpret_cast<const double*>(sp + TMA_PLANE_B);
     b2 = *reinterpret_cast<const double*>(sp + 2 * TMA_PLANE_B);
@@ -140,32 +179,31 @@ template <int MODE>
 __device__ __noinline__ RowOut tma_row_exact(StageArgs A, Grid g, Phys P, TmaCtx c, int q, Cell cur, FaceFlux Gb, double ey,
                                              double ex) {
   bool ok = true;
-  return tma_row_math<MODE, true>(A, g, P, c, q, cur, Gb, ey, ex, ok);
+  return tma_row_math<MODE, true, -1>(A, g, P, c, q, cur, Gb, ey, ex, ok);
 }
 
-// One row including the ring bookkeeping and the stores.  (cur,Gb) in, (nxt,Gt) out as in march_row.
-template <int MODE>
+// One row including the ring bookkeeping and the stores.  (cur,Gb) in, (nxt,Gt) out as in march_row.  ph = (q >> 2) & 1.
+template <int MODE, int S>
 __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const Phys& P, const TmaCtx& c,
-                                        const CUtensorMap* m_in, const CUtensorMap* m_base, int q,
-                                        const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& tyf, double& tyc,
-                                        double& spd) {
-  const int p = q + 1, j = c.jb + q;
-  // ---- the previous row left ring row p-1 and u^n row q-1 dead: re-arm their slots (kept next to the barrier wait
+                                        const CUtensorMap* m_in, const CUtensorMap* m_base, int q, uint32_t ph,
+                                        const Cell& cur, Cell& nxt, const FaceFlux& Gb, FaceFlux& Gt, double& spd) {
+  const int j = c.jb + q;
+  // ---- the previous row left ring row q and u^n row q-1 dead: re-arm their slots (kept next to the barrier wait
   //      so that the arithmetic of a row stays one basic block for the instruction scheduler)
   __syncwarp();
-  if (c.lane == 0) {
-    if (q + TMA_DEPTH < c.np) tma_issue_row<MODE>(c, m_in, q + TMA_DEPTH);
-    if (MODE == 2 && q >= 1 && q - 1 + TMA_BDEPTH < c.nrows) tma_issue_base(c, m_base, q - 1 + TMA_BDEPTH);
-  }
-  // ---- y tables of this row were loaded one row ago; fetch the next row's now
+  tma_rearm<MODE, S>(c, m_in, m_base, q);
+  // ---- y tables of this row
+  const double tyf = c.tab[q], tyc = c.tab[TMA_TAB_N + q];
   const double ey = c.exc_i * tyf, ex = c.exf_i * tyc, ec = c.exc_i * tyc;
-  tyf = A.eyf[min(j + 2, g.nyl)];
-  tyc = A.eyc[min(j + 1, g.nyl - 1)];
-  // ---- row j+1 (own column) must have landed; row j (left neighbour) landed a row ago
-  mbar_wait(c.bars + 8u * ((p + 1) & (TMA_DEPTH - 1)), ((p + 1) / TMA_DEPTH) & 1);
-  if (MODE == 2) mbar_wait(c.bars + 8u * (TMA_DEPTH + (q & (TMA_BDEPTH - 1))), (q / TMA_BDEPTH) & 1);
+  // ---- ring row q+2 (local row j+1, own column) must have landed; row q+1 (left neighbour) landed a row ago
+  {
+    const int s = ring_slot<S>(q, 2);
+    const uint32_t par = (S >= 0) ? ((S + 2 >= 4) ? (ph ^ 1u) : ph) : (uint32_t)(((q + 2) >> 2) & 1);
+    mbar_wait(c.bars + 8u * s, par);
+  }
+  if (MODE == 2) mbar_wait(c.bars + 8u * (TMA_DEPTH + ring_slot<S>(q, 0)), ph);
   bool ok = true;
-  RowOut o = tma_row_math<MODE, false>(A, g, P, c, q, cur, Gb, ey, ex, ok);
+  RowOut o = tma_row_math<MODE, false, S>(A, g, P, c, q, cur, Gb, ey, ex, ok);
   if (!__all_sync(0xffffffffu, ok)) o = tma_row_exact<MODE>(A, g, P, c, q, cur, Gb, ey, ex);
   nxt = o.nxt;
   Gt = o.Gt;
@@ -175,12 +213,12 @@ __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const
   st_if(dst + 3 * g.plane, o.n3, c.writer);
   if (MODE == 2) {
     const double s = centre_speed(A, g, P, (size_t)(j + 1) * g.pitch + min(c.i, g.nx - 1), ec, o.n0, o.n1, o.n2, o.n3);
-    spd = c.writer ? fmax(spd, s) : spd;
+    spd = (c.writer && s > spd) ? s : spd;
   }
 }
 
 template <int MODE, int MB>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, MB)
+__global__ void __launch_bounds__(TMA_WARPS * 32, MB * MARCH_WARPS / TMA_WARPS)
 k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CUtensorMap m_base, StageArgs A, Grid g, Phys P,
             int R) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
@@ -197,8 +235,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
       bookkeeping<MODE>(A.ctrl, A.parity, c.dt);
   }
   c.lane = threadIdx.x & 31;
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler
-  const int c0 = (blockIdx.x * MARCH_WARPS + warp) * MARCH_OUT;
+  const int warp = (TMA_WARPS == 1) ? 0 : __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int c0 = (blockIdx.x * TMA_WARPS + warp) * MARCH_OUT;
   if (c0 >= g.nx) return;                                 // whole warp: no block barriers in this kernel
   c.jb = A.row_begin + blockIdx.y * R;
   const int je = min(c.jb + R, A.row_end);
@@ -219,6 +257,14 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
   c.ring = smem_u32(c.wsm);
   c.bring = c.ring + TMA_DEPTH * TMA_SLOT_B;
   c.bars = c.bring + (MODE == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0);
+  double* tabw = reinterpret_cast<double*>(const_cast<unsigned char*>(c.wsm) + (TMA_DEPTH * TMA_SLOT_B +
+                                           (MODE == 2 ? TMA_BDEPTH * TMA_IN_PAD : 0) + TMA_BARS_B));
+  c.tab = tabw;
+  // ---- y tables of the strip: row q multiplies its face / centre x-table entries by exp(-a yf(jb+q+1)), exp(-a yc(jb+q))
+  for (int e = c.lane; e < TMA_TAB_N; e += 32) {
+    tabw[e] = A.eyf[min(c.jb + e + 1, g.nyl)];
+    tabw[TMA_TAB_N + e] = A.eyc[min(c.jb + e, g.nyl - 1)];
+  }
 
   // ---- barriers, then the first DEPTH rows
   if (c.lane == 0) {
@@ -236,26 +282,35 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
     }
   }
   __syncwarp();
-  double tyf = A.eyf[min(c.jb + 1, g.nyl)], tyc = A.eyc[min(c.jb, g.nyl - 1)];
 
   // ---- prologue: bottom face of the strip from rows jb-1 (p = 0) and jb (p = 1)
   Cell ca, cb;
   FaceFlux Ga, Gb2;
   {
     mbar_wait(c.bars, 0);
-    const Cell bel = tma_read_row(c, 0, c.own);
+    const Cell bel = tma_read_slot(c, 0, c.own);
     mbar_wait(c.bars + 8u, 0);
-    ca = tma_read_row(c, 1, c.own);
+    ca = tma_read_slot(c, 1, c.own);
     const double e = c.exc_i * A.eyf[c.jb];
     Ga = face_llf(P, P.rho0 * e, P.pe1 * e, bel.d0, bel.d2, bel.d1, bel.d3, ca.d0, ca.d2, ca.d1, ca.d3);
   }
   double spd = 0.0;
   int q = 0;
-  for (; q + 1 < c.nrows; q += 2) {      // two rows per trip: (ca,Ga)->(cb,Gb2)->(ca,Ga), no register rotation
-    tma_row<MODE>(A, g, P, c, &m_in, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
-    tma_row<MODE>(A, g, P, c, &m_in, &m_base, q + 1, cb, ca, Gb2, Ga, tyf, tyc, spd);
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (; q + 3 < c.nrows; q += 4) {     // four rows per trip: compile-time ring slots, (ca,Ga)->(cb,Gb2)->(ca,Ga) without moves
+    tma_row<MODE, 0>(A, g, P, c, &m_in, &m_base, q, ph, ca, cb, Ga, Gb2, spd);
+    tma_row<MODE, 1>(A, g, P, c, &m_in, &m_base, q + 1, ph, cb, ca, Gb2, Ga, spd);
+    tma_row<MODE, 2>(A, g, P, c, &m_in, &m_base, q + 2, ph, ca, cb, Ga, Gb2, spd);
+    tma_row<MODE, 3>(A, g, P, c, &m_in, &m_base, q + 3, ph, cb, ca, Gb2, Ga, spd);
+    ph ^= 1u;
   }
-  if (q < c.nrows) tma_row<MODE>(A, g, P, c, &m_in, &m_base, q, ca, cb, Ga, Gb2, tyf, tyc, spd);
+#pragma unroll 1
+  for (; q < c.nrows; ++q) {            // ragged tail of the last strip (cold: strips are 32 rows)
+    tma_row<MODE, -1>(A, g, P, c, &m_in, &m_base, q, (uint32_t)((q >> 2) & 1), ca, cb, Ga, Gb2, spd);
+    ca = cb;
+    Ga = Gb2;
+  }
   if (MODE == 2) {
     spd = warp_max(spd);
     if (c.lane == 0) atomic_max_nonneg(&A.ctrl->cmax_bits[A.parity ^ 1], spd);
