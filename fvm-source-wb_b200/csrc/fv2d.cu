@@ -452,10 +452,14 @@ __device__ __forceinline__ Cell load_cell(const StageArgs& A, const Grid& g, siz
 // Max wave speed of the updated cell (stage-2 CFL reduction, benchmark_2d.f90:264-295) from its delta form: the centre
 // equilibrium is rho0*e, p0/(gamma-1)*e with e = exp(-a xc) exp(-a yc) from the separable tables -- or, when the caller's
 // w_eq is not the analytic equilibrium, the planes it was given.
+// (out of line: the rare case must not cost the common one ten predicated-off instructions per cell)
+__device__ __noinline__ double2 centre_eq_supplied(const double* eqz, size_t plane, size_t o) {
+  return make_double2(eqz[o], eqz[plane + o]);
+}
 __device__ __forceinline__ double centre_speed(const StageArgs& A, const Grid& g, const Phys& P, size_t o, double e, double n0,
                                                double n1, double n2, double n3) {
   double re = P.rho0 * e, Ee = P.pe1 * e;
-  if (A.eq_exact) { re = A.eqz[o]; Ee = A.eqz[g.plane + o]; }
+  if (A.eq_exact) { const double2 q = centre_eq_supplied(A.eqz, g.plane, o); re = q.x; Ee = q.y; }
   return fast::speed(P, re + n0, n1, n2, Ee + n3);
 }
 

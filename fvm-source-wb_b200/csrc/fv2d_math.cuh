@@ -99,6 +99,13 @@ namespace fast {
 // is no FP64 min/max instruction: DSETP.MAX plus the NaN and signed-zero fix-ups), this costs three and gives the same
 // number for every pair of finite values; a NaN in `b` still propagates, and a NaN state poisons the fluxes anyway.
 __device__ __forceinline__ double max_speed2(double a, double b) { return a > b ? a : b; }
+// a > b ? a : b through PTX: written in C++ with a constant `b` the compiler recognises max.f64 and emits the nine-instruction
+// sequence again.  For finite or NaN a and a finite constant b this IS fmax(a, b).
+__device__ __forceinline__ double sel_gt(double a, double b) {
+  double d;
+  asm("{\n.reg .pred p;\nsetp.gt.f64 p, %1, %2;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(d) : "d"(a), "d"(b));
+  return d;
+}
 
 // 1/x: MUFU.RCP64H seed (~2^-20) + one cubic Newton step; relative error ~2^-53.
 __device__ __forceinline__ double rcp(double x) {
@@ -129,7 +136,7 @@ __device__ __forceinline__ Eval eval_state(const Phys& P, double rho, double mn,
   double vn = mn * r, vt = mt * r;
   double q = fma(vt, vt, vn * vn);
   double p = P.gm1 * fma(-0.5 * rho, q, E);
-  double pm = fmax(p, 1e-10);
+  double pm = sel_gt(p, 1e-10);      // == fmax(p, 1e-10) for every p, NaN included
   double rm = (rho >= 1e-10) ? r : 1e10;
   double c2 = (P.gamma * pm) * rm;
   double cs = sqrt_pos(c2);
@@ -168,7 +175,7 @@ __device__ __forceinline__ void eval_states(const Phys& P, const double (&rho)[N
   if (EXACT) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double pm = fmax(p[k], 1e-10);
+      const double pm = sel_gt(p[k], 1e-10);
       const double rm = (rho[k] >= 1e-10) ? r[k] : 1e10;
       c2[k] = (P.gamma * pm) * rm;
     }
@@ -216,7 +223,7 @@ __device__ __forceinline__ double speed(const Phys& P, double rho, double mx, do
   double vx = mx * r, vy = my * r;
   double q = fma(vy, vy, vx * vx);
   double p = P.gm1 * fma(-0.5 * rho, q, E);
-  double pm = fmax(p, 1e-10);
+  double pm = sel_gt(p, 1e-10);      // == fmax(p, 1e-10) for every p, NaN included
   double rm = (rho >= 1e-10) ? r : 1e10;
   double cs = sqrt_pos((P.gamma * pm) * rm);
   double vm = sqrt_pos(q + 1e-300);

@@ -75,7 +75,8 @@ __device__ __forceinline__ void st_if(double* p, double v, bool on) {
 }
 
 struct TmaCtx {
-  int lane, i, jb, np, nrows, jmin, jmax, x0, own;      // x0: first box column (even); own: this lane's column in the box
+  int lane, i, jb, np, nrows, jmin, jmax, x0, own, jgoff;
+  unsigned jgspan;              // row j is interior  <=>  (unsigned)(j + jgoff) < jgspan  (0 < g.j0 + j < ny - 1)      // x0: first box column (even); own: this lane's column in the box
   bool writer, col_interior;
   double exf_i, exc_i, dt;
   const unsigned char* wsm;     // this warp's shared-memory region (generic pointer)
@@ -112,7 +113,10 @@ template <int S> __device__ __forceinline__ int ring_slot(int q, int ahead) {
 // in uniform registers, and UTMALDG then needs no uniformisation loop.
 template <int MODE, int S>
 __device__ __forceinline__ void tma_rearm(const TmaCtx& c, const CUtensorMap* m_in, const CUtensorMap* m_base, int q) {
-  const int row = min(c.jb + q + TMA_DEPTH - 1, c.jmax) + 1;
+  const int over = c.jb + q + TMA_DEPTH - 1 - c.jmax;       // min() without a vector min: shifts and masks exist on the
+  int neg;                                                   // uniform datapath, so the row stays in a uniform register
+  asm("{\n.reg .s32 t;\nshr.s32 t, %1, 31;\nand.b32 %0, %1, t;\n}" : "=r"(neg) : "r"(over));      // (asm: NVVM turns the C++ form back into min)
+  const int row = c.jmax + neg + 1;
   const bool arm = (q + TMA_DEPTH < c.np), arm_b = (MODE == 2) && (q >= 1) && (q + 3 < c.nrows);
   if (c.lane == 0 && arm) {
     const int s = ring_slot<S>(q, 0);
@@ -168,8 +172,7 @@ __device__ __forceinline__ RowOut tma_row_math(const StageArgs& A, const Grid& g
   Fr.f0 = __shfl_down_sync(0xffffffffu, Fl.f0, 1); Fr.fn = __shfl_down_sync(0xffffffffu, Fl.fn, 1);
   Fr.ft = __shfl_down_sync(0xffffffffu, Fl.ft, 1); Fr.f3 = __shfl_down_sync(0xffffffffu, Fl.f3, 1);
   // ---- dudt in the reference's order (benchmark_2d.f90:601-607), RK axpy
-  const int jg = g.j0 + j;
-  const bool interior = c.col_interior && (jg > 0) && (jg < g.ny - 1);
+  const bool interior = c.col_interior && ((unsigned)(j + c.jgoff) < c.jgspan);
   cell_update<MODE>(P, cur, Fl, Fr, Gb, o.Gt, interior, c.dt, b0, b1, b2, b3, o.n0, o.n1, o.n2, o.n3);
   return o;
 }
@@ -248,6 +251,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
   c.own = c.i - c.x0;
   c.jmin = (g.j0 > 0) ? -1 : 0;
   c.jmax = (g.j0 + g.nyl < g.ny) ? g.nyl : g.nyl - 1;
+  c.jgoff = g.j0 - 1;
+  c.jgspan = (unsigned)max(g.ny - 2, 0);
   const int ic = min(c.i, g.nx - 1);
   c.exf_i = A.exf[ic];
   c.exc_i = A.exc[ic];
