@@ -1232,6 +1232,11 @@ struct wb_dg2d {
   wb::Nccl* comm = nullptr;
   double *sbuf_lo = nullptr, *sbuf_hi = nullptr, *rbuf_lo = nullptr, *rbuf_hi = nullptr, *red = nullptr;
   int rank = 0, nranks = 1, nyl = 0;
+  // overlap of the ghost exchange with the stage kernel: the two boundary rows, their pack / NCCL / unpack on a high-priority
+  // stream while the interior rows run on the main one (WB_DG2D_OVERLAP=0 switches it off)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+  bool overlap = true;
   // TMA-staged stage kernel: one 3-D tensor map (column, row, plane) per state buffer
   bool tma_ok = false;
   int march_rows = 32;         // rows per strip of k_dg_stage_split
@@ -1418,19 +1423,20 @@ int dg_limit_into(wb_dg2d* h, double* tmp, double* out, double* out2, double k3)
 
 // slab mode: fill the two ghost rows of a 4*nm-plane field.  Periodic box (bc = 1): ring of ranks; index clamp
 // (bc = 2, 3): chain, and the ghost row at a global edge is the rank's own boundary row (the clamped neighbour).
-int dg_exchange(wb_dg2d* h, double* field) {
+int dg_exchange(wb_dg2d* h, double* field, cudaStream_t stream = nullptr) {
   if (!h->g.slab) return WB_OK;
+  if (!stream) stream = h->stream;
   if (h->nranks > 1 && !h->comm) { set_error("nranks > 1 but wb_dg2d_comm_init was not called"); return WB_ERR_STATE; }
   const int npl = 4 * h->g.nm;
   const size_t cnt = (size_t)npl * h->g.nx;
   dim3 b(128), gr((h->g.nx + 127) / 128, npl);
-  k_dg_pack_rows<<<gr, b, 0, h->stream>>>(field, h->g, h->sbuf_lo, h->sbuf_hi);
+  k_dg_pack_rows<<<gr, b, 0, stream>>>(field, h->g, h->sbuf_lo, h->sbuf_hi);
   WB_LAUNCH_CHECK();
   const bool periodic = (h->phys.bc == 1);
   const int lo_peer = (h->rank > 0) ? h->rank - 1 : (periodic ? h->nranks - 1 : -1);
   const int hi_peer = (h->rank < h->nranks - 1) ? h->rank + 1 : (periodic ? 0 : -1);
-  WB_CHECK(nccl_ring_exchange(h->comm, lo_peer, hi_peer, h->sbuf_lo, h->sbuf_hi, h->rbuf_lo, h->rbuf_hi, cnt, h->stream));
-  k_dg_unpack_rows<<<gr, b, 0, h->stream>>>(field, h->g, lo_peer >= 0 ? h->rbuf_lo : h->sbuf_lo, hi_peer >= 0 ? h->rbuf_hi : h->sbuf_hi);
+  WB_CHECK(nccl_ring_exchange(h->comm, lo_peer, hi_peer, h->sbuf_lo, h->sbuf_hi, h->rbuf_lo, h->rbuf_hi, cnt, stream));
+  k_dg_unpack_rows<<<gr, b, 0, stream>>>(field, h->g, lo_peer >= 0 ? h->rbuf_lo : h->sbuf_lo, hi_peer >= 0 ? h->rbuf_hi : h->sbuf_hi);
   WB_LAUNCH_CHECK();
   return WB_OK;
 }
@@ -1521,6 +1527,23 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   if (h->tma_ok)
     for (int k = 0; k < 4; ++k)
       if (h->map_ptr[k] == in) m_in = &h->map[k];
+  if (m_in && h->split_ok && !lim_after && h->nranks > 1 && h->overlap && h->comm_stream && h->g.ny >= 6) {
+    // slab with neighbours: first and last owned row first, on the comm stream, followed by their exchange; the interior
+    // rows meanwhile on the main stream.  The ghost rows themselves are not computed: the exchange overwrites them.
+    const unsigned char* fz = h->phys.ninit == 12 ? h->fz : nullptr;
+    const int ny = h->g.ny;
+    WB_CUDA(cudaEventRecord(h->ev_main, h->stream));
+    WB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, 1, 2, h->comm_stream));
+    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, ny - 2, ny - 1,
+                                h->comm_stream));
+    WB_CHECK(dg_exchange(h, out, h->comm_stream));
+    if (out2) WB_CHECK(dg_exchange(h, out2, h->comm_stream));
+    WB_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
+    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, 2, ny - 2, h->stream));
+    WB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    return WB_OK;
+  }
   if (m_in && h->split_ok) {
     WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, h->phys.ninit == 12 ? h->fz : nullptr, h->g, h->phys, h->FB, h->ctrl,
                                 onp, h->march_rows, 0, h->g.ny, h->stream));
@@ -1733,6 +1756,14 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
     for (double** b : rows)
       if (e == cudaSuccess) e = cudaMalloc(b, rb);
     if (e == cudaSuccess) e = cudaMalloc(&h->red, sizeof(double) * 8);
+    if (h->nranks > 1) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming);
+      if (const char* ev = getenv("WB_DG2D_OVERLAP")) h->overlap = atoi(ev) != 0;
+    }
   }
   if (e != cudaSuccess) { set_error("device allocation failed: %s", cudaGetErrorString(e)); return fail(WB_ERR_CUDA); }
   cudaMemsetAsync(h->ctrl, 0, sizeof(DgCtrl), h->stream);
@@ -1771,6 +1802,9 @@ int wb_dg2d_destroy(wb_dg2d* h) {
   cudaFree(h->du); cudaFree(h->A); cudaFree(h->Bf); cudaFree(h->C); cudaFree(h->D); cudaFree(h->E); cudaFree(h->stage);
   cudaFree(h->gx); cudaFree(h->gy); cudaFree(h->xy); cudaFree(h->fz); cudaFree(h->ctrl); cudaFree(h->part1); cudaFree(h->part2);
   cudaFree(h->sbuf_lo); cudaFree(h->sbuf_hi); cudaFree(h->rbuf_lo); cudaFree(h->rbuf_hi); cudaFree(h->red);
+  if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   nccl_comm_destroy(h->comm);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -48,6 +48,8 @@ struct StageArgs {
   double tend;
   int max_iter;
   int row_begin, row_end;   // local rows [row_begin,row_end) covered by this launch
+  int rows_cap;             // TMA kernel: rows a strip computes (normally its stride R; 1 for the slab's two boundary rows, which
+                            // travel as ONE launch with stride nyl-1: strip 0 = row 0, strip 1 = row nyl-1)
   int pf_rows;              // marching kernel: L2 prefetch distance in rows (0 = off)
 };
 
@@ -802,7 +804,7 @@ int make_field_map(const wb_fv2d* h, const double* base, int nplanes, CUtensorMa
 
 template <int MODE>
 int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, double tend, int max_iter,
-                 bool wb_scheme = true, int row_begin = 0, int row_end = -1, cudaStream_t stream = nullptr) {
+                 bool wb_scheme = true, int row_begin = 0, int row_end = -1, cudaStream_t stream = nullptr, bool edge_pair = false) {
   if (row_end < 0) row_end = h->g.nyl;
   if (!stream) stream = h->stream;
   if (row_begin >= row_end) return WB_OK;
@@ -812,6 +814,16 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   A.ctrl = h->ctrl; A.parity = h->parity; A.tend = tend; A.max_iter = max_iter;
   A.row_begin = row_begin; A.row_end = row_end;
   A.pf_rows = h->pf_rows;
+  A.rows_cap = 1 << 30;
+  {
+    const CUtensorMap* mi = (in == h->u) ? &h->map_u : (in == h->w1) ? &h->map_w1 : nullptr;
+    const CUtensorMap* mb = (base == h->u) ? &h->map_u : (base == h->w1) ? &h->map_w1 : nullptr;
+    const bool tma = use_fast(h) && wb_scheme && h->tma_ok && mi && (MODE != 2 || mb);
+    if (edge_pair && !tma) {      // only the TMA kernel knows the paired form
+      WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, max_iter, wb_scheme, 0, 1, stream)));
+      return launch_stage<MODE>(h, in, base, out, tend, max_iter, wb_scheme, h->g.nyl - 1, h->g.nyl, stream);
+    }
+  }
   if (use_fast(h) && wb_scheme) {
     const int R = h->march_rows;
     const int ncols = (h->g.nx + MARCH_OUT - 1) / MARCH_OUT;
@@ -828,7 +840,9 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_WARPS * tma_warp_bytes(MODE)));
         configured = true;
       }
-      const int Rt = std::min(R, TMA_MAX_ROWS);      // the per-warp y tables hold one strip
+      int Rt = std::min(R, TMA_MAX_ROWS);            // the per-warp y tables hold one strip
+      A.rows_cap = Rt;
+      if (edge_pair) { Rt = h->g.nyl - 1; A.rows_cap = 1; A.row_begin = 0; A.row_end = h->g.nyl; }
       const dim3 bt(TMA_WARPS * 32), gt((ncols + TMA_WARPS - 1) / TMA_WARPS, (A.row_end - A.row_begin + Rt - 1) / Rt);
       kern<<<gt, bt, TMA_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, m_base ? *m_base : *m_in, A, h->g, h->phys, Rt);
     } else {
@@ -876,8 +890,7 @@ int stage_with_exchange(wb_fv2d* h, const double* in, const double* base, double
   }
   WB_CUDA(cudaEventRecord(h->ev_main, h->stream));               // inputs (and their ghosts) are ready
   WB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
-  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 0, 1, h->comm_stream)));
-  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, nyl - 1, nyl, h->comm_stream)));
+  WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 0, nyl, h->comm_stream, true)));     // rows 0 and nyl-1, one launch
   WB_CHECK(exchange_ghost_rows(h, out, 4, h->comm_stream));
   WB_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
   WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 1, nyl - 1, h->stream)));
@@ -920,7 +933,11 @@ int wb_fv2d_create(wb_fv2d** out, const wb_fv2d_params* p) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(WB_ERR_CUDA); }
   h->own_stream = true;
   if (p->nranks > 1) {
-    if (cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the boundary rows and the NCCL send/recv are enqueued before the interior kernel but would otherwise
+    // find every SM's registers taken by it and run at its tail, i.e. not overlapped at all
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming) != cudaSuccess) {
       set_error("comm stream/event creation failed");

@@ -242,7 +242,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CU
   const int c0 = (blockIdx.x * TMA_WARPS + warp) * MARCH_OUT;
   if (c0 >= g.nx) return;                                 // whole warp: no block barriers in this kernel
   c.jb = A.row_begin + blockIdx.y * R;
-  const int je = min(c.jb + R, A.row_end);
+  const int je = min(c.jb + min(R, A.rows_cap), A.row_end);
   if (c.jb >= je) return;
   c.nrows = je - c.jb;
   c.np = c.nrows + 2;                                       // ring rows p = 0..np-1  <->  local rows jb-1 .. je
