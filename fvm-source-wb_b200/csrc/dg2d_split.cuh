@@ -153,7 +153,6 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
     const bool full = it > 0;
     const int par = it & 1;
     double* TTp = TT + par * (M * 4 * 32);
-    double U[SRC ? M : 1][SRC ? M : 1];                      // nodal values of the own variable (source terms only)
     // RK operands of the NEXT row: ask L2 for them now (a plane's 32 columns are two 128-byte lines: lane l of warp v touches
     // line l&1 of plane v*NM + l/2), so that phase C of the next iteration finds them in L2 instead of waiting for DRAM
     // (ncu: long_scoreboard on the first use of A0 was 5-15 % of the stall samples).  Per-lane prefetch.global.L2, not the
@@ -163,6 +162,11 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A0 + po));
       if (C.na >= 2 && C.A1 != in) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A1 + po));
       if (OUT2) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.B1 + po));
+      if (SRC && v == 0 && P.source == 2) {                  // the gravity field of the next row (read by the node items of phase B)
+        const size_t pg = (size_t)(lane >> 1) * g.ne + (size_t)(j + 1) * g.nx + ic0 + (lane & 1) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + pg));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + pg));
+      }
     }
     // ------------------------------------------------------------------ phase A
     {
@@ -199,7 +203,6 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
 #pragma unroll
             for (int jm = 1; jm < M; ++jm)
               if (!zP<M>(qy, jm)) s = fma(a[jm], B.P[qy][jm], s);
-            if (SRC) U[SRC ? qx : 0][SRC ? qy : 0] = s;
             UB[((qx * M + qy) * NS + v) * 32 + lane] = s;
           }
         }
@@ -274,12 +277,24 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
 #pragma unroll 1
       for (int k = (sched >> 16) & 31; k < ((sched >> 21) & 31); ++k) {
         double* p = UB + (k * NS) * 32 + lane;
-        const double u1 = p[32], u2 = p[64], u3 = p[96];
-        const fastm::Prim w = fastm::prim(P, p[0], u1, u2, u3);
+        // kernels with a source term: the source of every variable at this node, evaluated ONCE here (get_source :1558-1576:
+        // (0, w0 g1, w0 g2, w0 (vx g1 + vy g2)); get_adv_source :1579-1596: (-rho, 0, 0, 0)) -- phase C picks its variable's.
+        // The two gravity loads are issued before the primitive variables are computed and were prefetched into L2 a row ago.
+        double g1 = 0.0, g2 = 0.0;
+        if (SRC && P.source == 2) {
+          const size_t ge = (size_t)((k % M) * M + k / M) * g.ne + (size_t)j * g.nx + ic0 + lane;      // node k = qx*M + qy
+          g1 = gx[ge]; g2 = gy[ge];
+        }
+        const double u0 = p[0], u1 = p[32], u2 = p[64], u3 = p[96];
+        const fastm::Prim w = fastm::prim(P, u0, u1, u2, u3);
         const double t = w.w0 * w.vx * w.vy, Ep = u3 + w.p;
         p[0] = w.w0 * w.vx; p[32] = fma(w.vx, u1, w.p); p[64] = t; p[96] = w.vx * Ep;
         p[128] = w.w0 * w.vy; p[160] = t; p[192] = fma(w.vy, u2, w.p); p[224] = w.vy * Ep;
-        if (SRC) { double* q = SW + (k * 3) * 32 + lane; q[0] = w.w0; q[32] = w.vx; q[64] = w.vy; }
+        if (SRC) {
+          double* q = SW + (k * 3) * 32 + lane;
+          if (P.source == 2) { q[0] = w.w0 * g1; q[32] = w.w0 * g2; q[64] = w.w0 * fma(w.vx, g1, w.vy * g2); }
+          else q[0] = u0;
+        }
       }
     }
     __syncthreads();
@@ -322,6 +337,9 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       // M*M accumulators -- the same sums in the same order as k_dg_stage_fast (vol: s = acc, then qy ascending; source:
       // s = 0, then qy ascending), with M instead of M*M fluxes alive.
       double sv[SRC ? M : 1][SRC ? M : 1];
+      // gravity (source 2): variable v > 0 takes slot v-1; advection sink (source 3): variable 0 takes -rho from slot 0
+      const bool src_on = SRC && (P.source == 2 ? v != 0 : v == 0), src_neg = SRC && P.source != 2;
+      const int src_slot = (SRC && P.source == 2 && v > 0) ? v - 1 : 0;
       if (SRC) {
 #pragma unroll
         for (int a = 0; a < M; ++a)
@@ -335,15 +353,9 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         for (int qx = 0; qx < M; ++qx) {
           const double* p = UB + ((qx * M + qy) * NS + v) * 32 + lane;
           f1[qx] = p[0]; f2[qx] = p[128];
-          if (SRC) {
-            if (P.source == 2) {                             // get_source :1558-1576
-              const double* q = SW + ((qx * M + qy) * 3) * 32 + lane;
-              const double w0 = q[0], vx = q[32], vy = q[64];
-              const double g1 = gx[(size_t)(qy * M + qx) * g.ne + e], g2 = gy[(size_t)(qy * M + qx) * g.ne + e];
-              S[qx] = v == 0 ? 0.0 : v == 1 ? w0 * g1 : v == 2 ? w0 * g2 : w0 * fma(vx, g1, vy * g2);
-            } else {                                         // get_adv_source :1579-1596
-              S[qx] = v == 0 ? -U[SRC ? qx : 0][SRC ? qy : 0] : 0.0;
-            }
+          if (SRC) {                                         // the node item of phase B left the sources in SW
+            const double x = SW[((qx * M + qy) * 3 + src_slot) * 32 + lane];
+            S[qx] = src_on ? (src_neg ? -x : x) : 0.0;
           }
         }
 #pragma unroll
