@@ -35,14 +35,18 @@ struct SplitLayout {                                   // shared memory, in doub
   static constexpr int NM = M * M, NP = 4 * NM;
   static constexpr int SLOT_D = NP * DGT_W;            // one TMA row slot
   static constexpr int TW = 34;                        // columns of the x-trace arrays (33 used: columns -1..31 / 0..32)
-  static constexpr int NS = 8;                         // slots per volume node: nodal values (0..3) -> both fluxes (0..7)
+  static constexpr int NS = 7;                         // slots per volume node: nodal values (0..3) -> both fluxes (0..6: the two
+                                                       // fluxes share rho*vx*vy, slot 2)
   static constexpr int OFF_UB = 2 * SLOT_D;            // [NM nodes][NS][32]
   static constexpr int OFF_TL = OFF_UB + NM * NS * 32; // [M][4][TW] left traces of columns 0..32 -> left-face fluxes
   static constexpr int OFF_TR = OFF_TL + M * 4 * TW;   // [M][4][TW] right traces of columns -1..31 (index c+1)
-  static constexpr int OFF_TT = OFF_TR + M * 4 * TW;   // [2][M][4][32] top traces -> top-face fluxes, by row parity
-  static constexpr int OFF_TB = OFF_TT + 2 * M * 4 * 32;   // [M][4][32] bottom traces of the row above
-  static constexpr int OFF_LIM = OFF_TB + M * 4 * 32;  // [8][32] mean and mode bound of every variable ('ONP' test)
-  static constexpr int OFF_SW = OFF_LIM + 8 * 32;      // [NM nodes][3][32] w0, vx, vy (kernels with a source term only)
+  static constexpr int OFF_TT = OFF_TR + M * 4 * TW;   // [M][4][32] top traces of the row -> top-face fluxes (the bottom-face
+                                                       // fluxes are last row's top-face fluxes: carried in registers)
+  static constexpr int OFF_TB = OFF_TT + M * 4 * 32;   // [M][4][32] bottom traces of the row above (phases A, B) ...
+  static constexpr int OFF_LIM = OFF_TB;               // ... and [8][32] mean and mode bound of every variable ('ONP' test, end of
+                                                       // phase C: TB is dead by then and the vote barrier closes the reads)
+  static constexpr int OFF_SW = OFF_TB + (M * 4 * 32 > 8 * 32 ? M * 4 * 32 : 8 * 32);
+                                                       // [NM nodes][3][32] gravity (g1, g2) -> sources (kernels with a source term)
   static constexpr int OFF_BAR_SRC = OFF_SW + NM * 3 * 32, OFF_BAR_NOSRC = OFF_SW;      // 2 mbarriers + the step's dt
   template <bool SRC> static constexpr int bytes() { return ((SRC ? OFF_BAR_SRC : OFF_BAR_NOSRC) + 3) * 8; }
   // work items of phase B: [0, NM) volume nodes, [NM, NM+M) left-face points, [NM+M, NM+2M) top-face points,
@@ -147,12 +151,15 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
   tma::mbar_wait(bars, 0);
   const int nit = j1 - j0 + 1;
   const unsigned sched = split_schedule<M>(v, rows_sched >> 16);
+  double Fbot[M];                                            // own variable's fluxes through the bottom face of the current row
+#pragma unroll
+  for (int q = 0; q < M; ++q) Fbot[q] = 0.0;
 #pragma unroll 1
   for (int it = 0; it < nit; ++it) {
     const int j = j0 - 1 + it;
     const bool full = it > 0;
     const int par = it & 1;
-    double* TTp = TT + par * (M * 4 * 32);
+    double* TTp = TT;
     // RK operands of the NEXT row: ask L2 for them now (a plane's 32 columns are two 128-byte lines: lane l of warp v touches
     // line l&1 of plane v*NM + l/2), so that phase C of the next iteration finds them in L2 instead of waiting for DRAM
     // (ncu: long_scoreboard on the first use of A0 was 5-15 % of the stall samples).  Per-lane prefetch.global.L2, not the
@@ -166,6 +173,20 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         const size_t pg = (size_t)(lane >> 1) * g.ne + (size_t)(j + 1) * g.nx + ic0 + (lane & 1) * 16;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + pg));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + pg));
+      }
+    }
+    // gravity field of this row: thread (v, column) fetches the nodes v, v+4, .. now and parks them in the source slots at the
+    // end of phase A, where the node items of phase B find them (the L2 latency hides behind phase A)
+    constexpr int NG = (NM + 3) / 4;
+    double ga[SRC ? NG : 1], gb[SRC ? NG : 1];
+    if (SRC && full && P.source == 2) {
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        const int k = v + 4 * i;                             // node k = qx*M + qy; the arrays are ordered qy*M + qx
+        if (k < NM) {
+          const size_t ge = (size_t)((k % M) * M + k / M) * g.ne + (size_t)j * g.nx + ic0 + lane;
+          ga[SRC ? i : 0] = gx[ge]; gb[SRC ? i : 0] = gy[ge];
+        }
       }
     }
     // ------------------------------------------------------------------ phase A
@@ -244,6 +265,13 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
 #pragma unroll
       for (int q = 0; q < M; ++q) TB[(q * 4 + v) * 32 + lane] = t1[q];
     }
+    if (SRC && full && P.source == 2) {
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        const int k = v + 4 * i;
+        if (k < NM) { SW[(k * 3) * 32 + lane] = ga[SRC ? i : 0]; SW[(k * 3 + 1) * 32 + lane] = gb[SRC ? i : 0]; }
+      }
+    }
     __syncthreads();
     if (threadIdx.x == 0 && j + 1 < j1) arm_slot(par, y_nb(g, P.bc, j + 2));   // row j is consumed
     // ------------------------------------------------------------------ phase B
@@ -279,17 +307,14 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         double* p = UB + (k * NS) * 32 + lane;
         // kernels with a source term: the source of every variable at this node, evaluated ONCE here (get_source :1558-1576:
         // (0, w0 g1, w0 g2, w0 (vx g1 + vy g2)); get_adv_source :1579-1596: (-rho, 0, 0, 0)) -- phase C picks its variable's.
-        // The two gravity loads are issued before the primitive variables are computed and were prefetched into L2 a row ago.
+        // (g1, g2) were fetched at the start of the row and wait in the slots that take the sources.
         double g1 = 0.0, g2 = 0.0;
-        if (SRC && P.source == 2) {
-          const size_t ge = (size_t)((k % M) * M + k / M) * g.ne + (size_t)j * g.nx + ic0 + lane;      // node k = qx*M + qy
-          g1 = gx[ge]; g2 = gy[ge];
-        }
+        if (SRC && P.source == 2) { g1 = SW[(k * 3) * 32 + lane]; g2 = SW[(k * 3 + 1) * 32 + lane]; }
         const double u0 = p[0], u1 = p[32], u2 = p[64], u3 = p[96];
         const fastm::Prim w = fastm::prim(P, u0, u1, u2, u3);
         const double t = w.w0 * w.vx * w.vy, Ep = u3 + w.p;
-        p[0] = w.w0 * w.vx; p[32] = fma(w.vx, u1, w.p); p[64] = t; p[96] = w.vx * Ep;
-        p[128] = w.w0 * w.vy; p[160] = t; p[192] = fma(w.vy, u2, w.p); p[224] = w.vy * Ep;
+        p[0] = w.w0 * w.vx; p[32] = fma(w.vx, u1, w.p); p[64] = t; p[96] = w.vx * Ep;      // x flux: slots 0..3
+        p[128] = w.w0 * w.vy; p[160] = fma(w.vy, u2, w.p); p[192] = w.vy * Ep;               // y flux: slots 4, 2, 5, 6
         if (SRC) {
           double* q = SW + (k * 3) * 32 + lane;
           if (P.source == 2) { q[0] = w.w0 * g1; q[32] = w.w0 * g2; q[64] = w.w0 * fma(w.vx, g1, w.vy * g2); }
@@ -298,7 +323,11 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       }
     }
     __syncthreads();
-    if (!full) continue;
+    if (!full) {                                             // row below the strip: only its top-face fluxes are needed
+#pragma unroll
+      for (int q = 0; q < M; ++q) Fbot[q] = TT[(q * 4 + v) * 32 + lane];
+      continue;
+    }
     // ------------------------------------------------------------------ phase C
     const size_t e = (size_t)j * g.nx + ic0 + lane;
     const size_t pe = (size_t)v * NM * g.ne + e;             // element of plane (v, 0)
@@ -325,17 +354,18 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
 #pragma unroll
       for (int q = 0; q < M; ++q) F[q] = TL[(q * 4 + v) * L::TW + lane + 1];
       face_accum1<M, 1>(B, F, acc);
+      face_accum1<M, 2>(B, Fbot, acc);                       // bottom face = the top face of the row below
 #pragma unroll
-      for (int q = 0; q < M; ++q) F[q] = TT[(par ^ 1) * (M * 4 * 32) + (q * 4 + v) * 32 + lane];
-      face_accum1<M, 2>(B, F, acc);
-#pragma unroll
-      for (int q = 0; q < M; ++q) F[q] = TTp[(q * 4 + v) * 32 + lane];
+      for (int q = 0; q < M; ++q) F[q] = TT[(q * 4 + v) * 32 + lane];
       face_accum1<M, 3>(B, F, acc);
+#pragma unroll
+      for (int q = 0; q < M; ++q) Fbot[q] = F[q];
     }
     {
       // Per quadrature row qy: fluxes of the own variable at its M nodes, their contraction over qx, and the update of the
       // M*M accumulators -- the same sums in the same order as k_dg_stage_fast (vol: s = acc, then qy ascending; source:
       // s = 0, then qy ascending), with M instead of M*M fluxes alive.
+      const int f2_slot = v == 0 ? 4 : v == 1 ? 2 : v + 3;   // the y flux of variable v (see the node items)
       double sv[SRC ? M : 1][SRC ? M : 1];
       // gravity (source 2): variable v > 0 takes slot v-1; advection sink (source 3): variable 0 takes -rho from slot 0
       const bool src_on = SRC && (P.source == 2 ? v != 0 : v == 0), src_neg = SRC && P.source != 2;
@@ -351,8 +381,8 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         double f1[M], f2[M], S[M];
 #pragma unroll
         for (int qx = 0; qx < M; ++qx) {
-          const double* p = UB + ((qx * M + qy) * NS + v) * 32 + lane;
-          f1[qx] = p[0]; f2[qx] = p[128];
+          const double* p = UB + ((qx * M + qy) * NS) * 32 + lane;
+          f1[qx] = p[v * 32]; f2[qx] = p[f2_slot * 32];
           if (SRC) {                                         // the node item of phase B left the sources in SW
             const double x = SW[((qx * M + qy) * 3 + src_slot) * 32 + lane];
             S[qx] = src_on ? (src_neg ? -x : x) : 0.0;
