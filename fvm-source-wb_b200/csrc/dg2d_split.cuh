@@ -366,51 +366,70 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       // M*M accumulators -- the same sums in the same order as k_dg_stage_fast (vol: s = acc, then qy ascending; source:
       // s = 0, then qy ascending), with M instead of M*M fluxes alive.
       const int f2_slot = v == 0 ? 4 : v == 1 ? 2 : v + 3;   // the y flux of variable v (see the node items)
-      double sv[SRC ? M : 1][SRC ? M : 1];
-      // gravity (source 2): variable v > 0 takes slot v-1; advection sink (source 3): variable 0 takes -rho from slot 0
-      const bool src_on = SRC && (P.source == 2 ? v != 0 : v == 0), src_neg = SRC && P.source != 2;
-      const int src_slot = (SRC && P.source == 2 && v > 0) ? v - 1 : 0;
-      if (SRC) {
-#pragma unroll
-        for (int a = 0; a < M; ++a)
-#pragma unroll
-          for (int b = 0; b < M; ++b) sv[SRC ? a : 0][SRC ? b : 0] = 0.0;
-      }
 #pragma unroll
       for (int qy = 0; qy < M; ++qy) {
-        double f1[M], f2[M], S[M];
+        double f1[M], f2[M];
 #pragma unroll
         for (int qx = 0; qx < M; ++qx) {
           const double* p = UB + ((qx * M + qy) * NS) * 32 + lane;
           f1[qx] = p[v * 32]; f2[qx] = p[f2_slot * 32];
-          if (SRC) {                                         // the node item of phase B left the sources in SW
-            const double x = SW[((qx * M + qy) * 3 + src_slot) * 32 + lane];
-            S[qx] = src_on ? (src_neg ? -x : x) : 0.0;
-          }
         }
 #pragma unroll
         for (int a = 0; a < M; ++a) {
-          double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          double s1 = 0.0, s2 = 0.0;
 #pragma unroll
           for (int qx = 0; qx < M; ++qx) {
             if (a > 0 && !zD<M>(qx, a)) s1 = fma(f1[qx], B.dPw[qx][a], s1);   // exact zeros of the tables: terms dropped
             if (!zP<M>(qx, a)) s2 = fma(f2[qx], B.Pw[qx][a], s2);
-            if (SRC && !zP<M>(qx, a)) s3 = fma(S[qx], B.Pw[qx][a], s3);
           }
 #pragma unroll
           for (int b = 0; b < M; ++b) {
             if (b > 0 && !zD<M>(qy, b)) acc[a][b] = fma(s2, B.dPw[qy][b], acc[a][b]);
             if (a > 0 && !zP<M>(qy, b)) acc[a][b] = fma(s1, B.Pw[qy][b], acc[a][b]);
-            if (SRC && !zP<M>(qy, b)) sv[SRC ? a : 0][SRC ? b : 0] = fma(s3, B.Pw[qy][b], sv[SRC ? a : 0][SRC ? b : 0]);
           }
         }
       }
       if (SRC) {
-        const double src_scale = 0.5 * P.dx;
+        // Source integral (:1403-1447), its own sums (s = 0, then qy ascending) added to the volume integral at the end.
+        // gravity (source 2): variable v > 0 finds its source in slot v-1; advection sink (source 3): variable 0 takes -rho
+        // from slot 0.  A warp is one variable, so the test is warp-uniform: the variables without a source skip the sums
+        // and add the +0.0 the sums would have produced (-0.0 + 0.0 = +0.0: same bits as fma(scale, +0.0, acc)).
+        const bool src_on = (P.source == 2) ? v != 0 : v == 0;
+        if (src_on) {
+          const double sgn = (P.source == 2) ? 1.0 : -1.0;
+          const double* sw = SW + ((P.source == 2) ? v - 1 : 0) * 32 + lane;
+          double sv[M][M];
 #pragma unroll
-        for (int a = 0; a < M; ++a)
+          for (int a = 0; a < M; ++a)
 #pragma unroll
-          for (int b = 0; b < M; ++b) acc[a][b] = fma(src_scale, sv[SRC ? a : 0][SRC ? b : 0], acc[a][b]);
+            for (int b = 0; b < M; ++b) sv[a][b] = 0.0;
+#pragma unroll
+          for (int qy = 0; qy < M; ++qy) {
+            double S[M];
+#pragma unroll
+            for (int qx = 0; qx < M; ++qx) S[qx] = sgn * sw[((qx * M + qy) * 3) * 32];
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+              double s3 = 0.0;
+#pragma unroll
+              for (int qx = 0; qx < M; ++qx)
+                if (!zP<M>(qx, a)) s3 = fma(S[qx], B.Pw[qx][a], s3);
+#pragma unroll
+              for (int b = 0; b < M; ++b)
+                if (!zP<M>(qy, b)) sv[a][b] = fma(s3, B.Pw[qy][b], sv[a][b]);
+            }
+          }
+          const double src_scale = 0.5 * P.dx;
+#pragma unroll
+          for (int a = 0; a < M; ++a)
+#pragma unroll
+            for (int b = 0; b < M; ++b) acc[a][b] = fma(src_scale, sv[a][b], acc[a][b]);
+        } else {
+#pragma unroll
+          for (int a = 0; a < M; ++a)
+#pragma unroll
+            for (int b = 0; b < M; ++b) acc[a][b] = acc[a][b] + 0.0;
+        }
       }
     }
     // ---- dudt scaling (:1449-1466), RK combination (:683-707).  c0*a0 with c0 == 1 is a0 exactly, so the first stage needs
