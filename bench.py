@@ -383,6 +383,7 @@ def slab_parity(world, rank, local_rank):
         u, weq = one.get_initial_conditions(3)
         ref, it1, t1, dt1 = one.evolve(u, weq, 1.0, steps)
     s = wd.make_slab_solver(wbeuler.FV2D, world, rank, local_rank, nx=nx, ny=ny)
+    res["fv_ghost_exchange"] = s.exchange_kind()
     got, it, t, dt = s.evolve(wd.scatter_rows(u, rank, world), wd.scatter_rows(weq, rank, world), 1.0, steps)
     full = wd.gather_rows(got, ny)
     s.close()
@@ -463,6 +464,8 @@ def run_ours(args):
     solver.set_stream(stream.cuda_stream)
     solver.init_device(3)
     cells_global = n * n
+    if world > 1:      # how the per-stage ghost rows travel: "p2p" (stored into peer memory by the stage kernel) or "nccl"
+        cfg["ghost_exchange"] = solver.exchange_kind()
 
     def barrier():
         if world > 1:

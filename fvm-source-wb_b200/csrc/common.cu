@@ -58,6 +58,7 @@ struct NcclApi {
                             cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -85,6 +86,7 @@ static void nccl_load() {
   WB_SYM(Recv, "ncclRecv")
   WB_SYM(AllReduce, "ncclAllReduce")
   WB_SYM(Broadcast, "ncclBroadcast")
+  WB_SYM(AllGather, "ncclAllGather")
   WB_SYM(GetErrorString, "ncclGetErrorString")
 #undef WB_SYM
   g_nccl_ok = true;
@@ -206,6 +208,11 @@ int nccl_halo_exchange(Nccl* c, int rank, int nranks, const double* send_lo, dou
 int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s) {
   if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
   WB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclUint64, ncclMax, c->comm, s));
+  return WB_OK;
+}
+int nccl_allgather_bytes(Nccl* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
+  if (!c || !c->comm) { set_error("NCCL communicator missing"); return WB_ERR_STATE; }
+  WB_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, ncclChar, c->comm, s));
   return WB_OK;
 }
 int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s) {

@@ -62,6 +62,7 @@ int nccl_halo_exchange_multi(Nccl* c, int lo_peer, int hi_peer, const HaloSeg* l
 int nccl_ring_exchange(Nccl* c, int lo_peer, int hi_peer, const double* send_lo, const double* send_hi, double* recv_lo,
                        double* recv_hi, size_t count, cudaStream_t s);
 int nccl_allreduce_max_u64(Nccl* c, unsigned long long* buf, size_t count, cudaStream_t s);
+int nccl_allgather_bytes(Nccl* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
 int nccl_allreduce_min_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
 int nccl_allreduce_max_f64(Nccl* c, double* buf, size_t count, cudaStream_t s);
 int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s);

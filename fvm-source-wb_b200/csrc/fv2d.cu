@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace wb { namespace fv2d {
@@ -51,6 +52,10 @@ struct StageArgs {
   int rows_cap;             // TMA kernel: rows a strip computes (normally its stride R; 1 for the slab's two boundary rows, which
                             // travel as ONE launch with stride nyl-1: strip 0 = row 0, strip 1 = row nyl-1)
   int pf_rows;              // marching kernel: L2 prefetch distance in rows (0 = off)
+  // slab boundary-row launch with peer-memory ghost rows: the row's results are ALSO stored into the neighbour's ghost row
+  // (row 0 -> top ghost row of the slab below, row nyl-1 -> bottom ghost row of the slab above), over NVLink
+  double* peer_lo; double* peer_hi;        // element (ghost row, column 0) of plane 0 of the neighbour's output field, or null
+  size_t peer_lo_plane, peer_hi_plane;     // the neighbour's plane stride (its slab may be one row taller)
 };
 
 // ------------------------------------------------------------------------------------ layout kernels
@@ -679,6 +684,16 @@ struct wb_fv2d {
   cudaStream_t comm_stream = nullptr;   // slab mode: boundary rows + NCCL ghost exchange run here, overlapped with the interior
   cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
   int overlap = 1;
+  // peer-memory ghost rows (one process per GPU: the neighbours' state buffers and flag words are mapped with CUDA IPC)
+  struct Peer {
+    bool active = false;
+    double *lo_u = nullptr, *lo_w1 = nullptr, *hi_u = nullptr, *hi_w1 = nullptr;      // neighbours' buffers (mapped)
+    unsigned long long *lo_flags = nullptr, *hi_flags = nullptr;                      // neighbours' flag words (mapped)
+    size_t lo_plane = 0, hi_plane = 0;
+    int lo_nyl = 0, hi_nyl = 0;
+    unsigned long long* flags = nullptr;      // own: [0] counts the rows received from below, [1] from above, [2] error word
+    unsigned long long seq = 0;               // exchanges enqueued so far (the same number on every rank)
+  } peer;
   int march_rows = 32;          // rows per strip of the marching kernel
   int pf_rows = 4;              // L2 prefetch distance of the LDG marching kernel (rows ahead; 0 = off)
   bool tma_ok = false;          // tensor maps built: the TMA-fed stage kernel is used
@@ -815,6 +830,7 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
   A.row_begin = row_begin; A.row_end = row_end;
   A.pf_rows = h->pf_rows;
   A.rows_cap = 1 << 30;
+  A.peer_lo = A.peer_hi = nullptr; A.peer_lo_plane = A.peer_hi_plane = 0;
   {
     const CUtensorMap* mi = (in == h->u) ? &h->map_u : (in == h->w1) ? &h->map_w1 : nullptr;
     const CUtensorMap* mb = (base == h->u) ? &h->map_u : (base == h->w1) ? &h->map_w1 : nullptr;
@@ -842,7 +858,16 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
       }
       int Rt = std::min(R, TMA_MAX_ROWS);            // the per-warp y tables hold one strip
       A.rows_cap = Rt;
-      if (edge_pair) { Rt = h->g.nyl - 1; A.rows_cap = 1; A.row_begin = 0; A.row_end = h->g.nyl; }
+      if (edge_pair) {
+        Rt = h->g.nyl - 1; A.rows_cap = 1; A.row_begin = 0; A.row_end = h->g.nyl;
+        if (h->peer.active) {      // (this is the TMA path: stage_with_exchange relies on exactly this condition)
+          const wb_fv2d::Peer& Pp = h->peer;
+          double* lo = (out == h->u) ? Pp.lo_u : Pp.lo_w1;
+          double* hi = (out == h->u) ? Pp.hi_u : Pp.hi_w1;
+          if (lo) { A.peer_lo = lo + (size_t)(Pp.lo_nyl + 1) * h->g.pitch; A.peer_lo_plane = Pp.lo_plane; }
+          if (hi) { A.peer_hi = hi; A.peer_hi_plane = Pp.hi_plane; }
+        }
+      }
       const dim3 bt(TMA_WARPS * 32), gt((ncols + TMA_WARPS - 1) / TMA_WARPS, (A.row_end - A.row_begin + Rt - 1) / Rt);
       kern<<<gt, bt, TMA_WARPS * tma_warp_bytes(MODE), stream>>>(*m_in, m_base ? *m_base : *m_in, A, h->g, h->phys, Rt);
     } else {
@@ -878,6 +903,96 @@ int reset_clock(wb_fv2d* h) {
   return launch_max_speed(h, h->u, 0, use_fast(h));
 }
 
+// ---- peer-memory ghost rows ------------------------------------------------------------------------------------
+// The boundary-row launch has stored its rows into the neighbours' ghost rows itself; what is left of the "exchange"
+// is one flag per direction: k_peer_signal (after the boundary launch, same stream: its stores are complete) publishes
+// the exchange number in the neighbours' flag words, k_peer_wait spins until both neighbours have published theirs.
+// No WAR hazard needs a second flag: a rank can only write ghost rows of stage s+1 after it has seen the neighbour's
+// flag of stage s, and the neighbour raises that flag after the only kernel that reads those ghost rows.
+__global__ void k_peer_signal(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long seq) {
+  __threadfence_system();
+  if (lo_flag) *reinterpret_cast<volatile unsigned long long*>(lo_flag) = seq;      // I am the slab ABOVE my lower neighbour: its word [1]
+  if (hi_flag) *reinterpret_cast<volatile unsigned long long*>(hi_flag) = seq;      // ... and BELOW my upper neighbour: its word [0]
+  __threadfence_system();
+}
+__global__ void k_peer_wait(unsigned long long* flags, int has_lo, int has_hi, unsigned long long seq) {
+  const volatile unsigned long long* f = flags;
+  const long long t0 = clock64();
+  while ((has_lo && f[0] < seq) || (has_hi && f[1] < seq)) {
+    if (clock64() - t0 > 20000000000LL) { flags[2] = seq; break; }      // ~10 s: a neighbour died; reported by wb_fv2d_sync
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+struct PeerRecord {      // what a rank tells the others (all-gathered once at comm_init)
+  cudaIpcMemHandle_t u, w1, flags;
+  unsigned long long plane;
+  int nyl, ok, dev, pad;
+};
+
+void peer_close(wb_fv2d* h) {
+  wb_fv2d::Peer& P = h->peer;
+  void* mapped[] = {P.lo_u, P.lo_w1, P.lo_flags, P.hi_u, P.hi_w1, P.hi_flags};
+  for (void* m : mapped)
+    if (m) cudaIpcCloseMemHandle(m);
+  P.lo_u = P.lo_w1 = P.hi_u = P.hi_w1 = nullptr;
+  P.lo_flags = P.hi_flags = nullptr;
+  P.active = false;
+}
+
+// Collective over the communicator.  Any failure on any rank (no IPC, no peer access, WB_FV2D_P2P=0) leaves every rank on
+// the NCCL send/recv path: the decision is all-reduced.
+int peer_setup(wb_fv2d* h) {
+  wb_fv2d::Peer& P = h->peer;
+  const int R = h->prm.nranks, r = h->prm.rank;
+  const char* env = getenv("WB_FV2D_P2P");
+  int ok = (!env || atoi(env) != 0) && h->tma_ok && h->overlap && h->g.nyl >= 3;
+  PeerRecord mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && !P.flags) ok = cudaMalloc(&P.flags, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(P.flags, 0, 4 * sizeof(unsigned long long), h->stream) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.u, h->u) == cudaSuccess && cudaIpcGetMemHandle(&mine.w1, h->w1) == cudaSuccess &&
+               cudaIpcGetMemHandle(&mine.flags, P.flags) == cudaSuccess;
+  cudaGetLastError();
+  mine.plane = h->g.plane; mine.nyl = h->g.nyl; mine.ok = ok; mine.dev = h->dev;
+  PeerRecord* d_all = nullptr;
+  std::vector<PeerRecord> all(R);
+  WB_CUDA(cudaMalloc(&d_all, sizeof(PeerRecord) * (R + 1)));
+  WB_CUDA(cudaMemcpyAsync(d_all + R, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  int st = nccl_allgather_bytes(h->comm, d_all + R, d_all, sizeof(PeerRecord), h->stream);
+  if (st == WB_OK) {
+    WB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerRecord) * R, cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(d_all);
+  WB_CHECK(st);
+  for (int k = 0; k < R; ++k) ok = ok && all[k].ok;
+  auto open = [&](const cudaIpcMemHandle_t& hd, void** out) {
+    return cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  };
+  if (ok && r > 0) {
+    ok = open(all[r - 1].u, (void**)&P.lo_u) && open(all[r - 1].w1, (void**)&P.lo_w1) && open(all[r - 1].flags, (void**)&P.lo_flags);
+    P.lo_plane = all[r - 1].plane; P.lo_nyl = all[r - 1].nyl;
+  }
+  if (ok && r < R - 1) {
+    ok = open(all[r + 1].u, (void**)&P.hi_u) && open(all[r + 1].w1, (void**)&P.hi_w1) && open(all[r + 1].flags, (void**)&P.hi_flags);
+    P.hi_plane = all[r + 1].plane; P.hi_nyl = all[r + 1].nyl;
+  }
+  cudaGetLastError();
+  // every rank must have opened its neighbours, or nobody uses the mapping
+  unsigned long long* d_bad = h->ctrl ? &h->ctrl->cmax_bits[0] : nullptr;      // scratch word (reset_clock rewrites it)
+  unsigned long long bad = ok ? 0ull : 1ull;
+  WB_CUDA(cudaMemcpyAsync(d_bad, &bad, sizeof(bad), cudaMemcpyHostToDevice, h->stream));
+  WB_CHECK(nccl_allreduce_max_u64(h->comm, d_bad, 1, h->stream));
+  WB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (bad) { peer_close(h); return WB_OK; }
+  P.active = true;
+  P.seq = 0;
+  return WB_OK;
+}
+
 // One RK stage in slab mode: the two boundary rows first (on the comm stream, followed by the NCCL send/recv of
 // those rows into the neighbours' ghost rows), the interior rows concurrently on the main stream.
 template <int MODE>
@@ -891,7 +1006,18 @@ int stage_with_exchange(wb_fv2d* h, const double* in, const double* base, double
   WB_CUDA(cudaEventRecord(h->ev_main, h->stream));               // inputs (and their ghosts) are ready
   WB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
   WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 0, nyl, h->comm_stream, true)));     // rows 0 and nyl-1, one launch
-  WB_CHECK(exchange_ghost_rows(h, out, 4, h->comm_stream));
+  // (the peer stores exist in the TMA-fed kernel only; whether it runs is decided from all-reduced flags: the same on every rank)
+  const bool tma_path = use_fast(h) && h->tma_ok && (in == h->u || in == h->w1) && (MODE != 2 || base == h->u || base == h->w1);
+  if (h->peer.active && tma_path) {      // the launch stored the rows into the neighbours' ghost rows itself: publish / await the flags
+    wb_fv2d::Peer& Pp = h->peer;
+    ++Pp.seq;
+    k_peer_signal<<<1, 1, 0, h->comm_stream>>>(Pp.lo_flags ? Pp.lo_flags + 1 : nullptr, Pp.hi_flags ? Pp.hi_flags + 0 : nullptr, Pp.seq);
+    WB_LAUNCH_CHECK();
+    k_peer_wait<<<1, 1, 0, h->comm_stream>>>(Pp.flags, Pp.lo_flags != nullptr, Pp.hi_flags != nullptr, Pp.seq);
+    WB_LAUNCH_CHECK();
+  } else {
+    WB_CHECK(exchange_ghost_rows(h, out, 4, h->comm_stream));
+  }
   WB_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
   WB_CHECK((launch_stage<MODE>(h, in, base, out, tend, -1, true, 1, nyl - 1, h->stream)));
   WB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));        // next stage needs the ghosts
@@ -994,6 +1120,13 @@ int wb_fv2d_destroy(wb_fv2d* h) {
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
   output_wait(&h->out_job);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->peer.active && h->comm) {      // nobody frees a buffer a neighbour still has mapped: close, meet, then free
+    peer_close(h);
+    nccl_allreduce_max_u64(h->comm, &h->ctrl->cmax_bits[0], 1, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(h->peer.flags);
   nccl_comm_destroy(h->comm);
   cudaFree(h->u); cudaFree(h->w1); cudaFree(h->weq); cudaFree(h->eqz); cudaFree(h->stage); cudaFree(h->tab);
   cudaFree(h->ctrl); cudaFree(h->eqflag);
@@ -1026,8 +1159,14 @@ int wb_fv2d_comm_init(wb_fv2d* h, const void* id128) {
   if (!h || !id128) { set_error("null argument"); return WB_ERR_ARG; }
   WB_REQUIRE(h->prm.nranks > 1, "comm_init needs nranks > 1");
   WB_CUDA(cudaSetDevice(h->dev));
-  if (h->comm) { nccl_comm_destroy(h->comm); h->comm = nullptr; }
-  return nccl_comm_create(&h->comm, id128, h->prm.rank, h->prm.nranks);
+  if (h->comm) { peer_close(h); nccl_comm_destroy(h->comm); h->comm = nullptr; }
+  WB_CHECK(nccl_comm_create(&h->comm, id128, h->prm.rank, h->prm.nranks));
+  return peer_setup(h);
+}
+
+const char* wb_fv2d_exchange_kind(const wb_fv2d* h) {
+  if (!h || h->prm.nranks <= 1) return "none";
+  return h->peer.active ? "p2p" : "nccl";
 }
 
 int wb_fv2d_upload(wb_fv2d* h, const double* u, const double* w_eq) {
@@ -1106,6 +1245,11 @@ int wb_fv2d_sync(wb_fv2d* h, int* iters_out, double* t_out, double* last_dt_out,
   WB_CUDA(cudaSetDevice(h->dev));
   WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->peer.active) {      // a ghost-row wait that gave up (a neighbour never published its flag) must not pass silently
+    unsigned long long err = 0;
+    WB_CUDA(cudaMemcpy(&err, h->peer.flags + 2, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) { set_error("peer-memory ghost-row exchange %llu timed out (a neighbouring rank stopped)", err); return WB_ERR_NCCL; }
+  }
   int s = (h->h_ctrl->iter[1] > h->h_ctrl->iter[0]) ? 1 : 0;
   if (iters_out) *iters_out = h->h_ctrl->iter[s];
   if (t_out) *t_out = h->h_ctrl->t[s];

@@ -214,6 +214,16 @@ __device__ __forceinline__ void tma_row(const StageArgs& A, const Grid& g, const
   double* dst = A.out + ((size_t)(j + 1) * g.pitch + c.i);
   st_if(dst, o.n0, c.writer); st_if(dst + g.plane, o.n1, c.writer); st_if(dst + 2 * g.plane, o.n2, c.writer);
   st_if(dst + 3 * g.plane, o.n3, c.writer);
+  if (S < 0) {      // only the generic (tail) instantiation: the slab's boundary rows are one-row strips
+    double* pr = nullptr;
+    size_t pp = 0;
+    if (j == 0 && A.peer_lo) { pr = A.peer_lo; pp = A.peer_lo_plane; }
+    else if (j == g.nyl - 1 && A.peer_hi) { pr = A.peer_hi; pp = A.peer_hi_plane; }
+    if (pr) {       // the same row into the neighbour's ghost row (peer memory, NVLink)
+      pr += c.i;
+      st_if(pr, o.n0, c.writer); st_if(pr + pp, o.n1, c.writer); st_if(pr + 2 * pp, o.n2, c.writer); st_if(pr + 3 * pp, o.n3, c.writer);
+    }
+  }
   if (MODE == 2) {
     const double s = centre_speed(A, g, P, (size_t)(j + 1) * g.pitch + min(c.i, g.nx - 1), ec, o.n0, o.n1, o.n2, o.n3);
     spd = (c.writer && s > spd) ? s : spd;

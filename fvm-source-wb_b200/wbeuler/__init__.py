@@ -125,6 +125,13 @@ class FV2D:
     def comm_init(self, unique_id_bytes):
         _check(lib().wb_fv2d_comm_init(self._h, C.c_char_p(unique_id_bytes)))
 
+    def exchange_kind(self):
+        """'p2p' (ghost rows stored into peer memory by the stage kernel), 'nccl' (send/recv) or 'none' (single rank)"""
+        f = lib().wb_fv2d_exchange_kind
+        f.restype = C.c_char_p
+        f.argtypes = [C.c_void_p]
+        return f(self._h).decode()
+
     # -- the reference's routines -----------------------------------------------------------------
     def compute_update_exact(self, u, w_eq):
         """compute_update_exact(u,w_eq,dudt)  benchmark_2d.f90:465-618"""

@@ -77,6 +77,10 @@ int wb_fv2d_set_stream(wb_fv2d* h, void* cuda_stream);
 /* nranks > 1 only: create the NCCL communicator used for the per-stage ghost-row send/recv and
  * the per-step max all-reduce */
 int wb_fv2d_comm_init(wb_fv2d* h, const void* nccl_unique_id128);
+/* how the per-stage ghost rows travel: "p2p" = the boundary-row launch of the stage kernel stores them straight into the
+ * neighbours' ghost rows (buffers mapped with CUDA IPC at comm_init, one flag word per direction), "nccl" = ncclSend/ncclRecv
+ * (fallback when IPC / peer access is unavailable or WB_FV2D_P2P=0), "none" = single rank.  No reference counterpart. */
+const char* wb_fv2d_exchange_kind(const wb_fv2d* h);
 
 /* --- stateless entries: same contract as the Fortran routines (host arrays in, host arrays out;
  *     H2D + kernel + D2H inside the call).  In slab mode the arrays are the LOCAL rows. -------- */

@@ -17,10 +17,14 @@ rank, world, local_rank = wd.env_rank_world()
 torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 ok = True
+kinds = set()
 for arith in (0, 1):
-    for overlap in ("1", "0"):
+    # ghost rows by peer-memory stores of the stage kernel / by NCCL send-recv overlapped with the interior / not overlapped
+    for overlap, p2p in (("1", "1"), ("1", "0"), ("0", "0")):
         os.environ["WB_FV2D_OVERLAP"] = overlap
+        os.environ["WB_FV2D_P2P"] = p2p
         s = wd.make_slab_solver(wbeuler.FV2D, world, rank, local_rank, nx=nx, ny=ny, arith=arith)
+        kinds.add(s.exchange_kind())
         # global fields from the library's own generator on a single-GPU handle (every rank, deterministic)
         with wbeuler.FV2D(nx, ny, arith=arith, device=local_rank) as one:
             u, weq = one.get_initial_conditions(3)
@@ -35,7 +39,8 @@ for arith in (0, 1):
         with wbeuler.FV2D(nx, ny, arith=arith, device=local_rank) as one:
             dref = one.compute_update_exact(u, weq)
         same = np.array_equal(full, ref_single) and it == it1 and t == t1 and c_slab == c_single and np.array_equal(dfull, dref)
-        msg = f"rank {rank}/{world} arith={arith} overlap={overlap}: slab == single-GPU bitwise: {same} (iters {it}, t {t:.6e})"
+        msg = (f"rank {rank}/{world} arith={arith} overlap={overlap} exchange={s.exchange_kind()}: slab == single-GPU bitwise: {same} "
+               f"(iters {it}, t {t:.6e})")
         if rank == 0:
             from oracle import wb_oracle as o
             p = o.fv2d_params(nx, ny)
@@ -47,5 +52,7 @@ for arith in (0, 1):
         ok = ok and same
         s.close()
         dist.barrier()
+if rank == 0:
+    print("exchange kinds exercised:", sorted(kinds), flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
