@@ -109,6 +109,22 @@ __global__ void k_modes_from_nodes(const double* __restrict__ nodes, double* __r
       for (int i = 0; i < M; ++i) PL(modes, g, v, j * M + i)[e] = md[v][i][j];
 }
 
+// Is the gravity field separable?  gx(qy,qx; j,i) == gx(0,qx; j0,i) and gy(qy,qx; j,i) == gy(qy,0; j,0) for every owned
+// element and node, compared bit for bit (so a NaN says no).  flag[0] is cleared on the first difference.
+__global__ void k_grad_sep_check(const double* __restrict__ gx, const double* __restrict__ gy, DgGrid g, int row0, int row1,
+                                 int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = row0 + blockIdx.y;
+  if (i >= g.nx || j >= row1) return;
+  bool same = true;
+  for (int qy = 0; qy < g.m; ++qy)
+    for (int qx = 0; qx < g.m; ++qx) {
+      const size_t e = (size_t)(qy * g.m + qx) * g.ne + (size_t)j * g.nx + i;
+      same = same && gx[e] == gx[(size_t)qx * g.ne + (size_t)row0 * g.nx + i] &&
+             gy[e] == gy[(size_t)(qy * g.m) * g.ne + (size_t)j * g.nx];
+    }
+  if (!same) *flag = 0;
+}
+
 // grad_phi :1599-1644 at every node, once per upload (x, y are static)
 __global__ void k_grad_phi(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ gx,
                            double* __restrict__ gy, size_t n, int grad_phi_case) {
@@ -1262,6 +1278,23 @@ int dg_ensure(wb_dg2d* h, double** buf) {
   if (!*buf) WB_CUDA(cudaMalloc(buf, sizeof(double) * h->nfield));
   return WB_OK;
 }
+// after k_grad_phi: decide once whether the stage kernel may read the gravity field from its separable lines
+int dg_grad_sep(wb_dg2d* h) {
+  h->phys.gsep = 0;
+  h->phys.grow = h->g.slab ? 1 : 0;
+  if (h->phys.source != 2) return WB_OK;
+  const int row0 = h->phys.grow, row1 = h->g.slab ? h->g.ny - 1 : h->g.ny;
+  int one = 1, *flag = reinterpret_cast<int*>(h->part2);      // scratch of the max-speed scan: free outside a step
+  WB_CUDA(cudaMemcpyAsync(flag, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  dim3 b(128), gr((h->g.nx + 127) / 128, row1 - row0);
+  k_grad_sep_check<<<gr, b, 0, h->stream>>>(h->gx, h->gy, h->g, row0, row1, flag);
+  WB_LAUNCH_CHECK();
+  WB_CUDA(cudaMemcpyAsync(&one, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (const char* e = getenv("WB_DG2D_GSEP")) one = one && atoi(e) != 0;
+  h->phys.gsep = one;
+  return WB_OK;
+}
 int dg_h2d_field(wb_dg2d* h, const double* host, double* soa) {
   WB_CHECK(dg_ensure(h, &h->stage));
   WB_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * 4 * h->g.nm * h->g.ne_own, cudaMemcpyHostToDevice, h->stream));
@@ -1297,6 +1330,7 @@ int dg_set_xy(wb_dg2d* h, const double* x, const double* y) {
   if (h->phys.source == 2) {
     k_grad_phi<<<gr, b, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case);
     WB_LAUNCH_CHECK();
+    WB_CHECK(dg_grad_sep(h));
   }
   if (h->phys.ninit == 12) {
     k_freeze_mask<<<gr, b, 0, h->stream>>>(h->xy, h->xy + n, h->fz, n, h->prm.boxlen_x / 2., h->prm.boxlen_y / 2.);
@@ -1723,6 +1757,7 @@ int wb_dg2d_create(wb_dg2d** out, const wb_dg2d_params* p) {
   P.oneoverdx = 1. / P.dx;
   P.eps = p->eps; P.M = p->M;
   P.rho_floor = (double)10e-10f; P.p_floor = 1e-10;
+  P.gsep = 0; P.grow = 0;
   P.bc = p->bc; P.source = p->source; P.flux_id = p->flux_id; P.ninit = p->ninit;
   {
     const int gll = h->B.gll;
@@ -2010,7 +2045,11 @@ int wb_dg2d_init_device(wb_dg2d* h, int ninit, double eta) {
   WB_CHECK(dg_fill_initial_nodes(h, ninit, eta, need_xy, 0.0, 0.0));
   if (need_xy) {
     dim3 b2(256), g2((unsigned)((n + 255) / 256));
-    if (h->phys.source == 2) { k_grad_phi<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case); WB_LAUNCH_CHECK(); }
+    if (h->phys.source == 2) {
+      k_grad_phi<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->gx, h->gy, n, h->prm.grad_phi_case);
+      WB_LAUNCH_CHECK();
+      WB_CHECK(dg_grad_sep(h));
+    }
     if (h->phys.ninit == 12) { k_freeze_mask<<<g2, b2, 0, h->stream>>>(h->xy, h->xy + n, h->fz, n, h->prm.boxlen_x / 2., h->prm.boxlen_y / 2.); WB_LAUNCH_CHECK(); }
   }
   h->have_xy = true;

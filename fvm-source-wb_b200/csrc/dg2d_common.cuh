@@ -25,6 +25,9 @@ struct DgPhys {
   double dt_num;              // cfl*min(1/9, gll_w_1/2)
   int bc, source, flux_id, ninit;
   double rho_floor, p_floor;  // (double)10e-10f of compute_primitive (:898) and the 1d-10 of the sound speed (:980)
+  int gsep, grow;             // gravity field found separable at upload (gx = f(column, qx), gy = f(row, qy), e.g. the shipped
+                              // grad_phi_case 1 on the tensor-product grid): the stage kernel then reads gx from the one row
+                              // `grow` and gy from column 0 -- L2-resident lines instead of 144 B of DRAM per element and stage
 };
 struct DgCtrl {
   double t, dt, tend;

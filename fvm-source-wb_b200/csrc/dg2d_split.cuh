@@ -169,7 +169,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A0 + po));
       if (C.na >= 2 && C.A1 != in) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.A1 + po));
       if (OUT2) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.B1 + po));
-      if (SRC && v == 0 && P.source == 2) {                  // the gravity field of the next row (read by the node items of phase B)
+      if (SRC && v == 0 && P.source == 2 && !P.gsep) {       // the gravity field of the next row (read by the node items of phase B)
         const size_t pg = (size_t)(lane >> 1) * g.ne + (size_t)(j + 1) * g.nx + ic0 + (lane & 1) * 16;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gx + pg));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + pg));
@@ -184,8 +184,11 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
       for (int i = 0; i < NG; ++i) {
         const int k = v + 4 * i;                             // node k = qx*M + qy; the arrays are ordered qy*M + qx
         if (k < NM) {
-          const size_t ge = (size_t)((k % M) * M + k / M) * g.ne + (size_t)j * g.nx + ic0 + lane;
-          ga[SRC ? i : 0] = gx[ge]; gb[SRC ? i : 0] = gy[ge];
+          const int qx = k / M, qy = k % M;
+          const size_t ge = (size_t)(qy * M + qx) * g.ne + (size_t)j * g.nx + ic0 + lane;
+          // separable field (DgPhys::gsep): the same numbers from the one row of gx / the one column of gy that stay in L2
+          ga[SRC ? i : 0] = gx[P.gsep ? (size_t)qx * g.ne + (size_t)P.grow * g.nx + ic0 + lane : ge];
+          gb[SRC ? i : 0] = gy[P.gsep ? (size_t)(qy * M) * g.ne + (size_t)j * g.nx : ge];
         }
       }
     }
