@@ -857,6 +857,8 @@ int launch_stage(wb_fv2d* h, const double* in, const double* base, double* out, 
         configured = true;
       }
       int Rt = std::min(R, TMA_MAX_ROWS);            // the per-warp y tables hold one strip
+      if ((A.row_end - A.row_begin + Rt - 1) / Rt > 65535) Rt = TMA_MAX_ROWS;      // grid.y limit (ny up to 4.19e6 rows per slab)
+      if ((A.row_end - A.row_begin + Rt - 1) / Rt > 65535) { set_error("slab of %d rows is too tall for one launch", A.row_end - A.row_begin); return WB_ERR_ARG; }
       A.rows_cap = Rt;
       if (edge_pair) {
         Rt = h->g.nyl - 1; A.rows_cap = 1; A.row_begin = 0; A.row_end = h->g.nyl;
