@@ -373,6 +373,26 @@ def test_split_kernel_equals_the_two_sided_ones(wb, oracle, monkeypatch, nx, mx,
     assert np.array_equal(a, b) and (it, t, dt) == (it2, t2, dt2)
 
 
+@pytest.mark.parametrize("rk_rows", [32, 5])
+def test_separable_gravity_field_is_only_a_different_address(wb, oracle, monkeypatch, rk_rows):
+    """grad_phi_case 1 on the tensor-product grid gives gx = f(column, qx), gy = f(row, qy): the stage kernel then reads the field
+    from one row of gx / one column of gy (L2-resident) instead of streaming 18 doubles per element.  The numbers are the same
+    numbers, so the bits must be: WB_DG2D_GSEP=0 forces the general addressing."""
+    kw = dict(flux="llf1", limiter="ONP", solver="RK4", ninit=2, source=2, grad_phi_case=1)
+    p, _, x, y = mk(oracle, wb, 64, 3, arith=0, bc=2, **kw)
+    u0 = oracle.dg2d_get_initial_conditions(p, x, y)
+    monkeypatch.setenv("WB_DG2D_ROWS", str(rk_rows))
+    with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, bc=2, **kw) as s:
+        a = s.evolve(u0, x, y, 1.0, 3)
+        assert s.stage_kernel() == "split"
+    monkeypatch.setenv("WB_DG2D_GSEP", "0")
+    with wb.DG2D(nx=64, ny=64, mx=3, my=3, arith=0, bc=2, **kw) as s:
+        b = s.evolve(u0, x, y, 1.0, 3)
+    assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    ref = oracle.dg2d_evolve(p, u0, x, y, 1.0, 3)[0]
+    assert rel(a[0], ref) <= 1e-12
+
+
 @pytest.mark.parametrize("mx", [2, 3, 4])
 def test_split_kernel_limiter_point_evaluations(wb, oracle, monkeypatch, mx):
     """Elements that fail the sufficient test of 'ONP' take the point evaluations of compute_positivity

@@ -263,3 +263,9 @@ def test_output_file_of_the_resident_state(wb, oracle, tmp_path):
     assert np.allclose(tab[..., 0], x.T if x.ndim == 2 else x[:, None], rtol=1e-5, atol=0)
     assert np.abs(tab[..., 2] - dp).max() <= 1e-5 * np.abs(dp).max() + 1e-17
     assert lines[0][:12] == "%12.5E" % float(x.flat[0])
+
+
+def test_single_rank_has_no_ghost_exchange(wb):
+    """wb_fv2d_exchange_kind: 'none' on one rank ('p2p' / 'nccl' on slabs: tools/slab_parity.py exercises both)"""
+    with wb.FV2D(64, 48) as s:
+        assert s.exchange_kind() == "none"
