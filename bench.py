@@ -305,8 +305,8 @@ def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
                                     solver="RK4", ninit=1, bc=1)
             s.set_stream(stream.cuda_stream)
             s.init_device(1)
-            s.step_async(5); s.sync()
-            steps = max(2, min(args.steps, 10))
+            s.step_async(3); s.sync()                      # W = 3 warm-up steps (15 stage launches, 0.25 s at 8192^2)
+            steps = max(2, min(args.steps, 5))             # K <= 5 timed steps = 25 stage launches of 17 ms each
             sampler = ClockSampler(local_rank)
             if rank == 0:
                 sampler.start()
