@@ -317,6 +317,35 @@ int output_wait(OutputJob** job) {
   return st;
 }
 
+// ---------------------------------------------------------------- peer-memory ghost rows: the flag protocol (common.cuh)
+namespace {
+__global__ void k_peer_signal(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long seq) {
+  __threadfence_system();
+  if (lo_flag) *reinterpret_cast<volatile unsigned long long*>(lo_flag) = seq;
+  if (hi_flag) *reinterpret_cast<volatile unsigned long long*>(hi_flag) = seq;
+  __threadfence_system();
+}
+__global__ void k_peer_wait(unsigned long long* flags, int has_lo, int has_hi, unsigned long long seq) {
+  const volatile unsigned long long* f = flags;
+  const long long t0 = clock64();
+  while ((has_lo && f[0] < seq) || (has_hi && f[1] < seq)) {
+    if (clock64() - t0 > 20000000000LL) { flags[2] = seq; break; }      // ~10 s: a neighbour died
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+}  // namespace
+int peer_signal(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long seq, cudaStream_t s) {
+  k_peer_signal<<<1, 1, 0, s>>>(lo_flag, hi_flag, seq);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+int peer_wait(unsigned long long* flags, int has_lo, int has_hi, unsigned long long seq, cudaStream_t s) {
+  k_peer_wait<<<1, 1, 0, s>>>(flags, has_lo, has_hi, seq);
+  WB_LAUNCH_CHECK();
+  return WB_OK;
+}
+
 }  // namespace wb
 
 extern "C" {

@@ -1253,6 +1253,18 @@ struct wb_dg2d {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
   bool overlap = true;
+  // ... and with the neighbours' four state buffers mapped (CUDA IPC) the boundary-row launches store their rows straight
+  // into the neighbours' ghost rows: no pack / NCCL / unpack, one flag word per direction (common.cuh: peer_signal / peer_wait)
+  struct Peer {
+    bool active = false;
+    double* lo[4] = {nullptr, nullptr, nullptr, nullptr};      // the lower neighbour's buffers, in the order of map_ptr[]
+    double* hi[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *lo_flags = nullptr, *hi_flags = nullptr, *flags = nullptr;
+    size_t lo_ne = 0, hi_ne = 0;
+    int lo_ny = 0, hi_ny = 0;
+    bool same = false;                                         // two ranks on a ring: both neighbours are the one other rank
+    unsigned long long seq = 0;
+  } peer;
   // TMA-staged stage kernel: one 3-D tensor map (column, row, plane) per state buffer
   bool tma_ok = false;
   int march_rows = 32;         // rows per strip of k_dg_stage_split
@@ -1543,6 +1555,114 @@ int dg_make_map(const wb_dg2d* h, const double* base, CUtensorMap* out) {
   return WB_OK;
 }
 
+// ---- peer-memory ghost rows (see wb_dg2d::Peer) -----------------------------------------------------------------
+int dg_buffer_index(const wb_dg2d* h, const double* p) {
+  for (int k = 0; k < 4; ++k)
+    if (h->map_ptr[k] == p) return k;
+  return -1;
+}
+// ghost-row targets of `out` (and `out2`) on the neighbours, or on the rank itself at a clamped global edge
+bool dg_peer_targets(const wb_dg2d* h, const double* out, const double* out2, StageCoef& C) {
+  const wb_dg2d::Peer& P = h->peer;
+  const int k = dg_buffer_index(h, out), k2 = out2 ? dg_buffer_index(h, out2) : -1;
+  if (k < 0 || (out2 && k2 < 0)) return false;
+  const size_t nx = h->g.nx;
+  // lower side: the neighbour's TOP ghost row (its local row ny-1); clamped edge: my own row 0
+  double* lo = P.lo[k] ? P.lo[k] : const_cast<double*>(h->map_ptr[k]);
+  double* lo2 = out2 ? (P.lo[k2] ? P.lo[k2] : const_cast<double*>(h->map_ptr[k2])) : nullptr;
+  const size_t lo_row = P.lo[k] ? (size_t)(P.lo_ny - 1) : 0;
+  C.peer_lo_ne = P.lo[k] ? P.lo_ne : h->g.ne;
+  C.peer_lo = lo + lo_row * nx;
+  C.peer2_lo = lo2 ? lo2 + lo_row * nx : nullptr;
+  // upper side: the neighbour's BOTTOM ghost row (its local row 0); clamped edge: my own row ny-1
+  double* hi = P.hi[k] ? P.hi[k] : const_cast<double*>(h->map_ptr[k]);
+  double* hi2 = out2 ? (P.hi[k2] ? P.hi[k2] : const_cast<double*>(h->map_ptr[k2])) : nullptr;
+  const size_t hi_row = P.hi[k] ? 0 : (size_t)(h->g.ny - 1);
+  C.peer_hi_ne = P.hi[k] ? P.hi_ne : h->g.ne;
+  C.peer_hi = hi + hi_row * nx;
+  C.peer2_hi = hi2 ? hi2 + hi_row * nx : nullptr;
+  return true;
+}
+
+struct DgPeerRecord {      // all-gathered once at comm_init
+  cudaIpcMemHandle_t buf[4], flags;
+  unsigned long long ne;
+  int ny, ok;
+};
+
+void dg_peer_close(wb_dg2d* h) {
+  wb_dg2d::Peer& P = h->peer;
+  for (int k = 0; k < 4; ++k) {
+    if (P.lo[k]) cudaIpcCloseMemHandle(P.lo[k]);
+    if (P.hi[k] && !P.same) cudaIpcCloseMemHandle(P.hi[k]);
+    P.lo[k] = P.hi[k] = nullptr;
+  }
+  if (P.lo_flags) cudaIpcCloseMemHandle(P.lo_flags);
+  if (P.hi_flags && !P.same) cudaIpcCloseMemHandle(P.hi_flags);
+  P.lo_flags = P.hi_flags = nullptr;
+  P.active = false;
+  cudaGetLastError();
+}
+
+// Collective over the communicator; any failure anywhere leaves every rank on pack / NCCL / unpack (all-reduced decision).
+int dg_peer_setup(wb_dg2d* h) {
+  wb_dg2d::Peer& P = h->peer;
+  const int R = h->nranks, r = h->rank;
+  const bool periodic = (h->phys.bc == 1);
+  const int lo_rank = (r > 0) ? r - 1 : (periodic ? R - 1 : -1), hi_rank = (r < R - 1) ? r + 1 : (periodic ? 0 : -1);
+  const char* env = getenv("WB_DG2D_P2P");
+  int ok = (!env || atoi(env) != 0) && h->tma_ok && h->split_ok && h->overlap && h->comm_stream && h->g.ny >= 6 && h->arith == 0;
+  DgPeerRecord mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && !P.flags) ok = cudaMalloc(&P.flags, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(P.flags, 0, 4 * sizeof(unsigned long long), h->stream) == cudaSuccess;
+  for (int k = 0; k < 4 && ok; ++k) ok = cudaIpcGetMemHandle(&mine.buf[k], const_cast<double*>(h->map_ptr[k])) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.flags, P.flags) == cudaSuccess;
+  cudaGetLastError();
+  mine.ne = h->g.ne; mine.ny = h->g.ny; mine.ok = ok;
+  DgPeerRecord* d_all = nullptr;
+  std::vector<DgPeerRecord> all(R);
+  WB_CUDA(cudaMalloc(&d_all, sizeof(DgPeerRecord) * (R + 1)));
+  WB_CUDA(cudaMemcpyAsync(d_all + R, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  int st = nccl_allgather_bytes(h->comm, d_all + R, d_all, sizeof(DgPeerRecord), h->stream);
+  if (st == WB_OK) {
+    WB_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(DgPeerRecord) * R, cudaMemcpyDeviceToHost, h->stream));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(d_all);
+  WB_CHECK(st);
+  for (int k = 0; k < R; ++k) ok = ok && all[k].ok;
+  auto open = [&](const cudaIpcMemHandle_t& hd, void** out) {
+    return cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  };
+  P.same = (lo_rank >= 0 && lo_rank == hi_rank);
+  if (ok && lo_rank >= 0) {
+    for (int k = 0; k < 4 && ok; ++k) ok = open(all[lo_rank].buf[k], (void**)&P.lo[k]);
+    if (ok) ok = open(all[lo_rank].flags, (void**)&P.lo_flags);
+    P.lo_ne = all[lo_rank].ne; P.lo_ny = all[lo_rank].ny;
+  }
+  if (ok && hi_rank >= 0) {
+    if (P.same) {      // a handle is opened once per process
+      for (int k = 0; k < 4; ++k) P.hi[k] = P.lo[k];
+      P.hi_flags = P.lo_flags;
+    } else {
+      for (int k = 0; k < 4 && ok; ++k) ok = open(all[hi_rank].buf[k], (void**)&P.hi[k]);
+      if (ok) ok = open(all[hi_rank].flags, (void**)&P.hi_flags);
+    }
+    P.hi_ne = all[hi_rank].ne; P.hi_ny = all[hi_rank].ny;
+  }
+  cudaGetLastError();
+  double bad = ok ? 0.0 : 1.0;      // every rank has its neighbours mapped, or nobody uses the mappings
+  WB_CUDA(cudaMemcpyAsync(h->red, &bad, sizeof(bad), cudaMemcpyHostToDevice, h->stream));
+  WB_CHECK(nccl_allreduce_max_f64(h->comm, h->red, 1, h->stream));
+  WB_CUDA(cudaMemcpyAsync(&bad, h->red, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+  WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (bad != 0.0) { dg_peer_close(h); return WB_OK; }
+  P.active = true;
+  P.seq = 0;
+  return WB_OK;
+}
+
 // one fused launch: out = limiter(c0*A0 + c1*A1 + cd*dt*L(in)) [+ the optional second combination]
 int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, double c0, const double* A1, double c1, double cd,
                   double* out2 = nullptr, const double* B0 = nullptr, double k0 = 0, const double* B1 = nullptr, double k1 = 0,
@@ -1556,6 +1676,7 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
   StageCoef C;
   C.A0 = A0; C.A1 = A1; C.c0 = c0; C.c1 = c1; C.cd = cd; C.na = A1 ? 2 : 1;
   C.out2 = out2; C.B0 = B0; C.B1 = B1; C.k0 = k0; C.k1 = k1; C.k2 = k2; C.k3 = lim_after ? 0.0 : k3; C.ke = ke;
+  C.peer_lo = C.peer_hi = C.peer2_lo = C.peer2_hi = nullptr; C.peer_lo_ne = C.peer_hi_ne = 0;
   const int onp = (h->prm.limiter_id == 1 && h->g.m > 1) ? 1 : 0;
   const CUtensorMap* m_in = nullptr;
   if (h->tma_ok)
@@ -1568,11 +1689,21 @@ int dg_stage_fast(wb_dg2d* h, const double* in, double* out, const double* A0, d
     const int ny = h->g.ny;
     WB_CUDA(cudaEventRecord(h->ev_main, h->stream));
     WB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
-    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, 1, 2, h->comm_stream));
-    WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, ny - 2, ny - 1,
+    StageCoef Ce = C;                       // the two boundary-row launches: with the peer ghost rows when they are mapped
+    const bool p2p = h->peer.active && dg_peer_targets(h, out, out2, Ce);
+    WB_CHECK(launch_stage_split(m_in, in, Ce, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, 1, 2, h->comm_stream));
+    WB_CHECK(launch_stage_split(m_in, in, Ce, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, ny - 2, ny - 1,
                                 h->comm_stream));
-    WB_CHECK(dg_exchange(h, out, h->comm_stream));
-    if (out2) WB_CHECK(dg_exchange(h, out2, h->comm_stream));
+    if (p2p) {
+      wb_dg2d::Peer& Pp = h->peer;
+      ++Pp.seq;
+      // I am the slab ABOVE my lower neighbour (its word [1]) and BELOW my upper one (its word [0])
+      WB_CHECK(peer_signal(Pp.lo_flags ? Pp.lo_flags + 1 : nullptr, Pp.hi_flags ? Pp.hi_flags + 0 : nullptr, Pp.seq, h->comm_stream));
+      WB_CHECK(peer_wait(Pp.flags, Pp.lo_flags != nullptr, Pp.hi_flags != nullptr, Pp.seq, h->comm_stream));
+    } else {
+      WB_CHECK(dg_exchange(h, out, h->comm_stream));
+      if (out2) WB_CHECK(dg_exchange(h, out2, h->comm_stream));
+    }
     WB_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
     WB_CHECK(launch_stage_split(m_in, in, C, stage_out, h->gx, h->gy, fz, h->g, h->phys, h->FB, h->ctrl, onp, h->march_rows, 2, ny - 2, h->stream));
     WB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
@@ -1837,7 +1968,14 @@ int wb_dg2d_destroy(wb_dg2d* h) {
   cudaFree(h->du); cudaFree(h->A); cudaFree(h->Bf); cudaFree(h->C); cudaFree(h->D); cudaFree(h->E); cudaFree(h->stage);
   cudaFree(h->gx); cudaFree(h->gy); cudaFree(h->xy); cudaFree(h->fz); cudaFree(h->ctrl); cudaFree(h->part1); cudaFree(h->part2);
   cudaFree(h->sbuf_lo); cudaFree(h->sbuf_hi); cudaFree(h->rbuf_lo); cudaFree(h->rbuf_hi); cudaFree(h->red);
-  if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->peer.active && h->comm) {      // nobody frees a buffer a neighbour still has mapped: close, meet, then free
+    dg_peer_close(h);
+    nccl_allreduce_max_f64(h->comm, h->red, 1, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(h->peer.flags);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   nccl_comm_destroy(h->comm);
@@ -1860,8 +1998,14 @@ int wb_dg2d_comm_init(wb_dg2d* h, const void* id128) {
   if (!h || !id128) { set_error("null argument"); return WB_ERR_ARG; }
   WB_REQUIRE(h->nranks > 1, "comm_init needs nranks > 1");
   WB_CUDA(cudaSetDevice(h->dev));
-  if (h->comm) { nccl_comm_destroy(h->comm); h->comm = nullptr; }
-  return nccl_comm_create(&h->comm, id128, h->rank, h->nranks);
+  if (h->comm) { dg_peer_close(h); nccl_comm_destroy(h->comm); h->comm = nullptr; }
+  WB_CHECK(nccl_comm_create(&h->comm, id128, h->rank, h->nranks));
+  return dg_peer_setup(h);
+}
+
+const char* wb_dg2d_exchange_kind(const wb_dg2d* h) {
+  if (!h || h->nranks <= 1) return "none";
+  return h->peer.active ? "p2p" : "nccl";
 }
 
 int wb_dg2d_local_rows(const wb_dg2d* h, int* j0, int* nrows) {
@@ -2089,6 +2233,11 @@ int wb_dg2d_sync(wb_dg2d* h, int* iters_out, double* t_out, double* last_dt_out)
   WB_CUDA(cudaSetDevice(h->dev));
   WB_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(DgCtrl), cudaMemcpyDeviceToHost, h->stream));
   WB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->peer.active) {
+    unsigned long long err = 0;
+    WB_CUDA(cudaMemcpy(&err, h->peer.flags + 2, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) { set_error("peer-memory ghost-row exchange %llu timed out (a neighbouring rank stopped)", err); return WB_ERR_NCCL; }
+  }
   if (iters_out) *iters_out = h->h_ctrl->iter;
   if (t_out) *t_out = h->h_ctrl->t;
   if (last_dt_out) *last_dt_out = h->h_ctrl->dt;

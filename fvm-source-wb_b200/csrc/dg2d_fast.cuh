@@ -37,6 +37,12 @@ struct StageCoef {          // out = limiter( c0*A0 + c1*A1 + cd*dt*L(in) )
   double* out2;
   const double *B0, *B1;
   double k0, k1, k2, k3, ke;
+  // slab boundary-row launches with peer-memory ghost rows (k_dg_stage_split only): local row 1 is ALSO stored into the ghost
+  // row `peer_lo` points at (plane (0,0), column 0 of the lower neighbour's top ghost row -- or of the rank's own bottom ghost
+  // row at a clamped global edge), local row ny-2 into `peer_hi`; plane strides of those fields in peer_*_ne; peer2_* = the
+  // same for out2.  All null in every other launch.
+  double *peer_lo, *peer_hi, *peer2_lo, *peer2_hi;
+  size_t peer_lo_ne, peer_hi_ne;
 };
 
 namespace fastm {

@@ -118,8 +118,14 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
   if (ctrl->skip) {
     for (int jc = j0; jc < j1; ++jc) {
       const size_t e = (size_t)jc * g.nx + ic0 + lane;
+      double* pp = jc == 1 ? C.peer_lo : jc == g.ny - 2 ? C.peer_hi : nullptr;       // the handed-through rows travel as well
+      const size_t pne = jc == 1 ? C.peer_lo_ne : C.peer_hi_ne;
 #pragma unroll
-      for (int m = 0; m < NM; ++m) PL(out, g, v, m)[e] = PL(in, g, v, m)[e];
+      for (int m = 0; m < NM; ++m) {
+        const double x = PL(in, g, v, m)[e];
+        PL(out, g, v, m)[e] = x;
+        if (pp) pp[((size_t)v * NM + m) * pne + ic0 + lane] = x;
+      }
     }
     return;
   }
@@ -576,6 +582,26 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
     for (int b = 0; b < M; ++b)
 #pragma unroll
       for (int a = 0; a < M; ++a) out[pe + (size_t)(b * M + a) * g.ne] = acc[a][b];
+    // slab boundary-row launches only (StageCoef): the same numbers straight into the neighbour's ghost row -- peer memory over
+    // NVLink.  Kept behind one uniform test and after the ordinary stores so that the other launches pay nothing for it; the
+    // second result is read back from where this thread has just put it.
+    if (C.peer_lo != nullptr || C.peer_hi != nullptr) {
+      double* pp = j == 1 ? C.peer_lo : j == g.ny - 2 ? C.peer_hi : nullptr;
+      const size_t pne = j == 1 ? C.peer_lo_ne : C.peer_hi_ne;
+      if (pp) {
+#pragma unroll
+        for (int b = 0; b < M; ++b)
+#pragma unroll
+          for (int a = 0; a < M; ++a) pp[((size_t)v * NM + b * M + a) * pne + ic0 + lane] = acc[a][b];
+      }
+      if (OUT2) {
+        double* pp2 = j == 1 ? C.peer2_lo : j == g.ny - 2 ? C.peer2_hi : nullptr;
+        if (pp2) {
+#pragma unroll 1
+          for (int m = 0; m < NM; ++m) pp2[((size_t)v * NM + m) * pne + ic0 + lane] = C.out2[pe + (size_t)m * g.ne];
+        }
+      }
+    }
   }
 }
 

@@ -911,22 +911,6 @@ int reset_clock(wb_fv2d* h) {
 // the exchange number in the neighbours' flag words, k_peer_wait spins until both neighbours have published theirs.
 // No WAR hazard needs a second flag: a rank can only write ghost rows of stage s+1 after it has seen the neighbour's
 // flag of stage s, and the neighbour raises that flag after the only kernel that reads those ghost rows.
-__global__ void k_peer_signal(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long seq) {
-  __threadfence_system();
-  if (lo_flag) *reinterpret_cast<volatile unsigned long long*>(lo_flag) = seq;      // I am the slab ABOVE my lower neighbour: its word [1]
-  if (hi_flag) *reinterpret_cast<volatile unsigned long long*>(hi_flag) = seq;      // ... and BELOW my upper neighbour: its word [0]
-  __threadfence_system();
-}
-__global__ void k_peer_wait(unsigned long long* flags, int has_lo, int has_hi, unsigned long long seq) {
-  const volatile unsigned long long* f = flags;
-  const long long t0 = clock64();
-  while ((has_lo && f[0] < seq) || (has_hi && f[1] < seq)) {
-    if (clock64() - t0 > 20000000000LL) { flags[2] = seq; break; }      // ~10 s: a neighbour died; reported by wb_fv2d_sync
-    __nanosleep(200);
-  }
-  __threadfence_system();
-}
-
 struct PeerRecord {      // what a rank tells the others (all-gathered once at comm_init)
   cudaIpcMemHandle_t u, w1, flags;
   unsigned long long plane;
@@ -1013,10 +997,9 @@ int stage_with_exchange(wb_fv2d* h, const double* in, const double* base, double
   if (h->peer.active && tma_path) {      // the launch stored the rows into the neighbours' ghost rows itself: publish / await the flags
     wb_fv2d::Peer& Pp = h->peer;
     ++Pp.seq;
-    k_peer_signal<<<1, 1, 0, h->comm_stream>>>(Pp.lo_flags ? Pp.lo_flags + 1 : nullptr, Pp.hi_flags ? Pp.hi_flags + 0 : nullptr, Pp.seq);
-    WB_LAUNCH_CHECK();
-    k_peer_wait<<<1, 1, 0, h->comm_stream>>>(Pp.flags, Pp.lo_flags != nullptr, Pp.hi_flags != nullptr, Pp.seq);
-    WB_LAUNCH_CHECK();
+    // I am the slab ABOVE my lower neighbour (its word [1]) and BELOW my upper one (its word [0])
+    WB_CHECK(peer_signal(Pp.lo_flags ? Pp.lo_flags + 1 : nullptr, Pp.hi_flags ? Pp.hi_flags + 0 : nullptr, Pp.seq, h->comm_stream));
+    WB_CHECK(peer_wait(Pp.flags, Pp.lo_flags != nullptr, Pp.hi_flags != nullptr, Pp.seq, h->comm_stream));
   } else {
     WB_CHECK(exchange_ghost_rows(h, out, 4, h->comm_stream));
   }

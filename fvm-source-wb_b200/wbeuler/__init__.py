@@ -234,6 +234,13 @@ class DG2D:
         """slab mode: wire the NCCL communicator (every rank, same 128-byte id)"""
         _check(lib().wb_dg2d_comm_init(self._h, C.c_char_p(unique_id_bytes)))
 
+    def exchange_kind(self):
+        """'p2p' (ghost rows stored into peer memory by the fused stage kernel), 'nccl' (pack, send/recv, unpack) or 'none'"""
+        f = lib().wb_dg2d_exchange_kind
+        f.restype = C.c_char_p
+        f.argtypes = [C.c_void_p]
+        return f(self._h).decode()
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().wb_dg2d_destroy(self._h)

@@ -158,6 +158,10 @@ int wb_dg2d_set_stream(wb_dg2d* h, void* cuda_stream);
  * modes travel once per RK stage (periodic box: ring, bc 2|3: chain), the order-dependent max-speed scan of
  * compute_max_speed is all-reduced in its two-phase form */
 int wb_dg2d_comm_init(wb_dg2d* h, const void* nccl_unique_id_128);
+/* like wb_fv2d_exchange_kind: "p2p" = the boundary-row launches of the fused stage kernel store their rows straight into the
+ * neighbours' ghost rows (element-local limiter flows; buffers mapped with CUDA IPC at comm_init), "nccl" = pack, ncclSend/Recv,
+ * unpack (always used by the neighbour-reading limiter flows and the stateless entries), "none" = single rank. */
+const char* wb_dg2d_exchange_kind(const wb_dg2d* h);
 int wb_dg2d_local_rows(const wb_dg2d* h, int* j0, int* nrows);
 /* which RK-stage kernel evolve / step_async launch on this handle: "split" (k_dg_stage_split: element split over four
  * threads, faces once, rows staged by TMA; nx % 32 == 0), "tma" / "march" / "fast" (one thread per element: earlier

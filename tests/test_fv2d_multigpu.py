@@ -30,7 +30,7 @@ def test_slab_evolve_equals_single_gpu_and_oracle(nx, ny, steps):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("n,m,steps", [(24, 3, 3), (17, 2, 4)])
+@pytest.mark.parametrize("n,m,steps", [(24, 3, 3), (17, 2, 4), (64, 3, 2)])      # 64: the split kernel, ghost rows by p2p and nccl
 def test_dg_slab_evolve_equals_single_gpu_and_oracle(n, m, steps):
     """2D DG on y slabs: ghost rows of modes once per RK stage (ring for the periodic box, chain for the clamped one),
     two-phase all-reduce of the order-dependent max-speed scan -> bit-identical to the single-GPU run."""
