@@ -331,10 +331,11 @@ def dg2d_section(args, stream, world=1, rank=0, local_rank=0, dev=None):
             achieved = 921.6 * n * n / world / (ms * 1e-3 / stage_launches) / 1e9      # per GPU
             prof = ncu_dg_profile()
             kern = s.stage_kernel()
+            xkind = s.exchange_kind() if world > 1 else None
             out.update({"value": rate, "ms_per_step": ms / steps, "steps": steps, "gpu_launches": wbeuler.kernel_launch_count() - l0,
                         "config": {"workload": f"2D modal DG, {n}x{n} elements, mx=my=3 (36 dof/element), SSPRK(5,4), llf1, ONP limiter, "
                                                "periodic Gaussian pulse (ninit=1), device-initialised", "grid": [n, n],
-                                   "parallelism": f"y-slabs x{world} (ring)" if world > 1 else "single GPU"},
+                                   "parallelism": f"y-slabs x{world} (ring), ghost rows: {xkind}" if world > 1 else "single GPU"},
                         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                      "traffic": (prof.get("dram_bytes_per_element_stage") or 0) * n * n / world or None,
                                      "kernel": f"k_dg_stage_{kern}<3> (fused update + RK combination + ONP: element split over four threads, "
@@ -396,6 +397,7 @@ def slab_parity(world, rank, local_rank):
     with wbeuler.DG2D(device=local_rank, **kw) as one:
         one.init_device(1); one.step_async(dsteps); r1 = one.sync(); refm = one.download_modes()
     s = wd.make_slab_solver(wbeuler.DG2D, world, rank, local_rank, **kw)
+    res["dg_ghost_exchange"] = s.exchange_kind()
     s.init_device(1); s.step_async(dsteps); r2 = s.sync()
     parts = [None] * world
     dist.all_gather_object(parts, s.download_modes())
