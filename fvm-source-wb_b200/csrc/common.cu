@@ -329,7 +329,7 @@ __global__ void k_peer_wait(unsigned long long* flags, int has_lo, int has_hi, u
   const volatile unsigned long long* f = flags;
   const long long t0 = clock64();
   while ((has_lo && f[0] < seq) || (has_hi && f[1] < seq)) {
-    if (clock64() - t0 > 20000000000LL) { flags[2] = seq; break; }      // ~10 s: a neighbour died
+    if (clock64() - t0 > 120000000000LL) { flags[2] = seq; break; }     // ~60 s of SM clocks: a neighbour died
     __nanosleep(200);
   }
   __threadfence_system();

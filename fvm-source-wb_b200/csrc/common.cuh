@@ -72,7 +72,7 @@ int nccl_bcast_f64(Nccl* c, double* buf, size_t count, int root, cudaStream_t s)
 // what is left of the exchange is one flag word per direction.  peer_signal (same stream, after that launch: its stores
 // are complete) writes the exchange number into the neighbours' flag words (null = no neighbour on that side);
 // peer_wait spins on the rank's own words [0] (written by the neighbour below) and [1] (above) until both have reached it,
-// gives up after ~10 s and records the exchange number in word [2] (checked by the *_sync entries).
+// gives up after ~60 s and records the exchange number in word [2] (checked by the *_sync entries).
 int peer_signal(unsigned long long* lo_flag, unsigned long long* hi_flag, unsigned long long seq, cudaStream_t s);
 int peer_wait(unsigned long long* flags, int has_lo, int has_hi, unsigned long long seq, cudaStream_t s);
 
