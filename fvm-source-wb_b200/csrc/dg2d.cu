@@ -1531,7 +1531,7 @@ int dg_axpy(wb_dg2d* h, int na, double* out, const double* A0, double c0, const 
   return WB_OK;
 }
 
-// 3-D tensor map (column, local row, plane) of a state buffer for k_dg_stage_tma
+// 3-D tensor map (column, local row, plane) of a state buffer for k_dg_stage_split
 int dg_make_map(const wb_dg2d* h, const double* base, CUtensorMap* out) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -1,7 +1,7 @@
 // k_dg_stage_split: the fused DG 2D RK-stage kernel with the ELEMENT SPLIT OVER FOUR THREADS (one per conserved variable).
 //
-// Why: k_dg_stage_tma keeps one element per thread -- 36 modes + 36 accumulators + the nodal fluxes in one thread = 255
-// registers, ~0.5 KB of spills, 8 warps per SM, 41 % of the HBM peak (profiles/r1_dg2d_tma_kernel_final.txt); it also evaluates
+// Why: round 1's kernel (k_dg_stage_tma, since removed) kept one element per thread -- 36 modes + 36 accumulators + the nodal fluxes in one thread = 255
+// registers, ~0.5 KB of spills, 8 warps per SM, 41 % of the HBM peak (profiles/r1_dg2d_tma_kernel_final.txt); it also evaluated
 // every face from both sides.  Everything in the stage that is LINEAR (traces, nodal values, volume / edge / source integrals,
 // RK combination) is independent per variable, so here
 //   * a block is 4 warps = 32 consecutive elements of a row x 4 variables: warp v owns variable v, lane l owns column ic0+l.
@@ -10,7 +10,8 @@
 //     face -- are "work items" dealt to all 128 threads through shared memory: 9 volume nodes + 3 left-face points + 3 top-face
 //     points per element, + the one x face behind the last column of the block;
 //   * every face flux is evaluated ONCE: the block marches up a strip of rows; the top-face flux of row j is the bottom-face
-//     flux of row j+1 (kept in shared memory), the right-face flux of column c is the left-face flux of column c+1;
+//     flux of row j+1 (carried in registers by the thread that needs it), the right-face flux of column c is the left-face
+//     flux of column c+1;
 //   * rows travel HBM -> shared memory once per strip as TMA tensor boxes (36 columns x 1 row x all planes, two slots,
 //     one mbarrier each); the slot of row j is re-armed with row j+2 as soon as the traces and nodal values of row j exist.
 // The arithmetic (operation order of every sum, the LLF routine with the low side first, the RK combination, the 'ONP' test)
@@ -25,7 +26,8 @@
 //   C  variable threads: edge integrals (left, right, bottom, top), fluxes of the own variable from the primitives, volume
 //      and source integrals, RK combination, sufficient test of 'ONP' (needs all four variables: one more exchange), stores
 // Reference: 2d/benchmark_2d_dg.f90:1137-1479 (compute_update), :683-707 (RK combination), 2d/limiters.f90:478-654 ('ONP').
-// Included by dg2d.cu after dg2d_fast.cuh and dg2d_tma.cuh (DGT_W, tma:: wrappers).  Needs nx % 32 == 0.
+// Slab boundary-row launches also store their rows into the neighbours' ghost rows (peer memory, StageCoef::peer_*).
+// Included by dg2d_split.cu after dg2d_fast.cuh and dg2d_tma.cuh (DGT_W, tma:: wrappers).  Needs nx % 32 == 0.
 #pragma once
 
 namespace wb { namespace dg {
