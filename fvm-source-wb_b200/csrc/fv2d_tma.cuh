@@ -13,7 +13,12 @@
 //     the left-neighbour shuffle and its lane-0 select disappear;
 //   * a slot is re-armed for row p+DEPTH as soon as row p is finished: DEPTH-2 rows are always in flight
 //     without holding registers (the LDG version stalled 40 % of its time on the first use of a prefetched row).
-// Warps stay independent: no block barrier anywhere.
+// Warps stay independent: no block barrier anywhere -- a CTA is ONE warp (TMA_WARPS), so that every TMA operand follows from
+// blockIdx and is provably uniform.  The main loop takes four rows per trip: the ring slot of a row (q & 3) is then a
+// compile-time constant and every slot / barrier address is base + immediate; the strip's y-table entries are staged once in
+// shared memory.  profiles/sass_loop.py counts the loop: 180 FP64 + 126.5 other instructions per row in stage 1.
+// In a slab's boundary-row launch (one-row strips, the generic "tail" instantiation) the results are also stored into the
+// neighbours' ghost rows: peer memory, StageArgs::peer_*.
 #pragma once
 #include <cuda.h>
 #include <cstdint>
