@@ -183,21 +183,23 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gy + pg));
       }
     }
-    // gravity field of this row: thread (v, column) fetches the nodes v, v+4, .. now and parks them in the source slots at the
-    // end of phase A, where the node items of phase B find them (the L2 latency hides behind phase A)
-    constexpr int NG = (NM + 3) / 4;
+    // gravity field of this row: warp v < M fetches the M nodes qx = v, qy = 0..M-1 of its column now (planes qy*M + qx of both
+    // arrays: one base address + a constant plane stride) and parks them in the source slots at the end of phase A, where the
+    // node items of phase B find them -- the L2 latency hides behind phase A.  Separable field (DgPhys::gsep): the same numbers
+    // from the one row of gx (plane qx, row `grow`: ONE value for all qy) and the one column of gy (plane qy*M, column 0).
+    constexpr int NG = M;
     double ga[SRC ? NG : 1], gb[SRC ? NG : 1];
-    if (SRC && full && P.source == 2) {
+    if (SRC && full && P.source == 2 && v < M) {
+      const size_t strideq = (size_t)M * g.ne;
+      if (P.gsep) {
+        const double gx1 = gx[(size_t)v * g.ne + (size_t)P.grow * g.nx + ic0 + lane];
+        const double* py = gy + (size_t)j * g.nx;
 #pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const int k = v + 4 * i;                             // node k = qx*M + qy; the arrays are ordered qy*M + qx
-        if (k < NM) {
-          const int qx = k / M, qy = k % M;
-          const size_t ge = (size_t)(qy * M + qx) * g.ne + (size_t)j * g.nx + ic0 + lane;
-          // separable field (DgPhys::gsep): the same numbers from the one row of gx / the one column of gy that stay in L2
-          ga[SRC ? i : 0] = gx[P.gsep ? (size_t)qx * g.ne + (size_t)P.grow * g.nx + ic0 + lane : ge];
-          gb[SRC ? i : 0] = gy[P.gsep ? (size_t)(qy * M) * g.ne + (size_t)j * g.nx : ge];
-        }
+        for (int i = 0; i < NG; ++i) { ga[SRC ? i : 0] = gx1; gb[SRC ? i : 0] = py[i * strideq]; }
+      } else {
+        const size_t o = (size_t)v * g.ne + (size_t)j * g.nx + ic0 + lane;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) { ga[SRC ? i : 0] = gx[o + i * strideq]; gb[SRC ? i : 0] = gy[o + i * strideq]; }
       }
     }
     // ------------------------------------------------------------------ phase A
@@ -276,11 +278,11 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
 #pragma unroll
       for (int q = 0; q < M; ++q) TB[(q * 4 + v) * 32 + lane] = t1[q];
     }
-    if (SRC && full && P.source == 2) {
+    if (SRC && full && P.source == 2 && v < M) {
 #pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const int k = v + 4 * i;
-        if (k < NM) { SW[(k * 3) * 32 + lane] = ga[SRC ? i : 0]; SW[(k * 3 + 1) * 32 + lane] = gb[SRC ? i : 0]; }
+      for (int i = 0; i < NG; ++i) {                         // node k = qx*M + qy = v*M + i
+        SW[((v * M + i) * 3) * 32 + lane] = ga[SRC ? i : 0];
+        SW[((v * M + i) * 3 + 1) * 32 + lane] = gb[SRC ? i : 0];
       }
     }
     __syncthreads();
