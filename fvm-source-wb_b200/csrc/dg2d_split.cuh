@@ -101,9 +101,15 @@ __device__ __forceinline__ void face_accum1(const FastBasis& B, const double (&F
 #ifndef DGS_MINB
 #define DGS_MINB 4
 #endif
+#ifndef DGS_MINB_OUT2
+#define DGS_MINB_OUT2 4
+#endif
+#ifndef DGS_MINB_SRC2
+#define DGS_MINB_SRC2 3      // the two-result launch with a source term: 168 registers without spills beat 128 with 100 B of them
+#endif
 
 template <int M, bool ANYFLUX, bool SRC, bool OUT2>
-__global__ void __launch_bounds__(128, (M <= 3 ? DGS_MINB : 2))
+__global__ void __launch_bounds__(128, (M <= 3 ? ((SRC && OUT2) ? DGS_MINB_SRC2 : OUT2 ? DGS_MINB_OUT2 : DGS_MINB) : 2))
 k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restrict__ in, StageCoef C, double* __restrict__ out,
                  const double* __restrict__ gx, const double* __restrict__ gy, const unsigned char* __restrict__ fz, DgGrid g,
                  DgPhys P, const __grid_constant__ FastBasis B, const DgCtrl* __restrict__ ctrl, int apply_onp, int rows_sched,
