@@ -415,7 +415,8 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
         // and add the +0.0 the sums would have produced (-0.0 + 0.0 = +0.0: same bits as fma(scale, +0.0, acc)).
         const bool src_on = (P.source == 2) ? v != 0 : v == 0;
         if (src_on) {
-          const double sgn = (P.source == 2) ? 1.0 : -1.0;
+          // the sink's minus sign rides on the final scale: negation commutes exactly with every product and sum below
+          const double src_scale = (P.source == 2) ? 0.5 * P.dx : -(0.5 * P.dx);
           const double* sw = SW + ((P.source == 2) ? v - 1 : 0) * 32 + lane;
           double sv[M][M];
 #pragma unroll
@@ -426,7 +427,7 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
           for (int qy = 0; qy < M; ++qy) {
             double S[M];
 #pragma unroll
-            for (int qx = 0; qx < M; ++qx) S[qx] = sgn * sw[((qx * M + qy) * 3) * 32];
+            for (int qx = 0; qx < M; ++qx) S[qx] = sw[((qx * M + qy) * 3) * 32];
 #pragma unroll
             for (int a = 0; a < M; ++a) {
               double s3 = 0.0;
@@ -438,7 +439,6 @@ k_dg_stage_split(const __grid_constant__ CUtensorMap m_in, const double* __restr
                 if (!zP<M>(qy, b)) sv[a][b] = fma(s3, B.Pw[qy][b], sv[a][b]);
             }
           }
-          const double src_scale = 0.5 * P.dx;
 #pragma unroll
           for (int a = 0; a < M; ++a)
 #pragma unroll
